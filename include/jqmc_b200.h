@@ -1,0 +1,157 @@
+/*
+ * jqmc_b200.h -- C ABI of the B200-native walker engine for jQMC.
+ *
+ * The jQMC reference has no FFI: its drivers call module-level, walker-batched JAX callables
+ * (SURVEY.md §8b).  Each entry point below replaces one of those callables; the cited file:line is
+ * the reference interface it stands in for.  All array arguments are DEVICE pointers (fp64,
+ * C-contiguous, walker axis leading, exactly the reference's array layouts) unless the name ends in
+ * `_host`; the engine never owns walker state.  Every call is asynchronous on `stream` (a
+ * cudaStream_t passed as void*, NULL = default stream) and returns 0 on success or a negative
+ * qe_status; qe_last_error() returns the message of the last failure on this thread.
+ *
+ * No torch / Python types appear here: the library links only against the CUDA runtime.
+ */
+#ifndef JQMC_B200_H
+#define JQMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qe_engine qe_engine;
+
+enum qe_status {
+  QE_OK = 0,
+  QE_ERR_INVALID = -1,     /* bad argument / inconsistent shapes (Python shim raises ValueError)   */
+  QE_ERR_UNSUPPORTED = -2, /* feature outside the engine's scope (e.g. NN Jastrow, l > 6, PBC)     */
+  QE_ERR_CUDA = -3,        /* CUDA runtime failure                                                 */
+  QE_ERR_NOMEM = -4
+};
+
+/* One orbital basis: the AO tables of AOs_sphe_data / AOs_cart_data
+ * (jqmc/atomic_orbital.py:780-929, :87-258) plus the optional MO layer of MOs_data
+ * (jqmc/molecular_orbital.py:85-140).  Primitives are stored per AO, as in the reference. */
+typedef struct {
+  int32_t cartesian;              /* 0: spherical (l,m); 1: Cartesian (nx,ny,nz)                    */
+  int32_t n_ao;
+  int32_t n_prim;                 /* = num_ao_prim                                                  */
+  const int32_t* nucleus_index;   /* [n_ao]                                                         */
+  const int32_t* angular_momentums; /* [n_ao]                                                       */
+  const int32_t* magnetic_quantum_numbers; /* [n_ao]  (spherical)                                   */
+  const int32_t* polynominal_order_x;      /* [n_ao]  (Cartesian; reference spelling kept)          */
+  const int32_t* polynominal_order_y;
+  const int32_t* polynominal_order_z;
+  const int32_t* orbital_indices; /* [n_prim] AO index of each primitive                            */
+  const double* exponents;        /* [n_prim]                                                       */
+  const double* coefficients;     /* [n_prim]                                                       */
+  int32_t n_mo;                   /* 0 => the orbitals are the AOs themselves                       */
+  const double* mo_coefficients;  /* [n_mo * n_ao] row-major                                        */
+} qe_basis_desc;
+
+/* Flat image of Hamiltonian_data (jqmc/hamiltonians.py:82-116): structure, geminal
+ * (jqmc/determinant.py:93-120), Jastrow (jqmc/jastrow_factor.py:560-600, 1110-1141, 1316-1335)
+ * and Coulomb/ECP tables (jqmc/coulomb_potential.py:187-233).  Host pointers, copied at create. */
+typedef struct {
+  int32_t n_atom;
+  const double* positions;        /* [n_atom*3] bohr                                                */
+  const double* effective_charges;/* [n_atom] atomic_numbers - z_cores                              */
+  int32_t n_up, n_dn;
+  qe_basis_desc orb_up, orb_dn;   /* Geminal_data.orb_data_{up,dn}_spin                             */
+  const double* lambda_matrix;    /* [orb_num_up * (orb_num_dn + n_up - n_dn)] row-major            */
+  int32_t j1_type;                /* 0 none, 1 'exp', 2 'pade'                                      */
+  double j1_param;
+  const double* j1_core_electrons;/* [n_atom]                                                       */
+  const double* j1_atomic_numbers;/* [n_atom]                                                       */
+  int32_t j2_type;                /* 0 none, 1 'pade', 2 'exp'                                      */
+  double j2_param;
+  int32_t j3_flag;                /* 0 none, 1 analytic three-body                                  */
+  qe_basis_desc j3_orb;
+  const double* j_matrix;         /* [n_orb_j3 * (n_orb_j3 + 1)] row-major                          */
+  int32_t ecp_flag;
+  int32_t n_ecp;
+  const int32_t* ecp_nucleus_index; /* [n_ecp]                                                      */
+  const int32_t* ecp_ang_moms;
+  const double* ecp_exponents;
+  const double* ecp_coefficients;
+  const int32_t* ecp_powers;      /* TREXIO power + 2, as stored by the reference                   */
+  const int32_t* ecp_max_ang_mom_plus_1; /* [n_atom]                                                */
+  int32_t Nv;                     /* quadrature points: 4, 6, 12 or 18 (jqmc/_setting.py:46)        */
+  int32_t NN;                     /* nearest nuclei for the non-local ECP (jqmc/_setting.py:47)     */
+} qe_system_desc;
+
+/* Build device tables for one Hamiltonian on the current CUDA device.  Rebuild whenever
+ * hamiltonian_data changes (e.g. every optimisation step). */
+int qe_create(const qe_system_desc* desc, qe_engine** out);
+void qe_destroy(qe_engine* h);
+const char* qe_last_error(void);
+/* Library/ABI version and whether it was compiled for sm_100a. */
+int qe_version(void);
+
+/* _geminal_inv_batched (jqmc/jqmc_mcmc.py:4248-4275) and GFMC_n's _jit_vmap_A_inv_n
+ * (jqmc/jqmc_gfmc.py:4706-4717):  r_up[nw,n_up,3], r_dn[nw,n_dn,3] -> G[nw,n_up,n_up], Ginv[...]. */
+int qe_geminal_init(qe_engine* h, int nw, const double* r_up, const double* r_dn, double* G, double* Ginv,
+                    void* stream);
+
+/* _jit_vmap_update (jqmc/jqmc_mcmc.py:4278-4533, 4728): nmpm single-electron Metropolis proposals
+ * per walker, updating r_up, r_dn, keys[nw,2] (uint32, jax.random raw keys), G, Ginv in place;
+ * acc/rej[nw] int32 receive the accepted / rejected counts of THIS call. */
+int qe_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, uint32_t* keys, double* G, double* Ginv,
+                   int nmpm, double Dt, double epsilon_AS, int32_t* acc, int32_t* rej, void* stream);
+
+/* _jit_vmap_generate_RTs (jqmc/jqmc_mcmc.py:4228-4245, 4738): keys[nw,2] -> RT[nw,3,3]; keys not advanced. */
+int qe_rotation(qe_engine* h, int nw, const uint32_t* keys, double* RT, void* stream);
+
+/* _jit_vmap_e_L_fast == vmap(compute_local_energy_fast) (jqmc/hamiltonians.py:225-290, jqmc_mcmc.py:4736).
+ * Optional per-walker breakdown (any may be NULL): T_elem[nw,n_up+n_dn] per-electron kinetic energies
+ * (jqmc/wavefunction.py:1141-1207), V_parts[nw,4] = {bare Coulomb, ECP local, ECP non-local, 0}. */
+int qe_local_energy(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT,
+                    const double* Ginv, double* e_L, double* T_elem, double* V_parts, void* stream);
+
+/* _jit_vmap_as_reg_fast (jqmc/determinant.py:1223-1260, jqmc_mcmc.py:4739). */
+int qe_as_factor(qe_engine* h, int nw, const double* G, const double* Ginv, double* R_AS, void* stream);
+
+/* vmap(evaluate_ln_wavefunction) (jqmc/wavefunction.py:677-720): ln|Psi| = J + ln|det G|, and the sign of det. */
+int qe_ln_wavefunction(qe_engine* h, int nw, const double* r_up, const double* r_dn, double* ln_psi,
+                       double* sign, void* stream);
+
+/* Parity/diagnostic entry for kernels 1-2: orbital values, gradients and Laplacians at arbitrary
+ * points.  which: 0 = geminal up basis, 1 = geminal dn basis, 2 = J3 basis; layer: 0 = AO layer
+ * (compute_AOs_value_grad_lap, jqmc/atomic_orbital.py:3594-3640), 1 = orbital layer
+ * (compute_MOs_value_grad_lap, jqmc/molecular_orbital.py:375-415).  r[n_pts,3];
+ * out[5, n_orb, n_pts] = value, d/dx, d/dy, d/dz, laplacian (orbital-major like the reference). */
+int qe_eval_orbitals(qe_engine* h, int which, int layer, int n_pts, const double* r, double* out, void* stream);
+
+/* Single-electron wavefunction ratios Psi(r')/Psi(r) for a batch of moves per walker
+ * (_compute_ratio_determinant_part_split_spin jqmc/determinant.py:1665-1783 times
+ *  _compute_ratio_Jastrow_part_split_spin jqmc/jastrow_factor.py:2696-2960).
+ * elec[n_moves] = electron index (0..n_up-1 up, n_up.. down) shared by all walkers,
+ * r_new[nw,n_moves,3]; det_ratio / jas_ratio [nw,n_moves] (either may be NULL). */
+int qe_move_ratios(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* Ginv, int n_moves,
+                   const int32_t* elec_host, const double* r_new, double* det_ratio, double* jas_ratio,
+                   void* stream);
+
+/* GFMC_n._projection_n (jqmc/jqmc_gfmc.py:4738-5358, 5656): nmpm LRDMC projections per walker.
+ * w[nw], r_up, r_dn, Ginv, keys updated in place; RT[nw,3,3], V_diag[nw], V_nondiag[nw] written.
+ * non_local_move: 0 = 'tmove', 1 = 'dltmove'. */
+int qe_lrdmc_project(qe_engine* h, int nw, double* w, double* r_up, double* r_dn, double* Ginv, uint32_t* keys,
+                     double E_scf, int nmpm, int random_discretized_mesh, int non_local_move, double alat,
+                     double* RT, double* V_diag, double* V_nondiag, void* stream);
+
+/* GFMC_n._compute_V_elements_n (jqmc/jqmc_gfmc.py:5360-5627, 5660). */
+int qe_lrdmc_velements(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT,
+                       const double* Ginv, int non_local_move, double alat, double* V_diag, double* V_nondiag,
+                       void* stream);
+
+/* Microbenchmark used by bench.py for the fp64 roofline denominator: runs `iters` dependent-free
+ * DFMA per thread on a full grid and returns the achieved TFLOP/s (synchronous). */
+int qe_measure_fp64_peak(int iters, double* tflops);
+
+/* Number of kernel launches issued by this engine since creation (bench.py's gpu_launches). */
+int64_t qe_launch_count(qe_engine* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JQMC_B200_H */

@@ -1,0 +1,1767 @@
+// B200-native walker engine for jQMC: host-side table construction, kernels, and the C ABI of
+// include/jqmc_b200.h.  Written for sm_100a (fp64 path: the Blackwell tcgen05 tensor cores have no fp64
+// mode, so the contractions run as DFMA fused into the AO evaluation).
+//
+// Thread mapping used by every kernel: LANES ARE WALKERS.  A warp holds 32 consecutive walkers and one
+// task (an electron, a quadrature point, a chunk of the AO basis); all lanes therefore execute the same
+// shell/primitive sequence, table loads are warp-broadcast and walker-state loads/stores are coalesced
+// through [item][walker] workspace layouts.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/jqmc_b200.h"
+#include "qe_device.cuh"
+
+using namespace qe;
+
+// =================================================================================================
+// error handling
+// =================================================================================================
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(x)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (x);                                                                        \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(QE_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_));                \
+  } while (0)
+
+// =================================================================================================
+// engine object
+// =================================================================================================
+struct DevPool {
+  std::vector<void*> ptrs;
+  template <class T>
+  cudaError_t upload(const std::vector<T>& v, const T** out) {
+    void* p = nullptr;
+    size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(p);
+    if (!v.empty()) e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    *out = (const T*)p;
+    return e;
+  }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+  }
+};
+
+struct HostBasis {
+  BasisDev dev{};
+  std::vector<int> chunk_begin;  // balanced chunks of groups, chunk_begin[n_chunk+1]
+  std::vector<double> grp_cost;
+  bool present = false;
+};
+
+struct SysDev {
+  int n_atom, n_up, n_dn, n_e;
+  const double* Rn;     // [n_atom*3]
+  const double* Zeff;   // [n_atom]
+  // geminal lambda in orbital basis: lam_p [nmo_pad][nmo_pad] (zero padded), lam_u [nmo_pad][n_up-n_dn]
+  const double* lam_p;
+  const double* lam_u;
+  int n_unp;
+  // Jastrow
+  int j1_type;
+  double j1_a;
+  const double* j1_A;   // (2 Z)^{3/4}
+  const double* j1_c;   // (2 Z)^{1/4}
+  int j2_type;
+  double j2_a;
+  // ECP
+  int ecp_flag, n_ecp, Nv, NN, ecp_lmax;  // ecp_lmax = global max_ang_mom_plus_1
+  const int* ecp_nuc;
+  const int* ecp_l;
+  const double* ecp_z;
+  const double* ecp_c;
+  const double* ecp_p;
+  const int* ecp_lmax_atom;  // [n_atom] max_ang_mom_plus_1
+  const int* ecp_off;        // [n_atom+1] terms sorted by atom
+  const double* quad_w;      // [Nv]
+  const double* quad_g;      // [Nv*3]
+  double v_ion_ion;
+};
+
+struct qe_engine {
+  DevPool pool;
+  HostBasis b_up, b_dn, b_j3;
+  bool same_ao_updn = true;
+  SysDev sys{};
+  int nmo_pad = 4;
+  // workspace
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  int64_t launches = 0;
+  int n_chunk_el = 1;    // chunks used by the electron VGL pass
+  int n_chunk_mc = 1;    // chunk warps of the Metropolis kernel
+  std::vector<int> chunk_el, chunk_mc;
+  const int* d_chunk_el = nullptr;
+  const int* d_chunk_mc = nullptr;
+};
+
+static int ensure_ws(qe_engine* h, size_t bytes) {
+  if (bytes <= h->ws_bytes) return QE_OK;
+  if (h->ws) cudaFree(h->ws);
+  h->ws = nullptr;
+  h->ws_bytes = 0;
+  CUDA_TRY(cudaMalloc(&h->ws, bytes));
+  h->ws_bytes = bytes;
+  return QE_OK;
+}
+
+// =================================================================================================
+// host: basis compression (per-AO primitive lists -> shells grouped by (nucleus, l))
+// =================================================================================================
+static double dfact(int n) {
+  double r = 1.0;
+  for (int i = 2; i <= n; ++i) r *= i;
+  return r;
+}
+
+static int cart_index(int l, int nx, int ny, int nz) {
+  // position of x^nx y^ny z^nz in itertools.combinations_with_replacement("xyz", l)
+  int k = 0;
+  for (int ax = l; ax >= 0; --ax)
+    for (int ay = l - ax; ay >= 0; --ay) {
+      int az = l - ax - ay;
+      if (ax == nx && ay == ny && az == nz) return k;
+      ++k;
+    }
+  return -1;
+}
+
+struct TmpShell {
+  int nuc, l;
+  std::vector<double> Z, c;  // c: reference coefficients (unnormalised) of the first AO of the shell
+  std::vector<short> slot;
+  int first_ao;
+};
+
+static int build_basis(const qe_basis_desc& d, int n_atom, int nmo_pad, DevPool& pool, HostBasis& hb) {
+  if (d.n_ao <= 0) return fail(QE_ERR_INVALID, "basis: n_ao must be positive");
+  const bool cart = d.cartesian != 0;
+  std::vector<std::vector<int>> prims(d.n_ao);
+  for (int p = 0; p < d.n_prim; ++p) {
+    int a = d.orbital_indices[p];
+    if (a < 0 || a >= d.n_ao) return fail(QE_ERR_INVALID, "basis: orbital_indices out of range");
+    prims[a].push_back(p);
+  }
+  std::vector<TmpShell> shells;
+  std::vector<double> ao_scale(d.n_ao, 1.0);
+  for (int a = 0; a < d.n_ao; ++a) {
+    const int l = d.angular_momentums[a];
+    const int nuc = d.nucleus_index[a];
+    if (l < 0 || l > QE_LMAX) return fail(QE_ERR_UNSUPPORTED, "basis: angular momentum > 6 is not supported");
+    if (nuc < 0 || nuc >= n_atom) return fail(QE_ERR_INVALID, "basis: nucleus_index out of range");
+    int k;
+    double extra = 1.0;
+    if (cart) {
+      const int nx = d.polynominal_order_x[a], ny = d.polynominal_order_y[a], nz = d.polynominal_order_z[a];
+      if (nx + ny + nz != l) return fail(QE_ERR_INVALID, "basis: nx+ny+nz != l");
+      k = cart_index(l, nx, ny, nz);
+      extra = std::sqrt(dfact(nx) * dfact(ny) * dfact(nz) / (dfact(2 * nx) * dfact(2 * ny) * dfact(2 * nz)));
+    } else {
+      const int m = d.magnetic_quantum_numbers[a];
+      if (m < -l || m > l) return fail(QE_ERR_INVALID, "basis: |m| > l");
+      k = m + l;
+    }
+    const auto& pl = prims[a];
+    // try to join the last shell
+    bool joined = false;
+    if (!shells.empty()) {
+      TmpShell& s = shells.back();
+      if (s.nuc == nuc && s.l == l && s.Z.size() == pl.size() && s.slot[k] < 0 && !pl.empty()) {
+        size_t piv = 0;
+        for (size_t i = 0; i < pl.size(); ++i)
+          if (std::fabs(s.c[i]) > std::fabs(s.c[piv])) piv = i;
+        const double ratio = d.coefficients[pl[piv]] / s.c[piv];
+        bool ok = std::isfinite(ratio);
+        for (size_t i = 0; ok && i < pl.size(); ++i) {
+          if (d.exponents[pl[i]] != s.Z[i]) ok = false;
+          const double ci = d.coefficients[pl[i]];
+          if (std::fabs(ci - ratio * s.c[i]) > 4e-15 * std::fabs(ci)) ok = false;
+        }
+        if (ok) {
+          s.slot[k] = (short)a;
+          ao_scale[a] = ratio * extra;
+          joined = true;
+        }
+      }
+    }
+    if (!joined) {
+      TmpShell s;
+      s.nuc = nuc;
+      s.l = l;
+      s.first_ao = a;
+      s.slot.assign(MAXF, -1);
+      for (int p : pl) {
+        s.Z.push_back(d.exponents[p]);
+        s.c.push_back(d.coefficients[p]);
+      }
+      s.slot[k] = (short)a;
+      ao_scale[a] = extra;
+      shells.push_back(std::move(s));
+    }
+  }
+  std::stable_sort(shells.begin(), shells.end(), [](const TmpShell& x, const TmpShell& y) {
+    return x.nuc != y.nuc ? x.nuc < y.nuc : x.l < y.l;
+  });
+  std::vector<int> grp_nuc, grp_l, grp_sh_begin, sh_prim_off{0};
+  std::vector<short> sh_slot;
+  std::vector<double> pr_Z, pr_c;
+  hb.grp_cost.clear();
+  for (size_t s = 0; s < shells.size(); ++s) {
+    const TmpShell& sh = shells[s];
+    if (s == 0 || sh.nuc != shells[s - 1].nuc || sh.l != shells[s - 1].l) {
+      grp_nuc.push_back(sh.nuc);
+      grp_l.push_back(sh.l);
+      grp_sh_begin.push_back((int)s);
+      hb.grp_cost.push_back(10.0 + 6.0 * sh.l * sh.l);
+    }
+    const int l = sh.l;
+    for (size_t i = 0; i < sh.Z.size(); ++i) {
+      const double Z = sh.Z[i];
+      double N;
+      if (cart)  // jqmc/atomic_orbital.py:2243-2244 (Z-dependent part; factorial part lives in ao_scale)
+        N = std::sqrt(std::pow(2.0 * Z / M_PI, 1.5) * std::pow(8.0 * Z, (double)l));
+      else  // jqmc/atomic_orbital.py:2316-2323, times sqrt((2l+1)/4pi) (:2349)
+        N = std::sqrt(std::pow(2.0, 2 * l + 3) * dfact(l + 1) * std::pow(2.0 * Z, l + 1.5) / (dfact(2 * l + 2) * std::sqrt(M_PI))) *
+            std::sqrt((2 * l + 1) / (4.0 * M_PI));
+      pr_Z.push_back(Z);
+      pr_c.push_back(sh.c[i] * N);
+    }
+    sh_prim_off.push_back((int)pr_Z.size());
+    sh_slot.insert(sh_slot.end(), sh.slot.begin(), sh.slot.end());
+    int nf = 0;
+    for (short v : sh.slot) nf += v >= 0;
+    hb.grp_cost.back() += 32.0 * sh.Z.size() + (nmo_pad + 2.0) * nf;
+  }
+  grp_sh_begin.push_back((int)shells.size());
+
+  BasisDev& B = hb.dev;
+  B.n_ao = d.n_ao;
+  B.n_mo = d.n_mo;
+  B.n_orb = d.n_mo > 0 ? d.n_mo : d.n_ao;
+  B.n_grp = (int)grp_nuc.size();
+  B.n_shell = (int)shells.size();
+  B.cart = cart ? 1 : 0;
+  B.nmo_pad = nmo_pad;
+  std::vector<double> Cs;
+  if (d.n_mo > 0) {
+    Cs.assign((size_t)d.n_ao * nmo_pad, 0.0);
+    for (int mo = 0; mo < d.n_mo; ++mo)
+      for (int a = 0; a < d.n_ao; ++a) Cs[(size_t)a * nmo_pad + mo] = d.mo_coefficients[(size_t)mo * d.n_ao + a] * ao_scale[a];
+  }
+  cudaError_t e = cudaSuccess;
+  e = pool.upload(grp_nuc, &B.grp_nuc);
+  if (e == cudaSuccess) e = pool.upload(grp_l, &B.grp_l);
+  if (e == cudaSuccess) e = pool.upload(grp_sh_begin, &B.grp_sh_begin);
+  if (e == cudaSuccess) e = pool.upload(sh_prim_off, &B.sh_prim_off);
+  if (e == cudaSuccess) e = pool.upload(sh_slot, &B.sh_slot);
+  if (e == cudaSuccess) e = pool.upload(pr_Z, &B.pr_Z);
+  if (e == cudaSuccess) e = pool.upload(pr_c, &B.pr_c);
+  if (e == cudaSuccess) e = pool.upload(ao_scale, &B.ao_scale);
+  if (e == cudaSuccess) e = pool.upload(Cs, &B.Cs);
+  if (e != cudaSuccess) return fail(QE_ERR_CUDA, std::string("basis upload: ") + cudaGetErrorString(e));
+  if (d.n_mo == 0) B.Cs = nullptr;
+  hb.present = true;
+  return QE_OK;
+}
+
+// split the groups into at most n_target contiguous chunks of roughly equal cost
+static std::vector<int> make_chunks(const std::vector<double>& cost, int n_target) {
+  const int n = (int)cost.size();
+  n_target = std::max(1, std::min(n_target, n));
+  double total = 0;
+  for (double c : cost) total += c;
+  // binary search the smallest max-chunk cost achievable with n_target contiguous chunks
+  double lo = 0, hi = total;
+  for (double c : cost) lo = std::max(lo, c);
+  for (int it = 0; it < 60; ++it) {
+    double mid = 0.5 * (lo + hi), acc = 0;
+    int used = 1;
+    for (double c : cost) {
+      if (acc + c > mid) {
+        ++used;
+        acc = 0;
+      }
+      acc += c;
+    }
+    if (used <= n_target) hi = mid; else lo = mid;
+  }
+  std::vector<int> out{0};
+  double acc = 0;
+  for (int g = 0; g < n; ++g) {
+    if (acc + cost[g] > hi * (1 + 1e-12) && g > out.back()) {
+      out.push_back(g);
+      acc = 0;
+    }
+    acc += cost[g];
+  }
+  out.push_back(n);
+  return out;
+}
+
+static bool same_ao_tables(const qe_basis_desc& x, const qe_basis_desc& y) {
+  if (x.cartesian != y.cartesian || x.n_ao != y.n_ao || x.n_prim != y.n_prim) return false;
+  for (int a = 0; a < x.n_ao; ++a) {
+    if (x.nucleus_index[a] != y.nucleus_index[a] || x.angular_momentums[a] != y.angular_momentums[a]) return false;
+    if (x.cartesian) {
+      if (x.polynominal_order_x[a] != y.polynominal_order_x[a] || x.polynominal_order_y[a] != y.polynominal_order_y[a] ||
+          x.polynominal_order_z[a] != y.polynominal_order_z[a])
+        return false;
+    } else if (x.magnetic_quantum_numbers[a] != y.magnetic_quantum_numbers[a])
+      return false;
+  }
+  for (int p = 0; p < x.n_prim; ++p)
+    if (x.orbital_indices[p] != y.orbital_indices[p] || x.exponents[p] != y.exponents[p] || x.coefficients[p] != y.coefficients[p])
+      return false;
+  return true;
+}
+
+// =================================================================================================
+// small device helpers
+// =================================================================================================
+// index of the atom with distance-rank `rank` from p (argsort semantics, first index wins ties;
+// jqmc/structure.py:410-426)
+__device__ __forceinline__ int nearest_atom(const double* __restrict__ Rn, int n_atom, double px, double py, double pz,
+                                            int rank, double* dist_out) {
+  if (rank == 0) {
+    int best = 0;
+    double bd = 1e300;
+    for (int a = 0; a < n_atom; ++a) {
+      const double dx = __ldg(Rn + 3 * a) - px, dy = __ldg(Rn + 3 * a + 1) - py, dz = __ldg(Rn + 3 * a + 2) - pz;
+      const double d = sqrt(dx * dx + dy * dy + dz * dz);
+      if (d < bd) {
+        bd = d;
+        best = a;
+      }
+    }
+    if (dist_out) *dist_out = bd;
+    return best;
+  }
+  for (int a = 0; a < n_atom; ++a) {
+    const double dx = __ldg(Rn + 3 * a) - px, dy = __ldg(Rn + 3 * a + 1) - py, dz = __ldg(Rn + 3 * a + 2) - pz;
+    const double da = sqrt(dx * dx + dy * dy + dz * dz);
+    int r = 0;
+    for (int b = 0; b < n_atom; ++b) {
+      const double ex = __ldg(Rn + 3 * b) - px, ey = __ldg(Rn + 3 * b + 1) - py, ez = __ldg(Rn + 3 * b + 2) - pz;
+      const double db = sqrt(ex * ex + ey * ey + ez * ez);
+      r += (db < da) || (db == da && b < a);
+    }
+    if (r == rank) {
+      if (dist_out) *dist_out = da;
+      return a;
+    }
+  }
+  return 0;
+}
+
+__device__ __forceinline__ double j1_f(int type, double a, double A, double c, double d) {
+  // jqmc/jastrow_factor.py:648-726
+  if (type == 1) return -A * (1.0 - exp(-a * c * d)) / (2.0 * a);
+  return -A * d / (2.0 * (1.0 + a * c * d));
+}
+__device__ __forceinline__ double j2_f(int type, double a, double d) {
+  // jqmc/jastrow_factor.py:1180-1251
+  if (type == 1) return d / (2.0 * (1.0 + a * d));
+  return (1.0 - exp(-a * d)) / (2.0 * a);
+}
+
+// Legendre P_l(x), l <= 6 (jqmc/_function_collections.py:47-65)
+__device__ __forceinline__ double legendre_l(int l, double x) {
+  const double x2 = x * x;
+  switch (l) {
+    case 0: return 1.0;
+    case 1: return x;
+    case 2: return 0.5 * (3.0 * x2 - 1.0);
+    case 3: return 0.5 * (5.0 * x2 - 3.0) * x;
+    case 4: return 0.125 * ((35.0 * x2 - 30.0) * x2 + 3.0);
+    case 5: return 0.125 * ((63.0 * x2 - 70.0) * x2 + 15.0) * x;
+    default: return 0.0625 * (((231.0 * x2 - 315.0) * x2 + 105.0) * x2 - 5.0);
+  }
+}
+
+// electron position accessors: global AoS arrays r_up[nw][n_up][3], r_dn[nw][n_dn][3]
+struct PosGlobal {
+  const double* __restrict__ up;
+  const double* __restrict__ dn;
+  int n_up, n_dn, w;
+  __device__ __forceinline__ void get(int e, double& x, double& y, double& z) const {
+    const double* p = e < n_up ? up + ((size_t)w * n_up + e) * 3 : dn + ((size_t)w * n_dn + (e - n_up)) * 3;
+    x = p[0];
+    y = p[1];
+    z = p[2];
+  }
+};
+
+// Jastrow (J1+J2) difference J(r') - J(r) for moving electron e from (ox,oy,oz) to (nx,ny,nz)
+template <class Pos>
+__device__ __forceinline__ double jastrow_delta(const SysDev& S, const Pos& pos, int e, double ox, double oy, double oz,
+                                                double nx, double ny, double nz) {
+  double dJ = 0.0;
+  if (S.j1_type) {
+    for (int a = 0; a < S.n_atom; ++a) {
+      const double X = __ldg(S.Rn + 3 * a), Y = __ldg(S.Rn + 3 * a + 1), Z = __ldg(S.Rn + 3 * a + 2);
+      const double dn_ = sqrt((nx - X) * (nx - X) + (ny - Y) * (ny - Y) + (nz - Z) * (nz - Z));
+      const double do_ = sqrt((ox - X) * (ox - X) + (oy - Y) * (oy - Y) + (oz - Z) * (oz - Z));
+      const double A = __ldg(S.j1_A + a), c = __ldg(S.j1_c + a);
+      dJ += j1_f(S.j1_type, S.j1_a, A, c, dn_) - j1_f(S.j1_type, S.j1_a, A, c, do_);
+    }
+  }
+  if (S.j2_type) {
+    for (int j = 0; j < S.n_e; ++j) {
+      if (j == e) continue;
+      double x, y, z;
+      pos.get(j, x, y, z);
+      const double dn_ = sqrt((nx - x) * (nx - x) + (ny - y) * (ny - y) + (nz - z) * (nz - z));
+      const double do_ = sqrt((ox - x) * (ox - x) + (oy - y) * (oy - y) + (oz - z) * (oz - z));
+      dJ += j2_f(S.j2_type, S.j2_a, dn_) - j2_f(S.j2_type, S.j2_a, do_);
+    }
+  }
+  return dJ;
+}
+
+// =================================================================================================
+// K1/K2 parity entry: orbital values / VGL at arbitrary points
+// =================================================================================================
+template <bool CART>
+__global__ void k_eval_ao(BasisDev B, const double* __restrict__ Rn, int n_pts, const double* __restrict__ r,
+                          double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pts) return;
+  SinkStoreAO sink{out + t, B.ao_scale, (long long)B.n_ao * n_pts, n_pts};
+  eval_vgl<CART>(B, Rn, r[3 * t], r[3 * t + 1], r[3 * t + 2], 0, B.n_grp, sink);
+}
+template <int NMO, bool CART>
+__global__ void k_eval_mo(BasisDev B, const double* __restrict__ Rn, int n_pts, const double* __restrict__ r,
+                          double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pts) return;
+  SinkMO5<NMO> sink;
+  sink.init(B.Cs);
+  eval_vgl<CART>(B, Rn, r[3 * t], r[3 * t + 1], r[3 * t + 2], 0, B.n_grp, sink);
+  for (int q = 0; q < 5; ++q)
+#pragma unroll
+    for (int mo = 0; mo < NMO; ++mo)
+      if (mo < B.n_mo) out[((long long)q * B.n_mo + mo) * n_pts + t] = sink.acc[q][mo];
+}
+
+// =================================================================================================
+// E1: orbital values (NQ=1) or value/grad/lap (NQ=5) of every MO at every electron of every walker.
+// thread = (chunk, electron, walker);  out[chunk][e][q][mo][w]
+// =================================================================================================
+template <int NMO, bool CART, int NQ>
+__global__ void __launch_bounds__(128)
+k_orb_electrons(BasisDev Bu, BasisDev Bd, SysDev S, int nw, const double* __restrict__ r_up,
+                const double* __restrict__ r_dn, const int* __restrict__ chunk_begin, int n_chunk,
+                double* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n_chunk * S.n_e * nw;
+  if (t >= total) return;
+  const int w = (int)(t % nw);
+  const int e = (int)((t / nw) % S.n_e);
+  const int c = (int)(t / ((long long)nw * S.n_e));
+  PosGlobal pos{r_up, r_dn, S.n_up, S.n_dn, w};
+  double x, y, z;
+  pos.get(e, x, y, z);
+  const BasisDev& B = e < S.n_up ? Bu : Bd;
+  const int gb = chunk_begin[c], ge = chunk_begin[c + 1];
+  double* o = out + (((size_t)c * S.n_e + e) * NQ * NMO) * nw + w;
+  if (NQ == 1) {
+    SinkMO<NMO> sink;
+    sink.init(B.Cs);
+    eval_val<CART>(B, S.Rn, x, y, z, gb, ge, sink);
+#pragma unroll
+    for (int mo = 0; mo < NMO; ++mo) o[(size_t)mo * nw] = sink.acc[mo];
+  } else {
+    SinkMO5<NMO> sink;
+    sink.init(B.Cs);
+    eval_vgl<CART>(B, S.Rn, x, y, z, gb, ge, sink);
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+#pragma unroll
+      for (int mo = 0; mo < NMO; ++mo) o[((size_t)q * NMO + mo) * nw] = sink.acc[q][mo];
+  }
+}
+
+// =================================================================================================
+// G2: per-walker geminal matrix, inverse (Gauss-Jordan, partial pivoting), ln|det|, Jastrow value.
+// thread = walker.  phi[chunk][e][1][mo][w]
+// =================================================================================================
+template <int NMO>
+__global__ void k_geminal(SysDev S, int nw, int n_chunk, const double* __restrict__ phi, const double* __restrict__ r_up,
+                          const double* __restrict__ r_dn, double* __restrict__ G_out, double* __restrict__ Ginv_out,
+                          double* __restrict__ lnpsi_out, double* __restrict__ sign_out) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  constexpr int NMAX = 16;
+  const int N = S.n_up, Nd = S.n_dn;
+  double G[NMAX * NMAX], I[NMAX * NMAX];
+  // G[i][j] = sum_{a,b} PhiU[a][i] lam_p[a][b] PhiD[b][j] ; unpaired columns: sum_a PhiU[a][i] lam_u[a][k]
+  for (int i = 0; i < N; ++i) {
+    double pu[NMO];
+    for (int a = 0; a < NMO; ++a) {
+      double s = 0;
+      for (int c = 0; c < n_chunk; ++c) s += phi[(((size_t)c * S.n_e + i) * NMO + a) * nw + w];
+      pu[a] = s;
+    }
+    double t[NMO];
+    for (int b = 0; b < NMO; ++b) {
+      double s = 0;
+      for (int a = 0; a < NMO; ++a) s = fma(pu[a], __ldg(S.lam_p + a * NMO + b), s);
+      t[b] = s;
+    }
+    for (int j = 0; j < Nd; ++j) {
+      double s = 0;
+      for (int b = 0; b < NMO; ++b) {
+        double pd = 0;
+        for (int c = 0; c < n_chunk; ++c) pd += phi[(((size_t)c * S.n_e + (N + j)) * NMO + b) * nw + w];
+        s = fma(t[b], pd, s);
+      }
+      G[i * N + j] = s;
+    }
+    for (int k = 0; k < S.n_unp; ++k) {
+      double s = 0;
+      for (int a = 0; a < NMO; ++a) s = fma(pu[a], __ldg(S.lam_u + a * S.n_unp + k), s);
+      G[i * N + Nd + k] = s;
+    }
+  }
+  if (G_out)
+    for (int i = 0; i < N * N; ++i) G_out[(size_t)w * N * N + i] = G[i];
+  // Gauss-Jordan with partial pivoting on a copy
+  double A[NMAX * NMAX];
+  for (int i = 0; i < N * N; ++i) {
+    A[i] = G[i];
+    I[i] = 0.0;
+  }
+  for (int i = 0; i < N; ++i) I[i * N + i] = 1.0;
+  double lndet = 0.0, sgn = 1.0;
+  for (int c = 0; c < N; ++c) {
+    int piv = c;
+    double best = fabs(A[c * N + c]);
+    for (int r = c + 1; r < N; ++r)
+      if (fabs(A[r * N + c]) > best) {
+        best = fabs(A[r * N + c]);
+        piv = r;
+      }
+    if (piv != c) {
+      for (int j = 0; j < N; ++j) {
+        double tmp = A[c * N + j];
+        A[c * N + j] = A[piv * N + j];
+        A[piv * N + j] = tmp;
+        tmp = I[c * N + j];
+        I[c * N + j] = I[piv * N + j];
+        I[piv * N + j] = tmp;
+      }
+      sgn = -sgn;
+    }
+    const double d = A[c * N + c];
+    lndet += log(fabs(d));
+    if (d < 0) sgn = -sgn;
+    const double inv = 1.0 / d;
+    for (int j = 0; j < N; ++j) {
+      A[c * N + j] *= inv;
+      I[c * N + j] *= inv;
+    }
+    for (int r = 0; r < N; ++r) {
+      if (r == c) continue;
+      const double f = A[r * N + c];
+      for (int j = 0; j < N; ++j) {
+        A[r * N + j] = fma(-f, A[c * N + j], A[r * N + j]);
+        I[r * N + j] = fma(-f, I[c * N + j], I[r * N + j]);
+      }
+    }
+  }
+  if (Ginv_out)
+    for (int i = 0; i < N * N; ++i) Ginv_out[(size_t)w * N * N + i] = I[i];
+  if (lnpsi_out) {
+    // Jastrow value J1 + J2 (jqmc/jastrow_factor.py:2127-2178)
+    PosGlobal pos{r_up, r_dn, S.n_up, S.n_dn, w};
+    double J = 0.0;
+    for (int e = 0; e < S.n_e; ++e) {
+      double x, y, z;
+      pos.get(e, x, y, z);
+      if (S.j1_type)
+        for (int a = 0; a < S.n_atom; ++a) {
+          const double dx = x - S.Rn[3 * a], dy = y - S.Rn[3 * a + 1], dz = z - S.Rn[3 * a + 2];
+          J += j1_f(S.j1_type, S.j1_a, S.j1_A[a], S.j1_c[a], sqrt(dx * dx + dy * dy + dz * dz));
+        }
+      if (S.j2_type)
+        for (int j = e + 1; j < S.n_e; ++j) {
+          double x2, y2, z2;
+          pos.get(j, x2, y2, z2);
+          J += j2_f(S.j2_type, S.j2_a, sqrt((x - x2) * (x - x2) + (y - y2) * (y - y2) + (z - z2) * (z - z2)));
+        }
+    }
+    lnpsi_out[w] = J + lndet;
+    if (sign_out) sign_out[w] = sgn;
+  }
+}
+
+// =================================================================================================
+// E2: per-(walker, electron) algebra: sum chunk partials, ratio weight vector W[:,e] = d(det ratio)/d(phi),
+//     grad/lap ln|det| (jqmc/determinant.py:2140-2250), Jastrow J1/J2 grad/lap
+//     (jqmc/jastrow_factor.py:960-1034, 3434-3558), per-electron kinetic energy
+//     (jqmc/wavefunction.py:1198-1207), bare Coulomb / ECP-local pieces (jqmc/coulomb_potential.py:2252-2281,
+//     1144-1246).   thread = (electron, walker)
+//     phi[chunk][e][NQ][mo][w];  W[e][mo][w];  Te/Vb/Vl[e][w]
+// =================================================================================================
+template <int NMO, int NQ>
+__global__ void k_electron_algebra(SysDev S, int nw, int n_chunk, const double* __restrict__ phi,
+                                   const double* __restrict__ r_up, const double* __restrict__ r_dn,
+                                   const double* __restrict__ Ginv, double* __restrict__ W, double* __restrict__ Te,
+                                   double* __restrict__ Vb, double* __restrict__ Vl) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)S.n_e * nw) return;
+  const int w = (int)(t % nw);
+  const int e = (int)(t / nw);
+  const int N = S.n_up, Nd = S.n_dn;
+  const bool up = e < N;
+  const double* Gi = Ginv + (size_t)w * N * N;
+  auto PHI = [&](int el, int q, int mo) {
+    double s = 0;
+    for (int c = 0; c < n_chunk; ++c) s += phi[((((size_t)c * S.n_e + el) * NQ + q) * NMO + mo) * nw + w];
+    return s;
+  };
+  // weight vector: det ratio for moving electron e to r' is  sum_mo phi_mo(r') * Wv[mo]
+  double Wv[NMO];
+  if (up) {
+    // Wv[a] = sum_j (lam_p PhiD)[a][j] Ginv[j][e] + sum_k lam_u[a][k] Ginv[Nd+k][e]
+    double y[NMO];
+    for (int b = 0; b < NMO; ++b) {
+      double s = 0;
+      for (int j = 0; j < Nd; ++j) s = fma(PHI(N + j, 0, b), Gi[j * N + e], s);
+      y[b] = s;
+    }
+    for (int a = 0; a < NMO; ++a) {
+      double s = 0;
+      for (int b = 0; b < NMO; ++b) s = fma(__ldg(S.lam_p + a * NMO + b), y[b], s);
+      for (int k = 0; k < S.n_unp; ++k) s = fma(__ldg(S.lam_u + a * S.n_unp + k), Gi[(Nd + k) * N + e], s);
+      Wv[a] = s;
+    }
+  } else {
+    // Wv[b] = sum_i Ginv[j][i] (PhiU^T lam_p)[i][b],  j = e - N
+    const int j = e - N;
+    double y[NMO];
+    for (int a = 0; a < NMO; ++a) {
+      double s = 0;
+      for (int i = 0; i < N; ++i) s = fma(PHI(i, 0, a), Gi[j * N + i], s);
+      y[a] = s;
+    }
+    for (int b = 0; b < NMO; ++b) {
+      double s = 0;
+      for (int a = 0; a < NMO; ++a) s = fma(y[a], __ldg(S.lam_p + a * NMO + b), s);
+      Wv[b] = s;
+    }
+  }
+  for (int mo = 0; mo < NMO; ++mo) W[((size_t)e * NMO + mo) * nw + w] = Wv[mo];
+  if (NQ == 1) return;
+
+  double gD[3] = {0, 0, 0}, lD = 0;
+  for (int mo = 0; mo < NMO; ++mo) {
+    gD[0] = fma(PHI(e, 1, mo), Wv[mo], gD[0]);
+    gD[1] = fma(PHI(e, 2, mo), Wv[mo], gD[1]);
+    gD[2] = fma(PHI(e, 3, mo), Wv[mo], gD[2]);
+    lD = fma(PHI(e, 4, mo), Wv[mo], lD);
+  }
+  lD -= gD[0] * gD[0] + gD[1] * gD[1] + gD[2] * gD[2];
+
+  PosGlobal pos{r_up, r_dn, N, Nd, w};
+  double x, y_, z;
+  pos.get(e, x, y_, z);
+  double gJ[3] = {0, 0, 0}, lJ = 0;
+  double v_bare = 0.0, v_loc = 0.0;
+  const double eps = 1.0e-12;
+  for (int a = 0; a < S.n_atom; ++a) {
+    const double dx = x - __ldg(S.Rn + 3 * a), dy = y_ - __ldg(S.Rn + 3 * a + 1), dz = z - __ldg(S.Rn + 3 * a + 2);
+    const double d = sqrt(dx * dx + dy * dy + dz * dz);
+    v_bare -= __ldg(S.Zeff + a) / d;
+    if (S.j1_type) {
+      const double rs = fmax(d, eps);
+      const double A = __ldg(S.j1_A + a), c = __ldg(S.j1_c + a), aa = S.j1_a;
+      double fp;
+      if (S.j1_type == 1) {
+        const double ex = exp(-aa * c * rs);
+        fp = -A * (c * 0.5) * ex;
+        lJ += A * (aa * c * c * 0.5) * ex - A * c * ex / rs;
+      } else {
+        const double den = 1.0 + aa * c * rs;
+        fp = -A / (2.0 * den * den);
+        lJ += A * aa * c / (den * den * den) + 2.0 * fp / rs;
+      }
+      const double s = fp / rs;
+      gJ[0] = fma(s, dx, gJ[0]);
+      gJ[1] = fma(s, dy, gJ[1]);
+      gJ[2] = fma(s, dz, gJ[2]);
+    }
+    if (S.ecp_flag) {
+      const int lloc = __ldg(S.ecp_lmax_atom + a);
+      double s = 0.0;
+      for (int k = __ldg(S.ecp_off + a); k < __ldg(S.ecp_off + a + 1); ++k)
+        if (__ldg(S.ecp_l + k) == lloc) s += __ldg(S.ecp_c + k) * pow(d, __ldg(S.ecp_p + k)) * exp(-__ldg(S.ecp_z + k) * d * d);
+      v_loc += s / (d * d);
+    }
+  }
+  for (int j = 0; j < S.n_e; ++j) {
+    if (j == e) continue;
+    double x2, y2, z2;
+    pos.get(j, x2, y2, z2);
+    const double dx = x - x2, dy = y_ - y2, dz = z - z2;
+    const double d = sqrt(dx * dx + dy * dy + dz * dz);
+    if (j > e) v_bare += 1.0 / d;
+    if (S.j2_type) {
+      const double rs = fmax(d, eps), aa = S.j2_a;
+      double fp;
+      if (S.j2_type == 1) {
+        const double den = 1.0 + aa * rs;
+        fp = 0.5 / (den * den);
+        lJ += -aa / (den * den * den) + 2.0 * fp / rs;
+      } else {
+        const double ex = exp(-aa * rs);
+        fp = 0.5 * ex;
+        lJ += -(aa * 0.5) * ex + 2.0 * fp / rs;
+      }
+      const double s = fp / rs;
+      gJ[0] = fma(s, dx, gJ[0]);
+      gJ[1] = fma(s, dy, gJ[1]);
+      gJ[2] = fma(s, dz, gJ[2]);
+    }
+  }
+  const double gx = gJ[0] + gD[0], gy = gJ[1] + gD[1], gz = gJ[2] + gD[2];
+  Te[(size_t)e * nw + w] = -0.5 * (lJ + lD + gx * gx + gy * gy + gz * gz);
+  Vb[(size_t)e * nw + w] = v_bare;
+  Vl[(size_t)e * nw + w] = v_loc;
+}
+
+// =================================================================================================
+// E3: non-local ECP on the rotated quadrature (jqmc/coulomb_potential.py:1477-1712).
+// thread = (point=(electron, nn, k), walker).   Vnl[pt][w]
+// =================================================================================================
+template <int NMO, bool CART>
+__global__ void __launch_bounds__(128)
+k_ecp_mesh(BasisDev Bu, BasisDev Bd, SysDev S, int nw, const double* __restrict__ r_up, const double* __restrict__ r_dn,
+           const double* __restrict__ RT, const double* __restrict__ W, int det_only, double* __restrict__ Vnl,
+           double* __restrict__ mesh_xyz) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int npt = S.n_e * S.NN * S.Nv;
+  if (t >= (long long)npt * nw) return;
+  const int w = (int)(t % nw);
+  const int pt = (int)(t / nw);
+  const int k = pt % S.Nv;
+  const int nn = (pt / S.Nv) % S.NN;
+  const int e = pt / (S.Nv * S.NN);
+  PosGlobal pos{r_up, r_dn, S.n_up, S.n_dn, w};
+  double x, y, z;
+  pos.get(e, x, y, z);
+  double d;
+  const int a = nearest_atom(S.Rn, S.n_atom, x, y, z, nn, &d);
+  const double relx = __ldg(S.Rn + 3 * a) - x, rely = __ldg(S.Rn + 3 * a + 1) - y, relz = __ldg(S.Rn + 3 * a + 2) - z;
+  d = sqrt(relx * relx + rely * rely + relz * relz);
+  // rotated grid point g = grid[k] @ RT
+  const double* rt = RT + (size_t)w * 9;
+  const double q0 = __ldg(S.quad_g + 3 * k), q1 = __ldg(S.quad_g + 3 * k + 1), q2 = __ldg(S.quad_g + 3 * k + 2);
+  const double gx = q0 * rt[0] + q1 * rt[3] + q2 * rt[6];
+  const double gy = q0 * rt[1] + q1 * rt[4] + q2 * rt[7];
+  const double gz = q0 * rt[2] + q1 * rt[5] + q2 * rt[8];
+  const double px = x + relx + d * gx, py = y + rely + d * gy, pz = z + relz + d * gz;
+  if (mesh_xyz) {
+    double* m = mesh_xyz + ((size_t)pt * 3) * nw + w;
+    m[0] = px;
+    m[(size_t)nw] = py;
+    m[(size_t)2 * nw] = pz;
+  }
+  const double gn = sqrt(gx * gx + gy * gy + gz * gz);
+  const double cos_t = (-relx / d) * (gx / gn) + (-rely / d) * (gy / gn) + (-relz / d) * (gz / gn);
+  // radial channels V_l(d) = sum_terms c d^(p-2) exp(-z d^2), non-local terms only
+  const int lloc = __ldg(S.ecp_lmax_atom + a);
+  double ang = 0.0;
+  for (int l = 0; l < lloc; ++l) {
+    double vl = 0.0;
+    for (int kk = __ldg(S.ecp_off + a); kk < __ldg(S.ecp_off + a + 1); ++kk)
+      if (__ldg(S.ecp_l + kk) == l) vl += __ldg(S.ecp_c + kk) * pow(d, __ldg(S.ecp_p + kk)) * exp(-__ldg(S.ecp_z + kk) * d * d);
+    ang = fma(vl / (d * d) * (2 * l + 1), legendre_l(l, cos_t), ang);
+  }
+  double val = 0.0;
+  if (lloc > 0) {  // uniform per warp only if all lanes agree; divergence here is cheap relative to the AO sweep
+    const BasisDev& B = e < S.n_up ? Bu : Bd;
+    SinkMO<NMO> sink;
+    sink.init(B.Cs);
+    eval_val<CART>(B, S.Rn, px, py, pz, 0, B.n_grp, sink);
+    double ratio = 0.0;
+#pragma unroll
+    for (int mo = 0; mo < NMO; ++mo) ratio = fma(sink.acc[mo], W[((size_t)e * NMO + mo) * nw + w], ratio);
+    if (!det_only) ratio *= exp(jastrow_delta(S, pos, e, x, y, z, px, py, pz));
+    val = ang * __ldg(S.quad_w + k) * ratio;
+  }
+  Vnl[(size_t)pt * nw + w] = val;
+}
+
+// E4: e_L = sum_e T_e + V_bare + V_ion_ion + V_ecp_local + sum_pts V_nl   (jqmc/hamiltonians.py:225-290)
+__global__ void k_reduce_eL(SysDev S, int nw, const double* __restrict__ Te, const double* __restrict__ Vb,
+                            const double* __restrict__ Vl, const double* __restrict__ Vnl, double* __restrict__ e_L,
+                            double* __restrict__ T_elem, double* __restrict__ V_parts) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  double T = 0, vb = S.v_ion_ion, vl = 0, vnl = 0;
+  for (int e = 0; e < S.n_e; ++e) {
+    const double te = Te[(size_t)e * nw + w];
+    T += te;
+    vb += Vb[(size_t)e * nw + w];
+    vl += Vl[(size_t)e * nw + w];
+    if (T_elem) T_elem[(size_t)w * S.n_e + e] = te;
+  }
+  if (S.ecp_flag) {
+    const int npt = S.n_e * S.NN * S.Nv;
+    for (int p = 0; p < npt; ++p) vnl += Vnl[(size_t)p * nw + w];
+  }
+  e_L[w] = T + (vb + (vl + vnl));
+  if (V_parts) {
+    V_parts[(size_t)w * 4 + 0] = vb;
+    V_parts[(size_t)w * 4 + 1] = vl;
+    V_parts[(size_t)w * 4 + 2] = vnl;
+    V_parts[(size_t)w * 4 + 3] = 0.0;
+  }
+}
+
+// generic single-electron move ratios (parity entry; also the LRDMC kinetic mesh): thread = (move, walker)
+template <int NMO, bool CART>
+__global__ void __launch_bounds__(128)
+k_move_ratios(BasisDev Bu, BasisDev Bd, SysDev S, int nw, const double* __restrict__ r_up, const double* __restrict__ r_dn,
+              const double* __restrict__ W, int n_moves, const int* __restrict__ elec, const double* __restrict__ r_new,
+              double* __restrict__ det_ratio, double* __restrict__ jas_ratio) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n_moves * nw) return;
+  const int w = (int)(t % nw);
+  const int mv = (int)(t / nw);
+  const int e = elec[mv];
+  const double* p = r_new + ((size_t)w * n_moves + mv) * 3;
+  const double px = p[0], py = p[1], pz = p[2];
+  PosGlobal pos{r_up, r_dn, S.n_up, S.n_dn, w};
+  if (det_ratio) {
+    const BasisDev& B = e < S.n_up ? Bu : Bd;
+    SinkMO<NMO> sink;
+    sink.init(B.Cs);
+    eval_val<CART>(B, S.Rn, px, py, pz, 0, B.n_grp, sink);
+    double ratio = 0.0;
+#pragma unroll
+    for (int mo = 0; mo < NMO; ++mo) ratio = fma(sink.acc[mo], W[((size_t)e * NMO + mo) * nw + w], ratio);
+    det_ratio[(size_t)w * n_moves + mv] = ratio;
+  }
+  if (jas_ratio) {
+    double x, y, z;
+    pos.get(e, x, y, z);
+    jas_ratio[(size_t)w * n_moves + mv] = exp(jastrow_delta(S, pos, e, x, y, z, px, py, pz));
+  }
+}
+
+// =================================================================================================
+// AS regularisation factor (jqmc/determinant.py:1223-1260): thread = walker
+// =================================================================================================
+__global__ void k_as_factor(int N, int nw, const double* __restrict__ G, const double* __restrict__ Ginv,
+                            double* __restrict__ R_AS) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  const double* g = G + (size_t)w * N * N;
+  const double* gi = Ginv + (size_t)w * N * N;
+  double F = 0, S = 1e300;
+  for (int i = 0; i < N * N; ++i) F = fma(gi[i], gi[i], F);
+  for (int i = 0; i < N; ++i) {
+    double r = 0, c = 0;
+    for (int j = 0; j < N; ++j) {
+      r = fma(g[i * N + j], g[i * N + j], r);
+      c = fma(g[j * N + i], g[j * N + i], c);
+    }
+    S = fmin(S, fmin(r, c));
+  }
+  const double SF = S * F;
+  R_AS[w] = SF > 0.0 ? pow(SF, -0.375) : 0.0;
+}
+
+// =================================================================================================
+// RNG kernels (semantics: oracle/jaxrng.py; call sites jqmc/jqmc_mcmc.py:4322-4367, 4499-4500, 4232-4233)
+// =================================================================================================
+// rotation matrix RT = R^T from split(key)[1], key not advanced (jqmc/jqmc_mcmc.py:4228-4245)
+__device__ __forceinline__ void rotation_RT(double al, double be, double ga, double* __restrict__ o) {
+  double sa, ca, sb, cb, sg, cg;
+  sincos(al, &sa, &ca);
+  sincos(be, &sb, &cb);
+  sincos(ga, &sg, &cg);
+  // R rows; store transposed
+  const double R00 = cb * cg, R01 = cg * sa * sb - ca * sg, R02 = sa * sg + ca * cg * sb;
+  const double R10 = cb * sg, R11 = ca * cg + sa * sb * sg, R12 = ca * sb * sg - cg * sa;
+  const double R20 = -sb, R21 = cb * sa, R22 = ca * cb;
+  o[0] = R00; o[1] = R10; o[2] = R20;
+  o[3] = R01; o[4] = R11; o[5] = R21;
+  o[6] = R02; o[7] = R12; o[8] = R22;
+}
+__global__ void k_rotation(int nw, const uint32_t* __restrict__ keys, double* __restrict__ RT) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  Key k{keys[2 * w], keys[2 * w + 1]};
+  const Key sub = threefry(k, 0u, 1u);
+  const double two_pi = 6.283185307179586;
+  const double al = rng_uniform_bits(rng_bits64(sub, 0u), -two_pi, two_pi);
+  const double be = rng_uniform_bits(rng_bits64(sub, 1u), -two_pi, two_pi);
+  const double ga = rng_uniform_bits(rng_bits64(sub, 2u), -two_pi, two_pi);
+  rotation_RT(al, be, ga, RT + (size_t)w * 9);
+}
+
+// key chain of the Metropolis loop: 6 splits per proposal.  thread = walker.  sub[(p*6+i)][w]
+__global__ void k_mcmc_keychain(int nw, int nmpm, uint32_t* __restrict__ keys, uint2* __restrict__ sub) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  Key k{keys[2 * w], keys[2 * w + 1]};
+  for (int p = 0; p < nmpm * 6; ++p) {
+    Key s;
+    rng_split(k, s);
+    sub[(size_t)p * nw + w] = make_uint2(s.a, s.b);
+  }
+  keys[2 * w] = k.a;
+  keys[2 * w + 1] = k.b;
+}
+// draws of every proposal: thread = (proposal, walker)
+__global__ void k_mcmc_draws(int nw, int nmpm, int n_up, int n_dn, const uint2* __restrict__ sub, int* __restrict__ rsel,
+                             int* __restrict__ raxis, double* __restrict__ rg, double* __restrict__ rb) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nmpm * nw) return;
+  const int w = (int)(t % nw);
+  const int p = (int)(t / nw);
+  auto K = [&](int i) {
+    const uint2 v = sub[((size_t)p * 6 + i) * nw + w];
+    return Key{v.x, v.y};
+  };
+  const bool is_up = rng_randint(K(0), (uint32_t)(n_up + n_dn)) < n_up;
+  const int iu = rng_randint(K(1), (uint32_t)n_up);
+  const int id = rng_randint(K(2), (uint32_t)n_dn);
+  rsel[t] = is_up ? iu : n_up + id;
+  rg[t] = rng_normal(K(3));
+  raxis[t] = rng_randint(K(4), 3u);
+  rb[t] = rng_uniform_bits(rng_bits64(K(5)), 0.0, 1.0);
+}
+
+// =================================================================================================
+// Metropolis kernel (jqmc/jqmc_mcmc.py:4278-4533).  CTA = 32 walkers (lanes) x (n_chunk + 1) warps.
+//   warps 0..n_chunk-1 : AO/MO evaluation of one basis chunk at the proposed position
+//   warp  n_chunk      : proposal bookkeeping, T_ratio and Jastrow ratio
+//   warp  0            : determinant ratio, Sherman-Morrison update, AS factor, accept/reject
+// Walker state lives in shared memory as [item][lane].
+// =================================================================================================
+struct McmcArgs {
+  int nw, nmpm, n_chunk;
+  double Dt, eps_AS;
+  double* r_up;
+  double* r_dn;
+  double* G;
+  double* Ginv;
+  int* acc;
+  int* rej;
+  const int* rsel;
+  const int* raxis;
+  const double* rg;
+  const double* rb;
+  const int* chunk_begin;
+};
+
+template <int NMO, bool CART>
+__global__ void __launch_bounds__(512)
+k_mcmc(BasisDev Bu, BasisDev Bd, SysDev S, McmcArgs P) {
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x, wid = threadIdx.y;
+  const int w = blockIdx.x * 32 + lane;
+  const bool live = w < P.nw;
+  const int ww = live ? w : P.nw - 1;  // dead lanes shadow the last walker (no stores)
+  const int N = S.n_up, Nd = S.n_dn, Ne = S.n_e, NN2 = N * N;
+  const int nch = P.n_chunk;
+  // shared-memory carve-up (all [item][32])
+  double* s_r = sm;                       // Ne*3
+  double* s_G = s_r + Ne * 3 * 32;        // N*N
+  double* s_Gi = s_G + NN2 * 32;          // N*N
+  double* s_phi = s_Gi + NN2 * 32;        // Ne*NMO   (orbital values at the electrons: [e][mo])
+  double* s_part = s_phi + Ne * NMO * 32; // nch*NMO
+  double* s_TJ = s_part + nch * NMO * 32; // 2: T_ratio, J_ratio
+#define SR(e, c) s_r[((e) * 3 + (c)) * 32 + lane]
+#define SG(i, j) s_G[((i) * N + (j)) * 32 + lane]
+#define SGI(i, j) s_Gi[((i) * N + (j)) * 32 + lane]
+#define SPHI(e, mo) s_phi[((e) * NMO + (mo)) * 32 + lane]
+#define SPART(c, mo) s_part[((c) * NMO + (mo)) * 32 + lane]
+
+  // ---- load state -------------------------------------------------------------------------------
+  const int tid = wid * 32 + lane, nthr = 32 * (nch + 1);
+  for (int idx = wid; idx < Ne * 3; idx += nch + 1) {
+    const int e = idx / 3, c = idx % 3;
+    SR(e, c) = e < N ? P.r_up[((size_t)ww * N + e) * 3 + c] : P.r_dn[((size_t)ww * Nd + (e - N)) * 3 + c];
+  }
+  for (int idx = wid; idx < NN2; idx += nch + 1) {
+    s_G[idx * 32 + lane] = P.G[(size_t)ww * NN2 + idx];
+    s_Gi[idx * 32 + lane] = P.Ginv[(size_t)ww * NN2 + idx];
+  }
+  (void)tid;
+  (void)nthr;
+  __syncthreads();
+
+  // ---- orbital values at every electron (cache for the row/column rebuild) -----------------------
+  for (int e = 0; e < Ne; ++e) {
+    if (wid < nch) {
+      const BasisDev& B = e < N ? Bu : Bd;
+      SinkMO<NMO> sink;
+      sink.init(B.Cs);
+      eval_val<CART>(B, S.Rn, SR(e, 0), SR(e, 1), SR(e, 2), P.chunk_begin[wid], P.chunk_begin[wid + 1], sink);
+#pragma unroll
+      for (int mo = 0; mo < NMO; ++mo) SPART(wid, mo) = sink.acc[mo];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+      for (int mo = 0; mo < NMO; ++mo) {
+        double s = 0;
+        for (int c = 0; c < nch; ++c) s += SPART(c, mo);
+        SPHI(e, mo) = s;
+      }
+    }
+    __syncthreads();
+  }
+
+  int n_acc = 0, n_rej = 0;
+  double R_AS_cur = 1.0;
+  if (wid == 0 && P.eps_AS > 0.0) {
+    double F = 0, Smin = 1e300;
+    for (int i = 0; i < NN2; ++i) F = fma(s_Gi[i * 32 + lane], s_Gi[i * 32 + lane], F);
+    for (int i = 0; i < N; ++i) {
+      double r = 0, c = 0;
+      for (int j = 0; j < N; ++j) {
+        r = fma(SG(i, j), SG(i, j), r);
+        c = fma(SG(j, i), SG(j, i), c);
+      }
+      Smin = fmin(Smin, fmin(r, c));
+    }
+    const double SF = Smin * F;
+    R_AS_cur = SF > 0.0 ? pow(SF, -0.375) : 0.0;
+  }
+
+  for (int it = 0; it < P.nmpm; ++it) {
+    // ---- phase A: proposal (every thread, redundantly; lane = walker) ----------------------------
+    const size_t ridx = (size_t)it * P.nw + ww;
+    const int ke = P.rsel[ridx];
+    const int axis = P.raxis[ridx];
+    const bool up = ke < N;
+    const double ox = SR(ke, 0), oy = SR(ke, 1), oz = SR(ke, 2);
+    double dist;
+    int ia = nearest_atom(S.Rn, S.n_atom, ox, oy, oz, 0, &dist);
+    double Zc = __ldg(S.Zeff + ia);
+    const double f_l = 1.0 / (Zc * Zc) * (1.0 + Zc * Zc * dist) / (1.0 + dist);
+    const double g = P.rg[ridx] * (f_l * P.Dt);
+    double nx = ox, ny = oy, nz = oz;
+    if (axis == 0) nx = ox + g;
+    else if (axis == 1) ny = oy + g;
+    else nz = oz + g;
+
+    // ---- phase B ---------------------------------------------------------------------------------
+    if (wid < nch) {
+      // same AO tables for both spins (checked at create); the MO coefficients may differ per lane
+      SinkMO<NMO> sink;
+      sink.init(up ? Bu.Cs : Bd.Cs);
+      eval_val<CART>(Bu, S.Rn, nx, ny, nz, P.chunk_begin[wid], P.chunk_begin[wid + 1], sink);
+#pragma unroll
+      for (int mo = 0; mo < NMO; ++mo) SPART(wid, mo) = sink.acc[mo];
+    } else {
+      ia = nearest_atom(S.Rn, S.n_atom, nx, ny, nz, 0, &dist);
+      Zc = __ldg(S.Zeff + ia);
+      const double f_p = 1.0 / (Zc * Zc) * (1.0 + Zc * Zc * dist) / (1.0 + dist);
+      const double dd = (nx - ox) * (nx - ox) + (ny - oy) * (ny - oy) + (nz - oz) * (nz - oz);
+      const double T_ratio =
+          (f_l / f_p) * exp(-dd * (1.0 / (2.0 * f_p * f_p * P.Dt * P.Dt) - 1.0 / (2.0 * f_l * f_l * P.Dt * P.Dt)));
+      struct PosS {
+        const double* s_r;
+        int lane;
+        __device__ __forceinline__ void get(int e, double& x, double& y, double& z) const {
+          x = s_r[(e * 3 + 0) * 32 + lane];
+          y = s_r[(e * 3 + 1) * 32 + lane];
+          z = s_r[(e * 3 + 2) * 32 + lane];
+        }
+      } pos{s_r, lane};
+      const double J_ratio = exp(jastrow_delta(S, pos, ke, ox, oy, oz, nx, ny, nz));
+      s_TJ[lane] = T_ratio;
+      s_TJ[32 + lane] = J_ratio;
+    }
+    __syncthreads();
+
+    // ---- phase C: warp 0 -------------------------------------------------------------------------
+    if (wid == 0) {
+      double phi[NMO];
+#pragma unroll
+      for (int mo = 0; mo < NMO; ++mo) {
+        double s = 0;
+        for (int c = 0; c < nch; ++c) s += SPART(c, mo);
+        phi[mo] = s;
+      }
+      // v (row difference) or u (column difference), Det_ratio = 1 + v^T Ginv u
+      double dvec[8 > NMO ? 8 : NMO];  // N <= 8 enforced on the host for this kernel
+      double Det;
+      if (up) {
+        const int k = ke;
+        double t[NMO];
+#pragma unroll
+        for (int b = 0; b < NMO; ++b) {
+          double s = 0;
+#pragma unroll
+          for (int a = 0; a < NMO; ++a) s = fma(phi[a], __ldg(S.lam_p + a * NMO + b), s);
+          t[b] = s;
+        }
+        double acc = 0;
+        for (int j = 0; j < Nd; ++j) {
+          double s = 0;
+#pragma unroll
+          for (int b = 0; b < NMO; ++b) s = fma(t[b], SPHI(N + j, b), s);
+          dvec[j] = s - SG(k, j);
+          acc = fma(dvec[j], SGI(j, k), acc);
+        }
+        for (int q = 0; q < S.n_unp; ++q) {
+          double s = 0;
+#pragma unroll
+          for (int a = 0; a < NMO; ++a) s = fma(phi[a], __ldg(S.lam_u + a * S.n_unp + q), s);
+          dvec[Nd + q] = s - SG(k, Nd + q);
+          acc = fma(dvec[Nd + q], SGI(Nd + q, k), acc);
+        }
+        Det = 1.0 + acc;
+      } else {
+        const int k = ke - N;
+        double t[NMO];
+#pragma unroll
+        for (int a = 0; a < NMO; ++a) {
+          double s = 0;
+#pragma unroll
+          for (int b = 0; b < NMO; ++b) s = fma(__ldg(S.lam_p + a * NMO + b), phi[b], s);
+          t[a] = s;
+        }
+        double acc = 0;
+        for (int i = 0; i < N; ++i) {
+          double s = 0;
+#pragma unroll
+          for (int a = 0; a < NMO; ++a) s = fma(SPHI(i, a), t[a], s);
+          dvec[i] = s - SG(i, k);
+          acc = fma(SGI(k, i), dvec[i], acc);
+        }
+        Det = 1.0 + acc;
+      }
+      const double T_ratio = s_TJ[lane], J_ratio = s_TJ[32 + lane];
+      // AS regularisation of the proposed state without materialising it
+      double R_AS_ratio = 1.0, R_AS_p = R_AS_cur;
+      if (P.eps_AS > 0.0) {
+        double F = 0, Smin = 1e300;
+        if (up) {
+          const int k = ke;
+          // Ginv' = Ginv - Ginv[:,k] (v^T Ginv) / Det
+          for (int jp = 0; jp < N; ++jp) {
+            double vt = 0;
+            for (int j = 0; j < N; ++j) vt = fma(dvec[j], SGI(j, jp), vt);
+            vt /= Det;
+            for (int i = 0; i < N; ++i) {
+              const double x = SGI(i, jp) - SGI(i, k) * vt;
+              F = fma(x, x, F);
+            }
+          }
+          for (int i = 0; i < N; ++i) {
+            double r = 0, c = 0;
+            for (int j = 0; j < N; ++j) {
+              const double gij = SG(i, j) + (i == k ? dvec[j] : 0.0);
+              const double gji = SG(j, i) + (j == k ? dvec[i] : 0.0);
+              r = fma(gij, gij, r);
+              c = fma(gji, gji, c);
+            }
+            Smin = fmin(Smin, fmin(r, c));
+          }
+        } else {
+          const int k = ke - N;
+          // Ginv' = Ginv - (Ginv u) Ginv[k,:] / Det
+          for (int i = 0; i < N; ++i) {
+            double au = 0;
+            for (int j = 0; j < N; ++j) au = fma(SGI(i, j), dvec[j], au);
+            au /= Det;
+            for (int j = 0; j < N; ++j) {
+              const double x = SGI(i, j) - au * SGI(k, j);
+              F = fma(x, x, F);
+            }
+          }
+          for (int i = 0; i < N; ++i) {
+            double r = 0, c = 0;
+            for (int j = 0; j < N; ++j) {
+              const double gij = SG(i, j) + (j == k ? dvec[i] : 0.0);
+              const double gji = SG(j, i) + (i == k ? dvec[j] : 0.0);
+              r = fma(gij, gij, r);
+              c = fma(gji, gji, c);
+            }
+            Smin = fmin(Smin, fmin(r, c));
+          }
+        }
+        const double SF = Smin * F;
+        R_AS_p = SF > 0.0 ? pow(SF, -0.375) : 0.0;
+        R_AS_ratio = (fmax(R_AS_p, P.eps_AS) / R_AS_p) / (fmax(R_AS_cur, P.eps_AS) / R_AS_cur);
+      }
+      const double wr = R_AS_ratio * J_ratio * Det;
+      const double x = wr * wr * T_ratio;
+      const double b = P.rb[ridx];
+      const bool ok = (x == x) && (b < fmin(1.0, x)) && (Det != 0.0);
+      if (ok) {
+        ++n_acc;
+        R_AS_cur = R_AS_p;
+        SR(ke, 0) = nx;
+        SR(ke, 1) = ny;
+        SR(ke, 2) = nz;
+#pragma unroll
+        for (int mo = 0; mo < NMO; ++mo) SPHI(ke, mo) = phi[mo];
+        const double invD = 1.0 / Det;
+        if (up) {
+          const int k = ke;
+          double col[8], vt[8];
+          for (int i = 0; i < N; ++i) col[i] = SGI(i, k);
+          for (int jp = 0; jp < N; ++jp) {
+            double s = 0;
+            for (int j = 0; j < N; ++j) s = fma(dvec[j], SGI(j, jp), s);
+            vt[jp] = s;
+          }
+          for (int i = 0; i < N; ++i)
+            for (int jp = 0; jp < N; ++jp) SGI(i, jp) = SGI(i, jp) - (col[i] * vt[jp]) * invD;
+          for (int j = 0; j < N; ++j) SG(k, j) += dvec[j];
+        } else {
+          const int k = ke - N;
+          double au[8], row[8];
+          for (int i = 0; i < N; ++i) {
+            double s = 0;
+            for (int j = 0; j < N; ++j) s = fma(SGI(i, j), dvec[j], s);
+            au[i] = s;
+          }
+          for (int j = 0; j < N; ++j) row[j] = SGI(k, j);
+          for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) SGI(i, j) = SGI(i, j) - (au[i] * row[j]) * invD;
+          for (int i = 0; i < N; ++i) SG(i, k) += dvec[i];
+        }
+      } else {
+        ++n_rej;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- write back ---------------------------------------------------------------------------------
+  if (live) {
+    for (int idx = wid; idx < Ne * 3; idx += nch + 1) {
+      const int e = idx / 3, c = idx % 3;
+      if (e < N) P.r_up[((size_t)w * N + e) * 3 + c] = SR(e, c);
+      else P.r_dn[((size_t)w * Nd + (e - N)) * 3 + c] = SR(e, c);
+    }
+    for (int idx = wid; idx < NN2; idx += nch + 1) {
+      P.G[(size_t)w * NN2 + idx] = s_G[idx * 32 + lane];
+      P.Ginv[(size_t)w * NN2 + idx] = s_Gi[idx * 32 + lane];
+    }
+    if (wid == 0) {
+      P.acc[w] = n_acc;
+      P.rej[w] = n_rej;
+    }
+  }
+#undef SR
+#undef SG
+#undef SGI
+#undef SPHI
+#undef SPART
+}
+
+// =================================================================================================
+// fp64 peak microbenchmark
+// =================================================================================================
+__global__ void k_dfma_peak(int iters, double* out) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+static const double QUAD4[] = {0.5773502691896258, 0.5773502691896258, 0.5773502691896258, 0.5773502691896258, -0.5773502691896258, -0.5773502691896258,
+                               -0.5773502691896258, 0.5773502691896258, -0.5773502691896258, -0.5773502691896258, -0.5773502691896258, 0.5773502691896258};
+
+static void quadrature(int Nv, std::vector<double>& w, std::vector<double>& g) {
+  // jqmc/coulomb_potential.py:102-184
+  w.clear();
+  g.clear();
+  if (Nv == 4) {
+    const double q = 1.0 / std::sqrt(3.0);
+    (void)QUAD4;
+    const double s[4][3] = {{q, q, q}, {q, -q, -q}, {-q, q, -q}, {-q, -q, q}};
+    for (auto& r : s) {
+      w.push_back(0.25);
+      g.insert(g.end(), r, r + 3);
+    }
+  } else if (Nv == 6 || Nv == 18) {
+    const double s[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+    for (auto& r : s) {
+      w.push_back(1.0 / 6.0);
+      g.insert(g.end(), r, r + 3);
+    }
+    if (Nv == 18) {
+      for (auto& x : w) x = 1.0 / 6.0;
+      const double p = 1.0 / std::sqrt(2.0);
+      const double t[12][3] = {{p, p, 0}, {p, -p, 0}, {-p, p, 0}, {-p, -p, 0}, {p, 0, p}, {p, 0, -p},
+                               {-p, 0, p}, {-p, 0, -p}, {0, p, p}, {0, -p, p}, {0, p, -p}, {0, -p, -p}};
+      for (auto& r : t) {
+        w.push_back(1.0 / 15.0);
+        g.insert(g.end(), r, r + 3);
+      }
+    }
+  } else if (Nv == 12) {
+    const double th = std::atan(2.0);
+    std::vector<std::pair<double, double>> sph{{0.0, 0.0}, {M_PI, 0.0}};
+    for (int k = 0; k < 5; ++k) sph.push_back({th, 2.0 * k * M_PI / 5.0});
+    for (int k = 0; k < 5; ++k) sph.push_back({M_PI - th, (2.0 * k + 1.0) * M_PI / 5.0});
+    for (auto& s : sph) {
+      w.push_back(1.0 / 12.0);
+      g.push_back(std::sin(s.first) * std::cos(s.second));
+      g.push_back(std::sin(s.first) * std::sin(s.second));
+      g.push_back(std::cos(s.first));
+    }
+  }
+}
+
+extern "C" const char* qe_last_error(void) { return g_err.c_str(); }
+extern "C" int qe_version(void) {
+  return 100;  // 0.1.0, sm_100a build
+}
+
+extern "C" void qe_destroy(qe_engine* h) {
+  if (!h) return;
+  h->pool.release();
+  if (h->ws) cudaFree(h->ws);
+  delete h;
+}
+
+extern "C" int qe_create(const qe_system_desc* d, qe_engine** out) {
+  if (!d || !out) return fail(QE_ERR_INVALID, "qe_create: null argument");
+  *out = nullptr;
+  if (d->n_atom <= 0 || d->n_up <= 0 || d->n_dn < 0 || d->n_dn > d->n_up)
+    return fail(QE_ERR_INVALID, "qe_create: need n_atom > 0 and n_up >= n_dn >= 0, n_up > 0");
+  if (d->j3_flag) return fail(QE_ERR_UNSUPPORTED, "three-body Jastrow is not implemented in this build");
+  if (d->orb_up.n_mo <= 0 || d->orb_dn.n_mo <= 0)
+    return fail(QE_ERR_UNSUPPORTED, "AO-basis geminals (JAGP) are not implemented in this build; use the MO representation");
+  if (d->orb_up.n_mo != d->orb_dn.n_mo) return fail(QE_ERR_INVALID, "orb_num_up != orb_num_dn");
+  if (d->orb_up.n_mo > 16) return fail(QE_ERR_UNSUPPORTED, "more than 16 molecular orbitals per spin is not implemented in this build");
+  if (d->n_up > 16) return fail(QE_ERR_UNSUPPORTED, "more than 16 electrons per spin is not implemented in this build");
+  if (d->ecp_flag && !(d->Nv == 4 || d->Nv == 6 || d->Nv == 12 || d->Nv == 18)) return fail(QE_ERR_INVALID, "Nv must be 4, 6, 12 or 18");
+  if (d->ecp_flag && (d->NN < 1 || d->NN > d->n_atom)) return fail(QE_ERR_INVALID, "NN must be in 1..n_atom");
+  if (!same_ao_tables(d->orb_up, d->orb_dn)) return fail(QE_ERR_UNSUPPORTED, "up/dn orbitals must share the same AO tables");
+
+  qe_engine* h = new qe_engine();
+  const int n_mo = d->orb_up.n_mo;
+  h->nmo_pad = n_mo <= 4 ? 4 : (n_mo <= 8 ? 8 : 16);
+  int rc = build_basis(d->orb_up, d->n_atom, h->nmo_pad, h->pool, h->b_up);
+  if (rc == QE_OK) rc = build_basis(d->orb_dn, d->n_atom, h->nmo_pad, h->pool, h->b_dn);
+  if (rc != QE_OK) {
+    qe_destroy(h);
+    return rc;
+  }
+  SysDev& S = h->sys;
+  S.n_atom = d->n_atom;
+  S.n_up = d->n_up;
+  S.n_dn = d->n_dn;
+  S.n_e = d->n_up + d->n_dn;
+  S.n_unp = d->n_up - d->n_dn;
+  std::vector<double> Rn(d->positions, d->positions + 3 * d->n_atom), Z(d->effective_charges, d->effective_charges + d->n_atom);
+  const int P = h->nmo_pad;
+  const int lam_cols = n_mo + S.n_unp;
+  std::vector<double> lam_p((size_t)P * P, 0.0), lam_u((size_t)P * std::max(1, S.n_unp), 0.0);
+  for (int a = 0; a < n_mo; ++a) {
+    for (int b = 0; b < n_mo; ++b) lam_p[(size_t)a * P + b] = d->lambda_matrix[(size_t)a * lam_cols + b];
+    for (int k = 0; k < S.n_unp; ++k) lam_u[(size_t)a * S.n_unp + k] = d->lambda_matrix[(size_t)a * lam_cols + n_mo + k];
+  }
+  std::vector<double> jA(d->n_atom, 0.0), jc(d->n_atom, 0.0);
+  S.j1_type = d->j1_type;
+  S.j1_a = d->j1_param;
+  if (d->j1_type) {
+    for (int a = 0; a < d->n_atom; ++a) {
+      const double z = d->j1_atomic_numbers[a] - d->j1_core_electrons[a];
+      jA[a] = std::pow(2.0 * z, 0.75);
+      jc[a] = std::pow(2.0 * z, 0.25);
+    }
+  }
+  S.j2_type = d->j2_type;
+  S.j2_a = d->j2_param;
+  S.ecp_flag = d->ecp_flag;
+  S.Nv = d->ecp_flag ? d->Nv : 0;
+  S.NN = d->ecp_flag ? d->NN : 0;
+  std::vector<int> e_nuc, e_l, e_off(d->n_atom + 1, 0), e_lmax(d->n_atom, 0);
+  std::vector<double> e_z, e_c, e_p, qw, qg;
+  S.ecp_lmax = 0;
+  if (d->ecp_flag) {
+    for (int a = 0; a < d->n_atom; ++a) {
+      e_lmax[a] = d->ecp_max_ang_mom_plus_1[a];
+      S.ecp_lmax = std::max(S.ecp_lmax, e_lmax[a]);
+      for (int k = 0; k < d->n_ecp; ++k)
+        if (d->ecp_nucleus_index[k] == a) {
+          e_nuc.push_back(a);
+          e_l.push_back(d->ecp_ang_moms[k]);
+          e_z.push_back(d->ecp_exponents[k]);
+          e_c.push_back(d->ecp_coefficients[k]);
+          e_p.push_back((double)d->ecp_powers[k]);
+        }
+      e_off[a + 1] = (int)e_nuc.size();
+    }
+    if (S.ecp_lmax > 7) {
+      qe_destroy(h);
+      return fail(QE_ERR_UNSUPPORTED, "ECP angular momentum > 6");
+    }
+    quadrature(d->Nv, qw, qg);
+  }
+  S.n_ecp = (int)e_nuc.size();
+  S.v_ion_ion = 0.0;  // jqmc/coulomb_potential.py:2521-2571
+  for (int a = 0; a < d->n_atom; ++a)
+    for (int b = a + 1; b < d->n_atom; ++b) {
+      const double dx = Rn[3 * a] - Rn[3 * b], dy = Rn[3 * a + 1] - Rn[3 * b + 1], dz = Rn[3 * a + 2] - Rn[3 * b + 2];
+      S.v_ion_ion += Z[a] * Z[b] / std::sqrt(dx * dx + dy * dy + dz * dz);
+    }
+  // chunk tables
+  h->chunk_el = make_chunks(h->b_up.grp_cost, 3);
+  h->chunk_mc = make_chunks(h->b_up.grp_cost, 7);
+  h->n_chunk_el = (int)h->chunk_el.size() - 1;
+  h->n_chunk_mc = (int)h->chunk_mc.size() - 1;
+  cudaError_t e = cudaSuccess;
+  DevPool& pl = h->pool;
+  e = pl.upload(Rn, &S.Rn);
+  if (e == cudaSuccess) e = pl.upload(Z, &S.Zeff);
+  if (e == cudaSuccess) e = pl.upload(lam_p, &S.lam_p);
+  if (e == cudaSuccess) e = pl.upload(lam_u, &S.lam_u);
+  if (e == cudaSuccess) e = pl.upload(jA, &S.j1_A);
+  if (e == cudaSuccess) e = pl.upload(jc, &S.j1_c);
+  if (e == cudaSuccess) e = pl.upload(e_nuc, &S.ecp_nuc);
+  if (e == cudaSuccess) e = pl.upload(e_l, &S.ecp_l);
+  if (e == cudaSuccess) e = pl.upload(e_z, &S.ecp_z);
+  if (e == cudaSuccess) e = pl.upload(e_c, &S.ecp_c);
+  if (e == cudaSuccess) e = pl.upload(e_p, &S.ecp_p);
+  if (e == cudaSuccess) e = pl.upload(e_lmax, &S.ecp_lmax_atom);
+  if (e == cudaSuccess) e = pl.upload(e_off, &S.ecp_off);
+  if (e == cudaSuccess) e = pl.upload(qw, &S.quad_w);
+  if (e == cudaSuccess) e = pl.upload(qg, &S.quad_g);
+  if (e == cudaSuccess) e = pl.upload(h->chunk_el, &h->d_chunk_el);
+  if (e == cudaSuccess) e = pl.upload(h->chunk_mc, &h->d_chunk_mc);
+  if (e != cudaSuccess) {
+    qe_destroy(h);
+    return fail(QE_ERR_CUDA, std::string("qe_create upload: ") + cudaGetErrorString(e));
+  }
+  *out = h;
+  return QE_OK;
+}
+
+extern "C" int64_t qe_launch_count(qe_engine* h) { return h ? h->launches : 0; }
+
+#define DISPATCH_NMO_CART(h, CALL)                                  \
+  do {                                                              \
+    const bool cart_ = (h)->b_up.dev.cart != 0;                     \
+    switch ((h)->nmo_pad) {                                         \
+      case 4: if (cart_) { CALL(4, true); } else { CALL(4, false); } break;   \
+      case 8: if (cart_) { CALL(8, true); } else { CALL(8, false); } break;   \
+      default: if (cart_) { CALL(16, true); } else { CALL(16, false); } break; \
+    }                                                               \
+  } while (0)
+#define DISPATCH_NMO(h, CALL)       \
+  do {                              \
+    switch ((h)->nmo_pad) {         \
+      case 4: CALL(4); break;       \
+      case 8: CALL(8); break;       \
+      default: CALL(16); break;     \
+    }                               \
+  } while (0)
+
+static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+#define CHECK_LAUNCH()                                                                    \
+  do {                                                                                    \
+    cudaError_t e_ = cudaGetLastError();                                                  \
+    if (e_ != cudaSuccess) return fail(QE_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" int qe_eval_orbitals(qe_engine* h, int which, int layer, int n_pts, const double* r, double* out, void* stream) {
+  if (!h || !r || !out || n_pts <= 0) return fail(QE_ERR_INVALID, "qe_eval_orbitals: bad argument");
+  HostBasis* hb = which == 0 ? &h->b_up : which == 1 ? &h->b_dn : &h->b_j3;
+  if (!hb->present) return fail(QE_ERR_INVALID, "qe_eval_orbitals: basis not present");
+  cudaStream_t st = (cudaStream_t)stream;
+  const BasisDev& B = hb->dev;
+  if (layer == 0 || B.n_mo == 0) {
+    if (B.cart) k_eval_ao<true><<<nblk(n_pts, 128), 128, 0, st>>>(B, h->sys.Rn, n_pts, r, out);
+    else k_eval_ao<false><<<nblk(n_pts, 128), 128, 0, st>>>(B, h->sys.Rn, n_pts, r, out);
+  } else {
+#define CALL(NMO, CART) k_eval_mo<NMO, CART><<<nblk(n_pts, 128), 128, 0, st>>>(B, h->sys.Rn, n_pts, r, out)
+    switch (B.nmo_pad) {
+      case 4: if (B.cart) { CALL(4, true); } else { CALL(4, false); } break;
+      case 8: if (B.cart) { CALL(8, true); } else { CALL(8, false); } break;
+      default: if (B.cart) { CALL(16, true); } else { CALL(16, false); } break;
+    }
+#undef CALL
+  }
+  h->launches++;
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+
+// workspace carve-up helper
+struct WsCarve {
+  char* base;
+  size_t off = 0;
+  template <class T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = (T*)(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+static size_t ws_need_common(const qe_engine* h, int nw, int n_chunk, int nq) {
+  const SysDev& S = h->sys;
+  size_t n = 0;
+  n += (size_t)n_chunk * S.n_e * nq * h->nmo_pad * nw * 8 + 256;  // phi
+  n += (size_t)S.n_e * h->nmo_pad * nw * 8 + 256;                 // W
+  n += 3 * ((size_t)S.n_e * nw * 8 + 256);                        // Te, Vb, Vl
+  n += (size_t)std::max(1, S.n_e * S.NN * S.Nv) * nw * 8 + 256;   // Vnl
+  return n + 4096;
+}
+
+extern "C" int qe_geminal_init(qe_engine* h, int nw, const double* r_up, const double* r_dn, double* G, double* Ginv,
+                               void* stream) {
+  if (!h || nw <= 0 || !r_up || (!r_dn && h->sys.n_dn > 0)) return fail(QE_ERR_INVALID, "qe_geminal_init: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const SysDev& S = h->sys;
+  int rc;
+  double* phi;
+  rc = ensure_ws(h, ws_need_common(h, nw, h->n_chunk_el, 1));
+  if (rc) return rc;
+  WsCarve c2{(char*)h->ws};
+  phi = c2.take<double>((size_t)h->n_chunk_el * S.n_e * h->nmo_pad * nw);
+  const long long total2 = (long long)h->n_chunk_el * S.n_e * nw;
+#define CALL(NMO, CART)                                                                                              \
+  k_orb_electrons<NMO, CART, 1><<<nblk(total2, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, \
+                                                                   h->d_chunk_el, h->n_chunk_el, phi)
+  DISPATCH_NMO_CART(h, CALL);
+#undef CALL
+  h->launches++;
+  CHECK_LAUNCH();
+#define CALL(NMO) k_geminal<NMO><<<nblk(nw, 64), 64, 0, st>>>(S, nw, h->n_chunk_el, phi, r_up, r_dn, G, Ginv, nullptr, nullptr)
+  DISPATCH_NMO(h, CALL);
+#undef CALL
+  h->launches++;
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+
+extern "C" int qe_ln_wavefunction(qe_engine* h, int nw, const double* r_up, const double* r_dn, double* ln_psi, double* sign,
+                                  void* stream) {
+  if (!h || nw <= 0 || !r_up || !ln_psi) return fail(QE_ERR_INVALID, "qe_ln_wavefunction: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const SysDev& S = h->sys;
+  int rc = ensure_ws(h, ws_need_common(h, nw, h->n_chunk_el, 1));
+  if (rc) return rc;
+  WsCarve c{(char*)h->ws};
+  double* phi = c.take<double>((size_t)h->n_chunk_el * S.n_e * h->nmo_pad * nw);
+  const long long total = (long long)h->n_chunk_el * S.n_e * nw;
+#define CALL(NMO, CART)                                                                                             \
+  k_orb_electrons<NMO, CART, 1><<<nblk(total, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, \
+                                                                  h->d_chunk_el, h->n_chunk_el, phi)
+  DISPATCH_NMO_CART(h, CALL);
+#undef CALL
+  h->launches++;
+  CHECK_LAUNCH();
+#define CALL(NMO) k_geminal<NMO><<<nblk(nw, 64), 64, 0, st>>>(S, nw, h->n_chunk_el, phi, r_up, r_dn, nullptr, nullptr, ln_psi, sign)
+  DISPATCH_NMO(h, CALL);
+#undef CALL
+  h->launches++;
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+
+extern "C" int qe_as_factor(qe_engine* h, int nw, const double* G, const double* Ginv, double* R_AS, void* stream) {
+  if (!h || nw <= 0 || !G || !Ginv || !R_AS) return fail(QE_ERR_INVALID, "qe_as_factor: bad argument");
+  k_as_factor<<<nblk(nw, 128), 128, 0, (cudaStream_t)stream>>>(h->sys.n_up, nw, G, Ginv, R_AS);
+  h->launches++;
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+
+extern "C" int qe_rotation(qe_engine* h, int nw, const uint32_t* keys, double* RT, void* stream) {
+  if (!h || nw <= 0 || !keys || !RT) return fail(QE_ERR_INVALID, "qe_rotation: bad argument");
+  k_rotation<<<nblk(nw, 128), 128, 0, (cudaStream_t)stream>>>(nw, keys, RT);
+  h->launches++;
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+
+extern "C" int qe_local_energy(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,
+                               double* e_L, double* T_elem, double* V_parts, void* stream) {
+  if (!h || nw <= 0 || !r_up || !Ginv || !e_L || (!r_dn && h->sys.n_dn > 0)) return fail(QE_ERR_INVALID, "qe_local_energy: bad argument");
+  if (h->sys.ecp_flag && !RT) return fail(QE_ERR_INVALID, "qe_local_energy: RT required for ECP systems");
+  cudaStream_t st = (cudaStream_t)stream;
+  const SysDev& S = h->sys;
+  const int nch = h->n_chunk_el, P = h->nmo_pad;
+  int rc = ensure_ws(h, ws_need_common(h, nw, nch, 5));
+  if (rc) return rc;
+  WsCarve c{(char*)h->ws};
+  double* phi = c.take<double>((size_t)nch * S.n_e * 5 * P * nw);
+  double* W = c.take<double>((size_t)S.n_e * P * nw);
+  double* Te = c.take<double>((size_t)S.n_e * nw);
+  double* Vb = c.take<double>((size_t)S.n_e * nw);
+  double* Vl = c.take<double>((size_t)S.n_e * nw);
+  double* Vnl = c.take<double>((size_t)std::max(1, S.n_e * S.NN * S.Nv) * nw);
+  const long long t1 = (long long)nch * S.n_e * nw;
+#define CALL(NMO, CART)                                                                                          \
+  k_orb_electrons<NMO, CART, 5><<<nblk(t1, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, \
+                                                               h->d_chunk_el, nch, phi)
+  DISPATCH_NMO_CART(h, CALL);
+#undef CALL
+  h->launches++;
+  CHECK_LAUNCH();
+  const long long t2 = (long long)S.n_e * nw;
+#define CALL(NMO) k_electron_algebra<NMO, 5><<<nblk(t2, 128), 128, 0, st>>>(S, nw, nch, phi, r_up, r_dn, Ginv, W, Te, Vb, Vl)
+  DISPATCH_NMO(h, CALL);
+#undef CALL
+  h->launches++;
+  CHECK_LAUNCH();
+  if (S.ecp_flag) {
+    const long long t3 = (long long)S.n_e * S.NN * S.Nv * nw;
+#define CALL(NMO, CART) \
+  k_ecp_mesh<NMO, CART><<<nblk(t3, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, RT, W, 0, Vnl, nullptr)
+    DISPATCH_NMO_CART(h, CALL);
+#undef CALL
+    h->launches++;
+    CHECK_LAUNCH();
+  }
+  k_reduce_eL<<<nblk(nw, 128), 128, 0, st>>>(S, nw, Te, Vb, Vl, Vnl, e_L, T_elem, V_parts);
+  h->launches++;
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+
+extern "C" int qe_move_ratios(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* Ginv, int n_moves,
+                              const int32_t* elec_host, const double* r_new, double* det_ratio, double* jas_ratio, void* stream) {
+  if (!h || nw <= 0 || n_moves <= 0 || !r_up || !Ginv || !elec_host || !r_new) return fail(QE_ERR_INVALID, "qe_move_ratios: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const SysDev& S = h->sys;
+  for (int i = 0; i < n_moves; ++i)
+    if (elec_host[i] < 0 || elec_host[i] >= S.n_e) return fail(QE_ERR_INVALID, "qe_move_ratios: electron index out of range");
+  const int nch = h->n_chunk_el, P = h->nmo_pad;
+  int rc = ensure_ws(h, ws_need_common(h, nw, nch, 1) + (size_t)n_moves * 4 + 256);
+  if (rc) return rc;
+  WsCarve c{(char*)h->ws};
+  double* phi = c.take<double>((size_t)nch * S.n_e * P * nw);
+  double* W = c.take<double>((size_t)S.n_e * P * nw);
+  int* elec = c.take<int>(n_moves);
+  CUDA_TRY(cudaMemcpyAsync(elec, elec_host, (size_t)n_moves * 4, cudaMemcpyHostToDevice, st));
+  const long long t1 = (long long)nch * S.n_e * nw;
+#define CALL(NMO, CART)                                                                                          \
+  k_orb_electrons<NMO, CART, 1><<<nblk(t1, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, \
+                                                               h->d_chunk_el, nch, phi)
+  DISPATCH_NMO_CART(h, CALL);
+#undef CALL
+  h->launches++;
+  CHECK_LAUNCH();
+  const long long t2 = (long long)S.n_e * nw;
+#define CALL(NMO) \
+  k_electron_algebra<NMO, 1><<<nblk(t2, 128), 128, 0, st>>>(S, nw, nch, phi, r_up, r_dn, Ginv, W, nullptr, nullptr, nullptr)
+  DISPATCH_NMO(h, CALL);
+#undef CALL
+  h->launches++;
+  CHECK_LAUNCH();
+  const long long t3 = (long long)n_moves * nw;
+#define CALL(NMO, CART)                                                                                                   \
+  k_move_ratios<NMO, CART><<<nblk(t3, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, W, n_moves, elec, \
+                                                          r_new, det_ratio, jas_ratio)
+  DISPATCH_NMO_CART(h, CALL);
+#undef CALL
+  h->launches++;
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+
+extern "C" int qe_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, uint32_t* keys, double* G, double* Ginv, int nmpm,
+                              double Dt, double epsilon_AS, int32_t* acc, int32_t* rej, void* stream) {
+  if (!h || nw <= 0 || nmpm < 0 || !r_up || !keys || !G || !Ginv || !acc || !rej || (!r_dn && h->sys.n_dn > 0))
+    return fail(QE_ERR_INVALID, "qe_mcmc_update: bad argument");
+  const SysDev& S = h->sys;
+  if (S.n_up > 8) return fail(QE_ERR_UNSUPPORTED, "qe_mcmc_update: more than 8 electrons per spin is not implemented in this build");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = h->nmo_pad, nch = h->n_chunk_mc;
+  const size_t n_draw = (size_t)std::max(1, nmpm) * nw;
+  int rc = ensure_ws(h, n_draw * (6 * 8 + 4 + 4 + 8 + 8) + 4096);
+  if (rc) return rc;
+  WsCarve c{(char*)h->ws};
+  uint2* sub = c.take<uint2>(n_draw * 6);
+  int* rsel = c.take<int>(n_draw);
+  int* raxis = c.take<int>(n_draw);
+  double* rg = c.take<double>(n_draw);
+  double* rb = c.take<double>(n_draw);
+  if (nmpm > 0) {
+    k_mcmc_keychain<<<nblk(nw, 64), 64, 0, st>>>(nw, nmpm, keys, sub);
+    h->launches++;
+    CHECK_LAUNCH();
+    k_mcmc_draws<<<nblk((long long)nmpm * nw, 128), 128, 0, st>>>(nw, nmpm, S.n_up, S.n_dn, sub, rsel, raxis, rg, rb);
+    h->launches++;
+    CHECK_LAUNCH();
+  }
+  McmcArgs A{nw, nmpm, nch, Dt, epsilon_AS, r_up, r_dn, G, Ginv, acc, rej, rsel, raxis, rg, rb, h->d_chunk_mc};
+  const size_t smem = (size_t)(S.n_e * 3 + 2 * S.n_up * S.n_up + S.n_e * P + nch * P + 2) * 32 * 8;
+  dim3 block(32, nch + 1);
+#define CALL(NMO, CART)                                                                                           \
+  do {                                                                                                            \
+    CUDA_TRY(cudaFuncSetAttribute(k_mcmc<NMO, CART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    k_mcmc<NMO, CART><<<nblk(nw, 32), block, smem, st>>>(h->b_up.dev, h->b_dn.dev, S, A);                         \
+  } while (0)
+  DISPATCH_NMO_CART(h, CALL);
+#undef CALL
+  h->launches++;
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+
+extern "C" int qe_lrdmc_project(qe_engine*, int, double*, double*, double*, double*, uint32_t*, double, int, int, int, double, double*,
+                                double*, double*, void*) {
+  return fail(QE_ERR_UNSUPPORTED, "qe_lrdmc_project: not implemented in this build");
+}
+extern "C" int qe_lrdmc_velements(qe_engine*, int, const double*, const double*, const double*, const double*, int, double, double*,
+                                  double*, void*) {
+  return fail(QE_ERR_UNSUPPORTED, "qe_lrdmc_velements: not implemented in this build");
+}
+
+extern "C" int qe_measure_fp64_peak(int iters, double* tflops) {
+  if (!tflops || iters <= 0) return fail(QE_ERR_INVALID, "qe_measure_fp64_peak: bad argument");
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double* out = nullptr;
+  CUDA_TRY(cudaMalloc(&out, 8));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const int blocks = sms * 8, threads = 256;
+  k_dfma_peak<<<blocks, threads>>>(iters / 4, out);
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaEventRecord(e0));
+  k_dfma_peak<<<blocks, threads>>>(iters, out);
+  CUDA_TRY(cudaEventRecord(e1));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+  cudaFree(out);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return QE_OK;
+}

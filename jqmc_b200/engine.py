@@ -1,0 +1,341 @@
+"""Host-side mirror of jQMC's walker-batched callables on top of the C ABI (include/jqmc_b200.h).
+
+``WalkerEngine`` flattens a ``Hamiltonian_data`` (the reference's own object or the mirrors in
+``jqmc_b200.data``) into device tables once, and then exposes the seams the reference's drivers call
+every step, with the same names, argument order and array layouts:
+
+=============================  ======================================================================
+reference callable             engine method
+=============================  ======================================================================
+``_geminal_inv_batched``       ``geminal_inv_batched(r_up, r_dn) -> (G, Ginv)``  jqmc_mcmc.py:4264
+``_jit_vmap_update``           ``update(r_up, r_dn, keys, nmpm, Dt, epsilon_AS, Ginv, G)``  :4728
+``_jit_vmap_generate_RTs``     ``generate_RTs(keys)``  :4738
+``_jit_vmap_e_L_fast``         ``e_L_fast(r_up, r_dn, RTs, Ginv)``  :4736
+``_jit_vmap_as_reg_fast``      ``as_reg_fast(G, Ginv)``  :4739
+``evaluate_ln_wavefunction``   ``ln_wavefunction(r_up, r_dn)``  wavefunction.py:677
+=============================  ======================================================================
+
+Arrays are fp64 / uint32 CUDA tensors with the walker axis leading.  Inputs may be torch CUDA tensors
+(zero copy), any object with ``__dlpack__`` such as a ``jax.Array`` (zero copy via DLPack), or NumPy
+arrays (copied host->device).  Outputs are torch CUDA tensors (``jax.dlpack.from_dlpack`` /
+``.cpu().numpy()`` on the caller's side).  PyTorch is only used for device memory and streams.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .data import is_cart, is_mos
+
+
+def _i32(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.int32))
+
+
+def _f64(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+
+
+def _p_i32(a):
+    return a.ctypes.data_as(_lib.i32p)
+
+
+def _p_f64(a):
+    return a.ctypes.data_as(_lib.f64p)
+
+
+def _basis_desc(orb, keep):
+    """qe_basis_desc from AOs_sphe_data / AOs_cart_data / MOs_data (attribute duck typing)."""
+    d = _lib.qe_basis_desc()
+    aos = orb.aos_data if is_mos(orb) else orb
+    d.cartesian = 1 if is_cart(aos) else 0
+    d.n_ao = int(aos.num_ao)
+    d.n_prim = int(aos.num_ao_prim)
+    arrs = dict(
+        nucleus_index=_i32(aos.nucleus_index),
+        angular_momentums=_i32(aos.angular_momentums),
+        orbital_indices=_i32(aos.orbital_indices),
+        exponents=_f64(aos.exponents),
+        coefficients=_f64(aos.coefficients),
+    )
+    if len(arrs["exponents"]) != d.n_prim or len(arrs["orbital_indices"]) != d.n_prim:
+        raise ValueError("AO tables: exponents/coefficients/orbital_indices must have num_ao_prim entries")
+    if len(arrs["nucleus_index"]) != d.n_ao or len(arrs["angular_momentums"]) != d.n_ao:
+        raise ValueError("AO tables: nucleus_index/angular_momentums must have num_ao entries")
+    if d.cartesian:
+        arrs["px"] = _i32(aos.polynominal_order_x)
+        arrs["py"] = _i32(aos.polynominal_order_y)
+        arrs["pz"] = _i32(aos.polynominal_order_z)
+        d.polynominal_order_x, d.polynominal_order_y, d.polynominal_order_z = (_p_i32(arrs[k]) for k in ("px", "py", "pz"))
+    else:
+        arrs["m"] = _i32(aos.magnetic_quantum_numbers)
+        d.magnetic_quantum_numbers = _p_i32(arrs["m"])
+    d.nucleus_index = _p_i32(arrs["nucleus_index"])
+    d.angular_momentums = _p_i32(arrs["angular_momentums"])
+    d.orbital_indices = _p_i32(arrs["orbital_indices"])
+    d.exponents = _p_f64(arrs["exponents"])
+    d.coefficients = _p_f64(arrs["coefficients"])
+    if is_mos(orb):
+        c = _f64(orb.mo_coefficients)
+        if c.shape != (int(orb.num_mo), d.n_ao):
+            raise ValueError(f"mo_coefficients shape {c.shape} != ({orb.num_mo}, {d.n_ao})")
+        arrs["C"] = c
+        d.n_mo = int(orb.num_mo)
+        d.mo_coefficients = _p_f64(c)
+    else:
+        d.n_mo = 0
+    keep.append(arrs)
+    return d
+
+
+class WalkerEngine:
+    """Device-resident tables of one Hamiltonian + the batched step kernels (see module docstring)."""
+
+    def __init__(self, hamiltonian_data, Nv: int = 6, NN: int = 1, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("jqmc_b200.WalkerEngine needs a CUDA device (there is no CPU path)")
+        self._lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        H = hamiltonian_data
+        wf = H.wavefunction_data
+        gem = wf.geminal_data
+        jas = wf.jastrow_data
+        cp = H.coulomb_potential_data
+        st = H.structure_data
+        if getattr(st, "pbc_flag", False):
+            raise NotImplementedError("periodic systems are not supported (as in the reference: trexio_wrapper.py:112-119)")
+        if getattr(jas, "jastrow_nn_data", None) is not None:
+            raise NotImplementedError("NN Jastrow is out of scope of the walker engine")
+        keep = []
+        d = _lib.qe_system_desc()
+        pos = _f64(st.positions).reshape(-1, 3)
+        z_all = _f64(st.atomic_numbers)
+        zeff = z_all - _f64(cp.z_cores) if cp.ecp_flag else z_all
+        d.n_atom = pos.shape[0]
+        d.positions = _p_f64(pos)
+        d.effective_charges = _p_f64(zeff)
+        d.n_up, d.n_dn = int(gem.num_electron_up), int(gem.num_electron_dn)
+        d.orb_up = _basis_desc(gem.orb_data_up_spin, keep)
+        d.orb_dn = _basis_desc(gem.orb_data_dn_spin, keep)
+        lam = _f64(gem.lambda_matrix)
+        n_orb_up = d.orb_up.n_mo or d.orb_up.n_ao
+        n_orb_dn = d.orb_dn.n_mo or d.orb_dn.n_ao
+        if lam.shape != (n_orb_up, n_orb_dn + d.n_up - d.n_dn):
+            raise ValueError(f"lambda_matrix shape {lam.shape} != ({n_orb_up}, {n_orb_dn + d.n_up - d.n_dn})")
+        d.lambda_matrix = _p_f64(lam)
+        j1 = getattr(jas, "jastrow_one_body_data", None)
+        j2 = getattr(jas, "jastrow_two_body_data", None)
+        j3 = getattr(jas, "jastrow_three_body_data", None)
+        if j1 is not None:
+            d.j1_type = {"exp": 1, "pade": 2}[j1.jastrow_1b_type]
+            d.j1_param = float(j1.jastrow_1b_param)
+            core = _f64(j1.core_electrons)
+            zj = _f64(j1.structure_data.atomic_numbers)
+            keep.append((core, zj))
+            d.j1_core_electrons, d.j1_atomic_numbers = _p_f64(core), _p_f64(zj)
+        if j2 is not None:
+            d.j2_type = {"pade": 1, "exp": 2}[j2.jastrow_2b_type]
+            d.j2_param = float(j2.jastrow_2b_param)
+        if j3 is not None:
+            d.j3_flag = 1
+            d.j3_orb = _basis_desc(j3.orb_data, keep)
+            jm = _f64(j3.j_matrix)
+            keep.append(jm)
+            d.j_matrix = _p_f64(jm)
+        if cp.ecp_flag:
+            d.ecp_flag = 1
+            d.n_ecp = int(cp.num_ecps)
+            e = dict(
+                nuc=_i32(cp.nucleus_index), l=_i32(cp.ang_moms), z=_f64(cp.exponents), c=_f64(cp.coefficients),
+                p=_i32(cp.powers), lmax=_i32(cp.max_ang_mom_plus_1),
+            )  # fmt: skip
+            keep.append(e)
+            d.ecp_nucleus_index, d.ecp_ang_moms, d.ecp_powers = _p_i32(e["nuc"]), _p_i32(e["l"]), _p_i32(e["p"])
+            d.ecp_exponents, d.ecp_coefficients = _p_f64(e["z"]), _p_f64(e["c"])
+            d.ecp_max_ang_mom_plus_1 = _p_i32(e["lmax"])
+        d.Nv, d.NN = int(Nv), int(NN)
+        keep += [pos, zeff, lam]
+        self.n_up, self.n_dn, self.n_atom = d.n_up, d.n_dn, d.n_atom
+        self.n_e = d.n_up + d.n_dn
+        self.Nv, self.NN = int(Nv), int(NN)
+        self.ecp_flag = bool(cp.ecp_flag)
+        self.n_orb = n_orb_up
+        self._n_ao = int(d.orb_up.n_ao)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.qe_create(C.byref(d), C.byref(h)), "qe_create")
+        self._h = h
+        del keep
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.qe_destroy(h)
+            except Exception:
+                pass
+
+    # ---- tensor plumbing -------------------------------------------------------------------------
+    def _dev(self, x, dtype=torch.float64):
+        if isinstance(x, torch.Tensor):
+            t = x
+        elif isinstance(x, np.ndarray):
+            t = torch.from_numpy(np.ascontiguousarray(x))
+        elif hasattr(x, "__dlpack__"):
+            t = torch.from_dlpack(x)
+        else:
+            t = torch.as_tensor(np.asarray(x))
+        if t.dtype != dtype:
+            if dtype == torch.uint32 and t.dtype in (torch.int32, torch.int64):
+                t = t.to(torch.int64).to(torch.uint32) if t.dtype == torch.int64 else t.view(torch.uint32)
+            else:
+                t = t.to(dtype)
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        return t.contiguous()
+
+    @staticmethod
+    def _ptr(t):
+        return C.c_void_p(t.data_ptr()) if t is not None and t.numel() else C.c_void_p(0)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _walkers(self, r_up, r_dn):
+        r_up = self._dev(r_up)
+        nw = r_up.shape[0]
+        if r_up.shape != (nw, self.n_up, 3):
+            raise ValueError(f"r_up_carts shape {tuple(r_up.shape)} != (nw, {self.n_up}, 3)")
+        r_dn = self._dev(r_dn) if self.n_dn else torch.zeros((nw, 0, 3), dtype=torch.float64, device=self.device)
+        if r_dn.shape != (nw, self.n_dn, 3):
+            raise ValueError(f"r_dn_carts shape {tuple(r_dn.shape)} != ({nw}, {self.n_dn}, 3)")
+        return r_up, r_dn, nw
+
+    def _mat(self, x, nw, name):
+        x = self._dev(x)
+        if x.shape != (nw, self.n_up, self.n_up):
+            raise ValueError(f"{name} shape {tuple(x.shape)} != ({nw}, {self.n_up}, {self.n_up})")
+        return x
+
+    def _keys(self, keys, nw):
+        keys = self._dev(keys, torch.uint32)
+        if keys.shape != (nw, 2):
+            raise ValueError(f"keys shape {tuple(keys.shape)} != ({nw}, 2)")
+        return keys
+
+    # ---- seams -----------------------------------------------------------------------------------
+    def geminal_inv_batched(self, r_up, r_dn):
+        r_up, r_dn, nw = self._walkers(r_up, r_dn)
+        G = torch.empty((nw, self.n_up, self.n_up), dtype=torch.float64, device=self.device)
+        Ginv = torch.empty_like(G)
+        rc = self._lib.qe_geminal_init(self._h, nw, self._ptr(r_up), self._ptr(r_dn), self._ptr(G), self._ptr(Ginv), self._stream())
+        _lib.check(rc, "qe_geminal_init")
+        return G, Ginv
+
+    def update(self, r_up, r_dn, keys, num_mcmc_per_measurement, Dt, epsilon_AS, Ginv, G, inplace=False):
+        """``nmpm`` Metropolis proposals per walker.  Returns
+        ``(accepted[nw], rejected[nw], r_up, r_dn, keys, Ginv, G)`` like the reference.  With
+        ``inplace=True`` the caller's CUDA tensors are updated directly (no clone)."""
+        r_up, r_dn, nw = self._walkers(r_up, r_dn)
+        keys = self._keys(keys, nw)
+        G, Ginv = self._mat(G, nw, "geminal"), self._mat(Ginv, nw, "geminal_inv")
+        if not inplace:
+            r_up, r_dn, keys, G, Ginv = (t.clone() for t in (r_up, r_dn, keys, G, Ginv))
+        acc = torch.empty(nw, dtype=torch.int32, device=self.device)
+        rej = torch.empty(nw, dtype=torch.int32, device=self.device)
+        rc = self._lib.qe_mcmc_update(
+            self._h, nw, self._ptr(r_up), self._ptr(r_dn), self._ptr(keys), self._ptr(G), self._ptr(Ginv),
+            int(num_mcmc_per_measurement), float(Dt), float(epsilon_AS), self._ptr(acc), self._ptr(rej), self._stream(),
+        )  # fmt: skip
+        _lib.check(rc, "qe_mcmc_update")
+        return acc, rej, r_up, r_dn, keys, Ginv, G
+
+    def generate_RTs(self, keys):
+        keys = self._dev(keys, torch.uint32)
+        nw = keys.shape[0]
+        keys = self._keys(keys, nw)
+        RT = torch.empty((nw, 3, 3), dtype=torch.float64, device=self.device)
+        _lib.check(self._lib.qe_rotation(self._h, nw, self._ptr(keys), self._ptr(RT), self._stream()), "qe_rotation")
+        return RT
+
+    def e_L_fast(self, r_up, r_dn, RTs, Ginv, return_parts=False):
+        r_up, r_dn, nw = self._walkers(r_up, r_dn)
+        Ginv = self._mat(Ginv, nw, "geminal_inverse")
+        if RTs is None:
+            RTs = torch.eye(3, dtype=torch.float64, device=self.device).repeat(nw, 1, 1)
+        RTs = self._dev(RTs)
+        if RTs.shape != (nw, 3, 3):
+            raise ValueError(f"RTs shape {tuple(RTs.shape)} != ({nw}, 3, 3)")
+        e_L = torch.empty(nw, dtype=torch.float64, device=self.device)
+        T = V = None
+        if return_parts:
+            T = torch.empty((nw, self.n_e), dtype=torch.float64, device=self.device)
+            V = torch.empty((nw, 4), dtype=torch.float64, device=self.device)
+        rc = self._lib.qe_local_energy(
+            self._h, nw, self._ptr(r_up), self._ptr(r_dn), self._ptr(RTs), self._ptr(Ginv), self._ptr(e_L),
+            self._ptr(T), self._ptr(V), self._stream(),
+        )  # fmt: skip
+        _lib.check(rc, "qe_local_energy")
+        return (e_L, T, V) if return_parts else e_L
+
+    def as_reg_fast(self, G, Ginv):
+        G = self._dev(G)
+        nw = G.shape[0]
+        G, Ginv = self._mat(G, nw, "geminal"), self._mat(Ginv, nw, "geminal_inv")
+        out = torch.empty(nw, dtype=torch.float64, device=self.device)
+        _lib.check(self._lib.qe_as_factor(self._h, nw, self._ptr(G), self._ptr(Ginv), self._ptr(out), self._stream()), "qe_as_factor")
+        return out
+
+    def ln_wavefunction(self, r_up, r_dn):
+        r_up, r_dn, nw = self._walkers(r_up, r_dn)
+        ln = torch.empty(nw, dtype=torch.float64, device=self.device)
+        sg = torch.empty(nw, dtype=torch.float64, device=self.device)
+        rc = self._lib.qe_ln_wavefunction(self._h, nw, self._ptr(r_up), self._ptr(r_dn), self._ptr(ln), self._ptr(sg), self._stream())
+        _lib.check(rc, "qe_ln_wavefunction")
+        return ln, sg
+
+    def eval_orbitals(self, which, layer, r):
+        """(5, n_orb, n_pts): value, d/dx, d/dy, d/dz, laplacian.  which: 'up'|'dn'|'j3'; layer: 'ao'|'orb'."""
+        r = self._dev(r).reshape(-1, 3)
+        wi = {"up": 0, "dn": 1, "j3": 2}[which]
+        li = {"ao": 0, "orb": 1}[layer]
+        n_orb = self._n_out(wi, li)
+        out = torch.zeros((5, n_orb, r.shape[0]), dtype=torch.float64, device=self.device)
+        rc = self._lib.qe_eval_orbitals(self._h, wi, li, r.shape[0], self._ptr(r), self._ptr(out), self._stream())
+        _lib.check(rc, "qe_eval_orbitals")
+        return out
+
+    def _n_out(self, wi, li):
+        return self._n_ao if li == 0 else self.n_orb
+
+    def move_ratios(self, r_up, r_dn, Ginv, elec, r_new, det=True, jas=True):
+        r_up, r_dn, nw = self._walkers(r_up, r_dn)
+        Ginv = self._mat(Ginv, nw, "A_old_inv")
+        elec = _i32(elec)
+        n_moves = len(elec)
+        r_new = self._dev(r_new)
+        if r_new.shape != (nw, n_moves, 3):
+            raise ValueError(f"r_new shape {tuple(r_new.shape)} != ({nw}, {n_moves}, 3)")
+        dr = torch.empty((nw, n_moves), dtype=torch.float64, device=self.device) if det else None
+        jr = torch.empty((nw, n_moves), dtype=torch.float64, device=self.device) if jas else None
+        rc = self._lib.qe_move_ratios(
+            self._h, nw, self._ptr(r_up), self._ptr(r_dn), self._ptr(Ginv), n_moves, _p_i32(elec), self._ptr(r_new),
+            self._ptr(dr), self._ptr(jr), self._stream(),
+        )  # fmt: skip
+        _lib.check(rc, "qe_move_ratios")
+        torch.cuda.current_stream(self.device).synchronize()  # elec is a host buffer
+        return dr, jr
+
+    def launch_count(self) -> int:
+        return int(self._lib.qe_launch_count(self._h))
+
+
+def measure_fp64_peak(iters: int = 20000) -> float:
+    """Achieved DFMA TFLOP/s of this GPU (roofline denominator for the fp64 kernels)."""
+    out = C.c_double()
+    _lib.check(_lib.load().qe_measure_fp64_peak(int(iters), C.byref(out)), "qe_measure_fp64_peak")
+    return float(out.value)
