@@ -151,6 +151,15 @@ int qe_measure_fp64_peak(int iters, double* tflops);
 /* Number of kernel launches issued by this engine since creation (bench.py's gpu_launches). */
 int64_t qe_launch_count(qe_engine* h);
 
+/* Optional per-kernel device timing for bench.py's roofline line: when enabled, every launch is
+ * bracketed by CUDA events on its own stream.  qe_profile(h, on) also clears the records;
+ * qe_profile_read() sums the elapsed time and the launch count of kernel `id` (0 .. qe_profile_kernels()-1,
+ * named by qe_profile_name) since then (synchronises on the recorded events). */
+int qe_profile(qe_engine* h, int enable);
+int qe_profile_kernels(void);
+const char* qe_profile_name(int id);
+int qe_profile_read(qe_engine* h, int id, double* total_ms, int64_t* count);
+
 #ifdef __cplusplus
 }
 #endif

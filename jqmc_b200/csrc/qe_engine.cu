@@ -102,11 +102,41 @@ struct qe_engine {
   void* ws = nullptr;
   size_t ws_bytes = 0;
   int64_t launches = 0;
+  // optional per-kernel timing (qe_profile): CUDA events recorded on the launch stream around each kernel
+  bool profiling = false;
+  struct ProfRec { int id; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
   int n_chunk_el = 1;    // chunks used by the electron VGL pass
   int n_chunk_mc = 1;    // chunk warps of the Metropolis kernel
   std::vector<int> chunk_el, chunk_mc;
   const int* d_chunk_el = nullptr;
   const int* d_chunk_mc = nullptr;
+};
+
+enum KernelId { K_ORB_EL = 0, K_GEMINAL, K_ALGEBRA, K_ECP_MESH, K_REDUCE, K_RATIOS, K_AS, K_ROT, K_KEYCHAIN, K_DRAWS, K_MCMC,
+                K_EVAL, K_LRDMC, K_COUNT };
+static const char* const KERNEL_NAMES[K_COUNT] = {"k_orb_electrons", "k_geminal", "k_electron_algebra", "k_ecp_mesh", "k_reduce_eL",
+                                                  "k_move_ratios", "k_as_factor", "k_rotation", "k_mcmc_keychain", "k_mcmc_draws",
+                                                  "k_mcmc", "k_eval_orbitals", "k_lrdmc"};
+struct LaunchScope {
+  qe_engine* h;
+  cudaStream_t st;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int id;
+  LaunchScope(qe_engine* h_, int id_, cudaStream_t st_) : h(h_), st(st_), id(id_) {
+    h->launches++;
+    if (h->profiling) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, st);
+    }
+  }
+  ~LaunchScope() {
+    if (e0) {
+      cudaEventRecord(e1, st);
+      h->prof.push_back({id, e0, e1});
+    }
+  }
 };
 
 static int ensure_ws(qe_engine* h, size_t bytes) {
@@ -1344,6 +1374,10 @@ extern "C" int qe_version(void) {
 
 extern "C" void qe_destroy(qe_engine* h) {
   if (!h) return;
+  for (auto& r : h->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
   h->pool.release();
   if (h->ws) cudaFree(h->ws);
   delete h;
@@ -1466,6 +1500,38 @@ extern "C" int qe_create(const qe_system_desc* d, qe_engine** out) {
 
 extern "C" int64_t qe_launch_count(qe_engine* h) { return h ? h->launches : 0; }
 
+static void prof_clear(qe_engine* h) {
+  for (auto& r : h->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  h->prof.clear();
+}
+extern "C" int qe_profile(qe_engine* h, int enable) {
+  if (!h) return fail(QE_ERR_INVALID, "qe_profile: null engine");
+  prof_clear(h);
+  h->profiling = enable != 0;
+  return QE_OK;
+}
+extern "C" int qe_profile_kernels(void) { return K_COUNT; }
+extern "C" const char* qe_profile_name(int id) { return (id >= 0 && id < K_COUNT) ? KERNEL_NAMES[id] : ""; }
+extern "C" int qe_profile_read(qe_engine* h, int id, double* total_ms, int64_t* count) {
+  if (!h || !total_ms || !count || id < 0 || id >= K_COUNT) return fail(QE_ERR_INVALID, "qe_profile_read: bad argument");
+  double tot = 0;
+  int64_t n = 0;
+  for (auto& r : h->prof)
+    if (r.id == id) {
+      CUDA_TRY(cudaEventSynchronize(r.e1));
+      float ms = 0;
+      CUDA_TRY(cudaEventElapsedTime(&ms, r.e0, r.e1));
+      tot += ms;
+      ++n;
+    }
+  *total_ms = tot;
+  *count = n;
+  return QE_OK;
+}
+
 #define DISPATCH_NMO_CART(h, CALL)                                  \
   do {                                                              \
     const bool cart_ = (h)->b_up.dev.cart != 0;                     \
@@ -1497,6 +1563,7 @@ extern "C" int qe_eval_orbitals(qe_engine* h, int which, int layer, int n_pts, c
   if (!hb->present) return fail(QE_ERR_INVALID, "qe_eval_orbitals: basis not present");
   cudaStream_t st = (cudaStream_t)stream;
   const BasisDev& B = hb->dev;
+  { LaunchScope ls_(h, K_EVAL, st);
   if (layer == 0 || B.n_mo == 0) {
     if (B.cart) k_eval_ao<true><<<nblk(n_pts, 128), 128, 0, st>>>(B, h->sys.Rn, n_pts, r, out);
     else k_eval_ao<false><<<nblk(n_pts, 128), 128, 0, st>>>(B, h->sys.Rn, n_pts, r, out);
@@ -1509,7 +1576,7 @@ extern "C" int qe_eval_orbitals(qe_engine* h, int which, int layer, int n_pts, c
     }
 #undef CALL
   }
-  h->launches++;
+  }
   CHECK_LAUNCH();
   return QE_OK;
 }
@@ -1549,17 +1616,19 @@ extern "C" int qe_geminal_init(qe_engine* h, int nw, const double* r_up, const d
   WsCarve c2{(char*)h->ws};
   phi = c2.take<double>((size_t)h->n_chunk_el * S.n_e * h->nmo_pad * nw);
   const long long total2 = (long long)h->n_chunk_el * S.n_e * nw;
+  { LaunchScope ls_(h, K_ORB_EL, st);
 #define CALL(NMO, CART)                                                                                              \
   k_orb_electrons<NMO, CART, 1><<<nblk(total2, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, \
                                                                    h->d_chunk_el, h->n_chunk_el, phi)
   DISPATCH_NMO_CART(h, CALL);
 #undef CALL
-  h->launches++;
+  }
   CHECK_LAUNCH();
+  { LaunchScope ls_(h, K_GEMINAL, st);
 #define CALL(NMO) k_geminal<NMO><<<nblk(nw, 64), 64, 0, st>>>(S, nw, h->n_chunk_el, phi, r_up, r_dn, G, Ginv, nullptr, nullptr)
   DISPATCH_NMO(h, CALL);
 #undef CALL
-  h->launches++;
+  }
   CHECK_LAUNCH();
   return QE_OK;
 }
@@ -1574,33 +1643,37 @@ extern "C" int qe_ln_wavefunction(qe_engine* h, int nw, const double* r_up, cons
   WsCarve c{(char*)h->ws};
   double* phi = c.take<double>((size_t)h->n_chunk_el * S.n_e * h->nmo_pad * nw);
   const long long total = (long long)h->n_chunk_el * S.n_e * nw;
+  { LaunchScope ls_(h, K_ORB_EL, st);
 #define CALL(NMO, CART)                                                                                             \
   k_orb_electrons<NMO, CART, 1><<<nblk(total, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, \
                                                                   h->d_chunk_el, h->n_chunk_el, phi)
   DISPATCH_NMO_CART(h, CALL);
 #undef CALL
-  h->launches++;
+  }
   CHECK_LAUNCH();
+  { LaunchScope ls_(h, K_GEMINAL, st);
 #define CALL(NMO) k_geminal<NMO><<<nblk(nw, 64), 64, 0, st>>>(S, nw, h->n_chunk_el, phi, r_up, r_dn, nullptr, nullptr, ln_psi, sign)
   DISPATCH_NMO(h, CALL);
 #undef CALL
-  h->launches++;
+  }
   CHECK_LAUNCH();
   return QE_OK;
 }
 
 extern "C" int qe_as_factor(qe_engine* h, int nw, const double* G, const double* Ginv, double* R_AS, void* stream) {
   if (!h || nw <= 0 || !G || !Ginv || !R_AS) return fail(QE_ERR_INVALID, "qe_as_factor: bad argument");
+  { LaunchScope ls_(h, K_AS, (cudaStream_t)stream);
   k_as_factor<<<nblk(nw, 128), 128, 0, (cudaStream_t)stream>>>(h->sys.n_up, nw, G, Ginv, R_AS);
-  h->launches++;
+  }
   CHECK_LAUNCH();
   return QE_OK;
 }
 
 extern "C" int qe_rotation(qe_engine* h, int nw, const uint32_t* keys, double* RT, void* stream) {
   if (!h || nw <= 0 || !keys || !RT) return fail(QE_ERR_INVALID, "qe_rotation: bad argument");
+  { LaunchScope ls_(h, K_ROT, (cudaStream_t)stream);
   k_rotation<<<nblk(nw, 128), 128, 0, (cudaStream_t)stream>>>(nw, keys, RT);
-  h->launches++;
+  }
   CHECK_LAUNCH();
   return QE_OK;
 }
@@ -1622,30 +1695,34 @@ extern "C" int qe_local_energy(qe_engine* h, int nw, const double* r_up, const d
   double* Vl = c.take<double>((size_t)S.n_e * nw);
   double* Vnl = c.take<double>((size_t)std::max(1, S.n_e * S.NN * S.Nv) * nw);
   const long long t1 = (long long)nch * S.n_e * nw;
+  { LaunchScope ls_(h, K_ORB_EL, st);
 #define CALL(NMO, CART)                                                                                          \
   k_orb_electrons<NMO, CART, 5><<<nblk(t1, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, \
                                                                h->d_chunk_el, nch, phi)
   DISPATCH_NMO_CART(h, CALL);
 #undef CALL
-  h->launches++;
+  }
   CHECK_LAUNCH();
   const long long t2 = (long long)S.n_e * nw;
+  { LaunchScope ls_(h, K_ALGEBRA, st);
 #define CALL(NMO) k_electron_algebra<NMO, 5><<<nblk(t2, 128), 128, 0, st>>>(S, nw, nch, phi, r_up, r_dn, Ginv, W, Te, Vb, Vl)
   DISPATCH_NMO(h, CALL);
 #undef CALL
-  h->launches++;
+  }
   CHECK_LAUNCH();
   if (S.ecp_flag) {
     const long long t3 = (long long)S.n_e * S.NN * S.Nv * nw;
+    { LaunchScope ls_(h, K_ECP_MESH, st);
 #define CALL(NMO, CART) \
   k_ecp_mesh<NMO, CART><<<nblk(t3, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, RT, W, 0, Vnl, nullptr)
     DISPATCH_NMO_CART(h, CALL);
 #undef CALL
-    h->launches++;
+    }
     CHECK_LAUNCH();
   }
+  { LaunchScope ls_(h, K_REDUCE, st);
   k_reduce_eL<<<nblk(nw, 128), 128, 0, st>>>(S, nw, Te, Vb, Vl, Vnl, e_L, T_elem, V_parts);
-  h->launches++;
+  }
   CHECK_LAUNCH();
   return QE_OK;
 }
@@ -1666,27 +1743,30 @@ extern "C" int qe_move_ratios(qe_engine* h, int nw, const double* r_up, const do
   int* elec = c.take<int>(n_moves);
   CUDA_TRY(cudaMemcpyAsync(elec, elec_host, (size_t)n_moves * 4, cudaMemcpyHostToDevice, st));
   const long long t1 = (long long)nch * S.n_e * nw;
+  { LaunchScope ls_(h, K_ORB_EL, st);
 #define CALL(NMO, CART)                                                                                          \
   k_orb_electrons<NMO, CART, 1><<<nblk(t1, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, \
                                                                h->d_chunk_el, nch, phi)
   DISPATCH_NMO_CART(h, CALL);
 #undef CALL
-  h->launches++;
+  }
   CHECK_LAUNCH();
   const long long t2 = (long long)S.n_e * nw;
+  { LaunchScope ls_(h, K_ALGEBRA, st);
 #define CALL(NMO) \
   k_electron_algebra<NMO, 1><<<nblk(t2, 128), 128, 0, st>>>(S, nw, nch, phi, r_up, r_dn, Ginv, W, nullptr, nullptr, nullptr)
   DISPATCH_NMO(h, CALL);
 #undef CALL
-  h->launches++;
+  }
   CHECK_LAUNCH();
   const long long t3 = (long long)n_moves * nw;
+  { LaunchScope ls_(h, K_RATIOS, st);
 #define CALL(NMO, CART)                                                                                                   \
   k_move_ratios<NMO, CART><<<nblk(t3, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, W, n_moves, elec, \
                                                           r_new, det_ratio, jas_ratio)
   DISPATCH_NMO_CART(h, CALL);
 #undef CALL
-  h->launches++;
+  }
   CHECK_LAUNCH();
   return QE_OK;
 }
@@ -1709,16 +1789,19 @@ extern "C" int qe_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, 
   double* rg = c.take<double>(n_draw);
   double* rb = c.take<double>(n_draw);
   if (nmpm > 0) {
+    { LaunchScope ls_(h, K_KEYCHAIN, st);
     k_mcmc_keychain<<<nblk(nw, 64), 64, 0, st>>>(nw, nmpm, keys, sub);
-    h->launches++;
+    }
     CHECK_LAUNCH();
+    { LaunchScope ls_(h, K_DRAWS, st);
     k_mcmc_draws<<<nblk((long long)nmpm * nw, 128), 128, 0, st>>>(nw, nmpm, S.n_up, S.n_dn, sub, rsel, raxis, rg, rb);
-    h->launches++;
+    }
     CHECK_LAUNCH();
   }
   McmcArgs A{nw, nmpm, nch, Dt, epsilon_AS, r_up, r_dn, G, Ginv, acc, rej, rsel, raxis, rg, rb, h->d_chunk_mc};
   const size_t smem = (size_t)(S.n_e * 3 + 2 * S.n_up * S.n_up + S.n_e * P + nch * P + 2) * 32 * 8;
   dim3 block(32, nch + 1);
+  { LaunchScope ls_(h, K_MCMC, st);
 #define CALL(NMO, CART)                                                                                           \
   do {                                                                                                            \
     CUDA_TRY(cudaFuncSetAttribute(k_mcmc<NMO, CART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
@@ -1726,7 +1809,7 @@ extern "C" int qe_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, 
   } while (0)
   DISPATCH_NMO_CART(h, CALL);
 #undef CALL
-  h->launches++;
+  }
   CHECK_LAUNCH();
   return QE_OK;
 }

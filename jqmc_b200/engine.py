@@ -333,6 +333,20 @@ class WalkerEngine:
     def launch_count(self) -> int:
         return int(self._lib.qe_launch_count(self._h))
 
+    def profile(self, enable: bool):
+        """Switch per-kernel CUDA-event timing on/off (clears previous records)."""
+        _lib.check(self._lib.qe_profile(self._h, 1 if enable else 0), "qe_profile")
+
+    def profile_read(self):
+        """{kernel name: (total_ms, launches)} since profile(True)."""
+        out = {}
+        for i in range(self._lib.qe_profile_kernels()):
+            ms, n = C.c_double(), C.c_int64()
+            _lib.check(self._lib.qe_profile_read(self._h, i, C.byref(ms), C.byref(n)), "qe_profile_read")
+            if n.value:
+                out[self._lib.qe_profile_name(i).decode()] = (ms.value, n.value)
+        return out
+
 
 def measure_fp64_peak(iters: int = 20000) -> float:
     """Achieved DFMA TFLOP/s of this GPU (roofline denominator for the fp64 kernels)."""

@@ -1,0 +1,300 @@
+"""``MCMC`` driver on the walker engine: the host-side mirror of jQMC's VMC sampler.
+
+Same constructor arguments, step loop, stored observables and ``get_E`` statistics as
+``jqmc.jqmc_mcmc.MCMC`` (jqmc/jqmc_mcmc.py:129-258 constructor, :448-1062 ``run``, :1064-1189
+``get_E``), with the per-step device work done by ``WalkerEngine`` instead of ``jit(vmap(...))``:
+
+    for each measurement step (jqmc_mcmc.py:664-747)
+        update   -> qe_mcmc_update        (nmpm Metropolis proposals per walker)
+        RTs      -> qe_rotation
+        e_L      -> qe_local_energy
+        w_L      -> qe_as_factor, w = (R_AS / max(R_AS, eps))^2
+
+Ranks: one process per GPU; rank r seeds with ``mcmc_seed * (r + 1)`` and owns ``num_walkers``
+walkers (jqmc_mcmc.py:191-197).  The only collectives are the ``get_E`` reductions, done with
+``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) when a process group is initialised.
+
+Out of scope here (SURVEY.md §8f "next"): parameter/position derivatives, ``run_optimize``.
+"""
+
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from . import rng_host
+from .engine import WalkerEngine
+
+
+def _dist():
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist
+    return None
+
+
+def _rank_size():
+    d = _dist()
+    return (d.get_rank(), d.get_world_size()) if d else (0, 1)
+
+
+def _allreduce_sum(values, device=None):
+    """Sum a small fp64 vector over ranks (NCCL needs CUDA tensors, gloo CPU tensors)."""
+    d = _dist()
+    a = np.atleast_1d(np.asarray(values, dtype=np.float64))
+    if d is None:
+        return a
+    dev = device if (device is not None and d.get_backend() == "nccl") else torch.device("cpu")
+    t = torch.from_numpy(a.copy()).to(dev)
+    d.all_reduce(t, op=d.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def generate_init_electron_configurations(n_up, n_dn, num_walkers, charges, coords):
+    """Initial walkers: electrons assigned to nuclei (valence-filling order over a farthest-atom sequence),
+    each placed on a uniform shell 0.1-1.0 bohr around its owner.  Same assignment rules and the same
+    ``np.random`` draw order as jqmc/_jqmc_utility.py:54-218 (dn offsets, then up offsets;
+    distance/theta/phi blocks), so a seeded run starts from the reference's configurations.
+    Returns (r_up[nw,n_up,3], r_dn[nw,n_dn,3], up_owner, dn_owner)."""
+    coords = np.asarray(coords, dtype=np.float64)
+    nion = coords.shape[0]
+    zeta = np.array([int(round(c)) for c in np.asarray(charges)], dtype=int)
+    max_dn = zeta // 2
+    # farthest-from-previous atom sequence
+    seq = [0]
+    free = np.ones(nion, dtype=bool)
+    free[0] = False
+    for _ in range(1, nion):
+        d2 = np.sum((coords[seq[-1]] - coords) ** 2, axis=1)
+        nxt = int(np.argmax(np.where(free, d2, -1.0)))
+        seq.append(nxt)
+        free[nxt] = False
+    seq = np.array(seq)
+    occ_tot = np.zeros(nion, dtype=int)
+    occ_dn = np.zeros(nion, dtype=int)
+    occ_up = np.zeros(nion, dtype=int)
+    dn_tmpl = np.empty(n_dn, dtype=int)
+    j = 0
+    for i in range(n_dn):
+        while True:
+            a = seq[j % nion]
+            if np.any(occ_dn < max_dn):
+                ok = occ_dn[a] < max_dn[a]
+            elif np.any((max_dn == 0) & (occ_tot < zeta)):
+                ok = max_dn[a] == 0 and occ_tot[a] < zeta[a]
+            else:
+                ok = occ_tot[a] < zeta[a]
+            j += 1
+            if ok:
+                dn_tmpl[i] = a
+                occ_dn[a] += 1
+                occ_tot[a] += 1
+                break
+    need = zeta - occ_dn
+    up_tmpl = np.empty(n_up, dtype=int)
+    n_extra = 0
+    if n_up <= int(need.sum()):
+        p = 0
+        for i in range(n_up):
+            while True:
+                a = seq[p % nion]
+                p += 1
+                if occ_up[a] < need[a]:
+                    up_tmpl[i] = a
+                    occ_up[a] += 1
+                    break
+    else:
+        c = 0
+        for a in seq:
+            for _ in range(int(need[a])):
+                up_tmpl[c] = a
+                c += 1
+        n_extra = n_up - int(need.sum())
+    dn_owner = np.broadcast_to(dn_tmpl, (num_walkers, n_dn)).copy() if n_dn else np.empty((num_walkers, 0), dtype=int)
+    up_owner = np.empty((num_walkers, n_up), dtype=int)
+    if n_extra:
+        det = n_up - n_extra
+        up_owner[:, :det] = up_tmpl[:det][None, :]
+        ridx = np.clip(np.floor(np.random.rand(num_walkers, n_extra) * nion).astype(int), 0, nion - 1)
+        up_owner[:, det:] = seq[ridx]
+    else:
+        up_owner[:] = up_tmpl[None, :]
+
+    def offsets(shape):
+        dist = np.random.uniform(0.1, 1.0, size=shape)
+        th = np.random.uniform(0.0, np.pi, size=shape)
+        ph = np.random.uniform(0.0, 2.0 * np.pi, size=shape)
+        st = np.sin(th)
+        return np.stack([dist * st * np.cos(ph), dist * st * np.sin(ph), dist * np.cos(th)], axis=-1)
+
+    off_dn = offsets((num_walkers, n_dn)) if n_dn else np.zeros((num_walkers, 0, 3))
+    off_up = offsets((num_walkers, n_up)) if n_up else np.zeros((num_walkers, 0, 3))
+    return coords[up_owner] + off_up, coords[dn_owner] + off_dn, up_owner, dn_owner
+
+
+class MCMC:
+    """VMC sampler (see module docstring).  Public surface follows jqmc.jqmc_mcmc.MCMC."""
+
+    def __init__(
+        self,
+        hamiltonian_data=None,
+        mcmc_seed: int = 34467,
+        num_walkers: int = 40,
+        num_mcmc_per_measurement: int = 16,
+        Dt: float = 2.0,
+        epsilon_AS: float = 1e-1,
+        comput_log_WF_param_deriv: bool = False,
+        comput_e_L_param_deriv: bool = False,
+        comput_position_deriv: bool = False,
+        random_discretized_mesh: bool = True,
+        use_swct: bool = True,
+        engine: WalkerEngine | None = None,
+    ) -> None:
+        if comput_log_WF_param_deriv or comput_e_L_param_deriv or comput_position_deriv:
+            raise NotImplementedError("parameter / position derivatives are outside the walker engine (SURVEY.md §8f)")
+        self.hamiltonian_data = hamiltonian_data
+        self.__mcmc_seed = mcmc_seed
+        self.__num_walkers = int(num_walkers)
+        self.__nmpm = int(num_mcmc_per_measurement)
+        self.__Dt = float(Dt)
+        self.__epsilon_AS = float(epsilon_AS)
+        self.__random_discretized_mesh = bool(random_discretized_mesh)
+        rank, _ = _rank_size()
+        self.__mpi_seed = mcmc_seed * (rank + 1)
+        self.engine = engine if engine is not None else WalkerEngine(hamiltonian_data)
+        dev = self.engine.device
+        keys = rng_host.split(rng_host.PRNGKey(self.__mpi_seed), self.__num_walkers)
+        self.__keys = torch.from_numpy(keys).to(dev)
+        np.random.seed(self.__mpi_seed % (2**32))
+        gem = hamiltonian_data.wavefunction_data.geminal_data
+        cp = hamiltonian_data.coulomb_potential_data
+        r_up, r_dn, _, _ = generate_init_electron_configurations(
+            gem.num_electron_up, gem.num_electron_dn, self.__num_walkers, cp.effective_charges,
+            hamiltonian_data.structure_data.positions,
+        )  # fmt: skip
+        self.__r_up = torch.from_numpy(np.ascontiguousarray(r_up)).to(dev)
+        self.__r_dn = torch.from_numpy(np.ascontiguousarray(r_dn)).to(dev)
+        self.__init_attributes()
+
+    def __init_attributes(self):
+        self.__mcmc_counter = 0
+        self.__accepted_moves = 0
+        self.__rejected_moves = 0
+        self.__stored_e_L = []
+        self.__stored_e_L2 = []
+        self.__stored_w_L = []
+        self.__timer = dict(total=0.0, update=0.0, e_L=0.0, misc=0.0)
+
+    # ---- properties (names as in the reference, jqmc_mcmc.py:260-447) --------------------------------
+    @property
+    def num_walkers(self):
+        return self.__num_walkers
+
+    @property
+    def mcmc_counter(self):
+        return self.__mcmc_counter
+
+    @property
+    def e_L(self):
+        return np.array(self.__stored_e_L).reshape(-1, self.__num_walkers)
+
+    @property
+    def e_L2(self):
+        return np.array(self.__stored_e_L2).reshape(-1, self.__num_walkers)
+
+    @property
+    def w_L(self):
+        return np.array(self.__stored_w_L).reshape(-1, self.__num_walkers)
+
+    @property
+    def latest_r_up_carts(self):
+        return self.__r_up
+
+    @property
+    def latest_r_dn_carts(self):
+        return self.__r_dn
+
+    @property
+    def jax_PRNG_key_list(self):
+        return self.__keys
+
+    @property
+    def accepted_moves(self):
+        return self.__accepted_moves
+
+    @property
+    def rejected_moves(self):
+        return self.__rejected_moves
+
+    @property
+    def timer(self):
+        return dict(self.__timer)
+
+    # ---- sampling ------------------------------------------------------------------------------------
+    def run(self, num_mcmc_steps: int = 0, max_time=86400) -> None:
+        eng = self.engine
+        t_start = time.perf_counter()
+        G, Ginv = eng.geminal_inv_batched(self.__r_up, self.__r_dn)
+        r_up, r_dn, keys = self.__r_up, self.__r_dn, self.__keys
+        eps = self.__epsilon_AS
+        for _ in range(num_mcmc_steps):
+            acc, rej, r_up, r_dn, keys, Ginv, G = eng.update(
+                r_up, r_dn, keys, self.__nmpm, self.__Dt, eps, Ginv, G, inplace=True
+            )
+            if self.__random_discretized_mesh:
+                RTs = eng.generate_RTs(keys)
+            else:
+                RTs = None
+            e_L = eng.e_L_fast(r_up, r_dn, RTs, Ginv)
+            R_AS = eng.as_reg_fast(G, Ginv)
+            if eps > 0:
+                w_L = (R_AS / torch.clamp(R_AS, min=eps)) ** 2
+            else:  # (R/max(R,0))^2 = 1, NaN when R_AS == 0 (0/0), as in jqmc_mcmc.py:743-747
+                w_L = torch.where(R_AS > 0, torch.ones_like(R_AS), torch.full_like(R_AS, float("nan")))
+            # one device->host read per step (the reference does three: jqmc_mcmc.py:720, 739, 747)
+            pack = torch.stack([e_L, w_L, acc.to(torch.float64), rej.to(torch.float64)]).cpu().numpy()
+            self.__stored_e_L.append(pack[0])
+            self.__stored_e_L2.append(pack[0] ** 2)
+            self.__stored_w_L.append(pack[1])
+            self.__accepted_moves += int(pack[2].sum())
+            self.__rejected_moves += int(pack[3].sum())
+            self.__mcmc_counter += 1
+            if time.perf_counter() - t_start > max_time:
+                break
+        self.__r_up, self.__r_dn, self.__keys = r_up, r_dn, keys
+        self.__timer["total"] += time.perf_counter() - t_start
+
+    def get_E(self, num_mcmc_warmup_steps: int = 50, num_mcmc_bin_blocks: int = 10):
+        """(E_mean, E_std, Var_mean, Var_std): binned jackknife over walkers x blocks, reduced over ranks
+        exactly as jqmc_mcmc.py:1064-1189 (sum reductions + two-pass variance)."""
+        if self.mcmc_counter < num_mcmc_warmup_steps:
+            raise ValueError("mcmc_counter should be larger than num_mcmc_warmup_steps")
+        if self.mcmc_counter - num_mcmc_warmup_steps < num_mcmc_bin_blocks:
+            raise ValueError("(mcmc_counter - num_mcmc_warmup_steps) should be larger than num_mcmc_bin_blocks.")
+        e_L = self.e_L[num_mcmc_warmup_steps:]
+        e_L2 = self.e_L2[num_mcmc_warmup_steps:]
+        w_L = self.w_L[num_mcmc_warmup_steps:]
+        return jackknife_E(w_L, e_L, e_L2, num_mcmc_bin_blocks, self.engine.device)
+
+
+def jackknife_E(w_L, e_L, e_L2, num_bin_blocks, device=None):
+    """Binned jackknife of the weighted energy and variance over (blocks x walkers) samples and all ranks."""
+
+    def binned(x):
+        return np.ravel([np.sum(a, axis=0) for a in np.array_split(x, num_bin_blocks, axis=0)])
+
+    wb, web, we2b = binned(w_L), binned(w_L * e_L), binned(w_L * e_L2)
+    g = _allreduce_sum([wb.sum(), web.sum(), we2b.sum(), wb.size], device)
+    W, WE, WE2, M_total = g[0], g[1], g[2], g[3]
+    E_jk = (WE - web) / (W - wb)
+    E2_jk = (WE2 - we2b) / (W - wb)
+    Var_jk = E2_jk - E_jk**2
+    s = _allreduce_sum([E_jk.sum(), Var_jk.sum()], device)
+    E_mean, Var_mean = s[0] / M_total, s[1] / M_total
+    c = _allreduce_sum([np.sum((E_jk - E_mean) ** 2), np.sum((Var_jk - Var_mean) ** 2)], device)
+    E_std = np.sqrt((M_total - 1) * c[0] / M_total)
+    Var_std = np.sqrt((M_total - 1) * c[1] / M_total)
+    return float(E_mean), float(E_std), float(Var_mean), float(Var_std)

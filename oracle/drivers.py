@@ -137,3 +137,140 @@ def update_electron_positions(H, r_up, r_dn, key, nmpm, Dt, epsilon_AS, Ginv, G,
         else:
             rej += 1
     return acc, rej, r_up, r_dn, key, Ginv, G
+
+
+# --------------------------------------------------------------------------------------
+# LRDMC (GFMC_n)                      jqmc/jqmc_gfmc.py:4738-5627
+# --------------------------------------------------------------------------------------
+_SHIFTS = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], dtype=np.float64)
+
+
+def discretized_kinetic_elements(wf, r_up, r_dn, Ginv, RT, alat):
+    """Off-diagonal LRDMC kinetic elements -Psi'/(2 a^2 Psi) on the 6 N_e mesh (x+,x-,y+,y-,z+,z- per
+    electron, up block then down block), shifts rotated as ``shifts @ RT``
+    (jqmc/wavefunction.py:1739-1860).  Returns (moves, elements); moves[k] = (spin_up, idx, r_new)."""
+    shifts = alat * _SHIFTS @ np.asarray(RT, dtype=np.float64)
+    moves, elems = [], []
+    for spin_up, rs in ((True, r_up), (False, r_dn)):
+        for i, r in enumerate(rs):
+            for s in shifts:
+                r_new = r + s
+                ratio = P.det_ratio_fast(wf.geminal_data, r_up, r_dn, Ginv, spin_up, i, r_new)
+                ratio *= P.jastrow_ratio(wf.jastrow_data, r_up, r_dn, spin_up, i, r_new)
+                moves.append((spin_up, i, r_new))
+                elems.append(-1.0 / (2.0 * alat**2) * ratio)
+    return moves, np.array(elems)
+
+
+def lrdmc_elements(H, r_up, r_dn, Ginv, RT, alat, non_local_move="tmove", NN=1, Nv=6):
+    """Diagonal / off-diagonal sums of the lattice-regularised Hamiltonian with importance sampling, the
+    move list and the (unnormalised, non-positive) move weights -- the body shared by
+    ``_body_step_core`` (jqmc/jqmc_gfmc.py:4807-5031) and ``_compute_V_elements_n`` (:5360-5627)."""
+    wf, cp = H.wavefunction_data, H.coulomb_potential_data
+    r_up = np.asarray(r_up, dtype=np.float64)
+    r_dn = np.asarray(r_dn, dtype=np.float64)
+    n_up, n_dn = len(r_up), len(r_dn)
+    diag_kin = 3.0 / (2.0 * alat**2) * (n_up + n_dn)
+    ke_up, ke_dn = P.compute_kinetic_energy_all_elements(wf, r_up, r_dn, Ginv)
+    moves, el = discretized_kinetic_elements(wf, r_up, r_dn, Ginv, RT, alat)
+    kin_FN = np.minimum(el, 0.0)
+    nondiag_kin = np.sum(kin_FN)
+    diag_kin_SP = np.sum(np.maximum(el, 0.0))
+    el6 = el.reshape(-1, 6)
+    flags = np.any(el6 >= 0, axis=1)
+    nd_elem = np.sum(el6 + 1.0 / (4.0 * alat**2), axis=1)
+    ei_up, ei_dn = P.compute_bare_coulomb_potential_el_ion_element_wise(cp, r_up, r_dn)
+    di_up, di_dn = P.compute_bare_coulomb_potential_el_ion_element_wise(cp, r_up, r_dn, alat=alat)
+    e_ion = np.concatenate([ei_up, ei_dn])
+    e_ion_disc = np.concatenate([di_up, di_dn])
+    ke = np.concatenate([ke_up, ke_dn])
+    zv = e_ion + ke - nd_elem
+    ei = e_ion if cp.ecp_flag else e_ion_disc
+    opt = np.where(flags, np.maximum(zv, ei), zv)
+    disc_bare = P.compute_bare_coulomb_potential_el_el(r_up, r_dn) + P.compute_bare_coulomb_potential_ion_ion(cp) + np.sum(opt)
+    if cp.ecp_flag:
+        local = P.compute_ecp_local_parts(cp, r_up, r_dn)
+        det_only = non_local_move == "dltmove"
+        mu, md, Vnl, _ = P.compute_ecp_non_local_parts_nearest_neighbors(cp, wf, r_up, r_dn, RT, NN, Nv, det_only=det_only, Ginv=Ginv)
+        FN = np.minimum(Vnl, 0.0)
+        SP = np.sum(np.maximum(Vnl, 0.0))
+        npt = len(Vnl)
+        per = NN * Nv
+        ecp_moves = []
+        for k in range(npt):
+            e = k // per
+            spin_up = e < n_up
+            idx = e if spin_up else e - n_up
+            r_new = (mu[k][idx] if spin_up else md[k][idx]).copy()
+            ecp_moves.append((spin_up, idx, r_new))
+        if det_only:
+            jr = np.array([P.jastrow_ratio(wf.jastrow_data, r_up, r_dn, su, i, rn) for (su, i, rn) in ecp_moves])
+            FN = FN * jr
+        nondiag = nondiag_kin + np.sum(FN)
+        diag = diag_kin + disc_bare + local + diag_kin_SP + SP
+        p = np.concatenate([kin_FN, FN])
+        moves = moves + ecp_moves
+    else:
+        nondiag = nondiag_kin
+        diag = diag_kin + disc_bare + diag_kin_SP
+        p = kin_FN
+    return diag, nondiag, p, moves
+
+
+def lrdmc_V_elements(H, r_up, r_dn, RT, non_local_move="tmove", alat=0.3):
+    """(V_diag, V_nondiag) at a configuration with a fresh SVD inverse (jqmc/jqmc_gfmc.py:5360-5627)."""
+    _, Ginv = geminal_inv(H.wavefunction_data.geminal_data, r_up, r_dn)
+    diag, nondiag, _, _ = lrdmc_elements(H, r_up, r_dn, Ginv, RT, alat, non_local_move)
+    return diag, nondiag
+
+
+def lrdmc_projection(H, w, r_up, r_dn, Ginv, key, E_scf, nmpm, random_discretized_mesh, non_local_move, alat, trace=None):
+    """``nmpm`` GFMC_n projections of one walker (jqmc/jqmc_gfmc.py:4738-5358).
+    Returns (w, r_up, r_dn, Ginv, key, RT, V_diag, V_nondiag)."""
+    r_up = np.array(r_up, dtype=np.float64)
+    r_dn = np.array(r_dn, dtype=np.float64)
+    Ginv = np.array(Ginv, dtype=np.float64)
+    gem = H.wavefunction_data.geminal_data
+    rot_keys, move_keys = [], []
+    for _ in range(nmpm):  # _split_step_keys (:5275-5283)
+        key, rk = R.split(key)
+        key, mk = R.split(key)
+        rot_keys.append(rk)
+        move_keys.append(mk)
+    RT = np.eye(3)
+    diag = nondiag = 0.0
+    for i in range(nmpm):
+        if random_discretized_mesh:
+            a, b, g = R.uniform(rot_keys[i], 3, -2 * np.pi, 2 * np.pi)
+        else:
+            a = b = g = 0.0
+        RT = rotation_from_angles(a, b, g).T
+        diag, nondiag, p, moves = lrdmc_elements(H, r_up, r_dn, Ginv, RT, alat, non_local_move)
+        b_x = 1.0 / (diag - E_scf) * (-nondiag)
+        w = w * b_x
+        cdf = np.cumsum(p / p.sum())
+        u = R.uniform(move_keys[i])
+        k = min(int(np.searchsorted(cdf, u, side="left")), len(cdf) - 1)
+        spin_up, idx, r_new = moves[k]
+        # Sherman-Morrison with row/column differences evaluated from scratch (:5083-5141)
+        p_up, p_dn = r_up.copy(), r_dn.copy()
+        (p_up if spin_up else p_dn)[idx] = r_new
+        G_old = P.compute_geminal_all_elements(gem, r_up, r_dn)
+        G_new = P.compute_geminal_all_elements(gem, p_up, p_dn)
+        n = len(r_up)
+        if spin_up:
+            v = (G_new[idx, :] - G_old[idx, :])[:, None]
+            u_ = np.zeros((n, 1))
+            u_[idx, 0] = 1.0
+        else:
+            u_ = (G_new[:, idx] - G_old[:, idx])[:, None]
+            v = np.zeros((n, 1))
+            v[idx, 0] = 1.0
+        Ainv_u = Ginv @ u_
+        vT_Ainv = v.T @ Ginv
+        det_ratio = 1.0 + (v.T @ Ainv_u)[0, 0]
+        Ginv = Ginv - (Ainv_u @ vT_Ainv) / det_ratio
+        if trace is not None:
+            trace.append(dict(k=k, u=u, b_x=b_x, diag=diag, nondiag=nondiag, spin_up=spin_up, idx=idx))
+        r_up, r_dn = p_up, p_dn
+    return w, r_up, r_dn, Ginv, key, RT, diag, nondiag

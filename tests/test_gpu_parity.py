@@ -1,0 +1,301 @@
+"""GPU parity tests: every kernel family of SURVEY.md §8(a) through the C ABI against the CPU oracle on
+the same seeded inputs.  Tolerances: fp64, 1e-10 relative (north_star) unless a looser bound is argued
+in the test; integer results (accept/reject counts, keys) bit-exact."""
+
+import copy
+
+import numpy as np
+import pytest
+
+from jqmc_b200.data import Jastrow_data, Jastrow_one_body_data, Jastrow_two_body_data
+from oracle import drivers as OD
+from oracle import jaxrng as R
+from oracle import physics as P
+from tests.conftest import load_system, random_walkers
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+SYSTEMS = ["water_ccecp_ccpvqz", "N2_ecp_ccpvtz_cart", "H2_ae_ccpvdz_cart", "Li_ae_ccpvdz_cart", "H2_ecp_ccpvtz"]
+
+
+def _engine(H, **kw):
+    from jqmc_b200.engine import WalkerEngine
+
+    return WalkerEngine(H, **kw)
+
+
+def _with_jastrow(H, kind):
+    H = copy.deepcopy(H)
+    cp = H.coulomb_potential_data
+    core = tuple(cp.z_cores) if cp.ecp_flag else tuple(0 for _ in H.structure_data.atomic_numbers)
+    if kind == "j2pade":
+        jd = Jastrow_data(jastrow_two_body_data=Jastrow_two_body_data(jastrow_2b_param=0.8, jastrow_2b_type="pade"))
+    elif kind == "j1exp_j2exp":
+        jd = Jastrow_data(
+            jastrow_one_body_data=Jastrow_one_body_data(jastrow_1b_param=0.9, jastrow_1b_type="exp", structure_data=H.structure_data, core_electrons=core),
+            jastrow_two_body_data=Jastrow_two_body_data(jastrow_2b_param=0.6, jastrow_2b_type="exp"),
+        )
+    elif kind == "j1pade_j2pade":
+        jd = Jastrow_data(
+            jastrow_one_body_data=Jastrow_one_body_data(jastrow_1b_param=1.3, jastrow_1b_type="pade", structure_data=H.structure_data, core_electrons=core),
+            jastrow_two_body_data=Jastrow_two_body_data(jastrow_2b_param=1.1, jastrow_2b_type="pade"),
+        )
+    else:
+        jd = Jastrow_data()
+    H.wavefunction_data.jastrow_data = jd
+    return H
+
+
+@pytest.mark.parametrize("name", SYSTEMS)
+def test_ao_and_mo_value_grad_lap(name):
+    """kernels 1-2: AO / MO value, gradient, Laplacian (a2-a4) vs the closed-form oracle."""
+    H = load_system(name)
+    eng = _engine(H)
+    mos = H.wavefunction_data.geminal_data.orb_data_up_spin
+    rng = np.random.default_rng(1)
+    Rn = np.asarray(H.structure_data.positions)
+    r = Rn[rng.integers(0, len(Rn), 40)] + rng.normal(scale=0.9, size=(40, 3))
+    r[0] = Rn[0]  # a point exactly on a nucleus
+    ref_ao = np.stack(P.compute_AOs_value_grad_lap(mos.aos_data, r))
+    got_ao = eng.eval_orbitals("up", "ao", r).cpu().numpy()
+    scale = np.abs(ref_ao).max(axis=(1, 2), keepdims=True)
+    np.testing.assert_allclose(got_ao, ref_ao, rtol=RTOL, atol=1e-12 * scale.max())
+    ref_mo = np.stack(P.compute_orb_value_grad_lap(mos, r))
+    got_mo = eng.eval_orbitals("up", "orb", r).cpu().numpy()
+    np.testing.assert_allclose(got_mo, ref_mo, rtol=RTOL, atol=1e-12 * np.abs(ref_mo).max())
+
+
+@pytest.mark.parametrize("name", SYSTEMS)
+def test_geminal_inverse_and_ln_wavefunction(name):
+    """kernel 3 (a5-a7, a21): G, Ginv, ln|Psi|."""
+    H = _with_jastrow(load_system(name), "j1exp_j2exp")
+    eng = _engine(H)
+    nw = 6
+    r_up, r_dn = random_walkers(H, nw, 21)
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    ln, sg = eng.ln_wavefunction(r_up, r_dn)
+    G, Ginv, ln, sg = (x.cpu().numpy() for x in (G, Ginv, ln, sg))
+    gem = H.wavefunction_data.geminal_data
+    for w in range(nw):
+        Gr = P.compute_geminal_all_elements(gem, r_up[w], r_dn[w])
+        np.testing.assert_allclose(G[w], Gr, rtol=RTOL, atol=1e-13 * np.abs(Gr).max())
+        Gir = P.geminal_inv_svd(Gr)
+        cond = np.linalg.cond(Gr)
+        np.testing.assert_allclose(Ginv[w], Gir, rtol=0, atol=1e-14 * cond * np.abs(Gir).max())
+        ref = P.evaluate_ln_wavefunction(H.wavefunction_data, r_up[w], r_dn[w])
+        np.testing.assert_allclose(ln[w], ref, rtol=RTOL, atol=1e-11)
+        assert sg[w] == np.sign(np.linalg.det(Gr))
+
+
+@pytest.mark.parametrize("name,jas", [("water_ccecp_ccpvqz", "none"), ("water_ccecp_ccpvqz", "j2pade"), ("water_ccecp_ccpvqz", "j1exp_j2exp"),
+                                      ("N2_ecp_ccpvtz_cart", "j1pade_j2pade"), ("H2_ae_ccpvdz_cart", "j1exp_j2exp"),
+                                      ("Li_ae_ccpvdz_cart", "j2pade"), ("H2_ecp_ccpvtz", "j1pade_j2pade")])  # fmt: skip
+def test_local_energy_and_parts(name, jas):
+    """kernels 4-5 (a10, a13-a16, a19, a23-a27): e_L, per-electron kinetic energies, potential pieces."""
+    H = _with_jastrow(load_system(name), jas)
+    eng = _engine(H)
+    nw = 5
+    r_up, r_dn = random_walkers(H, nw, 33)
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    keys = np.array([[3, 100 + i] for i in range(nw)], dtype=np.uint32)
+    RT = eng.generate_RTs(keys)
+    e_L, T, V = eng.e_L_fast(r_up, r_dn, RT, Ginv, return_parts=True)
+    e_L, T, V, RT, Ginv = (x.cpu().numpy() for x in (e_L, T, V, RT, Ginv))
+    wf, cp = H.wavefunction_data, H.coulomb_potential_data
+    for w in range(nw):
+        RTw = OD.generate_rotation_matrix((3, 100 + w))
+        np.testing.assert_allclose(RT[w], RTw, rtol=0, atol=1e-14)
+        Tu, Td = P.compute_kinetic_energy_all_elements(wf, r_up[w], r_dn[w], Ginv[w])
+        Tref = np.concatenate([Tu, Td])
+        np.testing.assert_allclose(T[w], Tref, rtol=RTOL, atol=1e-10 * np.abs(Tref).max())
+        vb = P.compute_bare_coulomb_potential(cp, r_up[w], r_dn[w])
+        np.testing.assert_allclose(V[w, 0], vb, rtol=RTOL)
+        if cp.ecp_flag:
+            np.testing.assert_allclose(V[w, 1], P.compute_ecp_local_parts(cp, r_up[w], r_dn[w]), rtol=RTOL, atol=1e-12)
+            vnl = P.compute_ecp_non_local_parts_nearest_neighbors(cp, wf, r_up[w], r_dn[w], RTw, NN=1, Nv=6, Ginv=Ginv[w])[3]
+            np.testing.assert_allclose(V[w, 2], vnl, rtol=1e-9, atol=1e-11)
+        ref = P.compute_local_energy(H, r_up[w], r_dn[w], RTw, Ginv=Ginv[w])
+        np.testing.assert_allclose(e_L[w], ref, rtol=RTOL, atol=1e-10 * np.abs(Tref).max())
+
+
+def test_local_energy_turborvb_golden(water):
+    """The GPU local energy reproduces the TurboRVB known answers of the reference's own test
+    (tests/test_comparison_with_turborvb_ECP.py:105-129, 231-274) directly."""
+    from tests.test_oracle_golden import DN_A, DN_B, NEW_UP2, UP_A, UP_B
+
+    for H, up, dn, kin, vpot in (
+        (water, UP_A, DN_A, 14.6961809426982, -17.0152290468758 + 0.328893830058865),
+        (_with_jastrow(water, "none"), UP_A, DN_A, 14.6961809426982, -17.0152290468758 + 0.328893830058865),
+    ):
+        eng = _engine(H)
+        new_up = up.copy()
+        new_up[2] = NEW_UP2
+        G, Ginv = eng.geminal_inv_batched(new_up[None], dn[None])
+        e_L, T, V = eng.e_L_fast(new_up[None], dn[None], np.eye(3)[None], Ginv, return_parts=True)
+        np.testing.assert_almost_equal(T.sum().item(), kin, decimal=6)
+        np.testing.assert_almost_equal(V[0, :3].sum().item(), vpot, decimal=5)
+    H = copy.deepcopy(water)
+    H.wavefunction_data.jastrow_data = Jastrow_data(jastrow_two_body_data=Jastrow_two_body_data(jastrow_2b_param=0.676718854150191))
+    eng = _engine(H)
+    new_up = UP_B.copy()
+    new_up[2] = NEW_UP2
+    G, Ginv = eng.geminal_inv_batched(new_up[None], DN_B[None])
+    e_L, T, V = eng.e_L_fast(new_up[None], DN_B[None], np.eye(3)[None], Ginv, return_parts=True)
+    np.testing.assert_almost_equal(T.sum().item(), 11.1237599317225, decimal=6)
+    np.testing.assert_almost_equal(V[0, :3].sum().item(), -27.03387193107 + 0.243517439611676, decimal=5)
+    # WF ratio^2 of the golden move through the move-ratio entry
+    G0, Ginv0 = eng.geminal_inv_batched(UP_B[None], DN_B[None])
+    dr, jr = eng.move_ratios(UP_B[None], DN_B[None], Ginv0, [2], np.array(NEW_UP2)[None, None, :])
+    np.testing.assert_almost_equal(((dr * jr) ** 2).item(), 0.881124604511419, decimal=6)
+
+
+@pytest.mark.parametrize("name,jas", [("water_ccecp_ccpvqz", "j1exp_j2exp"), ("Li_ae_ccpvdz_cart", "j1pade_j2pade"), ("N2_ecp_ccpvtz_cart", "j2pade")])
+def test_move_ratios(name, jas):
+    """a9 / a17: single-electron determinant and Jastrow ratios vs brute-force re-evaluation."""
+    H = _with_jastrow(load_system(name), jas)
+    eng = _engine(H)
+    nw = 4
+    r_up, r_dn = random_walkers(H, nw, 8)
+    n_up, n_dn = r_up.shape[1], r_dn.shape[1]
+    elec = list(range(n_up + n_dn)) * 2
+    rng = np.random.default_rng(5)
+    r_all = np.concatenate([r_up, r_dn], axis=1)
+    r_new = r_all[:, elec, :] + rng.normal(scale=0.4, size=(nw, len(elec), 3))
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    dr, jr = eng.move_ratios(r_up, r_dn, Ginv, elec, r_new)
+    dr, jr = dr.cpu().numpy(), jr.cpu().numpy()
+    wf = H.wavefunction_data
+    for w in range(nw):
+        for k, e in enumerate(elec):
+            up, idx = (True, e) if e < n_up else (False, e - n_up)
+            tot = P.wf_ratio_brute_force(wf, r_up[w], r_dn[w], up, idx, r_new[w, k])
+            det = P.wf_ratio_brute_force(wf, r_up[w], r_dn[w], up, idx, r_new[w, k], det_only=True)
+            np.testing.assert_allclose(dr[w, k], det, rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(dr[w, k] * jr[w, k], tot, rtol=1e-9, atol=1e-12)
+
+
+def test_as_factor(water):
+    eng = _engine(water)
+    r_up, r_dn = random_walkers(water, 7, 12)
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    got = eng.as_reg_fast(G, Ginv).cpu().numpy()
+    for w in range(7):
+        ref = P.compute_AS_regularization_factor(G[w].cpu().numpy(), Ginv[w].cpu().numpy())
+        np.testing.assert_allclose(got[w], ref, rtol=1e-12)
+
+
+@pytest.mark.parametrize("name,jas,eps,nmpm", [("water_ccecp_ccpvqz", "j2pade", 0.0, 24), ("water_ccecp_ccpvqz", "j1exp_j2exp", 0.05, 16),
+                                               ("Li_ae_ccpvdz_cart", "j2pade", 0.0, 20), ("N2_ecp_ccpvtz_cart", "j1pade_j2pade", 0.1, 10),
+                                               ("H2_ae_ccpvdz_cart", "none", 0.0, 30)])  # fmt: skip
+def test_mcmc_update_trajectory(name, jas, eps, nmpm):
+    """kernel 6 (a28): same keys -> same proposals, bit-exact accept/reject sequence, keys bit-exact,
+    positions/G/Ginv to round-off."""
+    H = _with_jastrow(load_system(name), jas)
+    eng = _engine(H)
+    nw = 3
+    r_up, r_dn = random_walkers(H, nw, 77, scale=0.6)
+    keys = np.array([[0, 4242 + 13 * i] for i in range(nw)], dtype=np.uint32)
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    acc, rej, ru, rd, k2, Gi2, G2 = eng.update(r_up, r_dn, keys, nmpm, 2.0, eps, Ginv, G)
+    acc, rej, ru, rd, k2, Gi2, G2 = (x.cpu().numpy() for x in (acc, rej, ru, rd, k2, Gi2, G2))
+    G, Ginv = G.cpu().numpy(), Ginv.cpu().numpy()
+    for w in range(nw):
+        a, r_, ru_o, rd_o, key_o, Gi_o, G_o = OD.update_electron_positions(
+            H, r_up[w], r_dn[w], (int(keys[w, 0]), int(keys[w, 1])), nmpm, 2.0, eps, Ginv[w], G[w]
+        )
+        assert (a, r_) == (int(acc[w]), int(rej[w]))
+        assert a + r_ == nmpm
+        assert tuple(int(x) for x in k2[w]) == tuple(key_o)
+        np.testing.assert_allclose(ru[w], ru_o, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(rd[w], rd_o, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(G2[w], G_o, rtol=1e-9, atol=1e-12 * np.abs(G_o).max())
+        np.testing.assert_allclose(Gi2[w], Gi_o, rtol=1e-8, atol=1e-10 * np.abs(Gi_o).max())
+        # the running inverse is still the inverse of the geminal at the final positions
+        Gfresh = P.compute_geminal_all_elements(H.wavefunction_data.geminal_data, ru[w], rd[w])
+        np.testing.assert_allclose(G2[w], Gfresh, rtol=1e-9, atol=1e-12 * np.abs(Gfresh).max())
+        np.testing.assert_allclose(Gi2[w] @ Gfresh, np.eye(len(Gfresh)), rtol=0, atol=1e-8)
+
+
+def test_rng_stream_bit_exact(water):
+    """Device RNG vs the NumPy jax.random restatement: key chain after nmpm proposals and RT angles."""
+    eng = _engine(water)
+    nw = 64
+    keys = np.stack([np.arange(nw, dtype=np.uint32) * 7919 + 1, np.arange(nw, dtype=np.uint32) ** 2 + 5], axis=1).astype(np.uint32)
+    r_up, r_dn = random_walkers(water, nw, 1)
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    out = eng.update(r_up, r_dn, keys, 5, 2.0, 0.0, Ginv, G)
+    k2 = out[4].cpu().numpy()
+    RT = eng.generate_RTs(keys).cpu().numpy()
+    for w in range(nw):
+        k = (int(keys[w, 0]), int(keys[w, 1]))
+        kk = k
+        for _ in range(5 * 6):
+            kk, _sub = R.split(kk)
+        assert tuple(int(x) for x in k2[w]) == kk
+        np.testing.assert_allclose(RT[w], OD.generate_rotation_matrix(k), rtol=0, atol=2e-15)
+        np.testing.assert_allclose(RT[w] @ RT[w].T, np.eye(3), atol=1e-14)
+
+
+def test_full_size_properties(water):
+    """BASELINE-size run (4096 walkers): size-independent properties -- counts add up, the running inverse
+    stays the inverse, e_L is finite, walkers sharing a key and a configuration stay identical."""
+    import torch
+
+    from jqmc_b200 import rng_host
+    from jqmc_b200.mcmc import generate_init_electron_configurations
+
+    H = _with_jastrow(water, "j2pade")
+    eng = _engine(H)
+    nw, nmpm = 4096, 40
+    np.random.seed(1)
+    r_up, r_dn, _, _ = generate_init_electron_configurations(4, 4, nw, H.coulomb_potential_data.effective_charges, H.structure_data.positions)
+    keys = rng_host.split(rng_host.PRNGKey(99), nw)
+    # duplicate walker 0 into the last slot (same key, same configuration) -> identical trajectory
+    r_up[-1], r_dn[-1], keys[-1] = r_up[0], r_dn[0], keys[0]
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    acc_t = torch.zeros(nw, dtype=torch.int64, device="cuda")
+    state = (r_up, r_dn, keys, Ginv, G)
+    for _ in range(3):
+        acc, rej, ru, rd, k2, Gi2, G2 = eng.update(state[0], state[1], state[2], nmpm, 2.0, 0.0, state[3], state[4])
+        assert torch.all(acc + rej == nmpm)
+        acc_t += acc
+        state = (ru, rd, k2, Gi2, G2)
+    ratio = acc_t.double().mean().item() / (3 * nmpm)
+    assert 0.2 < ratio < 0.95, ratio
+    Gf, Gif = eng.geminal_inv_batched(state[0], state[1])
+    err = (torch.bmm(state[3], Gf) - torch.eye(4, device="cuda", dtype=torch.float64)).abs().amax(dim=(1, 2))
+    assert err.median().item() < 1e-9 and err.max().item() < 1e-4
+    np.testing.assert_allclose(state[4].cpu().numpy(), Gf.cpu().numpy(), rtol=1e-7, atol=1e-12)
+    RT = eng.generate_RTs(state[2])
+    e_L = eng.e_L_fast(state[0], state[1], RT, state[3])
+    assert torch.isfinite(e_L).all()
+    assert -30.0 < e_L.mean().item() < -10.0
+    assert torch.equal(state[0][0], state[0][-1]) and torch.equal(state[2][0], state[2][-1]) and e_L[0] == e_L[-1]
+
+
+def test_shape_errors(water):
+    eng = _engine(water)
+    r_up, r_dn = random_walkers(water, 2, 0)
+    with pytest.raises(ValueError):
+        eng.geminal_inv_batched(r_up[:, :3], r_dn)
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    with pytest.raises(ValueError):
+        eng.e_L_fast(r_up, r_dn, np.eye(3)[None], Ginv)  # RT for 1 walker, 2 walkers given
+    with pytest.raises(ValueError):
+        eng.update(r_up, r_dn, np.zeros((3, 2), dtype=np.uint32), 4, 2.0, 0.0, Ginv, G)
+
+
+def test_mcmc_driver_runs(water):
+    from jqmc_b200.mcmc import MCMC
+
+    H = _with_jastrow(water, "j2pade")
+    m = MCMC(H, mcmc_seed=34456, num_walkers=64, num_mcmc_per_measurement=40, Dt=2.0, epsilon_AS=0.0)
+    m.run(num_mcmc_steps=30)
+    assert m.e_L.shape == (30, 64) and m.w_L.shape == (30, 64)
+    E, dE, Var, dVar = m.get_E(num_mcmc_warmup_steps=10, num_mcmc_bin_blocks=5)
+    assert -18.5 < E < -15.5 and dE > 0
+    # same seed -> same stream
+    m2 = MCMC(H, mcmc_seed=34456, num_walkers=64, num_mcmc_per_measurement=40, Dt=2.0, epsilon_AS=0.0)
+    m2.run(num_mcmc_steps=5)
+    np.testing.assert_array_equal(m2.e_L, m.e_L[:5])

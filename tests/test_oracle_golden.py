@@ -1,0 +1,162 @@
+"""Pin the CPU oracle against the reference's own known-answer numbers (TurboRVB, hard-coded in
+jQMC's tests/test_comparison_with_turborvb_ECP.py:75-274) and against itself (fast-update vs
+from-scratch, analytic vs finite differences) -- the reference's test patterns B, C and E."""
+
+import numpy as np
+import pytest
+
+from jqmc_b200.data import Geminal_data, Jastrow_data, Jastrow_one_body_data, Jastrow_two_body_data
+from oracle import physics as P
+from tests.conftest import load_system, random_walkers
+
+UP_A = np.array(
+    [
+        [-1.1345038587576, -0.698914730480577, -0.006290951981744008],
+        [-2.07761893946839, 1.30902541938751, -0.05220902114745041],
+        [0.276215481293413, 0.422863618938476, 0.27986648725301],
+        [-1.60902246286275, 0.499927465264998, 0.70010581636993],
+    ]
+)
+DN_A = np.array(
+    [
+        [-1.48583455555933, -1.01189391902775, 1.83998639430367],
+        [0.635659512640246, 0.398999201990364, -0.745191606127732],
+        [-2.00590358216444, 1.90796788491204, -0.195294104680795],
+        [-1.12726250654165, -0.739542218156325, -0.04817447678670805],
+    ]
+)
+UP_B = np.array(
+    [
+        [-1.1345038587576, -0.698914730480577, -0.006290951981744008],
+        [-2.30366220171161, 1.47326376760292, 0.126403765463162],
+        [0.276215481293413, 0.422863618938476, 0.27986648725301],
+        [-2.54518559687882, 0.822753144911055, 0.70010581636993],
+    ]
+)
+DN_B = np.array(
+    [
+        [-1.42343008909407, -1.13669461924113, 0.525171318204107],
+        [1.90701925586575, 0.398999201990364, -0.745191606127732],
+        [-2.00590358216444, 1.90796788491204, -0.195294104680795],
+        [-1.12726250654165, -0.678049640381367, -0.656537799033216],
+    ]
+)
+NEW_UP2 = [0.276215481293413, -0.270740090536313, 0.27986648725301]
+
+
+def _check_turborvb(H, old_up, old_dn, ratio_ref, kin_ref, vpot_ref, vpotoff_ref):
+    wf = H.wavefunction_data
+    new_up = old_up.copy()
+    new_up[2] = NEW_UP2
+    ratio = (P.evaluate_wavefunction(wf, new_up, old_dn) / P.evaluate_wavefunction(wf, old_up, old_dn)) ** 2
+    np.testing.assert_almost_equal(ratio, ratio_ref, decimal=6)
+    np.testing.assert_almost_equal(P.compute_kinetic_energy(wf, new_up, old_dn), kin_ref, decimal=6)
+    V = P.compute_coulomb_potential(H.coulomb_potential_data, wf, new_up, old_dn, RT=np.eye(3), NN=1, Nv=6)
+    np.testing.assert_almost_equal(V, vpot_ref + vpotoff_ref, decimal=5)
+    # fast (running inverse) path == brute force path
+    Ginv = np.linalg.inv(P.compute_geminal_all_elements(wf.geminal_data, new_up, old_dn))
+    Vf = P.compute_coulomb_potential(H.coulomb_potential_data, wf, new_up, old_dn, RT=np.eye(3), Ginv=Ginv)
+    np.testing.assert_allclose(Vf, V, rtol=1e-11)
+    np.testing.assert_allclose(
+        P.compute_kinetic_energy(wf, new_up, old_dn, Ginv), P.compute_kinetic_energy(wf, new_up, old_dn), rtol=1e-10
+    )
+
+
+def test_turborvb_wo_jastrow(water):
+    # tests/test_comparison_with_turborvb_ECP.py:105-129
+    _check_turborvb(water, UP_A, DN_A, 0.919592366177397, 14.6961809426982, -17.0152290468758, 0.328893830058865)
+
+
+def test_turborvb_w_2b_jastrow(water):
+    # tests/test_comparison_with_turborvb_ECP.py:231-274
+    import copy
+
+    H = copy.deepcopy(water)
+    H.wavefunction_data.jastrow_data = Jastrow_data(jastrow_two_body_data=Jastrow_two_body_data(jastrow_2b_param=0.676718854150191))
+    _check_turborvb(H, UP_B, DN_B, 0.881124604511419, 11.1237599317225, -27.03387193107, 0.243517439611676)
+
+
+@pytest.mark.parametrize("name", ["water_ccecp_ccpvqz", "N2_ecp_ccpvtz_cart", "H2_ae_ccpvdz_cart"])
+def test_ao_grad_lap_vs_finite_differences(name):
+    # pattern B (jQMC tests/test_AOs.py:463-1190)
+    H = load_system(name)
+    aos = H.wavefunction_data.geminal_data.orb_data_up_spin.aos_data
+    rng = np.random.default_rng(3)
+    r = np.asarray(H.structure_data.positions)[0] + rng.normal(scale=0.6, size=(3, 3))
+    v, gx, gy, gz, lap = P.compute_AOs_value_grad_lap(aos, r)
+    np.testing.assert_allclose(v, P.compute_AOs(aos, r), rtol=1e-13, atol=1e-15)
+    h = 1e-4
+    fd_lap = np.zeros_like(v)
+    for c, g in enumerate((gx, gy, gz)):
+        e = np.zeros(3)
+        e[c] = h
+        fp, fm = P.compute_AOs(aos, r + e), P.compute_AOs(aos, r - e)
+        np.testing.assert_allclose(g, (fp - fm) / (2 * h), rtol=2e-6, atol=2e-7)
+        fd_lap += (fp - 2 * v + fm) / h**2
+    np.testing.assert_allclose(lap, fd_lap, rtol=2e-5, atol=2e-5)
+
+
+def test_jastrow_grad_lap_vs_finite_differences(water):
+    jd = Jastrow_data(
+        jastrow_one_body_data=Jastrow_one_body_data(
+            jastrow_1b_param=0.9, structure_data=water.structure_data, core_electrons=tuple(water.coulomb_potential_data.z_cores)
+        ),
+        jastrow_two_body_data=Jastrow_two_body_data(jastrow_2b_param=0.7, jastrow_2b_type="exp"),
+    )
+    r_up, r_dn = (x[0] for x in random_walkers(water, 1, 5))
+    gu, gd, lu, ld = P.compute_grads_and_laplacian_Jastrow_part(jd, r_up, r_dn)
+    h = 1e-4
+    J0 = P.compute_Jastrow_part(jd, r_up, r_dn)
+    for i in range(len(r_up)):
+        lap = 0.0
+        for c in range(3):
+            p, m = r_up.copy(), r_up.copy()
+            p[i, c] += h
+            m[i, c] -= h
+            Jp, Jm = P.compute_Jastrow_part(jd, p, r_dn), P.compute_Jastrow_part(jd, m, r_dn)
+            np.testing.assert_allclose(gu[i, c], (Jp - Jm) / (2 * h), rtol=1e-6, atol=1e-8)
+            lap += (Jp - 2 * J0 + Jm) / h**2
+        np.testing.assert_allclose(lu[i], lap, rtol=1e-5, atol=1e-5)
+
+
+def test_geminal_mo_equals_ao_representation(water):
+    # JSD in the MO basis and its AO-basis (JAGP-form) conversion give the same G (determinant.py:686-722)
+    gem = water.wavefunction_data.geminal_data
+    gem_ao = Geminal_data.convert_from_MOs_to_AOs(gem)
+    gem_ao.sanity_check()
+    r_up, r_dn = (x[0] for x in random_walkers(water, 1, 11))
+    np.testing.assert_allclose(
+        P.compute_geminal_all_elements(gem_ao, r_up, r_dn), P.compute_geminal_all_elements(gem, r_up, r_dn), rtol=1e-10, atol=1e-14
+    )
+
+
+def test_ln_det_grads_fast_vs_scratch_open_shell():
+    H = load_system("Li_ae_ccpvdz_cart")  # 2 up, 1 dn: exercises the unpaired block
+    gem = H.wavefunction_data.geminal_data
+    assert gem.num_electron_up == 2 and gem.num_electron_dn == 1
+    r_up, r_dn = (x[0] for x in random_walkers(H, 1, 2))
+    G = P.compute_geminal_all_elements(gem, r_up, r_dn)
+    a = P.compute_grads_and_laplacian_ln_Det(gem, r_up, r_dn, np.linalg.inv(G))
+    b = P.compute_grads_and_laplacian_ln_Det(gem, r_up, r_dn)
+    for x, y in zip(a, b):
+        np.testing.assert_allclose(x, y, rtol=1e-9, atol=1e-12)
+    # gradient of ln|det| by finite differences
+    h = 1e-5
+    for i in range(2):
+        for c in range(3):
+            p, m = r_up.copy(), r_up.copy()
+            p[i, c] += h
+            m[i, c] -= h
+            fd = (P.compute_ln_det(gem, p, r_dn) - P.compute_ln_det(gem, m, r_dn)) / (2 * h)
+            np.testing.assert_allclose(a[0][i, c], fd, rtol=1e-6, atol=1e-7)
+
+
+def test_ecp_mesh_layout(water):
+    r_up, r_dn = (x[0] for x in random_walkers(water, 1, 4))
+    mu, md, v, s = P.compute_ecp_non_local_parts_nearest_neighbors(
+        water.coulomb_potential_data, water.wavefunction_data, r_up, r_dn, np.eye(3), NN=1, Nv=6
+    )
+    assert mu.shape == (48, 4, 3) and md.shape == (48, 4, 3) and v.shape == (48,)
+    np.testing.assert_allclose(s, v.sum())
+    # first 24 configurations move up electrons only
+    assert np.all(md[:24] == r_dn) and np.all(mu[24:] == r_up)
