@@ -142,7 +142,11 @@ int qe_lrdmc_project(qe_engine* h, int nw, double* w, double* r_up, double* r_dn
 /* GFMC_n._compute_V_elements_n (jqmc/jqmc_gfmc.py:5360-5627, 5660). */
 int qe_lrdmc_velements(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT,
                        const double* Ginv, int non_local_move, double alat, double* V_diag, double* V_nondiag,
-                       void* stream);
+                       void* stream);  /* Ginv: inverse at (r_up, r_dn), e.g. from qe_geminal_init as the reference does */
+
+/* qe_local_energy runs as ONE fused kernel (shared-memory resident walker state) when the system fits and
+ * `on` != 0 (default); otherwise as a chain of staged kernels through a global workspace.  Same results. */
+int qe_set_fused(qe_engine* h, int on);
 
 /* Microbenchmark used by bench.py for the fp64 roofline denominator: runs `iters` dependent-free
  * DFMA per thread on a full grid and returns the achieved TFLOP/s (synchronous). */

@@ -1,0 +1,284 @@
+// Shared declarations of the walker engine translation units (qe_engine.cu, qe_mcmc.cu, qe_walker.cu).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/jqmc_b200.h"
+#include "qe_device.cuh"
+
+using namespace qe;
+// =================================================================================================
+// error handling
+// =================================================================================================
+int qe_fail(int code, const std::string& msg);  // defined in qe_engine.cu (thread-local last error)
+#define fail qe_fail
+#define CUDA_TRY(x)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (x);                                                                        \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(QE_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_));                \
+  } while (0)
+
+// =================================================================================================
+// engine object
+// =================================================================================================
+struct DevPool {
+  std::vector<void*> ptrs;
+  template <class T>
+  cudaError_t upload(const std::vector<T>& v, const T** out) {
+    void* p = nullptr;
+    size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(p);
+    if (!v.empty()) e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    *out = (const T*)p;
+    return e;
+  }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+  }
+};
+
+struct HostBasis {
+  BasisDev dev{};
+  std::vector<int> chunk_begin;  // balanced chunks of groups, chunk_begin[n_chunk+1]
+  std::vector<double> grp_cost;
+  bool present = false;
+};
+
+struct SysDev {
+  int n_atom, n_up, n_dn, n_e;
+  const double* Rn;     // [n_atom*3]
+  const double* Zeff;   // [n_atom]
+  // geminal lambda in orbital basis: lam_p [nmo_pad][nmo_pad] (zero padded), lam_u [nmo_pad][n_up-n_dn]
+  const double* lam_p;
+  const double* lam_u;
+  int n_unp;
+  // Jastrow
+  int j1_type;
+  double j1_a;
+  const double* j1_A;   // (2 Z)^{3/4}
+  const double* j1_c;   // (2 Z)^{1/4}
+  int j2_type;
+  double j2_a;
+  // ECP
+  int ecp_flag, n_ecp, Nv, NN, ecp_lmax;  // ecp_lmax = global max_ang_mom_plus_1
+  const int* ecp_nuc;
+  const int* ecp_l;
+  const double* ecp_z;
+  const double* ecp_c;
+  const double* ecp_p;
+  const int* ecp_lmax_atom;  // [n_atom] max_ang_mom_plus_1
+  const int* ecp_off;        // [n_atom+1] terms sorted by atom
+  const double* quad_w;      // [Nv]
+  const double* quad_g;      // [Nv*3]
+  double v_ion_ion;
+};
+
+struct qe_engine {
+  DevPool pool;
+  HostBasis b_up, b_dn, b_j3;
+  bool same_ao_updn = true;
+  SysDev sys{};
+  int nmo_pad = 4;
+  // workspace
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  int64_t launches = 0;
+  // optional per-kernel timing (qe_profile): CUDA events recorded on the launch stream around each kernel
+  bool profiling = false;
+  bool fused = true;  // qe_local_energy uses the fused walker kernel when the system fits
+  struct ProfRec { int id; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
+  int n_chunk_el = 1;    // chunks used by the electron VGL pass
+  int n_chunk_mc = 1;    // chunk warps of the Metropolis kernel
+  std::vector<int> chunk_el, chunk_mc;
+  const int* d_chunk_el = nullptr;
+  const int* d_chunk_mc = nullptr;
+};
+
+enum KernelId { K_ORB_EL = 0, K_GEMINAL, K_ALGEBRA, K_ECP_MESH, K_REDUCE, K_RATIOS, K_AS, K_ROT, K_KEYCHAIN, K_DRAWS, K_MCMC,
+                K_EVAL, K_LRDMC, K_EL_FUSED, K_COUNT };
+static const char* const KERNEL_NAMES[K_COUNT] = {"k_orb_electrons", "k_geminal", "k_electron_algebra", "k_ecp_mesh", "k_reduce_eL",
+                                                  "k_move_ratios", "k_as_factor", "k_rotation", "k_mcmc_keychain", "k_mcmc_draws",
+                                                  "k_mcmc", "k_eval_orbitals", "k_walker(lrdmc)", "k_walker(e_L)"};
+struct LaunchScope {
+  qe_engine* h;
+  cudaStream_t st;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int id;
+  LaunchScope(qe_engine* h_, int id_, cudaStream_t st_) : h(h_), st(st_), id(id_) {
+    h->launches++;
+    if (h->profiling) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, st);
+    }
+  }
+  ~LaunchScope() {
+    if (e0) {
+      cudaEventRecord(e1, st);
+      h->prof.push_back({id, e0, e1});
+    }
+  }
+};
+
+static inline int ensure_ws(qe_engine* h, size_t bytes) {
+  if (bytes <= h->ws_bytes) return QE_OK;
+  if (h->ws) cudaFree(h->ws);
+  h->ws = nullptr;
+  h->ws_bytes = 0;
+  CUDA_TRY(cudaMalloc(&h->ws, bytes));
+  h->ws_bytes = bytes;
+  return QE_OK;
+}
+
+// =================================================================================================
+// small device helpers
+// =================================================================================================
+// index of the atom with distance-rank `rank` from p (argsort semantics, first index wins ties;
+// jqmc/structure.py:410-426)
+__device__ __forceinline__ int nearest_atom(const double* __restrict__ Rn, int n_atom, double px, double py, double pz,
+                                            int rank, double* dist_out) {
+  if (rank == 0) {
+    int best = 0;
+    double bd = 1e300;
+    for (int a = 0; a < n_atom; ++a) {
+      const double dx = Rn[3 * a] - px, dy = Rn[3 * a + 1] - py, dz = Rn[3 * a + 2] - pz;
+      const double d = sqrt(dx * dx + dy * dy + dz * dz);
+      if (d < bd) {
+        bd = d;
+        best = a;
+      }
+    }
+    if (dist_out) *dist_out = bd;
+    return best;
+  }
+  for (int a = 0; a < n_atom; ++a) {
+    const double dx = Rn[3 * a] - px, dy = Rn[3 * a + 1] - py, dz = Rn[3 * a + 2] - pz;
+    const double da = sqrt(dx * dx + dy * dy + dz * dz);
+    int r = 0;
+    for (int b = 0; b < n_atom; ++b) {
+      const double ex = Rn[3 * b] - px, ey = Rn[3 * b + 1] - py, ez = Rn[3 * b + 2] - pz;
+      const double db = sqrt(ex * ex + ey * ey + ez * ez);
+      r += (db < da) || (db == da && b < a);
+    }
+    if (r == rank) {
+      if (dist_out) *dist_out = da;
+      return a;
+    }
+  }
+  return 0;
+}
+
+__device__ __forceinline__ double j1_f(int type, double a, double A, double c, double d) {
+  // jqmc/jastrow_factor.py:648-726
+  if (type == 1) return -A * (1.0 - exp(-a * c * d)) / (2.0 * a);
+  return -A * d / (2.0 * (1.0 + a * c * d));
+}
+__device__ __forceinline__ double j2_f(int type, double a, double d) {
+  // jqmc/jastrow_factor.py:1180-1251
+  if (type == 1) return d / (2.0 * (1.0 + a * d));
+  return (1.0 - exp(-a * d)) / (2.0 * a);
+}
+
+// Legendre P_l(x), l <= 6 (jqmc/_function_collections.py:47-65)
+__device__ __forceinline__ double legendre_l(int l, double x) {
+  const double x2 = x * x;
+  switch (l) {
+    case 0: return 1.0;
+    case 1: return x;
+    case 2: return 0.5 * (3.0 * x2 - 1.0);
+    case 3: return 0.5 * (5.0 * x2 - 3.0) * x;
+    case 4: return 0.125 * ((35.0 * x2 - 30.0) * x2 + 3.0);
+    case 5: return 0.125 * ((63.0 * x2 - 70.0) * x2 + 15.0) * x;
+    default: return 0.0625 * (((231.0 * x2 - 315.0) * x2 + 105.0) * x2 - 5.0);
+  }
+}
+
+// electron position accessors: global AoS arrays r_up[nw][n_up][3], r_dn[nw][n_dn][3]
+struct PosGlobal {
+  const double* __restrict__ up;
+  const double* __restrict__ dn;
+  int n_up, n_dn, w;
+  __device__ __forceinline__ void get(int e, double& x, double& y, double& z) const {
+    const double* p = e < n_up ? up + ((size_t)w * n_up + e) * 3 : dn + ((size_t)w * n_dn + (e - n_up)) * 3;
+    x = p[0];
+    y = p[1];
+    z = p[2];
+  }
+};
+
+// Jastrow (J1+J2) difference J(r') - J(r) for moving electron e from (ox,oy,oz) to (nx,ny,nz)
+template <class Pos>
+__device__ __forceinline__ double jastrow_delta(const SysDev& S, const Pos& pos, int e, double ox, double oy, double oz,
+                                                double nx, double ny, double nz) {
+  double dJ = 0.0;
+  if (S.j1_type) {
+    for (int a = 0; a < S.n_atom; ++a) {
+      const double X = S.Rn[3 * a], Y = S.Rn[3 * a + 1], Z = S.Rn[3 * a + 2];
+      const double dn_ = sqrt((nx - X) * (nx - X) + (ny - Y) * (ny - Y) + (nz - Z) * (nz - Z));
+      const double do_ = sqrt((ox - X) * (ox - X) + (oy - Y) * (oy - Y) + (oz - Z) * (oz - Z));
+      const double A = S.j1_A[a], c = S.j1_c[a];
+      dJ += j1_f(S.j1_type, S.j1_a, A, c, dn_) - j1_f(S.j1_type, S.j1_a, A, c, do_);
+    }
+  }
+  if (S.j2_type) {
+    for (int j = 0; j < S.n_e; ++j) {
+      if (j == e) continue;
+      double x, y, z;
+      pos.get(j, x, y, z);
+      const double dn_ = sqrt((nx - x) * (nx - x) + (ny - y) * (ny - y) + (nz - z) * (nz - z));
+      const double do_ = sqrt((ox - x) * (ox - x) + (oy - y) * (oy - y) + (oz - z) * (oz - z));
+      dJ += j2_f(S.j2_type, S.j2_a, dn_) - j2_f(S.j2_type, S.j2_a, do_);
+    }
+  }
+  return dJ;
+}
+
+
+#define DISPATCH_NMO_CART(h, CALL)                                  \
+  do {                                                              \
+    const bool cart_ = (h)->b_up.dev.cart != 0;                     \
+    switch ((h)->nmo_pad) {                                         \
+      case 4: if (cart_) { CALL(4, true); } else { CALL(4, false); } break;   \
+      case 8: if (cart_) { CALL(8, true); } else { CALL(8, false); } break;   \
+      default: if (cart_) { CALL(16, true); } else { CALL(16, false); } break; \
+    }                                                               \
+  } while (0)
+#define DISPATCH_NMO(h, CALL)       \
+  do {                              \
+    switch ((h)->nmo_pad) {         \
+      case 4: CALL(4); break;       \
+      case 8: CALL(8); break;       \
+      default: CALL(16); break;     \
+    }                               \
+  } while (0)
+
+static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+#define CHECK_LAUNCH()                                                                    \
+  do {                                                                                    \
+    cudaError_t e_ = cudaGetLastError();                                                  \
+    if (e_ != cudaSuccess) return fail(QE_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+  } while (0)
+
+
+// workspace carve-up helper
+struct WsCarve {
+  char* base;
+  size_t off = 0;
+  template <class T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = (T*)(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+

@@ -23,8 +23,8 @@ struct BasisDev {
   const int* grp_sh_begin;   // [n_grp+1] shell range of the group
   const int* sh_prim_off;    // [n_shell+1]
   const short* sh_slot;      // [n_shell*MAXF] AO index of canonical function k, or -1
-  const double* pr_Z;        // [n_prim] exponent
-  const double* pr_c;        // [n_prim] coefficient * N_p * sqrt((2l+1)/4pi)   (jqmc/atomic_orbital.py:2316-2349)
+  int n_prim;                // compressed shell primitives
+  const double2* pr_zc;      // [n_prim] {exponent, coefficient * N_p * sqrt((2l+1)/4pi)}  (jqmc/atomic_orbital.py:2316-2349)
   const double* ao_scale;    // [n_ao]   per-AO factor (shell-relative coefficient ratio, Cartesian factorial part)
   const double* Cs;          // [n_ao*nmo_pad]  mo_coefficients^T * ao_scale  (MO layer), or nullptr
 };
@@ -153,7 +153,17 @@ __device__ __forceinline__ void eval_group_val(const BasisDev& B, int g, double 
   for (int s = sb; s < se; ++s) {
     const int pb = B.sh_prim_off[s], pe = B.sh_prim_off[s + 1];
     double R = 0.0;
-    for (int p = pb; p < pe; ++p) R = fma(__ldg(B.pr_c + p), exp(-__ldg(B.pr_Z + p) * r2), R);
+    int p = pb;
+    for (; p + 1 < pe; p += 2) {  // two independent exp chains per trip
+      const double2 a = B.pr_zc[p], b = B.pr_zc[p + 1];
+      const double ea = exp(-a.x * r2), eb = exp(-b.x * r2);
+      R = fma(a.y, ea, R);
+      R = fma(b.y, eb, R);
+    }
+    if (p < pe) {
+      const double2 a = B.pr_zc[p];
+      R = fma(a.y, exp(-a.x * r2), R);
+    }
     const short* slot = B.sh_slot + s * MAXF;
 #pragma unroll
     for (int k = 0; k < A::NF; ++k) {
@@ -173,8 +183,9 @@ __device__ __forceinline__ void eval_group_vgl(const BasisDev& B, int g, int l, 
     const int pb = B.sh_prim_off[s], pe = B.sh_prim_off[s + 1];
     double R0 = 0.0, R1 = 0.0, R2 = 0.0;
     for (int p = pb; p < pe; ++p) {
-      const double Z = __ldg(B.pr_Z + p);
-      const double e = __ldg(B.pr_c + p) * exp(-Z * r2);
+      const double2 zc = B.pr_zc[p];
+      const double Z = zc.x;
+      const double e = zc.y * exp(-Z * r2);
       R0 += e;
       R1 = fma(Z, e, R1);
       R2 = fma(Z * Z, e, R2);
@@ -204,7 +215,7 @@ __device__ __forceinline__ void eval_val(const BasisDev& B, const double* __rest
                                          int gb, int ge, Sink& sink) {
   for (int g = gb; g < ge; ++g) {
     const int nuc = B.grp_nuc[g];
-    const double dx = px - __ldg(Rn + 3 * nuc), dy = py - __ldg(Rn + 3 * nuc + 1), dz = pz - __ldg(Rn + 3 * nuc + 2);
+    const double dx = px - Rn[3 * nuc], dy = py - Rn[3 * nuc + 1], dz = pz - Rn[3 * nuc + 2];
     const double r2 = dx * dx + dy * dy + dz * dz;
     switch (B.grp_l[g]) {
       case 0: eval_group_val<typename Ang<CART, 0>::type>(B, g, dx, dy, dz, r2, sink); break;
@@ -223,7 +234,7 @@ __device__ __forceinline__ void eval_vgl(const BasisDev& B, const double* __rest
                                          int gb, int ge, Sink& sink) {
   for (int g = gb; g < ge; ++g) {
     const int nuc = B.grp_nuc[g];
-    const double dx = px - __ldg(Rn + 3 * nuc), dy = py - __ldg(Rn + 3 * nuc + 1), dz = pz - __ldg(Rn + 3 * nuc + 2);
+    const double dx = px - Rn[3 * nuc], dy = py - Rn[3 * nuc + 1], dz = pz - Rn[3 * nuc + 2];
     const double r2 = dx * dx + dy * dy + dz * dz;
     const int l = B.grp_l[g];
     switch (l) {
@@ -253,7 +264,7 @@ struct SinkMO {
   __device__ __forceinline__ void add(int a, double v) {
     const double* c = Cs + a * NMO;
 #pragma unroll
-    for (int i = 0; i < NMO; ++i) acc[i] = fma(__ldg(c + i), v, acc[i]);
+    for (int i = 0; i < NMO; ++i) acc[i] = fma(c[i], v, acc[i]);
   }
 };
 template <int NMO>
@@ -271,7 +282,7 @@ struct SinkMO5 {
     const double* c = Cs + a * NMO;
 #pragma unroll
     for (int i = 0; i < NMO; ++i) {
-      const double ci = __ldg(c + i);
+      const double ci = c[i];
       acc[0][i] = fma(ci, v, acc[0][i]);
       acc[1][i] = fma(ci, gx, acc[1][i]);
       acc[2][i] = fma(ci, gy, acc[2][i]);

@@ -6,147 +6,12 @@
 // task (an electron, a quadrature point, a chunk of the AO basis); all lanes therefore execute the same
 // shell/primitive sequence, table loads are warp-broadcast and walker-state loads/stores are coalesced
 // through [item][walker] workspace layouts.
-#include <algorithm>
-#include <cmath>
-#include <cstdio>
-#include <cstring>
-#include <map>
-#include <string>
-#include <vector>
+#include "qe_common.cuh"
 
-#include "../../include/jqmc_b200.h"
-#include "qe_device.cuh"
-
-using namespace qe;
-
-// =================================================================================================
-// error handling
-// =================================================================================================
 static thread_local std::string g_err;
-static int fail(int code, const std::string& msg) {
+int qe_fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
-}
-#define CUDA_TRY(x)                                                                              \
-  do {                                                                                           \
-    cudaError_t e_ = (x);                                                                        \
-    if (e_ != cudaSuccess)                                                                       \
-      return fail(QE_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_));                \
-  } while (0)
-
-// =================================================================================================
-// engine object
-// =================================================================================================
-struct DevPool {
-  std::vector<void*> ptrs;
-  template <class T>
-  cudaError_t upload(const std::vector<T>& v, const T** out) {
-    void* p = nullptr;
-    size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
-    cudaError_t e = cudaMalloc(&p, n);
-    if (e != cudaSuccess) return e;
-    ptrs.push_back(p);
-    if (!v.empty()) e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
-    *out = (const T*)p;
-    return e;
-  }
-  void release() {
-    for (void* p : ptrs) cudaFree(p);
-    ptrs.clear();
-  }
-};
-
-struct HostBasis {
-  BasisDev dev{};
-  std::vector<int> chunk_begin;  // balanced chunks of groups, chunk_begin[n_chunk+1]
-  std::vector<double> grp_cost;
-  bool present = false;
-};
-
-struct SysDev {
-  int n_atom, n_up, n_dn, n_e;
-  const double* Rn;     // [n_atom*3]
-  const double* Zeff;   // [n_atom]
-  // geminal lambda in orbital basis: lam_p [nmo_pad][nmo_pad] (zero padded), lam_u [nmo_pad][n_up-n_dn]
-  const double* lam_p;
-  const double* lam_u;
-  int n_unp;
-  // Jastrow
-  int j1_type;
-  double j1_a;
-  const double* j1_A;   // (2 Z)^{3/4}
-  const double* j1_c;   // (2 Z)^{1/4}
-  int j2_type;
-  double j2_a;
-  // ECP
-  int ecp_flag, n_ecp, Nv, NN, ecp_lmax;  // ecp_lmax = global max_ang_mom_plus_1
-  const int* ecp_nuc;
-  const int* ecp_l;
-  const double* ecp_z;
-  const double* ecp_c;
-  const double* ecp_p;
-  const int* ecp_lmax_atom;  // [n_atom] max_ang_mom_plus_1
-  const int* ecp_off;        // [n_atom+1] terms sorted by atom
-  const double* quad_w;      // [Nv]
-  const double* quad_g;      // [Nv*3]
-  double v_ion_ion;
-};
-
-struct qe_engine {
-  DevPool pool;
-  HostBasis b_up, b_dn, b_j3;
-  bool same_ao_updn = true;
-  SysDev sys{};
-  int nmo_pad = 4;
-  // workspace
-  void* ws = nullptr;
-  size_t ws_bytes = 0;
-  int64_t launches = 0;
-  // optional per-kernel timing (qe_profile): CUDA events recorded on the launch stream around each kernel
-  bool profiling = false;
-  struct ProfRec { int id; cudaEvent_t e0, e1; };
-  std::vector<ProfRec> prof;
-  int n_chunk_el = 1;    // chunks used by the electron VGL pass
-  int n_chunk_mc = 1;    // chunk warps of the Metropolis kernel
-  std::vector<int> chunk_el, chunk_mc;
-  const int* d_chunk_el = nullptr;
-  const int* d_chunk_mc = nullptr;
-};
-
-enum KernelId { K_ORB_EL = 0, K_GEMINAL, K_ALGEBRA, K_ECP_MESH, K_REDUCE, K_RATIOS, K_AS, K_ROT, K_KEYCHAIN, K_DRAWS, K_MCMC,
-                K_EVAL, K_LRDMC, K_COUNT };
-static const char* const KERNEL_NAMES[K_COUNT] = {"k_orb_electrons", "k_geminal", "k_electron_algebra", "k_ecp_mesh", "k_reduce_eL",
-                                                  "k_move_ratios", "k_as_factor", "k_rotation", "k_mcmc_keychain", "k_mcmc_draws",
-                                                  "k_mcmc", "k_eval_orbitals", "k_lrdmc"};
-struct LaunchScope {
-  qe_engine* h;
-  cudaStream_t st;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  int id;
-  LaunchScope(qe_engine* h_, int id_, cudaStream_t st_) : h(h_), st(st_), id(id_) {
-    h->launches++;
-    if (h->profiling) {
-      cudaEventCreate(&e0);
-      cudaEventCreate(&e1);
-      cudaEventRecord(e0, st);
-    }
-  }
-  ~LaunchScope() {
-    if (e0) {
-      cudaEventRecord(e1, st);
-      h->prof.push_back({id, e0, e1});
-    }
-  }
-};
-
-static int ensure_ws(qe_engine* h, size_t bytes) {
-  if (bytes <= h->ws_bytes) return QE_OK;
-  if (h->ws) cudaFree(h->ws);
-  h->ws = nullptr;
-  h->ws_bytes = 0;
-  CUDA_TRY(cudaMalloc(&h->ws, bytes));
-  h->ws_bytes = bytes;
-  return QE_OK;
 }
 
 // =================================================================================================
@@ -248,7 +113,7 @@ static int build_basis(const qe_basis_desc& d, int n_atom, int nmo_pad, DevPool&
   });
   std::vector<int> grp_nuc, grp_l, grp_sh_begin, sh_prim_off{0};
   std::vector<short> sh_slot;
-  std::vector<double> pr_Z, pr_c;
+  std::vector<double2> pr_zc;
   hb.grp_cost.clear();
   for (size_t s = 0; s < shells.size(); ++s) {
     const TmpShell& sh = shells[s];
@@ -267,10 +132,9 @@ static int build_basis(const qe_basis_desc& d, int n_atom, int nmo_pad, DevPool&
       else  // jqmc/atomic_orbital.py:2316-2323, times sqrt((2l+1)/4pi) (:2349)
         N = std::sqrt(std::pow(2.0, 2 * l + 3) * dfact(l + 1) * std::pow(2.0 * Z, l + 1.5) / (dfact(2 * l + 2) * std::sqrt(M_PI))) *
             std::sqrt((2 * l + 1) / (4.0 * M_PI));
-      pr_Z.push_back(Z);
-      pr_c.push_back(sh.c[i] * N);
+      pr_zc.push_back(make_double2(Z, sh.c[i] * N));
     }
-    sh_prim_off.push_back((int)pr_Z.size());
+    sh_prim_off.push_back((int)pr_zc.size());
     sh_slot.insert(sh_slot.end(), sh.slot.begin(), sh.slot.end());
     int nf = 0;
     for (short v : sh.slot) nf += v >= 0;
@@ -298,8 +162,8 @@ static int build_basis(const qe_basis_desc& d, int n_atom, int nmo_pad, DevPool&
   if (e == cudaSuccess) e = pool.upload(grp_sh_begin, &B.grp_sh_begin);
   if (e == cudaSuccess) e = pool.upload(sh_prim_off, &B.sh_prim_off);
   if (e == cudaSuccess) e = pool.upload(sh_slot, &B.sh_slot);
-  if (e == cudaSuccess) e = pool.upload(pr_Z, &B.pr_Z);
-  if (e == cudaSuccess) e = pool.upload(pr_c, &B.pr_c);
+  B.n_prim = (int)pr_zc.size();
+  if (e == cudaSuccess) e = pool.upload(pr_zc, &B.pr_zc);
   if (e == cudaSuccess) e = pool.upload(ao_scale, &B.ao_scale);
   if (e == cudaSuccess) e = pool.upload(Cs, &B.Cs);
   if (e != cudaSuccess) return fail(QE_ERR_CUDA, std::string("basis upload: ") + cudaGetErrorString(e));
@@ -357,109 +221,6 @@ static bool same_ao_tables(const qe_basis_desc& x, const qe_basis_desc& y) {
     if (x.orbital_indices[p] != y.orbital_indices[p] || x.exponents[p] != y.exponents[p] || x.coefficients[p] != y.coefficients[p])
       return false;
   return true;
-}
-
-// =================================================================================================
-// small device helpers
-// =================================================================================================
-// index of the atom with distance-rank `rank` from p (argsort semantics, first index wins ties;
-// jqmc/structure.py:410-426)
-__device__ __forceinline__ int nearest_atom(const double* __restrict__ Rn, int n_atom, double px, double py, double pz,
-                                            int rank, double* dist_out) {
-  if (rank == 0) {
-    int best = 0;
-    double bd = 1e300;
-    for (int a = 0; a < n_atom; ++a) {
-      const double dx = __ldg(Rn + 3 * a) - px, dy = __ldg(Rn + 3 * a + 1) - py, dz = __ldg(Rn + 3 * a + 2) - pz;
-      const double d = sqrt(dx * dx + dy * dy + dz * dz);
-      if (d < bd) {
-        bd = d;
-        best = a;
-      }
-    }
-    if (dist_out) *dist_out = bd;
-    return best;
-  }
-  for (int a = 0; a < n_atom; ++a) {
-    const double dx = __ldg(Rn + 3 * a) - px, dy = __ldg(Rn + 3 * a + 1) - py, dz = __ldg(Rn + 3 * a + 2) - pz;
-    const double da = sqrt(dx * dx + dy * dy + dz * dz);
-    int r = 0;
-    for (int b = 0; b < n_atom; ++b) {
-      const double ex = __ldg(Rn + 3 * b) - px, ey = __ldg(Rn + 3 * b + 1) - py, ez = __ldg(Rn + 3 * b + 2) - pz;
-      const double db = sqrt(ex * ex + ey * ey + ez * ez);
-      r += (db < da) || (db == da && b < a);
-    }
-    if (r == rank) {
-      if (dist_out) *dist_out = da;
-      return a;
-    }
-  }
-  return 0;
-}
-
-__device__ __forceinline__ double j1_f(int type, double a, double A, double c, double d) {
-  // jqmc/jastrow_factor.py:648-726
-  if (type == 1) return -A * (1.0 - exp(-a * c * d)) / (2.0 * a);
-  return -A * d / (2.0 * (1.0 + a * c * d));
-}
-__device__ __forceinline__ double j2_f(int type, double a, double d) {
-  // jqmc/jastrow_factor.py:1180-1251
-  if (type == 1) return d / (2.0 * (1.0 + a * d));
-  return (1.0 - exp(-a * d)) / (2.0 * a);
-}
-
-// Legendre P_l(x), l <= 6 (jqmc/_function_collections.py:47-65)
-__device__ __forceinline__ double legendre_l(int l, double x) {
-  const double x2 = x * x;
-  switch (l) {
-    case 0: return 1.0;
-    case 1: return x;
-    case 2: return 0.5 * (3.0 * x2 - 1.0);
-    case 3: return 0.5 * (5.0 * x2 - 3.0) * x;
-    case 4: return 0.125 * ((35.0 * x2 - 30.0) * x2 + 3.0);
-    case 5: return 0.125 * ((63.0 * x2 - 70.0) * x2 + 15.0) * x;
-    default: return 0.0625 * (((231.0 * x2 - 315.0) * x2 + 105.0) * x2 - 5.0);
-  }
-}
-
-// electron position accessors: global AoS arrays r_up[nw][n_up][3], r_dn[nw][n_dn][3]
-struct PosGlobal {
-  const double* __restrict__ up;
-  const double* __restrict__ dn;
-  int n_up, n_dn, w;
-  __device__ __forceinline__ void get(int e, double& x, double& y, double& z) const {
-    const double* p = e < n_up ? up + ((size_t)w * n_up + e) * 3 : dn + ((size_t)w * n_dn + (e - n_up)) * 3;
-    x = p[0];
-    y = p[1];
-    z = p[2];
-  }
-};
-
-// Jastrow (J1+J2) difference J(r') - J(r) for moving electron e from (ox,oy,oz) to (nx,ny,nz)
-template <class Pos>
-__device__ __forceinline__ double jastrow_delta(const SysDev& S, const Pos& pos, int e, double ox, double oy, double oz,
-                                                double nx, double ny, double nz) {
-  double dJ = 0.0;
-  if (S.j1_type) {
-    for (int a = 0; a < S.n_atom; ++a) {
-      const double X = __ldg(S.Rn + 3 * a), Y = __ldg(S.Rn + 3 * a + 1), Z = __ldg(S.Rn + 3 * a + 2);
-      const double dn_ = sqrt((nx - X) * (nx - X) + (ny - Y) * (ny - Y) + (nz - Z) * (nz - Z));
-      const double do_ = sqrt((ox - X) * (ox - X) + (oy - Y) * (oy - Y) + (oz - Z) * (oz - Z));
-      const double A = __ldg(S.j1_A + a), c = __ldg(S.j1_c + a);
-      dJ += j1_f(S.j1_type, S.j1_a, A, c, dn_) - j1_f(S.j1_type, S.j1_a, A, c, do_);
-    }
-  }
-  if (S.j2_type) {
-    for (int j = 0; j < S.n_e; ++j) {
-      if (j == e) continue;
-      double x, y, z;
-      pos.get(j, x, y, z);
-      const double dn_ = sqrt((nx - x) * (nx - x) + (ny - y) * (ny - y) + (nz - z) * (nz - z));
-      const double do_ = sqrt((ox - x) * (ox - x) + (oy - y) * (oy - y) + (oz - z) * (oz - z));
-      dJ += j2_f(S.j2_type, S.j2_a, dn_) - j2_f(S.j2_type, S.j2_a, do_);
-    }
-  }
-  return dJ;
 }
 
 // =================================================================================================
@@ -549,7 +310,7 @@ __global__ void k_geminal(SysDev S, int nw, int n_chunk, const double* __restric
     double t[NMO];
     for (int b = 0; b < NMO; ++b) {
       double s = 0;
-      for (int a = 0; a < NMO; ++a) s = fma(pu[a], __ldg(S.lam_p + a * NMO + b), s);
+      for (int a = 0; a < NMO; ++a) s = fma(pu[a], S.lam_p[a * NMO + b], s);
       t[b] = s;
     }
     for (int j = 0; j < Nd; ++j) {
@@ -563,7 +324,7 @@ __global__ void k_geminal(SysDev S, int nw, int n_chunk, const double* __restric
     }
     for (int k = 0; k < S.n_unp; ++k) {
       double s = 0;
-      for (int a = 0; a < NMO; ++a) s = fma(pu[a], __ldg(S.lam_u + a * S.n_unp + k), s);
+      for (int a = 0; a < NMO; ++a) s = fma(pu[a], S.lam_u[a * S.n_unp + k], s);
       G[i * N + Nd + k] = s;
     }
   }
@@ -676,8 +437,8 @@ __global__ void k_electron_algebra(SysDev S, int nw, int n_chunk, const double* 
     }
     for (int a = 0; a < NMO; ++a) {
       double s = 0;
-      for (int b = 0; b < NMO; ++b) s = fma(__ldg(S.lam_p + a * NMO + b), y[b], s);
-      for (int k = 0; k < S.n_unp; ++k) s = fma(__ldg(S.lam_u + a * S.n_unp + k), Gi[(Nd + k) * N + e], s);
+      for (int b = 0; b < NMO; ++b) s = fma(S.lam_p[a * NMO + b], y[b], s);
+      for (int k = 0; k < S.n_unp; ++k) s = fma(S.lam_u[a * S.n_unp + k], Gi[(Nd + k) * N + e], s);
       Wv[a] = s;
     }
   } else {
@@ -691,7 +452,7 @@ __global__ void k_electron_algebra(SysDev S, int nw, int n_chunk, const double* 
     }
     for (int b = 0; b < NMO; ++b) {
       double s = 0;
-      for (int a = 0; a < NMO; ++a) s = fma(y[a], __ldg(S.lam_p + a * NMO + b), s);
+      for (int a = 0; a < NMO; ++a) s = fma(y[a], S.lam_p[a * NMO + b], s);
       Wv[b] = s;
     }
   }
@@ -714,12 +475,12 @@ __global__ void k_electron_algebra(SysDev S, int nw, int n_chunk, const double* 
   double v_bare = 0.0, v_loc = 0.0;
   const double eps = 1.0e-12;
   for (int a = 0; a < S.n_atom; ++a) {
-    const double dx = x - __ldg(S.Rn + 3 * a), dy = y_ - __ldg(S.Rn + 3 * a + 1), dz = z - __ldg(S.Rn + 3 * a + 2);
+    const double dx = x - S.Rn[3 * a], dy = y_ - S.Rn[3 * a + 1], dz = z - S.Rn[3 * a + 2];
     const double d = sqrt(dx * dx + dy * dy + dz * dz);
-    v_bare -= __ldg(S.Zeff + a) / d;
+    v_bare -= S.Zeff[a] / d;
     if (S.j1_type) {
       const double rs = fmax(d, eps);
-      const double A = __ldg(S.j1_A + a), c = __ldg(S.j1_c + a), aa = S.j1_a;
+      const double A = S.j1_A[a], c = S.j1_c[a], aa = S.j1_a;
       double fp;
       if (S.j1_type == 1) {
         const double ex = exp(-aa * c * rs);
@@ -736,10 +497,10 @@ __global__ void k_electron_algebra(SysDev S, int nw, int n_chunk, const double* 
       gJ[2] = fma(s, dz, gJ[2]);
     }
     if (S.ecp_flag) {
-      const int lloc = __ldg(S.ecp_lmax_atom + a);
+      const int lloc = S.ecp_lmax_atom[a];
       double s = 0.0;
-      for (int k = __ldg(S.ecp_off + a); k < __ldg(S.ecp_off + a + 1); ++k)
-        if (__ldg(S.ecp_l + k) == lloc) s += __ldg(S.ecp_c + k) * pow(d, __ldg(S.ecp_p + k)) * exp(-__ldg(S.ecp_z + k) * d * d);
+      for (int k = S.ecp_off[a]; k < S.ecp_off[a + 1]; ++k)
+        if (S.ecp_l[k] == lloc) s += S.ecp_c[k] * pow(d, S.ecp_p[k]) * exp(-S.ecp_z[k] * d * d);
       v_loc += s / (d * d);
     }
   }
@@ -796,11 +557,11 @@ k_ecp_mesh(BasisDev Bu, BasisDev Bd, SysDev S, int nw, const double* __restrict_
   pos.get(e, x, y, z);
   double d;
   const int a = nearest_atom(S.Rn, S.n_atom, x, y, z, nn, &d);
-  const double relx = __ldg(S.Rn + 3 * a) - x, rely = __ldg(S.Rn + 3 * a + 1) - y, relz = __ldg(S.Rn + 3 * a + 2) - z;
+  const double relx = S.Rn[3 * a] - x, rely = S.Rn[3 * a + 1] - y, relz = S.Rn[3 * a + 2] - z;
   d = sqrt(relx * relx + rely * rely + relz * relz);
   // rotated grid point g = grid[k] @ RT
   const double* rt = RT + (size_t)w * 9;
-  const double q0 = __ldg(S.quad_g + 3 * k), q1 = __ldg(S.quad_g + 3 * k + 1), q2 = __ldg(S.quad_g + 3 * k + 2);
+  const double q0 = S.quad_g[3 * k], q1 = S.quad_g[3 * k + 1], q2 = S.quad_g[3 * k + 2];
   const double gx = q0 * rt[0] + q1 * rt[3] + q2 * rt[6];
   const double gy = q0 * rt[1] + q1 * rt[4] + q2 * rt[7];
   const double gz = q0 * rt[2] + q1 * rt[5] + q2 * rt[8];
@@ -814,12 +575,12 @@ k_ecp_mesh(BasisDev Bu, BasisDev Bd, SysDev S, int nw, const double* __restrict_
   const double gn = sqrt(gx * gx + gy * gy + gz * gz);
   const double cos_t = (-relx / d) * (gx / gn) + (-rely / d) * (gy / gn) + (-relz / d) * (gz / gn);
   // radial channels V_l(d) = sum_terms c d^(p-2) exp(-z d^2), non-local terms only
-  const int lloc = __ldg(S.ecp_lmax_atom + a);
+  const int lloc = S.ecp_lmax_atom[a];
   double ang = 0.0;
   for (int l = 0; l < lloc; ++l) {
     double vl = 0.0;
-    for (int kk = __ldg(S.ecp_off + a); kk < __ldg(S.ecp_off + a + 1); ++kk)
-      if (__ldg(S.ecp_l + kk) == l) vl += __ldg(S.ecp_c + kk) * pow(d, __ldg(S.ecp_p + kk)) * exp(-__ldg(S.ecp_z + kk) * d * d);
+    for (int kk = S.ecp_off[a]; kk < S.ecp_off[a + 1]; ++kk)
+      if (S.ecp_l[kk] == l) vl += S.ecp_c[kk] * pow(d, S.ecp_p[kk]) * exp(-S.ecp_z[kk] * d * d);
     ang = fma(vl / (d * d) * (2 * l + 1), legendre_l(l, cos_t), ang);
   }
   double val = 0.0;
@@ -832,7 +593,7 @@ k_ecp_mesh(BasisDev Bu, BasisDev Bd, SysDev S, int nw, const double* __restrict_
 #pragma unroll
     for (int mo = 0; mo < NMO; ++mo) ratio = fma(sink.acc[mo], W[((size_t)e * NMO + mo) * nw + w], ratio);
     if (!det_only) ratio *= exp(jastrow_delta(S, pos, e, x, y, z, px, py, pz));
-    val = ang * __ldg(S.quad_w + k) * ratio;
+    val = ang * S.quad_w[k] * ratio;
   }
   Vnl[(size_t)pt * nw + w] = val;
 }
@@ -919,394 +680,6 @@ __global__ void k_as_factor(int N, int nw, const double* __restrict__ G, const d
 }
 
 // =================================================================================================
-// RNG kernels (semantics: oracle/jaxrng.py; call sites jqmc/jqmc_mcmc.py:4322-4367, 4499-4500, 4232-4233)
-// =================================================================================================
-// rotation matrix RT = R^T from split(key)[1], key not advanced (jqmc/jqmc_mcmc.py:4228-4245)
-__device__ __forceinline__ void rotation_RT(double al, double be, double ga, double* __restrict__ o) {
-  double sa, ca, sb, cb, sg, cg;
-  sincos(al, &sa, &ca);
-  sincos(be, &sb, &cb);
-  sincos(ga, &sg, &cg);
-  // R rows; store transposed
-  const double R00 = cb * cg, R01 = cg * sa * sb - ca * sg, R02 = sa * sg + ca * cg * sb;
-  const double R10 = cb * sg, R11 = ca * cg + sa * sb * sg, R12 = ca * sb * sg - cg * sa;
-  const double R20 = -sb, R21 = cb * sa, R22 = ca * cb;
-  o[0] = R00; o[1] = R10; o[2] = R20;
-  o[3] = R01; o[4] = R11; o[5] = R21;
-  o[6] = R02; o[7] = R12; o[8] = R22;
-}
-__global__ void k_rotation(int nw, const uint32_t* __restrict__ keys, double* __restrict__ RT) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nw) return;
-  Key k{keys[2 * w], keys[2 * w + 1]};
-  const Key sub = threefry(k, 0u, 1u);
-  const double two_pi = 6.283185307179586;
-  const double al = rng_uniform_bits(rng_bits64(sub, 0u), -two_pi, two_pi);
-  const double be = rng_uniform_bits(rng_bits64(sub, 1u), -two_pi, two_pi);
-  const double ga = rng_uniform_bits(rng_bits64(sub, 2u), -two_pi, two_pi);
-  rotation_RT(al, be, ga, RT + (size_t)w * 9);
-}
-
-// key chain of the Metropolis loop: 6 splits per proposal.  thread = walker.  sub[(p*6+i)][w]
-__global__ void k_mcmc_keychain(int nw, int nmpm, uint32_t* __restrict__ keys, uint2* __restrict__ sub) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nw) return;
-  Key k{keys[2 * w], keys[2 * w + 1]};
-  for (int p = 0; p < nmpm * 6; ++p) {
-    Key s;
-    rng_split(k, s);
-    sub[(size_t)p * nw + w] = make_uint2(s.a, s.b);
-  }
-  keys[2 * w] = k.a;
-  keys[2 * w + 1] = k.b;
-}
-// draws of every proposal: thread = (proposal, walker)
-__global__ void k_mcmc_draws(int nw, int nmpm, int n_up, int n_dn, const uint2* __restrict__ sub, int* __restrict__ rsel,
-                             int* __restrict__ raxis, double* __restrict__ rg, double* __restrict__ rb) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)nmpm * nw) return;
-  const int w = (int)(t % nw);
-  const int p = (int)(t / nw);
-  auto K = [&](int i) {
-    const uint2 v = sub[((size_t)p * 6 + i) * nw + w];
-    return Key{v.x, v.y};
-  };
-  const bool is_up = rng_randint(K(0), (uint32_t)(n_up + n_dn)) < n_up;
-  const int iu = rng_randint(K(1), (uint32_t)n_up);
-  const int id = rng_randint(K(2), (uint32_t)n_dn);
-  rsel[t] = is_up ? iu : n_up + id;
-  rg[t] = rng_normal(K(3));
-  raxis[t] = rng_randint(K(4), 3u);
-  rb[t] = rng_uniform_bits(rng_bits64(K(5)), 0.0, 1.0);
-}
-
-// =================================================================================================
-// Metropolis kernel (jqmc/jqmc_mcmc.py:4278-4533).  CTA = 32 walkers (lanes) x (n_chunk + 1) warps.
-//   warps 0..n_chunk-1 : AO/MO evaluation of one basis chunk at the proposed position
-//   warp  n_chunk      : proposal bookkeeping, T_ratio and Jastrow ratio
-//   warp  0            : determinant ratio, Sherman-Morrison update, AS factor, accept/reject
-// Walker state lives in shared memory as [item][lane].
-// =================================================================================================
-struct McmcArgs {
-  int nw, nmpm, n_chunk;
-  double Dt, eps_AS;
-  double* r_up;
-  double* r_dn;
-  double* G;
-  double* Ginv;
-  int* acc;
-  int* rej;
-  const int* rsel;
-  const int* raxis;
-  const double* rg;
-  const double* rb;
-  const int* chunk_begin;
-};
-
-template <int NMO, bool CART>
-__global__ void __launch_bounds__(512)
-k_mcmc(BasisDev Bu, BasisDev Bd, SysDev S, McmcArgs P) {
-  extern __shared__ double sm[];
-  const int lane = threadIdx.x, wid = threadIdx.y;
-  const int w = blockIdx.x * 32 + lane;
-  const bool live = w < P.nw;
-  const int ww = live ? w : P.nw - 1;  // dead lanes shadow the last walker (no stores)
-  const int N = S.n_up, Nd = S.n_dn, Ne = S.n_e, NN2 = N * N;
-  const int nch = P.n_chunk;
-  // shared-memory carve-up (all [item][32])
-  double* s_r = sm;                       // Ne*3
-  double* s_G = s_r + Ne * 3 * 32;        // N*N
-  double* s_Gi = s_G + NN2 * 32;          // N*N
-  double* s_phi = s_Gi + NN2 * 32;        // Ne*NMO   (orbital values at the electrons: [e][mo])
-  double* s_part = s_phi + Ne * NMO * 32; // nch*NMO
-  double* s_TJ = s_part + nch * NMO * 32; // 2: T_ratio, J_ratio
-#define SR(e, c) s_r[((e) * 3 + (c)) * 32 + lane]
-#define SG(i, j) s_G[((i) * N + (j)) * 32 + lane]
-#define SGI(i, j) s_Gi[((i) * N + (j)) * 32 + lane]
-#define SPHI(e, mo) s_phi[((e) * NMO + (mo)) * 32 + lane]
-#define SPART(c, mo) s_part[((c) * NMO + (mo)) * 32 + lane]
-
-  // ---- load state -------------------------------------------------------------------------------
-  const int tid = wid * 32 + lane, nthr = 32 * (nch + 1);
-  for (int idx = wid; idx < Ne * 3; idx += nch + 1) {
-    const int e = idx / 3, c = idx % 3;
-    SR(e, c) = e < N ? P.r_up[((size_t)ww * N + e) * 3 + c] : P.r_dn[((size_t)ww * Nd + (e - N)) * 3 + c];
-  }
-  for (int idx = wid; idx < NN2; idx += nch + 1) {
-    s_G[idx * 32 + lane] = P.G[(size_t)ww * NN2 + idx];
-    s_Gi[idx * 32 + lane] = P.Ginv[(size_t)ww * NN2 + idx];
-  }
-  (void)tid;
-  (void)nthr;
-  __syncthreads();
-
-  // ---- orbital values at every electron (cache for the row/column rebuild) -----------------------
-  for (int e = 0; e < Ne; ++e) {
-    if (wid < nch) {
-      const BasisDev& B = e < N ? Bu : Bd;
-      SinkMO<NMO> sink;
-      sink.init(B.Cs);
-      eval_val<CART>(B, S.Rn, SR(e, 0), SR(e, 1), SR(e, 2), P.chunk_begin[wid], P.chunk_begin[wid + 1], sink);
-#pragma unroll
-      for (int mo = 0; mo < NMO; ++mo) SPART(wid, mo) = sink.acc[mo];
-    }
-    __syncthreads();
-    if (wid == 0) {
-#pragma unroll
-      for (int mo = 0; mo < NMO; ++mo) {
-        double s = 0;
-        for (int c = 0; c < nch; ++c) s += SPART(c, mo);
-        SPHI(e, mo) = s;
-      }
-    }
-    __syncthreads();
-  }
-
-  int n_acc = 0, n_rej = 0;
-  double R_AS_cur = 1.0;
-  if (wid == 0 && P.eps_AS > 0.0) {
-    double F = 0, Smin = 1e300;
-    for (int i = 0; i < NN2; ++i) F = fma(s_Gi[i * 32 + lane], s_Gi[i * 32 + lane], F);
-    for (int i = 0; i < N; ++i) {
-      double r = 0, c = 0;
-      for (int j = 0; j < N; ++j) {
-        r = fma(SG(i, j), SG(i, j), r);
-        c = fma(SG(j, i), SG(j, i), c);
-      }
-      Smin = fmin(Smin, fmin(r, c));
-    }
-    const double SF = Smin * F;
-    R_AS_cur = SF > 0.0 ? pow(SF, -0.375) : 0.0;
-  }
-
-  for (int it = 0; it < P.nmpm; ++it) {
-    // ---- phase A: proposal (every thread, redundantly; lane = walker) ----------------------------
-    const size_t ridx = (size_t)it * P.nw + ww;
-    const int ke = P.rsel[ridx];
-    const int axis = P.raxis[ridx];
-    const bool up = ke < N;
-    const double ox = SR(ke, 0), oy = SR(ke, 1), oz = SR(ke, 2);
-    double dist;
-    int ia = nearest_atom(S.Rn, S.n_atom, ox, oy, oz, 0, &dist);
-    double Zc = __ldg(S.Zeff + ia);
-    const double f_l = 1.0 / (Zc * Zc) * (1.0 + Zc * Zc * dist) / (1.0 + dist);
-    const double g = P.rg[ridx] * (f_l * P.Dt);
-    double nx = ox, ny = oy, nz = oz;
-    if (axis == 0) nx = ox + g;
-    else if (axis == 1) ny = oy + g;
-    else nz = oz + g;
-
-    // ---- phase B ---------------------------------------------------------------------------------
-    if (wid < nch) {
-      // same AO tables for both spins (checked at create); the MO coefficients may differ per lane
-      SinkMO<NMO> sink;
-      sink.init(up ? Bu.Cs : Bd.Cs);
-      eval_val<CART>(Bu, S.Rn, nx, ny, nz, P.chunk_begin[wid], P.chunk_begin[wid + 1], sink);
-#pragma unroll
-      for (int mo = 0; mo < NMO; ++mo) SPART(wid, mo) = sink.acc[mo];
-    } else {
-      ia = nearest_atom(S.Rn, S.n_atom, nx, ny, nz, 0, &dist);
-      Zc = __ldg(S.Zeff + ia);
-      const double f_p = 1.0 / (Zc * Zc) * (1.0 + Zc * Zc * dist) / (1.0 + dist);
-      const double dd = (nx - ox) * (nx - ox) + (ny - oy) * (ny - oy) + (nz - oz) * (nz - oz);
-      const double T_ratio =
-          (f_l / f_p) * exp(-dd * (1.0 / (2.0 * f_p * f_p * P.Dt * P.Dt) - 1.0 / (2.0 * f_l * f_l * P.Dt * P.Dt)));
-      struct PosS {
-        const double* s_r;
-        int lane;
-        __device__ __forceinline__ void get(int e, double& x, double& y, double& z) const {
-          x = s_r[(e * 3 + 0) * 32 + lane];
-          y = s_r[(e * 3 + 1) * 32 + lane];
-          z = s_r[(e * 3 + 2) * 32 + lane];
-        }
-      } pos{s_r, lane};
-      const double J_ratio = exp(jastrow_delta(S, pos, ke, ox, oy, oz, nx, ny, nz));
-      s_TJ[lane] = T_ratio;
-      s_TJ[32 + lane] = J_ratio;
-    }
-    __syncthreads();
-
-    // ---- phase C: warp 0 -------------------------------------------------------------------------
-    if (wid == 0) {
-      double phi[NMO];
-#pragma unroll
-      for (int mo = 0; mo < NMO; ++mo) {
-        double s = 0;
-        for (int c = 0; c < nch; ++c) s += SPART(c, mo);
-        phi[mo] = s;
-      }
-      // v (row difference) or u (column difference), Det_ratio = 1 + v^T Ginv u
-      double dvec[8 > NMO ? 8 : NMO];  // N <= 8 enforced on the host for this kernel
-      double Det;
-      if (up) {
-        const int k = ke;
-        double t[NMO];
-#pragma unroll
-        for (int b = 0; b < NMO; ++b) {
-          double s = 0;
-#pragma unroll
-          for (int a = 0; a < NMO; ++a) s = fma(phi[a], __ldg(S.lam_p + a * NMO + b), s);
-          t[b] = s;
-        }
-        double acc = 0;
-        for (int j = 0; j < Nd; ++j) {
-          double s = 0;
-#pragma unroll
-          for (int b = 0; b < NMO; ++b) s = fma(t[b], SPHI(N + j, b), s);
-          dvec[j] = s - SG(k, j);
-          acc = fma(dvec[j], SGI(j, k), acc);
-        }
-        for (int q = 0; q < S.n_unp; ++q) {
-          double s = 0;
-#pragma unroll
-          for (int a = 0; a < NMO; ++a) s = fma(phi[a], __ldg(S.lam_u + a * S.n_unp + q), s);
-          dvec[Nd + q] = s - SG(k, Nd + q);
-          acc = fma(dvec[Nd + q], SGI(Nd + q, k), acc);
-        }
-        Det = 1.0 + acc;
-      } else {
-        const int k = ke - N;
-        double t[NMO];
-#pragma unroll
-        for (int a = 0; a < NMO; ++a) {
-          double s = 0;
-#pragma unroll
-          for (int b = 0; b < NMO; ++b) s = fma(__ldg(S.lam_p + a * NMO + b), phi[b], s);
-          t[a] = s;
-        }
-        double acc = 0;
-        for (int i = 0; i < N; ++i) {
-          double s = 0;
-#pragma unroll
-          for (int a = 0; a < NMO; ++a) s = fma(SPHI(i, a), t[a], s);
-          dvec[i] = s - SG(i, k);
-          acc = fma(SGI(k, i), dvec[i], acc);
-        }
-        Det = 1.0 + acc;
-      }
-      const double T_ratio = s_TJ[lane], J_ratio = s_TJ[32 + lane];
-      // AS regularisation of the proposed state without materialising it
-      double R_AS_ratio = 1.0, R_AS_p = R_AS_cur;
-      if (P.eps_AS > 0.0) {
-        double F = 0, Smin = 1e300;
-        if (up) {
-          const int k = ke;
-          // Ginv' = Ginv - Ginv[:,k] (v^T Ginv) / Det
-          for (int jp = 0; jp < N; ++jp) {
-            double vt = 0;
-            for (int j = 0; j < N; ++j) vt = fma(dvec[j], SGI(j, jp), vt);
-            vt /= Det;
-            for (int i = 0; i < N; ++i) {
-              const double x = SGI(i, jp) - SGI(i, k) * vt;
-              F = fma(x, x, F);
-            }
-          }
-          for (int i = 0; i < N; ++i) {
-            double r = 0, c = 0;
-            for (int j = 0; j < N; ++j) {
-              const double gij = SG(i, j) + (i == k ? dvec[j] : 0.0);
-              const double gji = SG(j, i) + (j == k ? dvec[i] : 0.0);
-              r = fma(gij, gij, r);
-              c = fma(gji, gji, c);
-            }
-            Smin = fmin(Smin, fmin(r, c));
-          }
-        } else {
-          const int k = ke - N;
-          // Ginv' = Ginv - (Ginv u) Ginv[k,:] / Det
-          for (int i = 0; i < N; ++i) {
-            double au = 0;
-            for (int j = 0; j < N; ++j) au = fma(SGI(i, j), dvec[j], au);
-            au /= Det;
-            for (int j = 0; j < N; ++j) {
-              const double x = SGI(i, j) - au * SGI(k, j);
-              F = fma(x, x, F);
-            }
-          }
-          for (int i = 0; i < N; ++i) {
-            double r = 0, c = 0;
-            for (int j = 0; j < N; ++j) {
-              const double gij = SG(i, j) + (j == k ? dvec[i] : 0.0);
-              const double gji = SG(j, i) + (i == k ? dvec[j] : 0.0);
-              r = fma(gij, gij, r);
-              c = fma(gji, gji, c);
-            }
-            Smin = fmin(Smin, fmin(r, c));
-          }
-        }
-        const double SF = Smin * F;
-        R_AS_p = SF > 0.0 ? pow(SF, -0.375) : 0.0;
-        R_AS_ratio = (fmax(R_AS_p, P.eps_AS) / R_AS_p) / (fmax(R_AS_cur, P.eps_AS) / R_AS_cur);
-      }
-      const double wr = R_AS_ratio * J_ratio * Det;
-      const double x = wr * wr * T_ratio;
-      const double b = P.rb[ridx];
-      const bool ok = (x == x) && (b < fmin(1.0, x)) && (Det != 0.0);
-      if (ok) {
-        ++n_acc;
-        R_AS_cur = R_AS_p;
-        SR(ke, 0) = nx;
-        SR(ke, 1) = ny;
-        SR(ke, 2) = nz;
-#pragma unroll
-        for (int mo = 0; mo < NMO; ++mo) SPHI(ke, mo) = phi[mo];
-        const double invD = 1.0 / Det;
-        if (up) {
-          const int k = ke;
-          double col[8], vt[8];
-          for (int i = 0; i < N; ++i) col[i] = SGI(i, k);
-          for (int jp = 0; jp < N; ++jp) {
-            double s = 0;
-            for (int j = 0; j < N; ++j) s = fma(dvec[j], SGI(j, jp), s);
-            vt[jp] = s;
-          }
-          for (int i = 0; i < N; ++i)
-            for (int jp = 0; jp < N; ++jp) SGI(i, jp) = SGI(i, jp) - (col[i] * vt[jp]) * invD;
-          for (int j = 0; j < N; ++j) SG(k, j) += dvec[j];
-        } else {
-          const int k = ke - N;
-          double au[8], row[8];
-          for (int i = 0; i < N; ++i) {
-            double s = 0;
-            for (int j = 0; j < N; ++j) s = fma(SGI(i, j), dvec[j], s);
-            au[i] = s;
-          }
-          for (int j = 0; j < N; ++j) row[j] = SGI(k, j);
-          for (int i = 0; i < N; ++i)
-            for (int j = 0; j < N; ++j) SGI(i, j) = SGI(i, j) - (au[i] * row[j]) * invD;
-          for (int i = 0; i < N; ++i) SG(i, k) += dvec[i];
-        }
-      } else {
-        ++n_rej;
-      }
-    }
-    __syncthreads();
-  }
-
-  // ---- write back ---------------------------------------------------------------------------------
-  if (live) {
-    for (int idx = wid; idx < Ne * 3; idx += nch + 1) {
-      const int e = idx / 3, c = idx % 3;
-      if (e < N) P.r_up[((size_t)w * N + e) * 3 + c] = SR(e, c);
-      else P.r_dn[((size_t)w * Nd + (e - N)) * 3 + c] = SR(e, c);
-    }
-    for (int idx = wid; idx < NN2; idx += nch + 1) {
-      P.G[(size_t)w * NN2 + idx] = s_G[idx * 32 + lane];
-      P.Ginv[(size_t)w * NN2 + idx] = s_Gi[idx * 32 + lane];
-    }
-    if (wid == 0) {
-      P.acc[w] = n_acc;
-      P.rej[w] = n_rej;
-    }
-  }
-#undef SR
-#undef SG
-#undef SGI
-#undef SPHI
-#undef SPART
-}
-
-// =================================================================================================
 // fp64 peak microbenchmark
 // =================================================================================================
 __global__ void k_dfma_peak(int iters, double* out) {
@@ -1318,6 +691,9 @@ __global__ void k_dfma_peak(int iters, double* out) {
   }
   if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
 }
+
+int qe_local_energy_fused(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,
+                          double* e_L, double* T_elem, double* V_parts, cudaStream_t st);  // qe_walker.cu
 
 // =================================================================================================
 // C ABI
@@ -1499,6 +875,11 @@ extern "C" int qe_create(const qe_system_desc* d, qe_engine** out) {
 }
 
 extern "C" int64_t qe_launch_count(qe_engine* h) { return h ? h->launches : 0; }
+extern "C" int qe_set_fused(qe_engine* h, int on) {
+  if (!h) return fail(QE_ERR_INVALID, "qe_set_fused: null engine");
+  h->fused = on != 0;
+  return QE_OK;
+}
 
 static void prof_clear(qe_engine* h) {
   for (auto& r : h->prof) {
@@ -1532,31 +913,6 @@ extern "C" int qe_profile_read(qe_engine* h, int id, double* total_ms, int64_t* 
   return QE_OK;
 }
 
-#define DISPATCH_NMO_CART(h, CALL)                                  \
-  do {                                                              \
-    const bool cart_ = (h)->b_up.dev.cart != 0;                     \
-    switch ((h)->nmo_pad) {                                         \
-      case 4: if (cart_) { CALL(4, true); } else { CALL(4, false); } break;   \
-      case 8: if (cart_) { CALL(8, true); } else { CALL(8, false); } break;   \
-      default: if (cart_) { CALL(16, true); } else { CALL(16, false); } break; \
-    }                                                               \
-  } while (0)
-#define DISPATCH_NMO(h, CALL)       \
-  do {                              \
-    switch ((h)->nmo_pad) {         \
-      case 4: CALL(4); break;       \
-      case 8: CALL(8); break;       \
-      default: CALL(16); break;     \
-    }                               \
-  } while (0)
-
-static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
-#define CHECK_LAUNCH()                                                                    \
-  do {                                                                                    \
-    cudaError_t e_ = cudaGetLastError();                                                  \
-    if (e_ != cudaSuccess) return fail(QE_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
-  } while (0)
-
 extern "C" int qe_eval_orbitals(qe_engine* h, int which, int layer, int n_pts, const double* r, double* out, void* stream) {
   if (!h || !r || !out || n_pts <= 0) return fail(QE_ERR_INVALID, "qe_eval_orbitals: bad argument");
   HostBasis* hb = which == 0 ? &h->b_up : which == 1 ? &h->b_dn : &h->b_j3;
@@ -1580,19 +936,6 @@ extern "C" int qe_eval_orbitals(qe_engine* h, int which, int layer, int n_pts, c
   CHECK_LAUNCH();
   return QE_OK;
 }
-
-// workspace carve-up helper
-struct WsCarve {
-  char* base;
-  size_t off = 0;
-  template <class T>
-  T* take(size_t n) {
-    off = (off + 255) & ~size_t(255);
-    T* p = (T*)(base + off);
-    off += n * sizeof(T);
-    return p;
-  }
-};
 
 static size_t ws_need_common(const qe_engine* h, int nw, int n_chunk, int nq) {
   const SysDev& S = h->sys;
@@ -1669,21 +1012,16 @@ extern "C" int qe_as_factor(qe_engine* h, int nw, const double* G, const double*
   return QE_OK;
 }
 
-extern "C" int qe_rotation(qe_engine* h, int nw, const uint32_t* keys, double* RT, void* stream) {
-  if (!h || nw <= 0 || !keys || !RT) return fail(QE_ERR_INVALID, "qe_rotation: bad argument");
-  { LaunchScope ls_(h, K_ROT, (cudaStream_t)stream);
-  k_rotation<<<nblk(nw, 128), 128, 0, (cudaStream_t)stream>>>(nw, keys, RT);
-  }
-  CHECK_LAUNCH();
-  return QE_OK;
-}
-
 extern "C" int qe_local_energy(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,
                                double* e_L, double* T_elem, double* V_parts, void* stream) {
   if (!h || nw <= 0 || !r_up || !Ginv || !e_L || (!r_dn && h->sys.n_dn > 0)) return fail(QE_ERR_INVALID, "qe_local_energy: bad argument");
   if (h->sys.ecp_flag && !RT) return fail(QE_ERR_INVALID, "qe_local_energy: RT required for ECP systems");
   cudaStream_t st = (cudaStream_t)stream;
   const SysDev& S = h->sys;
+  if (h->fused) {
+    const int frc = qe_local_energy_fused(h, nw, r_up, r_dn, RT, Ginv, e_L, T_elem, V_parts, st);
+    if (frc != QE_ERR_UNSUPPORTED) return frc;
+  }
   const int nch = h->n_chunk_el, P = h->nmo_pad;
   int rc = ensure_ws(h, ws_need_common(h, nw, nch, 5));
   if (rc) return rc;
@@ -1769,58 +1107,6 @@ extern "C" int qe_move_ratios(qe_engine* h, int nw, const double* r_up, const do
   }
   CHECK_LAUNCH();
   return QE_OK;
-}
-
-extern "C" int qe_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, uint32_t* keys, double* G, double* Ginv, int nmpm,
-                              double Dt, double epsilon_AS, int32_t* acc, int32_t* rej, void* stream) {
-  if (!h || nw <= 0 || nmpm < 0 || !r_up || !keys || !G || !Ginv || !acc || !rej || (!r_dn && h->sys.n_dn > 0))
-    return fail(QE_ERR_INVALID, "qe_mcmc_update: bad argument");
-  const SysDev& S = h->sys;
-  if (S.n_up > 8) return fail(QE_ERR_UNSUPPORTED, "qe_mcmc_update: more than 8 electrons per spin is not implemented in this build");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int P = h->nmo_pad, nch = h->n_chunk_mc;
-  const size_t n_draw = (size_t)std::max(1, nmpm) * nw;
-  int rc = ensure_ws(h, n_draw * (6 * 8 + 4 + 4 + 8 + 8) + 4096);
-  if (rc) return rc;
-  WsCarve c{(char*)h->ws};
-  uint2* sub = c.take<uint2>(n_draw * 6);
-  int* rsel = c.take<int>(n_draw);
-  int* raxis = c.take<int>(n_draw);
-  double* rg = c.take<double>(n_draw);
-  double* rb = c.take<double>(n_draw);
-  if (nmpm > 0) {
-    { LaunchScope ls_(h, K_KEYCHAIN, st);
-    k_mcmc_keychain<<<nblk(nw, 64), 64, 0, st>>>(nw, nmpm, keys, sub);
-    }
-    CHECK_LAUNCH();
-    { LaunchScope ls_(h, K_DRAWS, st);
-    k_mcmc_draws<<<nblk((long long)nmpm * nw, 128), 128, 0, st>>>(nw, nmpm, S.n_up, S.n_dn, sub, rsel, raxis, rg, rb);
-    }
-    CHECK_LAUNCH();
-  }
-  McmcArgs A{nw, nmpm, nch, Dt, epsilon_AS, r_up, r_dn, G, Ginv, acc, rej, rsel, raxis, rg, rb, h->d_chunk_mc};
-  const size_t smem = (size_t)(S.n_e * 3 + 2 * S.n_up * S.n_up + S.n_e * P + nch * P + 2) * 32 * 8;
-  dim3 block(32, nch + 1);
-  { LaunchScope ls_(h, K_MCMC, st);
-#define CALL(NMO, CART)                                                                                           \
-  do {                                                                                                            \
-    CUDA_TRY(cudaFuncSetAttribute(k_mcmc<NMO, CART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    k_mcmc<NMO, CART><<<nblk(nw, 32), block, smem, st>>>(h->b_up.dev, h->b_dn.dev, S, A);                         \
-  } while (0)
-  DISPATCH_NMO_CART(h, CALL);
-#undef CALL
-  }
-  CHECK_LAUNCH();
-  return QE_OK;
-}
-
-extern "C" int qe_lrdmc_project(qe_engine*, int, double*, double*, double*, double*, uint32_t*, double, int, int, int, double, double*,
-                                double*, double*, void*) {
-  return fail(QE_ERR_UNSUPPORTED, "qe_lrdmc_project: not implemented in this build");
-}
-extern "C" int qe_lrdmc_velements(qe_engine*, int, const double*, const double*, const double*, const double*, int, double, double*,
-                                  double*, void*) {
-  return fail(QE_ERR_UNSUPPORTED, "qe_lrdmc_velements: not implemented in this build");
 }
 
 extern "C" int qe_measure_fp64_peak(int iters, double* tflops) {

@@ -1,0 +1,445 @@
+// Metropolis step of the VMC driver: jax.random-compatible draws, rotation matrices and the k_mcmc kernel.
+#include "qe_common.cuh"
+
+// =================================================================================================
+// RNG kernels (semantics: oracle/jaxrng.py; call sites jqmc/jqmc_mcmc.py:4322-4367, 4499-4500, 4232-4233)
+// =================================================================================================
+// rotation matrix RT = R^T from split(key)[1], key not advanced (jqmc/jqmc_mcmc.py:4228-4245)
+__device__ __forceinline__ void rotation_RT(double al, double be, double ga, double* __restrict__ o) {
+  double sa, ca, sb, cb, sg, cg;
+  sincos(al, &sa, &ca);
+  sincos(be, &sb, &cb);
+  sincos(ga, &sg, &cg);
+  // R rows; store transposed
+  const double R00 = cb * cg, R01 = cg * sa * sb - ca * sg, R02 = sa * sg + ca * cg * sb;
+  const double R10 = cb * sg, R11 = ca * cg + sa * sb * sg, R12 = ca * sb * sg - cg * sa;
+  const double R20 = -sb, R21 = cb * sa, R22 = ca * cb;
+  o[0] = R00; o[1] = R10; o[2] = R20;
+  o[3] = R01; o[4] = R11; o[5] = R21;
+  o[6] = R02; o[7] = R12; o[8] = R22;
+}
+__global__ void k_rotation(int nw, const uint32_t* __restrict__ keys, double* __restrict__ RT) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  Key k{keys[2 * w], keys[2 * w + 1]};
+  const Key sub = threefry(k, 0u, 1u);
+  const double two_pi = 6.283185307179586;
+  const double al = rng_uniform_bits(rng_bits64(sub, 0u), -two_pi, two_pi);
+  const double be = rng_uniform_bits(rng_bits64(sub, 1u), -two_pi, two_pi);
+  const double ga = rng_uniform_bits(rng_bits64(sub, 2u), -two_pi, two_pi);
+  rotation_RT(al, be, ga, RT + (size_t)w * 9);
+}
+
+// key chain of the Metropolis loop: 6 splits per proposal.  thread = walker.  sub[(p*6+i)][w]
+__global__ void k_mcmc_keychain(int nw, int nmpm, uint32_t* __restrict__ keys, uint2* __restrict__ sub) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  Key k{keys[2 * w], keys[2 * w + 1]};
+  for (int p = 0; p < nmpm * 6; ++p) {
+    Key s;
+    rng_split(k, s);
+    sub[(size_t)p * nw + w] = make_uint2(s.a, s.b);
+  }
+  keys[2 * w] = k.a;
+  keys[2 * w + 1] = k.b;
+}
+// draws of every proposal: thread = (proposal, walker)
+__global__ void k_mcmc_draws(int nw, int nmpm, int n_up, int n_dn, const uint2* __restrict__ sub, int* __restrict__ rsel,
+                             int* __restrict__ raxis, double* __restrict__ rg, double* __restrict__ rb) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nmpm * nw) return;
+  const int w = (int)(t % nw);
+  const int p = (int)(t / nw);
+  auto K = [&](int i) {
+    const uint2 v = sub[((size_t)p * 6 + i) * nw + w];
+    return Key{v.x, v.y};
+  };
+  const bool is_up = rng_randint(K(0), (uint32_t)(n_up + n_dn)) < n_up;
+  const int iu = rng_randint(K(1), (uint32_t)n_up);
+  const int id = rng_randint(K(2), (uint32_t)n_dn);
+  rsel[t] = is_up ? iu : n_up + id;
+  rg[t] = rng_normal(K(3));
+  raxis[t] = rng_randint(K(4), 3u);
+  rb[t] = rng_uniform_bits(rng_bits64(K(5)), 0.0, 1.0);
+}
+
+// =================================================================================================
+// Metropolis kernel (jqmc/jqmc_mcmc.py:4278-4533).  CTA = 32 walkers (lanes) x (n_chunk + 1) warps.
+//   warps 0..n_chunk-1 : AO/MO evaluation of one basis chunk at the proposed position
+//   warp  n_chunk      : proposal bookkeeping, T_ratio and Jastrow ratio
+//   warp  0            : determinant ratio, Sherman-Morrison update, AS factor, accept/reject
+// Walker state lives in shared memory as [item][lane].
+// =================================================================================================
+struct McmcArgs {
+  int nw, nmpm, n_chunk;
+  double Dt, eps_AS;
+  double* r_up;
+  double* r_dn;
+  double* G;
+  double* Ginv;
+  int* acc;
+  int* rej;
+  const int* rsel;
+  const int* raxis;
+  const double* rg;
+  const double* rb;
+  const int* chunk_begin;
+};
+
+template <int NMO, bool CART>
+__global__ void __launch_bounds__(512)
+k_mcmc(BasisDev Bu, BasisDev Bd, SysDev S, McmcArgs P) {
+  extern __shared__ double sm[];
+  const int lane = threadIdx.x, wid = threadIdx.y;
+  const int w = blockIdx.x * 32 + lane;
+  const bool live = w < P.nw;
+  const int ww = live ? w : P.nw - 1;  // dead lanes shadow the last walker (no stores)
+  const int N = S.n_up, Nd = S.n_dn, Ne = S.n_e, NN2 = N * N;
+  const int nch = P.n_chunk;
+  // shared-memory carve-up (all [item][32])
+  double* s_r = sm;                       // Ne*3
+  double* s_G = s_r + Ne * 3 * 32;        // N*N
+  double* s_Gi = s_G + NN2 * 32;          // N*N
+  double* s_phi = s_Gi + NN2 * 32;        // Ne*NMO   (orbital values at the electrons: [e][mo])
+  double* s_part = s_phi + Ne * NMO * 32; // nch*NMO
+  double* s_TJ = s_part + nch * NMO * 32; // 2: T_ratio, J_ratio
+#define SR(e, c) s_r[((e) * 3 + (c)) * 32 + lane]
+#define SG(i, j) s_G[((i) * N + (j)) * 32 + lane]
+#define SGI(i, j) s_Gi[((i) * N + (j)) * 32 + lane]
+#define SPHI(e, mo) s_phi[((e) * NMO + (mo)) * 32 + lane]
+#define SPART(c, mo) s_part[((c) * NMO + (mo)) * 32 + lane]
+
+  // ---- load state -------------------------------------------------------------------------------
+  const int tid = wid * 32 + lane, nthr = 32 * (nch + 1);
+  for (int idx = wid; idx < Ne * 3; idx += nch + 1) {
+    const int e = idx / 3, c = idx % 3;
+    SR(e, c) = e < N ? P.r_up[((size_t)ww * N + e) * 3 + c] : P.r_dn[((size_t)ww * Nd + (e - N)) * 3 + c];
+  }
+  for (int idx = wid; idx < NN2; idx += nch + 1) {
+    s_G[idx * 32 + lane] = P.G[(size_t)ww * NN2 + idx];
+    s_Gi[idx * 32 + lane] = P.Ginv[(size_t)ww * NN2 + idx];
+  }
+  (void)tid;
+  (void)nthr;
+  __syncthreads();
+
+  // ---- orbital values at every electron (cache for the row/column rebuild) -----------------------
+  for (int e = 0; e < Ne; ++e) {
+    if (wid < nch) {
+      const BasisDev& B = e < N ? Bu : Bd;
+      SinkMO<NMO> sink;
+      sink.init(B.Cs);
+      eval_val<CART>(B, S.Rn, SR(e, 0), SR(e, 1), SR(e, 2), P.chunk_begin[wid], P.chunk_begin[wid + 1], sink);
+#pragma unroll
+      for (int mo = 0; mo < NMO; ++mo) SPART(wid, mo) = sink.acc[mo];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+      for (int mo = 0; mo < NMO; ++mo) {
+        double s = 0;
+        for (int c = 0; c < nch; ++c) s += SPART(c, mo);
+        SPHI(e, mo) = s;
+      }
+    }
+    __syncthreads();
+  }
+
+  int n_acc = 0, n_rej = 0;
+  double R_AS_cur = 1.0;
+  if (wid == 0 && P.eps_AS > 0.0) {
+    double F = 0, Smin = 1e300;
+    for (int i = 0; i < NN2; ++i) F = fma(s_Gi[i * 32 + lane], s_Gi[i * 32 + lane], F);
+    for (int i = 0; i < N; ++i) {
+      double r = 0, c = 0;
+      for (int j = 0; j < N; ++j) {
+        r = fma(SG(i, j), SG(i, j), r);
+        c = fma(SG(j, i), SG(j, i), c);
+      }
+      Smin = fmin(Smin, fmin(r, c));
+    }
+    const double SF = Smin * F;
+    R_AS_cur = SF > 0.0 ? pow(SF, -0.375) : 0.0;
+  }
+
+  for (int it = 0; it < P.nmpm; ++it) {
+    // ---- phase A: proposal (every thread, redundantly; lane = walker) ----------------------------
+    const size_t ridx = (size_t)it * P.nw + ww;
+    const int ke = P.rsel[ridx];
+    const int axis = P.raxis[ridx];
+    const bool up = ke < N;
+    const double ox = SR(ke, 0), oy = SR(ke, 1), oz = SR(ke, 2);
+    double dist;
+    int ia = nearest_atom(S.Rn, S.n_atom, ox, oy, oz, 0, &dist);
+    double Zc = S.Zeff[ia];
+    const double f_l = 1.0 / (Zc * Zc) * (1.0 + Zc * Zc * dist) / (1.0 + dist);
+    const double g = P.rg[ridx] * (f_l * P.Dt);
+    double nx = ox, ny = oy, nz = oz;
+    if (axis == 0) nx = ox + g;
+    else if (axis == 1) ny = oy + g;
+    else nz = oz + g;
+
+    // ---- phase B ---------------------------------------------------------------------------------
+    if (wid < nch) {
+      // same AO tables for both spins (checked at create); the MO coefficients may differ per lane
+      SinkMO<NMO> sink;
+      sink.init(up ? Bu.Cs : Bd.Cs);
+      eval_val<CART>(Bu, S.Rn, nx, ny, nz, P.chunk_begin[wid], P.chunk_begin[wid + 1], sink);
+#pragma unroll
+      for (int mo = 0; mo < NMO; ++mo) SPART(wid, mo) = sink.acc[mo];
+    } else {
+      ia = nearest_atom(S.Rn, S.n_atom, nx, ny, nz, 0, &dist);
+      Zc = S.Zeff[ia];
+      const double f_p = 1.0 / (Zc * Zc) * (1.0 + Zc * Zc * dist) / (1.0 + dist);
+      const double dd = (nx - ox) * (nx - ox) + (ny - oy) * (ny - oy) + (nz - oz) * (nz - oz);
+      const double T_ratio =
+          (f_l / f_p) * exp(-dd * (1.0 / (2.0 * f_p * f_p * P.Dt * P.Dt) - 1.0 / (2.0 * f_l * f_l * P.Dt * P.Dt)));
+      struct PosS {
+        const double* s_r;
+        int lane;
+        __device__ __forceinline__ void get(int e, double& x, double& y, double& z) const {
+          x = s_r[(e * 3 + 0) * 32 + lane];
+          y = s_r[(e * 3 + 1) * 32 + lane];
+          z = s_r[(e * 3 + 2) * 32 + lane];
+        }
+      } pos{s_r, lane};
+      const double J_ratio = exp(jastrow_delta(S, pos, ke, ox, oy, oz, nx, ny, nz));
+      s_TJ[lane] = T_ratio;
+      s_TJ[32 + lane] = J_ratio;
+    }
+    __syncthreads();
+
+    // ---- phase C: warp 0 -------------------------------------------------------------------------
+    if (wid == 0) {
+      double phi[NMO];
+#pragma unroll
+      for (int mo = 0; mo < NMO; ++mo) {
+        double s = 0;
+        for (int c = 0; c < nch; ++c) s += SPART(c, mo);
+        phi[mo] = s;
+      }
+      // v (row difference) or u (column difference), Det_ratio = 1 + v^T Ginv u
+      double dvec[8 > NMO ? 8 : NMO];  // N <= 8 enforced on the host for this kernel
+      double Det;
+      if (up) {
+        const int k = ke;
+        double t[NMO];
+#pragma unroll
+        for (int b = 0; b < NMO; ++b) {
+          double s = 0;
+#pragma unroll
+          for (int a = 0; a < NMO; ++a) s = fma(phi[a], S.lam_p[a * NMO + b], s);
+          t[b] = s;
+        }
+        double acc = 0;
+        for (int j = 0; j < Nd; ++j) {
+          double s = 0;
+#pragma unroll
+          for (int b = 0; b < NMO; ++b) s = fma(t[b], SPHI(N + j, b), s);
+          dvec[j] = s - SG(k, j);
+          acc = fma(dvec[j], SGI(j, k), acc);
+        }
+        for (int q = 0; q < S.n_unp; ++q) {
+          double s = 0;
+#pragma unroll
+          for (int a = 0; a < NMO; ++a) s = fma(phi[a], S.lam_u[a * S.n_unp + q], s);
+          dvec[Nd + q] = s - SG(k, Nd + q);
+          acc = fma(dvec[Nd + q], SGI(Nd + q, k), acc);
+        }
+        Det = 1.0 + acc;
+      } else {
+        const int k = ke - N;
+        double t[NMO];
+#pragma unroll
+        for (int a = 0; a < NMO; ++a) {
+          double s = 0;
+#pragma unroll
+          for (int b = 0; b < NMO; ++b) s = fma(S.lam_p[a * NMO + b], phi[b], s);
+          t[a] = s;
+        }
+        double acc = 0;
+        for (int i = 0; i < N; ++i) {
+          double s = 0;
+#pragma unroll
+          for (int a = 0; a < NMO; ++a) s = fma(SPHI(i, a), t[a], s);
+          dvec[i] = s - SG(i, k);
+          acc = fma(SGI(k, i), dvec[i], acc);
+        }
+        Det = 1.0 + acc;
+      }
+      const double T_ratio = s_TJ[lane], J_ratio = s_TJ[32 + lane];
+      // AS regularisation of the proposed state without materialising it
+      double R_AS_ratio = 1.0, R_AS_p = R_AS_cur;
+      if (P.eps_AS > 0.0) {
+        double F = 0, Smin = 1e300;
+        if (up) {
+          const int k = ke;
+          // Ginv' = Ginv - Ginv[:,k] (v^T Ginv) / Det
+          for (int jp = 0; jp < N; ++jp) {
+            double vt = 0;
+            for (int j = 0; j < N; ++j) vt = fma(dvec[j], SGI(j, jp), vt);
+            vt /= Det;
+            for (int i = 0; i < N; ++i) {
+              const double x = SGI(i, jp) - SGI(i, k) * vt;
+              F = fma(x, x, F);
+            }
+          }
+          for (int i = 0; i < N; ++i) {
+            double r = 0, c = 0;
+            for (int j = 0; j < N; ++j) {
+              const double gij = SG(i, j) + (i == k ? dvec[j] : 0.0);
+              const double gji = SG(j, i) + (j == k ? dvec[i] : 0.0);
+              r = fma(gij, gij, r);
+              c = fma(gji, gji, c);
+            }
+            Smin = fmin(Smin, fmin(r, c));
+          }
+        } else {
+          const int k = ke - N;
+          // Ginv' = Ginv - (Ginv u) Ginv[k,:] / Det
+          for (int i = 0; i < N; ++i) {
+            double au = 0;
+            for (int j = 0; j < N; ++j) au = fma(SGI(i, j), dvec[j], au);
+            au /= Det;
+            for (int j = 0; j < N; ++j) {
+              const double x = SGI(i, j) - au * SGI(k, j);
+              F = fma(x, x, F);
+            }
+          }
+          for (int i = 0; i < N; ++i) {
+            double r = 0, c = 0;
+            for (int j = 0; j < N; ++j) {
+              const double gij = SG(i, j) + (j == k ? dvec[i] : 0.0);
+              const double gji = SG(j, i) + (i == k ? dvec[j] : 0.0);
+              r = fma(gij, gij, r);
+              c = fma(gji, gji, c);
+            }
+            Smin = fmin(Smin, fmin(r, c));
+          }
+        }
+        const double SF = Smin * F;
+        R_AS_p = SF > 0.0 ? pow(SF, -0.375) : 0.0;
+        R_AS_ratio = (fmax(R_AS_p, P.eps_AS) / R_AS_p) / (fmax(R_AS_cur, P.eps_AS) / R_AS_cur);
+      }
+      const double wr = R_AS_ratio * J_ratio * Det;
+      const double x = wr * wr * T_ratio;
+      const double b = P.rb[ridx];
+      const bool ok = (x == x) && (b < fmin(1.0, x)) && (Det != 0.0);
+      if (ok) {
+        ++n_acc;
+        R_AS_cur = R_AS_p;
+        SR(ke, 0) = nx;
+        SR(ke, 1) = ny;
+        SR(ke, 2) = nz;
+#pragma unroll
+        for (int mo = 0; mo < NMO; ++mo) SPHI(ke, mo) = phi[mo];
+        const double invD = 1.0 / Det;
+        if (up) {
+          const int k = ke;
+          double col[8], vt[8];
+          for (int i = 0; i < N; ++i) col[i] = SGI(i, k);
+          for (int jp = 0; jp < N; ++jp) {
+            double s = 0;
+            for (int j = 0; j < N; ++j) s = fma(dvec[j], SGI(j, jp), s);
+            vt[jp] = s;
+          }
+          for (int i = 0; i < N; ++i)
+            for (int jp = 0; jp < N; ++jp) SGI(i, jp) = SGI(i, jp) - (col[i] * vt[jp]) * invD;
+          for (int j = 0; j < N; ++j) SG(k, j) += dvec[j];
+        } else {
+          const int k = ke - N;
+          double au[8], row[8];
+          for (int i = 0; i < N; ++i) {
+            double s = 0;
+            for (int j = 0; j < N; ++j) s = fma(SGI(i, j), dvec[j], s);
+            au[i] = s;
+          }
+          for (int j = 0; j < N; ++j) row[j] = SGI(k, j);
+          for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) SGI(i, j) = SGI(i, j) - (au[i] * row[j]) * invD;
+          for (int i = 0; i < N; ++i) SG(i, k) += dvec[i];
+        }
+      } else {
+        ++n_rej;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- write back ---------------------------------------------------------------------------------
+  if (live) {
+    for (int idx = wid; idx < Ne * 3; idx += nch + 1) {
+      const int e = idx / 3, c = idx % 3;
+      if (e < N) P.r_up[((size_t)w * N + e) * 3 + c] = SR(e, c);
+      else P.r_dn[((size_t)w * Nd + (e - N)) * 3 + c] = SR(e, c);
+    }
+    for (int idx = wid; idx < NN2; idx += nch + 1) {
+      P.G[(size_t)w * NN2 + idx] = s_G[idx * 32 + lane];
+      P.Ginv[(size_t)w * NN2 + idx] = s_Gi[idx * 32 + lane];
+    }
+    if (wid == 0) {
+      P.acc[w] = n_acc;
+      P.rej[w] = n_rej;
+    }
+  }
+#undef SR
+#undef SG
+#undef SGI
+#undef SPHI
+#undef SPART
+}
+
+
+extern "C" int qe_rotation(qe_engine* h, int nw, const uint32_t* keys, double* RT, void* stream) {
+  if (!h || nw <= 0 || !keys || !RT) return fail(QE_ERR_INVALID, "qe_rotation: bad argument");
+  { LaunchScope ls_(h, K_ROT, (cudaStream_t)stream);
+  k_rotation<<<nblk(nw, 128), 128, 0, (cudaStream_t)stream>>>(nw, keys, RT);
+  }
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+
+
+extern "C" int qe_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, uint32_t* keys, double* G, double* Ginv, int nmpm,
+                              double Dt, double epsilon_AS, int32_t* acc, int32_t* rej, void* stream) {
+  if (!h || nw <= 0 || nmpm < 0 || !r_up || !keys || !G || !Ginv || !acc || !rej || (!r_dn && h->sys.n_dn > 0))
+    return fail(QE_ERR_INVALID, "qe_mcmc_update: bad argument");
+  const SysDev& S = h->sys;
+  if (S.n_up > 8) return fail(QE_ERR_UNSUPPORTED, "qe_mcmc_update: more than 8 electrons per spin is not implemented in this build");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = h->nmo_pad, nch = h->n_chunk_mc;
+  const size_t n_draw = (size_t)std::max(1, nmpm) * nw;
+  int rc = ensure_ws(h, n_draw * (6 * 8 + 4 + 4 + 8 + 8) + 4096);
+  if (rc) return rc;
+  WsCarve c{(char*)h->ws};
+  uint2* sub = c.take<uint2>(n_draw * 6);
+  int* rsel = c.take<int>(n_draw);
+  int* raxis = c.take<int>(n_draw);
+  double* rg = c.take<double>(n_draw);
+  double* rb = c.take<double>(n_draw);
+  if (nmpm > 0) {
+    { LaunchScope ls_(h, K_KEYCHAIN, st);
+    k_mcmc_keychain<<<nblk(nw, 64), 64, 0, st>>>(nw, nmpm, keys, sub);
+    }
+    CHECK_LAUNCH();
+    { LaunchScope ls_(h, K_DRAWS, st);
+    k_mcmc_draws<<<nblk((long long)nmpm * nw, 128), 128, 0, st>>>(nw, nmpm, S.n_up, S.n_dn, sub, rsel, raxis, rg, rb);
+    }
+    CHECK_LAUNCH();
+  }
+  McmcArgs A{nw, nmpm, nch, Dt, epsilon_AS, r_up, r_dn, G, Ginv, acc, rej, rsel, raxis, rg, rb, h->d_chunk_mc};
+  const size_t smem = (size_t)(S.n_e * 3 + 2 * S.n_up * S.n_up + S.n_e * P + nch * P + 2) * 32 * 8;
+  dim3 block(32, nch + 1);
+  { LaunchScope ls_(h, K_MCMC, st);
+#define CALL(NMO, CART)                                                                                           \
+  do {                                                                                                            \
+    CUDA_TRY(cudaFuncSetAttribute(k_mcmc<NMO, CART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    k_mcmc<NMO, CART><<<nblk(nw, 32), block, smem, st>>>(h->b_up.dev, h->b_dn.dev, S, A);                         \
+  } while (0)
+  DISPATCH_NMO_CART(h, CALL);
+#undef CALL
+  }
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+

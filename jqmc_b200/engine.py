@@ -330,6 +330,59 @@ class WalkerEngine:
         torch.cuda.current_stream(self.device).synchronize()  # elec is a host buffer
         return dr, jr
 
+    def set_fused(self, on: bool):
+        """Fused (one kernel, shared-memory resident) vs staged (kernel chain) local energy; same results."""
+        _lib.check(self._lib.qe_set_fused(self._h, 1 if on else 0), "qe_set_fused")
+
+    # ---- LRDMC (GFMC_n) seams: jqmc/jqmc_gfmc.py:4716, 5656-5663 ------------------------------------
+    _NLM = {"tmove": 0, "dltmove": 1}
+
+    def A_inv_n(self, r_up, r_dn):
+        """``_jit_vmap_A_inv_n``: fresh inverse of the geminal matrix per walker."""
+        return self.geminal_inv_batched(r_up, r_dn)[1]
+
+    def projection_n(self, w_L, r_up, r_dn, A_old_inv, keys, E_scf, num_mcmc_per_measurement, random_discretized_mesh,
+                     non_local_move, alat, inplace=False):
+        """``_jit_vmap_projection_n``: returns (w, r_up, r_dn, A_inv, keys, RT, V_diag, V_nondiag)."""
+        r_up, r_dn, nw = self._walkers(r_up, r_dn)
+        keys = self._keys(keys, nw)
+        Ginv = self._mat(A_old_inv, nw, "A_old_inv")
+        w = self._dev(w_L)
+        if w.shape != (nw,):
+            raise ValueError(f"w_L shape {tuple(w.shape)} != ({nw},)")
+        if non_local_move not in self._NLM:
+            raise NotImplementedError(f"non_local_move = {non_local_move} is not yet implemented.")
+        if not inplace:
+            w, r_up, r_dn, keys, Ginv = (t.clone() for t in (w, r_up, r_dn, keys, Ginv))
+        RT = torch.empty((nw, 3, 3), dtype=torch.float64, device=self.device)
+        Vd = torch.empty(nw, dtype=torch.float64, device=self.device)
+        Vn = torch.empty(nw, dtype=torch.float64, device=self.device)
+        rc = self._lib.qe_lrdmc_project(
+            self._h, nw, self._ptr(w), self._ptr(r_up), self._ptr(r_dn), self._ptr(Ginv), self._ptr(keys), float(E_scf),
+            int(num_mcmc_per_measurement), 1 if random_discretized_mesh else 0, self._NLM[non_local_move], float(alat),
+            self._ptr(RT), self._ptr(Vd), self._ptr(Vn), self._stream(),
+        )  # fmt: skip
+        _lib.check(rc, "qe_lrdmc_project")
+        return w, r_up, r_dn, Ginv, keys, RT, Vd, Vn
+
+    def V_elements_n(self, r_up, r_dn, RTs, non_local_move, alat, A_inv=None):
+        """``_jit_vmap_V_elements_n``: (V_diag, V_nondiag); the inverse is rebuilt unless ``A_inv`` is given."""
+        r_up, r_dn, nw = self._walkers(r_up, r_dn)
+        if non_local_move not in self._NLM:
+            raise NotImplementedError(f"non_local_move = {non_local_move} is not yet implemented.")
+        Ginv = self.A_inv_n(r_up, r_dn) if A_inv is None else self._mat(A_inv, nw, "A_inv")
+        RTs = self._dev(RTs)
+        if RTs.shape != (nw, 3, 3):
+            raise ValueError(f"RTs shape {tuple(RTs.shape)} != ({nw}, 3, 3)")
+        Vd = torch.empty(nw, dtype=torch.float64, device=self.device)
+        Vn = torch.empty(nw, dtype=torch.float64, device=self.device)
+        rc = self._lib.qe_lrdmc_velements(
+            self._h, nw, self._ptr(r_up), self._ptr(r_dn), self._ptr(RTs), self._ptr(Ginv), self._NLM[non_local_move],
+            float(alat), self._ptr(Vd), self._ptr(Vn), self._stream(),
+        )  # fmt: skip
+        _lib.check(rc, "qe_lrdmc_velements")
+        return Vd, Vn
+
     def launch_count(self) -> int:
         return int(self._lib.qe_launch_count(self._h))
 

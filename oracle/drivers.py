@@ -248,7 +248,10 @@ def lrdmc_projection(H, w, r_up, r_dn, Ginv, key, E_scf, nmpm, random_discretize
         diag, nondiag, p, moves = lrdmc_elements(H, r_up, r_dn, Ginv, RT, alat, non_local_move)
         b_x = 1.0 / (diag - E_scf) * (-nondiag)
         w = w * b_x
-        cdf = np.cumsum(p / p.sum())
+        tot = 0.0
+        for x in p:  # sequential fp64 sum (the engine's order; jnp.sum leaves the order unspecified)
+            tot += x
+        cdf = np.cumsum(p / tot)
         u = R.uniform(move_keys[i])
         k = min(int(np.searchsorted(cdf, u, side="left")), len(cdf) - 1)
         spin_up, idx, r_new = moves[k]

@@ -299,3 +299,68 @@ def test_mcmc_driver_runs(water):
     m2 = MCMC(H, mcmc_seed=34456, num_walkers=64, num_mcmc_per_measurement=40, Dt=2.0, epsilon_AS=0.0)
     m2.run(num_mcmc_steps=5)
     np.testing.assert_array_equal(m2.e_L, m.e_L[:5])
+
+
+@pytest.mark.parametrize("name,jas", [("water_ccecp_ccpvqz", "j2pade"), ("N2_ecp_ccpvtz_cart", "j1pade_j2pade"), ("Li_ae_ccpvdz_cart", "j2pade"),
+                                      ("H2_ecp_ccpvtz", "j1exp_j2exp")])  # fmt: skip
+def test_local_energy_fused_equals_staged(name, jas):
+    """The fused (one kernel) and staged (kernel chain) local-energy paths agree to round-off."""
+    H = _with_jastrow(load_system(name), jas)
+    eng = _engine(H)
+    nw = 70
+    r_up, r_dn = random_walkers(H, nw, 5)
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    RT = eng.generate_RTs(np.array([[1, i] for i in range(nw)], dtype=np.uint32))
+    eng.set_fused(True)
+    a = [x.cpu().numpy() for x in eng.e_L_fast(r_up, r_dn, RT, Ginv, return_parts=True)]
+    eng.set_fused(False)
+    b = [x.cpu().numpy() for x in eng.e_L_fast(r_up, r_dn, RT, Ginv, return_parts=True)]
+    for x, y in zip(a, b):
+        np.testing.assert_allclose(x, y, rtol=1e-11, atol=1e-11 * np.abs(y).max())
+
+
+@pytest.mark.parametrize("name,jas,nlm", [("water_ccecp_ccpvqz", "j2pade", "tmove"), ("water_ccecp_ccpvqz", "j1exp_j2exp", "dltmove"),
+                                          ("Li_ae_ccpvdz_cart", "j2pade", "tmove"), ("N2_ecp_ccpvtz_cart", "j1pade_j2pade", "tmove"),
+                                          ("H2_ae_ccpvdz_cart", "j1exp_j2exp", "tmove")])  # fmt: skip
+def test_lrdmc_V_elements(name, jas, nlm):
+    """a20, a23-a25, a30: V_diag / V_nondiag of the lattice-regularised Hamiltonian."""
+    H = _with_jastrow(load_system(name), jas)
+    eng = _engine(H)
+    nw = 3
+    r_up, r_dn = random_walkers(H, nw, 14, scale=0.7)
+    RT = eng.generate_RTs(np.array([[9, i] for i in range(nw)], dtype=np.uint32))
+    Vd, Vn = eng.V_elements_n(r_up, r_dn, RT, nlm, 0.3)
+    Vd, Vn, RT = Vd.cpu().numpy(), Vn.cpu().numpy(), RT.cpu().numpy()
+    for w in range(nw):
+        d, n = OD.lrdmc_V_elements(H, r_up[w], r_dn[w], RT[w], nlm, 0.3)
+        np.testing.assert_allclose(Vd[w], d, rtol=1e-9)
+        np.testing.assert_allclose(Vn[w], n, rtol=1e-9)
+
+
+@pytest.mark.parametrize("name,jas,nlm,mesh", [("water_ccecp_ccpvqz", "j2pade", "tmove", True), ("water_ccecp_ccpvqz", "j2pade", "dltmove", True),
+                                               ("Li_ae_ccpvdz_cart", "j1exp_j2exp", "tmove", True), ("N2_ecp_ccpvtz_cart", "j2pade", "tmove", False)])  # fmt: skip
+def test_lrdmc_projection_trajectory(name, jas, nlm, mesh):
+    """kernel 6 / a30: same keys -> the same mesh moves are selected (bit-exact positions up to round-off of the
+    mesh point), same weights, keys bit-exact."""
+    H = _with_jastrow(load_system(name), jas)
+    eng = _engine(H)
+    nw, nmpm, alat, E_scf = 3, 6, 0.3, -17.0 if "water" in name else -20.0
+    r_up, r_dn = random_walkers(H, nw, 41, scale=0.7)
+    keys = np.array([[0, 777 + 5 * i] for i in range(nw)], dtype=np.uint32)
+    Ginv = eng.A_inv_n(r_up, r_dn)
+    w0 = np.ones(nw)
+    out = eng.projection_n(w0, r_up, r_dn, Ginv, keys, E_scf, nmpm, mesh, nlm, alat)
+    w, ru, rd, Gi, k2, RT, Vd, Vn = (x.cpu().numpy() for x in out)
+    Ginv = Ginv.cpu().numpy()
+    for i in range(nw):
+        ow, oru, ord_, oGi, okey, oRT, od, on = OD.lrdmc_projection(
+            H, 1.0, r_up[i], r_dn[i], Ginv[i], (int(keys[i, 0]), int(keys[i, 1])), E_scf, nmpm, mesh, nlm, alat
+        )
+        assert tuple(int(x) for x in k2[i]) == tuple(okey)
+        np.testing.assert_allclose(ru[i], oru, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(rd[i], ord_, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(w[i], ow, rtol=1e-8)
+        np.testing.assert_allclose(RT[i], oRT, rtol=0, atol=1e-14)
+        np.testing.assert_allclose(Vd[i], od, rtol=1e-8)
+        np.testing.assert_allclose(Vn[i], on, rtol=1e-8)
+        np.testing.assert_allclose(Gi[i], oGi, rtol=1e-7, atol=1e-9 * np.abs(oGi).max())
