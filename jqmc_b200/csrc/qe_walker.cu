@@ -160,7 +160,6 @@ k_walker(BasisDev Bu_g, BasisDev Bd_g, SysDev S_g, WalkerArgs P) {
   const int n_kin = P.mode == 2 ? 0 : 6 * Ne;
   const int n_ecp = S.ecp_flag ? Ne * S.NN * S.Nv : 0;
   const int NPT = n_kin + n_ecp;
-  const int vb = P.ecp_n_chunk;  // electrons per round in the initial VGL pass (host: fits shared memory)
 
   double* s_r = cv.take<double>((size_t)Ne * 3 * 32);
   double* s_Gi = cv.take<double>((size_t)NN2 * 32);
@@ -169,7 +168,7 @@ k_walker(BasisDev Bu_g, BasisDev Bd_g, SysDev S_g, WalkerArgs P) {
   double* s_p = cv.take<double>((size_t)(NPT > 0 ? NPT : 1) * 32);
   double* s_j = cv.take<double>((size_t)(n_ecp > 0 ? n_ecp : 1) * 32);
   double* s_el = cv.take<double>((size_t)Ne * 5 * 32);  // [e*5 + {ke, ei, eid, loc, ee}]
-  double* s_part = cv.take<double>((size_t)vb * nch * 5 * NMO * 32);
+  double* s_part = cv.take<double>((size_t)2 * nch * NMO * 32);  // double buffer of per-chunk partials, one component at a time
   double* s_stage = cv.take<double>((size_t)5 * NMO * 32);
   double* s_misc = cv.take<double>((size_t)16 * 32);  // 0..8 RT, 9..11 new position, 12 selected electron
 #define SR(e, c) s_r[((e) * 3 + (c)) * 32 + lane]
@@ -177,7 +176,6 @@ k_walker(BasisDev Bu_g, BasisDev Bd_g, SysDev S_g, WalkerArgs P) {
 #define SPHI(e, q, mo) s_phi[(((e) * 5 + (q)) * NMO + (mo)) * 32 + lane]
 #define SW(e, mo) s_W[((e) * NMO + (mo)) * 32 + lane]
 #define SEL(e, i) s_el[((e) * 5 + (i)) * 32 + lane]
-#define SPART(slot, q, mo) s_part[(((slot) * 5 + (q)) * NMO + (mo)) * 32 + lane]
 #define SMISC(i) s_misc[(i) * 32 + lane]
 
   for (int idx = wid; idx < Ne * 3; idx += NW) {
@@ -189,31 +187,17 @@ k_walker(BasisDev Bu_g, BasisDev Bd_g, SysDev S_g, WalkerArgs P) {
     for (int c = 0; c < 9; ++c) SMISC(c) = P.RT_in ? P.RT_in[(size_t)ww * 9 + c] : (c % 4 == 0 ? 1.0 : 0.0);
   __syncthreads();
 
-  // ---- value/grad/lap of the MOs at every electron (cache) ------------------------------------------
-  for (int e0 = 0; e0 < Ne; e0 += vb) {
-    const int slot = wid / nch, c = wid % nch;
-    const int e = e0 + slot;
-    if (slot < vb && e < Ne) {
-      SinkMO5<NMO> sink;
-      sink.init(e < N ? Bu.Cs : Bd.Cs);
-      eval_vgl<CART>(Bu, S.Rn, SR(e, 0), SR(e, 1), SR(e, 2), P.chunk_begin[c], P.chunk_begin[c + 1], sink);
+  // ---- value/grad/lap of the MOs at every electron (cache): task = electron ----------------------------
+  for (int e = wid; e < Ne; e += NW) {
+    SinkMO5<NMO> sink;
+    sink.init(e < N ? Bu.Cs : Bd.Cs);
+    eval_vgl<CART>(Bu, S.Rn, SR(e, 0), SR(e, 1), SR(e, 2), 0, Bu.n_grp, sink);
 #pragma unroll
-      for (int q = 0; q < 5; ++q)
+    for (int q = 0; q < 5; ++q)
 #pragma unroll
-        for (int mo = 0; mo < NMO; ++mo) SPART(slot * nch + c, q, mo) = sink.acc[q][mo];
-    }
-    __syncthreads();
-    // reduce: items (slot, q, mo) spread over warps
-    for (int item = wid; item < vb * 5 * NMO; item += NW) {
-      const int sl = item / (5 * NMO), qm = item % (5 * NMO);
-      if (e0 + sl < Ne) {
-        double s = 0;
-        for (int cc = 0; cc < nch; ++cc) s += s_part[((sl * nch + cc) * 5 * NMO + qm) * 32 + lane];
-        s_phi[((e0 + sl) * 5 * NMO + qm) * 32 + lane] = s;
-      }
-    }
-    __syncthreads();
+      for (int mo = 0; mo < NMO; ++mo) SPHI(e, q, mo) = sink.acc[q][mo];
   }
+  __syncthreads();
 
   double w_L = (P.mode == 0) ? P.w[ww] : 1.0;
   double diag = 0.0, nondiag = 0.0;
@@ -486,22 +470,34 @@ k_walker(BasisDev Bu_g, BasisDev Bd_g, SysDev S_g, WalkerArgs P) {
     // ---- P4: refresh the moved electron, Sherman-Morrison ---------------------------------------------------
     const int es = (int)SMISC(12);
     const double nx = SMISC(9), ny = SMISC(10), nz = SMISC(11);
-    if (wid < nch) {
+    {
       SinkMO5<NMO> sink;
-      sink.init(es < N ? Bu.Cs : Bd.Cs);
-      eval_vgl<CART>(Bu, S.Rn, nx, ny, nz, P.chunk_begin[wid], P.chunk_begin[wid + 1], sink);
+      if (wid < nch) {
+        sink.init(es < N ? Bu.Cs : Bd.Cs);
+        eval_vgl<CART>(Bu, S.Rn, nx, ny, nz, P.chunk_begin[wid], P.chunk_begin[wid + 1], sink);
+      }
+      // deterministic reduction over chunks, one component at a time through a double buffer
 #pragma unroll
-      for (int q = 0; q < 5; ++q)
+      for (int q = 0; q < 5; ++q) {
+        double* buf = s_part + (size_t)(q & 1) * nch * NMO * 32;
+        if (wid < nch) {
 #pragma unroll
-        for (int mo = 0; mo < NMO; ++mo) SPART(wid, q, mo) = sink.acc[q][mo];
+          for (int mo = 0; mo < NMO; ++mo) buf[(wid * NMO + mo) * 32 + lane] = sink.acc[q][mo];
+        }
+        __syncthreads();
+        for (int mo = wid; mo < NMO; mo += NW) {
+          double s = 0;
+          for (int c = 0; c < nch; ++c) s += buf[(c * NMO + mo) * 32 + lane];
+          s_stage[(q * NMO + mo) * 32 + lane] = s;
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
     if (wid == 0) {
       double pn[NMO], po[NMO];
 #pragma unroll
       for (int mo = 0; mo < NMO; ++mo) {
-        double s = 0;
-        for (int c = 0; c < nch; ++c) s += SPART(c, 0, mo);
+        const double s = s_stage[mo * 32 + lane];
         pn[mo] = s - SPHI(es, 0, mo);  // phi_new - phi_old  (row/column DIFFERENCE is linear in it)
         po[mo] = s;
       }
@@ -571,12 +567,6 @@ k_walker(BasisDev Bu_g, BasisDev Bd_g, SysDev S_g, WalkerArgs P) {
       SR(es, 1) = ny;
       SR(es, 2) = nz;
       (void)po;
-    }
-    // cached value/grad/lap of the moved electron: items (q, mo) over warps
-    for (int item = wid; item < 5 * NMO; item += NW) {
-      double s = 0;
-      for (int c = 0; c < nch; ++c) s += s_part[((c * 5 * NMO) + item) * 32 + lane];
-      s_stage[item * 32 + lane] = s;  // the store into s_phi is deferred until warp 0 has consumed the old values
     }
     __syncthreads();
     for (int item = wid; item < 5 * NMO; item += NW) s_phi[(es * 5 * NMO + item) * 32 + lane] = s_stage[item * 32 + lane];
@@ -654,18 +644,11 @@ int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
   const int Ne = S.n_e;
   const int n_kin = A.mode == 2 ? 0 : 6 * Ne;
   const int n_ecp = S.ecp_flag ? Ne * S.NN * S.Nv : 0;
-  size_t smem = 0;
-  int vb = std::max(1, std::min(NW / std::max(1, nch), Ne));
-  for (; vb >= 1; --vb) {
-    size_t per_lane = (size_t)Ne * 3 + (size_t)S.n_up * S.n_up + (size_t)Ne * 5 * P + (size_t)Ne * P + std::max(1, n_kin + n_ecp) +
-                      std::max(1, n_ecp) + (size_t)Ne * 5 + (size_t)vb * nch * 5 * P + 5 * P + 16;
-    smem = table_bytes(h->b_up.dev, S, P) + (h->b_dn.dev.Cs != h->b_up.dev.Cs ? (size_t)h->b_dn.dev.n_ao * P * 8 + 16 : 0) +
-           per_lane * 32 * 8 + 16 * 12;
-    if (smem <= 160 * 1024) break;
-  }
-  if (vb < 1) vb = 1;
+  size_t per_lane = (size_t)Ne * 3 + (size_t)S.n_up * S.n_up + (size_t)Ne * 5 * P + (size_t)Ne * P + std::max(1, n_kin + n_ecp) +
+                    std::max(1, n_ecp) + (size_t)Ne * 5 + (size_t)2 * nch * P + 5 * P + 16;
+  size_t smem = table_bytes(h->b_up.dev, S, P) + (h->b_dn.dev.Cs != h->b_up.dev.Cs ? (size_t)h->b_dn.dev.n_ao * P * 8 + 16 : 0) +
+                per_lane * 32 * 8 + 16 * 12;
   if (smem > 227 * 1024) return fail(QE_ERR_UNSUPPORTED, "system too large for the fused walker kernel (shared memory)");
-  A.ecp_n_chunk = vb;
   dim3 block(32, NW);
   {
     LaunchScope ls_(h, kid, st);

@@ -320,8 +320,8 @@ def test_local_energy_fused_equals_staged(name, jas):
 
 
 @pytest.mark.parametrize("name,jas,nlm", [("water_ccecp_ccpvqz", "j2pade", "tmove"), ("water_ccecp_ccpvqz", "j1exp_j2exp", "dltmove"),
-                                          ("Li_ae_ccpvdz_cart", "j2pade", "tmove"), ("N2_ecp_ccpvtz_cart", "j1pade_j2pade", "tmove"),
-                                          ("H2_ae_ccpvdz_cart", "j1exp_j2exp", "tmove")])  # fmt: skip
+                                          ("Li_ae_ccpvdz_cart", "j2pade", "tmove"), ("H2_ecp_ccpvtz_cart", "j1pade_j2pade", "tmove"),
+                                          ("H2_ae_ccpvdz_cart", "j1exp_j2exp", "tmove"), ("H2_ecp_ccpvtz", "j2pade", "dltmove")])  # fmt: skip
 def test_lrdmc_V_elements(name, jas, nlm):
     """a20, a23-a25, a30: V_diag / V_nondiag of the lattice-regularised Hamiltonian."""
     H = _with_jastrow(load_system(name), jas)
@@ -338,13 +338,14 @@ def test_lrdmc_V_elements(name, jas, nlm):
 
 
 @pytest.mark.parametrize("name,jas,nlm,mesh", [("water_ccecp_ccpvqz", "j2pade", "tmove", True), ("water_ccecp_ccpvqz", "j2pade", "dltmove", True),
-                                               ("Li_ae_ccpvdz_cart", "j1exp_j2exp", "tmove", True), ("N2_ecp_ccpvtz_cart", "j2pade", "tmove", False)])  # fmt: skip
+                                               ("Li_ae_ccpvdz_cart", "j1exp_j2exp", "tmove", True), ("H2_ecp_ccpvtz_cart", "j2pade", "tmove", False)])  # fmt: skip
 def test_lrdmc_projection_trajectory(name, jas, nlm, mesh):
     """kernel 6 / a30: same keys -> the same mesh moves are selected (bit-exact positions up to round-off of the
     mesh point), same weights, keys bit-exact."""
     H = _with_jastrow(load_system(name), jas)
     eng = _engine(H)
-    nw, nmpm, alat, E_scf = 3, 6, 0.3, -17.0 if "water" in name else -20.0
+    nw, nmpm, alat = 3, 6, 0.3
+    E_scf = {"water_ccecp_ccpvqz": -17.0, "Li_ae_ccpvdz_cart": -7.4, "H2_ecp_ccpvtz_cart": -1.1}[name]
     r_up, r_dn = random_walkers(H, nw, 41, scale=0.7)
     keys = np.array([[0, 777 + 5 * i] for i in range(nw)], dtype=np.uint32)
     Ginv = eng.A_inv_n(r_up, r_dn)
