@@ -144,6 +144,25 @@ int qe_lrdmc_velements(qe_engine* h, int nw, const double* r_up, const double* r
                        const double* Ginv, int non_local_move, double alat, double* V_diag, double* V_nondiag,
                        void* stream);  /* Ginv: inverse at (r_up, r_dn), e.g. from qe_geminal_init as the reference does */
 
+/* Per-step weighted sums of GFMC_n.run (jqmc/jqmc_gfmc.py:5971-5976), e_L = V_diag + V_nondiag:
+ * out5 (device) = { nw, sum w, sum w/(V_diag-E_scf), sum w/(V_diag-E_scf) e_L, sum w/(V_diag-E_scf) e_L^2 }.
+ * The caller sums out5 over ranks (the reference: mpi reduce, :6016-6020). */
+int qe_lrdmc_collect(qe_engine* h, int nw, const double* w, const double* V_diag, const double* V_nondiag, double E_scf,
+                     double* out5, void* stream);
+
+/* Walker reconfiguration, index part (jqmc/jqmc_gfmc.py:6069-6135).  w_all[world*nw] holds the weights of ALL ranks in
+ * rank order (all-gathered by the caller); zeta in [0,1) is rank 0's np.random.random() (:5948-5952).  Every rank
+ * evaluates the same comb:  chosen_all[g] = searchsorted(global cumulative probabilities, (g + zeta)/(world*nw)),
+ * g = destination slot (rank = g / nw); *n_survived = number of distinct sources.  Summation order = the reference's
+ * (np.sum pairwise per rank, np.cumsum sequential, Exscan rank offsets), so the indices agree bit for bit. */
+int qe_lrdmc_branch(qe_engine* h, int nw, int world, const double* w_all, double zeta, int32_t* chosen_all,
+                    int32_t* n_survived, void* stream);
+
+/* Walker reconfiguration, data part (jqmc/jqmc_gfmc.py:6146-6318): dst walker i <- src walker chosen_local[i], where the
+ * src arrays are the all-gathered coordinates [world*nw, n_up|n_dn, 3] and chosen_local = chosen_all + rank*nw. */
+int qe_gather_walkers(qe_engine* h, int nw, const int32_t* chosen_local, const double* src_r_up, const double* src_r_dn,
+                      double* dst_r_up, double* dst_r_dn, void* stream);
+
 /* qe_local_energy runs as ONE fused kernel (shared-memory resident walker state) when the system fits and
  * `on` != 0 (default); otherwise as a chain of staged kernels through a global workspace.  Same results. */
 int qe_set_fused(qe_engine* h, int on);

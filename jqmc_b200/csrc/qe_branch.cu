@@ -1,0 +1,206 @@
+// LRDMC (GFMC_n) per-step statistics and walker reconfiguration on the device
+// (jqmc/jqmc_gfmc.py:5955-5976 weighted sums, :6059-6321 branching).
+//
+// The reference does this part on the host with NumPy + mpi4py: allreduce(sum w) -> local cumulative
+// probabilities -> Exscan rank offsets -> Allgather -> searchsorted with the comb z_i = (i + zeta)/N -> negotiated
+// point-to-point migration of the chosen walkers.  Here every rank holds the all-gathered weight vector
+// (NCCL all_gather of nw doubles per rank, done by the caller) and evaluates the SAME comb redundantly, so the only
+// data-path collectives are that all_gather and the one of the walker coordinates; each rank then gathers its
+// `nw` destination walkers from the gathered coordinate buffer by index.
+//
+// Floating-point order follows the reference so that the chosen indices agree bit for bit:
+//   S_r   = np.sum(w_r)                 NumPy pairwise summation (8 accumulators, blocks of 128, recursive halving)
+//   S     = S_0 + S_1 + ...             rank order
+//   p     = w / S ;  c_r = np.cumsum(p_r)   sequential ;  off_r = sum_{q<r} np.sum(p_q)  (pairwise, then rank order)
+//   idx_i = searchsorted(c + off, (i + zeta)/N, 'left')
+#include "qe_common.cuh"
+
+namespace {
+
+// NumPy's DOUBLE_pairwise_sum for a contiguous array (numpy/core/src/umath/loops_utils.h.src)
+__device__ double np_pairwise_sum(const double* __restrict__ a, int n) {
+  if (n < 8) {
+    double res = 0.0;
+    for (int i = 0; i < n; ++i) res += a[i];
+    return res;
+  }
+  if (n <= 128) {
+    double r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+      r0 += a[i];
+      r1 += a[i + 1];
+      r2 += a[i + 2];
+      r3 += a[i + 3];
+      r4 += a[i + 4];
+      r5 += a[i + 5];
+      r6 += a[i + 6];
+      r7 += a[i + 7];
+    }
+    double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; ++i) res += a[i];
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+}
+
+// block r: S[r] = np.sum(w_all[r*nw : (r+1)*nw])
+__global__ void k_branch_rank_sums(int nw, const double* __restrict__ w_all, double* __restrict__ S) {
+  if (threadIdx.x == 0) S[blockIdx.x] = np_pairwise_sum(w_all + (size_t)blockIdx.x * nw, nw);
+}
+
+// block r: p = w / sum_r S[r];  P[r] = np.sum(p_r);  c_r = cumsum(p_r) (sequential fp64)
+__global__ void k_branch_cumprob(int nw, int world, const double* __restrict__ w_all, const double* __restrict__ S,
+                                 double* __restrict__ c, double* __restrict__ P) {
+  const int r = blockIdx.x;
+  double gsum = 0.0;
+  for (int q = 0; q < world; ++q) gsum += S[q];
+  double* cr = c + (size_t)r * nw;
+  const double* wr = w_all + (size_t)r * nw;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) cr[i] = wr[i] / gsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    P[r] = np_pairwise_sum(cr, nw);
+    double acc = 0.0;
+    for (int i = 0; i < nw; ++i) {
+      acc += cr[i];
+      cr[i] = acc;
+    }
+  }
+}
+
+// thread g (global destination slot): chosen[g] = searchsorted(c + offset, (g + zeta)/N, 'left'), clamped to N-1
+__global__ void k_branch_select(int nw, int world, const double* __restrict__ c, const double* __restrict__ P, double zeta,
+                                int* __restrict__ chosen) {
+  const int N = nw * world;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N) return;
+  __shared__ double off[64];
+  if (threadIdx.x == 0) {
+    // MPI.Exscan(SUM): off_r = P_0 + ... + P_{r-1}; rank 0 uses 0.0 (jqmc/jqmc_gfmc.py:6088-6095)
+    double acc = 0.0;
+    for (int q = 0; q < world; ++q) {
+      off[q] = q == 0 ? 0.0 : acc;
+      acc += P[q];
+    }
+  }
+  __syncthreads();
+  const double z = ((double)g + zeta) / (double)N;
+  int lo = 0, hi = N;  // first i with cg[i] >= z
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const double v = c[mid] + off[mid / nw];
+    if (v < z) lo = mid + 1; else hi = mid;
+  }
+  chosen[g] = lo < N ? lo : N - 1;
+}
+
+// number of distinct chosen sources (chosen is non-decreasing): survivors (jqmc/jqmc_gfmc.py:6134-6135)
+__global__ void k_branch_count(int N, const int* __restrict__ chosen, int* __restrict__ n_survived) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N) return;
+  const int flag = (g == 0) || (chosen[g] != chosen[g - 1]);
+  const unsigned m = __ballot_sync(__activemask(), flag);
+  if ((threadIdx.x & 31) == 0) atomicAdd(n_survived, __popc(m));
+}
+
+// dst walker i of this rank <- gathered walker chosen[rank*nw + i]
+__global__ void k_gather_walkers(int nw, int per_up, int per_dn, const int* __restrict__ chosen_local,
+                                 const double* __restrict__ src_up, const double* __restrict__ src_dn,
+                                 double* __restrict__ dst_up, double* __restrict__ dst_dn) {
+  const int per = per_up + per_dn;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nw * per) return;
+  const int i = (int)(t / per), k = (int)(t % per);
+  const size_t s = (size_t)chosen_local[i];
+  if (k < per_up) dst_up[(size_t)i * per_up + k] = src_up[s * per_up + k];
+  else dst_dn[(size_t)i * per_dn + (k - per_up)] = src_dn[s * per_dn + (k - per_up)];
+}
+
+// per-step weighted sums (jqmc/jqmc_gfmc.py:5971-5976): out = {nw, sum w, sum w/(Vd-E), sum w/(Vd-E) e, sum w/(Vd-E) e^2}
+// one block, fixed-order tree reduction (deterministic)
+__global__ void k_lrdmc_collect(int nw, const double* __restrict__ w, const double* __restrict__ Vd,
+                                const double* __restrict__ Vn, double E_scf, double* __restrict__ out) {
+  __shared__ double sm[4][256];
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  for (int i = threadIdx.x; i < nw; i += 256) {
+    const double wi = w[i], e = Vd[i] + Vn[i], q = wi / (Vd[i] - E_scf);
+    a0 += wi;
+    a1 += q;
+    a2 += q * e;
+    a3 += q * e * e;
+  }
+  sm[0][threadIdx.x] = a0;
+  sm[1][threadIdx.x] = a1;
+  sm[2][threadIdx.x] = a2;
+  sm[3][threadIdx.x] = a3;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int k = 0; k < 4; ++k) sm[k][threadIdx.x] += sm[k][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[0] = (double)nw;
+    for (int k = 0; k < 4; ++k) out[1 + k] = sm[k][0];
+  }
+}
+
+}  // namespace
+
+extern "C" int qe_lrdmc_collect(qe_engine* h, int nw, const double* w, const double* V_diag, const double* V_nondiag, double E_scf,
+                                double* out5, void* stream) {
+  if (!h || nw <= 0 || !w || !V_diag || !V_nondiag || !out5) return fail(QE_ERR_INVALID, "qe_lrdmc_collect: bad argument");
+  {
+    LaunchScope ls_(h, K_COLLECT, (cudaStream_t)stream);
+    k_lrdmc_collect<<<1, 256, 0, (cudaStream_t)stream>>>(nw, w, V_diag, V_nondiag, E_scf, out5);
+  }
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+
+extern "C" int qe_lrdmc_branch(qe_engine* h, int nw, int world, const double* w_all, double zeta, int32_t* chosen_all,
+                               int32_t* n_survived, void* stream) {
+  if (!h || nw <= 0 || world <= 0 || world > 64 || !w_all || !chosen_all || !n_survived)
+    return fail(QE_ERR_INVALID, "qe_lrdmc_branch: bad argument (world must be 1..64)");
+  if (!(zeta >= 0.0 && zeta < 1.0)) return fail(QE_ERR_INVALID, "qe_lrdmc_branch: zeta must be in [0, 1)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = nw * world;
+  // private scratch (not the shared workspace: the walker buffers of the caller may live there in future)
+  if (h->branch_ws_n < (size_t)N + 2 * 64) {
+    if (h->branch_ws) cudaFree(h->branch_ws);
+    h->branch_ws = nullptr;
+    CUDA_TRY(cudaMalloc(&h->branch_ws, ((size_t)N + 2 * 64) * sizeof(double)));
+    h->branch_ws_n = (size_t)N + 2 * 64;
+  }
+  double* S = h->branch_ws;
+  double* P = S + 64;
+  double* c = P + 64;
+  CUDA_TRY(cudaMemsetAsync(n_survived, 0, sizeof(int32_t), st));
+  {
+    LaunchScope ls_(h, K_BRANCH, st);
+    k_branch_rank_sums<<<world, 32, 0, st>>>(nw, w_all, S);
+    k_branch_cumprob<<<world, 256, 0, st>>>(nw, world, w_all, S, c, P);
+    k_branch_select<<<nblk(N, 128), 128, 0, st>>>(nw, world, c, P, zeta, chosen_all);
+    k_branch_count<<<nblk(N, 128), 128, 0, st>>>(N, chosen_all, n_survived);
+    h->launches += 3;
+  }
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+
+extern "C" int qe_gather_walkers(qe_engine* h, int nw, const int32_t* chosen_local, const double* src_r_up, const double* src_r_dn,
+                                 double* dst_r_up, double* dst_r_dn, void* stream) {
+  if (!h || nw <= 0 || !chosen_local || !src_r_up || !dst_r_up || (h->sys.n_dn > 0 && (!src_r_dn || !dst_r_dn)))
+    return fail(QE_ERR_INVALID, "qe_gather_walkers: bad argument");
+  const int pu = 3 * h->sys.n_up, pd = 3 * h->sys.n_dn;
+  {
+    LaunchScope ls_(h, K_GATHER, (cudaStream_t)stream);
+    k_gather_walkers<<<nblk((long long)nw * (pu + pd), 256), 256, 0, (cudaStream_t)stream>>>(nw, pu, pd, chosen_local, src_r_up,
+                                                                                             src_r_dn, dst_r_up, dst_r_dn);
+  }
+  CHECK_LAUNCH();
+  return QE_OK;
+}

@@ -91,6 +91,8 @@ struct qe_engine {
   void* ws = nullptr;
   size_t ws_bytes = 0;
   int64_t launches = 0;
+  double* branch_ws = nullptr;  // scratch of qe_lrdmc_branch: rank sums, rank probabilities, cumulative probabilities
+  size_t branch_ws_n = 0;
   // optional per-kernel timing (qe_profile): CUDA events recorded on the launch stream around each kernel
   bool profiling = false;
   bool fused = true;  // qe_local_energy uses the fused walker kernel when the system fits
@@ -104,10 +106,11 @@ struct qe_engine {
 };
 
 enum KernelId { K_ORB_EL = 0, K_GEMINAL, K_ALGEBRA, K_ECP_MESH, K_REDUCE, K_RATIOS, K_AS, K_ROT, K_KEYCHAIN, K_DRAWS, K_MCMC,
-                K_EVAL, K_LRDMC, K_EL_FUSED, K_COUNT };
+                K_EVAL, K_LRDMC, K_EL_FUSED, K_LRDMC_PROJ, K_COLLECT, K_BRANCH, K_GATHER, K_COUNT };
 static const char* const KERNEL_NAMES[K_COUNT] = {"k_orb_electrons", "k_geminal", "k_electron_algebra", "k_ecp_mesh", "k_reduce_eL",
                                                   "k_move_ratios", "k_as_factor", "k_rotation", "k_mcmc_keychain", "k_mcmc_draws",
-                                                  "k_mcmc", "k_eval_orbitals", "k_walker(lrdmc)", "k_walker(e_L)"};
+                                                  "k_mcmc", "k_eval_orbitals", "k_walker(V_elements)", "k_walker(e_L)", "k_walker(projection)", "k_lrdmc_collect",
+                                                  "k_branch", "k_gather_walkers"};
 struct LaunchScope {
   qe_engine* h;
   cudaStream_t st;

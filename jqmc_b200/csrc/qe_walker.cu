@@ -707,7 +707,7 @@ extern "C" int qe_lrdmc_project(qe_engine* h, int nw, double* w, double* r_up, d
   A.V_nondiag = V_nondiag;
   A.rRT = rRT;
   A.ru = ru;
-  return launch_walker(h, A, st, K_EL_FUSED);
+  return launch_walker(h, A, st, K_LRDMC_PROJ);
 }
 
 extern "C" int qe_lrdmc_velements(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,

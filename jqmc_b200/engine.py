@@ -383,6 +383,48 @@ class WalkerEngine:
         _lib.check(rc, "qe_lrdmc_velements")
         return Vd, Vn
 
+    # ---- LRDMC per-step statistics and reconfiguration: jqmc/jqmc_gfmc.py:5955-6321 ---------------
+    def lrdmc_collect(self, w, V_diag, V_nondiag, E_scf):
+        """Device vector [nw, sum w, sum w/(V_diag-E), sum w/(V_diag-E) e_L, sum w/(V_diag-E) e_L^2] of this rank."""
+        w = self._dev(w)
+        nw = w.shape[0]
+        Vd, Vn = self._dev(V_diag), self._dev(V_nondiag)
+        if Vd.shape != (nw,) or Vn.shape != (nw,):
+            raise ValueError(f"V_diag / V_nondiag shapes {tuple(Vd.shape)} / {tuple(Vn.shape)} != ({nw},)")
+        out = torch.empty(5, dtype=torch.float64, device=self.device)
+        rc = self._lib.qe_lrdmc_collect(self._h, nw, self._ptr(w), self._ptr(Vd), self._ptr(Vn), float(E_scf), self._ptr(out), self._stream())
+        _lib.check(rc, "qe_lrdmc_collect")
+        return out
+
+    def lrdmc_branch(self, w_all, num_walkers, zeta):
+        """Comb selection over the all-gathered weights ``w_all[world*nw]``: returns
+        ``(chosen_all int32[world*nw], n_survived int32[1])`` (device), identical on every rank."""
+        w_all = self._dev(w_all)
+        nw = int(num_walkers)
+        if w_all.ndim != 1 or w_all.shape[0] % nw:
+            raise ValueError(f"w_all shape {tuple(w_all.shape)} is not (world*{nw},)")
+        world = w_all.shape[0] // nw
+        chosen = torch.empty(world * nw, dtype=torch.int32, device=self.device)
+        nsurv = torch.empty(1, dtype=torch.int32, device=self.device)
+        rc = self._lib.qe_lrdmc_branch(self._h, nw, world, self._ptr(w_all), float(zeta), self._ptr(chosen), self._ptr(nsurv), self._stream())
+        _lib.check(rc, "qe_lrdmc_branch")
+        return chosen, nsurv
+
+    def gather_walkers(self, chosen_local, src_r_up, src_r_dn):
+        """New local walkers ``src[chosen_local[i]]`` from the all-gathered coordinates."""
+        chosen_local = self._dev(chosen_local, torch.int32)
+        nw = chosen_local.shape[0]
+        src_up, src_dn = self._dev(src_r_up), self._dev(src_r_dn)
+        if src_up.shape[1:] != (self.n_up, 3) or src_dn.shape[1:] != (self.n_dn, 3) or src_up.shape[0] != src_dn.shape[0]:
+            raise ValueError(f"gathered coordinate shapes {tuple(src_up.shape)} / {tuple(src_dn.shape)} are inconsistent")
+        dst_up = torch.empty((nw, self.n_up, 3), dtype=torch.float64, device=self.device)
+        dst_dn = torch.empty((nw, self.n_dn, 3), dtype=torch.float64, device=self.device)
+        rc = self._lib.qe_gather_walkers(
+            self._h, nw, self._ptr(chosen_local), self._ptr(src_up), self._ptr(src_dn), self._ptr(dst_up), self._ptr(dst_dn), self._stream()
+        )
+        _lib.check(rc, "qe_gather_walkers")
+        return dst_up, dst_dn
+
     def launch_count(self) -> int:
         return int(self._lib.qe_launch_count(self._h))
 

@@ -1,0 +1,301 @@
+"""``GFMC_n`` driver (LRDMC, fixed number of projections per branching) on the walker engine: the host-side
+mirror of ``jqmc.jqmc_gfmc.GFMC_n`` (jqmc/jqmc_gfmc.py:4191-6650).
+
+Same constructor arguments, step loop, stored observables, on-the-fly ``E_scf`` update and ``get_E``
+statistics as the reference; the per-step device work is done by ``WalkerEngine``:
+
+    for each branching step (jqmc_gfmc.py:5774-6417)
+        w = 1;  projection_n  -> qe_lrdmc_project     (nmpm lattice-regularised projections per walker)
+        V_elements_n          -> qe_geminal_init + qe_lrdmc_velements   (e_L = V_diag + V_nondiag)
+        weighted sums         -> qe_lrdmc_collect + all_reduce(SUM) of 5 doubles            (:5971-6051)
+        reconfiguration       -> all_gather(w, r_up, r_dn) + qe_lrdmc_branch + qe_gather_walkers (:6059-6318)
+        A_inv refresh         -> qe_geminal_init                                             (:6319)
+        E_scf update          -> host jackknife of the stored (w, e_L) history               (:6327-6383)
+
+Differences from the reference, all behind the same observable results:
+
+* the reference moves every array to the host and talks mpi4py (reduce -> rank 0, Exscan, Allgather,
+  Alltoallv negotiation, Isend/Irecv of the migrating walkers); here the walker state never leaves the
+  GPU: one ``all_reduce`` of 5 doubles and one ``all_gather`` per array over NCCL/NVLink, and every rank
+  evaluates the identical comb redundantly (no negotiation round);
+* the comb offset ``zeta`` is rank 0's ``np.random.random()`` after ``np.random.seed(mcmc_seed)`` at the top of
+  ``run`` (:4669, :5948-5952); every rank replays that stream locally instead of receiving a broadcast;
+* the per-step averages are all-reduced, so every rank stores them (the reference keeps them on rank 0 only).
+
+Out of scope: atomic forces (``comput_position_deriv``), ``GFMC_t``.
+"""
+
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from . import rng_host
+from .engine import WalkerEngine
+from .mcmc import _dist, _rank_size, generate_init_electron_configurations
+
+# jqmc/_setting.py:59-61
+GFMC_ON_THE_FLY_WARMUP_STEPS = 20
+GFMC_ON_THE_FLY_COLLECT_STEPS = 10
+GFMC_ON_THE_FLY_BIN_BLOCKS = 10
+
+
+def compute_G_L(w_L: np.ndarray, num_gfmc_collect_steps: int) -> np.ndarray:
+    """G_L[n] = prod_{k=n-c}^{n-1} w_L[k], n = c .. A-1  (jqmc/jqmc_gfmc.py:136-152); w_L has shape (A, x)."""
+    w_L = np.asarray(w_L, dtype=np.float64)
+    A, c = w_L.shape[0], int(num_gfmc_collect_steps)
+    if A <= c:
+        return np.zeros((0,) + w_L.shape[1:], dtype=np.float64)
+    return np.stack([np.prod(w_L[n - c : n], axis=0) for n in range(c, A)])
+
+
+def jackknife_E_scf(G_L, G_e_L, num_bin_blocks):
+    """On-the-fly E_scf estimate (jqmc/jqmc_gfmc.py:6350-6365): binned jackknife of sum(G e)/sum(G)."""
+    G_e_L_binned = np.array([np.sum(x) for x in np.array_split(np.asarray(G_e_L), num_bin_blocks)])
+    G_binned = np.array([np.sum(x) for x in np.array_split(np.asarray(G_L), num_bin_blocks)])
+    s_e, s_g = np.sum(G_e_L_binned), np.sum(G_binned)
+    E_jk = [(s_e - G_e_L_binned[m]) / (s_g - G_binned[m]) for m in range(num_bin_blocks)]
+    return float(np.average(E_jk)), float(np.sqrt(num_bin_blocks - 1) * np.std(E_jk))
+
+
+class GFMC_n:
+    """LRDMC sampler (see module docstring).  Public surface follows jqmc.jqmc_gfmc.GFMC_n."""
+
+    def __init__(
+        self,
+        hamiltonian_data=None,
+        num_walkers: int = 40,
+        num_mcmc_per_measurement: int = 16,
+        num_gfmc_collect_steps: int = 5,
+        mcmc_seed: int = 34467,
+        E_scf: float = 0.0,
+        alat: float = 0.1,
+        random_discretized_mesh: bool = True,
+        non_local_move: str = "tmove",
+        comput_position_deriv: bool = False,
+        epsilon_PW: float = 0.0,
+        use_swct: bool = False,
+        engine=None,
+    ) -> None:
+        if comput_position_deriv:
+            raise NotImplementedError("atomic forces are outside the walker engine (SURVEY.md §8f)")
+        self.__hamiltonian_data = hamiltonian_data
+        self.__num_walkers = int(num_walkers)
+        self.__nmpm = int(num_mcmc_per_measurement)
+        self.__num_gfmc_collect_steps = int(num_gfmc_collect_steps)
+        self.__mcmc_seed = int(mcmc_seed)
+        self.__E_scf = float(E_scf)
+        self.__alat = float(alat)
+        self.__random_discretized_mesh = bool(random_discretized_mesh)
+        self.__non_local_move = non_local_move
+        rank, _ = _rank_size()
+        self.__mpi_seed = self.__mcmc_seed * (rank + 1)
+        self.engine = engine if engine is not None else WalkerEngine(hamiltonian_data)
+        dev = self.engine.device
+        keys = rng_host.split(rng_host.PRNGKey(self.__mpi_seed), self.__num_walkers)
+        self.__keys = torch.from_numpy(keys).to(dev)
+        np.random.seed(self.__mpi_seed % (2**32))
+        gem = hamiltonian_data.wavefunction_data.geminal_data
+        cp = hamiltonian_data.coulomb_potential_data
+        r_up, r_dn, _, _ = generate_init_electron_configurations(
+            gem.num_electron_up, gem.num_electron_dn, self.__num_walkers, cp.effective_charges,
+            hamiltonian_data.structure_data.positions,
+        )  # fmt: skip
+        self.__r_up = torch.from_numpy(np.ascontiguousarray(r_up)).to(dev)
+        self.__r_dn = torch.from_numpy(np.ascontiguousarray(r_dn)).to(dev)
+        self.__init_attributes()
+
+    def __init_attributes(self):
+        self.__mcmc_counter = 0
+        self.__num_survived_walkers = 0
+        self.__num_killed_walkers = 0
+        self.__stored_w_L = np.zeros((0, 1))
+        self.__stored_e_L = np.zeros((0, 1))
+        self.__stored_e_L2 = np.zeros((0, 1))
+        self.__G_L = []
+        self.__G_e_L = []
+        self.__timer = dict(total=0.0)
+
+    # ---- properties (jqmc_gfmc.py:4550-4634) ---------------------------------------------------------
+    @property
+    def hamiltonian_data(self):
+        return self.__hamiltonian_data
+
+    @property
+    def num_gfmc_collect_steps(self):
+        return self.__num_gfmc_collect_steps
+
+    @num_gfmc_collect_steps.setter
+    def num_gfmc_collect_steps(self, n):
+        self.__num_gfmc_collect_steps = int(n)
+
+    @property
+    def mcmc_counter(self) -> int:
+        return self.__mcmc_counter - self.__num_gfmc_collect_steps
+
+    @property
+    def num_walkers(self):
+        return self.__num_walkers
+
+    @property
+    def alat(self):
+        return self.__alat
+
+    @property
+    def E_scf(self):
+        return self.__E_scf
+
+    @property
+    def w_L(self):
+        return compute_G_L(self.__stored_w_L, self.__num_gfmc_collect_steps)
+
+    @property
+    def bare_w_L(self):
+        return np.asarray(self.__stored_w_L)
+
+    @property
+    def e_L(self):
+        return np.asarray(self.__stored_e_L)[self.__num_gfmc_collect_steps :]
+
+    @property
+    def e_L2(self):
+        return np.asarray(self.__stored_e_L2)[self.__num_gfmc_collect_steps :]
+
+    @property
+    def latest_r_up_carts(self):
+        return self.__r_up
+
+    @property
+    def latest_r_dn_carts(self):
+        return self.__r_dn
+
+    @property
+    def jax_PRNG_key_list(self):
+        return self.__keys
+
+    @property
+    def num_survived_walkers(self):
+        return self.__num_survived_walkers
+
+    @property
+    def num_killed_walkers(self):
+        return self.__num_killed_walkers
+
+    @property
+    def timer(self):
+        return dict(self.__timer)
+
+    # ---- one branching step on the device (no host synchronisation) ----------------------------------
+    def _step(self, r_up, r_dn, keys, A_inv, zeta, rank, world):
+        eng = self.engine
+        nw = self.__num_walkers
+        w = torch.ones(nw, dtype=torch.float64, device=eng.device)
+        w, r_up, r_dn, A_inv, keys, RTs, _, _ = eng.projection_n(
+            w, r_up, r_dn, A_inv, keys, self.__E_scf, self.__nmpm, self.__random_discretized_mesh, self.__non_local_move,
+            self.__alat, inplace=True,
+        )  # fmt: skip
+        V_diag, V_nondiag = eng.V_elements_n(r_up, r_dn, RTs, self.__non_local_move, self.__alat)
+        sums = eng.lrdmc_collect(w, V_diag, V_nondiag, self.__E_scf)
+        d = _dist()
+        if d is not None and world > 1:
+            d.all_reduce(sums, op=d.ReduceOp.SUM)
+            w_all = torch.empty(world * nw, dtype=w.dtype, device=w.device)
+            up_all = torch.empty((world * nw,) + tuple(r_up.shape[1:]), dtype=r_up.dtype, device=r_up.device)
+            dn_all = torch.empty((world * nw,) + tuple(r_dn.shape[1:]), dtype=r_dn.dtype, device=r_dn.device)
+            d.all_gather_into_tensor(w_all, w.contiguous())
+            d.all_gather_into_tensor(up_all, r_up.contiguous())
+            if r_dn.numel():
+                d.all_gather_into_tensor(dn_all, r_dn.contiguous())
+        else:
+            w_all, up_all, dn_all = w, r_up, r_dn
+        chosen_all, n_surv = eng.lrdmc_branch(w_all, nw, zeta)
+        r_up, r_dn = eng.gather_walkers(chosen_all[rank * nw : (rank + 1) * nw], up_all, dn_all)
+        A_inv = eng.A_inv_n(r_up, r_dn)
+        return r_up, r_dn, keys, A_inv, sums, n_surv
+
+    def run(self, num_mcmc_steps: int = 50, max_time: int = 86400) -> None:
+        rank, world = _rank_size()
+        eng = self.engine
+        t_start = time.perf_counter()
+        zeta_rng = np.random.RandomState(self.__mcmc_seed % (2**32))  # rank 0's stream after np.random.seed(mpi_seed), :4669
+        A_inv = eng.A_inv_n(self.__r_up, self.__r_dn)
+        r_up, r_dn, keys = self.__r_up, self.__r_dn, self.__keys
+        base = self.__mcmc_counter
+        n_store = base + num_mcmc_steps
+        self.__stored_e_L = np.concatenate([self.__stored_e_L, np.zeros((num_mcmc_steps, 1))])
+        self.__stored_e_L2 = np.concatenate([self.__stored_e_L2, np.zeros((num_mcmc_steps, 1))])
+        self.__stored_w_L = np.concatenate([self.__stored_w_L, np.zeros((num_mcmc_steps, 1))])
+        mcmc_interval = int(np.maximum(num_mcmc_steps / 100, 1))
+        eq_steps, n_collect, n_bins = GFMC_ON_THE_FLY_WARMUP_STEPS, GFMC_ON_THE_FLY_COLLECT_STEPS, GFMC_ON_THE_FLY_BIN_BLOCKS
+        pending = []  # (step index, device sums, device n_survived) not yet read back
+        done = 0
+
+        def flush():
+            # one device->host read for all pending steps (the reference reads every array every step)
+            if not pending:
+                return
+            S = torch.stack([p[1] for p in pending]).cpu().numpy()
+            NS = torch.stack([p[2].reshape(()) for p in pending]).cpu().numpy()
+            for (i, _, _), s, ns in zip(pending, S, NS):
+                nw_sum, w_sum, wq, weq, we2q = s
+                self.__stored_w_L[base + i, 0] = w_sum / nw_sum
+                self.__stored_e_L[base + i, 0] = weq / wq
+                self.__stored_e_L2[base + i, 0] = we2q / wq
+                self.__num_survived_walkers += int(ns)
+                self.__num_killed_walkers += int(nw_sum) - int(ns)
+                if i >= n_collect:  # :6336-6343
+                    G = np.prod(self.__stored_w_L[base + i - n_collect : base + i], axis=0)
+                    self.__G_L.append(G)
+                    self.__G_e_L.append(G * self.__stored_e_L[base + i])
+            pending.clear()
+
+        for i in range(num_mcmc_steps):
+            zeta = float(zeta_rng.random_sample())
+            r_up, r_dn, keys, A_inv, sums, n_surv = self._step(r_up, r_dn, keys, A_inv, zeta, rank, world)
+            pending.append((i, sums, n_surv))
+            if (i + 1) % mcmc_interval == 0 and i > eq_steps:  # :6345-6378
+                flush()
+                n_warm = int(np.minimum(eq_steps, i - eq_steps))
+                G_eq, G_e_eq = np.array(self.__G_L[n_warm:]), np.array(self.__G_e_L[n_warm:])
+                if len(G_eq) >= n_bins:
+                    self.__E_scf, _ = jackknife_E_scf(G_eq, G_e_eq, n_bins)
+            done += 1
+            if time.perf_counter() - t_start > max_time:
+                flush()
+                break
+        flush()
+        self.__mcmc_counter += done
+        ns = self.__mcmc_counter
+        self.__stored_e_L = self.__stored_e_L[:ns]
+        self.__stored_e_L2 = self.__stored_e_L2[:ns]
+        self.__stored_w_L = self.__stored_w_L[:ns]
+        assert n_store >= ns
+        self.__r_up, self.__r_dn, self.__keys = r_up, r_dn, keys
+        self.__timer["total"] += time.perf_counter() - t_start
+
+    def get_E(self, num_mcmc_warmup_steps: int = 50, num_mcmc_bin_blocks: int = 10):
+        """(E_mean, E_std, Var_mean, Var_std): binned jackknife with the accumulated weights G_L
+        (jqmc/jqmc_gfmc.py:6500-6700).  Every rank holds the same (M, 1) history, so no collective is needed."""
+        if self.mcmc_counter < num_mcmc_warmup_steps:
+            raise ValueError("mcmc_counter should be larger than num_mcmc_warmup_steps")
+        if self.mcmc_counter - num_mcmc_warmup_steps < num_mcmc_bin_blocks:
+            raise ValueError("(mcmc_counter - num_mcmc_warmup_steps) should be larger than num_mcmc_bin_blocks.")
+        e_L = self.e_L[num_mcmc_warmup_steps:]
+        e_L2 = self.e_L2[num_mcmc_warmup_steps:]
+        w_L = self.w_L[num_mcmc_warmup_steps:]
+
+        def binned(x):
+            return np.ravel([np.sum(a, axis=0) for a in np.array_split(x, num_mcmc_bin_blocks, axis=0)])
+
+        wb, web, we2b = binned(w_L), binned(w_L * e_L), binned(w_L * e_L2)
+        M = wb.size
+        E_jk = (np.sum(web) - web) / (np.sum(wb) - wb)
+        E2_jk = (np.sum(we2b) - we2b) / (np.sum(wb) - wb)
+        Var_jk = E2_jk - E_jk**2
+        E_mean = np.sum(E_jk) / M
+        E_std = np.sqrt((M - 1) * np.sum((E_jk - E_mean) ** 2) / M)
+        Var_mean = np.sum(Var_jk) / M
+        Var_std = np.sqrt((M - 1) * np.sum((Var_jk - Var_mean) ** 2) / M)
+        return float(E_mean), float(E_std), float(Var_mean), float(Var_std)

@@ -277,3 +277,41 @@ def lrdmc_projection(H, w, r_up, r_dn, Ginv, key, E_scf, nmpm, random_discretize
             trace.append(dict(k=k, u=u, b_x=b_x, diag=diag, nondiag=nondiag, spin_up=spin_up, idx=idx))
         r_up, r_dn = p_up, p_dn
     return w, r_up, r_dn, Ginv, key, RT, diag, nondiag
+
+
+# --------------------------------------------------------------------------------------
+# GFMC_n per-step statistics and walker reconfiguration    jqmc/jqmc_gfmc.py:5955-6321
+# --------------------------------------------------------------------------------------
+def lrdmc_collect(w, V_diag, V_nondiag, E_scf):
+    """[nw, sum w, sum w/(Vd-E), sum w/(Vd-E) e_L, sum w/(Vd-E) e_L^2] of one rank (:5971-5976)."""
+    w, Vd, Vn = (np.asarray(x, dtype=np.float64) for x in (w, V_diag, V_nondiag))
+    e = Vd + Vn
+    q = w / (Vd - E_scf)
+    return np.array([len(w), np.sum(w), np.sum(q), np.sum(q * e), np.sum(q * e**2)])
+
+
+def lrdmc_branch_indices(w_per_rank, zeta):
+    """Comb reconfiguration indices, rank by rank exactly as the reference computes them with NumPy + MPI
+    (:6069-6135): returns (chosen_all[int32, world*nw], n_survived)."""
+    w_per_rank = [np.asarray(w, dtype=np.float64) for w in w_per_rank]
+    world, nw = len(w_per_rank), len(w_per_rank[0])
+    global_weight_sum = 0.0
+    for w in w_per_rank:  # allreduce(SUM) of the local np.sum
+        global_weight_sum = global_weight_sum + np.sum(w)
+    cum, sums = [], []
+    for w in w_per_rank:
+        p = w / global_weight_sum
+        cum.append(np.cumsum(p))
+        sums.append(np.sum(p))
+    offset = 0.0
+    for r in range(world):  # Exscan: rank 0 uses 0.0
+        cum[r] = cum[r] + (0.0 if r == 0 else offset)
+        offset = offset + sums[r] if r > 0 else sums[0]
+    global_cumprob = np.concatenate(cum)
+    total = world * nw
+    chosen = []
+    for r in range(world):
+        z_local = (np.arange(r * nw, (r + 1) * nw) + zeta) / total
+        chosen.append(np.searchsorted(global_cumprob, z_local).astype(np.int32))
+    chosen = np.minimum(np.concatenate(chosen), total - 1).astype(np.int32)
+    return chosen, len(np.unique(chosen))

@@ -1,0 +1,89 @@
+"""Test double of ``jqmc_b200.engine.WalkerEngine`` backed by the CPU oracle (TEST INFRASTRUCTURE).
+
+It lets the host-side drivers (``jqmc_b200.mcmc.MCMC``, ``jqmc_b200.gfmc.GFMC_n``) and their collectives run on a
+machine without a GPU (``gloo`` backend), so that the N > 1 orchestration is covered by CPU tests.  It lives under
+tests/ on purpose: the product never falls back to it.
+"""
+
+import numpy as np
+import torch
+
+from oracle import drivers as OD
+from oracle import physics as OP
+
+
+def _np(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def _key(k):
+    return (int(k[0]), int(k[1]))
+
+
+class OracleEngine:
+    device = torch.device("cpu")
+
+    def __init__(self, H):
+        self.H = H
+        gem = H.wavefunction_data.geminal_data
+        self.n_up, self.n_dn = gem.num_electron_up, gem.num_electron_dn
+
+    def _t(self, a, dtype=torch.float64):
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(a))).to(dtype)
+
+    def geminal_inv_batched(self, r_up, r_dn):
+        r_up, r_dn = _np(r_up), _np(r_dn)
+        out = [OD.geminal_inv(self.H.wavefunction_data.geminal_data, u, d) for u, d in zip(r_up, r_dn)]
+        return self._t([o[0] for o in out]), self._t([o[1] for o in out])
+
+    def A_inv_n(self, r_up, r_dn):
+        return self.geminal_inv_batched(r_up, r_dn)[1]
+
+    def update(self, r_up, r_dn, keys, nmpm, Dt, eps, Ginv, G, inplace=False):
+        r_up, r_dn, keys, Ginv, G = (_np(x) for x in (r_up, r_dn, keys, Ginv, G))
+        res = [
+            OD.update_electron_positions(self.H, r_up[w], r_dn[w], _key(keys[w]), nmpm, Dt, eps, Ginv[w], G[w])
+            for w in range(len(r_up))
+        ]
+        acc = torch.tensor([r[0] for r in res], dtype=torch.int32)
+        rej = torch.tensor([r[1] for r in res], dtype=torch.int32)
+        k2 = torch.from_numpy(np.array([r[4] for r in res], dtype=np.uint32))
+        return acc, rej, self._t([r[2] for r in res]), self._t([r[3] for r in res]), k2, self._t([r[5] for r in res]), self._t([r[6] for r in res])
+
+    def generate_RTs(self, keys):
+        return self._t([OD.generate_rotation_matrix(_key(k)) for k in _np(keys)])
+
+    def e_L_fast(self, r_up, r_dn, RTs, Ginv):
+        r_up, r_dn, Ginv = _np(r_up), _np(r_dn), _np(Ginv)
+        RTs = _np(RTs) if RTs is not None else [np.eye(3)] * len(r_up)
+        return self._t([OP.compute_local_energy(self.H, r_up[w], r_dn[w], RTs[w], Ginv=Ginv[w]) for w in range(len(r_up))])
+
+    def as_reg_fast(self, G, Ginv):
+        return self._t([OP.compute_AS_regularization_factor(g, gi) for g, gi in zip(_np(G), _np(Ginv))])
+
+    def projection_n(self, w, r_up, r_dn, A_inv, keys, E_scf, nmpm, mesh, nlm, alat, inplace=False):
+        w, r_up, r_dn, A_inv, keys = (_np(x) for x in (w, r_up, r_dn, A_inv, keys))
+        res = [
+            OD.lrdmc_projection(self.H, w[i], r_up[i], r_dn[i], A_inv[i], _key(keys[i]), E_scf, nmpm, mesh, nlm, alat)
+            for i in range(len(w))
+        ]
+        k2 = torch.from_numpy(np.array([r[4] for r in res], dtype=np.uint32))
+        cols = lambda j: self._t([r[j] for r in res])  # noqa: E731
+        return cols(0), cols(1), cols(2), cols(3), k2, cols(5), cols(6), cols(7)
+
+    def V_elements_n(self, r_up, r_dn, RTs, nlm, alat, A_inv=None):
+        r_up, r_dn, RTs = _np(r_up), _np(r_dn), _np(RTs)
+        res = [OD.lrdmc_V_elements(self.H, r_up[i], r_dn[i], RTs[i], nlm, alat) for i in range(len(r_up))]
+        return self._t([r[0] for r in res]), self._t([r[1] for r in res])
+
+    def lrdmc_collect(self, w, Vd, Vn, E_scf):
+        return self._t(OD.lrdmc_collect(_np(w), _np(Vd), _np(Vn), E_scf))
+
+    def lrdmc_branch(self, w_all, nw, zeta):
+        w_all = _np(w_all)
+        chosen, ns = OD.lrdmc_branch_indices(np.split(w_all, len(w_all) // nw), zeta)
+        return torch.from_numpy(chosen), torch.tensor([ns], dtype=torch.int32)
+
+    def gather_walkers(self, chosen_local, src_up, src_dn):
+        idx = torch.as_tensor(_np(chosen_local).astype(np.int64))
+        return src_up[idx].clone(), src_dn[idx].clone()

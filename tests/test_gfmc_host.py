@@ -1,0 +1,167 @@
+"""Host-side LRDMC driver (jqmc_b200.gfmc.GFMC_n) on CPU: the step loop, the per-step reductions and the walker
+reconfiguration run through the real driver with an oracle-backed engine double, single process and with two
+``gloo`` ranks (the N > 1 path: all_reduce of the weighted sums, all_gather of weights and coordinates, identical
+comb on every rank).  Reference behaviour: jqmc/jqmc_gfmc.py:5774-6417; the reference's own two-rank test is
+tests/test_jqmc_gfmc_bra.py run under ``mpirun -np 2``."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from jqmc_b200 import rng_host
+from jqmc_b200.data import Jastrow_data, Jastrow_two_body_data
+from jqmc_b200.gfmc import GFMC_n, compute_G_L, jackknife_E_scf
+from jqmc_b200.mcmc import generate_init_electron_configurations
+from oracle import drivers as OD
+from tests.conftest import load_system
+from tests.oracle_engine import OracleEngine
+
+NW, NMPM, STEPS, SEED, ALAT, E_SCF = 2, 2, 3, 3446, 0.3, -1.0
+
+
+def _system():
+    H = load_system("H2_ae_ccpvdz_cart")
+    H.wavefunction_data.jastrow_data = Jastrow_data(jastrow_two_body_data=Jastrow_two_body_data(jastrow_2b_param=0.75))
+    return H
+
+
+def _reference_run(H, world):
+    """The same branching steps for `world` ranks emulated sequentially with plain oracle calls."""
+    gem, cp = H.wavefunction_data.geminal_data, H.coulomb_potential_data
+    ranks = []
+    for r in range(world):
+        seed = SEED * (r + 1)
+        keys = [tuple(int(x) for x in k) for k in rng_host.split(rng_host.PRNGKey(seed), NW)]
+        np.random.seed(seed)
+        r_up, r_dn, _, _ = generate_init_electron_configurations(
+            gem.num_electron_up, gem.num_electron_dn, NW, cp.effective_charges, H.structure_data.positions
+        )
+        ranks.append(dict(keys=keys, r_up=r_up, r_dn=r_dn))
+    zeta_rng = np.random.RandomState(SEED)
+    hist = []
+    for _ in range(STEPS):
+        W, S = [], np.zeros(5)
+        for st in ranks:
+            w_new, Vd, Vn = [], [], []
+            for i in range(NW):
+                _, Ginv = OD.geminal_inv(gem, st["r_up"][i], st["r_dn"][i])
+                w, ru, rd, _, key, RT, _, _ = OD.lrdmc_projection(
+                    H, 1.0, st["r_up"][i], st["r_dn"][i], Ginv, st["keys"][i], E_SCF, NMPM, True, "tmove", ALAT
+                )
+                st["r_up"][i], st["r_dn"][i], st["keys"][i] = ru, rd, key
+                d, n = OD.lrdmc_V_elements(H, ru, rd, RT, "tmove", ALAT)
+                w_new.append(w), Vd.append(d), Vn.append(n)
+            W.append(np.array(w_new))
+            S += OD.lrdmc_collect(w_new, Vd, Vn, E_SCF)
+        chosen, ns = OD.lrdmc_branch_indices(W, zeta_rng.random_sample())
+        up_all = np.concatenate([st["r_up"] for st in ranks])
+        dn_all = np.concatenate([st["r_dn"] for st in ranks])
+        for r, st in enumerate(ranks):
+            st["r_up"] = up_all[chosen[r * NW : (r + 1) * NW]].copy()
+            st["r_dn"] = dn_all[chosen[r * NW : (r + 1) * NW]].copy()
+        hist.append((S[1] / S[0], S[3] / S[2], S[4] / S[2], ns))
+    return hist, ranks
+
+
+def _driver_run(H):
+    g = GFMC_n(H, num_walkers=NW, num_mcmc_per_measurement=NMPM, num_gfmc_collect_steps=1, mcmc_seed=SEED, E_scf=E_SCF, alat=ALAT,
+               engine=OracleEngine(H))  # fmt: skip
+    g.run(STEPS)
+    return g
+
+
+def _check(g, hist, ranks, rank):
+    np.testing.assert_allclose(g.bare_w_L[:, 0], [h[0] for h in hist], rtol=1e-12)
+    np.testing.assert_allclose(g.e_L[:, 0], [h[1] for h in hist][1:], rtol=1e-12)
+    np.testing.assert_allclose(g.e_L2[:, 0], [h[2] for h in hist][1:], rtol=1e-12)
+    assert g.num_survived_walkers == sum(h[3] for h in hist)
+    np.testing.assert_array_equal(g.latest_r_up_carts.numpy(), ranks[rank]["r_up"])
+    np.testing.assert_array_equal(g.latest_r_dn_carts.numpy(), ranks[rank]["r_dn"])
+    assert [tuple(int(x) for x in k) for k in g.jax_PRNG_key_list.numpy()] == ranks[rank]["keys"]
+
+
+def test_gfmc_n_single_rank():
+    H = _system()
+    hist, ranks = _reference_run(H, 1)
+    g = _driver_run(H)
+    _check(g, hist, ranks, 0)
+    assert g.mcmc_counter == STEPS - 1 and g.w_L.shape == (STEPS - 1, 1)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        H = _system()
+        g = _driver_run(H)
+        q.put((rank, g.bare_w_L.copy(), g.e_L.copy(), g.e_L2.copy(), g.num_survived_walkers, g.latest_r_up_carts.numpy().copy(),
+               g.latest_r_dn_carts.numpy().copy(), g.jax_PRNG_key_list.numpy().copy()))  # fmt: skip
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_gfmc_n_two_ranks_gloo():
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = {}
+    for _ in procs:
+        res = q.get(timeout=500)
+        out[res[0]] = res[1:]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    H = _system()
+    hist, ranks = _reference_run(H, 2)
+    for rank in range(2):
+        w, e, e2, nsv, ru, rd, keys = out[rank]
+        np.testing.assert_allclose(w[:, 0], [h[0] for h in hist], rtol=1e-12)
+        np.testing.assert_allclose(e[:, 0], [h[1] for h in hist][1:], rtol=1e-12)
+        np.testing.assert_allclose(e2[:, 0], [h[2] for h in hist][1:], rtol=1e-12)
+        assert nsv == sum(h[3] for h in hist)
+        np.testing.assert_array_equal(ru, ranks[rank]["r_up"])
+        np.testing.assert_array_equal(rd, ranks[rank]["r_dn"])
+        assert [tuple(int(x) for x in k) for k in keys] == ranks[rank]["keys"]
+
+
+def test_G_L_and_E_scf_jackknife():
+    rng = np.random.default_rng(0)
+    w = rng.uniform(0.9, 1.1, size=(40, 1))
+    G = compute_G_L(w, 5)
+    assert G.shape == (35, 1)
+    np.testing.assert_allclose(G[0, 0], np.prod(w[0:5, 0]))
+    np.testing.assert_allclose(G[-1, 0], np.prod(w[34:39, 0]))
+    e = rng.normal(-17.0, 0.1, size=35)
+    E, s = jackknife_E_scf(G[:, 0], G[:, 0] * e, 10)
+    assert abs(E - np.sum(G[:, 0] * e) / np.sum(G[:, 0])) < 1e-3 and 0 < s < 0.1
+
+
+def test_branch_oracle_properties():
+    rng = np.random.default_rng(1)
+    w = [rng.uniform(0.5, 1.5, size=64) for _ in range(3)]
+    chosen, ns = OD.lrdmc_branch_indices(w, 0.37)
+    assert chosen.shape == (192,) and np.all(np.diff(chosen) >= 0) and 0 <= chosen.min() and chosen.max() < 192
+    assert ns == len(np.unique(chosen))
+    # equal weights: the comb picks every walker exactly once
+    chosen, ns = OD.lrdmc_branch_indices([np.ones(8), np.ones(8)], 0.5)
+    np.testing.assert_array_equal(chosen, np.arange(16))
+    # a walker with (almost) all the weight takes every slot
+    ww = np.full(8, 1e-14)
+    ww[5] = 1.0
+    chosen, ns = OD.lrdmc_branch_indices([ww], 0.2)
+    assert ns == 1 and np.all(chosen == 5)
+    assert isinstance(torch.tensor(chosen), torch.Tensor)

@@ -365,3 +365,73 @@ def test_lrdmc_projection_trajectory(name, jas, nlm, mesh):
         np.testing.assert_allclose(Vd[i], od, rtol=1e-8)
         np.testing.assert_allclose(Vn[i], on, rtol=1e-8)
         np.testing.assert_allclose(Gi[i], oGi, rtol=1e-7, atol=1e-9 * np.abs(oGi).max())
+
+
+@pytest.mark.parametrize("world,nw", [(1, 4096), (2, 1000), (8, 4096), (3, 7)])
+def test_lrdmc_branch_indices_bit_exact(water, world, nw):
+    """a30 reconfiguration: comb indices over the all-gathered weights are bit-identical to the reference's
+    NumPy/MPI arithmetic (np.sum pairwise, np.cumsum, Exscan offsets, searchsorted), survivors counted alike."""
+    eng = _engine(water)
+    rng = np.random.default_rng(100 + world)
+    for trial in range(3):
+        w = rng.uniform(0.2, 1.8, size=world * nw) * np.exp(rng.normal(scale=0.3, size=world * nw))
+        if trial == 2:
+            w[rng.integers(0, world * nw, size=max(1, nw // 10))] *= 40.0  # heavy walkers taking many slots
+        zeta = float(rng.random())
+        chosen, ns = eng.lrdmc_branch(w, nw, zeta)
+        ref, ref_ns = OD.lrdmc_branch_indices(np.split(w, world), zeta)
+        np.testing.assert_array_equal(chosen.cpu().numpy(), ref)
+        assert int(ns.item()) == ref_ns
+
+
+def test_lrdmc_collect_and_gather(water):
+    eng = _engine(water)
+    rng = np.random.default_rng(5)
+    nw = 777
+    w, Vd, Vn = rng.uniform(0.5, 1.5, nw), rng.normal(-10, 1, nw), rng.normal(-7, 1, nw)
+    out = eng.lrdmc_collect(w, Vd, Vn, -17.2).cpu().numpy()
+    np.testing.assert_allclose(out, OD.lrdmc_collect(w, Vd, Vn, -17.2), rtol=1e-13)
+    src_up, src_dn = rng.normal(size=(3 * nw, 4, 3)), rng.normal(size=(3 * nw, 4, 3))
+    idx = rng.integers(0, 3 * nw, size=nw).astype(np.int32)
+    du, dd = eng.gather_walkers(idx, src_up, src_dn)
+    np.testing.assert_array_equal(du.cpu().numpy(), src_up[idx])
+    np.testing.assert_array_equal(dd.cpu().numpy(), src_dn[idx])
+    with pytest.raises(ValueError):
+        eng.lrdmc_branch(np.ones(10), 3, 0.5)
+    with pytest.raises(ValueError):
+        eng.lrdmc_branch(np.ones(8), 4, 1.5)
+
+
+def test_gfmc_n_driver_matches_oracle_loop():
+    """a30: GFMC_n.run on the engine == the same branching steps done with plain oracle calls (same seeds):
+    stored averages, survivors, final walkers and keys."""
+    from jqmc_b200.gfmc import GFMC_n
+    from tests import test_gfmc_host as TH
+
+    H = TH._system()
+    hist, ranks = TH._reference_run(H, 1)
+    g = GFMC_n(H, num_walkers=TH.NW, num_mcmc_per_measurement=TH.NMPM, num_gfmc_collect_steps=1, mcmc_seed=TH.SEED, E_scf=TH.E_SCF,
+               alat=TH.ALAT)  # fmt: skip
+    g.run(TH.STEPS)
+    np.testing.assert_allclose(g.bare_w_L[:, 0], [h[0] for h in hist], rtol=1e-9)
+    np.testing.assert_allclose(g.e_L[:, 0], [h[1] for h in hist][1:], rtol=1e-9)
+    assert g.num_survived_walkers == sum(h[3] for h in hist)
+    np.testing.assert_allclose(g.latest_r_up_carts.cpu().numpy(), ranks[0]["r_up"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(g.latest_r_dn_carts.cpu().numpy(), ranks[0]["r_dn"], rtol=0, atol=1e-11)
+    assert [tuple(int(x) for x in k) for k in g.jax_PRNG_key_list.cpu().numpy()] == ranks[0]["keys"]
+
+
+def test_gfmc_n_driver_water_runs(water):
+    """LRDMC on the BASELINE system: 30 branching steps with 64 walkers; energies finite and in the physical range,
+    E_scf updated on the fly, get_E works."""
+    from jqmc_b200.gfmc import GFMC_n
+
+    H = _with_jastrow(water, "j2pade")
+    g = GFMC_n(H, num_walkers=64, num_mcmc_per_measurement=10, num_gfmc_collect_steps=2, mcmc_seed=11, E_scf=-17.0, alat=0.3)
+    g.run(30)
+    assert g.mcmc_counter == 28 and g.e_L.shape == (28, 1)
+    assert np.all(np.isfinite(g.e_L)) and -19.0 < g.e_L[5:].mean() < -15.5
+    assert g.E_scf != -17.0
+    E, s, V, sv = g.get_E(num_mcmc_warmup_steps=8, num_mcmc_bin_blocks=5)
+    assert -19.0 < E < -15.5 and s > 0
+    assert 0.5 < g.num_survived_walkers / (g.num_survived_walkers + g.num_killed_walkers) <= 1.0
