@@ -167,6 +167,10 @@ int qe_gather_walkers(qe_engine* h, int nw, const int32_t* chosen_local, const d
  * `on` != 0 (default); otherwise as a chain of staged kernels through a global workspace.  Same results. */
 int qe_set_fused(qe_engine* h, int on);
 
+/* Walkers per CTA of the fused walker kernel: 0 = chosen automatically so that the grid fills the SMs (default),
+ * 1..32 = fixed (tuning / tests; results do not depend on it beyond round-off of partial-sum order). */
+int qe_set_walkers_per_cta(qe_engine* h, int wpc);
+
 /* Microbenchmark used by bench.py for the fp64 roofline denominator: runs `iters` dependent-free
  * DFMA per thread on a full grid and returns the achieved TFLOP/s (synchronous). */
 int qe_measure_fp64_peak(int iters, double* tflops);

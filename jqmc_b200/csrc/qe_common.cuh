@@ -45,10 +45,12 @@ struct DevPool {
   }
 };
 
+#define QE_N_CHUNK 15  // target number of balanced basis chunks (partial sums are added in chunk order)
 struct HostBasis {
   BasisDev dev{};
-  std::vector<int> chunk_begin;  // balanced chunks of groups, chunk_begin[n_chunk+1]
-  std::vector<double> grp_cost;
+  int n_chunk = 1;   // balanced shell-granular chunks of the basis (deterministic partial sums)
+  int off_cseg = 0;  // byte offset of the chunk segment list (int4, same format as the group list) in the blob
+  int off_cbeg = 0;  // byte offset of chunk_begin[n_chunk+1] (first segment of each chunk)
   bool present = false;
 };
 
@@ -83,8 +85,7 @@ struct SysDev {
 
 struct qe_engine {
   DevPool pool;
-  HostBasis b_up, b_dn, b_j3;
-  bool same_ao_updn = true;
+  HostBasis b_up, b_j3;  // b_up carries both spins' MO coefficient tables (the AO tables are shared: checked at create)
   SysDev sys{};
   int nmo_pad = 4;
   // workspace
@@ -96,13 +97,9 @@ struct qe_engine {
   // optional per-kernel timing (qe_profile): CUDA events recorded on the launch stream around each kernel
   bool profiling = false;
   bool fused = true;  // qe_local_energy uses the fused walker kernel when the system fits
+  int wpc_override = 0;  // walkers per CTA of the fused walker kernel (0 = automatic)
   struct ProfRec { int id; cudaEvent_t e0, e1; };
   std::vector<ProfRec> prof;
-  int n_chunk_el = 1;    // chunks used by the electron VGL pass
-  int n_chunk_mc = 1;    // chunk warps of the Metropolis kernel
-  std::vector<int> chunk_el, chunk_mc;
-  const int* d_chunk_el = nullptr;
-  const int* d_chunk_mc = nullptr;
 };
 
 enum KernelId { K_ORB_EL = 0, K_GEMINAL, K_ALGEBRA, K_ECP_MESH, K_REDUCE, K_RATIOS, K_AS, K_ROT, K_KEYCHAIN, K_DRAWS, K_MCMC,
@@ -182,13 +179,23 @@ __device__ __forceinline__ int nearest_atom(const double* __restrict__ Rn, int n
 
 __device__ __forceinline__ double j1_f(int type, double a, double A, double c, double d) {
   // jqmc/jastrow_factor.py:648-726
-  if (type == 1) return -A * (1.0 - exp(-a * c * d)) / (2.0 * a);
+  if (type == 1) return -A * (1.0 - qexp(-a * c * d)) / (2.0 * a);
   return -A * d / (2.0 * (1.0 + a * c * d));
 }
 __device__ __forceinline__ double j2_f(int type, double a, double d) {
   // jqmc/jastrow_factor.py:1180-1251
   if (type == 1) return d / (2.0 * (1.0 + a * d));
-  return (1.0 - exp(-a * d)) / (2.0 * a);
+  return (1.0 - qexp(-a * d)) / (2.0 * a);
+}
+
+// d^n for the small integer powers of the ECP radial terms (stored as doubles; TREXIO power + 2, jqmc/coulomb_potential.py:1562-1568)
+__device__ __forceinline__ double ipow(double d, double pw) {
+  const int n = (int)pw;
+  if ((double)n != pw) return pow(d, pw);
+  double r = 1.0;
+  const int m = n < 0 ? -n : n;
+  for (int i = 0; i < m; ++i) r *= d;
+  return n < 0 ? 1.0 / r : r;
 }
 
 // Legendre P_l(x), l <= 6 (jqmc/_function_collections.py:47-65)
@@ -217,6 +224,30 @@ struct PosGlobal {
     z = p[2];
   }
 };
+
+// Part of the Jastrow exponent (J1+J2) that depends on electron e when it sits at (x,y,z):
+//   sum_a j1(|x - R_a|) + sum_{j != e} j2(|x - r_j|);   J(r') - J(r) = jastrow_single(r') - jastrow_single(r)
+template <class Pos>
+__device__ __forceinline__ double jastrow_single(const SysDev& S, const Pos& pos, int e, double x, double y, double z) {
+  double J = 0.0;
+  if (S.j1_type) {
+    for (int a = 0; a < S.n_atom; ++a) {
+      const double X = S.Rn[3 * a], Y = S.Rn[3 * a + 1], Z = S.Rn[3 * a + 2];
+      const double d = sqrt((x - X) * (x - X) + (y - Y) * (y - Y) + (z - Z) * (z - Z));
+      J += j1_f(S.j1_type, S.j1_a, S.j1_A[a], S.j1_c[a], d);
+    }
+  }
+  if (S.j2_type) {
+    for (int j = 0; j < S.n_e; ++j) {
+      if (j == e) continue;
+      double xj, yj, zj;
+      pos.get(j, xj, yj, zj);
+      const double d = sqrt((x - xj) * (x - xj) + (y - yj) * (y - yj) + (z - zj) * (z - zj));
+      J += j2_f(S.j2_type, S.j2_a, d);
+    }
+  }
+  return J;
+}
 
 // Jastrow (J1+J2) difference J(r') - J(r) for moving electron e from (ox,oy,oz) to (nx,ny,nz)
 template <class Pos>

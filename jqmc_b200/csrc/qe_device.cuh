@@ -12,22 +12,58 @@ namespace qe {
 constexpr int MAXF = 28;  // max functions per shell: Cartesian l=6 -> 28; spherical l=6 -> 13
 
 // ------------------------------------------------------------------------------------------------
-// Basis tables in device memory (built by qe_engine.cu::build_basis from the reference's per-AO tables:
-// AOs_sphe_data jqmc/atomic_orbital.py:780-929 / AOs_cart_data :87-258 / MOs_data molecular_orbital.py:85-140)
+// Basis image: ONE contiguous blob per AO basis, built by qe_engine.cu::build_basis from the reference's per-AO
+// tables (AOs_sphe_data jqmc/atomic_orbital.py:780-929 / AOs_cart_data :87-258 / MOs_data molecular_orbital.py:85-140)
+// and read either from global memory or, after one cooperative copy, from shared memory (`tab` below is the base of
+// whichever copy a kernel uses; every table is addressed as tab + byte offset so that the compiler keeps the address
+// space of `tab`: LDS for staged tables, LDG otherwise).
+//   seg  int4   {nucleus, l, shell_begin, shell_end}       one per (nucleus, l) group; chunk lists reuse the format
+//   sh   int4   {prim_begin, prim_end, row0, 0}            row0 = first row of the shell in the row-ordered tables
+//   pr   double2{-exponent, coefficient * N_p * sqrt((2l+1)/4pi)}   (jqmc/atomic_orbital.py:2316-2349; Cartesian :2243-2244)
+//   C    double [n_row][nmo_pad]   transposed MO coefficients * per-AO scale, rows in canonical shell order (row0 + k);
+//                                  rows of functions a shell does not have are zero
+//   row_ao int[n_row], row_scale double[n_row]            AO index (-1: hole) and per-AO scale of each row
+//   Rn   double [n_atom*3]
 // ------------------------------------------------------------------------------------------------
 struct BasisDev {
-  int n_ao, n_mo, n_orb, n_grp, n_shell, cart;
-  int nmo_pad;               // MO accumulators per thread (4, 8 or 16); Cs rows are zero-padded to this
-  const int* grp_nuc;        // [n_grp]   nucleus of the group
-  const int* grp_l;          // [n_grp]   angular momentum of the group
-  const int* grp_sh_begin;   // [n_grp+1] shell range of the group
-  const int* sh_prim_off;    // [n_shell+1]
-  const short* sh_slot;      // [n_shell*MAXF] AO index of canonical function k, or -1
-  int n_prim;                // compressed shell primitives
-  const double2* pr_zc;      // [n_prim] {exponent, coefficient * N_p * sqrt((2l+1)/4pi)}  (jqmc/atomic_orbital.py:2316-2349)
-  const double* ao_scale;    // [n_ao]   per-AO factor (shell-relative coefficient ratio, Cartesian factorial part)
-  const double* Cs;          // [n_ao*nmo_pad]  mo_coefficients^T * ao_scale  (MO layer), or nullptr
+  int n_ao, n_mo, n_orb, n_grp, n_shell, n_prim, n_row, cart, lmax;
+  int nmo_pad;                // MO accumulators per thread (4, 8 or 16); C rows are zero-padded to this
+  int off_seg, off_sh, off_pr, off_C, off_C2, off_rowao, off_rowscale, off_Rn;  // byte offsets into the blob (16-aligned)
+  int bytes;                  // blob size (multiple of 16)
+  const char* g;              // blob in global memory
 };
+
+// ------------------------------------------------------------------------------------------------
+// exp(x) for -707 <= x < 709 (every exponential on the hot path: Gaussian primitives, Jastrow, ECP radial terms, ratios).
+// Branch-free: k = rint(x log2 e) by the magic-number trick, r = x - k ln2 (two-term Cody-Waite with FMA),
+// degree-11 near-minimax polynomial (max relative error 1.7e-17 before rounding), scaling by 2^k through the exponent
+// field.  Arguments below -707 return a denormal (< 2.3e-308) instead of the exact tiny value: irrelevant at fp64 resolution.
+// ------------------------------------------------------------------------------------------------
+__constant__ double QE_EXPC[16] = {1.4426950408889634,      6755399441055744.0,      -0.6931471805599453,      -2.3190468138462996e-17,
+                                   2.5110037605963777e-08,  2.763263963904103e-07,   2.755724091857897e-06,    2.4801485482328494e-05,
+                                   0.00019841269890047113,  0.0013888888952314775,   0.008333333333319601,     0.0416666666664881,
+                                   0.1666666666666668,      0.5000000000000019,      1.0,                      -707.0};
+__device__ __forceinline__ double qexp(double x) {
+  // constants come from the constant bank (DFMA takes a c[][] operand directly; 64-bit immediates would cost two UMOVs each)
+  const bool under = x < QE_EXPC[15];  // result below 1e-307: return (a denormal close to) zero
+  const double t = fma(x, QE_EXPC[0], QE_EXPC[1]);
+  const double k = t - QE_EXPC[1];
+  double r = fma(k, QE_EXPC[2], x);
+  r = fma(k, QE_EXPC[3], r);
+  double p = QE_EXPC[4];
+  p = fma(p, r, QE_EXPC[5]);
+  p = fma(p, r, QE_EXPC[6]);
+  p = fma(p, r, QE_EXPC[7]);
+  p = fma(p, r, QE_EXPC[8]);
+  p = fma(p, r, QE_EXPC[9]);
+  p = fma(p, r, QE_EXPC[10]);
+  p = fma(p, r, QE_EXPC[11]);
+  p = fma(p, r, QE_EXPC[12]);
+  p = fma(p, r, QE_EXPC[13]);
+  p = fma(p, r, QE_EXPC[14]);
+  p = fma(p, r, QE_EXPC[14]);
+  return __hiloint2double(under ? 0 : __double2hiint(p) + (__double2loint(t) << 20), __double2loint(p));
+}
 
 // ------------------------------------------------------------------------------------------------
 // Threefry-2x32 and the jax.random draws used by jQMC (semantics: oracle/jaxrng.py)
@@ -133,7 +169,8 @@ __device__ __forceinline__ double rng_normal(Key k) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per-thread AO evaluator.  A sink receives (ao index, value[, gx, gy, gz, lap]) WITHOUT ao_scale.
+// Per-thread AO sweep.  A sink receives (row, value[, gx, gy, gz, lap]) WITHOUT the per-AO scale (it is folded into C
+// for the MO sinks; AO-layer sinks multiply by row_scale themselves).  `row` = row0 + canonical function index.
 // ------------------------------------------------------------------------------------------------
 template <bool CART, int L>
 struct Ang {
@@ -144,162 +181,277 @@ struct Ang<true, L> {
   using type = Cart<L>;
 };
 
-template <class A, class Sink>
-__device__ __forceinline__ void eval_group_val(const BasisDev& B, int g, double dx, double dy, double dz, double r2,
-                                               Sink& sink) {
-  double S[A::NF];
-  A::val(dx, dy, dz, S);
-  const int sb = B.grp_sh_begin[g], se = B.grp_sh_begin[g + 1];
+// radial sums of one shell: R0 = sum c e, and (VGL) R1 = sum Z c e, R2 = sum Z^2 c e, with e = exp(-Z r2)
+__device__ __forceinline__ double shell_radial(const double2* __restrict__ pr, int pb, int pe, double r2) {
+  double R = 0.0;
+  int p = pb;
+  for (; p + 3 < pe; p += 4) {  // four independent exp chains per trip
+    const double2 a = pr[p], b = pr[p + 1], c = pr[p + 2], d = pr[p + 3];
+    const double ea = qexp(a.x * r2), eb = qexp(b.x * r2), ec = qexp(c.x * r2), ed = qexp(d.x * r2);
+    R = fma(a.y, ea, R);
+    R = fma(b.y, eb, R);
+    R = fma(c.y, ec, R);
+    R = fma(d.y, ed, R);
+  }
+  for (; p < pe; ++p) {
+    const double2 a = pr[p];
+    R = fma(a.y, qexp(a.x * r2), R);
+  }
+  return R;
+}
+__device__ __forceinline__ void shell_radial3(const double2* __restrict__ pr, int pb, int pe, double r2, double& R0, double& R1,
+                                              double& R2) {
+  R0 = 0.0;
+  R1 = 0.0;
+  R2 = 0.0;
+  int p = pb;
+  for (; p + 1 < pe; p += 2) {
+    const double2 a = pr[p], b = pr[p + 1];
+    const double ea = a.y * qexp(a.x * r2), eb = b.y * qexp(b.x * r2);
+    R0 += ea;
+    R1 = fma(-a.x, ea, R1);
+    R2 = fma(a.x * a.x, ea, R2);
+    R0 += eb;
+    R1 = fma(-b.x, eb, R1);
+    R2 = fma(b.x * b.x, eb, R2);
+  }
+  if (p < pe) {
+    const double2 a = pr[p];
+    const double ea = a.y * qexp(a.x * r2);
+    R0 += ea;
+    R1 = fma(-a.x, ea, R1);
+    R2 = fma(a.x * a.x, ea, R2);
+  }
+}
+
+// radial sums R[i] = sum_p c_p exp(-Z_p r2[i]) of one shell at NP points (independent exp chains: 2 primitives x NP points)
+template <int NP>
+__device__ __forceinline__ void shell_radial_n(const double2* __restrict__ pr, int pb, int pe, const double* __restrict__ r2,
+                                               double* __restrict__ R) {
+#pragma unroll
+  for (int i = 0; i < NP; ++i) R[i] = 0.0;
+  int p = pb;
+  for (; p + 1 < pe; p += 2) {
+    const double2 a = pr[p], b = pr[p + 1];
+    double ea[NP], eb[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      ea[i] = qexp(a.x * r2[i]);
+      eb[i] = qexp(b.x * r2[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      R[i] = fma(a.y, ea[i], R[i]);
+      R[i] = fma(b.y, eb[i], R[i]);
+    }
+  }
+  if (p < pe) {
+    const double2 a = pr[p];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) R[i] = fma(a.y, qexp(a.x * r2[i]), R[i]);
+  }
+}
+
+template <class A, int NP, class Sink>
+__device__ __forceinline__ void eval_seg_val_n(const int4* __restrict__ sh, const double2* __restrict__ pr, int sb, int se,
+                                               const double* __restrict__ dx, const double* __restrict__ dy,
+                                               const double* __restrict__ dz, const double* __restrict__ r2, Sink& sink) {
+  double S[NP][A::NF];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) A::val(dx[i], dy[i], dz[i], S[i]);
   for (int s = sb; s < se; ++s) {
-    const int pb = B.sh_prim_off[s], pe = B.sh_prim_off[s + 1];
-    double R = 0.0;
-    int p = pb;
-    for (; p + 1 < pe; p += 2) {  // two independent exp chains per trip
-      const double2 a = B.pr_zc[p], b = B.pr_zc[p + 1];
-      const double ea = exp(-a.x * r2), eb = exp(-b.x * r2);
-      R = fma(a.y, ea, R);
-      R = fma(b.y, eb, R);
-    }
-    if (p < pe) {
-      const double2 a = B.pr_zc[p];
-      R = fma(a.y, exp(-a.x * r2), R);
-    }
-    const short* slot = B.sh_slot + s * MAXF;
+    const int4 q = sh[s];
+    double R[NP];
+    shell_radial_n<NP>(pr, q.x, q.y, r2, R);
 #pragma unroll
     for (int k = 0; k < A::NF; ++k) {
-      const int a = slot[k];
-      if (a >= 0) sink.add(a, R * S[k]);
+      double v[NP];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) v[i] = R[i] * S[i][k];
+      sink.add_n(q.z + k, v);
     }
   }
 }
 
+// Evaluate segments [gb, ge) of the list at byte offset off_list (B.off_seg for the whole basis, or a chunk list) at NP
+// points per thread (same shell / primitive sequence, tables loaded once).  `tab` = base of the blob copy (shared or global).
+template <bool CART, int LMAX, int NP, class Sink>
+__device__ __forceinline__ void eval_val_n(const char* __restrict__ tab, const BasisDev& B, int off_list, const double* __restrict__ px,
+                                           const double* __restrict__ py, const double* __restrict__ pz, int gb, int ge,
+                                           Sink& sink) {
+  const int4* seg = (const int4*)(tab + off_list);
+  const int4* sh = (const int4*)(tab + B.off_sh);
+  const double2* pr = (const double2*)(tab + B.off_pr);
+  const double* Rn = (const double*)(tab + B.off_Rn);
+  for (int g = gb; g < ge; ++g) {
+    const int4 q = seg[g];
+    const double X = Rn[3 * q.x], Y = Rn[3 * q.x + 1], Z = Rn[3 * q.x + 2];
+    double dx[NP], dy[NP], dz[NP], r2[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      dx[i] = px[i] - X;
+      dy[i] = py[i] - Y;
+      dz[i] = pz[i] - Z;
+      r2[i] = dx[i] * dx[i] + dy[i] * dy[i] + dz[i] * dz[i];
+    }
+    switch (q.y) {
+      case 0: eval_seg_val_n<typename Ang<CART, 0>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 1: eval_seg_val_n<typename Ang<CART, 1>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 2: eval_seg_val_n<typename Ang<CART, 2>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 3: if (LMAX >= 3) eval_seg_val_n<typename Ang<CART, (LMAX >= 3 ? 3 : 0)>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 4: if (LMAX >= 4) eval_seg_val_n<typename Ang<CART, (LMAX >= 4 ? 4 : 0)>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 5: if (LMAX >= 5) eval_seg_val_n<typename Ang<CART, (LMAX >= 5 ? 5 : 0)>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
+      default: if (LMAX >= 6) eval_seg_val_n<typename Ang<CART, (LMAX >= 6 ? 6 : 0)>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
+    }
+  }
+}
+template <bool CART, int LMAX, class Sink>
+__device__ __forceinline__ void eval_val(const char* __restrict__ tab, const BasisDev& B, int off_list, double px, double py, double pz,
+                                         int gb, int ge, Sink& sink) {
+  eval_val_n<CART, LMAX, 1, Sink>(tab, B, off_list, &px, &py, &pz, gb, ge, sink);
+}
+
 template <class A, class Sink>
-__device__ __forceinline__ void eval_group_vgl(const BasisDev& B, int g, int l, double dx, double dy, double dz, double r2,
-                                               Sink& sink) {
+__device__ __forceinline__ void eval_seg_vgl(const int4* __restrict__ sh, const double2* __restrict__ pr, int sb, int se, int l,
+                                             double dx, double dy, double dz, double r2, Sink& sink) {
   double S[A::NF], Sx[A::NF], Sy[A::NF], Sz[A::NF], Sl[A::NF];
   A::vgl(dx, dy, dz, S, Sx, Sy, Sz, Sl);
-  const int sb = B.grp_sh_begin[g], se = B.grp_sh_begin[g + 1];
   for (int s = sb; s < se; ++s) {
-    const int pb = B.sh_prim_off[s], pe = B.sh_prim_off[s + 1];
-    double R0 = 0.0, R1 = 0.0, R2 = 0.0;
-    for (int p = pb; p < pe; ++p) {
-      const double2 zc = B.pr_zc[p];
-      const double Z = zc.x;
-      const double e = zc.y * exp(-Z * r2);
-      R0 += e;
-      R1 = fma(Z, e, R1);
-      R2 = fma(Z * Z, e, R2);
-    }
+    const int4 q = sh[s];
+    double R0, R1, R2;
+    shell_radial3(pr, q.x, q.y, r2, R0, R1, R2);
     // phi = R0*A ; grad = R0*gradA - 2 R1 A d ; lap = R0*lapA + A (4 r2 R2 - 6 R1 - 4 l R1)
     // (r.gradA = l*A: A is homogeneous of degree l; jqmc/atomic_orbital.py:3575-3588, :3484-3505)
     const double m2R1 = -2.0 * R1;
     const double lapfac = 4.0 * r2 * R2 - (6.0 + 4.0 * l) * R1;
-    const short* slot = B.sh_slot + s * MAXF;
 #pragma unroll
     for (int k = 0; k < A::NF; ++k) {
-      const int a = slot[k];
-      if (a >= 0) {
-        const double Ak = S[k];
-        const double t = m2R1 * Ak;
-        double lp = lapfac * Ak;
-        if (!A::HARMONIC) lp = fma(R0, Sl[k], lp);
-        sink.add(a, R0 * Ak, fma(R0, Sx[k], t * dx), fma(R0, Sy[k], t * dy), fma(R0, Sz[k], t * dz), lp);
-      }
+      const double Ak = S[k];
+      const double t = m2R1 * Ak;
+      double lp = lapfac * Ak;
+      if (!A::HARMONIC) lp = fma(R0, Sl[k], lp);
+      sink.add(q.z + k, R0 * Ak, fma(R0, Sx[k], t * dx), fma(R0, Sy[k], t * dy), fma(R0, Sz[k], t * dz), lp);
     }
   }
 }
 
-// Evaluate groups [gb, ge) of basis B at point (px,py,pz); Rn = nuclear positions [n_atom*3].
-template <bool CART, class Sink>
-__device__ __forceinline__ void eval_val(const BasisDev& B, const double* __restrict__ Rn, double px, double py, double pz,
+template <bool CART, int LMAX, class Sink>
+__device__ __forceinline__ void eval_vgl(const char* __restrict__ tab, const BasisDev& B, int off_list, double px, double py, double pz,
                                          int gb, int ge, Sink& sink) {
+  const int4* seg = (const int4*)(tab + off_list);
+  const int4* sh = (const int4*)(tab + B.off_sh);
+  const double2* pr = (const double2*)(tab + B.off_pr);
+  const double* Rn = (const double*)(tab + B.off_Rn);
   for (int g = gb; g < ge; ++g) {
-    const int nuc = B.grp_nuc[g];
-    const double dx = px - Rn[3 * nuc], dy = py - Rn[3 * nuc + 1], dz = pz - Rn[3 * nuc + 2];
+    const int4 q = seg[g];
+    const double dx = px - Rn[3 * q.x], dy = py - Rn[3 * q.x + 1], dz = pz - Rn[3 * q.x + 2];
     const double r2 = dx * dx + dy * dy + dz * dz;
-    switch (B.grp_l[g]) {
-      case 0: eval_group_val<typename Ang<CART, 0>::type>(B, g, dx, dy, dz, r2, sink); break;
-      case 1: eval_group_val<typename Ang<CART, 1>::type>(B, g, dx, dy, dz, r2, sink); break;
-      case 2: eval_group_val<typename Ang<CART, 2>::type>(B, g, dx, dy, dz, r2, sink); break;
-      case 3: eval_group_val<typename Ang<CART, 3>::type>(B, g, dx, dy, dz, r2, sink); break;
-      case 4: eval_group_val<typename Ang<CART, 4>::type>(B, g, dx, dy, dz, r2, sink); break;
-      case 5: eval_group_val<typename Ang<CART, 5>::type>(B, g, dx, dy, dz, r2, sink); break;
-      default: eval_group_val<typename Ang<CART, 6>::type>(B, g, dx, dy, dz, r2, sink); break;
-    }
-  }
-}
-
-template <bool CART, class Sink>
-__device__ __forceinline__ void eval_vgl(const BasisDev& B, const double* __restrict__ Rn, double px, double py, double pz,
-                                         int gb, int ge, Sink& sink) {
-  for (int g = gb; g < ge; ++g) {
-    const int nuc = B.grp_nuc[g];
-    const double dx = px - Rn[3 * nuc], dy = py - Rn[3 * nuc + 1], dz = pz - Rn[3 * nuc + 2];
-    const double r2 = dx * dx + dy * dy + dz * dz;
-    const int l = B.grp_l[g];
+    const int l = q.y;
     switch (l) {
-      case 0: eval_group_vgl<typename Ang<CART, 0>::type>(B, g, l, dx, dy, dz, r2, sink); break;
-      case 1: eval_group_vgl<typename Ang<CART, 1>::type>(B, g, l, dx, dy, dz, r2, sink); break;
-      case 2: eval_group_vgl<typename Ang<CART, 2>::type>(B, g, l, dx, dy, dz, r2, sink); break;
-      case 3: eval_group_vgl<typename Ang<CART, 3>::type>(B, g, l, dx, dy, dz, r2, sink); break;
-      case 4: eval_group_vgl<typename Ang<CART, 4>::type>(B, g, l, dx, dy, dz, r2, sink); break;
-      case 5: eval_group_vgl<typename Ang<CART, 5>::type>(B, g, l, dx, dy, dz, r2, sink); break;
-      default: eval_group_vgl<typename Ang<CART, 6>::type>(B, g, l, dx, dy, dz, r2, sink); break;
+      case 0: eval_seg_vgl<typename Ang<CART, 0>::type>(sh, pr, q.z, q.w, l, dx, dy, dz, r2, sink); break;
+      case 1: eval_seg_vgl<typename Ang<CART, 1>::type>(sh, pr, q.z, q.w, l, dx, dy, dz, r2, sink); break;
+      case 2: eval_seg_vgl<typename Ang<CART, 2>::type>(sh, pr, q.z, q.w, l, dx, dy, dz, r2, sink); break;
+      case 3: if (LMAX >= 3) eval_seg_vgl<typename Ang<CART, (LMAX >= 3 ? 3 : 0)>::type>(sh, pr, q.z, q.w, l, dx, dy, dz, r2, sink); break;
+      case 4: if (LMAX >= 4) eval_seg_vgl<typename Ang<CART, (LMAX >= 4 ? 4 : 0)>::type>(sh, pr, q.z, q.w, l, dx, dy, dz, r2, sink); break;
+      case 5: if (LMAX >= 5) eval_seg_vgl<typename Ang<CART, (LMAX >= 5 ? 5 : 0)>::type>(sh, pr, q.z, q.w, l, dx, dy, dz, r2, sink); break;
+      default: if (LMAX >= 6) eval_seg_vgl<typename Ang<CART, (LMAX >= 6 ? 6 : 0)>::type>(sh, pr, q.z, q.w, l, dx, dy, dz, r2, sink); break;
     }
   }
 }
 
 // ---- sinks ---------------------------------------------------------------------------------------
-// MO accumulation: acc[mo] += Cs[a][mo] * v   (AO -> MO contraction fused into the AO evaluation,
-// jqmc/molecular_orbital.py:239-261; Cs already carries ao_scale)
+// MO accumulation: acc[mo] += C[row][mo] * v   (AO -> MO contraction fused into the AO evaluation,
+// jqmc/molecular_orbital.py:239-261; C already carries the per-AO scale)
 template <int NMO>
 struct SinkMO {
-  const double* __restrict__ Cs;
+  const double2* __restrict__ C;
   double acc[NMO];
-  __device__ __forceinline__ void init(const double* cs) {
-    Cs = cs;
+  __device__ __forceinline__ void init(const char* c_table) {
+    C = (const double2*)c_table;
 #pragma unroll
     for (int i = 0; i < NMO; ++i) acc[i] = 0.0;
   }
-  __device__ __forceinline__ void add(int a, double v) {
-    const double* c = Cs + a * NMO;
+  __device__ __forceinline__ void add(int row, double v) {
+    const double2* c = C + row * (NMO / 2);
 #pragma unroll
-    for (int i = 0; i < NMO; ++i) acc[i] = fma(c[i], v, acc[i]);
+    for (int i = 0; i < NMO / 2; ++i) {
+      const double2 ci = c[i];
+      acc[2 * i] = fma(ci.x, v, acc[2 * i]);
+      acc[2 * i + 1] = fma(ci.y, v, acc[2 * i + 1]);
+    }
+  }
+  __device__ __forceinline__ void add_n(int row, const double* __restrict__ v) { add(row, v[0]); }
+};
+// NP points per thread sharing ONE coefficient table (the caller pairs points of the same spin): a row is loaded once
+template <int NMO, int NP>
+struct SinkMOn {
+  const double2* __restrict__ C;
+  double acc[NP][NMO];
+  __device__ __forceinline__ void init(const char* c_table) {
+    C = (const double2*)c_table;
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+      for (int i = 0; i < NMO; ++i) acc[p][i] = 0.0;
+  }
+  __device__ __forceinline__ void add_n(int row, const double* __restrict__ v) {
+    const double2* c = C + row * (NMO / 2);
+#pragma unroll
+    for (int i = 0; i < NMO / 2; ++i) {
+      const double2 ci = c[i];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        acc[p][2 * i] = fma(ci.x, v[p], acc[p][2 * i]);
+        acc[p][2 * i + 1] = fma(ci.y, v[p], acc[p][2 * i + 1]);
+      }
+    }
   }
 };
 template <int NMO>
 struct SinkMO5 {
-  const double* __restrict__ Cs;
+  const double2* __restrict__ C;
   double acc[5][NMO];
-  __device__ __forceinline__ void init(const double* cs) {
-    Cs = cs;
+  __device__ __forceinline__ void init(const char* c_table) {
+    C = (const double2*)c_table;
 #pragma unroll
     for (int q = 0; q < 5; ++q)
 #pragma unroll
       for (int i = 0; i < NMO; ++i) acc[q][i] = 0.0;
   }
-  __device__ __forceinline__ void add(int a, double v, double gx, double gy, double gz, double lp) {
-    const double* c = Cs + a * NMO;
+  __device__ __forceinline__ void add(int row, double v, double gx, double gy, double gz, double lp) {
+    const double2* c = C + row * (NMO / 2);
 #pragma unroll
-    for (int i = 0; i < NMO; ++i) {
-      const double ci = c[i];
-      acc[0][i] = fma(ci, v, acc[0][i]);
-      acc[1][i] = fma(ci, gx, acc[1][i]);
-      acc[2][i] = fma(ci, gy, acc[2][i]);
-      acc[3][i] = fma(ci, gz, acc[3][i]);
-      acc[4][i] = fma(ci, lp, acc[4][i]);
+    for (int i = 0; i < NMO / 2; ++i) {
+      const double2 ci = c[i];
+      acc[0][2 * i] = fma(ci.x, v, acc[0][2 * i]);
+      acc[1][2 * i] = fma(ci.x, gx, acc[1][2 * i]);
+      acc[2][2 * i] = fma(ci.x, gy, acc[2][2 * i]);
+      acc[3][2 * i] = fma(ci.x, gz, acc[3][2 * i]);
+      acc[4][2 * i] = fma(ci.x, lp, acc[4][2 * i]);
+      acc[0][2 * i + 1] = fma(ci.y, v, acc[0][2 * i + 1]);
+      acc[1][2 * i + 1] = fma(ci.y, gx, acc[1][2 * i + 1]);
+      acc[2][2 * i + 1] = fma(ci.y, gy, acc[2][2 * i + 1]);
+      acc[3][2 * i + 1] = fma(ci.y, gz, acc[3][2 * i + 1]);
+      acc[4][2 * i + 1] = fma(ci.y, lp, acc[4][2 * i + 1]);
     }
   }
 };
 // Plain AO output (parity entry qe_eval_orbitals, layer 0): out[q][a][pt]
 struct SinkStoreAO {
   double* out;
-  const double* scale;
+  const int* row_ao;
+  const double* row_scale;
   long long stride_q;  // n_ao*n_pts
   int n_pts;
-  __device__ __forceinline__ void add(int a, double v) { out[(long long)a * n_pts] = v * scale[a]; }
-  __device__ __forceinline__ void add(int a, double v, double gx, double gy, double gz, double lp) {
-    const double s = scale[a];
+  __device__ __forceinline__ void add(int row, double v) {
+    const int a = row_ao[row];
+    if (a >= 0) out[(long long)a * n_pts] = v * row_scale[row];
+  }
+  __device__ __forceinline__ void add_n(int row, const double* __restrict__ v) { add(row, v[0]); }
+  __device__ __forceinline__ void add(int row, double v, double gx, double gy, double gz, double lp) {
+    const int a = row_ao[row];
+    if (a < 0) return;
+    const double s = row_scale[row];
     double* o = out + (long long)a * n_pts;
     o[0] = v * s;
     o[stride_q] = gx * s;

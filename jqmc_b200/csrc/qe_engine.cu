@@ -42,7 +42,75 @@ struct TmpShell {
   int first_ao;
 };
 
-static int build_basis(const qe_basis_desc& d, int n_atom, int nmo_pad, DevPool& pool, HostBasis& hb) {
+struct Blob {
+  std::vector<char> bytes;
+  template <class T>
+  int put(const std::vector<T>& v) {
+    const size_t off = (bytes.size() + 15) & ~size_t(15);
+    bytes.resize(off + std::max<size_t>(v.size(), 1) * sizeof(T), 0);
+    if (!v.empty()) std::memcpy(bytes.data() + off, v.data(), v.size() * sizeof(T));
+    return (int)off;
+  }
+  void finish() { bytes.resize((bytes.size() + 15) & ~size_t(15), 0); }
+};
+
+// split the shells (in table order) into at most n_target contiguous chunks of roughly equal cost; a chunk is a list of
+// segments {nucleus, l, shell_begin, shell_end} (cut at group boundaries).  cseg: segments, cbeg[n_chunk+1]: first segment
+static void make_chunks(const std::vector<int4>& grp, const std::vector<double>& sh_cost, const std::vector<double>& grp_overhead,
+                        int n_target, std::vector<int4>& cseg, std::vector<int>& cbeg) {
+  const int n_sh = (int)sh_cost.size();
+  std::vector<int> sh_grp(n_sh, 0);
+  for (int g = 0; g < (int)grp.size(); ++g)
+    for (int s = grp[g].z; s < grp[g].w; ++s) sh_grp[s] = g;
+  n_target = std::max(1, std::min(n_target, n_sh));
+  auto count_chunks = [&](double cap, std::vector<int>* cuts) {
+    int used = 1;
+    double acc = 0;
+    int cur_g = -1;
+    if (cuts) cuts->assign(1, 0);
+    for (int s = 0; s < n_sh; ++s) {
+      double c = sh_cost[s] + (sh_grp[s] != cur_g ? grp_overhead[sh_grp[s]] : 0.0);
+      if (acc > 0 && acc + c > cap) {
+        ++used;
+        acc = 0;
+        c = sh_cost[s] + grp_overhead[sh_grp[s]];  // a new chunk re-evaluates the angular part of its first group
+        if (cuts) cuts->push_back(s);
+      }
+      acc += c;
+      cur_g = sh_grp[s];
+    }
+    if (cuts) cuts->push_back(n_sh);
+    return used;
+  };
+  double lo = 0, hi = 0;
+  for (int s = 0; s < n_sh; ++s) {
+    lo = std::max(lo, sh_cost[s] + grp_overhead[sh_grp[s]]);
+    hi += sh_cost[s] + grp_overhead[sh_grp[s]];
+  }
+  for (int it = 0; it < 60; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (count_chunks(mid, nullptr) <= n_target) hi = mid; else lo = mid;
+  }
+  std::vector<int> cuts;
+  count_chunks(hi * (1 + 1e-12), &cuts);
+  cseg.clear();
+  cbeg.clear();
+  for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+    cbeg.push_back((int)cseg.size());
+    int s = cuts[c];
+    while (s < cuts[c + 1]) {
+      const int g = sh_grp[s];
+      const int e = std::min(cuts[c + 1], grp[g].w);
+      cseg.push_back(make_int4(grp[g].x, grp[g].y, s, e));
+      s = e;
+    }
+  }
+  cbeg.push_back((int)cseg.size());
+}
+
+// d2: second coefficient set sharing the AO tables (down-spin MOs), or nullptr
+static int build_basis(const qe_basis_desc& d, const qe_basis_desc* d2, int n_atom, const double* positions, int nmo_pad, int n_chunk_target,
+                       DevPool& pool, HostBasis& hb) {
   if (d.n_ao <= 0) return fail(QE_ERR_INVALID, "basis: n_ao must be positive");
   const bool cart = d.cartesian != 0;
   std::vector<std::vector<int>> prims(d.n_ao);
@@ -111,99 +179,94 @@ static int build_basis(const qe_basis_desc& d, int n_atom, int nmo_pad, DevPool&
   std::stable_sort(shells.begin(), shells.end(), [](const TmpShell& x, const TmpShell& y) {
     return x.nuc != y.nuc ? x.nuc < y.nuc : x.l < y.l;
   });
-  std::vector<int> grp_nuc, grp_l, grp_sh_begin, sh_prim_off{0};
-  std::vector<short> sh_slot;
-  std::vector<double2> pr_zc;
-  hb.grp_cost.clear();
+  std::vector<int4> grp, sh;
+  std::vector<double2> pr;
+  std::vector<int> row_ao;
+  std::vector<double> row_scale, sh_cost, grp_overhead;
   for (size_t s = 0; s < shells.size(); ++s) {
-    const TmpShell& sh = shells[s];
-    if (s == 0 || sh.nuc != shells[s - 1].nuc || sh.l != shells[s - 1].l) {
-      grp_nuc.push_back(sh.nuc);
-      grp_l.push_back(sh.l);
-      grp_sh_begin.push_back((int)s);
-      hb.grp_cost.push_back(10.0 + 6.0 * sh.l * sh.l);
+    const TmpShell& t = shells[s];
+    const int l = t.l;
+    const int nf = cart ? (l + 1) * (l + 2) / 2 : 2 * l + 1;
+    if (s == 0 || t.nuc != shells[s - 1].nuc || t.l != shells[s - 1].l) {
+      if (!grp.empty()) grp.back().w = (int)s;
+      grp.push_back(make_int4(t.nuc, t.l, (int)s, (int)s));
+      grp_overhead.push_back(10.0 + 6.0 * l * l);
     }
-    const int l = sh.l;
-    for (size_t i = 0; i < sh.Z.size(); ++i) {
-      const double Z = sh.Z[i];
+    const int pb = (int)pr.size();
+    for (size_t i = 0; i < t.Z.size(); ++i) {
+      const double Z = t.Z[i];
       double N;
-      if (cart)  // jqmc/atomic_orbital.py:2243-2244 (Z-dependent part; factorial part lives in ao_scale)
+      if (cart)  // jqmc/atomic_orbital.py:2243-2244 (Z-dependent part; factorial part lives in the per-AO scale)
         N = std::sqrt(std::pow(2.0 * Z / M_PI, 1.5) * std::pow(8.0 * Z, (double)l));
       else  // jqmc/atomic_orbital.py:2316-2323, times sqrt((2l+1)/4pi) (:2349)
         N = std::sqrt(std::pow(2.0, 2 * l + 3) * dfact(l + 1) * std::pow(2.0 * Z, l + 1.5) / (dfact(2 * l + 2) * std::sqrt(M_PI))) *
             std::sqrt((2 * l + 1) / (4.0 * M_PI));
-      pr_zc.push_back(make_double2(Z, sh.c[i] * N));
+      pr.push_back(make_double2(-Z, t.c[i] * N));
     }
-    sh_prim_off.push_back((int)pr_zc.size());
-    sh_slot.insert(sh_slot.end(), sh.slot.begin(), sh.slot.end());
-    int nf = 0;
-    for (short v : sh.slot) nf += v >= 0;
-    hb.grp_cost.back() += 32.0 * sh.Z.size() + (nmo_pad + 2.0) * nf;
+    sh.push_back(make_int4(pb, (int)pr.size(), (int)row_ao.size(), 0));
+    for (int k = 0; k < nf; ++k) {
+      const int a = t.slot[k];
+      row_ao.push_back(a);
+      row_scale.push_back(a >= 0 ? ao_scale[a] : 0.0);
+    }
+    sh_cost.push_back(22.0 * t.Z.size() + (nmo_pad + 3.0) * nf);
   }
-  grp_sh_begin.push_back((int)shells.size());
+  if (!grp.empty()) grp.back().w = (int)shells.size();
+  const int n_row = (int)row_ao.size();
 
   BasisDev& B = hb.dev;
+  B = BasisDev{};
   B.n_ao = d.n_ao;
   B.n_mo = d.n_mo;
   B.n_orb = d.n_mo > 0 ? d.n_mo : d.n_ao;
-  B.n_grp = (int)grp_nuc.size();
+  B.n_grp = (int)grp.size();
   B.n_shell = (int)shells.size();
+  B.n_prim = (int)pr.size();
+  B.n_row = n_row;
   B.cart = cart ? 1 : 0;
   B.nmo_pad = nmo_pad;
-  std::vector<double> Cs;
+  B.lmax = 0;
+  for (const TmpShell& t : shells) B.lmax = std::max(B.lmax, t.l);
+  auto c_table = [&](const qe_basis_desc& q) {
+    std::vector<double> C((size_t)n_row * nmo_pad, 0.0);
+    for (int r = 0; r < n_row; ++r) {
+      const int a = row_ao[r];
+      if (a < 0) continue;
+      for (int mo = 0; mo < q.n_mo; ++mo) C[(size_t)r * nmo_pad + mo] = q.mo_coefficients[(size_t)mo * q.n_ao + a] * ao_scale[a];
+    }
+    return C;
+  };
+  std::vector<int4> cseg;
+  std::vector<int> cbeg;
+  make_chunks(grp, sh_cost, grp_overhead, n_chunk_target, cseg, cbeg);
+  hb.n_chunk = (int)cbeg.size() - 1;
+  Blob blob;
+  B.off_seg = blob.put(grp);
+  B.off_sh = blob.put(sh);
+  B.off_pr = blob.put(pr);
+  B.off_C = B.off_C2 = 0;
   if (d.n_mo > 0) {
-    Cs.assign((size_t)d.n_ao * nmo_pad, 0.0);
-    for (int mo = 0; mo < d.n_mo; ++mo)
-      for (int a = 0; a < d.n_ao; ++a) Cs[(size_t)a * nmo_pad + mo] = d.mo_coefficients[(size_t)mo * d.n_ao + a] * ao_scale[a];
+    const std::vector<double> Cu = c_table(d);
+    B.off_C = blob.put(Cu);
+    B.off_C2 = B.off_C;
+    if (d2) {
+      const std::vector<double> Cd = c_table(*d2);
+      if (Cd != Cu) B.off_C2 = blob.put(Cd);  // restricted (same orbitals for both spins): one table
+    }
   }
-  cudaError_t e = cudaSuccess;
-  e = pool.upload(grp_nuc, &B.grp_nuc);
-  if (e == cudaSuccess) e = pool.upload(grp_l, &B.grp_l);
-  if (e == cudaSuccess) e = pool.upload(grp_sh_begin, &B.grp_sh_begin);
-  if (e == cudaSuccess) e = pool.upload(sh_prim_off, &B.sh_prim_off);
-  if (e == cudaSuccess) e = pool.upload(sh_slot, &B.sh_slot);
-  B.n_prim = (int)pr_zc.size();
-  if (e == cudaSuccess) e = pool.upload(pr_zc, &B.pr_zc);
-  if (e == cudaSuccess) e = pool.upload(ao_scale, &B.ao_scale);
-  if (e == cudaSuccess) e = pool.upload(Cs, &B.Cs);
+  B.off_rowao = blob.put(row_ao);
+  B.off_rowscale = blob.put(row_scale);
+  B.off_Rn = blob.put(std::vector<double>(positions, positions + 3 * n_atom));
+  hb.off_cseg = blob.put(cseg);
+  hb.off_cbeg = blob.put(cbeg);
+  blob.finish();
+  B.bytes = (int)blob.bytes.size();
+  const char* dev = nullptr;
+  cudaError_t e = pool.upload(blob.bytes, &dev);
   if (e != cudaSuccess) return fail(QE_ERR_CUDA, std::string("basis upload: ") + cudaGetErrorString(e));
-  if (d.n_mo == 0) B.Cs = nullptr;
+  B.g = dev;
   hb.present = true;
   return QE_OK;
-}
-
-// split the groups into at most n_target contiguous chunks of roughly equal cost
-static std::vector<int> make_chunks(const std::vector<double>& cost, int n_target) {
-  const int n = (int)cost.size();
-  n_target = std::max(1, std::min(n_target, n));
-  double total = 0;
-  for (double c : cost) total += c;
-  // binary search the smallest max-chunk cost achievable with n_target contiguous chunks
-  double lo = 0, hi = total;
-  for (double c : cost) lo = std::max(lo, c);
-  for (int it = 0; it < 60; ++it) {
-    double mid = 0.5 * (lo + hi), acc = 0;
-    int used = 1;
-    for (double c : cost) {
-      if (acc + c > mid) {
-        ++used;
-        acc = 0;
-      }
-      acc += c;
-    }
-    if (used <= n_target) hi = mid; else lo = mid;
-  }
-  std::vector<int> out{0};
-  double acc = 0;
-  for (int g = 0; g < n; ++g) {
-    if (acc + cost[g] > hi * (1 + 1e-12) && g > out.back()) {
-      out.push_back(g);
-      acc = 0;
-    }
-    acc += cost[g];
-  }
-  out.push_back(n);
-  return out;
 }
 
 static bool same_ao_tables(const qe_basis_desc& x, const qe_basis_desc& y) {
@@ -227,21 +290,19 @@ static bool same_ao_tables(const qe_basis_desc& x, const qe_basis_desc& y) {
 // K1/K2 parity entry: orbital values / VGL at arbitrary points
 // =================================================================================================
 template <bool CART>
-__global__ void k_eval_ao(BasisDev B, const double* __restrict__ Rn, int n_pts, const double* __restrict__ r,
-                          double* __restrict__ out) {
+__global__ void k_eval_ao(BasisDev B, int n_pts, const double* __restrict__ r, double* __restrict__ out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_pts) return;
-  SinkStoreAO sink{out + t, B.ao_scale, (long long)B.n_ao * n_pts, n_pts};
-  eval_vgl<CART>(B, Rn, r[3 * t], r[3 * t + 1], r[3 * t + 2], 0, B.n_grp, sink);
+  SinkStoreAO sink{out + t, (const int*)(B.g + B.off_rowao), (const double*)(B.g + B.off_rowscale), (long long)B.n_ao * n_pts, n_pts};
+  eval_vgl<CART, QE_LMAX>(B.g, B, B.off_seg, r[3 * t], r[3 * t + 1], r[3 * t + 2], 0, B.n_grp, sink);
 }
 template <int NMO, bool CART>
-__global__ void k_eval_mo(BasisDev B, const double* __restrict__ Rn, int n_pts, const double* __restrict__ r,
-                          double* __restrict__ out) {
+__global__ void k_eval_mo(BasisDev B, int dn, int n_pts, const double* __restrict__ r, double* __restrict__ out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_pts) return;
   SinkMO5<NMO> sink;
-  sink.init(B.Cs);
-  eval_vgl<CART>(B, Rn, r[3 * t], r[3 * t + 1], r[3 * t + 2], 0, B.n_grp, sink);
+  sink.init(B.g + (dn ? B.off_C2 : B.off_C));
+  eval_vgl<CART, QE_LMAX>(B.g, B, B.off_seg, r[3 * t], r[3 * t + 1], r[3 * t + 2], 0, B.n_grp, sink);
   for (int q = 0; q < 5; ++q)
 #pragma unroll
     for (int mo = 0; mo < NMO; ++mo)
@@ -254,9 +315,8 @@ __global__ void k_eval_mo(BasisDev B, const double* __restrict__ Rn, int n_pts, 
 // =================================================================================================
 template <int NMO, bool CART, int NQ>
 __global__ void __launch_bounds__(128)
-k_orb_electrons(BasisDev Bu, BasisDev Bd, SysDev S, int nw, const double* __restrict__ r_up,
-                const double* __restrict__ r_dn, const int* __restrict__ chunk_begin, int n_chunk,
-                double* __restrict__ out) {
+k_orb_electrons(BasisDev B, SysDev S, int nw, const double* __restrict__ r_up, const double* __restrict__ r_dn, int off_cseg,
+                int off_cbeg, int n_chunk, double* __restrict__ out) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)n_chunk * S.n_e * nw;
   if (t >= total) return;
@@ -266,19 +326,20 @@ k_orb_electrons(BasisDev Bu, BasisDev Bd, SysDev S, int nw, const double* __rest
   PosGlobal pos{r_up, r_dn, S.n_up, S.n_dn, w};
   double x, y, z;
   pos.get(e, x, y, z);
-  const BasisDev& B = e < S.n_up ? Bu : Bd;
-  const int gb = chunk_begin[c], ge = chunk_begin[c + 1];
+  const int* cbeg = (const int*)(B.g + off_cbeg);
+  const int gb = cbeg[c], ge = cbeg[c + 1];
+  const char* Ctab = B.g + (e < S.n_up ? B.off_C : B.off_C2);
   double* o = out + (((size_t)c * S.n_e + e) * NQ * NMO) * nw + w;
   if (NQ == 1) {
     SinkMO<NMO> sink;
-    sink.init(B.Cs);
-    eval_val<CART>(B, S.Rn, x, y, z, gb, ge, sink);
+    sink.init(Ctab);
+    eval_val<CART, QE_LMAX>(B.g, B, off_cseg, x, y, z, gb, ge, sink);
 #pragma unroll
     for (int mo = 0; mo < NMO; ++mo) o[(size_t)mo * nw] = sink.acc[mo];
   } else {
     SinkMO5<NMO> sink;
-    sink.init(B.Cs);
-    eval_vgl<CART>(B, S.Rn, x, y, z, gb, ge, sink);
+    sink.init(Ctab);
+    eval_vgl<CART, QE_LMAX>(B.g, B, off_cseg, x, y, z, gb, ge, sink);
 #pragma unroll
     for (int q = 0; q < 5; ++q)
 #pragma unroll
@@ -483,7 +544,7 @@ __global__ void k_electron_algebra(SysDev S, int nw, int n_chunk, const double* 
       const double A = S.j1_A[a], c = S.j1_c[a], aa = S.j1_a;
       double fp;
       if (S.j1_type == 1) {
-        const double ex = exp(-aa * c * rs);
+        const double ex = qexp(-aa * c * rs);
         fp = -A * (c * 0.5) * ex;
         lJ += A * (aa * c * c * 0.5) * ex - A * c * ex / rs;
       } else {
@@ -500,7 +561,7 @@ __global__ void k_electron_algebra(SysDev S, int nw, int n_chunk, const double* 
       const int lloc = S.ecp_lmax_atom[a];
       double s = 0.0;
       for (int k = S.ecp_off[a]; k < S.ecp_off[a + 1]; ++k)
-        if (S.ecp_l[k] == lloc) s += S.ecp_c[k] * pow(d, S.ecp_p[k]) * exp(-S.ecp_z[k] * d * d);
+        if (S.ecp_l[k] == lloc) s += S.ecp_c[k] * ipow(d, S.ecp_p[k]) * qexp(-S.ecp_z[k] * d * d);
       v_loc += s / (d * d);
     }
   }
@@ -519,7 +580,7 @@ __global__ void k_electron_algebra(SysDev S, int nw, int n_chunk, const double* 
         fp = 0.5 / (den * den);
         lJ += -aa / (den * den * den) + 2.0 * fp / rs;
       } else {
-        const double ex = exp(-aa * rs);
+        const double ex = qexp(-aa * rs);
         fp = 0.5 * ex;
         lJ += -(aa * 0.5) * ex + 2.0 * fp / rs;
       }
@@ -541,7 +602,7 @@ __global__ void k_electron_algebra(SysDev S, int nw, int n_chunk, const double* 
 // =================================================================================================
 template <int NMO, bool CART>
 __global__ void __launch_bounds__(128)
-k_ecp_mesh(BasisDev Bu, BasisDev Bd, SysDev S, int nw, const double* __restrict__ r_up, const double* __restrict__ r_dn,
+k_ecp_mesh(BasisDev B, SysDev S, int nw, const double* __restrict__ r_up, const double* __restrict__ r_dn,
            const double* __restrict__ RT, const double* __restrict__ W, int det_only, double* __restrict__ Vnl,
            double* __restrict__ mesh_xyz) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -580,19 +641,18 @@ k_ecp_mesh(BasisDev Bu, BasisDev Bd, SysDev S, int nw, const double* __restrict_
   for (int l = 0; l < lloc; ++l) {
     double vl = 0.0;
     for (int kk = S.ecp_off[a]; kk < S.ecp_off[a + 1]; ++kk)
-      if (S.ecp_l[kk] == l) vl += S.ecp_c[kk] * pow(d, S.ecp_p[kk]) * exp(-S.ecp_z[kk] * d * d);
+      if (S.ecp_l[kk] == l) vl += S.ecp_c[kk] * ipow(d, S.ecp_p[kk]) * qexp(-S.ecp_z[kk] * d * d);
     ang = fma(vl / (d * d) * (2 * l + 1), legendre_l(l, cos_t), ang);
   }
   double val = 0.0;
   if (lloc > 0) {  // uniform per warp only if all lanes agree; divergence here is cheap relative to the AO sweep
-    const BasisDev& B = e < S.n_up ? Bu : Bd;
     SinkMO<NMO> sink;
-    sink.init(B.Cs);
-    eval_val<CART>(B, S.Rn, px, py, pz, 0, B.n_grp, sink);
+    sink.init(B.g + (e < S.n_up ? B.off_C : B.off_C2));
+    eval_val<CART, QE_LMAX>(B.g, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);
     double ratio = 0.0;
 #pragma unroll
     for (int mo = 0; mo < NMO; ++mo) ratio = fma(sink.acc[mo], W[((size_t)e * NMO + mo) * nw + w], ratio);
-    if (!det_only) ratio *= exp(jastrow_delta(S, pos, e, x, y, z, px, py, pz));
+    if (!det_only) ratio *= qexp(jastrow_delta(S, pos, e, x, y, z, px, py, pz));
     val = ang * S.quad_w[k] * ratio;
   }
   Vnl[(size_t)pt * nw + w] = val;
@@ -628,7 +688,7 @@ __global__ void k_reduce_eL(SysDev S, int nw, const double* __restrict__ Te, con
 // generic single-electron move ratios (parity entry; also the LRDMC kinetic mesh): thread = (move, walker)
 template <int NMO, bool CART>
 __global__ void __launch_bounds__(128)
-k_move_ratios(BasisDev Bu, BasisDev Bd, SysDev S, int nw, const double* __restrict__ r_up, const double* __restrict__ r_dn,
+k_move_ratios(BasisDev B, SysDev S, int nw, const double* __restrict__ r_up, const double* __restrict__ r_dn,
               const double* __restrict__ W, int n_moves, const int* __restrict__ elec, const double* __restrict__ r_new,
               double* __restrict__ det_ratio, double* __restrict__ jas_ratio) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -640,10 +700,9 @@ k_move_ratios(BasisDev Bu, BasisDev Bd, SysDev S, int nw, const double* __restri
   const double px = p[0], py = p[1], pz = p[2];
   PosGlobal pos{r_up, r_dn, S.n_up, S.n_dn, w};
   if (det_ratio) {
-    const BasisDev& B = e < S.n_up ? Bu : Bd;
     SinkMO<NMO> sink;
-    sink.init(B.Cs);
-    eval_val<CART>(B, S.Rn, px, py, pz, 0, B.n_grp, sink);
+    sink.init(B.g + (e < S.n_up ? B.off_C : B.off_C2));
+    eval_val<CART, QE_LMAX>(B.g, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);
     double ratio = 0.0;
 #pragma unroll
     for (int mo = 0; mo < NMO; ++mo) ratio = fma(sink.acc[mo], W[((size_t)e * NMO + mo) * nw + w], ratio);
@@ -652,7 +711,7 @@ k_move_ratios(BasisDev Bu, BasisDev Bd, SysDev S, int nw, const double* __restri
   if (jas_ratio) {
     double x, y, z;
     pos.get(e, x, y, z);
-    jas_ratio[(size_t)w * n_moves + mv] = exp(jastrow_delta(S, pos, e, x, y, z, px, py, pz));
+    jas_ratio[(size_t)w * n_moves + mv] = qexp(jastrow_delta(S, pos, e, x, y, z, px, py, pz));
   }
 }
 
@@ -778,8 +837,7 @@ extern "C" int qe_create(const qe_system_desc* d, qe_engine** out) {
   qe_engine* h = new qe_engine();
   const int n_mo = d->orb_up.n_mo;
   h->nmo_pad = n_mo <= 4 ? 4 : (n_mo <= 8 ? 8 : 16);
-  int rc = build_basis(d->orb_up, d->n_atom, h->nmo_pad, h->pool, h->b_up);
-  if (rc == QE_OK) rc = build_basis(d->orb_dn, d->n_atom, h->nmo_pad, h->pool, h->b_dn);
+  int rc = build_basis(d->orb_up, &d->orb_dn, d->n_atom, d->positions, h->nmo_pad, QE_N_CHUNK, h->pool, h->b_up);
   if (rc != QE_OK) {
     qe_destroy(h);
     return rc;
@@ -843,11 +901,6 @@ extern "C" int qe_create(const qe_system_desc* d, qe_engine** out) {
       const double dx = Rn[3 * a] - Rn[3 * b], dy = Rn[3 * a + 1] - Rn[3 * b + 1], dz = Rn[3 * a + 2] - Rn[3 * b + 2];
       S.v_ion_ion += Z[a] * Z[b] / std::sqrt(dx * dx + dy * dy + dz * dz);
     }
-  // chunk tables
-  h->chunk_el = make_chunks(h->b_up.grp_cost, 3);
-  h->chunk_mc = make_chunks(h->b_up.grp_cost, 7);
-  h->n_chunk_el = (int)h->chunk_el.size() - 1;
-  h->n_chunk_mc = (int)h->chunk_mc.size() - 1;
   cudaError_t e = cudaSuccess;
   DevPool& pl = h->pool;
   e = pl.upload(Rn, &S.Rn);
@@ -865,8 +918,6 @@ extern "C" int qe_create(const qe_system_desc* d, qe_engine** out) {
   if (e == cudaSuccess) e = pl.upload(e_off, &S.ecp_off);
   if (e == cudaSuccess) e = pl.upload(qw, &S.quad_w);
   if (e == cudaSuccess) e = pl.upload(qg, &S.quad_g);
-  if (e == cudaSuccess) e = pl.upload(h->chunk_el, &h->d_chunk_el);
-  if (e == cudaSuccess) e = pl.upload(h->chunk_mc, &h->d_chunk_mc);
   if (e != cudaSuccess) {
     qe_destroy(h);
     return fail(QE_ERR_CUDA, std::string("qe_create upload: ") + cudaGetErrorString(e));
@@ -916,16 +967,16 @@ extern "C" int qe_profile_read(qe_engine* h, int id, double* total_ms, int64_t* 
 
 extern "C" int qe_eval_orbitals(qe_engine* h, int which, int layer, int n_pts, const double* r, double* out, void* stream) {
   if (!h || !r || !out || n_pts <= 0) return fail(QE_ERR_INVALID, "qe_eval_orbitals: bad argument");
-  HostBasis* hb = which == 0 ? &h->b_up : which == 1 ? &h->b_dn : &h->b_j3;
-  if (!hb->present) return fail(QE_ERR_INVALID, "qe_eval_orbitals: basis not present");
+  HostBasis* hb = which == 2 ? &h->b_j3 : &h->b_up;
+  if (which < 0 || which > 2 || !hb->present) return fail(QE_ERR_INVALID, "qe_eval_orbitals: basis not present");
   cudaStream_t st = (cudaStream_t)stream;
   const BasisDev& B = hb->dev;
   { LaunchScope ls_(h, K_EVAL, st);
   if (layer == 0 || B.n_mo == 0) {
-    if (B.cart) k_eval_ao<true><<<nblk(n_pts, 128), 128, 0, st>>>(B, h->sys.Rn, n_pts, r, out);
-    else k_eval_ao<false><<<nblk(n_pts, 128), 128, 0, st>>>(B, h->sys.Rn, n_pts, r, out);
+    if (B.cart) k_eval_ao<true><<<nblk(n_pts, 128), 128, 0, st>>>(B, n_pts, r, out);
+    else k_eval_ao<false><<<nblk(n_pts, 128), 128, 0, st>>>(B, n_pts, r, out);
   } else {
-#define CALL(NMO, CART) k_eval_mo<NMO, CART><<<nblk(n_pts, 128), 128, 0, st>>>(B, h->sys.Rn, n_pts, r, out)
+#define CALL(NMO, CART) k_eval_mo<NMO, CART><<<nblk(n_pts, 128), 128, 0, st>>>(B, which == 1, n_pts, r, out)
     switch (B.nmo_pad) {
       case 4: if (B.cart) { CALL(4, true); } else { CALL(4, false); } break;
       case 8: if (B.cart) { CALL(8, true); } else { CALL(8, false); } break;
@@ -955,21 +1006,21 @@ extern "C" int qe_geminal_init(qe_engine* h, int nw, const double* r_up, const d
   const SysDev& S = h->sys;
   int rc;
   double* phi;
-  rc = ensure_ws(h, ws_need_common(h, nw, h->n_chunk_el, 1));
+  rc = ensure_ws(h, ws_need_common(h, nw, h->b_up.n_chunk, 1));
   if (rc) return rc;
   WsCarve c2{(char*)h->ws};
-  phi = c2.take<double>((size_t)h->n_chunk_el * S.n_e * h->nmo_pad * nw);
-  const long long total2 = (long long)h->n_chunk_el * S.n_e * nw;
+  phi = c2.take<double>((size_t)h->b_up.n_chunk * S.n_e * h->nmo_pad * nw);
+  const long long total2 = (long long)h->b_up.n_chunk * S.n_e * nw;
   { LaunchScope ls_(h, K_ORB_EL, st);
 #define CALL(NMO, CART)                                                                                              \
-  k_orb_electrons<NMO, CART, 1><<<nblk(total2, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, \
-                                                                   h->d_chunk_el, h->n_chunk_el, phi)
+  k_orb_electrons<NMO, CART, 1><<<nblk(total2, 128), 128, 0, st>>>(h->b_up.dev, S, nw, r_up, r_dn, h->b_up.off_cseg, \
+                                                                   h->b_up.off_cbeg, h->b_up.n_chunk, phi)
   DISPATCH_NMO_CART(h, CALL);
 #undef CALL
   }
   CHECK_LAUNCH();
   { LaunchScope ls_(h, K_GEMINAL, st);
-#define CALL(NMO) k_geminal<NMO><<<nblk(nw, 64), 64, 0, st>>>(S, nw, h->n_chunk_el, phi, r_up, r_dn, G, Ginv, nullptr, nullptr)
+#define CALL(NMO) k_geminal<NMO><<<nblk(nw, 64), 64, 0, st>>>(S, nw, h->b_up.n_chunk, phi, r_up, r_dn, G, Ginv, nullptr, nullptr)
   DISPATCH_NMO(h, CALL);
 #undef CALL
   }
@@ -982,21 +1033,21 @@ extern "C" int qe_ln_wavefunction(qe_engine* h, int nw, const double* r_up, cons
   if (!h || nw <= 0 || !r_up || !ln_psi) return fail(QE_ERR_INVALID, "qe_ln_wavefunction: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const SysDev& S = h->sys;
-  int rc = ensure_ws(h, ws_need_common(h, nw, h->n_chunk_el, 1));
+  int rc = ensure_ws(h, ws_need_common(h, nw, h->b_up.n_chunk, 1));
   if (rc) return rc;
   WsCarve c{(char*)h->ws};
-  double* phi = c.take<double>((size_t)h->n_chunk_el * S.n_e * h->nmo_pad * nw);
-  const long long total = (long long)h->n_chunk_el * S.n_e * nw;
+  double* phi = c.take<double>((size_t)h->b_up.n_chunk * S.n_e * h->nmo_pad * nw);
+  const long long total = (long long)h->b_up.n_chunk * S.n_e * nw;
   { LaunchScope ls_(h, K_ORB_EL, st);
 #define CALL(NMO, CART)                                                                                             \
-  k_orb_electrons<NMO, CART, 1><<<nblk(total, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, \
-                                                                  h->d_chunk_el, h->n_chunk_el, phi)
+  k_orb_electrons<NMO, CART, 1><<<nblk(total, 128), 128, 0, st>>>(h->b_up.dev, S, nw, r_up, r_dn, h->b_up.off_cseg, \
+                                                                   h->b_up.off_cbeg, h->b_up.n_chunk, phi)
   DISPATCH_NMO_CART(h, CALL);
 #undef CALL
   }
   CHECK_LAUNCH();
   { LaunchScope ls_(h, K_GEMINAL, st);
-#define CALL(NMO) k_geminal<NMO><<<nblk(nw, 64), 64, 0, st>>>(S, nw, h->n_chunk_el, phi, r_up, r_dn, nullptr, nullptr, ln_psi, sign)
+#define CALL(NMO) k_geminal<NMO><<<nblk(nw, 64), 64, 0, st>>>(S, nw, h->b_up.n_chunk, phi, r_up, r_dn, nullptr, nullptr, ln_psi, sign)
   DISPATCH_NMO(h, CALL);
 #undef CALL
   }
@@ -1023,7 +1074,7 @@ extern "C" int qe_local_energy(qe_engine* h, int nw, const double* r_up, const d
     const int frc = qe_local_energy_fused(h, nw, r_up, r_dn, RT, Ginv, e_L, T_elem, V_parts, st);
     if (frc != QE_ERR_UNSUPPORTED) return frc;
   }
-  const int nch = h->n_chunk_el, P = h->nmo_pad;
+  const int nch = h->b_up.n_chunk, P = h->nmo_pad;
   int rc = ensure_ws(h, ws_need_common(h, nw, nch, 5));
   if (rc) return rc;
   WsCarve c{(char*)h->ws};
@@ -1036,8 +1087,8 @@ extern "C" int qe_local_energy(qe_engine* h, int nw, const double* r_up, const d
   const long long t1 = (long long)nch * S.n_e * nw;
   { LaunchScope ls_(h, K_ORB_EL, st);
 #define CALL(NMO, CART)                                                                                          \
-  k_orb_electrons<NMO, CART, 5><<<nblk(t1, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, \
-                                                               h->d_chunk_el, nch, phi)
+  k_orb_electrons<NMO, CART, 5><<<nblk(t1, 128), 128, 0, st>>>(h->b_up.dev, S, nw, r_up, r_dn, h->b_up.off_cseg, \
+                                                                   h->b_up.off_cbeg, nch, phi)
   DISPATCH_NMO_CART(h, CALL);
 #undef CALL
   }
@@ -1053,7 +1104,7 @@ extern "C" int qe_local_energy(qe_engine* h, int nw, const double* r_up, const d
     const long long t3 = (long long)S.n_e * S.NN * S.Nv * nw;
     { LaunchScope ls_(h, K_ECP_MESH, st);
 #define CALL(NMO, CART) \
-  k_ecp_mesh<NMO, CART><<<nblk(t3, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, RT, W, 0, Vnl, nullptr)
+  k_ecp_mesh<NMO, CART><<<nblk(t3, 128), 128, 0, st>>>(h->b_up.dev, S, nw, r_up, r_dn, RT, W, 0, Vnl, nullptr)
     DISPATCH_NMO_CART(h, CALL);
 #undef CALL
     }
@@ -1073,7 +1124,7 @@ extern "C" int qe_move_ratios(qe_engine* h, int nw, const double* r_up, const do
   const SysDev& S = h->sys;
   for (int i = 0; i < n_moves; ++i)
     if (elec_host[i] < 0 || elec_host[i] >= S.n_e) return fail(QE_ERR_INVALID, "qe_move_ratios: electron index out of range");
-  const int nch = h->n_chunk_el, P = h->nmo_pad;
+  const int nch = h->b_up.n_chunk, P = h->nmo_pad;
   int rc = ensure_ws(h, ws_need_common(h, nw, nch, 1) + (size_t)n_moves * 4 + 256);
   if (rc) return rc;
   WsCarve c{(char*)h->ws};
@@ -1084,8 +1135,8 @@ extern "C" int qe_move_ratios(qe_engine* h, int nw, const double* r_up, const do
   const long long t1 = (long long)nch * S.n_e * nw;
   { LaunchScope ls_(h, K_ORB_EL, st);
 #define CALL(NMO, CART)                                                                                          \
-  k_orb_electrons<NMO, CART, 1><<<nblk(t1, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, \
-                                                               h->d_chunk_el, nch, phi)
+  k_orb_electrons<NMO, CART, 1><<<nblk(t1, 128), 128, 0, st>>>(h->b_up.dev, S, nw, r_up, r_dn, h->b_up.off_cseg, \
+                                                                   h->b_up.off_cbeg, nch, phi)
   DISPATCH_NMO_CART(h, CALL);
 #undef CALL
   }
@@ -1101,7 +1152,7 @@ extern "C" int qe_move_ratios(qe_engine* h, int nw, const double* r_up, const do
   const long long t3 = (long long)n_moves * nw;
   { LaunchScope ls_(h, K_RATIOS, st);
 #define CALL(NMO, CART)                                                                                                   \
-  k_move_ratios<NMO, CART><<<nblk(t3, 128), 128, 0, st>>>(h->b_up.dev, h->b_dn.dev, S, nw, r_up, r_dn, W, n_moves, elec, \
+  k_move_ratios<NMO, CART><<<nblk(t3, 128), 128, 0, st>>>(h->b_up.dev, S, nw, r_up, r_dn, W, n_moves, elec, \
                                                           r_new, det_ratio, jas_ratio)
   DISPATCH_NMO_CART(h, CALL);
 #undef CALL

@@ -83,12 +83,12 @@ struct McmcArgs {
   const int* raxis;
   const double* rg;
   const double* rb;
-  const int* chunk_begin;
+  int off_cseg, off_cbeg;
 };
 
 template <int NMO, bool CART>
 __global__ void __launch_bounds__(512)
-k_mcmc(BasisDev Bu, BasisDev Bd, SysDev S, McmcArgs P) {
+k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
   extern __shared__ double sm[];
   const int lane = threadIdx.x, wid = threadIdx.y;
   const int w = blockIdx.x * 32 + lane;
@@ -96,6 +96,7 @@ k_mcmc(BasisDev Bu, BasisDev Bd, SysDev S, McmcArgs P) {
   const int ww = live ? w : P.nw - 1;  // dead lanes shadow the last walker (no stores)
   const int N = S.n_up, Nd = S.n_dn, Ne = S.n_e, NN2 = N * N;
   const int nch = P.n_chunk;
+  const int* cbeg = (const int*)(B.g + P.off_cbeg);
   // shared-memory carve-up (all [item][32])
   double* s_r = sm;                       // Ne*3
   double* s_G = s_r + Ne * 3 * 32;        // N*N
@@ -126,10 +127,9 @@ k_mcmc(BasisDev Bu, BasisDev Bd, SysDev S, McmcArgs P) {
   // ---- orbital values at every electron (cache for the row/column rebuild) -----------------------
   for (int e = 0; e < Ne; ++e) {
     if (wid < nch) {
-      const BasisDev& B = e < N ? Bu : Bd;
       SinkMO<NMO> sink;
-      sink.init(B.Cs);
-      eval_val<CART>(B, S.Rn, SR(e, 0), SR(e, 1), SR(e, 2), P.chunk_begin[wid], P.chunk_begin[wid + 1], sink);
+      sink.init(B.g + (e < N ? B.off_C : B.off_C2));
+      eval_val<CART, QE_LMAX>(B.g, B, P.off_cseg, SR(e, 0), SR(e, 1), SR(e, 2), cbeg[wid], cbeg[wid + 1], sink);
 #pragma unroll
       for (int mo = 0; mo < NMO; ++mo) SPART(wid, mo) = sink.acc[mo];
     }
@@ -183,8 +183,8 @@ k_mcmc(BasisDev Bu, BasisDev Bd, SysDev S, McmcArgs P) {
     if (wid < nch) {
       // same AO tables for both spins (checked at create); the MO coefficients may differ per lane
       SinkMO<NMO> sink;
-      sink.init(up ? Bu.Cs : Bd.Cs);
-      eval_val<CART>(Bu, S.Rn, nx, ny, nz, P.chunk_begin[wid], P.chunk_begin[wid + 1], sink);
+      sink.init(B.g + (up ? B.off_C : B.off_C2));
+      eval_val<CART, QE_LMAX>(B.g, B, P.off_cseg, nx, ny, nz, cbeg[wid], cbeg[wid + 1], sink);
 #pragma unroll
       for (int mo = 0; mo < NMO; ++mo) SPART(wid, mo) = sink.acc[mo];
     } else {
@@ -193,7 +193,7 @@ k_mcmc(BasisDev Bu, BasisDev Bd, SysDev S, McmcArgs P) {
       const double f_p = 1.0 / (Zc * Zc) * (1.0 + Zc * Zc * dist) / (1.0 + dist);
       const double dd = (nx - ox) * (nx - ox) + (ny - oy) * (ny - oy) + (nz - oz) * (nz - oz);
       const double T_ratio =
-          (f_l / f_p) * exp(-dd * (1.0 / (2.0 * f_p * f_p * P.Dt * P.Dt) - 1.0 / (2.0 * f_l * f_l * P.Dt * P.Dt)));
+          (f_l / f_p) * qexp(-dd * (1.0 / (2.0 * f_p * f_p * P.Dt * P.Dt) - 1.0 / (2.0 * f_l * f_l * P.Dt * P.Dt)));
       struct PosS {
         const double* s_r;
         int lane;
@@ -203,7 +203,7 @@ k_mcmc(BasisDev Bu, BasisDev Bd, SysDev S, McmcArgs P) {
           z = s_r[(e * 3 + 2) * 32 + lane];
         }
       } pos{s_r, lane};
-      const double J_ratio = exp(jastrow_delta(S, pos, ke, ox, oy, oz, nx, ny, nz));
+      const double J_ratio = qexp(jastrow_delta(S, pos, ke, ox, oy, oz, nx, ny, nz));
       s_TJ[lane] = T_ratio;
       s_TJ[32 + lane] = J_ratio;
     }
@@ -407,7 +407,7 @@ extern "C" int qe_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, 
   const SysDev& S = h->sys;
   if (S.n_up > 8) return fail(QE_ERR_UNSUPPORTED, "qe_mcmc_update: more than 8 electrons per spin is not implemented in this build");
   cudaStream_t st = (cudaStream_t)stream;
-  const int P = h->nmo_pad, nch = h->n_chunk_mc;
+  const int P = h->nmo_pad, nch = h->b_up.n_chunk;
   const size_t n_draw = (size_t)std::max(1, nmpm) * nw;
   int rc = ensure_ws(h, n_draw * (6 * 8 + 4 + 4 + 8 + 8) + 4096);
   if (rc) return rc;
@@ -427,14 +427,14 @@ extern "C" int qe_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, 
     }
     CHECK_LAUNCH();
   }
-  McmcArgs A{nw, nmpm, nch, Dt, epsilon_AS, r_up, r_dn, G, Ginv, acc, rej, rsel, raxis, rg, rb, h->d_chunk_mc};
+  McmcArgs A{nw, nmpm, nch, Dt, epsilon_AS, r_up, r_dn, G, Ginv, acc, rej, rsel, raxis, rg, rb, h->b_up.off_cseg, h->b_up.off_cbeg};
   const size_t smem = (size_t)(S.n_e * 3 + 2 * S.n_up * S.n_up + S.n_e * P + nch * P + 2) * 32 * 8;
   dim3 block(32, nch + 1);
   { LaunchScope ls_(h, K_MCMC, st);
 #define CALL(NMO, CART)                                                                                           \
   do {                                                                                                            \
     CUDA_TRY(cudaFuncSetAttribute(k_mcmc<NMO, CART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    k_mcmc<NMO, CART><<<nblk(nw, 32), block, smem, st>>>(h->b_up.dev, h->b_dn.dev, S, A);                         \
+    k_mcmc<NMO, CART><<<nblk(nw, 32), block, smem, st>>>(h->b_up.dev, S, A);                         \
   } while (0)
   DISPATCH_NMO_CART(h, CALL);
 #undef CALL

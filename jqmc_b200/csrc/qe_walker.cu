@@ -1,25 +1,28 @@
 // Fused per-walker kernel: LRDMC projection (GFMC_n._projection_n, jqmc/jqmc_gfmc.py:4738-5358), its
 // observable V_diag / V_nondiag (_compute_V_elements_n, :5360-5627) and the VMC local energy
-// (compute_local_energy_fast, jqmc/hamiltonians.py:225-290) share one kernel:
+// (compute_local_energy_fast, jqmc/hamiltonians.py:225-290) share one kernel.
 //
-//   CTA = 32 walkers (lanes) x NW warps.  Basis / Jastrow / ECP tables are staged in shared memory once per
-//   CTA; walker state (positions, running inverse, cached MO value/grad/lap of every electron, ratio weight
-//   vectors) lives in shared memory as [item][lane].  Warps take TASKS (a mesh point, an electron, a basis
-//   chunk); every lane of a warp executes the same task on its own walker, so control flow is uniform and
-//   table reads are warp-broadcast LDS.
+//   CTA = WPC walkers x NWARP warps.  The basis image and the Jastrow / ECP tables are staged in shared memory once per
+//   CTA; walker state (positions, running inverse, cached MO value/grad/lap of every electron, ratio weight vectors,
+//   mesh elements) lives in shared memory as [item][walker].
 //
-//   per projection:  P1  ratio weight vectors W[:,e] from the running inverse            (task = electron)
-//                    P2  6 N_e kinetic-mesh ratios, N_e*NN*Nv ECP-mesh ratios,
-//                        per-electron continuum kinetic energy and potential pieces       (task = point / electron)
-//                    P3  warp 0: fixed-node split, diagonal/off-diagonal sums, weight, move selection
-//                    P4  value/grad/lap of the moved electron (task = basis chunk), Sherman-Morrison update
+//   A thread is a (walker, task) pair.  The dominant tasks -- one AO sweep per mesh point -- are the SAME code for every
+//   point, so the 32 lanes of a warp hold 32/WPC consecutive mesh points of WPC walkers: control flow stays uniform, table
+//   reads are warp-broadcast LDS, and WPC is free to make the grid fill the 148 SMs (4096 walkers / 8 = 512 CTAs, 4 per SM).
+//   Several CTAs per SM also hide each other's short serial sections (selection, Sherman-Morrison).
+//
+//   per projection:  P1  ratio weight vectors W[:,e] = lambda Phi_dn Ginv[:,e] from the running inverse   (walker, electron)
+//                    P2  6 N_e kinetic-mesh ratios + N_e*NN*Nv ECP-mesh ratios (warp rounds handed out
+//                        by a shared counter), per-electron continuum kinetic energy and potentials          (walker, point)
+//                    P3  fixed-node split, diagonal / off-diagonal sums, weight, sequential-cumsum move selection
+//                    P4  value/grad/lap of the moved electron (warp = basis chunk), Sherman-Morrison update
 #include "qe_common.cuh"
 
 namespace {
 
 struct WalkerArgs {
   int nw, nmpm, mode;  // mode 0: projection, 1: V elements (no move), 2: VMC local energy
-  int dlt, ecp_n_chunk;
+  int dlt, wpc;
   double alat, E_scf;
   double* w;
   double* r_up;
@@ -34,18 +37,19 @@ struct WalkerArgs {
   double* V_parts;
   const double* rRT;  // mode 0 draws: [(it*9+c)][nw]
   const double* ru;   //               [it][nw]
-  const int* chunk_begin;
-  int n_chunk;
+  int off_cseg, off_cbeg, n_chunk;
 };
 
+// shared-memory carve-up by byte offsets from the (16-byte aligned) dynamic shared memory base
 struct Carve {
-  char* p;
-  __device__ __forceinline__ Carve(char* base) : p(base) {}
+  char* base;
+  size_t off;
+  __device__ Carve(char* b, size_t o) : base(b), off(o) {}
   template <class T>
-  __device__ __forceinline__ T* take(size_t n) {
-    p = (char*)(((uintptr_t)p + 15) & ~uintptr_t(15));
-    T* r = (T*)p;
-    p += n * sizeof(T);
+  __device__ T* take(size_t n) {
+    off = (off + 15) & ~size_t(15);
+    T* r = (T*)(base + off);
+    off += n * sizeof(T);
     return r;
   }
 };
@@ -55,18 +59,6 @@ __device__ __forceinline__ const T* stage(Carve& c, const T* src, size_t n, int 
   T* dst = c.take<T>(n);
   for (size_t i = tid; i < n; i += nthr) dst[i] = src[i];
   return dst;
-}
-
-__device__ __forceinline__ BasisDev stage_basis(const BasisDev& g, Carve& c, int tid, int nthr) {
-  BasisDev s = g;
-  s.grp_nuc = stage(c, g.grp_nuc, g.n_grp, tid, nthr);
-  s.grp_l = stage(c, g.grp_l, g.n_grp, tid, nthr);
-  s.grp_sh_begin = stage(c, g.grp_sh_begin, g.n_grp + 1, tid, nthr);
-  s.sh_prim_off = stage(c, g.sh_prim_off, g.n_shell + 1, tid, nthr);
-  s.sh_slot = stage(c, g.sh_slot, (size_t)g.n_shell * MAXF, tid, nthr);
-  s.pr_zc = stage(c, g.pr_zc, g.n_prim, tid, nthr);
-  s.Cs = stage(c, g.Cs, (size_t)g.n_ao * g.nmo_pad, tid, nthr);
-  return s;
 }
 
 __device__ __forceinline__ SysDev stage_sys(const SysDev& g, int nmo, Carve& c, int tid, int nthr) {
@@ -90,22 +82,20 @@ __device__ __forceinline__ SysDev stage_sys(const SysDev& g, int nmo, Carve& c, 
   return s;
 }
 
-size_t table_bytes(const BasisDev& b, const SysDev& s, int nmo) {
-  size_t n = 0;
-  n += (size_t)(3 * b.n_grp + 1 + b.n_shell + 1) * 4 + (size_t)b.n_shell * MAXF * 2 + (size_t)b.n_prim * 16 + (size_t)b.n_ao * b.nmo_pad * 8;
-  n += (size_t)(3 * s.n_atom + 3 * s.n_atom + nmo * nmo + nmo * (s.n_unp > 0 ? s.n_unp : 1)) * 8;
-  if (s.ecp_flag) n += (size_t)s.n_ecp * (4 + 24) + (size_t)s.n_atom * 8 + 4 + (size_t)s.Nv * 32;
-  return n + 16 * 32;  // alignment slack
+size_t sys_bytes(const SysDev& s, int nmo) {
+  size_t n = (size_t)(3 * s.n_atom + 3 * s.n_atom + nmo * nmo + nmo * (s.n_unp > 0 ? s.n_unp : 1)) * 8 + 6 * 16;
+  if (s.ecp_flag) n += (size_t)s.n_ecp * (4 + 24) + (size_t)s.n_atom * 8 + 4 + (size_t)s.Nv * 32 + 8 * 16;
+  return n;
 }
 
-// electron positions held in shared memory as [e*3+c][lane]
+// electron positions held in shared memory as [(e*3+c)][walker]
 struct PosShared {
   const double* s_r;
-  int lane;
+  int wpc, wl;
   __device__ __forceinline__ void get(int e, double& x, double& y, double& z) const {
-    x = s_r[(e * 3 + 0) * 32 + lane];
-    y = s_r[(e * 3 + 1) * 32 + lane];
-    z = s_r[(e * 3 + 2) * 32 + lane];
+    x = s_r[(e * 3 + 0) * wpc + wl];
+    y = s_r[(e * 3 + 1) * wpc + wl];
+    z = s_r[(e * 3 + 2) * wpc + wl];
   }
 };
 
@@ -133,65 +123,77 @@ __device__ __forceinline__ void ecp_point(const SysDev& S, const double* rt, dou
   for (int l = 0; l < lloc; ++l) {
     double vl = 0.0;
     for (int kk = S.ecp_off[a]; kk < S.ecp_off[a + 1]; ++kk)
-      if (S.ecp_l[kk] == l) vl += S.ecp_c[kk] * pow(d, S.ecp_p[kk]) * exp(-S.ecp_z[kk] * d * d);
+      if (S.ecp_l[kk] == l) vl += S.ecp_c[kk] * ipow(d, S.ecp_p[kk]) * qexp(-S.ecp_z[kk] * d * d);
     ang = fma(vl / (d * d) * (2 * l + 1), legendre_l(l, cos_t), ang);
   }
   ang_w = ang * S.quad_w[k];
 }
 
-template <int NMO, bool CART>
-__global__ void __launch_bounds__(512)
-k_walker(BasisDev Bu_g, BasisDev Bd_g, SysDev S_g, WalkerArgs P) {
+template <int NMO, bool CART, int LMAX>
+__global__ void __launch_bounds__(512, 1)
+k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
   extern __shared__ __align__(16) char smem_raw[];
-  const int lane = threadIdx.x, wid = threadIdx.y, NW = blockDim.y;
-  const int tid = wid * 32 + lane, nthr = NW * 32;
-  const int w = blockIdx.x * 32 + lane;
-  const bool live = w < P.nw;
-  const int ww = live ? w : P.nw - 1;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, wid = tid >> 5, NWARP = nthr >> 5;
+  const int WPC = P.wpc;
+  const int w0 = blockIdx.x * WPC;
 
   // ---- stage tables ------------------------------------------------------------------------------
-  Carve cv(smem_raw);
-  const BasisDev Bu = stage_basis(Bu_g, cv, tid, nthr);
-  BasisDev Bd = Bu;
-  if (Bd_g.Cs != Bu_g.Cs) Bd.Cs = stage(cv, Bd_g.Cs, (size_t)Bd_g.n_ao * Bd_g.nmo_pad, tid, nthr);
+  {
+    const int4* src = (const int4*)B.g;
+    int4* dst = (int4*)smem_raw;
+    for (int i = tid; i < B.bytes / 16; i += nthr) dst[i] = src[i];
+  }
+  const char* tab = smem_raw;
+  Carve cv(smem_raw, (size_t)B.bytes);
   const SysDev S = stage_sys(S_g, NMO, cv, tid, nthr);
   const int N = S.n_up, Nd = S.n_dn, Ne = S.n_e, NN2 = N * N;
-  const int nch = P.n_chunk;
   const int n_kin = P.mode == 2 ? 0 : 6 * Ne;
   const int n_ecp = S.ecp_flag ? Ne * S.NN * S.Nv : 0;
   const int NPT = n_kin + n_ecp;
 
-  double* s_r = cv.take<double>((size_t)Ne * 3 * 32);
-  double* s_Gi = cv.take<double>((size_t)NN2 * 32);
-  double* s_phi = cv.take<double>((size_t)Ne * 5 * NMO * 32);  // [(e*5+q)*NMO+mo]
-  double* s_W = cv.take<double>((size_t)Ne * NMO * 32);
-  double* s_p = cv.take<double>((size_t)(NPT > 0 ? NPT : 1) * 32);
-  double* s_j = cv.take<double>((size_t)(n_ecp > 0 ? n_ecp : 1) * 32);
-  double* s_el = cv.take<double>((size_t)Ne * 5 * 32);  // [e*5 + {ke, ei, eid, loc, ee}]
-  double* s_part = cv.take<double>((size_t)2 * nch * NMO * 32);  // double buffer of per-chunk partials, one component at a time
-  double* s_stage = cv.take<double>((size_t)5 * NMO * 32);
-  double* s_misc = cv.take<double>((size_t)16 * 32);  // 0..8 RT, 9..11 new position, 12 selected electron
-#define SR(e, c) s_r[((e) * 3 + (c)) * 32 + lane]
-#define SGI(i, j) s_Gi[((i) * N + (j)) * 32 + lane]
-#define SPHI(e, q, mo) s_phi[(((e) * 5 + (q)) * NMO + (mo)) * 32 + lane]
-#define SW(e, mo) s_W[((e) * NMO + (mo)) * 32 + lane]
-#define SEL(e, i) s_el[((e) * 5 + (i)) * 32 + lane]
-#define SMISC(i) s_misc[(i) * 32 + lane]
+  double* s_r = cv.take<double>((size_t)Ne * 3 * WPC);
+  double* s_Gi = cv.take<double>((size_t)NN2 * WPC);
+  double* s_phi = cv.take<double>((size_t)Ne * 5 * NMO * WPC);  // [(e*5+q)*NMO+mo]
+  double* s_W = cv.take<double>((size_t)Ne * NMO * WPC);
+  double* s_p = cv.take<double>((size_t)(NPT > 0 ? NPT : 1) * WPC);
+  double* s_j = cv.take<double>((size_t)(n_ecp > 0 ? n_ecp : 1) * WPC);
+  double* s_el = cv.take<double>((size_t)Ne * 8 * WPC);  // [e*8 + {ke|opt, ei, eid, loc, ee, kinFN, kinSP, -}]
+  double* s_part = cv.take<double>((size_t)NWARP * 5 * NMO * WPC);
+  double* s_stage = cv.take<double>((size_t)5 * NMO * WPC);
+  double* s_misc = cv.take<double>((size_t)16 * WPC);  // 0..8 RT, 9..11 new position, 12 selected electron, 13 total
+  int* s_ctr = cv.take<int>(4);
+#define SR(e, c) s_r[((e) * 3 + (c)) * WPC + wl]
+#define SGI(i, j) s_Gi[((i) * N + (j)) * WPC + wl]
+#define SPHI(e, q, mo) s_phi[(((e) * 5 + (q)) * NMO + (mo)) * WPC + wl]
+#define SW(e, mo) s_W[((e) * NMO + (mo)) * WPC + wl]
+#define SEL(e, i) s_el[((e) * 8 + (i)) * WPC + wl]
+#define SMISC(i) s_misc[(i) * WPC + wl]
+#define GW(wl_) (min(w0 + (wl_), P.nw - 1)) /* dead walkers of the last CTA shadow the last walker (no stores) */
 
-  for (int idx = wid; idx < Ne * 3; idx += NW) {
-    const int e = idx / 3, c = idx % 3;
-    SR(e, c) = e < N ? P.r_up[((size_t)ww * N + e) * 3 + c] : P.r_dn[((size_t)ww * Nd + (e - N)) * 3 + c];
+  for (int idx = tid; idx < Ne * 3 * WPC; idx += nthr) {
+    const int wl = idx % WPC, it = idx / WPC, e = it / 3, c = it % 3;
+    const int ww = GW(wl);
+    s_r[idx] = e < N ? P.r_up[((size_t)ww * N + e) * 3 + c] : P.r_dn[((size_t)ww * Nd + (e - N)) * 3 + c];
   }
-  for (int idx = wid; idx < NN2; idx += NW) s_Gi[idx * 32 + lane] = P.Ginv[(size_t)ww * NN2 + idx];
-  if (P.mode != 0 && wid == 0)
-    for (int c = 0; c < 9; ++c) SMISC(c) = P.RT_in ? P.RT_in[(size_t)ww * 9 + c] : (c % 4 == 0 ? 1.0 : 0.0);
+  for (int idx = tid; idx < NN2 * WPC; idx += nthr) {
+    const int wl = idx % WPC, it = idx / WPC;
+    s_Gi[idx] = P.Ginv[(size_t)GW(wl) * NN2 + it];
+  }
+  if (P.mode != 0)
+    for (int idx = tid; idx < 9 * WPC; idx += nthr) {
+      const int wl = idx % WPC, c = idx / WPC;
+      s_misc[idx] = P.RT_in ? P.RT_in[(size_t)GW(wl) * 9 + c] : (c % 4 == 0 ? 1.0 : 0.0);
+    }
+  if (tid == 0) s_ctr[0] = 0;
   __syncthreads();
 
-  // ---- value/grad/lap of the MOs at every electron (cache): task = electron ----------------------------
-  for (int e = wid; e < Ne; e += NW) {
+  // ---- value/grad/lap of the MOs at every electron (cache): task = (walker, electron) ------------------------
+  for (int s = tid; s < Ne * WPC; s += nthr) {
+    const int wl = s % WPC, e = s / WPC;
     SinkMO5<NMO> sink;
-    sink.init(e < N ? Bu.Cs : Bd.Cs);
-    eval_vgl<CART>(Bu, S.Rn, SR(e, 0), SR(e, 1), SR(e, 2), 0, Bu.n_grp, sink);
+    sink.init(tab + (e < N ? B.off_C : B.off_C2));
+    eval_vgl<CART, LMAX>(tab, B, B.off_seg, SR(e, 0), SR(e, 1), SR(e, 2), 0, B.n_grp, sink);
 #pragma unroll
     for (int q = 0; q < 5; ++q)
 #pragma unroll
@@ -199,180 +201,236 @@ k_walker(BasisDev Bu_g, BasisDev Bd_g, SysDev S_g, WalkerArgs P) {
   }
   __syncthreads();
 
-  double w_L = (P.mode == 0) ? P.w[ww] : 1.0;
-  double diag = 0.0, nondiag = 0.0;
   const double a2 = P.alat * P.alat;
   const int n_it = P.mode == 0 ? P.nmpm : 1;
+  double w_L = 1.0, diag = 0.0, nondiag = 0.0;  // meaningful in threads tid < WPC (wl = tid)
+  if (P.mode == 0 && tid < WPC) w_L = P.w[GW(tid)];
+  // mesh-point slot blocks (same spin => same MO coefficient table): kinetic up, kinetic dn, ECP up, ECP dn
+  const int n_eu = S.ecp_flag ? N * S.NN * S.Nv : 0, n_ed = S.ecp_flag ? Nd * S.NN * S.Nv : 0;
+  const int n_ku = P.mode == 2 ? 0 : 6 * N, n_kd = P.mode == 2 ? 0 : 6 * Nd;
+  const int blk_size[4] = {n_ku * WPC, n_kd * WPC, n_eu * WPC, n_ed * WPC};
+  const int blk_start[4] = {0, n_ku * WPC, n_kin * WPC, (n_kin + n_eu) * WPC};
+  const int blk_pairs[4] = {(blk_size[0] + 1) / 2, (blk_size[1] + 1) / 2, (blk_size[2] + 1) / 2, (blk_size[3] + 1) / 2};
+  const int n_rounds_pt = (blk_pairs[0] + blk_pairs[1] + blk_pairs[2] + blk_pairs[3] + 31) / 32;
+  const int n_rounds_el = (Ne * WPC + 31) / 32;
 
   for (int it = 0; it < n_it; ++it) {
-    // ---- P1: ratio weight vectors ---------------------------------------------------------------------
-    if (P.mode == 0 && wid == NW - 1)
-      for (int c = 0; c < 9; ++c) SMISC(c) = P.rRT[((size_t)it * 9 + c) * P.nw + ww];
-    for (int e = wid; e < Ne; e += NW) {
+    // ---- P1: ratio weight vectors, task = (walker, electron) -----------------------------------------------------
+    if (P.mode == 0)
+      for (int idx = tid; idx < 9 * WPC; idx += nthr) {
+        const int wl = idx % WPC, c = idx / WPC;
+        s_misc[idx] = P.rRT[((size_t)it * 9 + c) * P.nw + GW(wl)];
+      }
+    for (int s = tid; s < Ne * WPC; s += nthr) {
+      const int wl = s % WPC, e = s / WPC;
       double Wv[NMO];
       if (e < N) {
         double y[NMO];
 #pragma unroll
         for (int b = 0; b < NMO; ++b) {
-          double s = 0;
-          for (int j = 0; j < Nd; ++j) s = fma(SPHI(N + j, 0, b), SGI(j, e), s);
-          y[b] = s;
+          double sum = 0;
+          for (int j = 0; j < Nd; ++j) sum = fma(SPHI(N + j, 0, b), SGI(j, e), sum);
+          y[b] = sum;
         }
 #pragma unroll
         for (int a = 0; a < NMO; ++a) {
-          double s = 0;
+          double sum = 0;
 #pragma unroll
-          for (int b = 0; b < NMO; ++b) s = fma(S.lam_p[a * NMO + b], y[b], s);
-          for (int k = 0; k < S.n_unp; ++k) s = fma(S.lam_u[a * S.n_unp + k], SGI(Nd + k, e), s);
-          Wv[a] = s;
+          for (int b = 0; b < NMO; ++b) sum = fma(S.lam_p[a * NMO + b], y[b], sum);
+          for (int k = 0; k < S.n_unp; ++k) sum = fma(S.lam_u[a * S.n_unp + k], SGI(Nd + k, e), sum);
+          Wv[a] = sum;
         }
       } else {
         const int j = e - N;
         double y[NMO];
 #pragma unroll
         for (int a = 0; a < NMO; ++a) {
-          double s = 0;
-          for (int i = 0; i < N; ++i) s = fma(SPHI(i, 0, a), SGI(j, i), s);
-          y[a] = s;
+          double sum = 0;
+          for (int i = 0; i < N; ++i) sum = fma(SPHI(i, 0, a), SGI(j, i), sum);
+          y[a] = sum;
         }
 #pragma unroll
         for (int b = 0; b < NMO; ++b) {
-          double s = 0;
+          double sum = 0;
 #pragma unroll
-          for (int a = 0; a < NMO; ++a) s = fma(y[a], S.lam_p[a * NMO + b], s);
-          Wv[b] = s;
+          for (int a = 0; a < NMO; ++a) sum = fma(y[a], S.lam_p[a * NMO + b], sum);
+          Wv[b] = sum;
         }
       }
 #pragma unroll
       for (int mo = 0; mo < NMO; ++mo) SW(e, mo) = Wv[mo];
+      // Jastrow terms of electron e at its current position (shared by all of its mesh points)
+      PosShared pos{s_r, WPC, wl};
+      SEL(e, 7) = jastrow_single(S, pos, e, SR(e, 0), SR(e, 1), SR(e, 2));
     }
     __syncthreads();
 
-    // ---- P2: mesh ratios and per-electron terms ---------------------------------------------------------
-    PosShared pos{s_r, lane};
-    double rt[9];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) rt[c] = SMISC(c);
-    const int NT = NPT + Ne;
-    for (int t = wid; t < NT; t += NW) {
-      if (t < NPT) {
-        int e;
-        double px, py, pz, x, y, z, angw = 0.0;
-        const bool kin = t < n_kin;
-        if (kin) {
-          e = t / 6;
-          const int s = t % 6, ax = s >> 1;
-          const double sg = (s & 1) ? -P.alat : P.alat;
-          pos.get(e, x, y, z);
-          px = x + sg * rt[3 * ax];
-          py = y + sg * rt[3 * ax + 1];
-          pz = z + sg * rt[3 * ax + 2];
-        } else {
-          const int pt = t - n_kin;
-          const int k = pt % S.Nv, nn = (pt / S.Nv) % S.NN;
-          e = pt / (S.Nv * S.NN);
-          pos.get(e, x, y, z);
-          ecp_point(S, rt, x, y, z, nn, k, px, py, pz, angw, true);
+    // ---- P2: mesh ratios (rounds 0 .. n_rounds_pt-1) and per-electron terms (the following n_rounds_el rounds); a warp
+    //      takes the next round from a shared counter.  A thread evaluates TWO mesh points of the same spin block at once
+    //      (same shell / primitive sequence, coefficient rows loaded once, twice the independent DFMA chains) ------------------
+    for (;;) {
+      int r = 0;
+      if (lane == 0) r = atomicAdd(&s_ctr[0], 1);
+      r = __shfl_sync(0xffffffffu, r, 0);
+      if (r >= n_rounds_pt + n_rounds_el) break;
+      if (r < n_rounds_pt) {
+        int pi = r * 32 + lane;  // pair index -> block (kin up, kin dn, ecp up, ecp dn)
+        int blk = 0;
+        while (blk < 4 && pi >= blk_pairs[blk]) {
+          pi -= blk_pairs[blk];
+          ++blk;
         }
-        SinkMO<NMO> sink;
-        sink.init(e < N ? Bu.Cs : Bd.Cs);
-        eval_val<CART>(Bu, S.Rn, px, py, pz, 0, Bu.n_grp, sink);
-        double ratio = 0.0;
+        if (blk < 4) {
+          const int half = blk_pairs[blk];
+          const int sA = blk_start[blk] + pi;
+          const bool validB = pi + half < blk_size[blk];
+          const int sB = validB ? sA + half : sA;
+          const int sl[2] = {sA, sB};
+          double px[2], py[2], pz[2], angw[2], jold[2];
+          int el[2], wls[2];
 #pragma unroll
-        for (int mo = 0; mo < NMO; ++mo) ratio = fma(sink.acc[mo], SW(e, mo), ratio);
-        const double jr = exp(jastrow_delta(S, pos, e, x, y, z, px, py, pz));
-        if (kin) {
-          s_p[t * 32 + lane] = -1.0 / (2.0 * a2) * (ratio * jr);
-        } else {
-          s_p[t * 32 + lane] = P.dlt ? angw * ratio : angw * (ratio * jr);
-          s_j[(t - n_kin) * 32 + lane] = jr;
+          for (int i = 0; i < 2; ++i) {
+            const int wl = sl[i] % WPC, t = sl[i] / WPC;
+            wls[i] = wl;
+            PosShared pos{s_r, WPC, wl};
+            double rt[9];
+#pragma unroll
+            for (int c = 0; c < 9; ++c) rt[c] = SMISC(c);
+            double x, y, z;
+            angw[i] = 0.0;
+            if (blk < 2) {
+              const int e = t / 6;
+              const int s6 = t % 6, ax = s6 >> 1;
+              const double sg = (s6 & 1) ? -P.alat : P.alat;
+              pos.get(e, x, y, z);
+              px[i] = x + sg * rt[3 * ax];
+              py[i] = y + sg * rt[3 * ax + 1];
+              pz[i] = z + sg * rt[3 * ax + 2];
+              el[i] = e;
+            } else {
+              const int pt = t - n_kin;
+              const int k = pt % S.Nv, nn = (pt / S.Nv) % S.NN;
+              const int e = pt / (S.Nv * S.NN);
+              pos.get(e, x, y, z);
+              ecp_point(S, rt, x, y, z, nn, k, px[i], py[i], pz[i], angw[i], true);
+              el[i] = e;
+            }
+            jold[i] = SEL(el[i], 7);
+          }
+          SinkMOn<NMO, 2> sink;
+          sink.init(tab + ((blk & 1) ? B.off_C2 : B.off_C));
+          eval_val_n<CART, LMAX, 2>(tab, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int wl = wls[i], e = el[i];
+            PosShared pos{s_r, WPC, wl};
+            double ratio = 0.0;
+#pragma unroll
+            for (int mo = 0; mo < NMO; ++mo) ratio = fma(sink.acc[i][mo], SW(e, mo), ratio);
+            const double jr = qexp(jastrow_single(S, pos, e, px[i], py[i], pz[i]) - jold[i]);
+            if (i == 0 || validB) {
+              if (blk < 2) {
+                s_p[sl[i]] = -1.0 / (2.0 * a2) * (ratio * jr);
+              } else {
+                s_p[sl[i]] = P.dlt ? angw[i] * ratio : angw[i] * (ratio * jr);
+                s_j[sl[i] - n_kin * WPC] = jr;
+              }
+            }
+          }
         }
       } else {
         // per-electron: continuum kinetic energy, bare / discretised el-ion, ECP local, el-el (pairs j > e)
-        const int e = t - NPT;
-        double x, y, z;
-        pos.get(e, x, y, z);
-        double gD[3] = {0, 0, 0}, lD = 0;
+        const int s = (r - n_rounds_pt) * 32 + lane;
+        if (s < Ne * WPC) {
+          const int wl = s % WPC, e = s / WPC;
+          PosShared pos{s_r, WPC, wl};
+          double x, y, z;
+          pos.get(e, x, y, z);
+          double gD[3] = {0, 0, 0}, lD = 0;
 #pragma unroll
-        for (int mo = 0; mo < NMO; ++mo) {
-          const double wv = SW(e, mo);
-          gD[0] = fma(SPHI(e, 1, mo), wv, gD[0]);
-          gD[1] = fma(SPHI(e, 2, mo), wv, gD[1]);
-          gD[2] = fma(SPHI(e, 3, mo), wv, gD[2]);
-          lD = fma(SPHI(e, 4, mo), wv, lD);
-        }
-        lD -= gD[0] * gD[0] + gD[1] * gD[1] + gD[2] * gD[2];
-        double gJ[3] = {0, 0, 0}, lJ = 0, ei = 0, eid = 0, loc = 0, ee = 0;
-        const double eps = 1.0e-12;
-        for (int a = 0; a < S.n_atom; ++a) {
-          const double dx = x - S.Rn[3 * a], dy = y - S.Rn[3 * a + 1], dz = z - S.Rn[3 * a + 2];
-          const double d = sqrt(dx * dx + dy * dy + dz * dz);
-          ei -= S.Zeff[a] / d;
-          eid -= S.Zeff[a] / fmax(d, P.alat);
-          if (S.j1_type) {
-            const double rs = fmax(d, eps);
-            const double A = S.j1_A[a], c = S.j1_c[a], aa = S.j1_a;
-            double fp;
-            if (S.j1_type == 1) {
-              const double ex = exp(-aa * c * rs);
-              fp = -A * (c * 0.5) * ex;
-              lJ += A * (aa * c * c * 0.5) * ex - A * c * ex / rs;
-            } else {
-              const double den = 1.0 + aa * c * rs;
-              fp = -A / (2.0 * den * den);
-              lJ += A * aa * c / (den * den * den) + 2.0 * fp / rs;
+          for (int mo = 0; mo < NMO; ++mo) {
+            const double wv = SW(e, mo);
+            gD[0] = fma(SPHI(e, 1, mo), wv, gD[0]);
+            gD[1] = fma(SPHI(e, 2, mo), wv, gD[1]);
+            gD[2] = fma(SPHI(e, 3, mo), wv, gD[2]);
+            lD = fma(SPHI(e, 4, mo), wv, lD);
+          }
+          lD -= gD[0] * gD[0] + gD[1] * gD[1] + gD[2] * gD[2];
+          double gJ[3] = {0, 0, 0}, lJ = 0, ei = 0, eid = 0, loc = 0, ee = 0;
+          const double eps = 1.0e-12;
+          for (int a = 0; a < S.n_atom; ++a) {
+            const double dx = x - S.Rn[3 * a], dy = y - S.Rn[3 * a + 1], dz = z - S.Rn[3 * a + 2];
+            const double d = sqrt(dx * dx + dy * dy + dz * dz);
+            ei -= S.Zeff[a] / d;
+            eid -= S.Zeff[a] / fmax(d, P.alat);
+            if (S.j1_type) {
+              const double rs = fmax(d, eps);
+              const double A = S.j1_A[a], c = S.j1_c[a], aa = S.j1_a;
+              double fp;
+              if (S.j1_type == 1) {
+                const double ex = qexp(-aa * c * rs);
+                fp = -A * (c * 0.5) * ex;
+                lJ += A * (aa * c * c * 0.5) * ex - A * c * ex / rs;
+              } else {
+                const double den = 1.0 + aa * c * rs;
+                fp = -A / (2.0 * den * den);
+                lJ += A * aa * c / (den * den * den) + 2.0 * fp / rs;
+              }
+              const double sc = fp / rs;
+              gJ[0] = fma(sc, dx, gJ[0]);
+              gJ[1] = fma(sc, dy, gJ[1]);
+              gJ[2] = fma(sc, dz, gJ[2]);
             }
-            const double s = fp / rs;
-            gJ[0] = fma(s, dx, gJ[0]);
-            gJ[1] = fma(s, dy, gJ[1]);
-            gJ[2] = fma(s, dz, gJ[2]);
-          }
-          if (S.ecp_flag) {
-            const int lloc = S.ecp_lmax_atom[a];
-            double s = 0.0;
-            for (int k = S.ecp_off[a]; k < S.ecp_off[a + 1]; ++k)
-              if (S.ecp_l[k] == lloc) s += S.ecp_c[k] * pow(d, S.ecp_p[k]) * exp(-S.ecp_z[k] * d * d);
-            loc += s / (d * d);
-          }
-        }
-        for (int j = 0; j < Ne; ++j) {
-          if (j == e) continue;
-          double x2, y2, z2;
-          pos.get(j, x2, y2, z2);
-          const double dx = x - x2, dy = y - y2, dz = z - z2;
-          const double d = sqrt(dx * dx + dy * dy + dz * dz);
-          if (j > e) ee += 1.0 / d;
-          if (S.j2_type) {
-            const double rs = fmax(d, eps), aa = S.j2_a;
-            double fp;
-            if (S.j2_type == 1) {
-              const double den = 1.0 + aa * rs;
-              fp = 0.5 / (den * den);
-              lJ += -aa / (den * den * den) + 2.0 * fp / rs;
-            } else {
-              const double ex = exp(-aa * rs);
-              fp = 0.5 * ex;
-              lJ += -(aa * 0.5) * ex + 2.0 * fp / rs;
+            if (S.ecp_flag) {
+              const int lloc = S.ecp_lmax_atom[a];
+              double sum = 0.0;
+              for (int k = S.ecp_off[a]; k < S.ecp_off[a + 1]; ++k)
+                if (S.ecp_l[k] == lloc) sum += S.ecp_c[k] * ipow(d, S.ecp_p[k]) * qexp(-S.ecp_z[k] * d * d);
+              loc += sum / (d * d);
             }
-            const double s = fp / rs;
-            gJ[0] = fma(s, dx, gJ[0]);
-            gJ[1] = fma(s, dy, gJ[1]);
-            gJ[2] = fma(s, dz, gJ[2]);
           }
+          for (int j = 0; j < Ne; ++j) {
+            if (j == e) continue;
+            double x2, y2, z2;
+            pos.get(j, x2, y2, z2);
+            const double dx = x - x2, dy = y - y2, dz = z - z2;
+            const double d = sqrt(dx * dx + dy * dy + dz * dz);
+            if (j > e) ee += 1.0 / d;
+            if (S.j2_type) {
+              const double rs = fmax(d, eps), aa = S.j2_a;
+              double fp;
+              if (S.j2_type == 1) {
+                const double den = 1.0 + aa * rs;
+                fp = 0.5 / (den * den);
+                lJ += -aa / (den * den * den) + 2.0 * fp / rs;
+              } else {
+                const double ex = qexp(-aa * rs);
+                fp = 0.5 * ex;
+                lJ += -(aa * 0.5) * ex + 2.0 * fp / rs;
+              }
+              const double sc = fp / rs;
+              gJ[0] = fma(sc, dx, gJ[0]);
+              gJ[1] = fma(sc, dy, gJ[1]);
+              gJ[2] = fma(sc, dz, gJ[2]);
+            }
+          }
+          const double gx = gJ[0] + gD[0], gy = gJ[1] + gD[1], gz = gJ[2] + gD[2];
+          SEL(e, 0) = -0.5 * (lJ + lD + gx * gx + gy * gy + gz * gz);
+          SEL(e, 1) = ei;
+          SEL(e, 2) = eid;
+          SEL(e, 3) = loc;
+          SEL(e, 4) = ee;
         }
-        const double gx = gJ[0] + gD[0], gy = gJ[1] + gD[1], gz = gJ[2] + gD[2];
-        SEL(e, 0) = -0.5 * (lJ + lD + gx * gx + gy * gy + gz * gz);
-        SEL(e, 1) = ei;
-        SEL(e, 2) = eid;
-        SEL(e, 3) = loc;
-        SEL(e, 4) = ee;
       }
     }
     __syncthreads();
+    if (tid == 0) s_ctr[0] = 0;  // the next P2 starts after at least one more barrier
 
-    // ---- P3: assemble (warp 0) ---------------------------------------------------------------------------
-    if (wid == 0) {
-      if (P.mode == 2) {
+    // ---- P3: assemble -----------------------------------------------------------------------------------------------
+    if (P.mode == 2) {
+      if (tid < WPC) {
+        const int wl = tid, w = w0 + wl;
+        const bool live = w < P.nw;
         double T = 0, vbare = S.v_ion_ion, vl = 0, vnl = 0;
         for (int e = 0; e < Ne; ++e) {
           T += SEL(e, 0);
@@ -380,7 +438,7 @@ k_walker(BasisDev Bu_g, BasisDev Bd_g, SysDev S_g, WalkerArgs P) {
           vl += SEL(e, 3);
           if (P.T_elem && live) P.T_elem[(size_t)w * Ne + e] = SEL(e, 0);
         }
-        for (int k = 0; k < n_ecp; ++k) vnl += s_p[k * 32 + lane];
+        for (int k = 0; k < n_ecp; ++k) vnl += s_p[k * WPC + wl];
         if (live) {
           P.e_L[w] = T + (vbare + (vl + vnl));
           if (P.V_parts) {
@@ -390,208 +448,256 @@ k_walker(BasisDev Bu_g, BasisDev Bd_g, SysDev S_g, WalkerArgs P) {
             P.V_parts[(size_t)w * 4 + 3] = 0.0;
           }
         }
-      } else {
-        // fixed-node split and regularised diagonal (jqmc/jqmc_gfmc.py:4829-5053)
-        const double diag_kin = 3.0 / (2.0 * a2) * Ne;
-        double sum_kinFN = 0, SP_kin = 0, sum_opt_up = 0, sum_opt_dn = 0, ee = 0, loc = 0;
-        for (int e = 0; e < Ne; ++e) {
-          bool flip = false;
-          double nd = 0;
-          for (int s = 0; s < 6; ++s) {
-            const double v = s_p[(6 * e + s) * 32 + lane];
-            flip = flip || (v >= 0.0);
-            nd += v + 1.0 / (4.0 * a2);
-            const double fn = fmin(v, 0.0);
-            sum_kinFN += fn;
-            SP_kin += fmax(v, 0.0);
-            s_p[(6 * e + s) * 32 + lane] = fn;
-          }
-          const double zv = SEL(e, 1) + SEL(e, 0) - nd;
-          const double eib = S.ecp_flag ? SEL(e, 1) : SEL(e, 2);
-          const double opt = flip ? fmax(zv, eib) : zv;
-          if (e < N) sum_opt_up += opt; else sum_opt_dn += opt;
-          ee += SEL(e, 4);
-          loc += SEL(e, 3);
-        }
-        const double disc_bare = ee + S.v_ion_ion + sum_opt_up + sum_opt_dn;
-        double sum_eFN = 0, SP_e = 0;
-        for (int k = 0; k < n_ecp; ++k) {
-          const double v = s_p[(n_kin + k) * 32 + lane];
-          SP_e += fmax(v, 0.0);
-          double fn = fmin(v, 0.0);
-          if (P.dlt) fn *= s_j[k * 32 + lane];
-          sum_eFN += fn;
-          s_p[(n_kin + k) * 32 + lane] = fn;
-        }
-        nondiag = sum_kinFN + sum_eFN;
-        diag = S.ecp_flag ? diag_kin + disc_bare + loc + SP_kin + SP_e : diag_kin + disc_bare + SP_kin;
-        if (P.mode == 0) {
-          const double b_x = 1.0 / (diag - P.E_scf) * (-nondiag);
-          w_L *= b_x;
-          double tot = 0;
-          for (int k = 0; k < NPT; ++k) tot += s_p[k * 32 + lane];
-          const double u = P.ru[(size_t)it * P.nw + ww];
-          int ksel = NPT - 1;
-          double c = 0;
-          for (int k = 0; k < NPT; ++k) {
-            c += s_p[k * 32 + lane] / tot;
-            if (c >= u) {
-              ksel = k;
-              break;
-            }
-          }
-          int e;
-          double x, y, z, px, py, pz, dummy;
-          if (ksel < n_kin) {
-            e = ksel / 6;
-            const int s = ksel % 6, ax = s >> 1;
-            const double sg = (s & 1) ? -P.alat : P.alat;
-            pos.get(e, x, y, z);
-            px = x + sg * rt[3 * ax];
-            py = y + sg * rt[3 * ax + 1];
-            pz = z + sg * rt[3 * ax + 2];
-          } else {
-            const int pt = ksel - n_kin;
-            const int k = pt % S.Nv, nn = (pt / S.Nv) % S.NN;
-            e = pt / (S.Nv * S.NN);
-            pos.get(e, x, y, z);
-            ecp_point(S, rt, x, y, z, nn, k, px, py, pz, dummy, false);
-          }
-          SMISC(9) = px;
-          SMISC(10) = py;
-          SMISC(11) = pz;
-          SMISC(12) = (double)e;
-        }
+      }
+      break;
+    }
+    // (a) per (walker, electron): fixed-node split of its 6 kinetic elements, regularised el-ion term
+    //     (jqmc/jqmc_gfmc.py:4829-4939); the FN values overwrite s_p
+    for (int s = tid; s < Ne * WPC; s += nthr) {
+      const int wl = s % WPC, e = s / WPC;
+      bool flip = false;
+      double nd = 0, kinFN = 0, kinSP = 0;
+      for (int s6 = 0; s6 < 6; ++s6) {
+        const double v = s_p[(6 * e + s6) * WPC + wl];
+        flip = flip || (v >= 0.0);
+        nd += v + 1.0 / (4.0 * a2);
+        const double fn = fmin(v, 0.0);
+        kinFN += fn;
+        kinSP += fmax(v, 0.0);
+        s_p[(6 * e + s6) * WPC + wl] = fn;
+      }
+      const double zv = SEL(e, 1) + SEL(e, 0) - nd;
+      const double eib = S.ecp_flag ? SEL(e, 1) : SEL(e, 2);
+      SEL(e, 0) = flip ? fmax(zv, eib) : zv;  // regularised el-ion term of this electron
+      SEL(e, 5) = kinFN;
+      SEL(e, 6) = kinSP;
+    }
+    // (a') per (walker, ECP point): fixed-node split of the non-local elements (s_j: Jastrow ratio -> positive part)
+    for (int s = tid; s < n_ecp * WPC; s += nthr) {
+      const double v = s_p[n_kin * WPC + s];
+      double fn = fmin(v, 0.0);
+      if (P.dlt) fn *= s_j[s];
+      s_p[n_kin * WPC + s] = fn;
+      s_j[s] = fmax(v, 0.0);
+    }
+    __syncthreads();
+    // (b) per walker: sums, weight, normalisation of the move probabilities
+    if (tid < WPC) {
+      const int wl = tid;
+      const double diag_kin = 3.0 / (2.0 * a2) * Ne;
+      double sum_kinFN = 0, SP_kin = 0, sum_opt = 0, ee = 0, loc = 0;
+      for (int e = 0; e < Ne; ++e) {
+        sum_kinFN += SEL(e, 5);
+        SP_kin += SEL(e, 6);
+        sum_opt += SEL(e, 0);
+        ee += SEL(e, 4);
+        loc += SEL(e, 3);
+      }
+      const double disc_bare = ee + S.v_ion_ion + sum_opt;
+      double sum_eFN = 0, SP_e = 0;
+      for (int k = 0; k < n_ecp; ++k) {
+        sum_eFN += s_p[(n_kin + k) * WPC + wl];
+        SP_e += s_j[k * WPC + wl];
+      }
+      nondiag = sum_kinFN + sum_eFN;
+      diag = S.ecp_flag ? diag_kin + disc_bare + loc + SP_kin + SP_e : diag_kin + disc_bare + SP_kin;
+      if (P.mode == 0) {
+        const double b_x = 1.0 / (diag - P.E_scf) * (-nondiag);
+        w_L *= b_x;
+        double tot = 0;
+        for (int k = 0; k < NPT; ++k) tot += s_p[k * WPC + wl];  // sequential fp64 sum in the reference's vector order
+        SMISC(13) = tot;
       }
     }
     if (P.mode != 0) break;
     __syncthreads();
-
-    // ---- P4: refresh the moved electron, Sherman-Morrison ---------------------------------------------------
-    const int es = (int)SMISC(12);
-    const double nx = SMISC(9), ny = SMISC(10), nz = SMISC(11);
-    {
-      SinkMO5<NMO> sink;
-      if (wid < nch) {
-        sink.init(es < N ? Bu.Cs : Bd.Cs);
-        eval_vgl<CART>(Bu, S.Rn, nx, ny, nz, P.chunk_begin[wid], P.chunk_begin[wid + 1], sink);
-      }
-      // deterministic reduction over chunks, one component at a time through a double buffer
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        double* buf = s_part + (size_t)(q & 1) * nch * NMO * 32;
-        if (wid < nch) {
-#pragma unroll
-          for (int mo = 0; mo < NMO; ++mo) buf[(wid * NMO + mo) * 32 + lane] = sink.acc[q][mo];
+    // (c) all threads: p / total
+    for (int s = tid; s < NPT * WPC; s += nthr) s_p[s] = s_p[s] / s_misc[13 * WPC + (s % WPC)];
+    __syncthreads();
+    // (d) per walker: sequential cumulative sum, first c >= u (searchsorted 'left', jqmc/jqmc_gfmc.py:5057-5062)
+    if (tid < WPC) {
+      const int wl = tid;
+      PosShared pos{s_r, WPC, wl};
+      const double u = P.ru[(size_t)it * P.nw + GW(wl)];
+      int ksel = NPT - 1;
+      double c = 0;
+      for (int k = 0; k < NPT; ++k) {
+        c += s_p[k * WPC + wl];
+        if (c >= u) {
+          ksel = k;
+          break;
         }
-        __syncthreads();
-        for (int mo = wid; mo < NMO; mo += NW) {
-          double s = 0;
-          for (int c = 0; c < nch; ++c) s += buf[(c * NMO + mo) * 32 + lane];
-          s_stage[(q * NMO + mo) * 32 + lane] = s;
+      }
+      double rt[9];
+#pragma unroll
+      for (int cc = 0; cc < 9; ++cc) rt[cc] = SMISC(cc);
+      int e;
+      double x, y, z, px, py, pz, dummy;
+      if (ksel < n_kin) {
+        e = ksel / 6;
+        const int s6 = ksel % 6, ax = s6 >> 1;
+        const double sg = (s6 & 1) ? -P.alat : P.alat;
+        pos.get(e, x, y, z);
+        px = x + sg * rt[3 * ax];
+        py = y + sg * rt[3 * ax + 1];
+        pz = z + sg * rt[3 * ax + 2];
+      } else {
+        const int pt = ksel - n_kin;
+        const int k = pt % S.Nv, nn = (pt / S.Nv) % S.NN;
+        e = pt / (S.Nv * S.NN);
+        pos.get(e, x, y, z);
+        ecp_point(S, rt, x, y, z, nn, k, px, py, pz, dummy, false);
+      }
+      SMISC(9) = px;
+      SMISC(10) = py;
+      SMISC(11) = pz;
+      SMISC(12) = (double)e;
+    }
+    __syncthreads();
+
+    // ---- P4: value/grad/lap of the moved electron: warp = basis chunks wid, wid+NWARP, ..., lane = walker --------------
+    {
+      const int* cbeg = (const int*)(tab + P.off_cbeg);
+      for (int wl = lane; wl < WPC; wl += 32) {
+        const int es = (int)SMISC(12);
+        SinkMO5<NMO> sink;
+        sink.init(tab + (es < N ? B.off_C : B.off_C2));
+        for (int c = wid; c < P.n_chunk; c += NWARP)
+          eval_vgl<CART, LMAX>(tab, B, P.off_cseg, SMISC(9), SMISC(10), SMISC(11), cbeg[c], cbeg[c + 1], sink);
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+          for (int mo = 0; mo < NMO; ++mo) s_part[((wid * 5 + q) * NMO + mo) * WPC + wl] = sink.acc[q][mo];
+      }
+    }
+    __syncthreads();
+    for (int s = tid; s < 5 * NMO * WPC; s += nthr) {  // fixed-order sum over the warps' partials
+      double sum = 0;
+      for (int c = 0; c < NWARP; ++c) sum += s_part[(size_t)c * 5 * NMO * WPC + s];
+      s_stage[s] = sum;
+    }
+    __syncthreads();
+    // Sherman-Morrison (jqmc/jqmc_gfmc.py:5083-5141): task = (walker, row i); read phase, barrier, write phase
+    {  // N * WPC <= blockDim.x is guaranteed by launch_walker: one pass
+      double newrow[16];
+      const int s = tid;
+      const bool act = s < N * WPC;
+      int wl = 0, i = 0;
+      if (act) {
+        wl = s % WPC;
+        i = s / WPC;
+        const int es = (int)SMISC(12);
+        double pn[NMO];
+#pragma unroll
+        for (int mo = 0; mo < NMO; ++mo) pn[mo] = s_stage[mo * WPC + wl] - SPHI(es, 0, mo);  // phi_new - phi_old
+        if (es < N) {
+          const int k = es;
+          double t[NMO], vvec[16];
+#pragma unroll
+          for (int b = 0; b < NMO; ++b) {
+            double sum = 0;
+#pragma unroll
+            for (int a = 0; a < NMO; ++a) sum = fma(pn[a], S.lam_p[a * NMO + b], sum);
+            t[b] = sum;
+          }
+          double acc = 0;
+          for (int j = 0; j < Nd; ++j) {
+            double sum = 0;
+#pragma unroll
+            for (int b = 0; b < NMO; ++b) sum = fma(t[b], SPHI(N + j, 0, b), sum);
+            vvec[j] = sum;
+            acc = fma(sum, SGI(j, k), acc);
+          }
+          for (int q = 0; q < S.n_unp; ++q) {
+            double sum = 0;
+#pragma unroll
+            for (int a = 0; a < NMO; ++a) sum = fma(pn[a], S.lam_u[a * S.n_unp + q], sum);
+            vvec[Nd + q] = sum;
+            acc = fma(sum, SGI(Nd + q, k), acc);
+          }
+          const double invD = 1.0 / (1.0 + acc);
+          const double coli = SGI(i, k);
+          for (int jp = 0; jp < N; ++jp) {
+            double vt = 0;
+            for (int j = 0; j < N; ++j) vt = fma(vvec[j], SGI(j, jp), vt);
+            newrow[jp] = SGI(i, jp) - (coli * vt) * invD;
+          }
+        } else {
+          const int k = es - N;
+          double t[NMO], uvec[16];
+#pragma unroll
+          for (int a = 0; a < NMO; ++a) {
+            double sum = 0;
+#pragma unroll
+            for (int b = 0; b < NMO; ++b) sum = fma(S.lam_p[a * NMO + b], pn[b], sum);
+            t[a] = sum;
+          }
+          for (int ii = 0; ii < N; ++ii) {
+            double sum = 0;
+#pragma unroll
+            for (int a = 0; a < NMO; ++a) sum = fma(SPHI(ii, 0, a), t[a], sum);
+            uvec[ii] = sum;
+          }
+          double au_i = 0, au_k = 0;
+          for (int j = 0; j < N; ++j) {
+            au_i = fma(SGI(i, j), uvec[j], au_i);
+            au_k = fma(SGI(k, j), uvec[j], au_k);
+          }
+          const double invD = 1.0 / (1.0 + au_k);
+          for (int j = 0; j < N; ++j) newrow[j] = SGI(i, j) - (au_i * SGI(k, j)) * invD;
         }
       }
       __syncthreads();
-    }
-    if (wid == 0) {
-      double pn[NMO], po[NMO];
-#pragma unroll
-      for (int mo = 0; mo < NMO; ++mo) {
-        const double s = s_stage[mo * 32 + lane];
-        pn[mo] = s - SPHI(es, 0, mo);  // phi_new - phi_old  (row/column DIFFERENCE is linear in it)
-        po[mo] = s;
-      }
-      if (es < N) {
-        const int k = es;
-        double t[NMO], vvec[16];
-#pragma unroll
-        for (int b = 0; b < NMO; ++b) {
-          double s = 0;
-#pragma unroll
-          for (int a = 0; a < NMO; ++a) s = fma(pn[a], S.lam_p[a * NMO + b], s);
-          t[b] = s;
-        }
-        double acc = 0;
-        for (int j = 0; j < Nd; ++j) {
-          double s = 0;
-#pragma unroll
-          for (int b = 0; b < NMO; ++b) s = fma(t[b], SPHI(N + j, 0, b), s);
-          vvec[j] = s;
-          acc = fma(s, SGI(j, k), acc);
-        }
-        for (int q = 0; q < S.n_unp; ++q) {
-          double s = 0;
-#pragma unroll
-          for (int a = 0; a < NMO; ++a) s = fma(pn[a], S.lam_u[a * S.n_unp + q], s);
-          vvec[Nd + q] = s;
-          acc = fma(s, SGI(Nd + q, k), acc);
-        }
-        const double invD = 1.0 / (1.0 + acc);
-        double col[16], vt[16];
-        for (int i = 0; i < N; ++i) col[i] = SGI(i, k);
-        for (int jp = 0; jp < N; ++jp) {
-          double s = 0;
-          for (int j = 0; j < N; ++j) s = fma(vvec[j], SGI(j, jp), s);
-          vt[jp] = s;
-        }
-        for (int i = 0; i < N; ++i)
-          for (int jp = 0; jp < N; ++jp) SGI(i, jp) = SGI(i, jp) - (col[i] * vt[jp]) * invD;
-      } else {
-        const int k = es - N;
-        double t[NMO], uvec[16];
-#pragma unroll
-        for (int a = 0; a < NMO; ++a) {
-          double s = 0;
-#pragma unroll
-          for (int b = 0; b < NMO; ++b) s = fma(S.lam_p[a * NMO + b], pn[b], s);
-          t[a] = s;
-        }
-        for (int i = 0; i < N; ++i) {
-          double s = 0;
-#pragma unroll
-          for (int a = 0; a < NMO; ++a) s = fma(SPHI(i, 0, a), t[a], s);
-          uvec[i] = s;
-        }
-        double au[16], row[16];
-        for (int i = 0; i < N; ++i) {
-          double s = 0;
-          for (int j = 0; j < N; ++j) s = fma(SGI(i, j), uvec[j], s);
-          au[i] = s;
-        }
-        const double invD = 1.0 / (1.0 + au[k]);
-        for (int j = 0; j < N; ++j) row[j] = SGI(k, j);
-        for (int i = 0; i < N; ++i)
-          for (int j = 0; j < N; ++j) SGI(i, j) = SGI(i, j) - (au[i] * row[j]) * invD;
-      }
-      SR(es, 0) = nx;
-      SR(es, 1) = ny;
-      SR(es, 2) = nz;
-      (void)po;
+      if (act)
+        for (int j = 0; j < N; ++j) SGI(i, j) = newrow[j];
     }
     __syncthreads();
-    for (int item = wid; item < 5 * NMO; item += NW) s_phi[(es * 5 * NMO + item) * 32 + lane] = s_stage[item * 32 + lane];
+    for (int s = tid; s < 5 * NMO * WPC; s += nthr) {
+      const int wl = s % WPC, item = s / WPC;
+      const int es = (int)SMISC(12);
+      s_phi[(es * 5 * NMO + item) * WPC + wl] = s_stage[s];
+    }
+    if (tid < WPC) {
+      const int wl = tid;
+      const int es = (int)SMISC(12);
+      SR(es, 0) = SMISC(9);
+      SR(es, 1) = SMISC(10);
+      SR(es, 2) = SMISC(11);
+    }
     __syncthreads();
   }
 
   // ---- write back -------------------------------------------------------------------------------------------
-  if (live && P.mode != 2) {
-    if (wid == 0) {
-      P.V_diag[w] = diag;
-      P.V_nondiag[w] = nondiag;
-      if (P.mode == 0) {
-        P.w[w] = w_L;
-        for (int c = 0; c < 9; ++c) P.RT_out[(size_t)w * 9 + c] = SMISC(c);
-      }
-    }
+  if (P.mode == 2) return;
+  if (tid < WPC && w0 + tid < P.nw) {
+    const int wl = tid, w = w0 + tid;
+    P.V_diag[w] = diag;
+    P.V_nondiag[w] = nondiag;
     if (P.mode == 0) {
-      for (int idx = wid; idx < Ne * 3; idx += NW) {
-        const int e = idx / 3, c = idx % 3;
-        if (e < N) P.r_up[((size_t)w * N + e) * 3 + c] = SR(e, c);
-        else P.r_dn[((size_t)w * Nd + (e - N)) * 3 + c] = SR(e, c);
-      }
-      for (int idx = wid; idx < NN2; idx += NW) P.Ginv[(size_t)w * NN2 + idx] = s_Gi[idx * 32 + lane];
+      P.w[w] = w_L;
+      for (int c = 0; c < 9; ++c) P.RT_out[(size_t)w * 9 + c] = SMISC(c);
     }
   }
+  if (P.mode == 0) {
+    for (int idx = tid; idx < Ne * 3 * WPC; idx += nthr) {
+      const int wl = idx % WPC, it = idx / WPC, e = it / 3, c = it % 3;
+      const int w = w0 + wl;
+      if (w >= P.nw) continue;
+      if (e < N) P.r_up[((size_t)w * N + e) * 3 + c] = s_r[idx];
+      else P.r_dn[((size_t)w * Nd + (e - N)) * 3 + c] = s_r[idx];
+    }
+    for (int idx = tid; idx < NN2 * WPC; idx += nthr) {
+      const int wl = idx % WPC, it = idx / WPC;
+      if (w0 + wl < P.nw) P.Ginv[(size_t)(w0 + wl) * NN2 + it] = s_Gi[idx];
+    }
+  }
+#undef SR
+#undef SGI
+#undef SPHI
+#undef SW
+#undef SEL
+#undef SMISC
+#undef GW
 }
 
 // key chain of the projection loop: two splits per projection (jqmc/jqmc_gfmc.py:5275-5283). thread = walker
@@ -633,32 +739,69 @@ __global__ void k_lrdmc_draws(int nw, int nmpm, int random_mesh, const uint2* __
   ru[t] = rng_uniform_bits(rng_bits64(Key{mk.x, mk.y}), 0.0, 1.0);
 }
 
+// walkers per CTA: fill the SMs (`slots` CTAs can be resident at once) with as few idle lanes as possible
+int choose_wpc(int nw, int n_points, int sms, int ctas_per_sm, int wpc_max, int nthr) {
+  int best = 1;
+  double best_score = -1.0;
+  for (int wpc = 1; wpc <= wpc_max; ++wpc) {
+    const int ctas = (nw + wpc - 1) / wpc;
+    const int slots = sms * ctas_per_sm;
+    const int waves = (ctas + slots - 1) / slots;
+    const double fill = (double)ctas / ((double)waves * slots);
+    const int pairs = (n_points * wpc + 1) / 2;
+    const int rounds = (pairs + nthr - 1) / nthr;
+    const double lanes = (double)pairs / ((double)rounds * nthr);
+    const double score = fill * lanes * (1.0 - 0.15 / wpc);  // mild preference for amortising the table staging
+    if (score > best_score) {
+      best_score = score;
+      best = wpc;
+    }
+  }
+  return best;
+}
+
+// One CTA of 16 warps per SM: the warps of an SM then run the same phase of the projection loop at the same time, which
+// keeps the instruction working set (one phase, not the whole loop) inside the instruction caches; four independent
+// 4-warp CTAs per SM were measured 5x stalled on instruction fetch (profiles/r01_*).
 int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
   const SysDev& S = h->sys;
   const int P = h->nmo_pad;
   if (S.n_up > 16) return fail(QE_ERR_UNSUPPORTED, "more than 16 electrons per spin is not implemented in this build");
-  const int nch = h->n_chunk_mc;
-  const int NW = 16;
-  A.chunk_begin = h->d_chunk_mc;
-  A.n_chunk = nch;
+  const int NWARP = 16;
+  A.off_cseg = h->b_up.off_cseg;
+  A.off_cbeg = h->b_up.off_cbeg;
+  A.n_chunk = h->b_up.n_chunk;
   const int Ne = S.n_e;
   const int n_kin = A.mode == 2 ? 0 : 6 * Ne;
   const int n_ecp = S.ecp_flag ? Ne * S.NN * S.Nv : 0;
-  size_t per_lane = (size_t)Ne * 3 + (size_t)S.n_up * S.n_up + (size_t)Ne * 5 * P + (size_t)Ne * P + std::max(1, n_kin + n_ecp) +
-                    std::max(1, n_ecp) + (size_t)Ne * 5 + (size_t)2 * nch * P + 5 * P + 16;
-  size_t smem = table_bytes(h->b_up.dev, S, P) + (h->b_dn.dev.Cs != h->b_up.dev.Cs ? (size_t)h->b_dn.dev.n_ao * P * 8 + 16 : 0) +
-                per_lane * 32 * 8 + 16 * 12;
-  if (smem > 227 * 1024) return fail(QE_ERR_UNSUPPORTED, "system too large for the fused walker kernel (shared memory)");
-  dim3 block(32, NW);
+  const size_t per_walker = (size_t)Ne * 3 + (size_t)S.n_up * S.n_up + (size_t)Ne * 5 * P + (size_t)Ne * P + std::max(1, n_kin + n_ecp) +
+                            std::max(1, n_ecp) + (size_t)Ne * 8 + (size_t)NWARP * 5 * P + 5 * P + 16;
+  const size_t fixed = (size_t)h->b_up.dev.bytes + sys_bytes(S, P) + 14 * 16 + 64;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t budget = 227 * 1024;
+  if (budget < fixed + per_walker * 8) return fail(QE_ERR_UNSUPPORTED, "system too large for the fused walker kernel (shared memory)");
+  int wpc_max = (int)std::min<size_t>(32, (budget - fixed) / (per_walker * 8));
+  wpc_max = std::max(1, std::min(wpc_max, NWARP * 32 / S.n_up));  // Sherman-Morrison: one (walker, row) task per thread
+  A.wpc = h->wpc_override > 0 ? std::min(h->wpc_override, wpc_max)
+                              : choose_wpc(A.nw, std::max(1, n_kin + n_ecp), sms, 1, wpc_max, NWARP * 32);
+  const size_t smem = fixed + per_walker * 8 * A.wpc;
   {
     LaunchScope ls_(h, kid, st);
-#define CALL(NMO, CART)                                                                                        \
-  do {                                                                                                         \
-    CUDA_TRY(cudaFuncSetAttribute(k_walker<NMO, CART>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_walker<NMO, CART><<<nblk(A.nw, 32), block, smem, st>>>(h->b_up.dev, h->b_dn.dev, S, A);                  \
+#define CALL2(NMO, CART, LMAX)                                                                                         \
+  do {                                                                                                                 \
+    CUDA_TRY(cudaFuncSetAttribute(k_walker<NMO, CART, LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_walker<NMO, CART, LMAX><<<nblk(A.nw, A.wpc), NWARP * 32, smem, st>>>(h->b_up.dev, S, A);                          \
+  } while (0)
+#define CALL(NMO, CART)                                  \
+  do {                                                   \
+    if (h->b_up.dev.lmax <= 4) CALL2(NMO, CART, 4);      \
+    else CALL2(NMO, CART, 6);                            \
   } while (0)
     DISPATCH_NMO_CART(h, CALL);
 #undef CALL
+#undef CALL2
   }
   CHECK_LAUNCH();
   return QE_OK;
@@ -747,4 +890,10 @@ int qe_local_energy_fused(qe_engine* h, int nw, const double* r_up, const double
   A.T_elem = T_elem;
   A.V_parts = V_parts;
   return launch_walker(h, A, st, K_EL_FUSED);
+}
+
+extern "C" int qe_set_walkers_per_cta(qe_engine* h, int wpc) {
+  if (!h || wpc < 0 || wpc > 32) return fail(QE_ERR_INVALID, "qe_set_walkers_per_cta: wpc must be 0 (automatic) .. 32");
+  h->wpc_override = wpc;
+  return QE_OK;
 }

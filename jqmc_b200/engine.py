@@ -334,6 +334,10 @@ class WalkerEngine:
         """Fused (one kernel, shared-memory resident) vs staged (kernel chain) local energy; same results."""
         _lib.check(self._lib.qe_set_fused(self._h, 1 if on else 0), "qe_set_fused")
 
+    def set_walkers_per_cta(self, wpc: int):
+        """Walkers per CTA of the fused walker kernel (0 = automatic)."""
+        _lib.check(self._lib.qe_set_walkers_per_cta(self._h, int(wpc)), "qe_set_walkers_per_cta")
+
     # ---- LRDMC (GFMC_n) seams: jqmc/jqmc_gfmc.py:4716, 5656-5663 ------------------------------------
     _NLM = {"tmove": 0, "dltmove": 1}
 
