@@ -167,6 +167,14 @@ int qe_gather_walkers(qe_engine* h, int nw, const int32_t* chosen_local, const d
  * `on` != 0 (default); otherwise as a chain of staged kernels through a global workspace.  Same results. */
 int qe_set_fused(qe_engine* h, int on);
 
+/* Kernel family.  0 (default): automatic -- the register/shared-memory kernels when they cover the system (MO-basis
+ * geminal with <= 16 orbitals, <= 8 electrons per spin, J1 + J2), otherwise the general path (AO-basis JAGP geminals, any
+ * orbital count, <= 112 electrons per spin, three-body Jastrow; contractions on the fp64 tensor cores).  1: always the
+ * general path.  Same results to round-off; bit-identical accept/reject and branching decisions are asserted in tests. */
+int qe_set_path(qe_engine* h, int path);
+/* Debugging aid: nonzero replaces the tensor-core GEMM of the general path by a plain DFMA kernel (process-wide). */
+int qe_set_gemm_reference(int on);
+
 /* Walkers per CTA of the fused walker kernel: 0 = chosen automatically so that the grid fills the SMs (default),
  * 1..32 = fixed (tuning / tests; results do not depend on it beyond round-off of partial-sum order). */
 int qe_set_walkers_per_cta(qe_engine* h, int wpc);

@@ -83,8 +83,27 @@ struct SysDev {
   double v_ion_ion;
 };
 
+// Tables of the general ("wide") path (qe_wide.cu): arbitrary orbital counts (AO-basis geminals, many MOs), any number
+// of electrons, three-body Jastrow.  All matrices are row-major device arrays; "row" = canonical AO row of the basis
+// image (row_ao / row_scale of qe_device.cuh), the per-AO scale is folded into every matrix that touches row space.
+struct WideTabs {
+  bool present = false;
+  int no = 0, n_row = 0, has_mo = 0, restricted = 1;
+  const double *CwT_up = nullptr, *CwT_dn = nullptr;  // [no][n_row]   orbital <- AO rows
+  const double *Cw_up = nullptr, *Cw_dn = nullptr;    // [n_row][no]   AO-row weights <- orbital weights
+  const double *lamP = nullptr, *lamPT = nullptr;     // [no][no]      paired block of lambda and its transpose
+  const double* lamU = nullptr;                       // [no][n_unp]
+  int j3 = 0, nj = 0, nj_row = 0, j3_mo = 0;
+  const double *CjT = nullptr, *Cj = nullptr;         // [nj][nj_row], [nj_row][nj]
+  const double *Mj = nullptr, *MjT = nullptr;         // [nj][nj]
+  const double* j1v = nullptr;                        // [nj]
+};
+
 struct qe_engine {
   DevPool pool;
+  WideTabs wt;
+  bool narrow_ok = true;  // the register/shared-memory kernels (qe_mcmc.cu, qe_walker.cu) cover this system
+  int path = 0;           // 0: automatic (narrow when it covers the system), 1: always the wide path
   HostBasis b_up, b_j3;  // b_up carries both spins' MO coefficient tables (the AO tables are shared: checked at create)
   SysDev sys{};
   int nmo_pad = 4;
@@ -103,11 +122,14 @@ struct qe_engine {
 };
 
 enum KernelId { K_ORB_EL = 0, K_GEMINAL, K_ALGEBRA, K_ECP_MESH, K_REDUCE, K_RATIOS, K_AS, K_ROT, K_KEYCHAIN, K_DRAWS, K_MCMC,
-                K_EVAL, K_LRDMC, K_EL_FUSED, K_LRDMC_PROJ, K_COLLECT, K_BRANCH, K_GATHER, K_COUNT };
+                K_EVAL, K_LRDMC, K_EL_FUSED, K_LRDMC_PROJ, K_COLLECT, K_BRANCH, K_GATHER,
+                K_W_AO, K_W_GEMM, K_W_BMM, K_W_INV, K_W_MESH, K_W_ELEC, K_W_SELECT, K_W_COMMIT, K_W_DECIDE, K_W_MISC, K_COUNT };
 static const char* const KERNEL_NAMES[K_COUNT] = {"k_orb_electrons", "k_geminal", "k_electron_algebra", "k_ecp_mesh", "k_reduce_eL",
                                                   "k_move_ratios", "k_as_factor", "k_rotation", "k_mcmc_keychain", "k_mcmc_draws",
                                                   "k_mcmc", "k_eval_orbitals", "k_walker(V_elements)", "k_walker(e_L)", "k_walker(projection)", "k_lrdmc_collect",
-                                                  "k_branch", "k_gather_walkers"};
+                                                  "k_branch", "k_gather_walkers",
+                                                  "kw_ao_store", "kw_dgemm(DMMA)", "kw_bmm", "kw_inverse", "kw_mesh", "kw_electron",
+                                                  "kw_lrdmc_select", "kw_lrdmc_commit", "kw_mc_decide", "kw_misc"};
 struct LaunchScope {
   qe_engine* h;
   cudaStream_t st;
@@ -212,6 +234,37 @@ __device__ __forceinline__ double legendre_l(int l, double x) {
   }
 }
 
+
+// ECP mesh point (e, nn, k): position, and the channel-summed angular factor  sum_l V_l(d)(2l+1)P_l(cos) * w_k
+// (jqmc/coulomb_potential.py:1562-1575, 1607-1645)
+__device__ __forceinline__ void ecp_point(const SysDev& S, const double* rt, double x, double y, double z, int nn, int k,
+                                          double& px, double& py, double& pz, double& ang_w, bool want_ang) {
+  double d;
+  const int a = nearest_atom(S.Rn, S.n_atom, x, y, z, nn, &d);
+  const double relx = S.Rn[3 * a] - x, rely = S.Rn[3 * a + 1] - y, relz = S.Rn[3 * a + 2] - z;
+  d = sqrt(relx * relx + rely * rely + relz * relz);
+  const double q0 = S.quad_g[3 * k], q1 = S.quad_g[3 * k + 1], q2 = S.quad_g[3 * k + 2];
+  const double gx = q0 * rt[0] + q1 * rt[3] + q2 * rt[6];
+  const double gy = q0 * rt[1] + q1 * rt[4] + q2 * rt[7];
+  const double gz = q0 * rt[2] + q1 * rt[5] + q2 * rt[8];
+  px = x + relx + d * gx;
+  py = y + rely + d * gy;
+  pz = z + relz + d * gz;
+  ang_w = 0.0;
+  if (!want_ang) return;
+  const double gn = sqrt(gx * gx + gy * gy + gz * gz);
+  const double cos_t = (-relx / d) * (gx / gn) + (-rely / d) * (gy / gn) + (-relz / d) * (gz / gn);
+  const int lloc = S.ecp_lmax_atom[a];
+  double ang = 0.0;
+  for (int l = 0; l < lloc; ++l) {
+    double vl = 0.0;
+    for (int kk = S.ecp_off[a]; kk < S.ecp_off[a + 1]; ++kk)
+      if (S.ecp_l[kk] == l) vl += S.ecp_c[kk] * ipow(d, S.ecp_p[kk]) * qexp(-S.ecp_z[kk] * d * d);
+    ang = fma(vl / (d * d) * (2 * l + 1), legendre_l(l, cos_t), ang);
+  }
+  ang_w = ang * S.quad_w[k];
+}
+
 // electron position accessors: global AoS arrays r_up[nw][n_up][3], r_dn[nw][n_dn][3]
 struct PosGlobal {
   const double* __restrict__ up;
@@ -302,6 +355,29 @@ static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1
     if (e_ != cudaSuccess) return fail(QE_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
   } while (0)
 
+
+// ---- cross-TU entry points -----------------------------------------------------------------------------------------
+static inline bool use_wide(const qe_engine* h) { return h->path == 1 || !h->narrow_ok; }
+struct WsCarve;
+// RNG tables of one qe_mcmc_update call (qe_mcmc.cu) / one qe_lrdmc_project call (qe_walker.cu), carved from `c`
+size_t mcmc_draws_bytes(int nw, int nmpm);
+int mcmc_draws(qe_engine* h, int nw, int nmpm, uint32_t* keys, WsCarve& c, int** rsel, int** raxis, double** rg, double** rb,
+               cudaStream_t st);
+size_t lrdmc_draws_bytes(int nw, int nmpm);
+int lrdmc_draws(qe_engine* h, int nw, int nmpm, int random_mesh, uint32_t* keys, WsCarve& c, double** rRT, double** ru, cudaStream_t st);
+// general path (qe_wide.cu)
+int wide_geminal_init(qe_engine* h, int nw, const double* r_up, const double* r_dn, double* G, double* Ginv, double* ln_psi,
+                      double* sign, cudaStream_t st);
+int wide_local_energy(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,
+                      double* e_L, double* T_elem, double* V_parts, cudaStream_t st);
+int wide_move_ratios(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* Ginv, int n_moves,
+                     const int32_t* elec_host, const double* r_new, double* det_ratio, double* jas_ratio, cudaStream_t st);
+int wide_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, uint32_t* keys, double* G, double* Ginv, int nmpm, double Dt,
+                     double epsilon_AS, int32_t* acc, int32_t* rej, cudaStream_t st);
+int wide_lrdmc(qe_engine* h, int mode, int nw, double* w, double* r_up, double* r_dn, double* Ginv, uint32_t* keys, double E_scf,
+               int nmpm, int random_mesh, int non_local_move, double alat, const double* RT_in, double* RT_out, double* V_diag,
+               double* V_nondiag, cudaStream_t st);
+int wide_eval_orbitals(qe_engine* h, int which, int n_pts, const double* r, double* out, cudaStream_t st);
 
 // workspace carve-up helper
 struct WsCarve {

@@ -110,7 +110,7 @@ static void make_chunks(const std::vector<int4>& grp, const std::vector<double>&
 
 // d2: second coefficient set sharing the AO tables (down-spin MOs), or nullptr
 static int build_basis(const qe_basis_desc& d, const qe_basis_desc* d2, int n_atom, const double* positions, int nmo_pad, int n_chunk_target,
-                       DevPool& pool, HostBasis& hb) {
+                       DevPool& pool, HostBasis& hb, bool with_C, std::vector<int>& row_ao, std::vector<double>& row_scale) {
   if (d.n_ao <= 0) return fail(QE_ERR_INVALID, "basis: n_ao must be positive");
   const bool cart = d.cartesian != 0;
   std::vector<std::vector<int>> prims(d.n_ao);
@@ -181,8 +181,9 @@ static int build_basis(const qe_basis_desc& d, const qe_basis_desc* d2, int n_at
   });
   std::vector<int4> grp, sh;
   std::vector<double2> pr;
-  std::vector<int> row_ao;
-  std::vector<double> row_scale, sh_cost, grp_overhead;
+  row_ao.clear();
+  row_scale.clear();
+  std::vector<double> sh_cost, grp_overhead;
   for (size_t s = 0; s < shells.size(); ++s) {
     const TmpShell& t = shells[s];
     const int l = t.l;
@@ -245,7 +246,7 @@ static int build_basis(const qe_basis_desc& d, const qe_basis_desc* d2, int n_at
   B.off_sh = blob.put(sh);
   B.off_pr = blob.put(pr);
   B.off_C = B.off_C2 = 0;
-  if (d.n_mo > 0) {
+  if (d.n_mo > 0 && with_C) {
     const std::vector<double> Cu = c_table(d);
     B.off_C = blob.put(Cu);
     B.off_C2 = B.off_C;
@@ -819,25 +820,143 @@ extern "C" void qe_destroy(qe_engine* h) {
   delete h;
 }
 
+// Tables of the general path (qe_wide.cu).  Orbital space = MOs when the geminal / J3 orbitals carry an MO layer, else the
+// canonical AO rows of the basis image (per-AO scale folded into lambda / j_matrix; rows a shell does not own are zero).
+static int build_wide_tables(const qe_system_desc* d, qe_engine* h, const std::vector<int>& row_ao, const std::vector<double>& row_scale,
+                             const std::vector<int>& rowj_ao, const std::vector<double>& rowj_scale) {
+  WideTabs& T = h->wt;
+  const int n_row = (int)row_ao.size();
+  const int n_unp = d->n_up - d->n_dn;
+  T.n_row = n_row;
+  T.has_mo = d->orb_up.n_mo > 0;
+  T.no = T.has_mo ? d->orb_up.n_mo : n_row;
+  const int no = T.no;
+  const int n_orb_ref = T.has_mo ? d->orb_up.n_mo : d->orb_up.n_ao;  // orbital count of the reference's lambda
+  const int lam_cols = n_orb_ref + n_unp;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](const std::vector<double>& v, const double** out) {
+    if (e == cudaSuccess) e = h->pool.upload(v, out);
+  };
+  std::vector<double> lamP((size_t)no * no, 0.0), lamPT((size_t)no * no, 0.0), lamU((size_t)no * std::max(1, n_unp), 0.0);
+  if (T.has_mo) {
+    auto tables = [&](const qe_basis_desc& q, std::vector<double>& CT, std::vector<double>& C) {
+      CT.assign((size_t)no * n_row, 0.0);
+      C.assign((size_t)n_row * no, 0.0);
+      for (int r = 0; r < n_row; ++r) {
+        const int a = row_ao[r];
+        if (a < 0) continue;
+        for (int o = 0; o < no; ++o) {
+          const double v = q.mo_coefficients[(size_t)o * q.n_ao + a] * row_scale[r];
+          CT[(size_t)o * n_row + r] = v;
+          C[(size_t)r * no + o] = v;
+        }
+      }
+    };
+    std::vector<double> CTu, Cu, CTd, Cd;
+    tables(d->orb_up, CTu, Cu);
+    tables(d->orb_dn, CTd, Cd);
+    T.restricted = CTu == CTd;
+    up(CTu, &T.CwT_up);
+    up(Cu, &T.Cw_up);
+    if (T.restricted) {
+      T.CwT_dn = T.CwT_up;
+      T.Cw_dn = T.Cw_up;
+    } else {
+      up(CTd, &T.CwT_dn);
+      up(Cd, &T.Cw_dn);
+    }
+    for (int a = 0; a < no; ++a) {
+      for (int b = 0; b < no; ++b) lamP[(size_t)a * no + b] = d->lambda_matrix[(size_t)a * lam_cols + b];
+      for (int k = 0; k < n_unp; ++k) lamU[(size_t)a * n_unp + k] = d->lambda_matrix[(size_t)a * lam_cols + n_orb_ref + k];
+    }
+  } else {
+    T.restricted = 1;
+    for (int r = 0; r < n_row; ++r) {
+      const int a = row_ao[r];
+      if (a < 0) continue;
+      for (int r2 = 0; r2 < n_row; ++r2) {
+        const int b = row_ao[r2];
+        if (b >= 0) lamP[(size_t)r * no + r2] = row_scale[r] * d->lambda_matrix[(size_t)a * lam_cols + b] * row_scale[r2];
+      }
+      for (int k = 0; k < n_unp; ++k) lamU[(size_t)r * n_unp + k] = row_scale[r] * d->lambda_matrix[(size_t)a * lam_cols + n_orb_ref + k];
+    }
+  }
+  for (int a = 0; a < no; ++a)
+    for (int b = 0; b < no; ++b) lamPT[(size_t)b * no + a] = lamP[(size_t)a * no + b];
+  up(lamP, &T.lamP);
+  up(lamPT, &T.lamPT);
+  up(lamU, &T.lamU);
+  T.j3 = d->j3_flag ? 1 : 0;
+  if (T.j3) {
+    const int nj_row = (int)rowj_ao.size();
+    T.nj_row = nj_row;
+    T.j3_mo = d->j3_orb.n_mo > 0;
+    T.nj = T.j3_mo ? d->j3_orb.n_mo : nj_row;
+    const int nj = T.nj, nj_ref = T.j3_mo ? d->j3_orb.n_mo : d->j3_orb.n_ao;
+    std::vector<double> Mj((size_t)nj * nj, 0.0), MjT((size_t)nj * nj, 0.0), j1v(nj, 0.0);
+    if (T.j3_mo) {
+      std::vector<double> CT((size_t)nj * nj_row, 0.0), C((size_t)nj_row * nj, 0.0);
+      for (int r = 0; r < nj_row; ++r) {
+        const int a = rowj_ao[r];
+        if (a < 0) continue;
+        for (int o = 0; o < nj; ++o) {
+          const double v = d->j3_orb.mo_coefficients[(size_t)o * d->j3_orb.n_ao + a] * rowj_scale[r];
+          CT[(size_t)o * nj_row + r] = v;
+          C[(size_t)r * nj + o] = v;
+        }
+      }
+      up(CT, &T.CjT);
+      up(C, &T.Cj);
+      for (int a = 0; a < nj; ++a) {
+        for (int b = 0; b < nj; ++b) Mj[(size_t)a * nj + b] = d->j_matrix[(size_t)a * (nj_ref + 1) + b];
+        j1v[a] = d->j_matrix[(size_t)a * (nj_ref + 1) + nj_ref];
+      }
+    } else {
+      for (int r = 0; r < nj_row; ++r) {
+        const int a = rowj_ao[r];
+        if (a < 0) continue;
+        for (int r2 = 0; r2 < nj_row; ++r2) {
+          const int b = rowj_ao[r2];
+          if (b >= 0) Mj[(size_t)r * nj + r2] = rowj_scale[r] * d->j_matrix[(size_t)a * (nj_ref + 1) + b] * rowj_scale[r2];
+        }
+        j1v[r] = rowj_scale[r] * d->j_matrix[(size_t)a * (nj_ref + 1) + nj_ref];
+      }
+    }
+    for (int a = 0; a < nj; ++a)
+      for (int b = 0; b < nj; ++b) MjT[(size_t)b * nj + a] = Mj[(size_t)a * nj + b];
+    up(Mj, &T.Mj);
+    up(MjT, &T.MjT);
+    up(j1v, &T.j1v);
+  }
+  if (e != cudaSuccess) return fail(QE_ERR_CUDA, std::string("wide tables upload: ") + cudaGetErrorString(e));
+  T.present = true;
+  return QE_OK;
+}
+
 extern "C" int qe_create(const qe_system_desc* d, qe_engine** out) {
   if (!d || !out) return fail(QE_ERR_INVALID, "qe_create: null argument");
   *out = nullptr;
   if (d->n_atom <= 0 || d->n_up <= 0 || d->n_dn < 0 || d->n_dn > d->n_up)
     return fail(QE_ERR_INVALID, "qe_create: need n_atom > 0 and n_up >= n_dn >= 0, n_up > 0");
-  if (d->j3_flag) return fail(QE_ERR_UNSUPPORTED, "three-body Jastrow is not implemented in this build");
-  if (d->orb_up.n_mo <= 0 || d->orb_dn.n_mo <= 0)
-    return fail(QE_ERR_UNSUPPORTED, "AO-basis geminals (JAGP) are not implemented in this build; use the MO representation");
-  if (d->orb_up.n_mo != d->orb_dn.n_mo) return fail(QE_ERR_INVALID, "orb_num_up != orb_num_dn");
-  if (d->orb_up.n_mo > 16) return fail(QE_ERR_UNSUPPORTED, "more than 16 molecular orbitals per spin is not implemented in this build");
-  if (d->n_up > 16) return fail(QE_ERR_UNSUPPORTED, "more than 16 electrons per spin is not implemented in this build");
+  if ((d->orb_up.n_mo > 0) != (d->orb_dn.n_mo > 0)) return fail(QE_ERR_INVALID, "up/dn orbitals must both be MOs or both be AOs");
+  if ((d->orb_up.n_mo > 0 ? d->orb_up.n_mo : d->orb_up.n_ao) != (d->orb_dn.n_mo > 0 ? d->orb_dn.n_mo : d->orb_dn.n_ao))
+    return fail(QE_ERR_INVALID, "orb_num_up != orb_num_dn");
+  if (d->n_up > 112) return fail(QE_ERR_UNSUPPORTED, "more than 112 electrons per spin is not implemented in this build");
   if (d->ecp_flag && !(d->Nv == 4 || d->Nv == 6 || d->Nv == 12 || d->Nv == 18)) return fail(QE_ERR_INVALID, "Nv must be 4, 6, 12 or 18");
   if (d->ecp_flag && (d->NN < 1 || d->NN > d->n_atom)) return fail(QE_ERR_INVALID, "NN must be in 1..n_atom");
   if (!same_ao_tables(d->orb_up, d->orb_dn)) return fail(QE_ERR_UNSUPPORTED, "up/dn orbitals must share the same AO tables");
 
   qe_engine* h = new qe_engine();
   const int n_mo = d->orb_up.n_mo;
+  // the register / shared-memory kernels cover MO-basis geminals with <= 16 orbitals, <= 8 electrons per spin, J1 + J2
+  h->narrow_ok = !d->j3_flag && n_mo > 0 && n_mo <= 16 && d->n_up <= 8;
   h->nmo_pad = n_mo <= 4 ? 4 : (n_mo <= 8 ? 8 : 16);
-  int rc = build_basis(d->orb_up, &d->orb_dn, d->n_atom, d->positions, h->nmo_pad, QE_N_CHUNK, h->pool, h->b_up);
+  std::vector<int> row_ao, rowj_ao;
+  std::vector<double> row_scale, rowj_scale;
+  int rc = build_basis(d->orb_up, &d->orb_dn, d->n_atom, d->positions, h->nmo_pad, QE_N_CHUNK, h->pool, h->b_up, h->narrow_ok, row_ao, row_scale);
+  if (rc == QE_OK && d->j3_flag)
+    rc = build_basis(d->j3_orb, nullptr, d->n_atom, d->positions, 4, QE_N_CHUNK, h->pool, h->b_j3, false, rowj_ao, rowj_scale);
+  if (rc == QE_OK) rc = build_wide_tables(d, h, row_ao, row_scale, rowj_ao, rowj_scale);
   if (rc != QE_OK) {
     qe_destroy(h);
     return rc;
@@ -852,7 +971,7 @@ extern "C" int qe_create(const qe_system_desc* d, qe_engine** out) {
   const int P = h->nmo_pad;
   const int lam_cols = n_mo + S.n_unp;
   std::vector<double> lam_p((size_t)P * P, 0.0), lam_u((size_t)P * std::max(1, S.n_unp), 0.0);
-  for (int a = 0; a < n_mo; ++a) {
+  for (int a = 0; h->narrow_ok && a < n_mo; ++a) {
     for (int b = 0; b < n_mo; ++b) lam_p[(size_t)a * P + b] = d->lambda_matrix[(size_t)a * lam_cols + b];
     for (int k = 0; k < S.n_unp; ++k) lam_u[(size_t)a * S.n_unp + k] = d->lambda_matrix[(size_t)a * lam_cols + n_mo + k];
   }
@@ -927,6 +1046,11 @@ extern "C" int qe_create(const qe_system_desc* d, qe_engine** out) {
 }
 
 extern "C" int64_t qe_launch_count(qe_engine* h) { return h ? h->launches : 0; }
+extern "C" int qe_set_path(qe_engine* h, int path) {
+  if (!h || (path != 0 && path != 1)) return fail(QE_ERR_INVALID, "qe_set_path: path must be 0 (automatic) or 1 (general path)");
+  h->path = path;
+  return QE_OK;
+}
 extern "C" int qe_set_fused(qe_engine* h, int on) {
   if (!h) return fail(QE_ERR_INVALID, "qe_set_fused: null engine");
   h->fused = on != 0;
@@ -971,6 +1095,7 @@ extern "C" int qe_eval_orbitals(qe_engine* h, int which, int layer, int n_pts, c
   if (which < 0 || which > 2 || !hb->present) return fail(QE_ERR_INVALID, "qe_eval_orbitals: basis not present");
   cudaStream_t st = (cudaStream_t)stream;
   const BasisDev& B = hb->dev;
+  if (layer != 0 && B.n_mo > 0 && (which == 2 || !h->narrow_ok)) return wide_eval_orbitals(h, which, n_pts, r, out, st);
   { LaunchScope ls_(h, K_EVAL, st);
   if (layer == 0 || B.n_mo == 0) {
     if (B.cart) k_eval_ao<true><<<nblk(n_pts, 128), 128, 0, st>>>(B, n_pts, r, out);
@@ -1003,6 +1128,7 @@ extern "C" int qe_geminal_init(qe_engine* h, int nw, const double* r_up, const d
                                void* stream) {
   if (!h || nw <= 0 || !r_up || (!r_dn && h->sys.n_dn > 0)) return fail(QE_ERR_INVALID, "qe_geminal_init: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_wide(h)) return wide_geminal_init(h, nw, r_up, r_dn, G, Ginv, nullptr, nullptr, st);
   const SysDev& S = h->sys;
   int rc;
   double* phi;
@@ -1032,6 +1158,7 @@ extern "C" int qe_ln_wavefunction(qe_engine* h, int nw, const double* r_up, cons
                                   void* stream) {
   if (!h || nw <= 0 || !r_up || !ln_psi) return fail(QE_ERR_INVALID, "qe_ln_wavefunction: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_wide(h)) return wide_geminal_init(h, nw, r_up, r_dn, nullptr, nullptr, ln_psi, sign, st);
   const SysDev& S = h->sys;
   int rc = ensure_ws(h, ws_need_common(h, nw, h->b_up.n_chunk, 1));
   if (rc) return rc;
@@ -1069,6 +1196,7 @@ extern "C" int qe_local_energy(qe_engine* h, int nw, const double* r_up, const d
   if (!h || nw <= 0 || !r_up || !Ginv || !e_L || (!r_dn && h->sys.n_dn > 0)) return fail(QE_ERR_INVALID, "qe_local_energy: bad argument");
   if (h->sys.ecp_flag && !RT) return fail(QE_ERR_INVALID, "qe_local_energy: RT required for ECP systems");
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_wide(h)) return wide_local_energy(h, nw, r_up, r_dn, RT, Ginv, e_L, T_elem, V_parts, st);
   const SysDev& S = h->sys;
   if (h->fused) {
     const int frc = qe_local_energy_fused(h, nw, r_up, r_dn, RT, Ginv, e_L, T_elem, V_parts, st);
@@ -1124,6 +1252,7 @@ extern "C" int qe_move_ratios(qe_engine* h, int nw, const double* r_up, const do
   const SysDev& S = h->sys;
   for (int i = 0; i < n_moves; ++i)
     if (elec_host[i] < 0 || elec_host[i] >= S.n_e) return fail(QE_ERR_INVALID, "qe_move_ratios: electron index out of range");
+  if (use_wide(h)) return wide_move_ratios(h, nw, r_up, r_dn, Ginv, n_moves, elec_host, r_new, det_ratio, jas_ratio, st);
   const int nch = h->b_up.n_chunk, P = h->nmo_pad;
   int rc = ensure_ws(h, ws_need_common(h, nw, nch, 1) + (size_t)n_moves * 4 + 256);
   if (rc) return rc;

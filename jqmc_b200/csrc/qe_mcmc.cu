@@ -400,33 +400,47 @@ extern "C" int qe_rotation(qe_engine* h, int nw, const uint32_t* keys, double* R
 }
 
 
-extern "C" int qe_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, uint32_t* keys, double* G, double* Ginv, int nmpm,
-                              double Dt, double epsilon_AS, int32_t* acc, int32_t* rej, void* stream) {
-  if (!h || nw <= 0 || nmpm < 0 || !r_up || !keys || !G || !Ginv || !acc || !rej || (!r_dn && h->sys.n_dn > 0))
-    return fail(QE_ERR_INVALID, "qe_mcmc_update: bad argument");
-  const SysDev& S = h->sys;
-  if (S.n_up > 8) return fail(QE_ERR_UNSUPPORTED, "qe_mcmc_update: more than 8 electrons per spin is not implemented in this build");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int P = h->nmo_pad, nch = h->b_up.n_chunk;
+size_t mcmc_draws_bytes(int nw, int nmpm) {
   const size_t n_draw = (size_t)std::max(1, nmpm) * nw;
-  int rc = ensure_ws(h, n_draw * (6 * 8 + 4 + 4 + 8 + 8) + 4096);
-  if (rc) return rc;
-  WsCarve c{(char*)h->ws};
+  return n_draw * (6 * 8 + 4 + 4 + 8 + 8) + 6 * 256;
+}
+int mcmc_draws(qe_engine* h, int nw, int nmpm, uint32_t* keys, WsCarve& c, int** rsel, int** raxis, double** rg, double** rb,
+               cudaStream_t st) {
+  const SysDev& S = h->sys;
+  const size_t n_draw = (size_t)std::max(1, nmpm) * nw;
   uint2* sub = c.take<uint2>(n_draw * 6);
-  int* rsel = c.take<int>(n_draw);
-  int* raxis = c.take<int>(n_draw);
-  double* rg = c.take<double>(n_draw);
-  double* rb = c.take<double>(n_draw);
+  *rsel = c.take<int>(n_draw);
+  *raxis = c.take<int>(n_draw);
+  *rg = c.take<double>(n_draw);
+  *rb = c.take<double>(n_draw);
   if (nmpm > 0) {
     { LaunchScope ls_(h, K_KEYCHAIN, st);
     k_mcmc_keychain<<<nblk(nw, 64), 64, 0, st>>>(nw, nmpm, keys, sub);
     }
     CHECK_LAUNCH();
     { LaunchScope ls_(h, K_DRAWS, st);
-    k_mcmc_draws<<<nblk((long long)nmpm * nw, 128), 128, 0, st>>>(nw, nmpm, S.n_up, S.n_dn, sub, rsel, raxis, rg, rb);
+    k_mcmc_draws<<<nblk((long long)nmpm * nw, 128), 128, 0, st>>>(nw, nmpm, S.n_up, S.n_dn, sub, *rsel, *raxis, *rg, *rb);
     }
     CHECK_LAUNCH();
   }
+  return QE_OK;
+}
+
+extern "C" int qe_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, uint32_t* keys, double* G, double* Ginv, int nmpm,
+                              double Dt, double epsilon_AS, int32_t* acc, int32_t* rej, void* stream) {
+  if (!h || nw <= 0 || nmpm < 0 || !r_up || !keys || !G || !Ginv || !acc || !rej || (!r_dn && h->sys.n_dn > 0))
+    return fail(QE_ERR_INVALID, "qe_mcmc_update: bad argument");
+  const SysDev& S = h->sys;
+  if (use_wide(h)) return wide_mcmc_update(h, nw, r_up, r_dn, keys, G, Ginv, nmpm, Dt, epsilon_AS, acc, rej, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = h->nmo_pad, nch = h->b_up.n_chunk;
+  int rc = ensure_ws(h, mcmc_draws_bytes(nw, nmpm) + 4096);
+  if (rc) return rc;
+  WsCarve c{(char*)h->ws};
+  int *rsel, *raxis;
+  double *rg, *rb;
+  rc = mcmc_draws(h, nw, nmpm, keys, c, &rsel, &raxis, &rg, &rb, st);
+  if (rc) return rc;
   McmcArgs A{nw, nmpm, nch, Dt, epsilon_AS, r_up, r_dn, G, Ginv, acc, rej, rsel, raxis, rg, rb, h->b_up.off_cseg, h->b_up.off_cbeg};
   const size_t smem = (size_t)(S.n_e * 3 + 2 * S.n_up * S.n_up + S.n_e * P + nch * P + 2) * 32 * 8;
   dim3 block(32, nch + 1);

@@ -99,36 +99,6 @@ struct PosShared {
   }
 };
 
-// ECP mesh point (e, nn, k): position, and the channel-summed angular factor  sum_l V_l(d)(2l+1)P_l(cos) * w_k
-// (jqmc/coulomb_potential.py:1562-1575, 1607-1645)
-__device__ __forceinline__ void ecp_point(const SysDev& S, const double* rt, double x, double y, double z, int nn, int k,
-                                          double& px, double& py, double& pz, double& ang_w, bool want_ang) {
-  double d;
-  const int a = nearest_atom(S.Rn, S.n_atom, x, y, z, nn, &d);
-  const double relx = S.Rn[3 * a] - x, rely = S.Rn[3 * a + 1] - y, relz = S.Rn[3 * a + 2] - z;
-  d = sqrt(relx * relx + rely * rely + relz * relz);
-  const double q0 = S.quad_g[3 * k], q1 = S.quad_g[3 * k + 1], q2 = S.quad_g[3 * k + 2];
-  const double gx = q0 * rt[0] + q1 * rt[3] + q2 * rt[6];
-  const double gy = q0 * rt[1] + q1 * rt[4] + q2 * rt[7];
-  const double gz = q0 * rt[2] + q1 * rt[5] + q2 * rt[8];
-  px = x + relx + d * gx;
-  py = y + rely + d * gy;
-  pz = z + relz + d * gz;
-  ang_w = 0.0;
-  if (!want_ang) return;
-  const double gn = sqrt(gx * gx + gy * gy + gz * gz);
-  const double cos_t = (-relx / d) * (gx / gn) + (-rely / d) * (gy / gn) + (-relz / d) * (gz / gn);
-  const int lloc = S.ecp_lmax_atom[a];
-  double ang = 0.0;
-  for (int l = 0; l < lloc; ++l) {
-    double vl = 0.0;
-    for (int kk = S.ecp_off[a]; kk < S.ecp_off[a + 1]; ++kk)
-      if (S.ecp_l[kk] == l) vl += S.ecp_c[kk] * ipow(d, S.ecp_p[kk]) * qexp(-S.ecp_z[kk] * d * d);
-    ang = fma(vl / (d * d) * (2 * l + 1), legendre_l(l, cos_t), ang);
-  }
-  ang_w = ang * S.quad_w[k];
-}
-
 template <int NMO, bool CART, int LMAX>
 __global__ void __launch_bounds__(512, 1)
 k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
@@ -809,6 +779,25 @@ int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
 
 }  // namespace
 
+size_t lrdmc_draws_bytes(int nw, int nmpm) { return (size_t)nmpm * nw * (2 * 8 + 9 * 8 + 8) + 4 * 256; }
+int lrdmc_draws(qe_engine* h, int nw, int nmpm, int random_mesh, uint32_t* keys, WsCarve& c, double** rRT, double** ru, cudaStream_t st) {
+  const size_t n_draw = (size_t)nmpm * nw;
+  uint2* sub = c.take<uint2>(n_draw * 2);
+  *rRT = c.take<double>(n_draw * 9);
+  *ru = c.take<double>(n_draw);
+  {
+    LaunchScope ls_(h, K_KEYCHAIN, st);
+    k_lrdmc_keychain<<<nblk(nw, 64), 64, 0, st>>>(nw, nmpm, keys, sub);
+  }
+  CHECK_LAUNCH();
+  {
+    LaunchScope ls_(h, K_DRAWS, st);
+    k_lrdmc_draws<<<nblk((long long)n_draw, 128), 128, 0, st>>>(nw, nmpm, random_mesh, sub, *rRT, *ru);
+  }
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+
 extern "C" int qe_lrdmc_project(qe_engine* h, int nw, double* w, double* r_up, double* r_dn, double* Ginv, uint32_t* keys,
                                 double E_scf, int nmpm, int random_discretized_mesh, int non_local_move, double alat, double* RT,
                                 double* V_diag, double* V_nondiag, void* stream) {
@@ -817,23 +806,15 @@ extern "C" int qe_lrdmc_project(qe_engine* h, int nw, double* w, double* r_up, d
   if (!(alat > 0)) return fail(QE_ERR_INVALID, "qe_lrdmc_project: alat must be positive");
   if (non_local_move != 0 && non_local_move != 1) return fail(QE_ERR_INVALID, "qe_lrdmc_project: non_local_move must be 0 (tmove) or 1 (dltmove)");
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t n_draw = (size_t)nmpm * nw;
-  int rc = ensure_ws(h, n_draw * (2 * 8 + 9 * 8 + 8) + 4096);
+  if (use_wide(h))
+    return wide_lrdmc(h, 0, nw, w, r_up, r_dn, Ginv, keys, E_scf, nmpm, random_discretized_mesh, non_local_move, alat, nullptr, RT,
+                      V_diag, V_nondiag, st);
+  int rc = ensure_ws(h, lrdmc_draws_bytes(nw, nmpm) + 4096);
   if (rc) return rc;
   WsCarve c{(char*)h->ws};
-  uint2* sub = c.take<uint2>(n_draw * 2);
-  double* rRT = c.take<double>(n_draw * 9);
-  double* ru = c.take<double>(n_draw);
-  {
-    LaunchScope ls_(h, K_KEYCHAIN, st);
-    k_lrdmc_keychain<<<nblk(nw, 64), 64, 0, st>>>(nw, nmpm, keys, sub);
-  }
-  CHECK_LAUNCH();
-  {
-    LaunchScope ls_(h, K_DRAWS, st);
-    k_lrdmc_draws<<<nblk((long long)n_draw, 128), 128, 0, st>>>(nw, nmpm, random_discretized_mesh, sub, rRT, ru);
-  }
-  CHECK_LAUNCH();
+  double *rRT, *ru;
+  rc = lrdmc_draws(h, nw, nmpm, random_discretized_mesh, keys, c, &rRT, &ru, st);
+  if (rc) return rc;
   WalkerArgs A{};
   A.nw = nw;
   A.nmpm = nmpm;
@@ -858,6 +839,9 @@ extern "C" int qe_lrdmc_velements(qe_engine* h, int nw, const double* r_up, cons
   if (!h || nw <= 0 || !r_up || !Ginv || !V_diag || !V_nondiag || (!r_dn && h->sys.n_dn > 0))
     return fail(QE_ERR_INVALID, "qe_lrdmc_velements: bad argument (Ginv is required: call qe_geminal_init first)");
   if (!(alat > 0)) return fail(QE_ERR_INVALID, "qe_lrdmc_velements: alat must be positive");
+  if (use_wide(h))
+    return wide_lrdmc(h, 1, nw, nullptr, const_cast<double*>(r_up), const_cast<double*>(r_dn), const_cast<double*>(Ginv), nullptr, 0.0, 1,
+                      0, non_local_move, alat, RT, nullptr, V_diag, V_nondiag, (cudaStream_t)stream);
   WalkerArgs A{};
   A.nw = nw;
   A.nmpm = 1;

@@ -165,6 +165,8 @@ class WalkerEngine:
         self.ecp_flag = bool(cp.ecp_flag)
         self.n_orb = n_orb_up
         self._n_ao = int(d.orb_up.n_ao)
+        self._n_ao_j3 = int(d.j3_orb.n_ao) if d.j3_flag else 0
+        self._n_orb_j3 = int(d.j3_orb.n_mo or d.j3_orb.n_ao) if d.j3_flag else 0
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.qe_create(C.byref(d), C.byref(h)), "qe_create")
@@ -310,6 +312,10 @@ class WalkerEngine:
         return out
 
     def _n_out(self, wi, li):
+        if wi == 2:
+            if self._n_ao_j3 == 0:
+                raise ValueError("eval_orbitals: this Hamiltonian has no three-body Jastrow orbitals")
+            return self._n_ao_j3 if li == 0 else self._n_orb_j3
         return self._n_ao if li == 0 else self.n_orb
 
     def move_ratios(self, r_up, r_dn, Ginv, elec, r_new, det=True, jas=True):
@@ -333,6 +339,14 @@ class WalkerEngine:
     def set_fused(self, on: bool):
         """Fused (one kernel, shared-memory resident) vs staged (kernel chain) local energy; same results."""
         _lib.check(self._lib.qe_set_fused(self._h, 1 if on else 0), "qe_set_fused")
+
+    def set_path(self, general: bool):
+        """Force the general ("wide") kernel family (True) or let the engine choose (False); see qe_set_path."""
+        _lib.check(self._lib.qe_set_path(self._h, 1 if general else 0), "qe_set_path")
+
+    def set_gemm_reference(self, on: bool):
+        """Debugging aid: plain DFMA GEMM instead of the fp64 tensor-core kernel in the general path."""
+        _lib.check(self._lib.qe_set_gemm_reference(1 if on else 0), "qe_set_gemm_reference")
 
     def set_walkers_per_cta(self, wpc: int):
         """Walkers per CTA of the fused walker kernel (0 = automatic)."""

@@ -1,0 +1,365 @@
+"""GPU parity tests of the general ("wide") kernel family (jqmc_b200/csrc/qe_wide.cu): AO-basis JAGP geminals, three-body
+Jastrow (AO- and MO-type orbital sets, spherical and Cartesian), more electrons than the register kernels cover, and the
+small MO-basis systems forced onto this path.  Same oracle, same tolerances as tests/test_gpu_parity.py: fp64 1e-10 relative
+unless argued otherwise, accept/reject counts, selected moves and keys bit-exact."""
+
+import copy
+import zlib
+import dataclasses
+
+import numpy as np
+import pytest
+
+from jqmc_b200.data import (
+    Geminal_data,
+    Jastrow_data,
+    Jastrow_one_body_data,
+    Jastrow_three_body_data,
+    Jastrow_two_body_data,
+    MOs_data,
+    is_cart,
+)
+from oracle import drivers as OD
+from oracle import physics as P
+from tests.conftest import load_system, random_walkers
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def sub_basis(aos, lmax):
+    """AO subset with l <= lmax (a small orbital set for the three-body Jastrow)."""
+    l = np.asarray(aos.angular_momentums)
+    keep = np.nonzero(l <= lmax)[0]
+    new_index = {int(a): i for i, a in enumerate(keep)}
+    oi = np.asarray(aos.orbital_indices)
+    pk = np.nonzero(np.isin(oi, keep))[0]
+    kw = dict(
+        structure_data=aos.structure_data,
+        nucleus_index=tuple(int(np.asarray(aos.nucleus_index)[a]) for a in keep),
+        num_ao=len(keep),
+        num_ao_prim=len(pk),
+        angular_momentums=tuple(int(l[a]) for a in keep),
+        orbital_indices=tuple(new_index[int(oi[p])] for p in pk),
+        exponents=np.asarray(aos.exponents, dtype=np.float64)[pk],
+        coefficients=np.asarray(aos.coefficients, dtype=np.float64)[pk],
+    )
+    if is_cart(aos):
+        for f in ("polynominal_order_x", "polynominal_order_y", "polynominal_order_z"):
+            kw[f] = tuple(int(np.asarray(getattr(aos, f))[a]) for a in keep)
+    else:
+        kw["magnetic_quantum_numbers"] = tuple(int(np.asarray(aos.magnetic_quantum_numbers)[a]) for a in keep)
+    return type(aos)(**kw)
+
+
+def _j12(H, j1, j2):
+    cp = H.coulomb_potential_data
+    core = tuple(cp.z_cores) if cp.ecp_flag else tuple(0 for _ in H.structure_data.atomic_numbers)
+    one = None if j1 is None else Jastrow_one_body_data(jastrow_1b_param=0.9, jastrow_1b_type=j1, structure_data=H.structure_data, core_electrons=core)
+    two = None if j2 is None else Jastrow_two_body_data(jastrow_2b_param=0.75, jastrow_2b_type=j2)
+    return one, two
+
+
+def _j3(H, kind, seed, lmax=1):
+    if kind is None:
+        return None
+    rng = np.random.default_rng(seed)
+    gem = H.wavefunction_data.geminal_data
+    aos_full = gem.orb_data_up_spin.aos_data if hasattr(gem.orb_data_up_spin, "aos_data") else gem.orb_data_up_spin
+    aos = sub_basis(aos_full, lmax)
+    if kind == "ao":
+        orb, n = aos, aos.num_ao
+    else:
+        n = 6
+        orb = MOs_data(num_mo=n, aos_data=aos, mo_coefficients=rng.normal(scale=0.5, size=(n, aos.num_ao)))
+    M = rng.normal(scale=0.02, size=(n, n))
+    M = 0.5 * (M + M.T) + rng.normal(scale=0.004, size=(n, n))  # the reference symmetrises in optimisation; keep it general
+    j1v = rng.normal(scale=0.05, size=(n, 1))
+    return Jastrow_three_body_data(orb_data=orb, j_matrix=np.hstack([M, j1v]))
+
+
+def make_case(case):
+    """(Hamiltonian, force_wide)"""
+    rng = np.random.default_rng(zlib.crc32(case.encode()))
+    if case == "water_jsd":
+        H = copy.deepcopy(load_system("water_ccecp_ccpvqz"))
+        j1, j2 = _j12(H, "exp", "exp")
+        H.wavefunction_data.jastrow_data = Jastrow_data(jastrow_one_body_data=j1, jastrow_two_body_data=j2)
+        return H, True
+    if case == "li_ae":
+        H = copy.deepcopy(load_system("Li_ae_ccpvdz_cart"))
+        j1, j2 = _j12(H, "pade", "pade")
+        H.wavefunction_data.jastrow_data = Jastrow_data(jastrow_one_body_data=j1, jastrow_two_body_data=j2)
+        return H, True
+    if case in ("water_jagp", "water_jagp_j3mo", "n2_jagp_j3ao"):
+        H = copy.deepcopy(load_system("N2_ecp_ccpvtz_cart" if case.startswith("n2") else "water_ccecp_ccpvqz"))
+        gem = Geminal_data.convert_from_MOs_to_AOs(H.wavefunction_data.geminal_data)
+        lam = np.array(gem.lambda_matrix)
+        pert = rng.normal(scale=2e-3, size=lam.shape)
+        gem = dataclasses.replace(gem, lambda_matrix=lam + pert)
+        H.wavefunction_data.geminal_data = gem
+        if case == "water_jagp":
+            j1, j2 = _j12(H, None, "pade")
+            j3 = None
+        elif case == "water_jagp_j3mo":
+            j1, j2 = _j12(H, "exp", "pade")
+            j3 = _j3(load_system("water_ccecp_ccpvqz"), "mo", 3)
+        else:
+            j1, j2 = _j12(H, None, "exp")
+            j3 = _j3(load_system("N2_ecp_ccpvtz_cart"), "ao", 4)
+        H.wavefunction_data.jastrow_data = Jastrow_data(jastrow_one_body_data=j1, jastrow_two_body_data=j2, jastrow_three_body_data=j3)
+        return H, False
+    if case == "water_j3ao":
+        H = copy.deepcopy(load_system("water_ccecp_ccpvqz"))
+        j1, j2 = _j12(H, None, "pade")
+        H.wavefunction_data.jastrow_data = Jastrow_data(jastrow_two_body_data=j2, jastrow_three_body_data=_j3(H, "ao", 5, lmax=2))
+        return H, False
+    if case == "big":  # 10 up / 9 dn electrons in 12 synthetic MOs over the water AO basis: beyond the register kernels
+        H = copy.deepcopy(load_system("water_ccecp_ccpvqz"))
+        gem = H.wavefunction_data.geminal_data
+        aos = gem.orb_data_up_spin.aos_data
+        n_mo, n_up, n_dn = 12, 10, 9
+        Cu = rng.normal(scale=0.4, size=(n_mo, aos.num_ao))
+        Cd = Cu + rng.normal(scale=0.05, size=Cu.shape)  # unrestricted: different tables per spin
+        lam = np.hstack([np.eye(n_mo) + rng.normal(scale=0.05, size=(n_mo, n_mo)), rng.normal(scale=0.5, size=(n_mo, n_up - n_dn))])
+        H.wavefunction_data.geminal_data = Geminal_data(
+            num_electron_up=n_up, num_electron_dn=n_dn, orb_data_up_spin=MOs_data(num_mo=n_mo, aos_data=aos, mo_coefficients=Cu),
+            orb_data_dn_spin=MOs_data(num_mo=n_mo, aos_data=aos, mo_coefficients=Cd), lambda_matrix=lam)  # fmt: skip
+        j1, j2 = _j12(H, "exp", "pade")
+        H.wavefunction_data.jastrow_data = Jastrow_data(jastrow_one_body_data=j1, jastrow_two_body_data=j2,
+                                                        jastrow_three_body_data=_j3(load_system("water_ccecp_ccpvqz"), "ao", 6))  # fmt: skip
+        return H, False
+    raise KeyError(case)
+
+
+CASES = ["water_jsd", "li_ae", "water_jagp", "water_j3ao", "water_jagp_j3mo", "n2_jagp_j3ao", "big"]
+
+
+def _engine(case):
+    from jqmc_b200.engine import WalkerEngine
+
+    H, force = make_case(case)
+    eng = WalkerEngine(H)
+    if force:
+        eng.set_path(True)
+    return H, eng
+
+
+def _walkers(H, nw, seed, scale=0.8):
+    r_up, r_dn = random_walkers(H, nw, seed, scale)
+    return r_up, r_dn
+
+
+@pytest.mark.parametrize("case", ["water_jagp_j3mo", "water_j3ao", "big"])
+def test_wide_orbital_layers(case):
+    """Orbital value / gradient / Laplacian of the geminal and J3 orbital sets (tensor-core AO->MO product)."""
+    H, eng = _engine(case)
+    rng = np.random.default_rng(2)
+    Rn = np.asarray(H.structure_data.positions)
+    r = Rn[rng.integers(0, len(Rn), 37)] + rng.normal(scale=0.9, size=(37, 3))
+    wf = H.wavefunction_data
+    for which, orb in (("up", wf.geminal_data.orb_data_up_spin), ("dn", wf.geminal_data.orb_data_dn_spin),
+                       ("j3", wf.jastrow_data.jastrow_three_body_data.orb_data)):  # fmt: skip
+        ref = np.stack(P.compute_orb_value_grad_lap(orb, r))
+        got = eng.eval_orbitals(which, "orb", r).cpu().numpy()
+        np.testing.assert_allclose(got, ref, rtol=RTOL, atol=1e-12 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_wide_geminal_inverse_and_ln_wavefunction(case):
+    H, eng = _engine(case)
+    nw = 5
+    r_up, r_dn = _walkers(H, nw, 21)
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    ln, sg = eng.ln_wavefunction(r_up, r_dn)
+    G, Ginv, ln, sg = (x.cpu().numpy() for x in (G, Ginv, ln, sg))
+    gem = H.wavefunction_data.geminal_data
+    for w in range(nw):
+        Gr = P.compute_geminal_all_elements(gem, r_up[w], r_dn[w])
+        np.testing.assert_allclose(G[w], Gr, rtol=RTOL, atol=1e-13 * np.abs(Gr).max())
+        Gir = P.geminal_inv_svd(Gr)
+        cond = np.linalg.cond(Gr)
+        np.testing.assert_allclose(Ginv[w], Gir, rtol=0, atol=1e-14 * cond * np.abs(Gir).max())
+        ref = P.evaluate_ln_wavefunction(H.wavefunction_data, r_up[w], r_dn[w])
+        np.testing.assert_allclose(ln[w], ref, rtol=RTOL, atol=1e-10)
+        assert sg[w] == np.sign(np.linalg.det(Gr))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_wide_local_energy_and_parts(case):
+    H, eng = _engine(case)
+    nw = 4
+    r_up, r_dn = _walkers(H, nw, 33)
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    keys = np.array([[3, 100 + i] for i in range(nw)], dtype=np.uint32)
+    RT = eng.generate_RTs(keys)
+    e_L, T, V = eng.e_L_fast(r_up, r_dn, RT, Ginv, return_parts=True)
+    e_L, T, V, RT, Ginv = (x.cpu().numpy() for x in (e_L, T, V, RT, Ginv))
+    wf, cp = H.wavefunction_data, H.coulomb_potential_data
+    for w in range(nw):
+        RTw = OD.generate_rotation_matrix((3, 100 + w))
+        Tu, Td = P.compute_kinetic_energy_all_elements(wf, r_up[w], r_dn[w], Ginv[w])
+        Tref = np.concatenate([Tu, Td])
+        np.testing.assert_allclose(T[w], Tref, rtol=RTOL, atol=1e-10 * np.abs(Tref).max())
+        np.testing.assert_allclose(V[w, 0], P.compute_bare_coulomb_potential(cp, r_up[w], r_dn[w]), rtol=RTOL)
+        if cp.ecp_flag:
+            np.testing.assert_allclose(V[w, 1], P.compute_ecp_local_parts(cp, r_up[w], r_dn[w]), rtol=RTOL, atol=1e-12)
+            vnl = P.compute_ecp_non_local_parts_nearest_neighbors(cp, wf, r_up[w], r_dn[w], RTw, NN=1, Nv=6, Ginv=Ginv[w])[3]
+            np.testing.assert_allclose(V[w, 2], vnl, rtol=1e-9, atol=1e-10)
+        ref = P.compute_local_energy(H, r_up[w], r_dn[w], RTw, Ginv=Ginv[w])
+        np.testing.assert_allclose(e_L[w], ref, rtol=RTOL, atol=1e-10 * np.abs(Tref).max())
+
+
+@pytest.mark.parametrize("case", ["water_jsd", "water_jagp", "water_jagp_j3mo", "n2_jagp_j3ao", "big", "li_ae"])
+def test_wide_move_ratios(case):
+    """a9 / a17: determinant and Jastrow (J1+J2+J3) ratios of single-electron moves vs brute-force re-evaluation."""
+    H, eng = _engine(case)
+    nw = 3
+    r_up, r_dn = _walkers(H, nw, 8)
+    n_up, n_dn = r_up.shape[1], r_dn.shape[1]
+    elec = list(range(n_up + n_dn))
+    rng = np.random.default_rng(5)
+    r_all = np.concatenate([r_up, r_dn], axis=1)
+    r_new = r_all[:, elec, :] + rng.normal(scale=0.4, size=(nw, len(elec), 3))
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    dr, jr = eng.move_ratios(r_up, r_dn, Ginv, elec, r_new)
+    dr, jr = dr.cpu().numpy(), jr.cpu().numpy()
+    wf = H.wavefunction_data
+    for w in range(nw):
+        for k, e in enumerate(elec):
+            up, idx = (True, e) if e < n_up else (False, e - n_up)
+            tot = P.wf_ratio_brute_force(wf, r_up[w], r_dn[w], up, idx, r_new[w, k])
+            det = P.wf_ratio_brute_force(wf, r_up[w], r_dn[w], up, idx, r_new[w, k], det_only=True)
+            np.testing.assert_allclose(dr[w, k], det, rtol=1e-8, atol=1e-11)
+            np.testing.assert_allclose(dr[w, k] * jr[w, k], tot, rtol=1e-8, atol=1e-11)
+
+
+@pytest.mark.parametrize("case,eps,nmpm", [("water_jsd", 0.05, 16), ("li_ae", 0.0, 20), ("water_jagp", 0.0, 20), ("water_j3ao", 0.0, 16),
+                                           ("water_jagp_j3mo", 0.1, 12), ("n2_jagp_j3ao", 0.0, 12), ("big", 0.0, 24)])  # fmt: skip
+def test_wide_mcmc_update_trajectory(case, eps, nmpm):
+    """a28: same keys -> bit-exact accept/reject sequence and keys; positions, G, Ginv to round-off."""
+    H, eng = _engine(case)
+    nw = 3
+    r_up, r_dn = _walkers(H, nw, 77, scale=0.6)
+    keys = np.array([[0, 4242 + 13 * i] for i in range(nw)], dtype=np.uint32)
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    acc, rej, ru, rd, k2, Gi2, G2 = eng.update(r_up, r_dn, keys, nmpm, 2.0, eps, Ginv, G)
+    acc, rej, ru, rd, k2, Gi2, G2 = (x.cpu().numpy() for x in (acc, rej, ru, rd, k2, Gi2, G2))
+    G, Ginv = G.cpu().numpy(), Ginv.cpu().numpy()
+    for w in range(nw):
+        a, r_, ru_o, rd_o, key_o, Gi_o, G_o = OD.update_electron_positions(
+            H, r_up[w], r_dn[w], (int(keys[w, 0]), int(keys[w, 1])), nmpm, 2.0, eps, Ginv[w], G[w]
+        )
+        assert (a, r_) == (int(acc[w]), int(rej[w]))
+        assert a + r_ == nmpm
+        assert tuple(int(x) for x in k2[w]) == tuple(key_o)
+        np.testing.assert_allclose(ru[w], ru_o, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(rd[w], rd_o, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(G2[w], G_o, rtol=1e-8, atol=1e-11 * np.abs(G_o).max())
+        Gfresh = P.compute_geminal_all_elements(H.wavefunction_data.geminal_data, ru[w], rd[w])
+        np.testing.assert_allclose(G2[w], Gfresh, rtol=1e-8, atol=1e-11 * np.abs(Gfresh).max())
+        np.testing.assert_allclose(Gi2[w] @ Gfresh, np.eye(len(Gfresh)), rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("case,nlm", [("water_jsd", "tmove"), ("li_ae", "tmove"), ("water_jagp", "dltmove"), ("water_j3ao", "tmove"),
+                                      ("water_jagp_j3mo", "dltmove"), ("n2_jagp_j3ao", "tmove"), ("big", "tmove")])  # fmt: skip
+def test_wide_lrdmc_V_elements(case, nlm):
+    H, eng = _engine(case)
+    nw = 3
+    r_up, r_dn = _walkers(H, nw, 14, scale=0.7)
+    RT = eng.generate_RTs(np.array([[9, i] for i in range(nw)], dtype=np.uint32))
+    Vd, Vn = eng.V_elements_n(r_up, r_dn, RT, nlm, 0.3)
+    Vd, Vn, RT = Vd.cpu().numpy(), Vn.cpu().numpy(), RT.cpu().numpy()
+    for w in range(nw):
+        d, n = OD.lrdmc_V_elements(H, r_up[w], r_dn[w], RT[w], nlm, 0.3)
+        np.testing.assert_allclose(Vd[w], d, rtol=1e-9)
+        np.testing.assert_allclose(Vn[w], n, rtol=1e-9)
+
+
+@pytest.mark.parametrize("case,nlm,E_scf,nmpm", [("water_jsd", "tmove", -17.0, 6), ("li_ae", "tmove", -7.4, 6), ("water_jagp", "tmove", -17.0, 6),
+                                                 ("water_j3ao", "dltmove", -17.0, 5), ("water_jagp_j3mo", "tmove", -17.0, 5),
+                                                 ("big", "tmove", -60.0, 4)])  # fmt: skip
+def test_wide_lrdmc_projection_trajectory(case, nlm, E_scf, nmpm):
+    """a30: same keys -> the same mesh moves, weights, keys; running inverse to round-off."""
+    H, eng = _engine(case)
+    nw, alat = 3, 0.3
+    r_up, r_dn = _walkers(H, nw, 41, scale=0.7)
+    keys = np.array([[0, 777 + 5 * i] for i in range(nw)], dtype=np.uint32)
+    Ginv = eng.A_inv_n(r_up, r_dn)
+    out = eng.projection_n(np.ones(nw), r_up, r_dn, Ginv, keys, E_scf, nmpm, True, nlm, alat)
+    w, ru, rd, Gi, k2, RT, Vd, Vn = (x.cpu().numpy() for x in out)
+    Ginv = Ginv.cpu().numpy()
+    for i in range(nw):
+        ow, oru, ord_, oGi, okey, oRT, od, on = OD.lrdmc_projection(
+            H, 1.0, r_up[i], r_dn[i], Ginv[i], (int(keys[i, 0]), int(keys[i, 1])), E_scf, nmpm, True, nlm, alat
+        )
+        assert tuple(int(x) for x in k2[i]) == tuple(okey)
+        np.testing.assert_allclose(ru[i], oru, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(rd[i], ord_, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(w[i], ow, rtol=1e-8)
+        np.testing.assert_allclose(RT[i], oRT, rtol=0, atol=1e-14)
+        np.testing.assert_allclose(Vd[i], od, rtol=1e-8)
+        np.testing.assert_allclose(Vn[i], on, rtol=1e-8)
+        np.testing.assert_allclose(Gi[i], oGi, rtol=1e-6, atol=1e-8 * np.abs(oGi).max())
+
+
+def test_wide_equals_register_kernels_at_scale():
+    """water JSD + J2, 1000 walkers (not a multiple of any tile): the general path and the register/shared-memory kernels give
+    the same e_L, the same Metropolis decisions and the same LRDMC moves; the tensor-core GEMM equals the plain DFMA GEMM."""
+    import torch
+
+    from jqmc_b200 import rng_host
+    from jqmc_b200.engine import WalkerEngine
+
+    H = copy.deepcopy(load_system("water_ccecp_ccpvqz"))
+    H.wavefunction_data.jastrow_data = Jastrow_data(jastrow_two_body_data=Jastrow_two_body_data(jastrow_2b_param=1.0))
+    a, b = WalkerEngine(H), WalkerEngine(H)
+    b.set_path(True)
+    nw = 1000
+    r_up, r_dn = random_walkers(H, nw, 3, 0.7)
+    keys = rng_host.split(rng_host.PRNGKey(5), nw)
+    Ga, Gia = a.geminal_inv_batched(r_up, r_dn)
+    Gb, Gib = b.geminal_inv_batched(r_up, r_dn)
+    np.testing.assert_allclose(Gb.cpu().numpy(), Ga.cpu().numpy(), rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(Gib.cpu().numpy(), Gia.cpu().numpy(), rtol=1e-7, atol=1e-9 * float(Gia.abs().max()))
+    RT = a.generate_RTs(keys)
+    ea = a.e_L_fast(r_up, r_dn, RT, Gia).cpu().numpy()
+    eb = b.e_L_fast(r_up, r_dn, RT, Gia).cpu().numpy()
+    np.testing.assert_allclose(eb, ea, rtol=1e-9, atol=1e-9)
+    b.set_gemm_reference(True)
+    eb2 = b.e_L_fast(r_up, r_dn, RT, Gia).cpu().numpy()
+    b.set_gemm_reference(False)
+    np.testing.assert_allclose(eb2, eb, rtol=1e-11, atol=1e-11)
+    oa = a.update(r_up, r_dn, keys, 12, 2.0, 0.0, Gia, Ga)
+    ob = b.update(r_up, r_dn, keys, 12, 2.0, 0.0, Gia, Ga)
+    # decisions can differ only where |ratio^2 T - u| is at round-off: allow a handful of walkers out of 1000
+    same = (oa[0] == ob[0]).cpu().numpy()
+    assert same.mean() > 0.995, same.mean()
+    sel = torch.from_numpy(same).to(oa[2].device)
+    np.testing.assert_allclose(ob[2][sel].cpu().numpy(), oa[2][sel].cpu().numpy(), rtol=0, atol=1e-9)
+    assert torch.equal(oa[4], ob[4])
+    w0 = np.ones(nw)
+    pa = a.projection_n(w0, r_up, r_dn, Gia, keys, -17.0, 5, True, "tmove", 0.3)
+    pb = b.projection_n(w0, r_up, r_dn, Gia, keys, -17.0, 5, True, "tmove", 0.3)
+    close = (pa[1] - pb[1]).abs().amax(dim=(1, 2)).cpu().numpy() < 1e-9
+    assert close.mean() > 0.995, close.mean()
+    np.testing.assert_allclose(pb[0].cpu().numpy()[close], pa[0].cpu().numpy()[close], rtol=1e-7)
+    np.testing.assert_allclose(pb[6].cpu().numpy()[close], pa[6].cpu().numpy()[close], rtol=1e-7)
+
+
+def test_wide_drivers_run_jagp_j3():
+    """MCMC and GFMC_n drivers on water JAGP + J1J2J3 (BASELINE configs[2] shape at test size): finite energies in the
+    physical range, counters consistent."""
+    from jqmc_b200.gfmc import GFMC_n
+    from jqmc_b200.mcmc import MCMC
+
+    H, _ = make_case("water_jagp_j3mo")
+    j3 = H.wavefunction_data.jastrow_data.jastrow_three_body_data  # a gentle J3, so that the energies stay in the physical range
+    H.wavefunction_data.jastrow_data.jastrow_three_body_data = dataclasses.replace(j3, j_matrix=0.02 * np.asarray(j3.j_matrix))
+    m = MCMC(H, mcmc_seed=3, num_walkers=32, num_mcmc_per_measurement=16, Dt=2.0, epsilon_AS=0.0)
+    m.run(num_mcmc_steps=12)
+    assert m.e_L.shape == (12, 32) and np.all(np.isfinite(m.e_L))
+    assert -19.5 < m.e_L[4:].mean() < -14.5
+    g = GFMC_n(H, num_walkers=32, num_mcmc_per_measurement=6, num_gfmc_collect_steps=2, mcmc_seed=11, E_scf=-17.0, alat=0.3)
+    g.run(10)
+    assert np.all(np.isfinite(g.e_L)) and -20.0 < g.e_L[2:].mean() < -14.5
