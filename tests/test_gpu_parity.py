@@ -16,7 +16,7 @@ from tests.conftest import load_system, random_walkers
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-10
-SYSTEMS = ["water_ccecp_ccpvqz", "N2_ecp_ccpvtz_cart", "H2_ae_ccpvdz_cart", "Li_ae_ccpvdz_cart", "H2_ecp_ccpvtz"]
+SYSTEMS = ["water_ccecp_ccpvqz", "N2_ecp_ccpvtz_cart", "H2_ae_ccpvdz_cart", "Li_ae_ccpvdz_cart", "H2_ecp_ccpvtz", "H_ecp_ccpvqz"]
 
 
 def _engine(H, **kw):
@@ -90,7 +90,8 @@ def test_geminal_inverse_and_ln_wavefunction(name):
 
 @pytest.mark.parametrize("name,jas", [("water_ccecp_ccpvqz", "none"), ("water_ccecp_ccpvqz", "j2pade"), ("water_ccecp_ccpvqz", "j1exp_j2exp"),
                                       ("N2_ecp_ccpvtz_cart", "j1pade_j2pade"), ("H2_ae_ccpvdz_cart", "j1exp_j2exp"),
-                                      ("Li_ae_ccpvdz_cart", "j2pade"), ("H2_ecp_ccpvtz", "j1pade_j2pade")])  # fmt: skip
+                                      ("Li_ae_ccpvdz_cart", "j2pade"), ("H2_ecp_ccpvtz", "j1pade_j2pade"),
+                                      ("H_ecp_ccpvqz", "j1exp_j2exp")])  # fmt: skip
 def test_local_energy_and_parts(name, jas):
     """kernels 4-5 (a10, a13-a16, a19, a23-a27): e_L, per-electron kinetic energies, potential pieces."""
     H = _with_jastrow(load_system(name), jas)
@@ -187,7 +188,8 @@ def test_as_factor(water):
 
 @pytest.mark.parametrize("name,jas,eps,nmpm", [("water_ccecp_ccpvqz", "j2pade", 0.0, 24), ("water_ccecp_ccpvqz", "j1exp_j2exp", 0.05, 16),
                                                ("Li_ae_ccpvdz_cart", "j2pade", 0.0, 20), ("N2_ecp_ccpvtz_cart", "j1pade_j2pade", 0.1, 10),
-                                               ("H2_ae_ccpvdz_cart", "none", 0.0, 30)])  # fmt: skip
+                                               ("H2_ae_ccpvdz_cart", "none", 0.0, 30),
+                                               ("H_ecp_ccpvqz", "j1pade_j2pade", 0.0, 14)])  # fmt: skip  (no down electron: _update_electron_positions_only_up_electron, jqmc_mcmc.py:4536-4722)
 def test_mcmc_update_trajectory(name, jas, eps, nmpm):
     """kernel 6 (a28): same keys -> same proposals, bit-exact accept/reject sequence, keys bit-exact,
     positions/G/Ginv to round-off."""
@@ -321,7 +323,8 @@ def test_local_energy_fused_equals_staged(name, jas):
 
 @pytest.mark.parametrize("name,jas,nlm", [("water_ccecp_ccpvqz", "j2pade", "tmove"), ("water_ccecp_ccpvqz", "j1exp_j2exp", "dltmove"),
                                           ("Li_ae_ccpvdz_cart", "j2pade", "tmove"), ("H2_ecp_ccpvtz_cart", "j1pade_j2pade", "tmove"),
-                                          ("H2_ae_ccpvdz_cart", "j1exp_j2exp", "tmove"), ("H2_ecp_ccpvtz", "j2pade", "dltmove")])  # fmt: skip
+                                          ("H2_ae_ccpvdz_cart", "j1exp_j2exp", "tmove"), ("H2_ecp_ccpvtz", "j2pade", "dltmove"),
+                                          ("H_ecp_ccpvqz", "j1exp_j2exp", "tmove")])  # fmt: skip
 def test_lrdmc_V_elements(name, jas, nlm):
     """a20, a23-a25, a30: V_diag / V_nondiag of the lattice-regularised Hamiltonian."""
     H = _with_jastrow(load_system(name), jas)
@@ -338,14 +341,15 @@ def test_lrdmc_V_elements(name, jas, nlm):
 
 
 @pytest.mark.parametrize("name,jas,nlm,mesh", [("water_ccecp_ccpvqz", "j2pade", "tmove", True), ("water_ccecp_ccpvqz", "j2pade", "dltmove", True),
-                                               ("Li_ae_ccpvdz_cart", "j1exp_j2exp", "tmove", True), ("H2_ecp_ccpvtz_cart", "j2pade", "tmove", False)])  # fmt: skip
+                                               ("Li_ae_ccpvdz_cart", "j1exp_j2exp", "tmove", True), ("H2_ecp_ccpvtz_cart", "j2pade", "tmove", False),
+                                               ("H_ecp_ccpvqz", "j1exp_j2exp", "tmove", True)])  # fmt: skip
 def test_lrdmc_projection_trajectory(name, jas, nlm, mesh):
     """kernel 6 / a30: same keys -> the same mesh moves are selected (bit-exact positions up to round-off of the
     mesh point), same weights, keys bit-exact."""
     H = _with_jastrow(load_system(name), jas)
     eng = _engine(H)
     nw, nmpm, alat = 3, 6, 0.3
-    E_scf = {"water_ccecp_ccpvqz": -17.0, "Li_ae_ccpvdz_cart": -7.4, "H2_ecp_ccpvtz_cart": -1.1}[name]
+    E_scf = {"water_ccecp_ccpvqz": -17.0, "Li_ae_ccpvdz_cart": -7.4, "H2_ecp_ccpvtz_cart": -1.1, "H_ecp_ccpvqz": -0.45}[name]
     r_up, r_dn = random_walkers(H, nw, 41, scale=0.7)
     keys = np.array([[0, 777 + 5 * i] for i in range(nw)], dtype=np.uint32)
     Ginv = eng.A_inv_n(r_up, r_dn)

@@ -86,6 +86,11 @@ def make_case(case):
         j1, j2 = _j12(H, "exp", "exp")
         H.wavefunction_data.jastrow_data = Jastrow_data(jastrow_one_body_data=j1, jastrow_two_body_data=j2)
         return H, True
+    if case == "h_atom":  # one up electron, no down electron
+        H = copy.deepcopy(load_system("H_ecp_ccpvqz"))
+        j1, j2 = _j12(H, "exp", "pade")
+        H.wavefunction_data.jastrow_data = Jastrow_data(jastrow_one_body_data=j1, jastrow_two_body_data=j2)
+        return H, True
     if case == "li_ae":
         H = copy.deepcopy(load_system("Li_ae_ccpvdz_cart"))
         j1, j2 = _j12(H, "pade", "pade")
@@ -129,10 +134,20 @@ def make_case(case):
         H.wavefunction_data.jastrow_data = Jastrow_data(jastrow_one_body_data=j1, jastrow_two_body_data=j2,
                                                         jastrow_three_body_data=_j3(load_system("water_ccecp_ccpvqz"), "ao", 6))  # fmt: skip
         return H, False
+    from jqmc_b200 import synthetic as SY
+
+    if case == "benzene":  # BASELINE configs[3] shape: 30 electrons, 258 spherical AOs, 15 MOs, J1+J2+J3
+        return SY.benzene_shape(), False
+    if case == "benzene_jagp":  # the same with the 258 x 258 AO-basis geminal
+        return SY.benzene_shape(jagp=True), False
+    if case == "grid48":  # 48 electrons, 360 Cartesian AOs (partial last shell), 24 MOs, J2+J3
+        return SY.grid_molecule(12, 4, 30, 24, j3_ao_per_atom=4), False
+    if case == "S":  # BASELINE configs[4]: 100 electrons, 1000 Cartesian AOs, 50 MOs
+        return SY.grid_molecule(), False
     raise KeyError(case)
 
 
-CASES = ["water_jsd", "li_ae", "water_jagp", "water_j3ao", "water_jagp_j3mo", "n2_jagp_j3ao", "big"]
+CASES = ["water_jsd", "h_atom", "li_ae", "water_jagp", "water_j3ao", "water_jagp_j3mo", "n2_jagp_j3ao", "big"]
 
 
 def _engine(case):
@@ -146,8 +161,94 @@ def _engine(case):
 
 
 def _walkers(H, nw, seed, scale=0.8):
-    r_up, r_dn = random_walkers(H, nw, seed, scale)
-    return r_up, r_dn
+    if len(H.structure_data.positions) > 3:  # synthetic shapes: electrons spread over the atoms
+        from jqmc_b200 import synthetic as SY
+
+        return SY.init_walkers(H, nw, seed, sigma=scale)
+    return random_walkers(H, nw, seed, scale)
+
+
+@pytest.mark.parametrize("case,nw", [("benzene", 2), ("benzene_jagp", 2), ("grid48", 2), ("S", 1)])
+def test_wide_synthetic_shapes_local_energy(case, nw):
+    """BASELINE configs[3] / [4] shapes (synthetic coefficients): G, ln|Psi|, per-electron kinetic energies, potentials, e_L."""
+    H, eng = _engine(case)
+    r_up, r_dn = _walkers(H, nw, 3)
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    ln, sg = eng.ln_wavefunction(r_up, r_dn)
+    keys = np.array([[1, 50 + i] for i in range(nw)], dtype=np.uint32)
+    RT = eng.generate_RTs(keys)
+    e_L, T, V = eng.e_L_fast(r_up, r_dn, RT, Ginv, return_parts=True)
+    G, Ginv, ln, e_L, T, V, RT = (x.cpu().numpy() for x in (G, Ginv, ln, e_L, T, V, RT))
+    wf, cp = H.wavefunction_data, H.coulomb_potential_data
+    for w in range(nw):
+        Gr = P.compute_geminal_all_elements(wf.geminal_data, r_up[w], r_dn[w])
+        np.testing.assert_allclose(G[w], Gr, rtol=1e-9, atol=1e-12 * np.abs(Gr).max())
+        np.testing.assert_allclose(Ginv[w] @ Gr, np.eye(len(Gr)), rtol=0, atol=1e-13 * np.linalg.cond(Gr))
+        np.testing.assert_allclose(ln[w], P.evaluate_ln_wavefunction(wf, r_up[w], r_dn[w]), rtol=1e-10, atol=1e-9)
+        Tu, Td = P.compute_kinetic_energy_all_elements(wf, r_up[w], r_dn[w], Ginv[w])
+        Tref = np.concatenate([Tu, Td])
+        np.testing.assert_allclose(T[w], Tref, rtol=1e-9, atol=1e-9 * np.abs(Tref).max())
+        ref = P.compute_local_energy(H, r_up[w], r_dn[w], RT[w], Ginv=Ginv[w])
+        np.testing.assert_allclose(e_L[w], ref, rtol=1e-9, atol=1e-9 * np.abs(Tref).max())
+
+
+@pytest.mark.parametrize("case", ["benzene", "grid48"])
+def test_wide_synthetic_shapes_trajectories(case):
+    """Metropolis and LRDMC trajectories on the synthetic shapes: decisions / selected moves and keys bit-exact."""
+    H, eng = _engine(case)
+    nw = 2
+    r_up, r_dn = _walkers(H, nw, 9)
+    keys = np.array([[0, 31 + 7 * i] for i in range(nw)], dtype=np.uint32)
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    acc, rej, ru, rd, k2, Gi2, G2 = (x.cpu().numpy() for x in eng.update(r_up, r_dn, keys, 10, 2.0, 0.0, Ginv, G))
+    Gn, Gin = G.cpu().numpy(), Ginv.cpu().numpy()
+    for w in range(nw):
+        a, r_, ru_o, rd_o, key_o, Gi_o, G_o = OD.update_electron_positions(H, r_up[w], r_dn[w], (0, 31 + 7 * w), 10, 2.0, 0.0, Gin[w], Gn[w])
+        assert (a, r_) == (int(acc[w]), int(rej[w])) and tuple(int(x) for x in k2[w]) == tuple(key_o)
+        np.testing.assert_allclose(ru[w], ru_o, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(rd[w], rd_o, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(G2[w], G_o, rtol=1e-7, atol=1e-10 * np.abs(G_o).max())
+    out = eng.projection_n(np.ones(nw), r_up, r_dn, Ginv, keys, -40.0, 2, True, "tmove", 0.3)
+    w_, ru, rd, Gi, k2, RT, Vd, Vn = (x.cpu().numpy() for x in out)
+    for i in range(nw):
+        ow, oru, ord_, oGi, okey, oRT, od, on = OD.lrdmc_projection(H, 1.0, r_up[i], r_dn[i], Gin[i], (0, 31 + 7 * i), -40.0, 2, True, "tmove", 0.3)
+        assert tuple(int(x) for x in k2[i]) == tuple(okey)
+        np.testing.assert_allclose(ru[i], oru, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(rd[i], ord_, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(w_[i], ow, rtol=1e-7)
+        np.testing.assert_allclose(Vd[i], od, rtol=1e-7)
+        np.testing.assert_allclose(Vn[i], on, rtol=1e-7)
+
+
+def test_wide_S_size_properties():
+    """BASELINE configs[4] (100 electrons / 1000 AOs / 50 MOs) at 256 walkers: counts add up, the running inverse stays the
+    inverse of the geminal at the final positions, duplicated walkers stay identical, e_L and V elements are finite."""
+    import torch
+
+    from jqmc_b200 import rng_host
+
+    H, eng = _engine("S")
+    nw = 256
+    r_up, r_dn = _walkers(H, nw, 2)
+    keys = rng_host.split(rng_host.PRNGKey(7), nw)
+    r_up[-1], r_dn[-1], keys[-1] = r_up[0], r_dn[0], keys[0]
+    G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+    acc, rej, ru, rd, k2, Gi2, G2 = eng.update(r_up, r_dn, keys, 30, 2.0, 0.0, Ginv, G)
+    assert torch.all(acc + rej == 30) and 0.05 < acc.double().mean().item() / 30 < 0.98
+    Gf, Gif = eng.geminal_inv_batched(ru, rd)
+    np.testing.assert_allclose(G2.cpu().numpy(), Gf.cpu().numpy(), rtol=1e-6, atol=1e-10 * float(Gf.abs().max()))
+    err = (torch.bmm(Gi2, Gf) - torch.eye(50, device="cuda", dtype=torch.float64)).abs().amax(dim=(1, 2))
+    assert err.median().item() < 1e-6, err.median().item()
+    assert torch.equal(ru[0], ru[-1]) and torch.equal(k2[0], k2[-1])
+    RT = eng.generate_RTs(k2)
+    e_L = eng.e_L_fast(ru, rd, RT, Gi2)
+    Vd, Vn = eng.V_elements_n(ru, rd, RT, "tmove", 0.3, A_inv=Gi2)
+    assert torch.isfinite(e_L).all() and torch.isfinite(Vd).all() and torch.isfinite(Vn).all() and e_L[0] == e_L[-1]
+    out = eng.projection_n(np.ones(nw), ru, rd, Gi2, k2, float(e_L.mean()) - 50.0, 3, True, "tmove", 0.3)
+    assert torch.isfinite(out[0]).all() and torch.equal(out[1][0], out[1][-1])
+    Gf2, _ = eng.geminal_inv_batched(out[1], out[2])
+    err = (torch.bmm(out[3], Gf2) - torch.eye(50, device="cuda", dtype=torch.float64)).abs().amax(dim=(1, 2))
+    assert err.median().item() < 1e-6, err.median().item()
 
 
 @pytest.mark.parametrize("case", ["water_jagp_j3mo", "water_j3ao", "big"])
@@ -234,7 +335,7 @@ def test_wide_move_ratios(case):
             np.testing.assert_allclose(dr[w, k] * jr[w, k], tot, rtol=1e-8, atol=1e-11)
 
 
-@pytest.mark.parametrize("case,eps,nmpm", [("water_jsd", 0.05, 16), ("li_ae", 0.0, 20), ("water_jagp", 0.0, 20), ("water_j3ao", 0.0, 16),
+@pytest.mark.parametrize("case,eps,nmpm", [("water_jsd", 0.05, 16), ("h_atom", 0.0, 12), ("li_ae", 0.0, 20), ("water_jagp", 0.0, 20), ("water_j3ao", 0.0, 16),
                                            ("water_jagp_j3mo", 0.1, 12), ("n2_jagp_j3ao", 0.0, 12), ("big", 0.0, 24)])  # fmt: skip
 def test_wide_mcmc_update_trajectory(case, eps, nmpm):
     """a28: same keys -> bit-exact accept/reject sequence and keys; positions, G, Ginv to round-off."""
@@ -276,7 +377,7 @@ def test_wide_lrdmc_V_elements(case, nlm):
         np.testing.assert_allclose(Vn[w], n, rtol=1e-9)
 
 
-@pytest.mark.parametrize("case,nlm,E_scf,nmpm", [("water_jsd", "tmove", -17.0, 6), ("li_ae", "tmove", -7.4, 6), ("water_jagp", "tmove", -17.0, 6),
+@pytest.mark.parametrize("case,nlm,E_scf,nmpm", [("water_jsd", "tmove", -17.0, 6), ("h_atom", "tmove", -0.45, 5), ("li_ae", "tmove", -7.4, 6), ("water_jagp", "tmove", -17.0, 6),
                                                  ("water_j3ao", "dltmove", -17.0, 5), ("water_jagp_j3mo", "tmove", -17.0, 5),
                                                  ("big", "tmove", -60.0, 4)])  # fmt: skip
 def test_wide_lrdmc_projection_trajectory(case, nlm, E_scf, nmpm):
@@ -354,7 +455,9 @@ def test_wide_drivers_run_jagp_j3():
     from jqmc_b200.mcmc import MCMC
 
     H, _ = make_case("water_jagp_j3mo")
-    j3 = H.wavefunction_data.jastrow_data.jastrow_three_body_data  # a gentle J3, so that the energies stay in the physical range
+    # the Hartree-Fock geminal in AO form (no random perturbation) and a gentle J3, so that the energies stay physical
+    H.wavefunction_data.geminal_data = Geminal_data.convert_from_MOs_to_AOs(load_system("water_ccecp_ccpvqz").wavefunction_data.geminal_data)
+    j3 = H.wavefunction_data.jastrow_data.jastrow_three_body_data
     H.wavefunction_data.jastrow_data.jastrow_three_body_data = dataclasses.replace(j3, j_matrix=0.02 * np.asarray(j3.j_matrix))
     m = MCMC(H, mcmc_seed=3, num_walkers=32, num_mcmc_per_measurement=16, Dt=2.0, epsilon_AS=0.0)
     m.run(num_mcmc_steps=12)
