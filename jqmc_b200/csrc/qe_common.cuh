@@ -111,6 +111,8 @@ struct qe_engine {
   void* ws = nullptr;
   size_t ws_bytes = 0;
   int64_t launches = 0;
+  double* gemm_ws = nullptr;    // split-K partial products of the general path's GEMM (grow-only)
+  size_t gemm_ws_bytes = 0;
   double* branch_ws = nullptr;  // scratch of qe_lrdmc_branch: rank sums, rank probabilities, cumulative probabilities
   size_t branch_ws_n = 0;
   // optional per-kernel timing (qe_profile): CUDA events recorded on the launch stream around each kernel
@@ -164,6 +166,28 @@ static inline int ensure_ws(qe_engine* h, size_t bytes) {
 // =================================================================================================
 // small device helpers
 // =================================================================================================
+// Fast fp64 reciprocal square root / reciprocal for the O(N_e) pair loops evaluated at EVERY mesh point (Jastrow ratios):
+// single-precision MUFU seed + two Newton steps (relative error ~1e-16, i.e. fp64 round-off), ~10 DFMA-class instructions
+// instead of the ~80 of the IEEE sqrt + divide sequences.  Arguments must lie in the float range (distances, 1 + a d).
+__device__ __forceinline__ double qrsqrt(double x) {
+  double y = (double)rsqrtf((float)x);
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+__device__ __forceinline__ double qrcp(double x) {
+  double y = (double)__frcp_rn((float)x);
+  y = y * fma(-x, y, 2.0);
+  y = y * fma(-x, y, 2.0);
+  return y;
+}
+// |(dx,dy,dz)| ; distances below 1e-15 bohr are clamped (the reference's Jastrow derivatives clamp at 1e-12)
+__device__ __forceinline__ double qdist(double dx, double dy, double dz) {
+  const double r2 = fmax(fma(dx, dx, fma(dy, dy, dz * dz)), 1.0e-30);
+  return r2 * qrsqrt(r2);
+}
+
 // index of the atom with distance-rank `rank` from p (argsort semantics, first index wins ties;
 // jqmc/structure.py:410-426)
 __device__ __forceinline__ int nearest_atom(const double* __restrict__ Rn, int n_atom, double px, double py, double pz,
@@ -171,15 +195,15 @@ __device__ __forceinline__ int nearest_atom(const double* __restrict__ Rn, int n
   if (rank == 0) {
     int best = 0;
     double bd = 1e300;
-    for (int a = 0; a < n_atom; ++a) {
+    for (int a = 0; a < n_atom; ++a) {  // squared distances: one sqrt at the end (same order as the norms)
       const double dx = Rn[3 * a] - px, dy = Rn[3 * a + 1] - py, dz = Rn[3 * a + 2] - pz;
-      const double d = sqrt(dx * dx + dy * dy + dz * dz);
+      const double d = dx * dx + dy * dy + dz * dz;
       if (d < bd) {
         bd = d;
         best = a;
       }
     }
-    if (dist_out) *dist_out = bd;
+    if (dist_out) *dist_out = sqrt(bd);
     return best;
   }
   for (int a = 0; a < n_atom; ++a) {
@@ -208,6 +232,15 @@ __device__ __forceinline__ double j2_f(int type, double a, double d) {
   // jqmc/jastrow_factor.py:1180-1251
   if (type == 1) return d / (2.0 * (1.0 + a * d));
   return (1.0 - qexp(-a * d)) / (2.0 * a);
+}
+// the same functions with the fast reciprocal, `inv2a` = 1 / (2a): used inside the per-mesh-point pair loops
+__device__ __forceinline__ double j1_fq(int type, double a, double inv2a, double A, double c, double d) {
+  if (type == 1) return -A * (1.0 - qexp(-a * c * d)) * inv2a;
+  return -0.5 * A * d * qrcp(fma(a * c, d, 1.0));
+}
+__device__ __forceinline__ double j2_fq(int type, double a, double inv2a, double d) {
+  if (type == 1) return 0.5 * d * qrcp(fma(a, d, 1.0));
+  return (1.0 - qexp(-a * d)) * inv2a;
 }
 
 // d^n for the small integer powers of the ECP radial terms (stored as doubles; TREXIO power + 2, jqmc/coulomb_potential.py:1562-1568)
@@ -324,6 +357,55 @@ __device__ __forceinline__ double jastrow_delta(const SysDev& S, const Pos& pos,
       const double dn_ = sqrt((nx - x) * (nx - x) + (ny - y) * (ny - y) + (nz - z) * (nz - z));
       const double do_ = sqrt((ox - x) * (ox - x) + (oy - y) * (oy - y) + (oz - z) * (oz - z));
       dJ += j2_f(S.j2_type, S.j2_a, dn_) - j2_f(S.j2_type, S.j2_a, do_);
+    }
+  }
+  return dJ;
+}
+
+// The same two functions with the fast reciprocal square root / reciprocal (general path: its mesh kernel is bound by the
+// latency of these pair loops when N_e is large; the register kernels are fp64-issue bound and keep the IEEE sequences)
+template <class Pos>
+__device__ __forceinline__ double jastrow_single_q(const SysDev& S, const Pos& pos, int e, double x, double y, double z) {
+  double J = 0.0;
+  if (S.j1_type) {
+    const double inv2a = 1.0 / (2.0 * S.j1_a);
+    for (int a = 0; a < S.n_atom; ++a) {
+      const double d = qdist(x - S.Rn[3 * a], y - S.Rn[3 * a + 1], z - S.Rn[3 * a + 2]);
+      J += j1_fq(S.j1_type, S.j1_a, inv2a, S.j1_A[a], S.j1_c[a], d);
+    }
+  }
+  if (S.j2_type) {
+    const double inv2a = 1.0 / (2.0 * S.j2_a);
+    for (int j = 0; j < S.n_e; ++j) {
+      if (j == e) continue;
+      double xj, yj, zj;
+      pos.get(j, xj, yj, zj);
+      J += j2_fq(S.j2_type, S.j2_a, inv2a, qdist(x - xj, y - yj, z - zj));
+    }
+  }
+  return J;
+}
+
+template <class Pos>
+__device__ __forceinline__ double jastrow_delta_q(const SysDev& S, const Pos& pos, int e, double ox, double oy, double oz,
+                                                double nx, double ny, double nz) {
+  double dJ = 0.0;
+  if (S.j1_type) {
+    const double inv2a = 1.0 / (2.0 * S.j1_a);
+    for (int a = 0; a < S.n_atom; ++a) {
+      const double X = S.Rn[3 * a], Y = S.Rn[3 * a + 1], Z = S.Rn[3 * a + 2];
+      const double A = S.j1_A[a], c = S.j1_c[a];
+      dJ += j1_fq(S.j1_type, S.j1_a, inv2a, A, c, qdist(nx - X, ny - Y, nz - Z)) -
+            j1_fq(S.j1_type, S.j1_a, inv2a, A, c, qdist(ox - X, oy - Y, oz - Z));
+    }
+  }
+  if (S.j2_type) {
+    const double inv2a = 1.0 / (2.0 * S.j2_a);
+    for (int j = 0; j < S.n_e; ++j) {
+      if (j == e) continue;
+      double x, y, z;
+      pos.get(j, x, y, z);
+      dJ += j2_fq(S.j2_type, S.j2_a, inv2a, qdist(nx - x, ny - y, nz - z)) - j2_fq(S.j2_type, S.j2_a, inv2a, qdist(ox - x, oy - y, oz - z));
     }
   }
   return dJ;

@@ -261,6 +261,10 @@ __device__ __forceinline__ void eval_seg_val_n(const int4* __restrict__ sh, cons
   for (int i = 0; i < NP; ++i) A::val(dx[i], dy[i], dz[i], S[i]);
   for (int s = sb; s < se; ++s) {
     const int4 q = sh[s];
+    // sinks that contract with a per-walker weight vector issue the loads of this shell's weights BEFORE the exponentials
+    // (the loads then overlap the radial part instead of stalling every multiply-add); a no-op for the other sinks
+    double wv[A::NF];
+    sink.template prefetch<A::NF>(q.z, wv);
     double R[NP];
     shell_radial_n<NP>(pr, q.x, q.y, r2, R);
 #pragma unroll
@@ -268,7 +272,7 @@ __device__ __forceinline__ void eval_seg_val_n(const int4* __restrict__ sh, cons
       double v[NP];
 #pragma unroll
       for (int i = 0; i < NP; ++i) v[i] = R[i] * S[i][k];
-      sink.add_n(q.z + k, v);
+      sink.add_nw(q.z + k, v, wv[k]);
     }
   }
 }
@@ -381,6 +385,9 @@ struct SinkMO {
     }
   }
   __device__ __forceinline__ void add_n(int row, const double* __restrict__ v) { add(row, v[0]); }
+  template <int NF>
+  __device__ __forceinline__ void prefetch(int, double*) const {}
+  __device__ __forceinline__ void add_nw(int row, const double* __restrict__ v, double) { add(row, v[0]); }
 };
 // NP points per thread sharing ONE coefficient table (the caller pairs points of the same spin): a row is loaded once
 template <int NMO, int NP>
@@ -406,6 +413,9 @@ struct SinkMOn {
       }
     }
   }
+  template <int NF>
+  __device__ __forceinline__ void prefetch(int, double*) const {}
+  __device__ __forceinline__ void add_nw(int row, const double* __restrict__ v, double) { add_n(row, v); }
 };
 template <int NMO>
 struct SinkMO5 {
@@ -448,6 +458,9 @@ struct SinkStoreAO {
     if (a >= 0) out[(long long)a * n_pts] = v * row_scale[row];
   }
   __device__ __forceinline__ void add_n(int row, const double* __restrict__ v) { add(row, v[0]); }
+  template <int NF>
+  __device__ __forceinline__ void prefetch(int, double*) const {}
+  __device__ __forceinline__ void add_nw(int row, const double* __restrict__ v, double) { add(row, v[0]); }
   __device__ __forceinline__ void add(int row, double v, double gx, double gy, double gz, double lp) {
     const int a = row_ao[row];
     if (a < 0) return;

@@ -817,6 +817,7 @@ extern "C" void qe_destroy(qe_engine* h) {
   h->pool.release();
   if (h->ws) cudaFree(h->ws);
   if (h->branch_ws) cudaFree(h->branch_ws);
+  if (h->gemm_ws) cudaFree(h->gemm_ws);
   delete h;
 }
 

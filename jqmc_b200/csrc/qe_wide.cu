@@ -35,21 +35,26 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 __global__ void __launch_bounds__(128)
 kw_dgemm(int m, long long n, int k, const double* __restrict__ A, int lda, const double* __restrict__ B, long long ldb,
-         double* __restrict__ D, long long ldd, long long sB, long long sD) {
+         double* __restrict__ D, long long ldd, long long sB, long long sD, int ksplit, int kchunk, long long sPart) {
+  // blockIdx.z = batch * ksplit + ks: split ks covers k in [ks*kchunk, (ks+1)*kchunk) and writes its partial product to
+  // D + ks*sPart (ksplit == 1: the product itself); kw_sum_parts adds the partials in a fixed order
   __shared__ double As[GM][GK + 4];
   __shared__ double Bs[GK][GN + 4];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const long long n0 = (long long)blockIdx.x * GN;
   const int m0 = blockIdx.y * GM;
-  B += (long long)blockIdx.z * sB;
-  D += (long long)blockIdx.z * sD;
+  const int ks = blockIdx.z % ksplit, bz = blockIdx.z / ksplit;
+  B += (long long)bz * sB;
+  D += (long long)bz * sD + (long long)ks * sPart;
+  const int kbeg = ks * kchunk;
+  k = min(k, kbeg + kchunk);
   const int g = lane >> 2, t = lane & 3;
   double acc[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  for (int k0 = 0; k0 < k; k0 += GK) {
+  for (int k0 = kbeg; k0 < k; k0 += GK) {
     for (int i = tid; i < GM * GK; i += 128) {
       const int r = i / GK, c = i % GK;
       As[r][c] = (m0 + r < m && k0 + c < k) ? A[(size_t)(m0 + r) * lda + k0 + c] : 0.0;
@@ -98,6 +103,19 @@ __global__ void kw_dgemm_ref(int m, long long n, int k, const double* __restrict
   double s = 0.0;
   for (int kk = 0; kk < k; ++kk) s = fma(A[(size_t)row * lda + kk], B[(long long)kk * ldb + col], s);
   D[(long long)row * ldd + col] = s;
+}
+
+// D[i] = sum_s part[s][i]  (fixed order: deterministic)
+__global__ void kw_sum_parts(long long n, int ksplit, const double* __restrict__ part, double* __restrict__ D, long long rows_n,
+                             long long ldd, long long ncol) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double s = 0.0;
+  for (int i = 0; i < ksplit; ++i) s += part[(long long)i * n + t];
+  // t = (batch*m + row) * ncol + col  ->  D[batch*sD + row*ldd + col] with sD = rows_n (elements per batch in D)
+  const long long col = t % ncol, br = t / ncol;
+  (void)rows_n;
+  D[br * ldd + col] = s;
 }
 
 // per-walker product  D[i][j][w] = sum_a X[a][i][w] Y[a][j][w]  with arbitrary (element) strides; thread = (i, j, w)
@@ -173,6 +191,9 @@ struct SinkRows {
   size_t sr, sq;
   __device__ __forceinline__ void add(int row, double v) { o[row * sr] = v; }
   __device__ __forceinline__ void add_n(int row, const double* __restrict__ v) { o[row * sr] = v[0]; }
+  template <int NF>
+  __device__ __forceinline__ void prefetch(int, double*) const {}
+  __device__ __forceinline__ void add_nw(int row, const double* __restrict__ v, double) { o[row * sr] = v[0]; }
   __device__ __forceinline__ void add(int row, double v, double gx, double gy, double gz, double lp) {
     double* p = o + row * sr;
     p[0] = v;
@@ -215,6 +236,15 @@ struct SinkDotN {
 #pragma unroll
     for (int i = 0; i < NP; ++i) acc[i] = fma(v[i], wv, acc[i]);
   }
+  template <int NF>
+  __device__ __forceinline__ void prefetch(int row0, double* __restrict__ w) const {
+#pragma unroll
+    for (int k = 0; k < NF; ++k) w[k] = W[(row0 + k) * sr];
+  }
+  __device__ __forceinline__ void add_nw(int, const double* __restrict__ v, double wv) {
+#pragma unroll
+    for (int i = 0; i < NP; ++i) acc[i] = fma(v[i], wv, acc[i]);
+  }
 };
 
 // =================================================================================================
@@ -231,6 +261,7 @@ struct MeshArgs {
   const double* Wrow;   // [n_row][Ne][w]
   const double* gJrow;  // [nj_row][Ne][w]
   const double* cJ;     // [Ne][w]  chi(r_e) . g_e
+  const double* el;     // [Ne][8][w]: slot 7 = J1+J2 terms of electron e at its current position (kw_electron)
   double* p;
   double* sj;
 };
@@ -278,7 +309,7 @@ kw_mesh(BasisDev B, BasisDev BJ, int has_j3, SysDev S, MeshArgs P) {
   eval_val_n<CART, QE_LMAX, 2>(B.g, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);
   double jr[2] = {1.0, 1.0};
   if (!P.det_only) {
-    const double jold = jastrow_single(S, pos, e, x, y, z);
+    const double jold = P.el[((size_t)e * 8 + 7) * nw + w];
     double d3[2] = {0.0, 0.0};
     if (has_j3) {
       SinkDotN<2> sj3;
@@ -289,7 +320,7 @@ kw_mesh(BasisDev B, BasisDev BJ, int has_j3, SysDev S, MeshArgs P) {
       d3[1] = sj3.acc[1] - c0;
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) jr[i] = qexp(jastrow_single(S, pos, e, px[i], py[i], pz[i]) - jold + d3[i]);
+    for (int i = 0; i < 2; ++i) jr[i] = qexp(jastrow_single_q(S, pos, e, px[i], py[i], pz[i]) - jold + d3[i]);
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -326,7 +357,7 @@ kw_move_ratios(BasisDev B, BasisDev BJ, int has_j3, SysDev S, int nw, const doub
   if (jas_ratio) {
     double x, y, z;
     pos.get(e, x, y, z);
-    double d = jastrow_single(S, pos, e, px[0], py[0], pz[0]) - jastrow_single(S, pos, e, x, y, z);
+    double d = jastrow_single_q(S, pos, e, px[0], py[0], pz[0]) - jastrow_single_q(S, pos, e, x, y, z);
     if (has_j3) {
       SinkDotN<1> sj3;
       sj3.init(gJrow + (size_t)e * nw + w, (size_t)Ne * nw);
@@ -479,6 +510,7 @@ kw_electron(SysDev S, ElecArgs P) {
   o[(size_t)2 * nw] = eid;
   o[(size_t)3 * nw] = loc;
   o[(size_t)4 * nw] = ee;
+  o[(size_t)7 * nw] = jastrow_single_q(S, pos, e, x, y, z);  // shared by all mesh points of this electron
 }
 
 // e_L = sum_e T_e + V_bare + V_ion_ion + V_ecp_local + sum_pts V_nl   (jqmc/hamiltonians.py:225-290); thread = walker
@@ -657,26 +689,40 @@ struct SelectArgs {
   int* es;          // [w] selected electron
   double* pnew;     // [3][w]
 };
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 kw_lrdmc_select(SysDev S, SelectArgs P) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= P.nw) return;
+  // block = 32 walkers (x) x 8 (y).  Each y owns a contiguous block of electrons (their 6 kinetic elements) and a contiguous
+  // block of ECP points: fixed-node split and partial sums in parallel, then the move is located by chunk sums of the
+  // normalised probabilities (vector order [kinetic mesh, ECP mesh]) and a sequential scan inside the chunk.
+  constexpr int TY = 8;
+  __shared__ double s_red[7][TY][32];
+  __shared__ double s_chunk[2 * TY][32];
+  const int lane = threadIdx.x, ty = threadIdx.y;
   const int nw = P.nw, Ne = S.n_e, n_kin = P.n_kin, n_ecp = P.n_ecp, NPT = n_kin + n_ecp;
+  const int wq = blockIdx.x * 32 + lane;
+  const bool live = wq < nw;
+  const int w = live ? wq : nw - 1;  // dead lanes shadow the last walker (no stores)
   const double a2 = P.alat * P.alat;
 #define EL(e, i) P.el[((size_t)(e) * 8 + (i)) * nw + w]
 #define PP(k) P.p[(size_t)(k) * nw + w]
-  double sum_kinFN = 0, SP_kin = 0, sum_opt = 0, ee = 0, loc = 0;
-  for (int e = 0; e < Ne; ++e) {
+  const int EB = (Ne + TY - 1) / TY, e0 = min(Ne, ty * EB), e1 = min(Ne, e0 + EB);
+  const int PB = (n_ecp + TY - 1) / TY, q0 = min(n_ecp, ty * PB), q1 = min(n_ecp, q0 + PB);
+  double sum_kinFN = 0, SP_kin = 0, sum_opt = 0, ee = 0, loc = 0, sum_eFN = 0, SP_e = 0;
+  for (int e = e0; e < e1; ++e) {
+    double v6[6];
+#pragma unroll
+    for (int s6 = 0; s6 < 6; ++s6) v6[s6] = PP(6 * e + s6);
     bool flip = false;
     double nd = 0, kinFN = 0, kinSP = 0;
+#pragma unroll
     for (int s6 = 0; s6 < 6; ++s6) {
-      const double v = PP(6 * e + s6);
+      const double v = v6[s6];
       flip = flip || (v >= 0.0);
       nd += v + 1.0 / (4.0 * a2);
       const double fn = fmin(v, 0.0);
       kinFN += fn;
       kinSP += fmax(v, 0.0);
-      PP(6 * e + s6) = fn;
+      if (live) PP(6 * e + s6) = fn;
     }
     const double zv = EL(e, 1) + EL(e, 0) - nd;
     const double eib = S.ecp_flag ? EL(e, 1) : EL(e, 2);
@@ -686,30 +732,67 @@ kw_lrdmc_select(SysDev S, SelectArgs P) {
     ee += EL(e, 4);
     loc += EL(e, 3);
   }
-  double sum_eFN = 0, SP_e = 0;
-  for (int k = 0; k < n_ecp; ++k) {
+  for (int k = q0; k < q1; ++k) {
     const double v = PP(n_kin + k);
     double fn = fmin(v, 0.0);
     if (P.dlt) fn *= P.sj[(size_t)k * nw + w];
-    PP(n_kin + k) = fn;
+    if (live) PP(n_kin + k) = fn;
     sum_eFN += fn;
     SP_e += fmax(v, 0.0);
   }
+  s_red[0][ty][lane] = sum_kinFN;
+  s_red[1][ty][lane] = SP_kin;
+  s_red[2][ty][lane] = sum_opt;
+  s_red[3][ty][lane] = ee;
+  s_red[4][ty][lane] = loc;
+  s_red[5][ty][lane] = sum_eFN;
+  s_red[6][ty][lane] = SP_e;
+  __syncthreads();
+  double tot7[7];
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    double t = 0;
+    for (int y = 0; y < TY; ++y) t += s_red[q][y][lane];
+    tot7[q] = t;
+  }
   const double diag_kin = 3.0 / (2.0 * a2) * Ne;
-  const double disc_bare = ee + S.v_ion_ion + sum_opt;
-  const double nondiag = sum_kinFN + sum_eFN;
-  const double diag = S.ecp_flag ? diag_kin + disc_bare + loc + SP_kin + SP_e : diag_kin + disc_bare + SP_kin;
-  P.V_diag[w] = diag;
-  P.V_nondiag[w] = nondiag;
+  const double disc_bare = tot7[3] + S.v_ion_ion + tot7[2];
+  const double nondiag = tot7[0] + tot7[5];
+  const double diag = S.ecp_flag ? diag_kin + disc_bare + tot7[4] + tot7[1] + tot7[6] : diag_kin + disc_bare + tot7[1];
+  if (ty == 0 && live) {
+    P.V_diag[w] = diag;
+    P.V_nondiag[w] = nondiag;
+  }
   if (P.mode != 0) return;
-  const double b_x = 1.0 / (diag - P.E_scf) * (-nondiag);
-  P.wL[w] *= b_x;
-  double tot = 0;
-  for (int k = 0; k < NPT; ++k) tot += PP(k);
+  if (ty == 0 && live) P.wL[w] *= 1.0 / (diag - P.E_scf) * (-nondiag);
+  const double tot = nondiag;  // sum of all fixed-node elements = normalisation of the move probabilities
+  {
+    double ck = 0, ce = 0;
+    for (int k = 6 * e0; k < 6 * e1; ++k) ck += PP(k) / tot;
+    for (int k = q0; k < q1; ++k) ce += PP(n_kin + k) / tot;
+    s_chunk[ty][lane] = ck;
+    s_chunk[TY + ty][lane] = ce;
+  }
+  __syncthreads();
+  if (ty != 0) return;
   const double u = P.ru[(size_t)P.it * nw + w];
-  int ksel = NPT - 1;
+  // first chunk whose cumulative probability reaches u, then the first element inside it (searchsorted 'left',
+  // jqmc/jqmc_gfmc.py:5057-5062); the scan continues past the chunk if round-off moved the crossing
   double c = 0;
-  for (int k = 0; k < NPT; ++k) {
+  int kstart = 0;
+  for (int ci = 0; ci < 2 * TY; ++ci) {
+    const double cs = s_chunk[ci][lane];
+    const int y = ci < TY ? ci : ci - TY;
+    const int kb = ci < TY ? 6 * min(Ne, y * EB) : n_kin + min(n_ecp, y * PB);
+    if (c + cs >= u) {
+      kstart = kb;
+      break;
+    }
+    c += cs;
+    kstart = ci < TY ? 6 * min(Ne, min(Ne, y * EB) + EB) : n_kin + min(n_ecp, min(n_ecp, y * PB) + PB);
+  }
+  int ksel = NPT - 1;
+  for (int k = kstart; k < NPT; ++k) {
     c += PP(k) / tot;
     if (c >= u) {
       ksel = k;
@@ -737,10 +820,12 @@ kw_lrdmc_select(SysDev S, SelectArgs P) {
     pos.get(e, x, y, z);
     ecp_point(S, rt, x, y, z, nn, k, px, py, pz, dummy, false);
   }
-  P.es[w] = e;
-  P.pnew[w] = px;
-  P.pnew[(size_t)nw + w] = py;
-  P.pnew[(size_t)2 * nw + w] = pz;
+  if (live) {
+    P.es[w] = e;
+    P.pnew[w] = px;
+    P.pnew[(size_t)nw + w] = py;
+    P.pnew[(size_t)2 * nw + w] = pz;
+  }
 #undef EL
 #undef PP
 }
@@ -954,7 +1039,7 @@ __global__ void kw_mc_propose(SysDev S, int nw, int it, double Dt, const double*
   const double f_p = 1.0 / (Zc * Zc) * (1.0 + Zc * Zc * dist) / (1.0 + dist);
   const double dd = (nx - ox) * (nx - ox) + (ny - oy) * (ny - oy) + (nz - oz) * (nz - oz);
   Tr[w] = (f_l / f_p) * qexp(-dd * (1.0 / (2.0 * f_p * f_p * Dt * Dt) - 1.0 / (2.0 * f_l * f_l * Dt * Dt)));
-  J12[w] = jastrow_delta(S, pos, ke, ox, oy, oz, nx, ny, nz);
+  J12[w] = jastrow_delta_q(S, pos, ke, ox, oy, oz, nx, ny, nz);
   es[w] = ke;
   pnew[w] = nx;
   pnew[(size_t)nw + w] = ny;
@@ -1010,15 +1095,47 @@ bool g_gemm_ref = false;  // qe_set_path debugging: plain DFMA GEMM instead of t
 int w_gemm(qe_engine* h, cudaStream_t st, int m, long long n, int k, const double* A, int lda, const double* B, long long ldb,
            double* D, long long ldd, int batch = 1, long long sB = 0, long long sD = 0) {
   if (m <= 0 || n <= 0 || k <= 0) return QE_OK;
-  LaunchScope ls_(h, K_W_GEMM, st);
   if (g_gemm_ref) {
+    LaunchScope ls_(h, K_W_GEMM, st);
     dim3 grid(nblk(n, 128), m, batch);
     kw_dgemm_ref<<<grid, 128, 0, st>>>(m, n, k, A, lda, B, ldb, D, ldd, sB, sD);
-  } else {
-    dim3 grid(nblk(n, GN), (m + GM - 1) / GM, batch);
-    kw_dgemm<<<grid, 128, 0, st>>>(m, n, k, A, lda, B, ldb, D, ldd, sB, sD);
+    CHECK_LAUNCH();
+    return QE_OK;
   }
-  CHECK_LAUNCH();
+  const long long ctas = (long long)nblk(n, GN) * ((m + GM - 1) / GM) * batch;
+  // few output tiles but a long contraction (one new point per walker against ~1000 AO rows): split k over CTAs so that the
+  // grid fills the GPU; partial products go to a scratch buffer and are summed in a fixed order.  Needs sD == m*ldd (dense batches).
+  int ksplit = 1;
+  if (ctas < 148 && k >= 256 && (batch == 1 || sD == (long long)m * ldd)) ksplit = (int)std::min<long long>((k + 63) / 64, std::max<long long>(1, 592 / ctas));
+  if (ksplit <= 1) {
+    LaunchScope ls_(h, K_W_GEMM, st);
+    dim3 grid(nblk(n, GN), (m + GM - 1) / GM, batch);
+    kw_dgemm<<<grid, 128, 0, st>>>(m, n, k, A, lda, B, ldb, D, ldd, sB, sD, 1, k, 0);
+    CHECK_LAUNCH();
+    return QE_OK;
+  }
+  const int kchunk = (((k + ksplit - 1) / ksplit) + GK - 1) / GK * GK;
+  ksplit = (k + kchunk - 1) / kchunk;
+  const long long per = (long long)batch * m * n;
+  const size_t need = (size_t)per * ksplit * 8;
+  if (need > h->gemm_ws_bytes) {
+    if (h->gemm_ws) cudaFree(h->gemm_ws);
+    h->gemm_ws = nullptr;
+    h->gemm_ws_bytes = 0;
+    CUDA_TRY(cudaMalloc((void**)&h->gemm_ws, need));
+    h->gemm_ws_bytes = need;
+  }
+  {
+    LaunchScope ls_(h, K_W_GEMM, st);
+    dim3 grid(nblk(n, GN), (m + GM - 1) / GM, batch * ksplit);
+    kw_dgemm<<<grid, 128, 0, st>>>(m, n, k, A, lda, B, ldb, h->gemm_ws, n, sB, (long long)m * n, ksplit, kchunk, per);
+    CHECK_LAUNCH();
+  }
+  {
+    LaunchScope ls_(h, K_W_GEMM, st);
+    kw_sum_parts<<<nblk(per, 256), 256, 0, st>>>(per, ksplit, h->gemm_ws, D, 0, ldd, n);
+    CHECK_LAUNCH();
+  }
   return QE_OK;
 }
 int w_bmm(qe_engine* h, cudaStream_t st, int ni, int nj, int na, int nw, const double* X, long long sxa, long long sxi, const double* Y,
@@ -1274,7 +1391,7 @@ int wide_geminal_init(qe_engine* h, int nw, const double* r_up, const double* r_
   TRY(build_G(h, st, X, X.Gs));
   TRY(launch_inverse(h, st, nw, X.Gs, nullptr, G, Ginv, ln_psi, sign));
   if (ln_psi) {
-    MISC(st, kw_add_jastrow<<<nblk(nw, 128), 128, 0, st>>>(S, nw, T.j3, T.nj, X.rs, T.j1v, X.Chi, X.U, ln_psi));
+    MISC(st, kw_add_jastrow<<<nblk(nw, 32), 32, 0, st>>>(S, nw, T.j3, T.nj, X.rs, T.j1v, X.Chi, X.U, ln_psi));
   }
   return QE_OK;
 }
@@ -1310,10 +1427,10 @@ int wide_local_energy(qe_engine* h, int nw, const double* r_up, const double* r_
   }
   CHECK_LAUNCH();
   if (n_ecp > 0) {
-    MeshArgs M{nw, 0, n_ecp, 0, 0, 1.0, X.rs, RTs, X.Wrow, X.gJrow, X.cJ, p, nullptr};
+    MeshArgs M{nw, 0, n_ecp, 0, 0, 1.0, X.rs, RTs, X.Wrow, X.gJrow, X.cJ, el, p, nullptr};
     TRY(launch_mesh(h, st, M));
   }
-  MISC(st, kw_reduce_eL<<<nblk(nw, 128), 128, 0, st>>>(S, nw, n_ecp, el, p, e_L, T_elem, V_parts));
+  MISC(st, kw_reduce_eL<<<nblk(nw, 32), 32, 0, st>>>(S, nw, n_ecp, el, p, e_L, T_elem, V_parts));
   return QE_OK;
 }
 
@@ -1396,12 +1513,12 @@ int wide_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, uint32_t*
   MISC(st, kw_fill_i<<<nblk(nw, 256), 256, 0, st>>>(nw, 0, acc));
   MISC(st, kw_fill_i<<<nblk(nw, 256), 256, 0, st>>>(nw, 0, rej));
   if (epsilon_AS > 0.0) {
-    MISC(st, kw_as_factor<<<nblk(nw, 128), 128, 0, st>>>(N, nw, X.Gs, X.Gi, R_AS));
+    MISC(st, kw_as_factor<<<nblk(nw, 32), 32, 0, st>>>(N, nw, X.Gs, X.Gi, R_AS));
   } else {
     MISC(st, kw_fill<<<nblk(nw, 256), 256, 0, st>>>(nw, 1.0, R_AS));
   }
   for (int it = 0; it < nmpm; ++it) {
-    MISC(st, kw_mc_propose<<<nblk(nw, 128), 128, 0, st>>>(S, nw, it, Dt, X.rs, rsel, raxis, rg, es, pnew, Tr, J12));
+    MISC(st, kw_mc_propose<<<nblk(nw, 32), 32, 0, st>>>(S, nw, it, Dt, X.rs, rsel, raxis, rg, es, pnew, Tr, J12));
     TRY(eval_newpoint(h, st, nw, 1, pnew, P));
     MoveArgs A{};
     A.nw = nw; A.no = T.no; A.nj = T.nj; A.has_j3 = T.j3; A.NQ = 1; A.decide = 1; A.it = it;
@@ -1459,18 +1576,18 @@ int wide_lrdmc(qe_engine* h, int mode, int nw, double* w, double* r_up, double* 
   for (int it = 0; it < n_it; ++it) {
     if (mode == 0) RTcur = rRT + (size_t)it * 9 * nw;  // rRT[(it*9+c)][w]
     TRY(build_weights(h, st, X));
-    MeshArgs M{nw, n_kin, n_ecp, non_local_move, 0, alat, X.rs, RTcur, X.Wrow, X.gJrow, X.cJ, p, sj};
-    TRY(launch_mesh(h, st, M));
     ElecArgs E{nw, T.no, T.nj, T.j3, alat, X.rs, X.Phi, X.Worb, X.Chi, X.gJ, el};
     {
       LaunchScope ls_(h, K_W_ELEC, st);
       kw_electron<<<nblk((long long)Ne * nw, 128), 128, 0, st>>>(S, E);
     }
     CHECK_LAUNCH();
+    MeshArgs M{nw, n_kin, n_ecp, non_local_move, 0, alat, X.rs, RTcur, X.Wrow, X.gJrow, X.cJ, el, p, sj};
+    TRY(launch_mesh(h, st, M));
     SelectArgs Q{nw, n_kin, n_ecp, non_local_move, mode, it, alat, E_scf, X.rs, RTcur, p, sj, el, w, ru, V_diag, V_nondiag, es, pnew};
     {
       LaunchScope ls_(h, K_W_SELECT, st);
-      kw_lrdmc_select<<<nblk(nw, 128), 128, 0, st>>>(S, Q);
+      kw_lrdmc_select<<<nblk(nw, 32), dim3(32, 8), 0, st>>>(S, Q);
     }
     CHECK_LAUNCH();
     if (mode != 0) break;

@@ -458,7 +458,10 @@ def test_wide_drivers_run_jagp_j3():
     # the Hartree-Fock geminal in AO form (no random perturbation) and a gentle J3, so that the energies stay physical
     H.wavefunction_data.geminal_data = Geminal_data.convert_from_MOs_to_AOs(load_system("water_ccecp_ccpvqz").wavefunction_data.geminal_data)
     j3 = H.wavefunction_data.jastrow_data.jastrow_three_body_data
-    H.wavefunction_data.jastrow_data.jastrow_three_body_data = dataclasses.replace(j3, j_matrix=0.02 * np.asarray(j3.j_matrix))
+    H.wavefunction_data.jastrow_data = Jastrow_data(
+        jastrow_two_body_data=Jastrow_two_body_data(jastrow_2b_param=1.0),
+        jastrow_three_body_data=dataclasses.replace(j3, j_matrix=0.02 * np.asarray(j3.j_matrix)),
+    )
     m = MCMC(H, mcmc_seed=3, num_walkers=32, num_mcmc_per_measurement=16, Dt=2.0, epsilon_AS=0.0)
     m.run(num_mcmc_steps=12)
     assert m.e_L.shape == (12, 32) and np.all(np.isfinite(m.e_L))
