@@ -9,7 +9,7 @@ polynomial); ``randint`` (int64) = two 64-bit draws combined modulo the span.
 
 JAX is a third-party dependency that is absent from /root/reference and from this image, so this
 file follows JAX's published algorithm.  The Threefry block function is pinned against the
-Random123 known-answer vectors (tests/test_rng.py); the derived stream is "parity unpinned".
+Random123 known-answer vectors (tests/test_rng.py); the derived stream is pinned only through the scalar-draw known answers of tests/test_rng.py ("parity unpinned" for the 64-bit draws).
 
 Call sites in the reference: jqmc/jqmc_mcmc.py:4322-4367, 4499-4500, 4232-4233;
 jqmc/jqmc_gfmc.py:5275-5283, 4813-4815, 5059.

@@ -21,6 +21,37 @@ def test_legacy_split_known_answer():
     assert [a[0], b[0], a[1], b[1]] == [4146024105, 967050713, 2718843009, 1272950319]
 
 
+def _normal_f32(key, fold):
+    """jax.random.normal(key, ()) in float32 from the restated pieces: one Threefry block on counter (0, 0), 32 random bits
+    = fold(hi, lo), 23-bit mantissa fill, XLA's single-precision erf_inv polynomial (Giles)."""
+    f32 = np.float32
+    hi, lo = R.threefry2x32(key[0], key[1], 0, 0)
+    u = np.uint32((fold(hi, lo) >> 9) | 0x3F800000).view(f32) - f32(1)
+    m = np.nextafter(f32(-1), f32(0))
+    x = max(m, f32(u * f32(f32(1) - m) + m))
+    w = f32(-np.log(f32((f32(1) - x) * (f32(1) + x))))
+    if w < f32(5):
+        w = f32(w - f32(2.5))
+        cs = [2.81022636e-08, 3.43273939e-07, -3.5233877e-06, -4.39150654e-06, 0.00021858087, -0.00125372503, -0.00417768164, 0.246640727, 1.50140941]
+    else:
+        w = f32(np.sqrt(w) - f32(3))
+        cs = [-0.000200214257, 0.000100950558, 0.00134934322, -0.00367342844, 0.00573950773, -0.0076224613, 0.00943887047, 1.00167406, 2.83297682]
+    p = f32(cs[0])
+    for c in cs[1:]:
+        p = f32(f32(c) + f32(p * w))
+    return float(f32(np.sqrt(f32(2))) * f32(p * x))
+
+
+def test_scalar_draw_known_answers_from_jax_documentation():
+    """Known answers printed in the JAX documentation pin the key layout (PRNGKey(seed) = [0, seed]), the counter of a scalar
+    draw ((0, 0)) and the partitionable bit layout: `random.normal(random.key(42))` = -0.028304616 (current docs,
+    jax_threefry_partitionable=True: 32 bits = hi ^ lo); the pre-0.5 docs print -0.18471177 for PRNGKey(42) and -0.20584226
+    for PRNGKey(0) (32 bits = first output word)."""
+    np.testing.assert_allclose(_normal_f32(R.PRNGKey(42), lambda h, l: h ^ l), -0.028304616, rtol=2e-7)
+    np.testing.assert_allclose(_normal_f32(R.PRNGKey(42), lambda h, l: h), -0.18471177, rtol=2e-7)
+    np.testing.assert_allclose(_normal_f32(R.PRNGKey(0), lambda h, l: h), -0.20584226, rtol=2e-7)
+
+
 def test_host_split_matches_oracle():
     key = rng_host.PRNGKey(34456 * 3)
     assert tuple(int(x) for x in key) == R.PRNGKey(34456 * 3)
