@@ -404,6 +404,27 @@ def test_wide_lrdmc_projection_trajectory(case, nlm, E_scf, nmpm):
         np.testing.assert_allclose(Gi[i], oGi, rtol=1e-6, atol=1e-8 * np.abs(oGi).max())
 
 
+@pytest.mark.parametrize("name", ["w_2b_3b_w_ecp", "w_2b_1b3b_w_ecp", "w_1b_2b_1b3b_ae"])
+def test_wide_turborvb_three_body_jastrow_known_answers(name):
+    """The GPU path reproduces the TurboRVB known answers of the reference's J3 tests directly
+    (tests/test_comparison_with_turborvb_ECP.py:376-416, 518-558; _AE.py:163-271): WF ratio^2 of the golden move through the
+    move-ratio entry, kinetic energy and potential through the local-energy entry."""
+    from jqmc_b200.engine import WalkerEngine
+    from tests.conftest import turbo_j3_case
+
+    H, up, dn, new_up, new_dn, spin, idx, ratio_ref, kin_ref, v_ref = turbo_j3_case(name)
+    eng = WalkerEngine(H)
+    G0, Ginv0 = eng.geminal_inv_batched(up[None], dn[None])
+    e = idx if spin == "up" else len(up) + idx
+    new = (new_up if spin == "up" else new_dn)[idx]
+    dr, jr = eng.move_ratios(up[None], dn[None], Ginv0, [e], np.array(new)[None, None, :])
+    np.testing.assert_almost_equal(((dr * jr) ** 2).item(), ratio_ref, decimal=6)
+    G, Ginv = eng.geminal_inv_batched(new_up[None], new_dn[None])
+    e_L, T, V = eng.e_L_fast(new_up[None], new_dn[None], np.eye(3)[None], Ginv, return_parts=True)
+    np.testing.assert_almost_equal(T.sum().item(), kin_ref, decimal=6)
+    np.testing.assert_almost_equal(V[0, :3].sum().item(), v_ref, decimal=5 if H.coulomb_potential_data.ecp_flag else 2)
+
+
 def test_wide_equals_register_kernels_at_scale():
     """water JSD + J2, 1000 walkers (not a multiple of any tile): the general path and the register/shared-memory kernels give
     the same e_L, the same Metropolis decisions and the same LRDMC moves; the tensor-core GEMM equals the plain DFMA GEMM."""

@@ -160,3 +160,24 @@ def test_ecp_mesh_layout(water):
     np.testing.assert_allclose(s, v.sum())
     # first 24 configurations move up electrons only
     assert np.all(md[:24] == r_dn) and np.all(mu[24:] == r_up)
+
+
+@pytest.mark.parametrize("name", ["w_2b_3b_w_ecp", "w_2b_1b3b_w_ecp", "w_1b_2b_1b3b_ae"])
+def test_turborvb_three_body_jastrow_known_answers(name):
+    """The J3 (and J1) restatement against the TurboRVB numbers of the reference's tests
+    (tests/test_comparison_with_turborvb_ECP.py:376-416, 518-558; tests/test_comparison_with_turborvb_AE.py:163-271), with
+    the Jastrow factors recovered from the TurboRVB wavefunction files (tools/turbo_jastrow.py).  Reference tolerances."""
+    from tests.conftest import turbo_j3_case
+
+    H, up, dn, new_up, new_dn, spin, idx, ratio_ref, kin_ref, v_ref = turbo_j3_case(name)
+    wf = H.wavefunction_data
+    ratio = (P.evaluate_wavefunction(wf, new_up, new_dn) / P.evaluate_wavefunction(wf, up, dn)) ** 2
+    np.testing.assert_almost_equal(ratio, ratio_ref, decimal=6)
+    np.testing.assert_almost_equal(P.compute_kinetic_energy(wf, new_up, new_dn), kin_ref, decimal=6)
+    V = P.compute_coulomb_potential(H.coulomb_potential_data, wf, new_up, new_dn, RT=np.eye(3), NN=1, Nv=6)
+    np.testing.assert_almost_equal(V, v_ref, decimal=5 if H.coulomb_potential_data.ecp_flag else 2)
+    # incremental Jastrow ratio == brute force (reference test pattern B for a17)
+    new = (new_up if spin == "up" else new_dn)[idx]
+    jr = P.jastrow_ratio(wf.jastrow_data, up, dn, spin == "up", idx, new)
+    dr = P.wf_ratio_brute_force(wf, up, dn, spin == "up", idx, new, det_only=True)
+    np.testing.assert_allclose((jr * dr) ** 2, ratio, rtol=1e-11)

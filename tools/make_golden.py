@@ -23,6 +23,7 @@ FILES = [
     "N_ae_ccpvdz_cart.h5",
     "N2_ecp_ccpvtz_cart.h5",
     "H_ecp_ccpvqz.h5",
+    "H2_ae_ccpvqz.h5",
 ]
 
 
