@@ -120,3 +120,26 @@ def turbo_j3_case(name):
     new_up, new_dn = up.copy(), dn.copy()
     (new_up if spin == "up" else new_dn)[idx] = new
     return H, up, dn, new_up, new_dn, spin, idx, ratio, kin, vpot + vpotoff
+
+
+# The "full" TurboRVB known-answer case of the reference (tests/test_comparison_with_turborvb_ECP.py:660-945): one Metropolis
+# proposal on water ccECP with J2 + J1-part-of-J3, Dt = 2, epsilon_AS = 0.3.
+TURBO_FULL = dict(
+    old_up=[[-1.13450385875760, -0.698914730480577, -6.290951981744008e-003], [-2.25378719009775, 0.693895756460611, -4.612006323250584e-002],
+            [-0.753191857352684, 0.314330338959413, 0.456739833308641], [-1.60902246286275, 0.499927465264998, 0.700105816369930]],
+    old_dn=[[-1.52590493546481, -1.13601932859996, 0.586518269898014], [0.635659512640246, 0.398999201990364, -0.745191606127732],
+            [-2.00590358216444, -0.465069404417879, 0.360171216755478], [-0.302866379660751, -0.890252305196045, 0.345597836490454]],
+    new_up2=[-0.753191857352684, -1.183650619518406e-002, 0.456739833308641],
+    fa=0.470249568592385, fb=0.437344721251066, T_ratio=1.06518922117014, final_ratio=0.901584512996174,
+    WF_ratio=0.846407844801284, kinc=13.8637480286375, vpot=-30.808883190726, vpotoff=0.168465630163985,
+    R_AS_old=0.124245223553222, R_AS_new=0.116703654039403, reweight=0.151330476290540,
+    F_old=53823.3438428566, S_old=4.833741852724715e-003, F_new=54231.8526090902, S_new=5.669181330133306e-003,
+    geminal_old_T=[[0.186887184114679, 7.221020612173907e-003, 2.919097229181558e-002, 5.283664938570871e-002],
+                   [2.711743127945612e-002, -1.872067172512451e-002, 5.968147400894821e-002, -1.363982711796792e-002],
+                   [0.196787090743597, 9.308561211374290e-002, 5.042625023653007e-003, 0.135256480405370],
+                   [0.152575006966341, -3.569426461507245e-002, 9.441528784169728e-002, 1.156481954187638e-002]],
+    geminal_new_T=[[0.186887184114679, 7.221020612173907e-03, 7.892154586169434e-02, 5.283664938570871e-02],
+                   [2.711743127945612e-02, -1.872067172512451e-02, 6.631227501216763e-02, -1.363982711796792e-02],
+                   [0.196787090743597, 9.308561211374290e-02, 4.145830624511430e-02, 0.135256480405370],
+                   [0.152575006966341, -3.569426461507245e-02, 0.140717058457383, 1.156481954187638e-02]],
+)  # fmt: skip

@@ -425,6 +425,35 @@ def test_wide_turborvb_three_body_jastrow_known_answers(name):
     np.testing.assert_almost_equal(V[0, :3].sum().item(), v_ref, decimal=5 if H.coulomb_potential_data.ecp_flag else 2)
 
 
+def test_wide_turborvb_full_metropolis_known_answers():
+    """tests/test_comparison_with_turborvb_ECP.py:660-945 through the engine: geminal before / after the golden move, AS
+    factors, WF ratio^2 (x AS regularisation, epsilon = 0.3), kinetic energy and potential at the new configuration."""
+    from jqmc_b200.engine import WalkerEngine
+    from tests.conftest import TURBO_FULL as T, load_turbo_jastrow
+
+    H = copy.deepcopy(load_system("water_ccecp_ccpvqz"))
+    H.wavefunction_data.jastrow_data = load_turbo_jastrow("w_2b_1b3b_w_ecp", H.structure_data)
+    eng = WalkerEngine(H)
+    up, dn = np.array(T["old_up"]), np.array(T["old_dn"])
+    new_up = up.copy()
+    new_up[2] = T["new_up2"]
+    G0, Gi0 = eng.geminal_inv_batched(up[None], dn[None])
+    G1, Gi1 = eng.geminal_inv_batched(new_up[None], dn[None])
+    np.testing.assert_almost_equal(G0[0].cpu().numpy(), np.array(T["geminal_old_T"]).T, decimal=6)
+    np.testing.assert_almost_equal(G1[0].cpu().numpy(), np.array(T["geminal_new_T"]).T, decimal=6)
+    R0, R1 = eng.as_reg_fast(G0, Gi0).item(), eng.as_reg_fast(G1, Gi1).item()
+    np.testing.assert_almost_equal(R0, T["R_AS_old"], decimal=6)
+    np.testing.assert_almost_equal(R1, T["R_AS_new"], decimal=6)
+    dr, jr = eng.move_ratios(up[None], dn[None], Gi0, [2], np.array(T["new_up2"])[None, None, :])
+    eps = 0.30
+    ratio = ((dr * jr) ** 2).item() * ((max(R1, eps) / R1) / (max(R0, eps) / R0)) ** 2
+    np.testing.assert_almost_equal(ratio, T["WF_ratio"], decimal=6)
+    np.testing.assert_almost_equal(ratio * T["T_ratio"], T["final_ratio"], decimal=6)
+    e_L, Tk, V = eng.e_L_fast(new_up[None], dn[None], np.eye(3)[None], Gi1, return_parts=True)
+    np.testing.assert_almost_equal(Tk.sum().item(), T["kinc"], decimal=6)
+    np.testing.assert_almost_equal(V[0, :3].sum().item(), T["vpot"] + T["vpotoff"], decimal=5)
+
+
 def test_wide_equals_register_kernels_at_scale():
     """water JSD + J2, 1000 walkers (not a multiple of any tile): the general path and the register/shared-memory kernels give
     the same e_L, the same Metropolis decisions and the same LRDMC moves; the tensor-core GEMM equals the plain DFMA GEMM."""

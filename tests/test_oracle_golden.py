@@ -181,3 +181,43 @@ def test_turborvb_three_body_jastrow_known_answers(name):
     jr = P.jastrow_ratio(wf.jastrow_data, up, dn, spin == "up", idx, new)
     dr = P.wf_ratio_brute_force(wf, up, dn, spin == "up", idx, new, det_only=True)
     np.testing.assert_allclose((jr * dr) ** 2, ratio, rtol=1e-11)
+
+
+def test_turborvb_full_metropolis_known_answers():
+    """tests/test_comparison_with_turborvb_ECP.py:660-945: proposal factors f_a, f_b, T_ratio, geminal matrices before / after
+    the move, AS regularisation (S, F, R_AS with epsilon = 0.3), regularised WF ratio^2, final acceptance ratio, kinetic
+    energy and potential -- the arithmetic of one Metropolis proposal (a28) and of the AS factor (a12)."""
+    import copy
+
+    from oracle import drivers as OD
+    from tests.conftest import TURBO_FULL as T, load_turbo_jastrow
+
+    H = copy.deepcopy(load_system("water_ccecp_ccpvqz"))
+    H.wavefunction_data.jastrow_data = load_turbo_jastrow("w_2b_1b3b_w_ecp", H.structure_data)
+    wf, gem = H.wavefunction_data, H.wavefunction_data.geminal_data
+    up, dn = np.array(T["old_up"]), np.array(T["old_dn"])
+    new_up = up.copy()
+    new_up[2] = T["new_up2"]
+    Dt, eps = 2.0, 0.30
+    fa, fb = OD._f_l(H, up[2]), OD._f_l(H, new_up[2])
+    np.testing.assert_almost_equal(fa, T["fa"], decimal=6)
+    np.testing.assert_almost_equal(fb, T["fb"], decimal=6)
+    d2 = np.sum((new_up[2] - up[2]) ** 2)
+    T_ratio = (fa / fb) * np.exp(-d2 * (1.0 / (2.0 * fb**2 * Dt**2) - 1.0 / (2.0 * fa**2 * Dt**2)))
+    np.testing.assert_almost_equal(T_ratio, T["T_ratio"], decimal=6)
+    G_old, G_new = P.compute_geminal_all_elements(gem, up, dn), P.compute_geminal_all_elements(gem, new_up, dn)
+    np.testing.assert_almost_equal(G_old, np.array(T["geminal_old_T"]).T, decimal=6)
+    np.testing.assert_almost_equal(G_new, np.array(T["geminal_new_T"]).T, decimal=6)
+    R_old = P.compute_AS_regularization_factor(G_old, np.linalg.inv(G_old))
+    R_new = P.compute_AS_regularization_factor(G_new, np.linalg.inv(G_new))
+    np.testing.assert_almost_equal(R_old, T["R_AS_old"], decimal=6)
+    np.testing.assert_almost_equal(R_new, T["R_AS_new"], decimal=6)
+    np.testing.assert_almost_equal(np.sum(np.linalg.inv(G_old) ** 2) / T["F_old"], 1.0, decimal=6)
+    ratio = (P.evaluate_wavefunction(wf, new_up, dn) / P.evaluate_wavefunction(wf, up, dn)) ** 2
+    ratio *= ((max(R_new, eps) / R_new) / (max(R_old, eps) / R_old)) ** 2
+    np.testing.assert_almost_equal(ratio, T["WF_ratio"], decimal=6)
+    np.testing.assert_almost_equal(ratio * T_ratio, T["final_ratio"], decimal=6)
+    np.testing.assert_almost_equal((R_new / max(R_new, eps)) ** 2, T["reweight"], decimal=6)
+    np.testing.assert_almost_equal(P.compute_kinetic_energy(wf, new_up, dn), T["kinc"], decimal=6)
+    V = P.compute_coulomb_potential(H.coulomb_potential_data, wf, new_up, dn, RT=np.eye(3), NN=1, Nv=6)
+    np.testing.assert_almost_equal(V, T["vpot"] + T["vpotoff"], decimal=5)
