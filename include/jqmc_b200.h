@@ -167,6 +167,16 @@ int qe_gather_walkers(qe_engine* h, int nw, const int32_t* chosen_local, const d
  * `on` != 0 (default); otherwise as a chain of staged kernels through a global workspace.  Same results. */
 int qe_set_fused(qe_engine* h, int on);
 
+/* _jit_vmap_grad_ln_psi_params_fast == vmap(grad(evaluate_ln_wavefunction_fast)) (jqmc/jqmc_mcmc.py:4748, 854-876): per-walker
+ * derivatives of ln|Psi| with respect to the variational parameters, running inverse held fixed -- the O_k of stochastic
+ * reconfiguration, in the reference's parameter layout (blocks of jqmc/wavefunction.py:515-674; before get_dln_WF's
+ * projection / symmetrisation, jqmc_mcmc.py:1372-1513).  Any output may be NULL:
+ *   d_j1[nw], d_j2[nw]                    d/d jastrow_1b_param, d/d jastrow_2b_param
+ *   d_j3[nw, n_orb_j3, n_orb_j3 + 1]      d/d j_matrix (last column: one-body vector)
+ *   d_lambda[nw, n_orb, n_orb + n_up - n_dn]   d/d lambda_matrix (paired block | unpaired columns) */
+int qe_dln_wf(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* Ginv, double* d_j1, double* d_j2,
+              double* d_j3, double* d_lambda, void* stream);
+
 /* Kernel family.  0 (default): automatic -- the register/shared-memory kernels when they cover the system (MO-basis
  * geminal with <= 16 orbitals, <= 8 electrons per spin, J1 + J2), otherwise the general path (AO-basis JAGP geminals, any
  * orbital count, <= 112 electrons per spin, three-body Jastrow; contractions on the fp64 tensor cores).  1: always the

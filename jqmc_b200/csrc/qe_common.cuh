@@ -460,6 +460,8 @@ int wide_lrdmc(qe_engine* h, int mode, int nw, double* w, double* r_up, double* 
                int nmpm, int random_mesh, int non_local_move, double alat, const double* RT_in, double* RT_out, double* V_diag,
                double* V_nondiag, cudaStream_t st);
 int wide_eval_orbitals(qe_engine* h, int which, int n_pts, const double* r, double* out, cudaStream_t st);
+int wide_dln_wf(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* Ginv, double* d_j1, double* d_j2,
+                double* d_j3, double* d_lambda, cudaStream_t st);
 
 // workspace carve-up helper
 struct WsCarve {

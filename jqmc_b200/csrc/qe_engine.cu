@@ -1291,6 +1291,15 @@ extern "C" int qe_move_ratios(qe_engine* h, int nw, const double* r_up, const do
   return QE_OK;
 }
 
+extern "C" int qe_dln_wf(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* Ginv, double* d_j1, double* d_j2,
+                         double* d_j3, double* d_lambda, void* stream) {
+  if (!h || nw <= 0 || !r_up || !Ginv || (!r_dn && h->sys.n_dn > 0)) return fail(QE_ERR_INVALID, "qe_dln_wf: bad argument");
+  if (d_j1 && !h->sys.j1_type) return fail(QE_ERR_INVALID, "qe_dln_wf: no one-body Jastrow in this Hamiltonian");
+  if (d_j2 && !h->sys.j2_type) return fail(QE_ERR_INVALID, "qe_dln_wf: no two-body Jastrow in this Hamiltonian");
+  if (d_j3 && !h->wt.j3) return fail(QE_ERR_INVALID, "qe_dln_wf: no three-body Jastrow in this Hamiltonian");
+  return wide_dln_wf(h, nw, r_up, r_dn, Ginv, d_j1, d_j2, d_j3, d_lambda, (cudaStream_t)stream);
+}
+
 extern "C" int qe_measure_fp64_peak(int iters, double* tflops) {
   if (!tflops || iters <= 0) return fail(QE_ERR_INVALID, "qe_measure_fp64_peak: bad argument");
   int dev = 0, sms = 0;

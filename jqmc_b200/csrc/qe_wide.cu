@@ -1081,6 +1081,85 @@ __global__ void kw_rt_identity(int nw, double* __restrict__ RT) {
 }
 
 // =================================================================================================
+// parameter derivatives of ln|Psi| (stochastic reconfiguration O_k; the reference: jax.grad of evaluate_ln_wavefunction_fast,
+// jqmc/jqmc_mcmc.py:4748, 854-876; parameter blocks jqmc/wavefunction.py:515-674)
+// =================================================================================================
+// d(J1 + J2)/d(parameter): thread = walker
+__global__ void kw_j12_dparam(SysDev S, int nw, const double* __restrict__ rs, double* __restrict__ d_j1, double* __restrict__ d_j2) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  PosSoA pos{rs, nw, w};
+  const int Ne = S.n_e;
+  double g1 = 0.0, g2 = 0.0;
+  for (int e = 0; e < Ne; ++e) {
+    double x, y, z;
+    pos.get(e, x, y, z);
+    if (S.j1_type && d_j1) {
+      const double a = S.j1_a;
+      for (int n = 0; n < S.n_atom; ++n) {
+        const double dx = x - S.Rn[3 * n], dy = y - S.Rn[3 * n + 1], dz = z - S.Rn[3 * n + 2];
+        const double d = sqrt(dx * dx + dy * dy + dz * dz), A = S.j1_A[n], c = S.j1_c[n];
+        if (S.j1_type == 1) {
+          const double ex = qexp(-a * c * d);
+          g1 += -A * (a * c * d * ex - (1.0 - ex)) / (2.0 * a * a);
+        } else {
+          const double den = 1.0 + a * c * d;
+          g1 += A * c * d * d / (2.0 * den * den);
+        }
+      }
+    }
+    if (S.j2_type && d_j2) {
+      const double a = S.j2_a;
+      for (int j = e + 1; j < Ne; ++j) {
+        double x2, y2, z2;
+        pos.get(j, x2, y2, z2);
+        const double d = sqrt((x - x2) * (x - x2) + (y - y2) * (y - y2) + (z - z2) * (z - z2));
+        if (S.j2_type == 1) {
+          const double den = 1.0 + a * d;
+          g2 += -d * d / (2.0 * den * den);
+        } else {
+          const double ex = qexp(-a * d);
+          g2 += (a * d * ex - (1.0 - ex)) / (2.0 * a * a);
+        }
+      }
+    }
+  }
+  if (d_j1) d_j1[w] = g1;
+  if (d_j2) d_j2[w] = g2;
+}
+// exclusive prefix over electrons P[o][e][w] = sum_{i<e} X[o][i][w] and row sums R[o][w] = sum_e X[o][e][w]; thread = (o, w)
+__global__ void kw_prefix_excl(int no, int Ne, int nw, const double* __restrict__ X, double* __restrict__ Pf, double* __restrict__ R) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)no * nw) return;
+  const int w = (int)(t % nw), o = (int)(t / nw);
+  const double* x = X + (size_t)o * Ne * nw + w;
+  double* p = Pf + (size_t)o * Ne * nw + w;
+  double s = 0.0;
+  for (int e = 0; e < Ne; ++e) {
+    p[(size_t)e * nw] = s;
+    s += x[(size_t)e * nw];
+  }
+  R[t] = s;
+}
+// dst[w][m1(r1)][col0 + m2(r2)] = sc1[r1] sc2[r2] src[r1*s1 + r2*s2 + w]   (m = identity, sc = 1 when the map is null;
+// rows mapped to -1 are basis-image holes and are skipped): engine row space -> the reference's parameter layout
+__global__ void kw_scatter_mat(int nw, int n1, int n2, const int* __restrict__ map1, const double* __restrict__ sc1,
+                               const int* __restrict__ map2, const double* __restrict__ sc2, const double* __restrict__ src, long long s1,
+                               long long s2, double* __restrict__ dst, int ld, long long stride_w, int col0) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n1 * n2 * nw) return;
+  const int w = (int)(t % nw);
+  const int r2 = (int)((t / nw) % n2);
+  const int r1 = (int)(t / ((long long)nw * n2));
+  const int a = map1 ? map1[r1] : r1, b = map2 ? map2[r2] : r2;
+  if (a < 0 || b < 0) return;
+  double v = src[r1 * s1 + r2 * s2 + w];
+  if (sc1) v *= sc1[r1];
+  if (sc2) v *= sc2[r2];
+  dst[(long long)w * stride_w + (long long)a * ld + col0 + b] = v;
+}
+
+// =================================================================================================
 // host side
 // =================================================================================================
 struct WState {
@@ -1603,6 +1682,65 @@ int wide_lrdmc(qe_engine* h, int mode, int nw, double* w, double* r_up, double* 
     MISC(st, kw_pos_to_aos<<<nblk((long long)Ne * 3 * nw, 256), 256, 0, st>>>(nw, N, Nd, X.rs, r_up, r_dn));
     MISC(st, kw_to_aos<<<nblk((long long)N * N * nw, 256), 256, 0, st>>>(nw, N * N, X.Gi, Ginv));
     MISC(st, kw_to_aos<<<nblk(9LL * nw, 256), 256, 0, st>>>(nw, 9, RTcur, RT_out));
+  }
+  return QE_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// vmap(grad(evaluate_ln_wavefunction_fast)) w.r.t. the variational parameters
+// -------------------------------------------------------------------------------------------------
+int wide_dln_wf(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* Ginv, double* d_j1, double* d_j2,
+                double* d_j3, double* d_lambda, cudaStream_t st) {
+  const SysDev& S = h->sys;
+  const WideTabs& T = h->wt;
+  const long long N = S.n_up, Nd = S.n_dn, Ne = S.n_e, W = nw;
+  const int no = T.no, nj = T.nj;
+  size_t need = state_bytes(h, nw, 1, false) + ((size_t)no * N + (size_t)no * no) * W * 8 + 8192;
+  if (T.j3) need += ((size_t)nj * Ne + nj + (size_t)nj * nj) * W * 8 + 4096;
+  TRY(ensure_ws(h, need));
+  WsCarve c{(char*)h->ws};
+  WState X;
+  carve_state(h, c, nw, 1, false, X);
+  double* A = c.take<double>((size_t)no * N * W);
+  double* DL = c.take<double>((size_t)no * no * W);
+  TRY(build_state(h, st, X, r_up, r_dn));
+  if (d_j1 || d_j2) {
+    MISC(st, kw_j12_dparam<<<nblk(nw, 32), 32, 0, st>>>(S, nw, X.rs, S.j1_type ? d_j1 : nullptr, S.j2_type ? d_j2 : nullptr));
+  }
+  const BasisDev& B = h->b_up.dev;
+  const int* rmap = T.has_mo ? nullptr : (const int*)(B.g + B.off_rowao);
+  const double* rsc = T.has_mo ? nullptr : (const double*)(B.g + B.off_rowscale);
+  if (d_lambda) {
+    const int n_ref = T.has_mo ? no : B.n_ao, ld = n_ref + (int)(N - Nd);
+    MISC(st, kw_to_soa<<<nblk(N * N * W, 256), 256, 0, st>>>(nw, (int)(N * N), Ginv, X.Gi));
+    // A[a][j] = sum_i Phi_up[a][i] Ginv[j][i];   DL[a][b] = sum_{j < Nd} A[a][j] Phi_dn[b][j]
+    TRY(w_bmm(h, st, no, (int)N, (int)N, nw, X.Phi, W, Ne * W, X.Gi, W, N * W, A, N * W, W));
+    TRY(w_bmm(h, st, no, no, (int)Nd, nw, A, W, N * W, X.Phi + N * W, W, Ne * W, DL, (long long)no * W, W));
+    CUDA_TRY(cudaMemsetAsync(d_lambda, 0, (size_t)nw * n_ref * ld * 8, st));
+    MISC(st, kw_scatter_mat<<<nblk((long long)no * no * W, 256), 256, 0, st>>>(nw, no, no, rmap, rsc, rmap, rsc, DL, (long long)no * W, W,
+                                                                              d_lambda, ld, (long long)n_ref * ld, 0));
+    if (N > Nd) {
+      MISC(st, kw_scatter_mat<<<nblk((long long)no * (N - Nd) * W, 256), 256, 0, st>>>(nw, no, (int)(N - Nd), rmap, rsc, nullptr, nullptr,
+                                                                                      A + Nd * W, N * W, W, d_lambda, ld,
+                                                                                      (long long)n_ref * ld, n_ref));
+    }
+  }
+  if (d_j3 && T.j3) {
+    const BasisDev& BJ = h->b_j3.dev;
+    const int* jmap = T.j3_mo ? nullptr : (const int*)(BJ.g + BJ.off_rowao);
+    const double* jsc = T.j3_mo ? nullptr : (const double*)(BJ.g + BJ.off_rowscale);
+    const int n_ref = T.j3_mo ? nj : BJ.n_ao, ld = n_ref + 1;
+    double* Pf = c.take<double>((size_t)nj * Ne * W);
+    double* Rs = c.take<double>((size_t)nj * W);
+    double* DM = c.take<double>((size_t)nj * nj * W);
+    MISC(st, kw_prefix_excl<<<nblk((long long)nj * W, 128), 128, 0, st>>>(nj, (int)Ne, nw, X.Chi, Pf, Rs));
+    // DM[a][b] = sum_j (sum_{i<j} chi[a][i]) chi[b][j]
+    TRY(w_bmm(h, st, nj, nj, (int)Ne, nw, Pf, W, Ne * W, X.Chi, W, Ne * W, DM, (long long)nj * W, W));
+    CUDA_TRY(cudaMemsetAsync(d_j3, 0, (size_t)nw * n_ref * ld * 8, st));
+    MISC(st, kw_scatter_mat<<<nblk((long long)nj * nj * W, 256), 256, 0, st>>>(nw, nj, nj, jmap, jsc, jmap, jsc, DM, (long long)nj * W, W, d_j3,
+                                                                              ld, (long long)n_ref * ld, 0));
+    MISC(st, kw_scatter_mat<<<nblk((long long)nj * W, 256), 256, 0, st>>>(nw, nj, 1, jmap, jsc, nullptr, nullptr, Rs, W, 0, d_j3, ld,
+                                                                         (long long)n_ref * ld, n_ref));
   }
   return QE_OK;
 }

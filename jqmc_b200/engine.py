@@ -165,6 +165,7 @@ class WalkerEngine:
         self.ecp_flag = bool(cp.ecp_flag)
         self.n_orb = n_orb_up
         self._n_ao = int(d.orb_up.n_ao)
+        self._has_j1, self._has_j2 = bool(d.j1_type), bool(d.j2_type)
         self._n_ao_j3 = int(d.j3_orb.n_ao) if d.j3_flag else 0
         self._n_orb_j3 = int(d.j3_orb.n_mo or d.j3_orb.n_ao) if d.j3_flag else 0
         h = C.c_void_p()
@@ -335,6 +336,28 @@ class WalkerEngine:
         _lib.check(rc, "qe_move_ratios")
         torch.cuda.current_stream(self.device).synchronize()  # elec is a host buffer
         return dr, jr
+
+    def grad_ln_psi_params_fast(self, r_up, r_dn, Ginv):
+        """``_jit_vmap_grad_ln_psi_params_fast`` (jqmc/jqmc_mcmc.py:4748): per-walker d ln|Psi| / d parameter for every
+        variational block of this Hamiltonian, as a dict keyed like the reference's blocks:
+        ``j1_param`` [nw], ``j2_param`` [nw], ``j3_matrix`` [nw, n, n+1], ``lambda_matrix`` [nw, n_orb, n_orb + n_up - n_dn]."""
+        r_up, r_dn, nw = self._walkers(r_up, r_dn)
+        Ginv = self._mat(Ginv, nw, "A_old_inv")
+        out = {}
+        mk = lambda *shape: torch.empty((nw,) + shape, dtype=torch.float64, device=self.device)  # noqa: E731
+        if self._has_j1:
+            out["j1_param"] = mk()
+        if self._has_j2:
+            out["j2_param"] = mk()
+        if self._n_orb_j3:
+            out["j3_matrix"] = mk(self._n_orb_j3, self._n_orb_j3 + 1)
+        out["lambda_matrix"] = mk(self.n_orb, self.n_orb + self.n_up - self.n_dn)
+        rc = self._lib.qe_dln_wf(
+            self._h, nw, self._ptr(r_up), self._ptr(r_dn), self._ptr(Ginv), self._ptr(out.get("j1_param")), self._ptr(out.get("j2_param")),
+            self._ptr(out.get("j3_matrix")), self._ptr(out["lambda_matrix"]), self._stream(),
+        )  # fmt: skip
+        _lib.check(rc, "qe_dln_wf")
+        return out
 
     def set_fused(self, on: bool):
         """Fused (one kernel, shared-memory resident) vs staged (kernel chain) local energy; same results."""

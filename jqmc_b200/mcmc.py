@@ -14,7 +14,12 @@ Ranks: one process per GPU; rank r seeds with ``mcmc_seed * (r + 1)`` and owns `
 walkers (jqmc_mcmc.py:191-197).  The only collectives are the ``get_E`` reductions, done with
 ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) when a process group is initialised.
 
-Out of scope here (SURVEY.md §8f "next"): parameter/position derivatives, ``run_optimize``.
+With ``comput_log_WF_param_deriv=True`` every step also stores O_k = d ln|Psi| / d parameter (qe_dln_wf; blocks ``j1_param``,
+``j2_param``, ``j3_matrix``, ``lambda_matrix`` as in jqmc/wavefunction.py:542-624), and ``get_dln_WF`` / ``get_gF`` give the
+flattened derivative matrix and the jackknifed generalised forces (jqmc_mcmc.py:1372-1513, 1516-1692).
+
+Out of scope here (SURVEY.md §8f "next"): e_L parameter derivatives, position derivatives (forces), the lambda projection
+and block symmetrisation of ``get_dln_WF``, ``run_optimize``.
 """
 
 from __future__ import annotations
@@ -153,8 +158,9 @@ class MCMC:
         use_swct: bool = True,
         engine: WalkerEngine | None = None,
     ) -> None:
-        if comput_log_WF_param_deriv or comput_e_L_param_deriv or comput_position_deriv:
-            raise NotImplementedError("parameter / position derivatives are outside the walker engine (SURVEY.md §8f)")
+        if comput_e_L_param_deriv or comput_position_deriv:
+            raise NotImplementedError("e_L parameter derivatives / position derivatives are outside the walker engine (SURVEY.md §8f)")
+        self.__comput_log_WF_param_deriv = bool(comput_log_WF_param_deriv)
         self.hamiltonian_data = hamiltonian_data
         self.__mcmc_seed = mcmc_seed
         self.__num_walkers = int(num_walkers)
@@ -186,6 +192,7 @@ class MCMC:
         self.__stored_e_L = []
         self.__stored_e_L2 = []
         self.__stored_w_L = []
+        self.__stored_dln = {}
         self.__timer = dict(total=0.0, update=0.0, e_L=0.0, misc=0.0)
 
     # ---- properties (names as in the reference, jqmc_mcmc.py:260-447) --------------------------------
@@ -208,6 +215,11 @@ class MCMC:
     @property
     def w_L(self):
         return np.array(self.__stored_w_L).reshape(-1, self.__num_walkers)
+
+    @property
+    def dln_Psi_dc(self):
+        """{block name: array (steps, num_walkers, *block shape)} of d ln|Psi| / d parameter (jqmc_mcmc.py:300-330)."""
+        return {k: np.array(v) for k, v in self.__stored_dln.items()}
 
     @property
     def latest_r_up_carts(self):
@@ -255,6 +267,9 @@ class MCMC:
             else:  # (R/max(R,0))^2 = 1, NaN when R_AS == 0 (0/0), as in jqmc_mcmc.py:743-747
                 w_L = torch.where(R_AS > 0, torch.ones_like(R_AS), torch.full_like(R_AS, float("nan")))
             # one device->host read per step (the reference does three: jqmc_mcmc.py:720, 739, 747)
+            if self.__comput_log_WF_param_deriv:  # jqmc_mcmc.py:854-876
+                for name, g in eng.grad_ln_psi_params_fast(r_up, r_dn, Ginv).items():
+                    self.__stored_dln.setdefault(name, []).append(g.cpu().numpy())
             pack = torch.stack([e_L, w_L, acc.to(torch.float64), rej.to(torch.float64)]).cpu().numpy()
             self.__stored_e_L.append(pack[0])
             self.__stored_e_L2.append(pack[0] ** 2)
@@ -278,6 +293,49 @@ class MCMC:
         e_L2 = self.e_L2[num_mcmc_warmup_steps:]
         w_L = self.w_L[num_mcmc_warmup_steps:]
         return jackknife_E(w_L, e_L, e_L2, num_mcmc_bin_blocks, self.engine.device)
+
+
+    BLOCK_ORDER = ("j1_param", "j2_param", "j3_matrix", "lambda_matrix")  # jqmc/wavefunction.py:515-674
+
+    def get_dln_WF(self, num_mcmc_warmup_steps: int = 50, chosen_param_index=None, blocks=None):
+        """O_matrix (M, num_walkers, K): the stored derivatives after warm-up, blocks concatenated in the reference's order and
+        flattened row-major (jqmc_mcmc.py:1372-1420).  ``blocks``: optional list of block names (default: all stored)."""
+        if not self.__stored_dln:
+            raise ValueError("no parameter derivatives stored: construct MCMC with comput_log_WF_param_deriv=True")
+        names = [n for n in self.BLOCK_ORDER if n in self.__stored_dln and (blocks is None or n in blocks)]
+        parts = []
+        for n in names:
+            a = np.array(self.__stored_dln[n])
+            parts.append(a.reshape(a.shape[0], a.shape[1], -1))
+        O = np.concatenate(parts, axis=2)[num_mcmc_warmup_steps:]
+        return O if chosen_param_index is None else O[:, :, chosen_param_index]
+
+    def get_gF(self, num_mcmc_warmup_steps: int = 50, num_mcmc_bin_blocks: int = 10, chosen_param_index=None, blocks=None):
+        """Generalised forces f_k = -2 (<e_L O_k> - <e_L><O_k>) with jackknife error bars over (bins x walkers) samples of all
+        ranks (jqmc_mcmc.py:1516-1692: same binning, same reductions, two-pass standard deviation)."""
+        w_L = self.w_L[num_mcmc_warmup_steps:]
+        e_L = self.e_L[num_mcmc_warmup_steps:]
+        O = self.get_dln_WF(num_mcmc_warmup_steps, chosen_param_index, blocks)
+        return jackknife_gF(w_L, e_L, O, num_mcmc_bin_blocks, self.engine.device)
+
+
+def jackknife_gF(w_L, e_L, O, num_bin_blocks, device=None):
+    """(mean[K], std[K]) of -2 (<e_L O> - <e_L><O>) by binned jackknife; sums over ranks via torch.distributed."""
+
+    def binned(x):  # (M, nw, ...) -> (bins*nw, ...)
+        s = np.array([np.sum(a, axis=0) for a in np.array_split(x, num_bin_blocks, axis=0)])
+        return s.reshape((-1,) + s.shape[2:])
+
+    wb, web = binned(w_L), binned(w_L * e_L)
+    wOb, weOb = binned(w_L[:, :, None] * O), binned((w_L * e_L)[:, :, None] * O)
+    K = O.shape[2]
+    g = _allreduce_sum(np.concatenate([[wb.sum(), web.sum(), wb.size], wOb.sum(axis=0), weOb.sum(axis=0)]), device)
+    W, WE, M_total, WO, WEO = g[0], g[1], g[2], g[3 : 3 + K], g[3 + K :]
+    den = (W - wb)[:, None]
+    f = -2.0 * ((WEO - weOb) / den - ((WE - web) / (W - wb))[:, None] * ((WO - wOb) / den))
+    mean = _allreduce_sum(f.sum(axis=0), device) / M_total
+    var = _allreduce_sum(np.sum((f - mean) ** 2, axis=0), device) / M_total
+    return mean, np.sqrt((M_total - 1) * var)
 
 
 def jackknife_E(w_L, e_L, e_L2, num_bin_blocks, device=None):

@@ -430,6 +430,65 @@ def compute_kinetic_energy(wf, r_up, r_dn, Ginv=None):
 
 
 # --------------------------------------------------------------------------------------
+# Derivatives of ln|Psi| with respect to the variational parameters (stochastic reconfiguration O_k)
+# --------------------------------------------------------------------------------------
+def compute_dln_wf_dparams(wf, r_up, r_dn, Ginv=None):
+    """d ln|Psi| / d{jastrow_1b_param, jastrow_2b_param, j_matrix, lambda_matrix} -- what the reference obtains as
+    jax.grad(evaluate_ln_wavefunction_fast) (jqmc/jqmc_mcmc.py:4748, 854-876; parameter blocks jqmc/wavefunction.py:515-674),
+    written out analytically:  d ln|det G| / d lambda[a,b] = sum_ij Ginv[j,i] dG[i,j]/d lambda[a,b]  with the running
+    inverse held fixed, and the explicit parameter derivatives of J1, J2, J3.  Returns a dict (None for absent blocks)."""
+    r_up = np.asarray(r_up, dtype=np.float64).reshape(-1, 3)
+    r_dn = np.asarray(r_dn, dtype=np.float64).reshape(-1, 3)
+    gem, jd = wf.geminal_data, wf.jastrow_data
+    n_up, n_dn = len(r_up), len(r_dn)
+    out = dict(j1_param=None, j2_param=None, j3_matrix=None, lambda_matrix=None)  # the reference's block names (wavefunction.py:542-624)
+    ou = compute_orb(gem.orb_data_up_spin, r_up)
+    od = compute_orb(gem.orb_data_dn_spin, r_dn) if n_dn else np.zeros((gem.orb_num_dn, 0))
+    if Ginv is None:
+        Ginv = np.linalg.inv(compute_geminal_all_elements(gem, r_up, r_dn))
+    A = ou @ Ginv.T  # [a, j] = sum_i phi_a(r_i) Ginv[j, i]
+    out["lambda_matrix"] = np.hstack([A[:, :n_dn] @ od.T, A[:, n_dn:]])
+    j1 = jd.jastrow_one_body_data
+    if j1 is not None:
+        R, zeff = _j1_params(j1)
+        a = float(j1.jastrow_1b_param)
+        g = 0.0
+        for r in itertools.chain(r_up, r_dn):
+            for Rc, Z in zip(R, zeff):
+                c, Apre = (2.0 * Z) ** 0.25, (2.0 * Z) ** 0.75
+                d = np.linalg.norm(r - Rc)
+                if j1.jastrow_1b_type == "exp":
+                    e = np.exp(-a * c * d)
+                    g += -Apre * (a * c * d * e - (1.0 - e)) / (2.0 * a * a)
+                else:
+                    g += Apre * c * d * d / (2.0 * (1.0 + a * c * d) ** 2)
+        out["j1_param"] = g
+    j2 = jd.jastrow_two_body_data
+    if j2 is not None:
+        a = float(j2.jastrow_2b_param)
+        r_all = np.vstack([r_up, r_dn])
+        g = 0.0
+        for i, j in itertools.combinations(range(len(r_all)), 2):
+            d = np.linalg.norm(r_all[i] - r_all[j])
+            if j2.jastrow_2b_type == "pade":
+                g += -d * d / (2.0 * (1.0 + a * d) ** 2)
+            else:
+                e = np.exp(-a * d)
+                g += (a * d * e - (1.0 - e)) / (2.0 * a * a)
+        out["j2_param"] = g
+    j3 = jd.jastrow_three_body_data
+    if j3 is not None:
+        x = compute_orb(j3.orb_data, np.vstack([r_up, r_dn]))  # electrons ordered up then down
+        n = x.shape[1]
+        dM = np.zeros((x.shape[0], x.shape[0]))
+        for i in range(n):
+            for j in range(i + 1, n):
+                dM += np.outer(x[:, i], x[:, j])
+        out["j3_matrix"] = np.hstack([dM, x.sum(axis=1)[:, None]])
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # Wavefunction ratios for single-electron moves
 # --------------------------------------------------------------------------------------
 def wf_ratio_brute_force(wf, r_up, r_dn, spin_up: bool, idx: int, r_new, det_only=False):

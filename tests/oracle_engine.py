@@ -50,6 +50,11 @@ class OracleEngine:
         k2 = torch.from_numpy(np.array([r[4] for r in res], dtype=np.uint32))
         return acc, rej, self._t([r[2] for r in res]), self._t([r[3] for r in res]), k2, self._t([r[5] for r in res]), self._t([r[6] for r in res])
 
+    def grad_ln_psi_params_fast(self, r_up, r_dn, Ginv):
+        r_up, r_dn, Ginv = _np(r_up), _np(r_dn), _np(Ginv)
+        res = [OP.compute_dln_wf_dparams(self.H.wavefunction_data, r_up[w], r_dn[w], Ginv=Ginv[w]) for w in range(len(r_up))]
+        return {k: self._t(np.array([r[k] for r in res])) for k in res[0] if res[0][k] is not None}
+
     def generate_RTs(self, keys):
         return self._t([OD.generate_rotation_matrix(_key(k)) for k in _np(keys)])
 

@@ -221,3 +221,64 @@ def test_turborvb_full_metropolis_known_answers():
     np.testing.assert_almost_equal(P.compute_kinetic_energy(wf, new_up, dn), T["kinc"], decimal=6)
     V = P.compute_coulomb_potential(H.coulomb_potential_data, wf, new_up, dn, RT=np.eye(3), NN=1, Nv=6)
     np.testing.assert_almost_equal(V, T["vpot"] + T["vpotoff"], decimal=5)
+
+
+def test_parameter_derivatives_match_finite_differences():
+    """O_k = d ln|Psi| / d parameter (the reference: jax.grad of evaluate_ln_wavefunction_fast): the analytic restatement
+    against central finite differences of the oracle's own ln|Psi| for every block (J1, J2, J3 matrix incl. one-body column,
+    lambda incl. the unpaired column) -- reference test pattern C."""
+    import copy
+    import dataclasses
+
+    from jqmc_b200.data import Jastrow_three_body_data
+    from tests.conftest import load_turbo_jastrow
+
+    H = copy.deepcopy(load_system("Li_ae_ccpvdz_cart"))  # 2 up, 1 down: lambda has an unpaired column
+    aos = H.wavefunction_data.geminal_data.orb_data_up_spin.aos_data
+    rng = np.random.default_rng(3)
+    from tests.test_gpu_wide import sub_basis
+
+    j3b = sub_basis(aos, 1)
+    n = j3b.num_ao
+    jd = Jastrow_data(
+        jastrow_one_body_data=Jastrow_one_body_data(jastrow_1b_param=0.8, jastrow_1b_type="exp", structure_data=H.structure_data, core_electrons=(0.0,)),
+        jastrow_two_body_data=Jastrow_two_body_data(jastrow_2b_param=0.7, jastrow_2b_type="pade"),
+        jastrow_three_body_data=Jastrow_three_body_data(orb_data=j3b, j_matrix=rng.normal(scale=0.05, size=(n, n + 1))),
+    )
+    H.wavefunction_data.jastrow_data = jd
+    wf = H.wavefunction_data
+    r_up, r_dn = random_walkers(H, 1, 4)
+    r_up, r_dn = r_up[0], r_dn[0]
+    g = P.compute_dln_wf_dparams(wf, r_up, r_dn)
+
+    def fd(setter, h):
+        vals = []
+        for s in (+1, -1):
+            w2 = copy.deepcopy(wf)
+            setter(w2, s * h)
+            vals.append(P.evaluate_ln_wavefunction(w2, r_up, r_dn))
+        return (vals[0] - vals[1]) / (2 * h)
+
+    def set_j1(w, d):
+        w.jastrow_data.jastrow_one_body_data = dataclasses.replace(w.jastrow_data.jastrow_one_body_data, jastrow_1b_param=0.8 + d)
+
+    def set_j2(w, d):
+        w.jastrow_data.jastrow_two_body_data = dataclasses.replace(w.jastrow_data.jastrow_two_body_data, jastrow_2b_param=0.7 + d)
+
+    np.testing.assert_allclose(g["j1_param"], fd(set_j1, 1e-5), rtol=1e-7)
+    np.testing.assert_allclose(g["j2_param"], fd(set_j2, 1e-5), rtol=1e-7)
+    for idx in [(0, 0), (2, 1), (1, 3), (n - 1, n), (0, n)]:
+        def set_j3(w, d, idx=idx):
+            m = np.array(w.jastrow_data.jastrow_three_body_data.j_matrix)
+            m[idx] += d
+            w.jastrow_data.jastrow_three_body_data = dataclasses.replace(w.jastrow_data.jastrow_three_body_data, j_matrix=m)
+
+        np.testing.assert_allclose(g["j3_matrix"][idx], fd(set_j3, 1e-5), rtol=1e-6, atol=1e-9)
+    lam_shape = np.shape(wf.geminal_data.lambda_matrix)
+    for idx in [(0, 0), (1, 0), (0, 1), (lam_shape[0] - 1, lam_shape[1] - 1), (1, lam_shape[1] - 1)]:
+        def set_lam(w, d, idx=idx):
+            m = np.array(w.geminal_data.lambda_matrix)
+            m[idx] += d
+            w.geminal_data = dataclasses.replace(w.geminal_data, lambda_matrix=m)
+
+        np.testing.assert_allclose(g["lambda_matrix"][idx], fd(set_lam, 1e-6), rtol=1e-6, atol=1e-8)
