@@ -54,16 +54,40 @@ kw_dgemm(int m, long long n, int k, const double* __restrict__ A, int lda, const
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  // software pipeline: the next k-tile travels global -> registers while the tensor cores work on the current shared tiles
+  double ra[GM * GK / 128], rb[GK * GN / 128];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < GM * GK / 128; ++u) {
+      const int i = tid + u * 128, r = i / GK, c = i % GK;
+      ra[u] = (m0 + r < m && k0 + c < k) ? A[(size_t)(m0 + r) * lda + k0 + c] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < GK * GN / 128; ++u) {
+      const int i = tid + u * 128, r = i / GN, c = i % GN;
+      rb[u] = (k0 + r < k && n0 + c < n) ? B[(long long)(k0 + r) * ldb + n0 + c] : 0.0;
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int u = 0; u < GM * GK / 128; ++u) {
+      const int i = tid + u * 128;
+      As[i / GK][i % GK] = ra[u];
+    }
+#pragma unroll
+    for (int u = 0; u < GK * GN / 128; ++u) {
+      const int i = tid + u * 128;
+      Bs[i / GN][i % GN] = rb[u];
+    }
+  };
+  if (kbeg < k) {
+    fetch(kbeg);
+    stash();
+  }
+  __syncthreads();
   for (int k0 = kbeg; k0 < k; k0 += GK) {
-    for (int i = tid; i < GM * GK; i += 128) {
-      const int r = i / GK, c = i % GK;
-      As[r][c] = (m0 + r < m && k0 + c < k) ? A[(size_t)(m0 + r) * lda + k0 + c] : 0.0;
-    }
-    for (int i = tid; i < GK * GN; i += 128) {
-      const int r = i / GN, c = i % GN;
-      Bs[r][c] = (k0 + r < k && n0 + c < n) ? B[(long long)(k0 + r) * ldb + n0 + c] : 0.0;
-    }
-    __syncthreads();
+    const bool more = k0 + GK < k;
+    if (more) fetch(k0 + GK);
 #pragma unroll
     for (int kk = 0; kk < GK; kk += 4) {
       double a[4], b[4];
@@ -77,6 +101,10 @@ kw_dgemm(int m, long long n, int k, const double* __restrict__ A, int lda, const
         for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
     __syncthreads();
+    if (more) {
+      stash();
+      __syncthreads();
+    }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -265,72 +293,89 @@ struct MeshArgs {
   double* p;
   double* sj;
 };
-template <bool CART, bool CARTJ>
+template <bool CART, bool CARTJ, int LMAX, bool SMEM>
 __global__ void __launch_bounds__(128)
 kw_mesh(BasisDev B, BasisDev BJ, int has_j3, SysDev S, MeshArgs P) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // basis images (shell / primitive tables of the determinant and J3 bases) staged in shared memory once per CTA; the CTA
+  // then walks its share of the (pair, walker) work items with a grid-stride loop
+  extern __shared__ __align__(16) char sm_mesh[];
+  const char* tab = B.g;
+  const char* tabJ = BJ.g;
+  if (SMEM) {
+    const int nB = B.bytes / 16, nJ = has_j3 ? BJ.bytes / 16 : 0;
+    int4* dst = (int4*)sm_mesh;
+    const int4* srcB = (const int4*)B.g;
+    const int4* srcJ = (const int4*)BJ.g;
+    for (int i = threadIdx.x; i < nB; i += blockDim.x) dst[i] = srcB[i];
+    for (int i = threadIdx.x; i < nJ; i += blockDim.x) dst[nB + i] = srcJ[i];
+    __syncthreads();
+    tab = sm_mesh;
+    tabJ = sm_mesh + B.bytes;
+  }
   const int n_pairs = (P.n_kin + P.n_ecp) / 2;
-  if (t >= (long long)n_pairs * P.nw) return;
-  const int w = (int)(t % P.nw);
-  const int t0 = 2 * (int)(t / P.nw);
+  const long long total = (long long)n_pairs * P.nw;
   const int Ne = S.n_e, nw = P.nw;
-  PosSoA pos{P.rs, nw, w};
-  double rt[9];
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(t % P.nw);
+    const int t0 = 2 * (int)(t / P.nw);
+    PosSoA pos{P.rs, nw, w};
+    double rt[9];
 #pragma unroll
-  for (int c = 0; c < 9; ++c) rt[c] = P.RT[(size_t)c * nw + w];
-  int e;
-  double px[2], py[2], pz[2], angw[2] = {0.0, 0.0};
-  double x, y, z;
-  const bool kin = t0 < P.n_kin;
-  if (kin) {
-    e = t0 / 6;
-    pos.get(e, x, y, z);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int s6 = (t0 + i) % 6, ax = s6 >> 1;
-      const double sg = (s6 & 1) ? -P.alat : P.alat;
-      px[i] = x + sg * rt[3 * ax];
-      py[i] = y + sg * rt[3 * ax + 1];
-      pz[i] = z + sg * rt[3 * ax + 2];
-    }
-  } else {
-    const int pt0 = t0 - P.n_kin;
-    e = pt0 / (S.Nv * S.NN);
-    pos.get(e, x, y, z);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int pt = pt0 + i;
-      const int k = pt % S.Nv, nn = (pt / S.Nv) % S.NN;
-      ecp_point(S, rt, x, y, z, nn, k, px[i], py[i], pz[i], angw[i], true);
-    }
-  }
-  SinkDotN<2> sink;
-  sink.init(P.Wrow + (size_t)e * nw + w, (size_t)Ne * nw);
-  eval_val_n<CART, QE_LMAX, 2>(B.g, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);
-  double jr[2] = {1.0, 1.0};
-  if (!P.det_only) {
-    const double jold = P.el[((size_t)e * 8 + 7) * nw + w];
-    double d3[2] = {0.0, 0.0};
-    if (has_j3) {
-      SinkDotN<2> sj3;
-      sj3.init(P.gJrow + (size_t)e * nw + w, (size_t)Ne * nw);
-      eval_val_n<CARTJ, QE_LMAX, 2>(BJ.g, BJ, BJ.off_seg, px, py, pz, 0, BJ.n_grp, sj3);
-      const double c0 = P.cJ[(size_t)e * nw + w];
-      d3[0] = sj3.acc[0] - c0;
-      d3[1] = sj3.acc[1] - c0;
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) jr[i] = qexp(jastrow_single_q(S, pos, e, px[i], py[i], pz[i]) - jold + d3[i]);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const double ratio = sink.acc[i];
-    const size_t idx = (size_t)(t0 + i) * nw + w;
+    for (int c = 0; c < 9; ++c) rt[c] = P.RT[(size_t)c * nw + w];
+    int e;
+    double px[2], py[2], pz[2], angw[2] = {0.0, 0.0};
+    double x, y, z;
+    const bool kin = t0 < P.n_kin;
     if (kin) {
-      P.p[idx] = -1.0 / (2.0 * P.alat * P.alat) * (ratio * jr[i]);
+      e = t0 / 6;
+      pos.get(e, x, y, z);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int s6 = (t0 + i) % 6, ax = s6 >> 1;
+        const double sg = (s6 & 1) ? -P.alat : P.alat;
+        px[i] = x + sg * rt[3 * ax];
+        py[i] = y + sg * rt[3 * ax + 1];
+        pz[i] = z + sg * rt[3 * ax + 2];
+      }
     } else {
-      P.p[idx] = P.dlt ? angw[i] * ratio : angw[i] * (ratio * jr[i]);
-      if (P.sj) P.sj[idx - (size_t)P.n_kin * nw] = jr[i];
+      const int pt0 = t0 - P.n_kin;
+      e = pt0 / (S.Nv * S.NN);
+      pos.get(e, x, y, z);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int pt = pt0 + i;
+        const int k = pt % S.Nv, nn = (pt / S.Nv) % S.NN;
+        ecp_point(S, rt, x, y, z, nn, k, px[i], py[i], pz[i], angw[i], true);
+      }
+    }
+    SinkDotN<2> sink;
+    sink.init(P.Wrow + (size_t)e * nw + w, (size_t)Ne * nw);
+    eval_val_n<CART, LMAX, 2>(tab, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);
+    double jr[2] = {1.0, 1.0};
+    if (!P.det_only) {
+      const double jold = P.el[((size_t)e * 8 + 7) * nw + w];
+      double d3[2] = {0.0, 0.0};
+      if (has_j3) {
+        SinkDotN<2> sj3;
+        sj3.init(P.gJrow + (size_t)e * nw + w, (size_t)Ne * nw);
+        eval_val_n<CARTJ, LMAX, 2>(tabJ, BJ, BJ.off_seg, px, py, pz, 0, BJ.n_grp, sj3);
+        const double c0 = P.cJ[(size_t)e * nw + w];
+        d3[0] = sj3.acc[0] - c0;
+        d3[1] = sj3.acc[1] - c0;
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) jr[i] = qexp(jastrow_single_q(S, pos, e, px[i], py[i], pz[i]) - jold + d3[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const double ratio = sink.acc[i];
+      const size_t idx = (size_t)(t0 + i) * nw + w;
+      if (kin) {
+        P.p[idx] = -1.0 / (2.0 * P.alat * P.alat) * (ratio * jr[i]);
+      } else {
+        P.p[idx] = P.dlt ? angw[i] * ratio : angw[i] * (ratio * jr[i]);
+        if (P.sj) P.sj[idx - (size_t)P.n_kin * nw] = jr[i];
+      }
     }
   }
 }
@@ -1378,13 +1423,34 @@ int launch_mesh(qe_engine* h, cudaStream_t st, const MeshArgs& A) {
   const BasisDev& B = h->b_up.dev;
   const BasisDev BJ = h->wt.j3 ? h->b_j3.dev : B;
   const int j3 = h->wt.j3;
-#define CALL(C1, C2) kw_mesh<C1, C2><<<nblk(total, 128), 128, 0, st>>>(B, BJ, j3, h->sys, A)
+  // angular code up to l = LMAX is compiled in (register allocation follows the largest shell type): l <= 2, <= 4, <= 6
+  const int lmax = std::max(B.lmax, j3 ? BJ.lmax : 0);
+  const size_t smem = (size_t)B.bytes + (j3 ? (size_t)BJ.bytes : 0);
+  const bool use_smem = smem <= 48 * 1024;  // 4 resident CTAs per SM keep their images within the 227 KB
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)std::min<long long>(nblk(total, 128), (long long)sms * 16);
+#define CALL4(C1, C2, L, SM) kw_mesh<C1, C2, L, SM><<<grid, 128, SM ? smem : 0, st>>>(B, BJ, j3, h->sys, A)
+#define CALL3(C1, C2, L)             \
+  do {                               \
+    if (use_smem) CALL4(C1, C2, L, true); \
+    else CALL4(C1, C2, L, false);    \
+  } while (0)
+#define CALL(C1, C2)                   \
+  do {                                 \
+    if (lmax <= 2) CALL3(C1, C2, 2);   \
+    else if (lmax <= 4) CALL3(C1, C2, 4); \
+    else CALL3(C1, C2, 6);             \
+  } while (0)
   if (B.cart) {
     if (BJ.cart) CALL(true, true); else CALL(true, false);
   } else {
     if (BJ.cart) CALL(false, true); else CALL(false, false);
   }
 #undef CALL
+#undef CALL3
+#undef CALL4
   CHECK_LAUNCH();
   return QE_OK;
 }
