@@ -46,14 +46,65 @@ __device__ double np_pairwise_sum(const double* __restrict__ a, int n) {
   return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
 }
 
-// block r: S[r] = np.sum(w_all[r*nw : (r+1)*nw])
-__global__ void k_branch_rank_sums(int nw, const double* __restrict__ w_all, double* __restrict__ S) {
-  if (threadIdx.x == 0) S[blockIdx.x] = np_pairwise_sum(w_all + (size_t)blockIdx.x * nw, nw);
+// The same sum with the leaves (contiguous runs of <= 128 elements, summed with NumPy's 8 accumulators) computed by different
+// threads and combined by thread 0 in NumPy's recursion order: bit-identical to np_pairwise_sum, ~30x shorter critical path.
+constexpr int MAX_LEAVES = 1024;
+__device__ void np_enum_leaves(int off, int n, int* lo, int* ln, int& cnt) {
+  if (n <= 128) {
+    lo[cnt] = off;
+    ln[cnt] = n;
+    ++cnt;
+    return;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  np_enum_leaves(off, n2, lo, ln, cnt);
+  np_enum_leaves(off + n2, n - n2, lo, ln, cnt);
+}
+__device__ double np_combine(int n, const double* leaf, int& idx) {
+  if (n <= 128) return leaf[idx++];
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  const double a = np_combine(n2, leaf, idx);
+  const double b = np_combine(n - n2, leaf, idx);
+  return a + b;
+}
+// all threads of the block call this; the result is valid in thread 0.  `a` may be global or shared memory.
+__device__ double block_np_sum(const double* __restrict__ a, int n, int* s_lo, int* s_ln, double* s_leaf, int* s_cnt) {
+  if (n > 128 * MAX_LEAVES / 2) return threadIdx.x == 0 ? np_pairwise_sum(a, n) : 0.0;  // very long vectors: serial
+  if (threadIdx.x == 0) {
+    int cnt = 0;
+    np_enum_leaves(0, n, s_lo, s_ln, cnt);
+    *s_cnt = cnt;
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < *s_cnt; l += blockDim.x) s_leaf[l] = np_pairwise_sum(a + s_lo[l], s_ln[l]);
+  __syncthreads();
+  double res = 0.0;
+  if (threadIdx.x == 0) {
+    int idx = 0;
+    res = np_combine(n, s_leaf, idx);
+  }
+  __syncthreads();
+  return res;
 }
 
-// block r: p = w / sum_r S[r];  P[r] = np.sum(p_r);  c_r = cumsum(p_r) (sequential fp64)
+// block r: S[r] = np.sum(w_all[r*nw : (r+1)*nw])
+__global__ void k_branch_rank_sums(int nw, const double* __restrict__ w_all, double* __restrict__ S) {
+  __shared__ int s_lo[MAX_LEAVES], s_ln[MAX_LEAVES], s_cnt;
+  __shared__ double s_leaf[MAX_LEAVES];
+  const double v = block_np_sum(w_all + (size_t)blockIdx.x * nw, nw, s_lo, s_ln, s_leaf, &s_cnt);
+  if (threadIdx.x == 0) S[blockIdx.x] = v;
+}
+
+// block r: p = w / sum_r S[r];  P[r] = np.sum(p_r);  c_r = cumsum(p_r) (sequential fp64, staged through shared memory)
 __global__ void k_branch_cumprob(int nw, int world, const double* __restrict__ w_all, const double* __restrict__ S,
                                  double* __restrict__ c, double* __restrict__ P) {
+  __shared__ int s_lo[MAX_LEAVES], s_ln[MAX_LEAVES], s_cnt;
+  __shared__ double s_leaf[MAX_LEAVES];
+  constexpr int CH = 2048;
+  __shared__ double s_buf[CH];
+  __shared__ double s_acc;
   const int r = blockIdx.x;
   double gsum = 0.0;
   for (int q = 0; q < world; ++q) gsum += S[q];
@@ -61,13 +112,27 @@ __global__ void k_branch_cumprob(int nw, int world, const double* __restrict__ w
   const double* wr = w_all + (size_t)r * nw;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) cr[i] = wr[i] / gsum;
   __syncthreads();
+  const double pr = block_np_sum(cr, nw, s_lo, s_ln, s_leaf, &s_cnt);
   if (threadIdx.x == 0) {
-    P[r] = np_pairwise_sum(cr, nw);
-    double acc = 0.0;
-    for (int i = 0; i < nw; ++i) {
-      acc += cr[i];
-      cr[i] = acc;
+    P[r] = pr;
+    s_acc = 0.0;
+  }
+  __syncthreads();
+  for (int base = 0; base < nw; base += CH) {
+    const int m = min(CH, nw - base);
+    for (int i = threadIdx.x; i < m; i += blockDim.x) s_buf[i] = cr[base + i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double acc = s_acc;
+      for (int i = 0; i < m; ++i) {
+        acc += s_buf[i];
+        s_buf[i] = acc;
+      }
+      s_acc = acc;
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) cr[base + i] = s_buf[i];
+    __syncthreads();
   }
 }
 
@@ -181,7 +246,7 @@ extern "C" int qe_lrdmc_branch(qe_engine* h, int nw, int world, const double* w_
   CUDA_TRY(cudaMemsetAsync(n_survived, 0, sizeof(int32_t), st));
   {
     LaunchScope ls_(h, K_BRANCH, st);
-    k_branch_rank_sums<<<world, 32, 0, st>>>(nw, w_all, S);
+    k_branch_rank_sums<<<world, 256, 0, st>>>(nw, w_all, S);
     k_branch_cumprob<<<world, 256, 0, st>>>(nw, world, w_all, S, c, P);
     k_branch_select<<<nblk(N, 128), 128, 0, st>>>(nw, world, c, P, zeta, chosen_all);
     k_branch_count<<<nblk(N, 128), 128, 0, st>>>(N, chosen_all, n_survived);

@@ -352,70 +352,103 @@ k_orb_electrons(BasisDev B, SysDev S, int nw, const double* __restrict__ r_up, c
 // G2: per-walker geminal matrix, inverse (Gauss-Jordan, partial pivoting), ln|det|, Jastrow value.
 // thread = walker.  phi[chunk][e][1][mo][w]
 // =================================================================================================
-template <int NMO>
+// NT = N_up when it is known at compile time (1..8: matrices live in registers, loops fully unrolled), 0 = run-time N <= 16
+template <int NMO, int NT>
 __global__ void k_geminal(SysDev S, int nw, int n_chunk, const double* __restrict__ phi, const double* __restrict__ r_up,
                           const double* __restrict__ r_dn, double* __restrict__ G_out, double* __restrict__ Ginv_out,
                           double* __restrict__ lnpsi_out, double* __restrict__ sign_out) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nw) return;
-  constexpr int NMAX = 16;
-  const int N = S.n_up, Nd = S.n_dn;
+  // block = 32 walkers (x) x 8 (y): the chunk partial sums of the orbital values are reduced cooperatively into shared
+  // memory (fixed chunk order), then one thread per walker does the small dense algebra
+  extern __shared__ double s_phi_g[];  // [(e*NMO + mo)][32]
+  const int lane = threadIdx.x;
+  const int wq = blockIdx.x * 32 + lane;
+  const int w = wq < nw ? wq : nw - 1;
+  constexpr int NMAX = NT ? NT : 16;
+  const int N = NT ? NT : S.n_up, Nd = S.n_dn;
+  for (int it = threadIdx.y; it < S.n_e * NMO; it += blockDim.y) {
+    double s = 0;
+    for (int c = 0; c < n_chunk; ++c) s += phi[((size_t)c * S.n_e * NMO + it) * nw + w];
+    s_phi_g[it * 32 + lane] = s;
+  }
+  __syncthreads();
+  if (threadIdx.y != 0 || wq >= nw) return;
+#define PHIS(e, mo) s_phi_g[((e) * NMO + (mo)) * 32 + lane]
   double G[NMAX * NMAX], I[NMAX * NMAX];
   // G[i][j] = sum_{a,b} PhiU[a][i] lam_p[a][b] PhiD[b][j] ; unpaired columns: sum_a PhiU[a][i] lam_u[a][k]
-  for (int i = 0; i < N; ++i) {
-    double pu[NMO];
-    for (int a = 0; a < NMO; ++a) {
-      double s = 0;
-      for (int c = 0; c < n_chunk; ++c) s += phi[(((size_t)c * S.n_e + i) * NMO + a) * nw + w];
-      pu[a] = s;
-    }
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+    if (i >= N) break;
     double t[NMO];
+#pragma unroll
     for (int b = 0; b < NMO; ++b) {
       double s = 0;
-      for (int a = 0; a < NMO; ++a) s = fma(pu[a], S.lam_p[a * NMO + b], s);
+#pragma unroll
+      for (int a = 0; a < NMO; ++a) s = fma(PHIS(i, a), S.lam_p[a * NMO + b], s);
       t[b] = s;
     }
-    for (int j = 0; j < Nd; ++j) {
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) {
+      if (j >= N) break;
       double s = 0;
-      for (int b = 0; b < NMO; ++b) {
-        double pd = 0;
-        for (int c = 0; c < n_chunk; ++c) pd += phi[(((size_t)c * S.n_e + (N + j)) * NMO + b) * nw + w];
-        s = fma(t[b], pd, s);
+      if (j < Nd) {
+#pragma unroll
+        for (int b = 0; b < NMO; ++b) s = fma(t[b], PHIS(N + j, b), s);
+      } else {
+        const int k = j - Nd;
+        for (int a = 0; a < NMO; ++a) s = fma(PHIS(i, a), S.lam_u[a * S.n_unp + k], s);
       }
       G[i * N + j] = s;
     }
-    for (int k = 0; k < S.n_unp; ++k) {
-      double s = 0;
-      for (int a = 0; a < NMO; ++a) s = fma(pu[a], S.lam_u[a * S.n_unp + k], s);
-      G[i * N + Nd + k] = s;
-    }
   }
-  if (G_out)
-    for (int i = 0; i < N * N; ++i) G_out[(size_t)w * N * N + i] = G[i];
+#undef PHIS
+  if (G_out) {
+#pragma unroll
+    for (int i = 0; i < NMAX * NMAX; ++i)
+      if (i < N * N) G_out[(size_t)w * N * N + i] = G[i];
+  }
   // Gauss-Jordan with partial pivoting on a copy
   double A[NMAX * NMAX];
-  for (int i = 0; i < N * N; ++i) {
-    A[i] = G[i];
-    I[i] = 0.0;
-  }
-  for (int i = 0; i < N; ++i) I[i * N + i] = 1.0;
+#pragma unroll
+  for (int i = 0; i < NMAX * NMAX; ++i)
+    if (i < N * N) {
+      A[i] = G[i];
+      I[i] = (i / N == i % N) ? 1.0 : 0.0;
+    }
   double lndet = 0.0, sgn = 1.0;
+#pragma unroll
   for (int c = 0; c < N; ++c) {
     int piv = c;
     double best = fabs(A[c * N + c]);
+#pragma unroll
     for (int r = c + 1; r < N; ++r)
       if (fabs(A[r * N + c]) > best) {
         best = fabs(A[r * N + c]);
         piv = r;
       }
     if (piv != c) {
-      for (int j = 0; j < N; ++j) {
-        double tmp = A[c * N + j];
-        A[c * N + j] = A[piv * N + j];
-        A[piv * N + j] = tmp;
-        tmp = I[c * N + j];
-        I[c * N + j] = I[piv * N + j];
-        I[piv * N + j] = tmp;
+      if (NT) {  // compile-time row indices only (registers): conditional swap against every candidate row
+#pragma unroll
+        for (int r = c + 1; r < N; ++r)
+          if (r == piv) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+              double tmp = A[c * N + j];
+              A[c * N + j] = A[r * N + j];
+              A[r * N + j] = tmp;
+              tmp = I[c * N + j];
+              I[c * N + j] = I[r * N + j];
+              I[r * N + j] = tmp;
+            }
+          }
+      } else {
+        for (int j = 0; j < N; ++j) {
+          double tmp = A[c * N + j];
+          A[c * N + j] = A[piv * N + j];
+          A[piv * N + j] = tmp;
+          tmp = I[c * N + j];
+          I[c * N + j] = I[piv * N + j];
+          I[piv * N + j] = tmp;
+        }
       }
       sgn = -sgn;
     }
@@ -423,21 +456,27 @@ __global__ void k_geminal(SysDev S, int nw, int n_chunk, const double* __restric
     lndet += log(fabs(d));
     if (d < 0) sgn = -sgn;
     const double inv = 1.0 / d;
+#pragma unroll
     for (int j = 0; j < N; ++j) {
       A[c * N + j] *= inv;
       I[c * N + j] *= inv;
     }
+#pragma unroll
     for (int r = 0; r < N; ++r) {
       if (r == c) continue;
       const double f = A[r * N + c];
+#pragma unroll
       for (int j = 0; j < N; ++j) {
         A[r * N + j] = fma(-f, A[c * N + j], A[r * N + j]);
         I[r * N + j] = fma(-f, I[c * N + j], I[r * N + j]);
       }
     }
   }
-  if (Ginv_out)
-    for (int i = 0; i < N * N; ++i) Ginv_out[(size_t)w * N * N + i] = I[i];
+  if (Ginv_out) {
+#pragma unroll
+    for (int i = 0; i < NMAX * NMAX; ++i)
+      if (i < N * N) Ginv_out[(size_t)w * N * N + i] = I[i];
+  }
   if (lnpsi_out) {
     // Jastrow value J1 + J2 (jqmc/jastrow_factor.py:2127-2178)
     PosGlobal pos{r_up, r_dn, S.n_up, S.n_dn, w};
@@ -1115,6 +1154,26 @@ extern "C" int qe_eval_orbitals(qe_engine* h, int which, int layer, int n_pts, c
   return QE_OK;
 }
 
+// k_geminal with N_up as a compile-time constant when it is small (register-resident Gauss-Jordan)
+#define GEMINAL_LAUNCH(NMO, NT, ARGS)                                                                                     \
+  do {                                                                                                                    \
+    const size_t smem_ = (size_t)S.n_e * NMO * 32 * 8;                                                                    \
+    CUDA_TRY(cudaFuncSetAttribute(k_geminal<NMO, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_));         \
+    k_geminal<NMO, NT><<<nblk(nw, 32), dim3(32, 8), smem_, st>>> ARGS;                                                    \
+  } while (0)
+#define GEMINAL_NT(NMO, ARGS)                          \
+  do {                                                 \
+    switch (S.n_up) {                                  \
+      case 1: GEMINAL_LAUNCH(NMO, 1, ARGS); break;     \
+      case 2: GEMINAL_LAUNCH(NMO, 2, ARGS); break;     \
+      case 3: GEMINAL_LAUNCH(NMO, 3, ARGS); break;     \
+      case 4: GEMINAL_LAUNCH(NMO, 4, ARGS); break;     \
+      case 5: GEMINAL_LAUNCH(NMO, 5, ARGS); break;     \
+      case 6: GEMINAL_LAUNCH(NMO, 6, ARGS); break;     \
+      default: GEMINAL_LAUNCH(NMO, 0, ARGS); break;    \
+    }                                                  \
+  } while (0)
+
 static size_t ws_need_common(const qe_engine* h, int nw, int n_chunk, int nq) {
   const SysDev& S = h->sys;
   size_t n = 0;
@@ -1147,7 +1206,7 @@ extern "C" int qe_geminal_init(qe_engine* h, int nw, const double* r_up, const d
   }
   CHECK_LAUNCH();
   { LaunchScope ls_(h, K_GEMINAL, st);
-#define CALL(NMO) k_geminal<NMO><<<nblk(nw, 64), 64, 0, st>>>(S, nw, h->b_up.n_chunk, phi, r_up, r_dn, G, Ginv, nullptr, nullptr)
+#define CALL(NMO) GEMINAL_NT(NMO, (S, nw, h->b_up.n_chunk, phi, r_up, r_dn, G, Ginv, nullptr, nullptr))
   DISPATCH_NMO(h, CALL);
 #undef CALL
   }
@@ -1175,7 +1234,7 @@ extern "C" int qe_ln_wavefunction(qe_engine* h, int nw, const double* r_up, cons
   }
   CHECK_LAUNCH();
   { LaunchScope ls_(h, K_GEMINAL, st);
-#define CALL(NMO) k_geminal<NMO><<<nblk(nw, 64), 64, 0, st>>>(S, nw, h->b_up.n_chunk, phi, r_up, r_dn, nullptr, nullptr, ln_psi, sign)
+#define CALL(NMO) GEMINAL_NT(NMO, (S, nw, h->b_up.n_chunk, phi, r_up, r_dn, nullptr, nullptr, ln_psi, sign))
   DISPATCH_NMO(h, CALL);
 #undef CALL
   }
