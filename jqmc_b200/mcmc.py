@@ -319,6 +319,64 @@ class MCMC:
         return jackknife_gF(w_L, e_L, O, num_mcmc_bin_blocks, self.engine.device)
 
 
+    def get_sr_direction(self, num_mcmc_warmup_steps: int = 0, epsilon: float = 1e-3, use_cg: bool = False, blocks=None,
+                         cg_max_iter: int = 10000, cg_tol: float = 1e-10):  # fmt: skip
+        """Natural-gradient direction theta (flattened over ``blocks`` in BLOCK_ORDER) from the stored samples of all ranks:
+        the SR solve of jqmc_mcmc.py:2960-3330 on the device (jqmc_b200.sr).  Returns (theta[K] ndarray, info)."""
+        from .sr import sr_natural_gradient
+
+        dev = self.engine.device
+        O = torch.from_numpy(self.get_dln_WF(num_mcmc_warmup_steps, None, blocks)).to(dev)
+        w = torch.from_numpy(self.w_L[num_mcmc_warmup_steps:]).to(dev)
+        e = torch.from_numpy(self.e_L[num_mcmc_warmup_steps:]).to(dev)
+        theta, info = sr_natural_gradient(w, e, O, epsilon=epsilon, use_cg=use_cg, cg_max_iter=cg_max_iter, cg_tol=cg_tol)
+        return theta.cpu().numpy(), info
+
+    def run_optimize(self, num_mcmc_steps: int = 100, num_opt_steps: int = 1, num_mcmc_warmup_steps: int = 0, delta: float = 1e-2,
+                     epsilon: float = 1e-3, use_cg: bool = False, opt_J1_param: bool = True, opt_J2_param: bool = True,
+                     opt_J3_param: bool = True, opt_lambda_param: bool = False, num_mcmc_bin_blocks: int = 5):  # fmt: skip
+        """Plain SR optimisation loop (the ``sr`` branch of jqmc_mcmc.py:2368-3900 without its adaptive learning rate, SNR
+        filters, lambda projection and block symmetrisation): sample, solve, c <- c + delta * theta, rebuild the device
+        tables (qe_create) and continue from the current walkers.  Returns [(E, dE, max|f|)] per step."""
+        import dataclasses
+
+        if not self.__comput_log_WF_param_deriv:
+            raise ValueError("run_optimize needs comput_log_WF_param_deriv=True")
+        flags = dict(j1_param=opt_J1_param, j2_param=opt_J2_param, j3_matrix=opt_J3_param, lambda_matrix=opt_lambda_param)
+        history = []
+        for _ in range(num_opt_steps):
+            self.__init_attributes()
+            self.run(num_mcmc_steps)
+            E, dE, _, _ = self.get_E(num_mcmc_warmup_steps, min(num_mcmc_bin_blocks, self.mcmc_counter - num_mcmc_warmup_steps))
+            blocks = [n for n in self.BLOCK_ORDER if n in self.__stored_dln and flags[n]]
+            theta, info = self.get_sr_direction(num_mcmc_warmup_steps, epsilon, use_cg, blocks)
+            history.append((E, dE, float(info["f"].abs().max())))
+            H = self.hamiltonian_data
+            wf = H.wavefunction_data
+            jd, gem = wf.jastrow_data, wf.geminal_data
+            off = 0
+            for n in blocks:
+                shape = np.array(self.__stored_dln[n][0]).shape[1:]
+                size = int(np.prod(shape)) if shape else 1
+                step = delta * theta[off : off + size].reshape(shape)
+                off += size
+                if n == "j1_param":
+                    j1 = jd.jastrow_one_body_data
+                    jd = dataclasses.replace(jd, jastrow_one_body_data=dataclasses.replace(j1, jastrow_1b_param=float(j1.jastrow_1b_param + step)))
+                elif n == "j2_param":
+                    j2 = jd.jastrow_two_body_data
+                    jd = dataclasses.replace(jd, jastrow_two_body_data=dataclasses.replace(j2, jastrow_2b_param=float(j2.jastrow_2b_param + step)))
+                elif n == "j3_matrix":
+                    j3 = jd.jastrow_three_body_data
+                    jd = dataclasses.replace(jd, jastrow_three_body_data=dataclasses.replace(j3, j_matrix=np.asarray(j3.j_matrix) + step))
+                else:
+                    gem = dataclasses.replace(gem, lambda_matrix=np.asarray(gem.lambda_matrix) + step)
+            self.hamiltonian_data = dataclasses.replace(H, wavefunction_data=dataclasses.replace(wf, jastrow_data=jd, geminal_data=gem))
+            self.engine = WalkerEngine(self.hamiltonian_data, Nv=self.engine.Nv, NN=self.engine.NN)  # tables change with the parameters
+            self.__init_attributes()  # the stored samples belong to the old parameters
+        return history
+
+
 def jackknife_gF(w_L, e_L, O, num_bin_blocks, device=None):
     """(mean[K], std[K]) of -2 (<e_L O> - <e_L><O>) by binned jackknife; sums over ranks via torch.distributed."""
 

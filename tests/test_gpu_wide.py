@@ -475,6 +475,33 @@ def test_parameter_derivatives(case):
             np.testing.assert_allclose(got[k][w], v, rtol=1e-9, atol=1e-11 * max(1.0, np.abs(v).max()))
 
 
+def test_sr_optimisation_moves_a_bad_jastrow_parameter_towards_lower_energy():
+    """BASELINE configs[3] capability at test size: VMC with stored O_k, generalised forces and SR steps on the device.  Start
+    from a deliberately poor two-body parameter (a = 2.5): every natural-gradient step must move it towards the optimum."""
+    from jqmc_b200.mcmc import MCMC
+
+    H = copy.deepcopy(load_system("water_ccecp_ccpvqz"))
+    H.wavefunction_data.jastrow_data = Jastrow_data(jastrow_two_body_data=Jastrow_two_body_data(jastrow_2b_param=2.5))
+    m = MCMC(H, mcmc_seed=5, num_walkers=1024, num_mcmc_per_measurement=16, Dt=2.0, epsilon_AS=0.0, comput_log_WF_param_deriv=True)
+    a_hist = [2.5]
+    for _ in range(4):  # the optimum of this one-parameter Jastrow is a ~ 0.7 (the TurboRVB-optimised value of the golden tests)
+        m.run_optimize(num_mcmc_steps=34, num_opt_steps=1, num_mcmc_warmup_steps=4, delta=0.02, epsilon=1e-3)
+        a_hist.append(m.hamiltonian_data.wavefunction_data.jastrow_data.jastrow_two_body_data.jastrow_2b_param)
+    assert all(b < a for a, b in zip(a_hist, a_hist[1:])), a_hist
+    assert a_hist[-1] < 2.3, a_hist
+    m.run(34)
+    f, df = m.get_gF(num_mcmc_warmup_steps=4, num_mcmc_bin_blocks=5)
+    assert f.shape == (1,) and df[0] > 0 and f[0] < 0, (f, df)  # f = -dE/da < 0: the energy still falls towards smaller a
+    # with lambda: the flattened O matrix has the reference's block layout
+    m2 = MCMC(H, mcmc_seed=5, num_walkers=64, num_mcmc_per_measurement=8, Dt=2.0, epsilon_AS=0.0, comput_log_WF_param_deriv=True)
+    m2.run(6)
+    O = m2.get_dln_WF(num_mcmc_warmup_steps=1)
+    lam = np.shape(H.wavefunction_data.geminal_data.lambda_matrix)
+    assert O.shape == (5, 64, 1 + lam[0] * lam[1])
+    theta, info = m2.get_sr_direction(1, epsilon=1e-2)
+    assert theta.shape == (1 + lam[0] * lam[1],) and np.all(np.isfinite(theta))
+
+
 def test_wide_equals_register_kernels_at_scale():
     """water JSD + J2, 1000 walkers (not a multiple of any tile): the general path and the register/shared-memory kernels give
     the same e_L, the same Metropolis decisions and the same LRDMC moves; the tensor-core GEMM equals the plain DFMA GEMM."""
