@@ -485,12 +485,12 @@ def test_sr_optimisation_moves_a_bad_jastrow_parameter_towards_lower_energy():
     m = MCMC(H, mcmc_seed=5, num_walkers=1024, num_mcmc_per_measurement=16, Dt=2.0, epsilon_AS=0.0, comput_log_WF_param_deriv=True)
     # E(a) of this one-parameter wavefunction falls steeply with a up to a ~ 3 (profiles/r01_sr_landscape.md: E(1.0) = -16.61,
     # E(1.5) = -16.89, E(2.5) = -17.00, f(1.0) = -dE/da = +1.05): every natural-gradient step must increase a
-    hist = m.run_optimize(num_mcmc_steps=34, num_opt_steps=5, num_mcmc_warmup_steps=4, delta=0.005, epsilon=1e-3)
+    hist = m.run_optimize(num_mcmc_steps=44, num_opt_steps=5, num_mcmc_warmup_steps=14, delta=0.05, epsilon=1e-3)
     a_new = m.hamiltonian_data.wavefunction_data.jastrow_data.jastrow_two_body_data.jastrow_2b_param
-    assert a_new > 1.1, (a_new, hist)
-    assert hist[-1][0] < hist[0][0] - 0.05, hist
+    assert a_new > 1.2, (a_new, hist)
+    assert hist[-1][0] < hist[0][0] - 0.1, hist
     m.run(34)
-    f, df = m.get_gF(num_mcmc_warmup_steps=4, num_mcmc_bin_blocks=5)
+    f, df = m.get_gF(num_mcmc_warmup_steps=4, num_mcmc_bin_blocks=5, blocks=["j2_param"])
     assert f.shape == (1,) and df[0] > 0 and f[0] > 3 * df[0], (f, df)  # still downhill towards larger a
     # with lambda: the flattened O matrix has the reference's block layout
     m2 = MCMC(H, mcmc_seed=5, num_walkers=64, num_mcmc_per_measurement=8, Dt=2.0, epsilon_AS=0.0, comput_log_WF_param_deriv=True)
