@@ -262,7 +262,7 @@ def run_gpu(args, rank, local_rank, world):
 
     def step_lrdmc(state):
         r_up, r_dn, keys, A_inv = state
-        r_up, r_dn, keys, A_inv, sums, n_surv = gf._step(r_up, r_dn, keys, A_inv, float(zeta_rng.random_sample()), rank, world)
+        r_up, r_dn, keys, A_inv, sums, n_surv, _ = gf._step(r_up, r_dn, keys, A_inv, float(zeta_rng.random_sample()), rank, world)
         return (r_up, r_dn, keys, A_inv), (sums, n_surv)
 
     def barrier():

@@ -139,6 +139,16 @@ int qe_lrdmc_project(qe_engine* h, int nw, double* w, double* r_up, double* r_dn
                      double E_scf, int nmpm, int random_discretized_mesh, int non_local_move, double alat,
                      double* RT, double* V_diag, double* V_nondiag, void* stream);
 
+/* GFMC_t projection loop (jqmc/jqmc_gfmc.py:724-1110 `_projection_t_core`, driver `_run_projection_loop` :1539-1570):
+ * every walker is propagated for the imaginary time tau by continuous-time lattice-regularised projections
+ * (time step log(1-xi)/V_nondiag, weight *= exp(-dt e_L), move chosen as in GFMC_n) until its time is used up.
+ * w[nw], r_up, r_dn, Ginv, keys updated in place; projection_counter[nw] (int32), e_L[nw], RT[nw,3,3] written.
+ * As in the reference's vmapped while_loop, walkers that finish early keep splitting their keys (three splits per
+ * iteration) until the slowest walker OF THIS CALL is done, and e_L / RT belong to that last iteration. */
+int qe_lrdmc_project_tau(qe_engine* h, int nw, double* w, double* r_up, double* r_dn, double* Ginv, uint32_t* keys,
+                         double tau, int random_discretized_mesh, int non_local_move, double alat,
+                         int32_t* projection_counter, double* e_L, double* RT, void* stream);
+
 /* GFMC_n._compute_V_elements_n (jqmc/jqmc_gfmc.py:5360-5627, 5660). */
 int qe_lrdmc_velements(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT,
                        const double* Ginv, int non_local_move, double alat, double* V_diag, double* V_nondiag,
@@ -146,7 +156,9 @@ int qe_lrdmc_velements(qe_engine* h, int nw, const double* r_up, const double* r
 
 /* Per-step weighted sums of GFMC_n.run (jqmc/jqmc_gfmc.py:5971-5976), e_L = V_diag + V_nondiag:
  * out5 (device) = { nw, sum w, sum w/(V_diag-E_scf), sum w/(V_diag-E_scf) e_L, sum w/(V_diag-E_scf) e_L^2 }.
- * The caller sums out5 over ranks (the reference: mpi reduce, :6016-6020). */
+ * The caller sums out5 over ranks (the reference: mpi reduce, :6016-6020).
+ * GFMC_t form (jqmc/jqmc_gfmc.py:1929-1932): V_diag == NULL, V_nondiag holds e_L; out5 = { nw, sum w, sum w, sum w e_L,
+ * sum w e_L^2 }. */
 int qe_lrdmc_collect(qe_engine* h, int nw, const double* w, const double* V_diag, const double* V_nondiag, double E_scf,
                      double* out5, void* stream);
 

@@ -90,6 +90,10 @@ EXPORTS = {
         C.c_int,
         [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_double, C.c_int, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 4,
     ),
+    "qe_lrdmc_project_tau": (
+        C.c_int,
+        [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_double, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 4,
+    ),
     "qe_lrdmc_velements": (
         C.c_int,
         [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_double] + [C.c_void_p] * 3,

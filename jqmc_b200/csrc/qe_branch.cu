@@ -185,13 +185,15 @@ __global__ void k_gather_walkers(int nw, int per_up, int per_dn, const int* __re
 }
 
 // per-step weighted sums (jqmc/jqmc_gfmc.py:5971-5976): out = {nw, sum w, sum w/(Vd-E), sum w/(Vd-E) e, sum w/(Vd-E) e^2}
+// GFMC_t form when Vd == nullptr (jqmc/jqmc_gfmc.py:1929-1932): Vn holds e_L, q = w (no division by V_diag - E_scf)
 // one block, fixed-order tree reduction (deterministic)
 __global__ void k_lrdmc_collect(int nw, const double* __restrict__ w, const double* __restrict__ Vd,
                                 const double* __restrict__ Vn, double E_scf, double* __restrict__ out) {
   __shared__ double sm[4][256];
   double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
   for (int i = threadIdx.x; i < nw; i += 256) {
-    const double wi = w[i], e = Vd[i] + Vn[i], q = wi / (Vd[i] - E_scf);
+    const double wi = w[i];
+    const double e = Vd ? Vd[i] + Vn[i] : Vn[i], q = Vd ? wi / (Vd[i] - E_scf) : wi;
     a0 += wi;
     a1 += q;
     a2 += q * e;
@@ -217,7 +219,7 @@ __global__ void k_lrdmc_collect(int nw, const double* __restrict__ w, const doub
 
 extern "C" int qe_lrdmc_collect(qe_engine* h, int nw, const double* w, const double* V_diag, const double* V_nondiag, double E_scf,
                                 double* out5, void* stream) {
-  if (!h || nw <= 0 || !w || !V_diag || !V_nondiag || !out5) return fail(QE_ERR_INVALID, "qe_lrdmc_collect: bad argument");
+  if (!h || nw <= 0 || !w || !V_nondiag || !out5) return fail(QE_ERR_INVALID, "qe_lrdmc_collect: bad argument");
   {
     LaunchScope ls_(h, K_COLLECT, (cudaStream_t)stream);
     k_lrdmc_collect<<<1, 256, 0, (cudaStream_t)stream>>>(nw, w, V_diag, V_nondiag, E_scf, out5);

@@ -125,13 +125,14 @@ struct qe_engine {
 
 enum KernelId { K_ORB_EL = 0, K_GEMINAL, K_ALGEBRA, K_ECP_MESH, K_REDUCE, K_RATIOS, K_AS, K_ROT, K_KEYCHAIN, K_DRAWS, K_MCMC,
                 K_EVAL, K_LRDMC, K_EL_FUSED, K_LRDMC_PROJ, K_COLLECT, K_BRANCH, K_GATHER,
-                K_W_AO, K_W_GEMM, K_W_BMM, K_W_INV, K_W_MESH, K_W_ELEC, K_W_SELECT, K_W_COMMIT, K_W_DECIDE, K_W_MISC, K_COUNT };
+                K_W_AO, K_W_GEMM, K_W_BMM, K_W_INV, K_W_MESH, K_W_ELEC, K_W_SELECT, K_W_COMMIT, K_W_DECIDE, K_W_MISC, K_LRDMC_TAU, K_LRDMC_TAU_TAIL, K_COUNT };
 static const char* const KERNEL_NAMES[K_COUNT] = {"k_orb_electrons", "k_geminal", "k_electron_algebra", "k_ecp_mesh", "k_reduce_eL",
                                                   "k_move_ratios", "k_as_factor", "k_rotation", "k_mcmc_keychain", "k_mcmc_draws",
                                                   "k_mcmc", "k_eval_orbitals", "k_walker(V_elements)", "k_walker(e_L)", "k_walker(projection)", "k_lrdmc_collect",
                                                   "k_branch", "k_gather_walkers",
                                                   "kw_ao_store", "kw_dgemm(DMMA)", "kw_bmm", "kw_inverse", "kw_mesh", "kw_electron",
-                                                  "kw_lrdmc_select", "kw_lrdmc_commit", "kw_mc_decide", "kw_misc"};
+                                                  "kw_lrdmc_select", "kw_lrdmc_commit", "kw_mc_decide", "kw_misc", "k_walker(projection_tau)",
+                                                  "k_walker(projection_tau tail)"};
 struct LaunchScope {
   qe_engine* h;
   cudaStream_t st;
@@ -459,6 +460,8 @@ int wide_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, uint32_t*
 int wide_lrdmc(qe_engine* h, int mode, int nw, double* w, double* r_up, double* r_dn, double* Ginv, uint32_t* keys, double E_scf,
                int nmpm, int random_mesh, int non_local_move, double alat, const double* RT_in, double* RT_out, double* V_diag,
                double* V_nondiag, cudaStream_t st);
+int wide_lrdmc_tau(qe_engine* h, int nw, double* w, double* r_up, double* r_dn, double* Ginv, uint32_t* keys, double tau,
+                   int random_mesh, int non_local_move, double alat, int32_t* pc, double* e_L, double* RT_out, cudaStream_t st);
 int wide_eval_orbitals(qe_engine* h, int which, int n_pts, const double* r, double* out, cudaStream_t st);
 int wide_dln_wf(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* Ginv, double* d_j1, double* d_j2,
                 double* d_j3, double* d_lambda, cudaStream_t st);

@@ -38,7 +38,27 @@ struct WalkerArgs {
   const double* rRT;  // mode 0 draws: [(it*9+c)][nw]
   const double* ru;   //               [it][nw]
   int off_cseg, off_cbeg, n_chunk;
+  // continuous-time projection (GFMC_t, template TAU): the draws are made in the kernel because the number of
+  // projections is not known in advance
+  double tau;
+  int tail, random_mesh;
+  uint32_t* keys;  // [nw][2], advanced in place
+  int* pc;         // [nw] projection counter (out)
+  int* n_cta;      // [grid] projections this CTA executed (out in the main pass, in in the tail pass)
+  int* n_max;      // [1] max over the grid (atomicMax in the main pass)
 };
+
+// R^T (row-major) of R = Rz(gamma) Ry(beta) Rx(alpha), jqmc/jqmc_mcmc.py:4237-4244
+__device__ __forceinline__ void rt_from_angles(double al, double be, double ga, double* RT) {
+  double sa, ca, sb, cb, sg, cg;
+  sincos(al, &sa, &ca);
+  sincos(be, &sb, &cb);
+  sincos(ga, &sg, &cg);
+  const double R[9] = {cb * cg, cg * sa * sb - ca * sg, sa * sg + ca * cg * sb, cb * sg, ca * cg + sa * sb * sg,
+                       ca * sb * sg - cg * sa, -sb, cb * sa, ca * cb};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) RT[i * 3 + j] = R[j * 3 + i];
+}
 
 // shared-memory carve-up by byte offsets from the (16-byte aligned) dynamic shared memory base
 struct Carve {
@@ -99,11 +119,20 @@ struct PosShared {
   }
 };
 
-template <int NMO, bool CART, int LMAX>
+template <int NMO, bool CART, int LMAX, bool TAU>
 __global__ void __launch_bounds__(512, 1)
 k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
   extern __shared__ __align__(16) char smem_raw[];
   const int tid = threadIdx.x, nthr = blockDim.x;
+  // GFMC_t tail pass: this CTA replays the no-op iterations the reference's while_loop makes every walker run until the
+  // slowest walker of the rank has used up its time (jqmc/jqmc_gfmc.py:1539-1570)
+  int n_extra = 0;
+  if constexpr (TAU) {
+    if (P.tail) {
+      n_extra = *P.n_max - P.n_cta[blockIdx.x];
+      if (n_extra <= 0) return;
+    }
+  }
   const int lane = tid & 31, wid = tid >> 5, NWARP = nthr >> 5;
   const int WPC = P.wpc;
   const int w0 = blockIdx.x * WPC;
@@ -174,7 +203,23 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
   const double a2 = P.alat * P.alat;
   const int n_it = P.mode == 0 ? P.nmpm : 1;
   double w_L = 1.0, diag = 0.0, nondiag = 0.0;  // meaningful in threads tid < WPC (wl = tid)
-  if (P.mode == 0 && tid < WPC) w_L = P.w[GW(tid)];
+  if (P.mode == 0 && tid < WPC && !(TAU && P.tail)) w_L = P.w[GW(tid)];
+  // GFMC_t per-walker registers (threads tid < WPC)
+  Key key{0u, 0u};
+  double tau_left = 0.0, xi = 0.0, u_move = 0.0;
+  int pc = 0, n_done = 0;
+  if constexpr (TAU) {
+    if (tid < WPC) {
+      const int ww = GW(tid);
+      key = Key{P.keys[2 * ww], P.keys[2 * ww + 1]};
+      if (!P.tail) tau_left = P.tau;
+      else
+        for (int i = 0; i < 3 * (n_extra - 1); ++i) {
+          Key sub;
+          rng_split(key, sub);
+        }
+    }
+  }
   // mesh-point slot blocks (same spin => same MO coefficient table): kinetic up, kinetic dn, ECP up, ECP dn
   const int n_eu = S.ecp_flag ? N * S.NN * S.Nv : 0, n_ed = S.ecp_flag ? Nd * S.NN * S.Nv : 0;
   const int n_ku = P.mode == 2 ? 0 : 6 * N, n_kd = P.mode == 2 ? 0 : 6 * Nd;
@@ -184,9 +229,31 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
   const int n_rounds_pt = (blk_pairs[0] + blk_pairs[1] + blk_pairs[2] + blk_pairs[3] + 31) / 32;
   const int n_rounds_el = (Ne * WPC + 31) / 32;
 
-  for (int it = 0; it < n_it; ++it) {
+  for (int it = 0; TAU || it < n_it; ++it) {
     // ---- P1: ratio weight vectors, task = (walker, electron) -----------------------------------------------------
-    if (P.mode == 0)
+    if constexpr (TAU) {
+      // three splits per projection: rotation angles, time draw, move draw (jqmc/jqmc_gfmc.py:770-776, 1004-1018)
+      if (tid < WPC) {
+        const int wl = tid;
+        Key sub;
+        rng_split(key, sub);
+        double al = 0, be = 0, ga = 0;
+        if (P.random_mesh) {
+          const double two_pi = 6.283185307179586;
+          al = rng_uniform_bits(rng_bits64(sub, 0u), -two_pi, two_pi);
+          be = rng_uniform_bits(rng_bits64(sub, 1u), -two_pi, two_pi);
+          ga = rng_uniform_bits(rng_bits64(sub, 2u), -two_pi, two_pi);
+        }
+        double RTl[9];
+        rt_from_angles(al, be, ga, RTl);
+#pragma unroll
+        for (int c = 0; c < 9; ++c) SMISC(c) = RTl[c];
+        rng_split(key, sub);
+        xi = rng_uniform_bits(rng_bits64(sub), 0.0, 1.0);
+        rng_split(key, sub);
+        u_move = rng_uniform_bits(rng_bits64(sub), 0.0, 1.0);
+      }
+    } else if (P.mode == 0)
       for (int idx = tid; idx < 9 * WPC; idx += nthr) {
         const int wl = idx % WPC, c = idx / WPC;
         s_misc[idx] = P.rRT[((size_t)it * 9 + c) * P.nw + GW(wl)];
@@ -471,7 +538,19 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       }
       nondiag = sum_kinFN + sum_eFN;
       diag = S.ecp_flag ? diag_kin + disc_bare + loc + SP_kin + SP_e : diag_kin + disc_bare + SP_kin;
-      if (P.mode == 0) {
+      if constexpr (TAU) {
+        // time spent in this configuration, weight, remaining time (jqmc/jqmc_gfmc.py:1003-1012); the move is suppressed
+        // once the time is used up (:1024-1025)
+        const double e_L = diag + nondiag;
+        if (tau_left > 0.0) ++pc;
+        const double tau_update = fmin(tau_left, log(1.0 - xi) / nondiag);
+        w_L *= qexp(-tau_update * e_L);
+        tau_left -= tau_update;
+        SMISC(14) = tau_left <= 0.0 ? 0.0 : 1.0;
+        double tot = 0;
+        for (int k = 0; k < NPT; ++k) tot += s_p[k * WPC + wl];
+        SMISC(13) = tot;
+      } else if (P.mode == 0) {
         const double b_x = 1.0 / (diag - P.E_scf) * (-nondiag);
         w_L *= b_x;
         double tot = 0;
@@ -479,8 +558,14 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
         SMISC(13) = tot;
       }
     }
-    if (P.mode != 0) break;
-    __syncthreads();
+    if constexpr (TAU) {
+      n_done = it + 1;
+      const int mv = (tid < WPC) ? (s_misc[14 * WPC + tid] != 0.0) : 0;
+      if (!__syncthreads_or(mv)) break;  // every walker of the CTA has used up its time
+    } else {
+      if (P.mode != 0) break;
+      __syncthreads();
+    }
     // (c) all threads: p / total
     for (int s = tid; s < NPT * WPC; s += nthr) s_p[s] = s_p[s] / s_misc[13 * WPC + (s % WPC)];
     __syncthreads();
@@ -488,7 +573,7 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
     if (tid < WPC) {
       const int wl = tid;
       PosShared pos{s_r, WPC, wl};
-      const double u = P.ru[(size_t)it * P.nw + GW(wl)];
+      const double u = TAU ? u_move : P.ru[(size_t)it * P.nw + GW(wl)];
       int ksel = NPT - 1;
       double c = 0;
       for (int k = 0; k < NPT; ++k) {
@@ -551,11 +636,14 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
     {  // N * WPC <= blockDim.x is guaranteed by launch_walker: one pass
       double newrow[16];
       const int s = tid;
-      const bool act = s < N * WPC;
+      bool act = s < N * WPC;
       int wl = 0, i = 0;
       if (act) {
         wl = s % WPC;
         i = s / WPC;
+        if (TAU && SMISC(14) == 0.0) act = false;  // walker out of time: no move
+      }
+      if (act) {
         const int es = (int)SMISC(12);
         double pn[NMO];
 #pragma unroll
@@ -625,9 +713,10 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
     for (int s = tid; s < 5 * NMO * WPC; s += nthr) {
       const int wl = s % WPC, item = s / WPC;
       const int es = (int)SMISC(12);
+      if (TAU && SMISC(14) == 0.0) continue;
       s_phi[(es * 5 * NMO + item) * WPC + wl] = s_stage[s];
     }
-    if (tid < WPC) {
+    if (tid < WPC && !(TAU && s_misc[14 * WPC + tid] == 0.0)) {
       const int wl = tid;
       const int es = (int)SMISC(12);
       SR(es, 0) = SMISC(9);
@@ -639,7 +728,24 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
 
   // ---- write back -------------------------------------------------------------------------------------------
   if (P.mode == 2) return;
-  if (tid < WPC && w0 + tid < P.nw) {
+  if constexpr (TAU) {
+    if (tid < WPC && w0 + tid < P.nw) {
+      const int wl = tid, w = w0 + tid;
+      P.e_L[w] = diag + nondiag;
+      for (int c = 0; c < 9; ++c) P.RT_out[(size_t)w * 9 + c] = SMISC(c);
+      P.keys[2 * w] = key.a;
+      P.keys[2 * w + 1] = key.b;
+      if (!P.tail) {
+        P.w[w] = w_L;
+        P.pc[w] = pc;
+      }
+    }
+    if (P.tail) return;
+    if (tid == 0) {
+      P.n_cta[blockIdx.x] = n_done;
+      atomicMax(P.n_max, n_done);
+    }
+  } else if (tid < WPC && w0 + tid < P.nw) {
     const int wl = tid, w = w0 + tid;
     P.V_diag[w] = diag;
     P.V_nondiag[w] = nondiag;
@@ -733,7 +839,7 @@ int choose_wpc(int nw, int n_points, int sms, int ctas_per_sm, int wpc_max, int 
 // One CTA of 16 warps per SM: the warps of an SM then run the same phase of the projection loop at the same time, which
 // keeps the instruction working set (one phase, not the whole loop) inside the instruction caches; four independent
 // 4-warp CTAs per SM were measured 5x stalled on instruction fetch (profiles/r01_*).
-int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
+int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid, bool tau_mode = false) {
   const SysDev& S = h->sys;
   const int P = h->nmo_pad;
   if (S.n_up > 16) return fail(QE_ERR_UNSUPPORTED, "more than 16 electrons per spin is not implemented in this build");
@@ -759,10 +865,15 @@ int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
   const size_t smem = fixed + per_walker * 8 * A.wpc;
   {
     LaunchScope ls_(h, kid, st);
-#define CALL2(NMO, CART, LMAX)                                                                                         \
-  do {                                                                                                                 \
-    CUDA_TRY(cudaFuncSetAttribute(k_walker<NMO, CART, LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_walker<NMO, CART, LMAX><<<nblk(A.nw, A.wpc), NWARP * 32, smem, st>>>(h->b_up.dev, S, A);                          \
+#define CALL3(NMO, CART, LMAX, TAU)                                                                                         \
+  do {                                                                                                                      \
+    CUDA_TRY(cudaFuncSetAttribute(k_walker<NMO, CART, LMAX, TAU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_walker<NMO, CART, LMAX, TAU><<<nblk(A.nw, A.wpc), NWARP * 32, smem, st>>>(h->b_up.dev, S, A);                          \
+  } while (0)
+#define CALL2(NMO, CART, LMAX)                 \
+  do {                                         \
+    if (tau_mode) CALL3(NMO, CART, LMAX, true); \
+    else CALL3(NMO, CART, LMAX, false);        \
   } while (0)
 #define CALL(NMO, CART)                                  \
   do {                                                   \
@@ -772,6 +883,7 @@ int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
     DISPATCH_NMO_CART(h, CALL);
 #undef CALL
 #undef CALL2
+#undef CALL3
   }
   CHECK_LAUNCH();
   return QE_OK;
@@ -832,6 +944,55 @@ extern "C" int qe_lrdmc_project(qe_engine* h, int nw, double* w, double* r_up, d
   A.rRT = rRT;
   A.ru = ru;
   return launch_walker(h, A, st, K_LRDMC_PROJ);
+}
+
+// GFMC_t projection: every walker is propagated for the imaginary time tau (jqmc/jqmc_gfmc.py:724-1110, 1539-1570).
+// Main pass: one CTA runs its walkers until all of them are out of time and records how many projections that took; tail
+// pass: CTAs that finished before the slowest one replay the remaining (no-move) iterations of the reference's
+// while_loop -- three key splits each and a last evaluation of e_L with that iteration's mesh rotation -- so that keys,
+// e_L and RT equal what the reference returns.
+extern "C" int qe_lrdmc_project_tau(qe_engine* h, int nw, double* w, double* r_up, double* r_dn, double* Ginv, uint32_t* keys,
+                                    double tau, int random_discretized_mesh, int non_local_move, double alat,
+                                    int32_t* projection_counter, double* e_L, double* RT, void* stream) {
+  if (!h || nw <= 0 || !w || !r_up || !Ginv || !keys || !RT || !e_L || !projection_counter || (!r_dn && h->sys.n_dn > 0))
+    return fail(QE_ERR_INVALID, "qe_lrdmc_project_tau: bad argument");
+  if (!(alat > 0)) return fail(QE_ERR_INVALID, "qe_lrdmc_project_tau: alat must be positive");
+  if (!(tau > 0)) return fail(QE_ERR_INVALID, "qe_lrdmc_project_tau: tau must be positive");
+  if (non_local_move != 0 && non_local_move != 1)
+    return fail(QE_ERR_INVALID, "qe_lrdmc_project_tau: non_local_move must be 0 (tmove) or 1 (dltmove)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_wide(h))
+    return wide_lrdmc_tau(h, nw, w, r_up, r_dn, Ginv, keys, tau, random_discretized_mesh, non_local_move, alat, projection_counter,
+                          e_L, RT, st);
+  int rc = ensure_ws(h, (size_t)(nw + 8) * sizeof(int) + 4096);
+  if (rc) return rc;
+  WsCarve c{(char*)h->ws};
+  int* n_max = c.take<int>(4);
+  int* n_cta = c.take<int>((size_t)nw);
+  CUDA_TRY(cudaMemsetAsync(n_max, 0, 4 * sizeof(int), st));
+  WalkerArgs A{};
+  A.nw = nw;
+  A.nmpm = 1;
+  A.mode = 0;
+  A.dlt = non_local_move;
+  A.alat = alat;
+  A.w = w;
+  A.r_up = r_up;
+  A.r_dn = r_dn;
+  A.Ginv = Ginv;
+  A.RT_out = RT;
+  A.e_L = e_L;
+  A.tau = tau;
+  A.random_mesh = random_discretized_mesh;
+  A.keys = keys;
+  A.pc = projection_counter;
+  A.n_cta = n_cta;
+  A.n_max = n_max;
+  A.tail = 0;
+  rc = launch_walker(h, A, st, K_LRDMC_TAU, true);
+  if (rc) return rc;
+  A.tail = 1;
+  return launch_walker(h, A, st, K_LRDMC_TAU_TAIL, true);
 }
 
 extern "C" int qe_lrdmc_velements(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,

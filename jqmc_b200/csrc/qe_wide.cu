@@ -733,6 +733,14 @@ struct SelectArgs {
   double* V_nondiag;
   int* es;          // [w] selected electron
   double* pnew;     // [3][w]
+  // mode 3 (GFMC_t, jqmc/jqmc_gfmc.py:724-1110): per-walker remaining time, time draw, projection counter, local energy,
+  // move mask and the any-walker-still-running flag
+  double* tau_left;
+  const double* xi;
+  int* pc;
+  double* e_L;
+  int* active;
+  int* any_active;
 };
 __global__ void __launch_bounds__(256)
 kw_lrdmc_select(SysDev S, SelectArgs P) {
@@ -804,12 +812,29 @@ kw_lrdmc_select(SysDev S, SelectArgs P) {
   const double disc_bare = tot7[3] + S.v_ion_ion + tot7[2];
   const double nondiag = tot7[0] + tot7[5];
   const double diag = S.ecp_flag ? diag_kin + disc_bare + tot7[4] + tot7[1] + tot7[6] : diag_kin + disc_bare + tot7[1];
-  if (ty == 0 && live) {
+  if (ty == 0 && live && P.V_diag) {
     P.V_diag[w] = diag;
     P.V_nondiag[w] = nondiag;
   }
-  if (P.mode != 0) return;
-  if (ty == 0 && live) P.wL[w] *= 1.0 / (diag - P.E_scf) * (-nondiag);
+  if (P.mode == 3) {
+    if (ty == 0 && live) {
+      // time spent in this configuration, weight, remaining time; no move once the time is used up (:1003-1025)
+      const double e_L = diag + nondiag;
+      double tl = P.tau_left[w];
+      if (tl > 0.0) P.pc[w] += 1;
+      const double tau_update = fmin(tl, log(1.0 - P.xi[w]) / nondiag);
+      P.wL[w] *= qexp(-tau_update * e_L);
+      tl -= tau_update;
+      P.tau_left[w] = tl;
+      P.e_L[w] = e_L;
+      const int act = tl <= 0.0 ? 0 : 1;
+      P.active[w] = act;
+      if (act) atomicOr(P.any_active, 1);
+    }
+  } else {
+    if (P.mode != 0) return;
+    if (ty == 0 && live) P.wL[w] *= 1.0 / (diag - P.E_scf) * (-nondiag);
+  }
   const double tot = nondiag;  // sum of all fixed-node elements = normalisation of the move probabilities
   {
     double ck = 0, ce = 0;
@@ -912,6 +937,7 @@ struct MoveArgs {
   double* R_AS;         // [w] current AS factor
   int* acc;
   int* rej;
+  const int* active;    // [w] optional move mask (GFMC_t: walkers that are out of time do not move)
 };
 __global__ void __launch_bounds__(512)
 kw_move(SysDev S, MoveArgs P) {
@@ -1021,6 +1047,7 @@ kw_move(SysDev S, MoveArgs P) {
         }
       }
     }
+    if (P.active && P.active[ww] == 0) ok = false;
     s_flag[lane] = ok ? 1.0 : 0.0;
     s_flag[32 + lane] = 1.0 / Det;
   }
@@ -1683,15 +1710,68 @@ int wide_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, uint32_t*
 // -------------------------------------------------------------------------------------------------
 // GFMC_n._projection_n (mode 0) and _compute_V_elements_n (mode 1)
 // -------------------------------------------------------------------------------------------------
+// GFMC_t draws of one projection: three splits per walker (rotation, time, move), keys advanced in place; thread = walker
+__global__ void kw_tau_draws(int nw, int random_mesh, uint32_t* __restrict__ keys, double* __restrict__ RT, double* __restrict__ xi,
+                             double* __restrict__ u) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  Key key{keys[2 * w], keys[2 * w + 1]}, sub;
+  rng_split(key, sub);
+  double al = 0, be = 0, ga = 0;
+  if (random_mesh) {
+    const double two_pi = 6.283185307179586;
+    al = rng_uniform_bits(rng_bits64(sub, 0u), -two_pi, two_pi);
+    be = rng_uniform_bits(rng_bits64(sub, 1u), -two_pi, two_pi);
+    ga = rng_uniform_bits(rng_bits64(sub, 2u), -two_pi, two_pi);
+  }
+  double sa, ca, sb, cb, sg, cg;
+  sincos(al, &sa, &ca);
+  sincos(be, &sb, &cb);
+  sincos(ga, &sg, &cg);
+  const double R[9] = {cb * cg, cg * sa * sb - ca * sg, sa * sg + ca * cg * sb, cb * sg, ca * cg + sa * sb * sg,
+                       ca * sb * sg - cg * sa, -sb, cb * sa, ca * cb};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) RT[(size_t)(i * 3 + j) * nw + w] = R[j * 3 + i];
+  rng_split(key, sub);
+  xi[w] = rng_uniform_bits(rng_bits64(sub), 0.0, 1.0);
+  rng_split(key, sub);
+  u[w] = rng_uniform_bits(rng_bits64(sub), 0.0, 1.0);
+  keys[2 * w] = key.a;
+  keys[2 * w + 1] = key.b;
+}
+
+struct TauArgs {
+  double tau;
+  int32_t* pc;
+  double* e_L;
+};
+static int wide_lrdmc_impl(qe_engine* h, int mode, int nw, double* w, double* r_up, double* r_dn, double* Ginv, uint32_t* keys,
+                           double E_scf, int nmpm, int random_mesh, int non_local_move, double alat, const double* RT_in,
+                           double* RT_out, double* V_diag, double* V_nondiag, const TauArgs* ta, cudaStream_t st);
 int wide_lrdmc(qe_engine* h, int mode, int nw, double* w, double* r_up, double* r_dn, double* Ginv, uint32_t* keys, double E_scf,
                int nmpm, int random_mesh, int non_local_move, double alat, const double* RT_in, double* RT_out, double* V_diag,
                double* V_nondiag, cudaStream_t st) {
+  return wide_lrdmc_impl(h, mode, nw, w, r_up, r_dn, Ginv, keys, E_scf, nmpm, random_mesh, non_local_move, alat, RT_in, RT_out, V_diag,
+                         V_nondiag, nullptr, st);
+}
+// GFMC_t projection on the general path: the reference's while_loop literally -- every walker runs every iteration (walkers
+// that are out of time make no move) until none has time left (jqmc/jqmc_gfmc.py:1539-1570).  The loop condition is read
+// back once per iteration (4 bytes; the iteration itself is ~ms of launches on the systems this path serves).
+int wide_lrdmc_tau(qe_engine* h, int nw, double* w, double* r_up, double* r_dn, double* Ginv, uint32_t* keys, double tau,
+                   int random_mesh, int non_local_move, double alat, int32_t* pc, double* e_L, double* RT_out, cudaStream_t st) {
+  TauArgs ta{tau, pc, e_L};
+  return wide_lrdmc_impl(h, 3, nw, w, r_up, r_dn, Ginv, keys, 0.0, 1, random_mesh, non_local_move, alat, nullptr, RT_out, nullptr,
+                         nullptr, &ta, st);
+}
+static int wide_lrdmc_impl(qe_engine* h, int mode, int nw, double* w, double* r_up, double* r_dn, double* Ginv, uint32_t* keys,
+                           double E_scf, int nmpm, int random_mesh, int non_local_move, double alat, const double* RT_in,
+                           double* RT_out, double* V_diag, double* V_nondiag, const TauArgs* ta, cudaStream_t st) {
   const SysDev& S = h->sys;
   const WideTabs& T = h->wt;
   const int N = S.n_up, Nd = S.n_dn, Ne = S.n_e;
   const int n_kin = 6 * Ne, n_ecp = S.ecp_flag ? Ne * S.NN * S.Nv : 0, NPT = n_kin + n_ecp;
   size_t need = state_bytes(h, nw, 5, false) + newpoint_bytes(h, nw, 5) +
-                ((size_t)NPT + std::max(1, n_ecp) + (size_t)Ne * 8 + 9 + 8) * nw * 8 + 16384;
+                ((size_t)NPT + std::max(1, n_ecp) + (size_t)Ne * 8 + 9 + 8 + 6) * nw * 8 + 16384;
   if (mode == 0) need += lrdmc_draws_bytes(nw, nmpm);
   TRY(ensure_ws(h, need));
   WsCarve c{(char*)h->ws};
@@ -1707,9 +1787,20 @@ int wide_lrdmc(qe_engine* h, int mode, int nw, double* w, double* r_up, double* 
   double* RTs = c.take<double>((size_t)9 * nw);
   int* es = c.take<int>(nw);
   double* pnew = c.take<double>((size_t)3 * nw);
+  double *tau_left = nullptr, *xi = nullptr, *u_tau = nullptr;
+  int *active = nullptr, *any_active = nullptr;
+  if (mode == 3) {
+    tau_left = c.take<double>(nw);
+    xi = c.take<double>(nw);
+    u_tau = c.take<double>(nw);
+    active = c.take<int>(nw);
+    any_active = c.take<int>(4);
+    MISC(st, kw_fill<<<nblk(nw, 256), 256, 0, st>>>(nw, ta->tau, tau_left));
+    MISC(st, kw_fill_i<<<nblk(nw, 256), 256, 0, st>>>(nw, 0, ta->pc));
+  }
   TRY(build_state(h, st, X, r_up, r_dn));
   MISC(st, kw_to_soa<<<nblk((long long)N * N * nw, 256), 256, 0, st>>>(nw, N * N, Ginv, X.Gi));
-  if (mode != 0) {
+  if (mode != 0 && mode != 3) {
     if (RT_in) {
       MISC(st, kw_to_soa<<<nblk(9LL * nw, 256), 256, 0, st>>>(nw, 9, RT_in, RTs));
     } else {
@@ -1718,8 +1809,12 @@ int wide_lrdmc(qe_engine* h, int mode, int nw, double* w, double* r_up, double* 
   }
   const int n_it = mode == 0 ? nmpm : 1;
   const double* RTcur = RTs;
-  for (int it = 0; it < n_it; ++it) {
+  for (int it = 0; mode == 3 || it < n_it; ++it) {
     if (mode == 0) RTcur = rRT + (size_t)it * 9 * nw;  // rRT[(it*9+c)][w]
+    if (mode == 3) {
+      MISC(st, kw_tau_draws<<<nblk(nw, 128), 128, 0, st>>>(nw, random_mesh, keys, RTs, xi, u_tau));
+      CUDA_TRY(cudaMemsetAsync(any_active, 0, sizeof(int), st));
+    }
     TRY(build_weights(h, st, X));
     ElecArgs E{nw, T.no, T.nj, T.j3, alat, X.rs, X.Phi, X.Worb, X.Chi, X.gJ, el};
     {
@@ -1729,22 +1824,37 @@ int wide_lrdmc(qe_engine* h, int mode, int nw, double* w, double* r_up, double* 
     CHECK_LAUNCH();
     MeshArgs M{nw, n_kin, n_ecp, non_local_move, 0, alat, X.rs, RTcur, X.Wrow, X.gJrow, X.cJ, el, p, sj};
     TRY(launch_mesh(h, st, M));
-    SelectArgs Q{nw, n_kin, n_ecp, non_local_move, mode, it, alat, E_scf, X.rs, RTcur, p, sj, el, w, ru, V_diag, V_nondiag, es, pnew};
+    SelectArgs Q{nw, n_kin, n_ecp, non_local_move, mode, mode == 3 ? 0 : it, alat, E_scf, X.rs, RTcur, p, sj, el, w,
+                 mode == 3 ? u_tau : ru, V_diag, V_nondiag, es, pnew};
+    if (mode == 3) {
+      Q.tau_left = tau_left;
+      Q.xi = xi;
+      Q.pc = ta->pc;
+      Q.e_L = ta->e_L;
+      Q.active = active;
+      Q.any_active = any_active;
+    }
     {
       LaunchScope ls_(h, K_W_SELECT, st);
       kw_lrdmc_select<<<nblk(nw, 32), dim3(32, 8), 0, st>>>(S, Q);
     }
     CHECK_LAUNCH();
-    if (mode != 0) break;
+    if (mode == 3) {
+      int any = 0;
+      CUDA_TRY(cudaMemcpyAsync(&any, any_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      if (!any) break;
+    } else if (mode != 0) break;
     TRY(eval_newpoint(h, st, nw, 5, pnew, P));
     MoveArgs A{};
     A.nw = nw; A.no = T.no; A.nj = T.nj; A.has_j3 = T.j3; A.NQ = 5; A.decide = 0; A.it = it;
     A.rs = X.rs; A.Gs = nullptr; A.Gi = X.Gi; A.Phi = X.Phi; A.Mfull = X.Mfull; A.MupT = X.MupT; A.Chi = X.Chi; A.U = X.U; A.V = X.V;
     A.es = es; A.pnew = pnew; A.PhiN_up = P.PhiN_up; A.PhiN_dn = P.PhiN_dn; A.T1 = P.T1; A.T2 = P.T2;
     A.ChiN = P.ChiN; A.UN = P.UN; A.VN = P.VN; A.j1v = T.j1v;
+    A.active = mode == 3 ? active : nullptr;
     TRY(launch_move(h, st, A));
   }
-  if (mode == 0) {
+  if (mode == 0 || mode == 3) {
     MISC(st, kw_pos_to_aos<<<nblk((long long)Ne * 3 * nw, 256), 256, 0, st>>>(nw, N, Nd, X.rs, r_up, r_dn));
     MISC(st, kw_to_aos<<<nblk((long long)N * N * nw, 256), 256, 0, st>>>(nw, N * N, X.Gi, Ginv));
     MISC(st, kw_to_aos<<<nblk(9LL * nw, 256), 256, 0, st>>>(nw, 9, RTcur, RT_out));

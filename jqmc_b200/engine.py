@@ -406,6 +406,31 @@ class WalkerEngine:
         _lib.check(rc, "qe_lrdmc_project")
         return w, r_up, r_dn, Ginv, keys, RT, Vd, Vn
 
+    def projection_t(self, w_L, r_up, r_dn, A_old_inv, keys, tau, random_discretized_mesh, non_local_move, alat, inplace=False):
+        """``GFMC_t``'s ``_run_projection_loop`` (jqmc/jqmc_gfmc.py:1539-1570; body ``_projection_t_core`` :724-1110) with
+        ``projection_counter = 0`` and ``tau_left = tau`` on entry, as the driver sets them every branching step (:1700-1703).
+        Returns (e_L, projection_counter, w, r_up, r_dn, A_inv, keys, RT)."""
+        r_up, r_dn, nw = self._walkers(r_up, r_dn)
+        keys = self._keys(keys, nw)
+        Ginv = self._mat(A_old_inv, nw, "A_old_inv")
+        w = self._dev(w_L)
+        if w.shape != (nw,):
+            raise ValueError(f"w_L shape {tuple(w.shape)} != ({nw},)")
+        if non_local_move not in self._NLM:
+            raise NotImplementedError(f"non_local_move = {non_local_move} is not yet implemented.")
+        if not inplace:
+            w, r_up, r_dn, keys, Ginv = (t.clone() for t in (w, r_up, r_dn, keys, Ginv))
+        RT = torch.empty((nw, 3, 3), dtype=torch.float64, device=self.device)
+        e_L = torch.empty(nw, dtype=torch.float64, device=self.device)
+        pc = torch.zeros(nw, dtype=torch.int32, device=self.device)
+        rc = self._lib.qe_lrdmc_project_tau(
+            self._h, nw, self._ptr(w), self._ptr(r_up), self._ptr(r_dn), self._ptr(Ginv), self._ptr(keys), float(tau),
+            1 if random_discretized_mesh else 0, self._NLM[non_local_move], float(alat), self._ptr(pc), self._ptr(e_L),
+            self._ptr(RT), self._stream(),
+        )  # fmt: skip
+        _lib.check(rc, "qe_lrdmc_project_tau")
+        return e_L, pc, w, r_up, r_dn, Ginv, keys, RT
+
     def V_elements_n(self, r_up, r_dn, RTs, non_local_move, alat, A_inv=None):
         """``_jit_vmap_V_elements_n``: (V_diag, V_nondiag); the inverse is rebuilt unless ``A_inv`` is given."""
         r_up, r_dn, nw = self._walkers(r_up, r_dn)
@@ -434,6 +459,17 @@ class WalkerEngine:
             raise ValueError(f"V_diag / V_nondiag shapes {tuple(Vd.shape)} / {tuple(Vn.shape)} != ({nw},)")
         out = torch.empty(5, dtype=torch.float64, device=self.device)
         rc = self._lib.qe_lrdmc_collect(self._h, nw, self._ptr(w), self._ptr(Vd), self._ptr(Vn), float(E_scf), self._ptr(out), self._stream())
+        _lib.check(rc, "qe_lrdmc_collect")
+        return out
+
+    def lrdmc_collect_t(self, w, e_L):
+        """GFMC_t per-step sums (jqmc/jqmc_gfmc.py:1929-1932): device vector [nw, sum w, sum w, sum w e_L, sum w e_L^2]."""
+        w, e = self._dev(w), self._dev(e_L)
+        nw = w.shape[0]
+        if e.shape != (nw,):
+            raise ValueError(f"e_L shape {tuple(e.shape)} != ({nw},)")
+        out = torch.empty(5, dtype=torch.float64, device=self.device)
+        rc = self._lib.qe_lrdmc_collect(self._h, nw, self._ptr(w), None, self._ptr(e), 0.0, self._ptr(out), self._stream())
         _lib.check(rc, "qe_lrdmc_collect")
         return out
 

@@ -1,5 +1,6 @@
-"""``GFMC_n`` driver (LRDMC, fixed number of projections per branching) on the walker engine: the host-side
-mirror of ``jqmc.jqmc_gfmc.GFMC_n`` (jqmc/jqmc_gfmc.py:4191-6650).
+"""``GFMC_n`` (LRDMC, fixed number of projections per branching) and ``GFMC_t`` (LRDMC, fixed imaginary time per
+branching) drivers on the walker engine: the host-side mirrors of ``jqmc.jqmc_gfmc.GFMC_n`` (jqmc/jqmc_gfmc.py:4191-6650)
+and ``jqmc.jqmc_gfmc.GFMC_t`` (:173-2880).
 
 Same constructor arguments, step loop, stored observables, on-the-fly ``E_scf`` update and ``get_E``
 statistics as the reference; the per-step device work is done by ``WalkerEngine``:
@@ -22,7 +23,13 @@ Differences from the reference, all behind the same observable results:
   ``run`` (:4669, :5948-5952); every rank replays that stream locally instead of receiving a broadcast;
 * the per-step averages are all-reduced, so every rank stores them (the reference keeps them on rank 0 only).
 
-Out of scope: atomic forces (``comput_position_deriv``), ``GFMC_t``.
+``GFMC_t`` (jqmc_gfmc.py:646-2391) shares the reconfiguration and the statistics; its step is
+
+    w = 1, tau_left = tau;  projection loop -> qe_lrdmc_project_tau  (until every walker has used up tau)
+    weighted sums  sum w, sum w e_L, sum w e_L^2 (no division by V_diag - E_scf, :1929-1932) -> qe_lrdmc_collect
+    reconfiguration, A_inv refresh as above; the mean projection count of the rank is stored per step (:2095, 2271)
+
+Out of scope: atomic forces (``comput_position_deriv``).
 """
 
 from __future__ import annotations
@@ -60,144 +67,120 @@ def jackknife_E_scf(G_L, G_e_L, num_bin_blocks):
     return float(np.average(E_jk)), float(np.sqrt(num_bin_blocks - 1) * np.std(E_jk))
 
 
-class GFMC_n:
-    """LRDMC sampler (see module docstring).  Public surface follows jqmc.jqmc_gfmc.GFMC_n."""
+class _GFMC:
+    """What GFMC_n and GFMC_t share: walker initialisation, stored observables, the branching-step loop with its single
+    device->host read per print interval, the reconfiguration and ``get_E`` (jqmc/jqmc_gfmc.py:4222-4634, 6500-6700;
+    GFMC_t: :208-620, 2393-2587 -- the same code in the reference)."""
 
-    def __init__(
-        self,
-        hamiltonian_data=None,
-        num_walkers: int = 40,
-        num_mcmc_per_measurement: int = 16,
-        num_gfmc_collect_steps: int = 5,
-        mcmc_seed: int = 34467,
-        E_scf: float = 0.0,
-        alat: float = 0.1,
-        random_discretized_mesh: bool = True,
-        non_local_move: str = "tmove",
-        comput_position_deriv: bool = False,
-        epsilon_PW: float = 0.0,
-        use_swct: bool = False,
-        engine=None,
-    ) -> None:
+    def _setup(self, hamiltonian_data, num_walkers, num_gfmc_collect_steps, mcmc_seed, alat, random_discretized_mesh,
+               non_local_move, comput_position_deriv, engine):  # fmt: skip
         if comput_position_deriv:
             raise NotImplementedError("atomic forces are outside the walker engine (SURVEY.md §8f)")
-        self.__hamiltonian_data = hamiltonian_data
-        self.__num_walkers = int(num_walkers)
-        self.__nmpm = int(num_mcmc_per_measurement)
-        self.__num_gfmc_collect_steps = int(num_gfmc_collect_steps)
-        self.__mcmc_seed = int(mcmc_seed)
-        self.__E_scf = float(E_scf)
-        self.__alat = float(alat)
-        self.__random_discretized_mesh = bool(random_discretized_mesh)
-        self.__non_local_move = non_local_move
+        self._hamiltonian_data = hamiltonian_data
+        self._num_walkers = int(num_walkers)
+        self._num_gfmc_collect_steps = int(num_gfmc_collect_steps)
+        self._mcmc_seed = int(mcmc_seed)
+        self._alat = float(alat)
+        self._random_discretized_mesh = bool(random_discretized_mesh)
+        self._non_local_move = non_local_move
         rank, _ = _rank_size()
-        self.__mpi_seed = self.__mcmc_seed * (rank + 1)
+        self._mpi_seed = self._mcmc_seed * (rank + 1)
         self.engine = engine if engine is not None else WalkerEngine(hamiltonian_data)
         dev = self.engine.device
-        keys = rng_host.split(rng_host.PRNGKey(self.__mpi_seed), self.__num_walkers)
-        self.__keys = torch.from_numpy(keys).to(dev)
-        np.random.seed(self.__mpi_seed % (2**32))
+        keys = rng_host.split(rng_host.PRNGKey(self._mpi_seed), self._num_walkers)
+        self._keys = torch.from_numpy(keys).to(dev)
+        np.random.seed(self._mpi_seed % (2**32))
         gem = hamiltonian_data.wavefunction_data.geminal_data
         cp = hamiltonian_data.coulomb_potential_data
         r_up, r_dn, _, _ = generate_init_electron_configurations(
-            gem.num_electron_up, gem.num_electron_dn, self.__num_walkers, cp.effective_charges,
+            gem.num_electron_up, gem.num_electron_dn, self._num_walkers, cp.effective_charges,
             hamiltonian_data.structure_data.positions,
         )  # fmt: skip
-        self.__r_up = torch.from_numpy(np.ascontiguousarray(r_up)).to(dev)
-        self.__r_dn = torch.from_numpy(np.ascontiguousarray(r_dn)).to(dev)
-        self.__init_attributes()
+        self._r_up = torch.from_numpy(np.ascontiguousarray(r_up)).to(dev)
+        self._r_dn = torch.from_numpy(np.ascontiguousarray(r_dn)).to(dev)
+        self._init_attributes()
 
-    def __init_attributes(self):
-        self.__mcmc_counter = 0
-        self.__num_survived_walkers = 0
-        self.__num_killed_walkers = 0
-        self.__stored_w_L = np.zeros((0, 1))
-        self.__stored_e_L = np.zeros((0, 1))
-        self.__stored_e_L2 = np.zeros((0, 1))
-        self.__G_L = []
-        self.__G_e_L = []
-        self.__timer = dict(total=0.0)
+    def _init_attributes(self):
+        self._mcmc_counter = 0
+        self._num_survived_walkers = 0
+        self._num_killed_walkers = 0
+        self._stored_w_L = np.zeros((0, 1))
+        self._stored_e_L = np.zeros((0, 1))
+        self._stored_e_L2 = np.zeros((0, 1))
+        self._stored_average_projection_counter = np.zeros((0,))
+        self._G_L = []
+        self._G_e_L = []
+        self._timer = dict(total=0.0)
 
-    # ---- properties (jqmc_gfmc.py:4550-4634) ---------------------------------------------------------
+    # ---- properties (jqmc_gfmc.py:4550-4634, 533-620) ------------------------------------------------
     @property
     def hamiltonian_data(self):
-        return self.__hamiltonian_data
+        return self._hamiltonian_data
 
     @property
     def num_gfmc_collect_steps(self):
-        return self.__num_gfmc_collect_steps
+        return self._num_gfmc_collect_steps
 
     @num_gfmc_collect_steps.setter
     def num_gfmc_collect_steps(self, n):
-        self.__num_gfmc_collect_steps = int(n)
+        self._num_gfmc_collect_steps = int(n)
 
     @property
     def mcmc_counter(self) -> int:
-        return self.__mcmc_counter - self.__num_gfmc_collect_steps
+        return self._mcmc_counter - self._num_gfmc_collect_steps
 
     @property
     def num_walkers(self):
-        return self.__num_walkers
+        return self._num_walkers
 
     @property
     def alat(self):
-        return self.__alat
-
-    @property
-    def E_scf(self):
-        return self.__E_scf
+        return self._alat
 
     @property
     def w_L(self):
-        return compute_G_L(self.__stored_w_L, self.__num_gfmc_collect_steps)
+        return compute_G_L(self._stored_w_L, self._num_gfmc_collect_steps)
 
     @property
     def bare_w_L(self):
-        return np.asarray(self.__stored_w_L)
+        return np.asarray(self._stored_w_L)
 
     @property
     def e_L(self):
-        return np.asarray(self.__stored_e_L)[self.__num_gfmc_collect_steps :]
+        return np.asarray(self._stored_e_L)[self._num_gfmc_collect_steps :]
 
     @property
     def e_L2(self):
-        return np.asarray(self.__stored_e_L2)[self.__num_gfmc_collect_steps :]
+        return np.asarray(self._stored_e_L2)[self._num_gfmc_collect_steps :]
 
     @property
     def latest_r_up_carts(self):
-        return self.__r_up
+        return self._r_up
 
     @property
     def latest_r_dn_carts(self):
-        return self.__r_dn
+        return self._r_dn
 
     @property
     def jax_PRNG_key_list(self):
-        return self.__keys
+        return self._keys
 
     @property
     def num_survived_walkers(self):
-        return self.__num_survived_walkers
+        return self._num_survived_walkers
 
     @property
     def num_killed_walkers(self):
-        return self.__num_killed_walkers
+        return self._num_killed_walkers
 
     @property
     def timer(self):
-        return dict(self.__timer)
+        return dict(self._timer)
 
-    # ---- one branching step on the device (no host synchronisation) ----------------------------------
-    def _step(self, r_up, r_dn, keys, A_inv, zeta, rank, world):
+    # ---- walker reconfiguration on the device (jqmc_gfmc.py:6059-6321 == :2008-2277) -------------------
+    def _reconfigure(self, w, r_up, r_dn, sums, zeta, rank, world):
         eng = self.engine
-        nw = self.__num_walkers
-        w = torch.ones(nw, dtype=torch.float64, device=eng.device)
-        w, r_up, r_dn, A_inv, keys, RTs, _, _ = eng.projection_n(
-            w, r_up, r_dn, A_inv, keys, self.__E_scf, self.__nmpm, self.__random_discretized_mesh, self.__non_local_move,
-            self.__alat, inplace=True,
-        )  # fmt: skip
-        V_diag, V_nondiag = eng.V_elements_n(r_up, r_dn, RTs, self.__non_local_move, self.__alat)
-        sums = eng.lrdmc_collect(w, V_diag, V_nondiag, self.__E_scf)
+        nw = self._num_walkers
         d = _dist()
         if d is not None and world > 1:
             d.all_reduce(sums, op=d.ReduceOp.SUM)
@@ -213,23 +196,30 @@ class GFMC_n:
         chosen_all, n_surv = eng.lrdmc_branch(w_all, nw, zeta)
         r_up, r_dn = eng.gather_walkers(chosen_all[rank * nw : (rank + 1) * nw], up_all, dn_all)
         A_inv = eng.A_inv_n(r_up, r_dn)
-        return r_up, r_dn, keys, A_inv, sums, n_surv
+        return r_up, r_dn, A_inv, n_surv
+
+    def _step(self, r_up, r_dn, keys, A_inv, zeta, rank, world):  # -> r_up, r_dn, keys, A_inv, sums, n_surv, extra
+        raise NotImplementedError
+
+    def _after_interval(self, i, eq_steps, n_bins):
+        pass
 
     def run(self, num_mcmc_steps: int = 50, max_time: int = 86400) -> None:
         rank, world = _rank_size()
         eng = self.engine
         t_start = time.perf_counter()
-        zeta_rng = np.random.RandomState(self.__mcmc_seed % (2**32))  # rank 0's stream after np.random.seed(mpi_seed), :4669
-        A_inv = eng.A_inv_n(self.__r_up, self.__r_dn)
-        r_up, r_dn, keys = self.__r_up, self.__r_dn, self.__keys
-        base = self.__mcmc_counter
+        zeta_rng = np.random.RandomState(self._mcmc_seed % (2**32))  # rank 0's stream after np.random.seed(mpi_seed), :4669
+        A_inv = eng.A_inv_n(self._r_up, self._r_dn)
+        r_up, r_dn, keys = self._r_up, self._r_dn, self._keys
+        base = self._mcmc_counter
         n_store = base + num_mcmc_steps
-        self.__stored_e_L = np.concatenate([self.__stored_e_L, np.zeros((num_mcmc_steps, 1))])
-        self.__stored_e_L2 = np.concatenate([self.__stored_e_L2, np.zeros((num_mcmc_steps, 1))])
-        self.__stored_w_L = np.concatenate([self.__stored_w_L, np.zeros((num_mcmc_steps, 1))])
+        self._stored_e_L = np.concatenate([self._stored_e_L, np.zeros((num_mcmc_steps, 1))])
+        self._stored_e_L2 = np.concatenate([self._stored_e_L2, np.zeros((num_mcmc_steps, 1))])
+        self._stored_w_L = np.concatenate([self._stored_w_L, np.zeros((num_mcmc_steps, 1))])
+        self._stored_average_projection_counter = np.concatenate([self._stored_average_projection_counter, np.zeros(num_mcmc_steps)])
         mcmc_interval = int(np.maximum(num_mcmc_steps / 100, 1))
         eq_steps, n_collect, n_bins = GFMC_ON_THE_FLY_WARMUP_STEPS, GFMC_ON_THE_FLY_COLLECT_STEPS, GFMC_ON_THE_FLY_BIN_BLOCKS
-        pending = []  # (step index, device sums, device n_survived) not yet read back
+        pending = []  # (step index, device sums, device n_survived, device extra) not yet read back
         done = 0
 
         def flush():
@@ -238,46 +228,47 @@ class GFMC_n:
                 return
             S = torch.stack([p[1] for p in pending]).cpu().numpy()
             NS = torch.stack([p[2].reshape(()) for p in pending]).cpu().numpy()
-            for (i, _, _), s, ns in zip(pending, S, NS):
+            X = torch.stack([p[3].reshape(()) for p in pending]).cpu().numpy() if pending[0][3] is not None else None
+            for n, ((i, _, _, _), s, ns) in enumerate(zip(pending, S, NS)):
                 nw_sum, w_sum, wq, weq, we2q = s
-                self.__stored_w_L[base + i, 0] = w_sum / nw_sum
-                self.__stored_e_L[base + i, 0] = weq / wq
-                self.__stored_e_L2[base + i, 0] = we2q / wq
-                self.__num_survived_walkers += int(ns)
-                self.__num_killed_walkers += int(nw_sum) - int(ns)
+                self._stored_w_L[base + i, 0] = w_sum / nw_sum
+                self._stored_e_L[base + i, 0] = weq / wq
+                self._stored_e_L2[base + i, 0] = we2q / wq
+                if X is not None:
+                    self._stored_average_projection_counter[base + i] = X[n]
+                self._num_survived_walkers += int(ns)
+                self._num_killed_walkers += int(nw_sum) - int(ns)
                 if i >= n_collect:  # :6336-6343
-                    G = np.prod(self.__stored_w_L[base + i - n_collect : base + i], axis=0)
-                    self.__G_L.append(G)
-                    self.__G_e_L.append(G * self.__stored_e_L[base + i])
+                    G = np.prod(self._stored_w_L[base + i - n_collect : base + i], axis=0)
+                    self._G_L.append(G)
+                    self._G_e_L.append(G * self._stored_e_L[base + i])
             pending.clear()
 
         for i in range(num_mcmc_steps):
             zeta = float(zeta_rng.random_sample())
-            r_up, r_dn, keys, A_inv, sums, n_surv = self._step(r_up, r_dn, keys, A_inv, zeta, rank, world)
-            pending.append((i, sums, n_surv))
+            r_up, r_dn, keys, A_inv, sums, n_surv, extra = self._step(r_up, r_dn, keys, A_inv, zeta, rank, world)
+            pending.append((i, sums, n_surv, extra))
             if (i + 1) % mcmc_interval == 0 and i > eq_steps:  # :6345-6378
                 flush()
-                n_warm = int(np.minimum(eq_steps, i - eq_steps))
-                G_eq, G_e_eq = np.array(self.__G_L[n_warm:]), np.array(self.__G_e_L[n_warm:])
-                if len(G_eq) >= n_bins:
-                    self.__E_scf, _ = jackknife_E_scf(G_eq, G_e_eq, n_bins)
+                self._after_interval(i, eq_steps, n_bins)
             done += 1
             if time.perf_counter() - t_start > max_time:
                 flush()
                 break
         flush()
-        self.__mcmc_counter += done
-        ns = self.__mcmc_counter
-        self.__stored_e_L = self.__stored_e_L[:ns]
-        self.__stored_e_L2 = self.__stored_e_L2[:ns]
-        self.__stored_w_L = self.__stored_w_L[:ns]
+        self._mcmc_counter += done
+        ns = self._mcmc_counter
+        self._stored_e_L = self._stored_e_L[:ns]
+        self._stored_e_L2 = self._stored_e_L2[:ns]
+        self._stored_w_L = self._stored_w_L[:ns]
+        self._stored_average_projection_counter = self._stored_average_projection_counter[:ns]
         assert n_store >= ns
-        self.__r_up, self.__r_dn, self.__keys = r_up, r_dn, keys
-        self.__timer["total"] += time.perf_counter() - t_start
+        self._r_up, self._r_dn, self._keys = r_up, r_dn, keys
+        self._timer["total"] += time.perf_counter() - t_start
 
     def get_E(self, num_mcmc_warmup_steps: int = 50, num_mcmc_bin_blocks: int = 10):
         """(E_mean, E_std, Var_mean, Var_std): binned jackknife with the accumulated weights G_L
-        (jqmc/jqmc_gfmc.py:6500-6700).  Every rank holds the same (M, 1) history, so no collective is needed."""
+        (jqmc/jqmc_gfmc.py:6500-6700, 2393-2587).  Every rank holds the same (M, 1) history, so no collective is needed."""
         if self.mcmc_counter < num_mcmc_warmup_steps:
             raise ValueError("mcmc_counter should be larger than num_mcmc_warmup_steps")
         if self.mcmc_counter - num_mcmc_warmup_steps < num_mcmc_bin_blocks:
@@ -299,3 +290,96 @@ class GFMC_n:
         Var_mean = np.sum(Var_jk) / M
         Var_std = np.sqrt((M - 1) * np.sum((Var_jk - Var_mean) ** 2) / M)
         return float(E_mean), float(E_std), float(Var_mean), float(Var_std)
+
+
+class GFMC_n(_GFMC):
+    """LRDMC sampler with ``num_mcmc_per_measurement`` projections per branching (see module docstring).  Public surface
+    follows jqmc.jqmc_gfmc.GFMC_n."""
+
+    def __init__(
+        self,
+        hamiltonian_data=None,
+        num_walkers: int = 40,
+        num_mcmc_per_measurement: int = 16,
+        num_gfmc_collect_steps: int = 5,
+        mcmc_seed: int = 34467,
+        E_scf: float = 0.0,
+        alat: float = 0.1,
+        random_discretized_mesh: bool = True,
+        non_local_move: str = "tmove",
+        comput_position_deriv: bool = False,
+        epsilon_PW: float = 0.0,
+        use_swct: bool = False,
+        engine=None,
+    ) -> None:
+        self._nmpm = int(num_mcmc_per_measurement)
+        self._E_scf = float(E_scf)
+        self._setup(hamiltonian_data, num_walkers, num_gfmc_collect_steps, mcmc_seed, alat, random_discretized_mesh, non_local_move,
+                    comput_position_deriv, engine)  # fmt: skip
+
+    @property
+    def E_scf(self):
+        return self._E_scf
+
+    # ---- one branching step on the device (no host synchronisation) ----------------------------------
+    def _step(self, r_up, r_dn, keys, A_inv, zeta, rank, world):
+        eng = self.engine
+        nw = self._num_walkers
+        w = torch.ones(nw, dtype=torch.float64, device=eng.device)
+        w, r_up, r_dn, A_inv, keys, RTs, _, _ = eng.projection_n(
+            w, r_up, r_dn, A_inv, keys, self._E_scf, self._nmpm, self._random_discretized_mesh, self._non_local_move,
+            self._alat, inplace=True,
+        )  # fmt: skip
+        V_diag, V_nondiag = eng.V_elements_n(r_up, r_dn, RTs, self._non_local_move, self._alat)
+        sums = eng.lrdmc_collect(w, V_diag, V_nondiag, self._E_scf)
+        r_up, r_dn, A_inv, n_surv = self._reconfigure(w, r_up, r_dn, sums, zeta, rank, world)
+        return r_up, r_dn, keys, A_inv, sums, n_surv, None
+
+    def _after_interval(self, i, eq_steps, n_bins):  # on-the-fly E_scf, jqmc_gfmc.py:6345-6378
+        n_warm = int(np.minimum(eq_steps, i - eq_steps))
+        G_eq, G_e_eq = np.array(self._G_L[n_warm:]), np.array(self._G_e_L[n_warm:])
+        if len(G_eq) >= n_bins:
+            self._E_scf, _ = jackknife_E_scf(G_eq, G_e_eq, n_bins)
+
+
+class GFMC_t(_GFMC):
+    """LRDMC sampler that propagates every walker for the imaginary time ``tau`` per branching (continuous-time
+    projections).  Public surface follows jqmc.jqmc_gfmc.GFMC_t (jqmc/jqmc_gfmc.py:173-2880)."""
+
+    def __init__(
+        self,
+        hamiltonian_data=None,
+        num_walkers: int = 40,
+        num_gfmc_collect_steps: int = 5,
+        mcmc_seed: int = 34467,
+        tau: float = 0.1,
+        alat: float = 0.1,
+        random_discretized_mesh: bool = True,
+        non_local_move: str = "tmove",
+        comput_position_deriv: bool = False,
+        epsilon_PW: float = 0.0,
+        use_swct: bool = False,
+        engine=None,
+    ) -> None:
+        self._tau = float(tau)
+        self._setup(hamiltonian_data, num_walkers, num_gfmc_collect_steps, mcmc_seed, alat, random_discretized_mesh, non_local_move,
+                    comput_position_deriv, engine)  # fmt: skip
+
+    @property
+    def tau(self):
+        return self._tau
+
+    @property
+    def average_projection_counter(self):
+        return np.asarray(self._stored_average_projection_counter)
+
+    def _step(self, r_up, r_dn, keys, A_inv, zeta, rank, world):
+        eng = self.engine
+        nw = self._num_walkers
+        w = torch.ones(nw, dtype=torch.float64, device=eng.device)  # weights, time and counter restart every step (:1700-1703)
+        e_L, pc, w, r_up, r_dn, A_inv, keys, _ = eng.projection_t(
+            w, r_up, r_dn, A_inv, keys, self._tau, self._random_discretized_mesh, self._non_local_move, self._alat, inplace=True
+        )
+        sums = eng.lrdmc_collect_t(w, e_L)
+        r_up, r_dn, A_inv, n_surv = self._reconfigure(w, r_up, r_dn, sums, zeta, rank, world)
+        return r_up, r_dn, keys, A_inv, sums, n_surv, pc.to(torch.float64).mean()  # rank-local mean, as the reference (:2095)

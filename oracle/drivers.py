@@ -5,6 +5,7 @@
 * ``update_electron_positions``  jqmc/jqmc_mcmc.py:4278-4533 (Metropolis, nmpm single-electron proposals)
 * ``lrdmc_projection``           jqmc/jqmc_gfmc.py:4738-5358 (GFMC_n projection, legacy kinetic path)
 * ``lrdmc_V_elements``           jqmc/jqmc_gfmc.py:5360-5627
+* ``lrdmc_projection_t_step/_loop``  jqmc/jqmc_gfmc.py:724-1110, 1539-1570 (GFMC_t continuous-time projection, legacy path)
 
 Unlike the reference these evaluate the determinant/Jastrow ratios from scratch (brute force) so
 that they do not share the rank-1 algebra of the CUDA kernels; the running inverse is still carried
@@ -277,6 +278,99 @@ def lrdmc_projection(H, w, r_up, r_dn, Ginv, key, E_scf, nmpm, random_discretize
             trace.append(dict(k=k, u=u, b_x=b_x, diag=diag, nondiag=nondiag, spin_up=spin_up, idx=idx))
         r_up, r_dn = p_up, p_dn
     return w, r_up, r_dn, Ginv, key, RT, diag, nondiag
+
+
+# --------------------------------------------------------------------------------------
+# LRDMC (GFMC_t)                      jqmc/jqmc_gfmc.py:724-1110, 1539-1570
+# --------------------------------------------------------------------------------------
+def _move_with_sherman_morrison(gem, r_up, r_dn, Ginv, spin_up, idx, r_new):
+    """Single-electron move and rank-1 update of the inverse, row/column differences from scratch (:1027-1094)."""
+    p_up, p_dn = r_up.copy(), r_dn.copy()
+    (p_up if spin_up else p_dn)[idx] = r_new
+    G_old = P.compute_geminal_all_elements(gem, r_up, r_dn)
+    G_new = P.compute_geminal_all_elements(gem, p_up, p_dn)
+    n = len(r_up)
+    if spin_up:
+        v = (G_new[idx, :] - G_old[idx, :])[:, None]
+        u_ = np.zeros((n, 1))
+        u_[idx, 0] = 1.0
+    else:
+        u_ = (G_new[:, idx] - G_old[:, idx])[:, None]
+        v = np.zeros((n, 1))
+        v[idx, 0] = 1.0
+    Ainv_u = Ginv @ u_
+    vT_Ainv = v.T @ Ginv
+    det_ratio = 1.0 + (v.T @ Ainv_u)[0, 0]
+    return p_up, p_dn, Ginv - (Ainv_u @ vT_Ainv) / det_ratio
+
+
+def lrdmc_projection_t_step(H, pc, tau_left, w, r_up, r_dn, Ginv, key, random_discretized_mesh, non_local_move, alat, trace=None):
+    """One ``_projection_t_core`` call for one walker (jqmc/jqmc_gfmc.py:724-1110).
+    Returns (e_L, pc, tau_left, w, r_up, r_dn, Ginv, key, RT)."""
+    gem = H.wavefunction_data.geminal_data
+    if tau_left > 0.0:
+        pc = pc + 1
+    key, sub = R.split(key)
+    if random_discretized_mesh:
+        a, b, g = R.uniform(sub, 3, -2 * np.pi, 2 * np.pi)
+    else:
+        a = b = g = 0.0
+    RT = rotation_from_angles(a, b, g).T
+    diag, nondiag, p, moves = lrdmc_elements(H, r_up, r_dn, Ginv, RT, alat, non_local_move)
+    e_L = diag + nondiag
+    key, sub = R.split(key)
+    xi = R.uniform(sub)
+    tau_update = min(tau_left, np.log(1.0 - xi) / nondiag)
+    w = w * np.exp(-tau_update * e_L)
+    tau_left = tau_left - tau_update
+    key, sub = R.split(key)
+    u = R.uniform(sub)
+    tot = 0.0
+    for x in p:
+        tot += x
+    cdf = np.cumsum(p / tot)
+    k = min(int(np.searchsorted(cdf, u, side="left")), len(cdf) - 1)
+    moved = not (tau_left <= 0.0)
+    if trace is not None:
+        trace.append(dict(k=k, u=u, xi=xi, tau_update=tau_update, e_L=e_L, moved=moved))
+    if moved:
+        spin_up, idx, r_new = moves[k]
+        r_up, r_dn, Ginv = _move_with_sherman_morrison(gem, r_up, r_dn, Ginv, spin_up, idx, r_new)
+    return e_L, pc, tau_left, w, r_up, r_dn, Ginv, key, RT
+
+
+def lrdmc_projection_t_loop(H, w, r_up, r_dn, Ginv, keys, tau, random_discretized_mesh, non_local_move, alat, trace=None):
+    """``_run_projection_loop`` over a batch of walkers (jqmc/jqmc_gfmc.py:1539-1570): the vmapped body runs once, then
+    again for EVERY walker while any walker has time left -- finished walkers still split their keys and re-evaluate
+    e_L with a fresh mesh rotation.  Arrays carry a leading walker axis.
+    Returns (e_L, pc, w, r_up, r_dn, Ginv, keys, RT, n_iterations)."""
+    nw = len(w)
+    st = [
+        dict(pc=0, tl=float(tau), w=float(w[i]), ru=np.array(r_up[i], dtype=np.float64), rd=np.array(r_dn[i], dtype=np.float64),
+             gi=np.array(Ginv[i], dtype=np.float64), key=(int(keys[i][0]), int(keys[i][1])), e=0.0, RT=np.eye(3))
+        for i in range(nw)
+    ]  # fmt: skip
+    n_it = 0
+    while True:
+        for i, s in enumerate(st):
+            tr = None if trace is None else trace[i]
+            s["e"], s["pc"], s["tl"], s["w"], s["ru"], s["rd"], s["gi"], s["key"], s["RT"] = lrdmc_projection_t_step(
+                H, s["pc"], s["tl"], s["w"], s["ru"], s["rd"], s["gi"], s["key"], random_discretized_mesh, non_local_move, alat, tr
+            )
+        n_it += 1
+        if not max(s["tl"] for s in st) > 0.0:
+            break
+    return (
+        np.array([s["e"] for s in st]), np.array([s["pc"] for s in st], dtype=np.int32), np.array([s["w"] for s in st]),
+        np.array([s["ru"] for s in st]), np.array([s["rd"] for s in st]), np.array([s["gi"] for s in st]),
+        np.array([s["key"] for s in st], dtype=np.uint32), np.array([s["RT"] for s in st]), n_it,
+    )  # fmt: skip
+
+
+def lrdmc_collect_t(w, e_L):
+    """[nw, sum w, sum w e_L, sum w e_L^2] of one rank (GFMC_t, jqmc/jqmc_gfmc.py:1929-1932)."""
+    w, e = np.asarray(w, dtype=np.float64), np.asarray(e_L, dtype=np.float64)
+    return np.array([len(w), np.sum(w), np.sum(w * e), np.sum(w * e**2)])
 
 
 # --------------------------------------------------------------------------------------

@@ -76,6 +76,15 @@ class OracleEngine:
         cols = lambda j: self._t([r[j] for r in res])  # noqa: E731
         return cols(0), cols(1), cols(2), cols(3), k2, cols(5), cols(6), cols(7)
 
+    def projection_t(self, w, r_up, r_dn, A_inv, keys, tau, mesh, nlm, alat, inplace=False):
+        w, r_up, r_dn, A_inv, keys = (_np(x) for x in (w, r_up, r_dn, A_inv, keys))
+        e, pc, w2, ru, rd, gi, k2, RT, _ = OD.lrdmc_projection_t_loop(self.H, w, r_up, r_dn, A_inv, keys, tau, mesh, nlm, alat)
+        return self._t(e), torch.from_numpy(pc), self._t(w2), self._t(ru), self._t(rd), self._t(gi), torch.from_numpy(k2), self._t(RT)
+
+    def lrdmc_collect_t(self, w, e_L):
+        s = OD.lrdmc_collect_t(_np(w), _np(e_L))
+        return self._t([s[0], s[1], s[1], s[2], s[3]])
+
     def V_elements_n(self, r_up, r_dn, RTs, nlm, alat, A_inv=None):
         r_up, r_dn, RTs = _np(r_up), _np(r_dn), _np(RTs)
         res = [OD.lrdmc_V_elements(self.H, r_up[i], r_dn[i], RTs[i], nlm, alat) for i in range(len(r_up))]

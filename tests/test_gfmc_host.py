@@ -13,7 +13,7 @@ import torch
 
 from jqmc_b200 import rng_host
 from jqmc_b200.data import Jastrow_data, Jastrow_two_body_data
-from jqmc_b200.gfmc import GFMC_n, compute_G_L, jackknife_E_scf
+from jqmc_b200.gfmc import GFMC_n, GFMC_t, compute_G_L, jackknife_E_scf
 from jqmc_b200.mcmc import generate_init_electron_configurations
 from oracle import drivers as OD
 from tests.conftest import load_system
@@ -91,14 +91,14 @@ def test_gfmc_n_single_rank():
     assert g.mcmc_counter == STEPS - 1 and g.w_L.shape == (STEPS - 1, 1)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, kind="n"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
 
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         H = _system()
-        g = _driver_run(H)
+        g = _driver_run(H) if kind == "n" else _driver_run_t(H)
         q.put((rank, g.bare_w_L.copy(), g.e_L.copy(), g.e_L2.copy(), g.num_survived_walkers, g.latest_r_up_carts.numpy().copy(),
                g.latest_r_dn_carts.numpy().copy(), g.jax_PRNG_key_list.numpy().copy()))  # fmt: skip
     finally:
@@ -106,7 +106,8 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(600)
-def test_gfmc_n_two_ranks_gloo():
+@pytest.mark.parametrize("kind", ["n", "t"])
+def test_gfmc_two_ranks_gloo(kind):
     import torch.multiprocessing as mp
 
     s = socket.socket()
@@ -115,7 +116,7 @@ def test_gfmc_n_two_ranks_gloo():
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, kind)) for r in range(2)]
     for p in procs:
         p.start()
     out = {}
@@ -126,7 +127,7 @@ def test_gfmc_n_two_ranks_gloo():
         p.join(60)
         assert p.exitcode == 0
     H = _system()
-    hist, ranks = _reference_run(H, 2)
+    hist, ranks = _reference_run(H, 2) if kind == "n" else _reference_run_t(H, 2)
     for rank in range(2):
         w, e, e2, nsv, ru, rd, keys = out[rank]
         np.testing.assert_allclose(w[:, 0], [h[0] for h in hist], rtol=1e-12)
@@ -136,6 +137,99 @@ def test_gfmc_n_two_ranks_gloo():
         np.testing.assert_array_equal(ru, ranks[rank]["r_up"])
         np.testing.assert_array_equal(rd, ranks[rank]["r_dn"])
         assert [tuple(int(x) for x in k) for k in keys] == ranks[rank]["keys"]
+
+
+# ---- GFMC_t (jqmc/jqmc_gfmc.py:646-2391) ---------------------------------------------------------------------------------
+TAU = 0.02
+
+
+def _reference_run_t(H, world):
+    """GFMC_t branching steps for `world` ranks emulated sequentially with plain oracle calls: the projection loop of a
+    rank runs all of its walkers until the slowest one is out of time."""
+    gem, cp = H.wavefunction_data.geminal_data, H.coulomb_potential_data
+    ranks = []
+    for r in range(world):
+        seed = SEED * (r + 1)
+        keys = np.array(rng_host.split(rng_host.PRNGKey(seed), NW), dtype=np.uint32)
+        np.random.seed(seed)
+        r_up, r_dn, _, _ = generate_init_electron_configurations(
+            gem.num_electron_up, gem.num_electron_dn, NW, cp.effective_charges, H.structure_data.positions
+        )
+        ranks.append(dict(keys=keys, r_up=r_up, r_dn=r_dn, pc=[]))
+    zeta_rng = np.random.RandomState(SEED)
+    hist = []
+    for _ in range(STEPS):
+        W, S = [], np.zeros(4)
+        for st in ranks:
+            Ginv = np.array([OD.geminal_inv(gem, st["r_up"][i], st["r_dn"][i])[1] for i in range(NW)])
+            e, pc, w, ru, rd, _, k2, _, _ = OD.lrdmc_projection_t_loop(H, np.ones(NW), st["r_up"], st["r_dn"], Ginv, st["keys"], TAU, True, "tmove", ALAT)
+            st["r_up"], st["r_dn"], st["keys"] = ru, rd, k2
+            st["pc"].append(np.mean(pc))
+            W.append(w)
+            S += OD.lrdmc_collect_t(w, e)
+        chosen, ns = OD.lrdmc_branch_indices(W, zeta_rng.random_sample())
+        up_all = np.concatenate([st["r_up"] for st in ranks])
+        dn_all = np.concatenate([st["r_dn"] for st in ranks])
+        for r, st in enumerate(ranks):
+            st["r_up"] = up_all[chosen[r * NW : (r + 1) * NW]].copy()
+            st["r_dn"] = dn_all[chosen[r * NW : (r + 1) * NW]].copy()
+        hist.append((S[1] / S[0], S[2] / S[1], S[3] / S[1], ns))
+    for st in ranks:
+        st["keys"] = [tuple(int(x) for x in k) for k in st["keys"]]
+    return hist, ranks
+
+
+def _driver_run_t(H):
+    g = GFMC_t(H, num_walkers=NW, num_gfmc_collect_steps=1, mcmc_seed=SEED, tau=TAU, alat=ALAT, engine=OracleEngine(H))
+    g.run(STEPS)
+    return g
+
+
+def test_gfmc_t_single_rank():
+    H = _system()
+    hist, ranks = _reference_run_t(H, 1)
+    g = _driver_run_t(H)
+    _check(g, hist, ranks, 0)
+    np.testing.assert_allclose(g.average_projection_counter, ranks[0]["pc"])
+    assert g.mcmc_counter == STEPS - 1 and g.w_L.shape == (STEPS - 1, 1) and g.tau == TAU
+    assert np.all(g.average_projection_counter >= 1.0)
+
+
+def test_projection_t_oracle_properties():
+    """The continuous-time projection of the oracle: time bookkeeping, the no-move rule at tau_left <= 0 and the key
+    schedule of the vmapped while_loop (every walker splits three keys per iteration until the slowest is done)."""
+    H = _system()
+    gem = H.wavefunction_data.geminal_data
+    rng = np.random.default_rng(3)
+    nw = 3
+    r_up = rng.normal(scale=0.8, size=(nw, 1, 3))
+    r_dn = rng.normal(scale=0.8, size=(nw, 1, 3))
+    Ginv = np.array([OD.geminal_inv(gem, r_up[i], r_dn[i])[1] for i in range(nw)])
+    keys = np.array([[0, 5 + i] for i in range(nw)], dtype=np.uint32)
+    trace = [[] for _ in range(nw)]
+    e, pc, w, ru, rd, gi, k2, RT, n_it = OD.lrdmc_projection_t_loop(H, np.ones(nw), r_up, r_dn, Ginv, keys, 0.05, True, "tmove", ALAT, trace)
+    assert n_it == max(pc) and min(pc) >= 1
+    for i in range(nw):
+        tr = trace[i]
+        assert len(tr) == n_it
+        np.testing.assert_allclose(sum(t["tau_update"] for t in tr), 0.05, rtol=1e-12)
+        assert [t["moved"] for t in tr] == [True] * (pc[i] - 1) + [False] * (n_it - pc[i] + 1)
+        np.testing.assert_allclose(w[i], np.exp(-sum(t["tau_update"] * t["e_L"] for t in tr)), rtol=1e-12)
+        key = (int(keys[i, 0]), int(keys[i, 1]))
+        for _ in range(3 * n_it):
+            key, _sub = rng_host_split(key)
+        assert tuple(int(x) for x in k2[i]) == key
+        # the inverse carried by Sherman-Morrison is the inverse at the final configuration
+        np.testing.assert_allclose(gi[i], OD.geminal_inv(gem, ru[i], rd[i])[1], rtol=1e-8, atol=1e-10)
+    # fixed mesh: rotation is the identity
+    out = OD.lrdmc_projection_t_loop(H, np.ones(nw), r_up, r_dn, Ginv, keys, 0.01, False, "tmove", ALAT)
+    np.testing.assert_array_equal(out[7], np.broadcast_to(np.eye(3), (nw, 3, 3)))
+
+
+def rng_host_split(key):
+    from oracle import jaxrng as R
+
+    return R.split(key)
 
 
 def test_G_L_and_E_scf_jackknife():

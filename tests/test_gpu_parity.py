@@ -371,6 +371,74 @@ def test_lrdmc_projection_trajectory(name, jas, nlm, mesh):
         np.testing.assert_allclose(Gi[i], oGi, rtol=1e-7, atol=1e-9 * np.abs(oGi).max())
 
 
+def _check_projection_t(H, eng, nw, tau, mesh, nlm, alat, seed=41):
+    r_up, r_dn = random_walkers(H, nw, seed, scale=0.7)
+    keys = np.array([[0, 977 + 5 * i] for i in range(nw)], dtype=np.uint32)
+    Ginv = eng.A_inv_n(r_up, r_dn)
+    out = eng.projection_t(np.ones(nw), r_up, r_dn, Ginv, keys, tau, mesh, nlm, alat)
+    e_L, pc, w, ru, rd, Gi, k2, RT = (x.cpu().numpy() for x in out)
+    oe, opc, ow, oru, ord_, oGi, ok2, oRT, n_it = OD.lrdmc_projection_t_loop(H, np.ones(nw), r_up, r_dn, Ginv.cpu().numpy(), keys, tau, mesh, nlm, alat)
+    np.testing.assert_array_equal(pc, opc)  # the same number of projections for every walker
+    np.testing.assert_array_equal(k2, ok2)  # keys bit-exact, including the no-move iterations of the early finishers
+    np.testing.assert_allclose(ru, oru, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(rd, ord_, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(w, ow, rtol=1e-8)
+    np.testing.assert_allclose(e_L, oe, rtol=1e-8)
+    np.testing.assert_allclose(RT, oRT, rtol=0, atol=1e-14)
+    for i in range(nw):
+        np.testing.assert_allclose(Gi[i], oGi[i], rtol=1e-6, atol=1e-8 * np.abs(oGi[i]).max())
+    return opc, n_it
+
+
+@pytest.mark.parametrize("name,jas,nlm,mesh,tau,wpc", [("water_ccecp_ccpvqz", "j2pade", "tmove", True, 0.04, 2), ("water_ccecp_ccpvqz", "j1exp_j2exp", "dltmove", True, 0.03, 0),
+                                                       ("Li_ae_ccpvdz_cart", "j1exp_j2exp", "tmove", True, 0.03, 1), ("H2_ecp_ccpvtz_cart", "j2pade", "tmove", False, 0.1, 2),
+                                                       ("H_ecp_ccpvqz", "j1exp_j2exp", "tmove", True, 0.2, 3)])  # fmt: skip
+def test_lrdmc_projection_t_trajectory(name, jas, nlm, mesh, tau, wpc):
+    """(f).2 GFMC_t: the continuous-time projection loop (jqmc/jqmc_gfmc.py:724-1110, 1539-1570) against the oracle's literal
+    while_loop: per-walker projection counts, moves, weights, e_L and RT of the LAST iteration, and keys bit-exact.  Several
+    CTAs with different iteration counts (wpc walkers per CTA) exercise the tail pass."""
+    H = _with_jastrow(load_system(name), jas)
+    eng = _engine(H)
+    eng.set_walkers_per_cta(wpc)
+    pc, n_it = _check_projection_t(H, eng, 5, tau, mesh, nlm, 0.3)
+    assert n_it == pc.max() and pc.min() >= 1
+
+
+def test_gfmc_t_driver_matches_oracle_loop():
+    """(f).2: GFMC_t.run on the engine == the same branching steps done with plain oracle calls (same seeds)."""
+    from jqmc_b200.gfmc import GFMC_t
+    from tests import test_gfmc_host as TH
+
+    H = TH._system()
+    hist, ranks = TH._reference_run_t(H, 1)
+    g = GFMC_t(H, num_walkers=TH.NW, num_gfmc_collect_steps=1, mcmc_seed=TH.SEED, tau=TH.TAU, alat=TH.ALAT)
+    g.run(TH.STEPS)
+    np.testing.assert_allclose(g.bare_w_L[:, 0], [h[0] for h in hist], rtol=1e-9)
+    np.testing.assert_allclose(g.e_L[:, 0], [h[1] for h in hist][1:], rtol=1e-9)
+    np.testing.assert_allclose(g.average_projection_counter, ranks[0]["pc"])
+    assert g.num_survived_walkers == sum(h[3] for h in hist)
+    np.testing.assert_allclose(g.latest_r_up_carts.cpu().numpy(), ranks[0]["r_up"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(g.latest_r_dn_carts.cpu().numpy(), ranks[0]["r_dn"], rtol=0, atol=1e-11)
+    assert [tuple(int(x) for x in k) for k in g.jax_PRNG_key_list.cpu().numpy()] == ranks[0]["keys"]
+
+
+def test_gfmc_t_driver_water_runs(water):
+    """GFMC_t on the BASELINE system: 30 branching steps of tau = 0.05 with 256 walkers; energies in the physical range, the
+    projection count matches tau x |V_nondiag|, total weight and time bookkeeping are consistent."""
+    from jqmc_b200.gfmc import GFMC_t
+
+    H = _with_jastrow(water, "j2pade")
+    g = GFMC_t(H, num_walkers=256, num_gfmc_collect_steps=2, mcmc_seed=11, tau=0.05, alat=0.3)
+    g.run(30)
+    assert g.mcmc_counter == 28 and g.e_L.shape == (28, 1)
+    assert np.all(np.isfinite(g.e_L)) and -19.0 < g.e_L[5:].mean() < -15.5
+    apc = g.average_projection_counter
+    assert apc.shape == (30,) and np.all(apc > 2.0) and np.all(apc < 40.0)
+    E, s, V, sv = g.get_E(num_mcmc_warmup_steps=8, num_mcmc_bin_blocks=5)
+    assert -19.0 < E < -15.5 and s > 0
+    assert 0.5 < g.num_survived_walkers / (g.num_survived_walkers + g.num_killed_walkers) <= 1.0
+
+
 @pytest.mark.parametrize("world,nw", [(1, 4096), (2, 1000), (8, 4096), (3, 7)])
 def test_lrdmc_branch_indices_bit_exact(water, world, nw):
     """a30 reconfiguration: comb indices over the all-gathered weights are bit-identical to the reference's

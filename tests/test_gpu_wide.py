@@ -404,6 +404,31 @@ def test_wide_lrdmc_projection_trajectory(case, nlm, E_scf, nmpm):
         np.testing.assert_allclose(Gi[i], oGi, rtol=1e-6, atol=1e-8 * np.abs(oGi).max())
 
 
+@pytest.mark.parametrize("case,nlm,tau", [("water_jsd", "tmove", 0.04), ("li_ae", "tmove", 0.03), ("water_jagp", "dltmove", 0.03), ("water_jagp_j3mo", "tmove", 0.03)])
+def test_wide_lrdmc_projection_t_trajectory(case, nlm, tau):
+    """(f).2 GFMC_t on the general path: the literal while_loop (every walker runs every iteration, walkers out of time do
+    not move) against the oracle: projection counts and keys bit-exact, moves, weights, e_L and RT of the last iteration."""
+    H, eng = _engine(case)
+
+    nw, alat = 4, 0.3
+    r_up, r_dn = _walkers(H, nw, 43, scale=0.7)
+    keys = np.array([[0, 977 + 5 * i] for i in range(nw)], dtype=np.uint32)
+    Ginv = eng.A_inv_n(r_up, r_dn)
+    out = eng.projection_t(np.ones(nw), r_up, r_dn, Ginv, keys, tau, True, nlm, alat)
+    e_L, pc, w, ru, rd, Gi, k2, RT = (x.cpu().numpy() for x in out)
+    oe, opc, ow, oru, ord_, oGi, ok2, oRT, n_it = OD.lrdmc_projection_t_loop(H, np.ones(nw), r_up, r_dn, Ginv.cpu().numpy(), keys, tau, True, nlm, alat)
+    np.testing.assert_array_equal(pc, opc)
+    np.testing.assert_array_equal(k2, ok2)
+    np.testing.assert_allclose(ru, oru, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(rd, ord_, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(w, ow, rtol=1e-8)
+    np.testing.assert_allclose(e_L, oe, rtol=1e-8)
+    np.testing.assert_allclose(RT, oRT, rtol=0, atol=1e-14)
+    for i in range(nw):
+        np.testing.assert_allclose(Gi[i], oGi[i], rtol=1e-6, atol=1e-8 * np.abs(oGi[i]).max())
+    assert n_it == opc.max()
+
+
 @pytest.mark.parametrize("name", ["w_2b_3b_w_ecp", "w_2b_1b3b_w_ecp", "w_1b_2b_1b3b_ae"])
 def test_wide_turborvb_three_body_jastrow_known_answers(name):
     """The GPU path reproduces the TurboRVB known answers of the reference's J3 tests directly
