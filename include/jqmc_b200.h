@@ -196,10 +196,16 @@ int qe_dln_wf(qe_engine* h, int nw, const double* r_up, const double* r_dn, cons
 int qe_set_path(qe_engine* h, int path);
 /* Debugging aid: nonzero replaces the tensor-core GEMM of the general path by a plain DFMA kernel (process-wide). */
 int qe_set_gemm_reference(int on);
+/* General family: walkers per slice of a call (0 = automatic from the free device memory).  Calls over more walkers run as
+ * consecutive slices through one workspace; results do not depend on the slicing.  Process-wide, like the switch above. */
+int qe_set_wide_slice(int walkers);
 
 /* Walkers per CTA of the fused walker kernel: 0 = chosen automatically so that the grid fills the SMs (default),
  * 1..32 = fixed (tuning / tests; results do not depend on it beyond round-off of partial-sum order). */
 int qe_set_walkers_per_cta(qe_engine* h, int wpc);
+/* Tuning knob: warps per CTA of the fused walker kernel: 0 / 16 = one 16-warp CTA per SM (default), 8 = two CTAs per SM,
+ * 4 = four.  Same results. */
+int qe_set_walker_warps(qe_engine* h, int warps);
 
 /* Microbenchmark used by bench.py for the fp64 roofline denominator: runs `iters` dependent-free
  * DFMA per thread on a full grid and returns the achieved TFLOP/s (synchronous). */

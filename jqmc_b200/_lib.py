@@ -105,6 +105,8 @@ EXPORTS = {
     "qe_launch_count": (C.c_int64, [C.c_void_p]),
     "qe_set_fused": (C.c_int, [C.c_void_p, C.c_int]),
     "qe_set_walkers_per_cta": (C.c_int, [C.c_void_p, C.c_int]),
+    "qe_set_walker_warps": (C.c_int, [C.c_void_p, C.c_int]),
+    "qe_set_wide_slice": (C.c_int, [C.c_int]),
     "qe_dln_wf": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p]),
     "qe_set_path": (C.c_int, [C.c_void_p, C.c_int]),
     "qe_set_gemm_reference": (C.c_int, [C.c_int]),

@@ -119,6 +119,7 @@ struct qe_engine {
   bool profiling = false;
   bool fused = true;  // qe_local_energy uses the fused walker kernel when the system fits
   int wpc_override = 0;  // walkers per CTA of the fused walker kernel (0 = automatic)
+  int walker_warps = 0;  // warps per CTA of the fused walker kernel (0 = 16: one CTA per SM; 8: two CTAs per SM; 4: four)
   struct ProfRec { int id; cudaEvent_t e0, e1; };
   std::vector<ProfRec> prof;
 };

@@ -162,18 +162,33 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
     R_AS_cur = SF > 0.0 ? pow(SF, -0.375) : 0.0;
   }
 
+  // draws of the next proposal are fetched one iteration ahead (their L2 latency hides behind phases B and C)
+  int ke_n = 0, axis_n = 0;
+  double rg_n = 0.0, rb_n = 0.0;
+  if (P.nmpm > 0) {
+    ke_n = P.rsel[ww];
+    axis_n = P.raxis[ww];
+    rg_n = P.rg[ww];
+    rb_n = P.rb[ww];
+  }
   for (int it = 0; it < P.nmpm; ++it) {
     // ---- phase A: proposal (every thread, redundantly; lane = walker) ----------------------------
-    const size_t ridx = (size_t)it * P.nw + ww;
-    const int ke = P.rsel[ridx];
-    const int axis = P.raxis[ridx];
+    const int ke = ke_n, axis = axis_n;
+    const double rg_c = rg_n, rb_c = rb_n;
+    if (it + 1 < P.nmpm) {
+      const size_t rnext = (size_t)(it + 1) * P.nw + ww;
+      ke_n = P.rsel[rnext];
+      axis_n = P.raxis[rnext];
+      rg_n = P.rg[rnext];
+      rb_n = P.rb[rnext];
+    }
     const bool up = ke < N;
     const double ox = SR(ke, 0), oy = SR(ke, 1), oz = SR(ke, 2);
     double dist;
     int ia = nearest_atom(S.Rn, S.n_atom, ox, oy, oz, 0, &dist);
     double Zc = S.Zeff[ia];
     const double f_l = 1.0 / (Zc * Zc) * (1.0 + Zc * Zc * dist) / (1.0 + dist);
-    const double g = P.rg[ridx] * (f_l * P.Dt);
+    const double g = rg_c * (f_l * P.Dt);
     double nx = ox, ny = oy, nz = oz;
     if (axis == 0) nx = ox + g;
     else if (axis == 1) ny = oy + g;
@@ -323,7 +338,7 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
       }
       const double wr = R_AS_ratio * J_ratio * Det;
       const double x = wr * wr * T_ratio;
-      const double b = P.rb[ridx];
+      const double b = rb_c;
       const bool ok = (x == x) && (b < fmin(1.0, x)) && (Det != 0.0);
       if (ok) {
         ++n_acc;

@@ -1,895 +1,6 @@
-// Fused per-walker kernel: LRDMC projection (GFMC_n._projection_n, jqmc/jqmc_gfmc.py:4738-5358), its
-// observable V_diag / V_nondiag (_compute_V_elements_n, :5360-5627) and the VMC local energy
-// (compute_local_energy_fast, jqmc/hamiltonians.py:225-290) share one kernel.
-//
-//   CTA = WPC walkers x NWARP warps.  The basis image and the Jastrow / ECP tables are staged in shared memory once per
-//   CTA; walker state (positions, running inverse, cached MO value/grad/lap of every electron, ratio weight vectors,
-//   mesh elements) lives in shared memory as [item][walker].
-//
-//   A thread is a (walker, task) pair.  The dominant tasks -- one AO sweep per mesh point -- are the SAME code for every
-//   point, so the 32 lanes of a warp hold 32/WPC consecutive mesh points of WPC walkers: control flow stays uniform, table
-//   reads are warp-broadcast LDS, and WPC is free to make the grid fill the 148 SMs (4096 walkers / 8 = 512 CTAs, 4 per SM).
-//   Several CTAs per SM also hide each other's short serial sections (selection, Sherman-Morrison).
-//
-//   per projection:  P1  ratio weight vectors W[:,e] = lambda Phi_dn Ginv[:,e] from the running inverse   (walker, electron)
-//                    P2  6 N_e kinetic-mesh ratios + N_e*NN*Nv ECP-mesh ratios (warp rounds handed out
-//                        by a shared counter), per-electron continuum kinetic energy and potentials          (walker, point)
-//                    P3  fixed-node split, diagonal / off-diagonal sums, weight, sequential-cumsum move selection
-//                    P4  value/grad/lap of the moved electron (warp = basis chunk), Sherman-Morrison update
-#include "qe_common.cuh"
-
-namespace {
-
-struct WalkerArgs {
-  int nw, nmpm, mode;  // mode 0: projection, 1: V elements (no move), 2: VMC local energy
-  int dlt, wpc;
-  double alat, E_scf;
-  double* w;
-  double* r_up;
-  double* r_dn;
-  double* Ginv;
-  const double* RT_in;  // modes 1, 2: [nw][9]
-  double* RT_out;       // mode 0
-  double* V_diag;
-  double* V_nondiag;
-  double* e_L;
-  double* T_elem;
-  double* V_parts;
-  const double* rRT;  // mode 0 draws: [(it*9+c)][nw]
-  const double* ru;   //               [it][nw]
-  int off_cseg, off_cbeg, n_chunk;
-  // continuous-time projection (GFMC_t, template TAU): the draws are made in the kernel because the number of
-  // projections is not known in advance
-  double tau;
-  int tail, random_mesh;
-  uint32_t* keys;  // [nw][2], advanced in place
-  int* pc;         // [nw] projection counter (out)
-  int* n_cta;      // [grid] projections this CTA executed (out in the main pass, in in the tail pass)
-  int* n_max;      // [1] max over the grid (atomicMax in the main pass)
-};
-
-// R^T (row-major) of R = Rz(gamma) Ry(beta) Rx(alpha), jqmc/jqmc_mcmc.py:4237-4244
-__device__ __forceinline__ void rt_from_angles(double al, double be, double ga, double* RT) {
-  double sa, ca, sb, cb, sg, cg;
-  sincos(al, &sa, &ca);
-  sincos(be, &sb, &cb);
-  sincos(ga, &sg, &cg);
-  const double R[9] = {cb * cg, cg * sa * sb - ca * sg, sa * sg + ca * cg * sb, cb * sg, ca * cg + sa * sb * sg,
-                       ca * sb * sg - cg * sa, -sb, cb * sa, ca * cb};
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) RT[i * 3 + j] = R[j * 3 + i];
-}
-
-// shared-memory carve-up by byte offsets from the (16-byte aligned) dynamic shared memory base
-struct Carve {
-  char* base;
-  size_t off;
-  __device__ Carve(char* b, size_t o) : base(b), off(o) {}
-  template <class T>
-  __device__ T* take(size_t n) {
-    off = (off + 15) & ~size_t(15);
-    T* r = (T*)(base + off);
-    off += n * sizeof(T);
-    return r;
-  }
-};
-
-template <class T>
-__device__ __forceinline__ const T* stage(Carve& c, const T* src, size_t n, int tid, int nthr) {
-  T* dst = c.take<T>(n);
-  for (size_t i = tid; i < n; i += nthr) dst[i] = src[i];
-  return dst;
-}
-
-__device__ __forceinline__ SysDev stage_sys(const SysDev& g, int nmo, Carve& c, int tid, int nthr) {
-  SysDev s = g;
-  s.Rn = stage(c, g.Rn, 3 * g.n_atom, tid, nthr);
-  s.Zeff = stage(c, g.Zeff, g.n_atom, tid, nthr);
-  s.lam_p = stage(c, g.lam_p, (size_t)nmo * nmo, tid, nthr);
-  s.lam_u = stage(c, g.lam_u, (size_t)nmo * (g.n_unp > 0 ? g.n_unp : 1), tid, nthr);
-  s.j1_A = stage(c, g.j1_A, g.n_atom, tid, nthr);
-  s.j1_c = stage(c, g.j1_c, g.n_atom, tid, nthr);
-  if (g.ecp_flag) {
-    s.ecp_l = stage(c, g.ecp_l, g.n_ecp, tid, nthr);
-    s.ecp_z = stage(c, g.ecp_z, g.n_ecp, tid, nthr);
-    s.ecp_c = stage(c, g.ecp_c, g.n_ecp, tid, nthr);
-    s.ecp_p = stage(c, g.ecp_p, g.n_ecp, tid, nthr);
-    s.ecp_lmax_atom = stage(c, g.ecp_lmax_atom, g.n_atom, tid, nthr);
-    s.ecp_off = stage(c, g.ecp_off, g.n_atom + 1, tid, nthr);
-    s.quad_w = stage(c, g.quad_w, g.Nv, tid, nthr);
-    s.quad_g = stage(c, g.quad_g, 3 * g.Nv, tid, nthr);
-  }
-  return s;
-}
-
-size_t sys_bytes(const SysDev& s, int nmo) {
-  size_t n = (size_t)(3 * s.n_atom + 3 * s.n_atom + nmo * nmo + nmo * (s.n_unp > 0 ? s.n_unp : 1)) * 8 + 6 * 16;
-  if (s.ecp_flag) n += (size_t)s.n_ecp * (4 + 24) + (size_t)s.n_atom * 8 + 4 + (size_t)s.Nv * 32 + 8 * 16;
-  return n;
-}
-
-// electron positions held in shared memory as [(e*3+c)][walker]
-struct PosShared {
-  const double* s_r;
-  int wpc, wl;
-  __device__ __forceinline__ void get(int e, double& x, double& y, double& z) const {
-    x = s_r[(e * 3 + 0) * wpc + wl];
-    y = s_r[(e * 3 + 1) * wpc + wl];
-    z = s_r[(e * 3 + 2) * wpc + wl];
-  }
-};
-
-template <int NMO, bool CART, int LMAX, bool TAU>
-__global__ void __launch_bounds__(512, 1)
-k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
-  extern __shared__ __align__(16) char smem_raw[];
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  // GFMC_t tail pass: this CTA replays the no-op iterations the reference's while_loop makes every walker run until the
-  // slowest walker of the rank has used up its time (jqmc/jqmc_gfmc.py:1539-1570)
-  int n_extra = 0;
-  if constexpr (TAU) {
-    if (P.tail) {
-      n_extra = *P.n_max - P.n_cta[blockIdx.x];
-      if (n_extra <= 0) return;
-    }
-  }
-  const int lane = tid & 31, wid = tid >> 5, NWARP = nthr >> 5;
-  const int WPC = P.wpc;
-  const int w0 = blockIdx.x * WPC;
-
-  // ---- stage tables ------------------------------------------------------------------------------
-  {
-    const int4* src = (const int4*)B.g;
-    int4* dst = (int4*)smem_raw;
-    for (int i = tid; i < B.bytes / 16; i += nthr) dst[i] = src[i];
-  }
-  const char* tab = smem_raw;
-  Carve cv(smem_raw, (size_t)B.bytes);
-  const SysDev S = stage_sys(S_g, NMO, cv, tid, nthr);
-  const int N = S.n_up, Nd = S.n_dn, Ne = S.n_e, NN2 = N * N;
-  const int n_kin = P.mode == 2 ? 0 : 6 * Ne;
-  const int n_ecp = S.ecp_flag ? Ne * S.NN * S.Nv : 0;
-  const int NPT = n_kin + n_ecp;
-
-  double* s_r = cv.take<double>((size_t)Ne * 3 * WPC);
-  double* s_Gi = cv.take<double>((size_t)NN2 * WPC);
-  double* s_phi = cv.take<double>((size_t)Ne * 5 * NMO * WPC);  // [(e*5+q)*NMO+mo]
-  double* s_W = cv.take<double>((size_t)Ne * NMO * WPC);
-  double* s_p = cv.take<double>((size_t)(NPT > 0 ? NPT : 1) * WPC);
-  double* s_j = cv.take<double>((size_t)(n_ecp > 0 ? n_ecp : 1) * WPC);
-  double* s_el = cv.take<double>((size_t)Ne * 8 * WPC);  // [e*8 + {ke|opt, ei, eid, loc, ee, kinFN, kinSP, -}]
-  double* s_part = cv.take<double>((size_t)NWARP * 5 * NMO * WPC);
-  double* s_stage = cv.take<double>((size_t)5 * NMO * WPC);
-  double* s_misc = cv.take<double>((size_t)16 * WPC);  // 0..8 RT, 9..11 new position, 12 selected electron, 13 total
-  int* s_ctr = cv.take<int>(4);
-#define SR(e, c) s_r[((e) * 3 + (c)) * WPC + wl]
-#define SGI(i, j) s_Gi[((i) * N + (j)) * WPC + wl]
-#define SPHI(e, q, mo) s_phi[(((e) * 5 + (q)) * NMO + (mo)) * WPC + wl]
-#define SW(e, mo) s_W[((e) * NMO + (mo)) * WPC + wl]
-#define SEL(e, i) s_el[((e) * 8 + (i)) * WPC + wl]
-#define SMISC(i) s_misc[(i) * WPC + wl]
-#define GW(wl_) (min(w0 + (wl_), P.nw - 1)) /* dead walkers of the last CTA shadow the last walker (no stores) */
-
-  for (int idx = tid; idx < Ne * 3 * WPC; idx += nthr) {
-    const int wl = idx % WPC, it = idx / WPC, e = it / 3, c = it % 3;
-    const int ww = GW(wl);
-    s_r[idx] = e < N ? P.r_up[((size_t)ww * N + e) * 3 + c] : P.r_dn[((size_t)ww * Nd + (e - N)) * 3 + c];
-  }
-  for (int idx = tid; idx < NN2 * WPC; idx += nthr) {
-    const int wl = idx % WPC, it = idx / WPC;
-    s_Gi[idx] = P.Ginv[(size_t)GW(wl) * NN2 + it];
-  }
-  if (P.mode != 0)
-    for (int idx = tid; idx < 9 * WPC; idx += nthr) {
-      const int wl = idx % WPC, c = idx / WPC;
-      s_misc[idx] = P.RT_in ? P.RT_in[(size_t)GW(wl) * 9 + c] : (c % 4 == 0 ? 1.0 : 0.0);
-    }
-  if (tid == 0) s_ctr[0] = 0;
-  __syncthreads();
-
-  // ---- value/grad/lap of the MOs at every electron (cache): task = (walker, electron) ------------------------
-  for (int s = tid; s < Ne * WPC; s += nthr) {
-    const int wl = s % WPC, e = s / WPC;
-    SinkMO5<NMO> sink;
-    sink.init(tab + (e < N ? B.off_C : B.off_C2));
-    eval_vgl<CART, LMAX>(tab, B, B.off_seg, SR(e, 0), SR(e, 1), SR(e, 2), 0, B.n_grp, sink);
-#pragma unroll
-    for (int q = 0; q < 5; ++q)
-#pragma unroll
-      for (int mo = 0; mo < NMO; ++mo) SPHI(e, q, mo) = sink.acc[q][mo];
-  }
-  __syncthreads();
-
-  const double a2 = P.alat * P.alat;
-  const int n_it = P.mode == 0 ? P.nmpm : 1;
-  double w_L = 1.0, diag = 0.0, nondiag = 0.0;  // meaningful in threads tid < WPC (wl = tid)
-  if (P.mode == 0 && tid < WPC && !(TAU && P.tail)) w_L = P.w[GW(tid)];
-  // GFMC_t per-walker registers (threads tid < WPC)
-  Key key{0u, 0u};
-  double tau_left = 0.0, xi = 0.0, u_move = 0.0;
-  int pc = 0, n_done = 0;
-  if constexpr (TAU) {
-    if (tid < WPC) {
-      const int ww = GW(tid);
-      key = Key{P.keys[2 * ww], P.keys[2 * ww + 1]};
-      if (!P.tail) tau_left = P.tau;
-      else
-        for (int i = 0; i < 3 * (n_extra - 1); ++i) {
-          Key sub;
-          rng_split(key, sub);
-        }
-    }
-  }
-  // mesh-point slot blocks (same spin => same MO coefficient table): kinetic up, kinetic dn, ECP up, ECP dn
-  const int n_eu = S.ecp_flag ? N * S.NN * S.Nv : 0, n_ed = S.ecp_flag ? Nd * S.NN * S.Nv : 0;
-  const int n_ku = P.mode == 2 ? 0 : 6 * N, n_kd = P.mode == 2 ? 0 : 6 * Nd;
-  const int blk_size[4] = {n_ku * WPC, n_kd * WPC, n_eu * WPC, n_ed * WPC};
-  const int blk_start[4] = {0, n_ku * WPC, n_kin * WPC, (n_kin + n_eu) * WPC};
-  const int blk_pairs[4] = {(blk_size[0] + 1) / 2, (blk_size[1] + 1) / 2, (blk_size[2] + 1) / 2, (blk_size[3] + 1) / 2};
-  const int n_rounds_pt = (blk_pairs[0] + blk_pairs[1] + blk_pairs[2] + blk_pairs[3] + 31) / 32;
-  const int n_rounds_el = (Ne * WPC + 31) / 32;
-
-  for (int it = 0; TAU || it < n_it; ++it) {
-    // ---- P1: ratio weight vectors, task = (walker, electron) -----------------------------------------------------
-    if constexpr (TAU) {
-      // three splits per projection: rotation angles, time draw, move draw (jqmc/jqmc_gfmc.py:770-776, 1004-1018)
-      if (tid < WPC) {
-        const int wl = tid;
-        Key sub;
-        rng_split(key, sub);
-        double al = 0, be = 0, ga = 0;
-        if (P.random_mesh) {
-          const double two_pi = 6.283185307179586;
-          al = rng_uniform_bits(rng_bits64(sub, 0u), -two_pi, two_pi);
-          be = rng_uniform_bits(rng_bits64(sub, 1u), -two_pi, two_pi);
-          ga = rng_uniform_bits(rng_bits64(sub, 2u), -two_pi, two_pi);
-        }
-        double RTl[9];
-        rt_from_angles(al, be, ga, RTl);
-#pragma unroll
-        for (int c = 0; c < 9; ++c) SMISC(c) = RTl[c];
-        rng_split(key, sub);
-        xi = rng_uniform_bits(rng_bits64(sub), 0.0, 1.0);
-        rng_split(key, sub);
-        u_move = rng_uniform_bits(rng_bits64(sub), 0.0, 1.0);
-      }
-    } else if (P.mode == 0)
-      for (int idx = tid; idx < 9 * WPC; idx += nthr) {
-        const int wl = idx % WPC, c = idx / WPC;
-        s_misc[idx] = P.rRT[((size_t)it * 9 + c) * P.nw + GW(wl)];
-      }
-    for (int s = tid; s < Ne * WPC; s += nthr) {
-      const int wl = s % WPC, e = s / WPC;
-      double Wv[NMO];
-      if (e < N) {
-        double y[NMO];
-#pragma unroll
-        for (int b = 0; b < NMO; ++b) {
-          double sum = 0;
-          for (int j = 0; j < Nd; ++j) sum = fma(SPHI(N + j, 0, b), SGI(j, e), sum);
-          y[b] = sum;
-        }
-#pragma unroll
-        for (int a = 0; a < NMO; ++a) {
-          double sum = 0;
-#pragma unroll
-          for (int b = 0; b < NMO; ++b) sum = fma(S.lam_p[a * NMO + b], y[b], sum);
-          for (int k = 0; k < S.n_unp; ++k) sum = fma(S.lam_u[a * S.n_unp + k], SGI(Nd + k, e), sum);
-          Wv[a] = sum;
-        }
-      } else {
-        const int j = e - N;
-        double y[NMO];
-#pragma unroll
-        for (int a = 0; a < NMO; ++a) {
-          double sum = 0;
-          for (int i = 0; i < N; ++i) sum = fma(SPHI(i, 0, a), SGI(j, i), sum);
-          y[a] = sum;
-        }
-#pragma unroll
-        for (int b = 0; b < NMO; ++b) {
-          double sum = 0;
-#pragma unroll
-          for (int a = 0; a < NMO; ++a) sum = fma(y[a], S.lam_p[a * NMO + b], sum);
-          Wv[b] = sum;
-        }
-      }
-#pragma unroll
-      for (int mo = 0; mo < NMO; ++mo) SW(e, mo) = Wv[mo];
-      // Jastrow terms of electron e at its current position (shared by all of its mesh points)
-      PosShared pos{s_r, WPC, wl};
-      SEL(e, 7) = jastrow_single(S, pos, e, SR(e, 0), SR(e, 1), SR(e, 2));
-    }
-    __syncthreads();
-
-    // ---- P2: mesh ratios (rounds 0 .. n_rounds_pt-1) and per-electron terms (the following n_rounds_el rounds); a warp
-    //      takes the next round from a shared counter.  A thread evaluates TWO mesh points of the same spin block at once
-    //      (same shell / primitive sequence, coefficient rows loaded once, twice the independent DFMA chains) ------------------
-    for (;;) {
-      int r = 0;
-      if (lane == 0) r = atomicAdd(&s_ctr[0], 1);
-      r = __shfl_sync(0xffffffffu, r, 0);
-      if (r >= n_rounds_pt + n_rounds_el) break;
-      if (r < n_rounds_pt) {
-        int pi = r * 32 + lane;  // pair index -> block (kin up, kin dn, ecp up, ecp dn)
-        int blk = 0;
-        while (blk < 4 && pi >= blk_pairs[blk]) {
-          pi -= blk_pairs[blk];
-          ++blk;
-        }
-        if (blk < 4) {
-          const int half = blk_pairs[blk];
-          const int sA = blk_start[blk] + pi;
-          const bool validB = pi + half < blk_size[blk];
-          const int sB = validB ? sA + half : sA;
-          const int sl[2] = {sA, sB};
-          double px[2], py[2], pz[2], angw[2], jold[2];
-          int el[2], wls[2];
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int wl = sl[i] % WPC, t = sl[i] / WPC;
-            wls[i] = wl;
-            PosShared pos{s_r, WPC, wl};
-            double rt[9];
-#pragma unroll
-            for (int c = 0; c < 9; ++c) rt[c] = SMISC(c);
-            double x, y, z;
-            angw[i] = 0.0;
-            if (blk < 2) {
-              const int e = t / 6;
-              const int s6 = t % 6, ax = s6 >> 1;
-              const double sg = (s6 & 1) ? -P.alat : P.alat;
-              pos.get(e, x, y, z);
-              px[i] = x + sg * rt[3 * ax];
-              py[i] = y + sg * rt[3 * ax + 1];
-              pz[i] = z + sg * rt[3 * ax + 2];
-              el[i] = e;
-            } else {
-              const int pt = t - n_kin;
-              const int k = pt % S.Nv, nn = (pt / S.Nv) % S.NN;
-              const int e = pt / (S.Nv * S.NN);
-              pos.get(e, x, y, z);
-              ecp_point(S, rt, x, y, z, nn, k, px[i], py[i], pz[i], angw[i], true);
-              el[i] = e;
-            }
-            jold[i] = SEL(el[i], 7);
-          }
-          SinkMOn<NMO, 2> sink;
-          sink.init(tab + ((blk & 1) ? B.off_C2 : B.off_C));
-          eval_val_n<CART, LMAX, 2>(tab, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int wl = wls[i], e = el[i];
-            PosShared pos{s_r, WPC, wl};
-            double ratio = 0.0;
-#pragma unroll
-            for (int mo = 0; mo < NMO; ++mo) ratio = fma(sink.acc[i][mo], SW(e, mo), ratio);
-            const double jr = qexp(jastrow_single(S, pos, e, px[i], py[i], pz[i]) - jold[i]);
-            if (i == 0 || validB) {
-              if (blk < 2) {
-                s_p[sl[i]] = -1.0 / (2.0 * a2) * (ratio * jr);
-              } else {
-                s_p[sl[i]] = P.dlt ? angw[i] * ratio : angw[i] * (ratio * jr);
-                s_j[sl[i] - n_kin * WPC] = jr;
-              }
-            }
-          }
-        }
-      } else {
-        // per-electron: continuum kinetic energy, bare / discretised el-ion, ECP local, el-el (pairs j > e)
-        const int s = (r - n_rounds_pt) * 32 + lane;
-        if (s < Ne * WPC) {
-          const int wl = s % WPC, e = s / WPC;
-          PosShared pos{s_r, WPC, wl};
-          double x, y, z;
-          pos.get(e, x, y, z);
-          double gD[3] = {0, 0, 0}, lD = 0;
-#pragma unroll
-          for (int mo = 0; mo < NMO; ++mo) {
-            const double wv = SW(e, mo);
-            gD[0] = fma(SPHI(e, 1, mo), wv, gD[0]);
-            gD[1] = fma(SPHI(e, 2, mo), wv, gD[1]);
-            gD[2] = fma(SPHI(e, 3, mo), wv, gD[2]);
-            lD = fma(SPHI(e, 4, mo), wv, lD);
-          }
-          lD -= gD[0] * gD[0] + gD[1] * gD[1] + gD[2] * gD[2];
-          double gJ[3] = {0, 0, 0}, lJ = 0, ei = 0, eid = 0, loc = 0, ee = 0;
-          const double eps = 1.0e-12;
-          for (int a = 0; a < S.n_atom; ++a) {
-            const double dx = x - S.Rn[3 * a], dy = y - S.Rn[3 * a + 1], dz = z - S.Rn[3 * a + 2];
-            const double d = sqrt(dx * dx + dy * dy + dz * dz);
-            ei -= S.Zeff[a] / d;
-            eid -= S.Zeff[a] / fmax(d, P.alat);
-            if (S.j1_type) {
-              const double rs = fmax(d, eps);
-              const double A = S.j1_A[a], c = S.j1_c[a], aa = S.j1_a;
-              double fp;
-              if (S.j1_type == 1) {
-                const double ex = qexp(-aa * c * rs);
-                fp = -A * (c * 0.5) * ex;
-                lJ += A * (aa * c * c * 0.5) * ex - A * c * ex / rs;
-              } else {
-                const double den = 1.0 + aa * c * rs;
-                fp = -A / (2.0 * den * den);
-                lJ += A * aa * c / (den * den * den) + 2.0 * fp / rs;
-              }
-              const double sc = fp / rs;
-              gJ[0] = fma(sc, dx, gJ[0]);
-              gJ[1] = fma(sc, dy, gJ[1]);
-              gJ[2] = fma(sc, dz, gJ[2]);
-            }
-            if (S.ecp_flag) {
-              const int lloc = S.ecp_lmax_atom[a];
-              double sum = 0.0;
-              for (int k = S.ecp_off[a]; k < S.ecp_off[a + 1]; ++k)
-                if (S.ecp_l[k] == lloc) sum += S.ecp_c[k] * ipow(d, S.ecp_p[k]) * qexp(-S.ecp_z[k] * d * d);
-              loc += sum / (d * d);
-            }
-          }
-          for (int j = 0; j < Ne; ++j) {
-            if (j == e) continue;
-            double x2, y2, z2;
-            pos.get(j, x2, y2, z2);
-            const double dx = x - x2, dy = y - y2, dz = z - z2;
-            const double d = sqrt(dx * dx + dy * dy + dz * dz);
-            if (j > e) ee += 1.0 / d;
-            if (S.j2_type) {
-              const double rs = fmax(d, eps), aa = S.j2_a;
-              double fp;
-              if (S.j2_type == 1) {
-                const double den = 1.0 + aa * rs;
-                fp = 0.5 / (den * den);
-                lJ += -aa / (den * den * den) + 2.0 * fp / rs;
-              } else {
-                const double ex = qexp(-aa * rs);
-                fp = 0.5 * ex;
-                lJ += -(aa * 0.5) * ex + 2.0 * fp / rs;
-              }
-              const double sc = fp / rs;
-              gJ[0] = fma(sc, dx, gJ[0]);
-              gJ[1] = fma(sc, dy, gJ[1]);
-              gJ[2] = fma(sc, dz, gJ[2]);
-            }
-          }
-          const double gx = gJ[0] + gD[0], gy = gJ[1] + gD[1], gz = gJ[2] + gD[2];
-          SEL(e, 0) = -0.5 * (lJ + lD + gx * gx + gy * gy + gz * gz);
-          SEL(e, 1) = ei;
-          SEL(e, 2) = eid;
-          SEL(e, 3) = loc;
-          SEL(e, 4) = ee;
-        }
-      }
-    }
-    __syncthreads();
-    if (tid == 0) s_ctr[0] = 0;  // the next P2 starts after at least one more barrier
-
-    // ---- P3: assemble -----------------------------------------------------------------------------------------------
-    if (P.mode == 2) {
-      if (tid < WPC) {
-        const int wl = tid, w = w0 + wl;
-        const bool live = w < P.nw;
-        double T = 0, vbare = S.v_ion_ion, vl = 0, vnl = 0;
-        for (int e = 0; e < Ne; ++e) {
-          T += SEL(e, 0);
-          vbare += SEL(e, 1) + SEL(e, 4);
-          vl += SEL(e, 3);
-          if (P.T_elem && live) P.T_elem[(size_t)w * Ne + e] = SEL(e, 0);
-        }
-        for (int k = 0; k < n_ecp; ++k) vnl += s_p[k * WPC + wl];
-        if (live) {
-          P.e_L[w] = T + (vbare + (vl + vnl));
-          if (P.V_parts) {
-            P.V_parts[(size_t)w * 4 + 0] = vbare;
-            P.V_parts[(size_t)w * 4 + 1] = vl;
-            P.V_parts[(size_t)w * 4 + 2] = vnl;
-            P.V_parts[(size_t)w * 4 + 3] = 0.0;
-          }
-        }
-      }
-      break;
-    }
-    // (a) per (walker, electron): fixed-node split of its 6 kinetic elements, regularised el-ion term
-    //     (jqmc/jqmc_gfmc.py:4829-4939); the FN values overwrite s_p
-    for (int s = tid; s < Ne * WPC; s += nthr) {
-      const int wl = s % WPC, e = s / WPC;
-      bool flip = false;
-      double nd = 0, kinFN = 0, kinSP = 0;
-      for (int s6 = 0; s6 < 6; ++s6) {
-        const double v = s_p[(6 * e + s6) * WPC + wl];
-        flip = flip || (v >= 0.0);
-        nd += v + 1.0 / (4.0 * a2);
-        const double fn = fmin(v, 0.0);
-        kinFN += fn;
-        kinSP += fmax(v, 0.0);
-        s_p[(6 * e + s6) * WPC + wl] = fn;
-      }
-      const double zv = SEL(e, 1) + SEL(e, 0) - nd;
-      const double eib = S.ecp_flag ? SEL(e, 1) : SEL(e, 2);
-      SEL(e, 0) = flip ? fmax(zv, eib) : zv;  // regularised el-ion term of this electron
-      SEL(e, 5) = kinFN;
-      SEL(e, 6) = kinSP;
-    }
-    // (a') per (walker, ECP point): fixed-node split of the non-local elements (s_j: Jastrow ratio -> positive part)
-    for (int s = tid; s < n_ecp * WPC; s += nthr) {
-      const double v = s_p[n_kin * WPC + s];
-      double fn = fmin(v, 0.0);
-      if (P.dlt) fn *= s_j[s];
-      s_p[n_kin * WPC + s] = fn;
-      s_j[s] = fmax(v, 0.0);
-    }
-    __syncthreads();
-    // (b) per walker: sums, weight, normalisation of the move probabilities
-    if (tid < WPC) {
-      const int wl = tid;
-      const double diag_kin = 3.0 / (2.0 * a2) * Ne;
-      double sum_kinFN = 0, SP_kin = 0, sum_opt = 0, ee = 0, loc = 0;
-      for (int e = 0; e < Ne; ++e) {
-        sum_kinFN += SEL(e, 5);
-        SP_kin += SEL(e, 6);
-        sum_opt += SEL(e, 0);
-        ee += SEL(e, 4);
-        loc += SEL(e, 3);
-      }
-      const double disc_bare = ee + S.v_ion_ion + sum_opt;
-      double sum_eFN = 0, SP_e = 0;
-      for (int k = 0; k < n_ecp; ++k) {
-        sum_eFN += s_p[(n_kin + k) * WPC + wl];
-        SP_e += s_j[k * WPC + wl];
-      }
-      nondiag = sum_kinFN + sum_eFN;
-      diag = S.ecp_flag ? diag_kin + disc_bare + loc + SP_kin + SP_e : diag_kin + disc_bare + SP_kin;
-      if constexpr (TAU) {
-        // time spent in this configuration, weight, remaining time (jqmc/jqmc_gfmc.py:1003-1012); the move is suppressed
-        // once the time is used up (:1024-1025)
-        const double e_L = diag + nondiag;
-        if (tau_left > 0.0) ++pc;
-        const double tau_update = fmin(tau_left, log(1.0 - xi) / nondiag);
-        w_L *= qexp(-tau_update * e_L);
-        tau_left -= tau_update;
-        SMISC(14) = tau_left <= 0.0 ? 0.0 : 1.0;
-        double tot = 0;
-        for (int k = 0; k < NPT; ++k) tot += s_p[k * WPC + wl];
-        SMISC(13) = tot;
-      } else if (P.mode == 0) {
-        const double b_x = 1.0 / (diag - P.E_scf) * (-nondiag);
-        w_L *= b_x;
-        double tot = 0;
-        for (int k = 0; k < NPT; ++k) tot += s_p[k * WPC + wl];  // sequential fp64 sum in the reference's vector order
-        SMISC(13) = tot;
-      }
-    }
-    if constexpr (TAU) {
-      n_done = it + 1;
-      const int mv = (tid < WPC) ? (s_misc[14 * WPC + tid] != 0.0) : 0;
-      if (!__syncthreads_or(mv)) break;  // every walker of the CTA has used up its time
-    } else {
-      if (P.mode != 0) break;
-      __syncthreads();
-    }
-    // (c) all threads: p / total
-    for (int s = tid; s < NPT * WPC; s += nthr) s_p[s] = s_p[s] / s_misc[13 * WPC + (s % WPC)];
-    __syncthreads();
-    // (d) per walker: sequential cumulative sum, first c >= u (searchsorted 'left', jqmc/jqmc_gfmc.py:5057-5062)
-    if (tid < WPC) {
-      const int wl = tid;
-      PosShared pos{s_r, WPC, wl};
-      const double u = TAU ? u_move : P.ru[(size_t)it * P.nw + GW(wl)];
-      int ksel = NPT - 1;
-      double c = 0;
-      for (int k = 0; k < NPT; ++k) {
-        c += s_p[k * WPC + wl];
-        if (c >= u) {
-          ksel = k;
-          break;
-        }
-      }
-      double rt[9];
-#pragma unroll
-      for (int cc = 0; cc < 9; ++cc) rt[cc] = SMISC(cc);
-      int e;
-      double x, y, z, px, py, pz, dummy;
-      if (ksel < n_kin) {
-        e = ksel / 6;
-        const int s6 = ksel % 6, ax = s6 >> 1;
-        const double sg = (s6 & 1) ? -P.alat : P.alat;
-        pos.get(e, x, y, z);
-        px = x + sg * rt[3 * ax];
-        py = y + sg * rt[3 * ax + 1];
-        pz = z + sg * rt[3 * ax + 2];
-      } else {
-        const int pt = ksel - n_kin;
-        const int k = pt % S.Nv, nn = (pt / S.Nv) % S.NN;
-        e = pt / (S.Nv * S.NN);
-        pos.get(e, x, y, z);
-        ecp_point(S, rt, x, y, z, nn, k, px, py, pz, dummy, false);
-      }
-      SMISC(9) = px;
-      SMISC(10) = py;
-      SMISC(11) = pz;
-      SMISC(12) = (double)e;
-    }
-    __syncthreads();
-
-    // ---- P4: value/grad/lap of the moved electron: warp = basis chunks wid, wid+NWARP, ..., lane = walker --------------
-    {
-      const int* cbeg = (const int*)(tab + P.off_cbeg);
-      for (int wl = lane; wl < WPC; wl += 32) {
-        const int es = (int)SMISC(12);
-        SinkMO5<NMO> sink;
-        sink.init(tab + (es < N ? B.off_C : B.off_C2));
-        for (int c = wid; c < P.n_chunk; c += NWARP)
-          eval_vgl<CART, LMAX>(tab, B, P.off_cseg, SMISC(9), SMISC(10), SMISC(11), cbeg[c], cbeg[c + 1], sink);
-#pragma unroll
-        for (int q = 0; q < 5; ++q)
-#pragma unroll
-          for (int mo = 0; mo < NMO; ++mo) s_part[((wid * 5 + q) * NMO + mo) * WPC + wl] = sink.acc[q][mo];
-      }
-    }
-    __syncthreads();
-    for (int s = tid; s < 5 * NMO * WPC; s += nthr) {  // fixed-order sum over the warps' partials
-      double sum = 0;
-      for (int c = 0; c < NWARP; ++c) sum += s_part[(size_t)c * 5 * NMO * WPC + s];
-      s_stage[s] = sum;
-    }
-    __syncthreads();
-    // Sherman-Morrison (jqmc/jqmc_gfmc.py:5083-5141): task = (walker, row i); read phase, barrier, write phase
-    {  // N * WPC <= blockDim.x is guaranteed by launch_walker: one pass
-      double newrow[16];
-      const int s = tid;
-      bool act = s < N * WPC;
-      int wl = 0, i = 0;
-      if (act) {
-        wl = s % WPC;
-        i = s / WPC;
-        if (TAU && SMISC(14) == 0.0) act = false;  // walker out of time: no move
-      }
-      if (act) {
-        const int es = (int)SMISC(12);
-        double pn[NMO];
-#pragma unroll
-        for (int mo = 0; mo < NMO; ++mo) pn[mo] = s_stage[mo * WPC + wl] - SPHI(es, 0, mo);  // phi_new - phi_old
-        if (es < N) {
-          const int k = es;
-          double t[NMO], vvec[16];
-#pragma unroll
-          for (int b = 0; b < NMO; ++b) {
-            double sum = 0;
-#pragma unroll
-            for (int a = 0; a < NMO; ++a) sum = fma(pn[a], S.lam_p[a * NMO + b], sum);
-            t[b] = sum;
-          }
-          double acc = 0;
-          for (int j = 0; j < Nd; ++j) {
-            double sum = 0;
-#pragma unroll
-            for (int b = 0; b < NMO; ++b) sum = fma(t[b], SPHI(N + j, 0, b), sum);
-            vvec[j] = sum;
-            acc = fma(sum, SGI(j, k), acc);
-          }
-          for (int q = 0; q < S.n_unp; ++q) {
-            double sum = 0;
-#pragma unroll
-            for (int a = 0; a < NMO; ++a) sum = fma(pn[a], S.lam_u[a * S.n_unp + q], sum);
-            vvec[Nd + q] = sum;
-            acc = fma(sum, SGI(Nd + q, k), acc);
-          }
-          const double invD = 1.0 / (1.0 + acc);
-          const double coli = SGI(i, k);
-          for (int jp = 0; jp < N; ++jp) {
-            double vt = 0;
-            for (int j = 0; j < N; ++j) vt = fma(vvec[j], SGI(j, jp), vt);
-            newrow[jp] = SGI(i, jp) - (coli * vt) * invD;
-          }
-        } else {
-          const int k = es - N;
-          double t[NMO], uvec[16];
-#pragma unroll
-          for (int a = 0; a < NMO; ++a) {
-            double sum = 0;
-#pragma unroll
-            for (int b = 0; b < NMO; ++b) sum = fma(S.lam_p[a * NMO + b], pn[b], sum);
-            t[a] = sum;
-          }
-          for (int ii = 0; ii < N; ++ii) {
-            double sum = 0;
-#pragma unroll
-            for (int a = 0; a < NMO; ++a) sum = fma(SPHI(ii, 0, a), t[a], sum);
-            uvec[ii] = sum;
-          }
-          double au_i = 0, au_k = 0;
-          for (int j = 0; j < N; ++j) {
-            au_i = fma(SGI(i, j), uvec[j], au_i);
-            au_k = fma(SGI(k, j), uvec[j], au_k);
-          }
-          const double invD = 1.0 / (1.0 + au_k);
-          for (int j = 0; j < N; ++j) newrow[j] = SGI(i, j) - (au_i * SGI(k, j)) * invD;
-        }
-      }
-      __syncthreads();
-      if (act)
-        for (int j = 0; j < N; ++j) SGI(i, j) = newrow[j];
-    }
-    __syncthreads();
-    for (int s = tid; s < 5 * NMO * WPC; s += nthr) {
-      const int wl = s % WPC, item = s / WPC;
-      const int es = (int)SMISC(12);
-      if (TAU && SMISC(14) == 0.0) continue;
-      s_phi[(es * 5 * NMO + item) * WPC + wl] = s_stage[s];
-    }
-    if (tid < WPC && !(TAU && s_misc[14 * WPC + tid] == 0.0)) {
-      const int wl = tid;
-      const int es = (int)SMISC(12);
-      SR(es, 0) = SMISC(9);
-      SR(es, 1) = SMISC(10);
-      SR(es, 2) = SMISC(11);
-    }
-    __syncthreads();
-  }
-
-  // ---- write back -------------------------------------------------------------------------------------------
-  if (P.mode == 2) return;
-  if constexpr (TAU) {
-    if (tid < WPC && w0 + tid < P.nw) {
-      const int wl = tid, w = w0 + tid;
-      P.e_L[w] = diag + nondiag;
-      for (int c = 0; c < 9; ++c) P.RT_out[(size_t)w * 9 + c] = SMISC(c);
-      P.keys[2 * w] = key.a;
-      P.keys[2 * w + 1] = key.b;
-      if (!P.tail) {
-        P.w[w] = w_L;
-        P.pc[w] = pc;
-      }
-    }
-    if (P.tail) return;
-    if (tid == 0) {
-      P.n_cta[blockIdx.x] = n_done;
-      atomicMax(P.n_max, n_done);
-    }
-  } else if (tid < WPC && w0 + tid < P.nw) {
-    const int wl = tid, w = w0 + tid;
-    P.V_diag[w] = diag;
-    P.V_nondiag[w] = nondiag;
-    if (P.mode == 0) {
-      P.w[w] = w_L;
-      for (int c = 0; c < 9; ++c) P.RT_out[(size_t)w * 9 + c] = SMISC(c);
-    }
-  }
-  if (P.mode == 0) {
-    for (int idx = tid; idx < Ne * 3 * WPC; idx += nthr) {
-      const int wl = idx % WPC, it = idx / WPC, e = it / 3, c = it % 3;
-      const int w = w0 + wl;
-      if (w >= P.nw) continue;
-      if (e < N) P.r_up[((size_t)w * N + e) * 3 + c] = s_r[idx];
-      else P.r_dn[((size_t)w * Nd + (e - N)) * 3 + c] = s_r[idx];
-    }
-    for (int idx = tid; idx < NN2 * WPC; idx += nthr) {
-      const int wl = idx % WPC, it = idx / WPC;
-      if (w0 + wl < P.nw) P.Ginv[(size_t)(w0 + wl) * NN2 + it] = s_Gi[idx];
-    }
-  }
-#undef SR
-#undef SGI
-#undef SPHI
-#undef SW
-#undef SEL
-#undef SMISC
-#undef GW
-}
-
-// key chain of the projection loop: two splits per projection (jqmc/jqmc_gfmc.py:5275-5283). thread = walker
-__global__ void k_lrdmc_keychain(int nw, int nmpm, uint32_t* __restrict__ keys, uint2* __restrict__ sub) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nw) return;
-  Key k{keys[2 * w], keys[2 * w + 1]};
-  for (int p = 0; p < nmpm * 2; ++p) {
-    Key s;
-    rng_split(k, s);
-    sub[(size_t)p * nw + w] = make_uint2(s.a, s.b);
-  }
-  keys[2 * w] = k.a;
-  keys[2 * w + 1] = k.b;
-}
-// rotation matrix (R^T, row-major) and move uniform of every projection: thread = (projection, walker)
-__global__ void k_lrdmc_draws(int nw, int nmpm, int random_mesh, const uint2* __restrict__ sub, double* __restrict__ rRT,
-                              double* __restrict__ ru) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)nmpm * nw) return;
-  const int w = (int)(t % nw), p = (int)(t / nw);
-  const uint2 rk = sub[((size_t)p * 2) * nw + w], mk = sub[((size_t)p * 2 + 1) * nw + w];
-  double al = 0, be = 0, ga = 0;
-  if (random_mesh) {
-    const double two_pi = 6.283185307179586;
-    const Key k{rk.x, rk.y};
-    al = rng_uniform_bits(rng_bits64(k, 0u), -two_pi, two_pi);
-    be = rng_uniform_bits(rng_bits64(k, 1u), -two_pi, two_pi);
-    ga = rng_uniform_bits(rng_bits64(k, 2u), -two_pi, two_pi);
-  }
-  double sa, ca, sb, cb, sg, cg;
-  sincos(al, &sa, &ca);
-  sincos(be, &sb, &cb);
-  sincos(ga, &sg, &cg);
-  const double R[9] = {cb * cg, cg * sa * sb - ca * sg, sa * sg + ca * cg * sb, cb * sg, ca * cg + sa * sb * sg,
-                       ca * sb * sg - cg * sa, -sb, cb * sa, ca * cb};
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) rRT[((size_t)p * 9 + i * 3 + j) * nw + w] = R[j * 3 + i];
-  ru[t] = rng_uniform_bits(rng_bits64(Key{mk.x, mk.y}), 0.0, 1.0);
-}
-
-// walkers per CTA: fill the SMs (`slots` CTAs can be resident at once) with as few idle lanes as possible
-int choose_wpc(int nw, int n_points, int sms, int ctas_per_sm, int wpc_max, int nthr) {
-  int best = 1;
-  double best_score = -1.0;
-  for (int wpc = 1; wpc <= wpc_max; ++wpc) {
-    const int ctas = (nw + wpc - 1) / wpc;
-    const int slots = sms * ctas_per_sm;
-    const int waves = (ctas + slots - 1) / slots;
-    const double fill = (double)ctas / ((double)waves * slots);
-    const int pairs = (n_points * wpc + 1) / 2;
-    const int rounds = (pairs + nthr - 1) / nthr;
-    const double lanes = (double)pairs / ((double)rounds * nthr);
-    const double score = fill * lanes * (1.0 - 0.15 / wpc);  // mild preference for amortising the table staging
-    if (score > best_score) {
-      best_score = score;
-      best = wpc;
-    }
-  }
-  return best;
-}
-
-// One CTA of 16 warps per SM: the warps of an SM then run the same phase of the projection loop at the same time, which
-// keeps the instruction working set (one phase, not the whole loop) inside the instruction caches; four independent
-// 4-warp CTAs per SM were measured 5x stalled on instruction fetch (profiles/r01_*).
-int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid, bool tau_mode = false) {
-  const SysDev& S = h->sys;
-  const int P = h->nmo_pad;
-  if (S.n_up > 16) return fail(QE_ERR_UNSUPPORTED, "more than 16 electrons per spin is not implemented in this build");
-  const int NWARP = 16;
-  A.off_cseg = h->b_up.off_cseg;
-  A.off_cbeg = h->b_up.off_cbeg;
-  A.n_chunk = h->b_up.n_chunk;
-  const int Ne = S.n_e;
-  const int n_kin = A.mode == 2 ? 0 : 6 * Ne;
-  const int n_ecp = S.ecp_flag ? Ne * S.NN * S.Nv : 0;
-  const size_t per_walker = (size_t)Ne * 3 + (size_t)S.n_up * S.n_up + (size_t)Ne * 5 * P + (size_t)Ne * P + std::max(1, n_kin + n_ecp) +
-                            std::max(1, n_ecp) + (size_t)Ne * 8 + (size_t)NWARP * 5 * P + 5 * P + 16;
-  const size_t fixed = (size_t)h->b_up.dev.bytes + sys_bytes(S, P) + 14 * 16 + 64;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const size_t budget = 227 * 1024;
-  if (budget < fixed + per_walker * 8) return fail(QE_ERR_UNSUPPORTED, "system too large for the fused walker kernel (shared memory)");
-  int wpc_max = (int)std::min<size_t>(32, (budget - fixed) / (per_walker * 8));
-  wpc_max = std::max(1, std::min(wpc_max, NWARP * 32 / S.n_up));  // Sherman-Morrison: one (walker, row) task per thread
-  A.wpc = h->wpc_override > 0 ? std::min(h->wpc_override, wpc_max)
-                              : choose_wpc(A.nw, std::max(1, n_kin + n_ecp), sms, 1, wpc_max, NWARP * 32);
-  const size_t smem = fixed + per_walker * 8 * A.wpc;
-  {
-    LaunchScope ls_(h, kid, st);
-#define CALL3(NMO, CART, LMAX, TAU)                                                                                         \
-  do {                                                                                                                      \
-    CUDA_TRY(cudaFuncSetAttribute(k_walker<NMO, CART, LMAX, TAU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_walker<NMO, CART, LMAX, TAU><<<nblk(A.nw, A.wpc), NWARP * 32, smem, st>>>(h->b_up.dev, S, A);                          \
-  } while (0)
-#define CALL2(NMO, CART, LMAX)                 \
-  do {                                         \
-    if (tau_mode) CALL3(NMO, CART, LMAX, true); \
-    else CALL3(NMO, CART, LMAX, false);        \
-  } while (0)
-#define CALL(NMO, CART)                                  \
-  do {                                                   \
-    if (h->b_up.dev.lmax <= 4) CALL2(NMO, CART, 4);      \
-    else CALL2(NMO, CART, 6);                            \
-  } while (0)
-    DISPATCH_NMO_CART(h, CALL);
-#undef CALL
-#undef CALL2
-#undef CALL3
-  }
-  CHECK_LAUNCH();
-  return QE_OK;
-}
-
-}  // namespace
+// Exported entries of the fused per-walker kernel (qe_walker_kernel.cuh): GFMC_n projection, V elements, VMC local energy.
+// The GFMC_t instantiations live in qe_walker_tau.cu (separate translation unit: the two compile in parallel).
+#include "qe_walker_kernel.cuh"
 
 size_t lrdmc_draws_bytes(int nw, int nmpm) { return (size_t)nmpm * nw * (2 * 8 + 9 * 8 + 8) + 4 * 256; }
 int lrdmc_draws(qe_engine* h, int nw, int nmpm, int random_mesh, uint32_t* keys, WsCarve& c, double** rRT, double** ru, cudaStream_t st) {
@@ -943,56 +54,7 @@ extern "C" int qe_lrdmc_project(qe_engine* h, int nw, double* w, double* r_up, d
   A.V_nondiag = V_nondiag;
   A.rRT = rRT;
   A.ru = ru;
-  return launch_walker(h, A, st, K_LRDMC_PROJ);
-}
-
-// GFMC_t projection: every walker is propagated for the imaginary time tau (jqmc/jqmc_gfmc.py:724-1110, 1539-1570).
-// Main pass: one CTA runs its walkers until all of them are out of time and records how many projections that took; tail
-// pass: CTAs that finished before the slowest one replay the remaining (no-move) iterations of the reference's
-// while_loop -- three key splits each and a last evaluation of e_L with that iteration's mesh rotation -- so that keys,
-// e_L and RT equal what the reference returns.
-extern "C" int qe_lrdmc_project_tau(qe_engine* h, int nw, double* w, double* r_up, double* r_dn, double* Ginv, uint32_t* keys,
-                                    double tau, int random_discretized_mesh, int non_local_move, double alat,
-                                    int32_t* projection_counter, double* e_L, double* RT, void* stream) {
-  if (!h || nw <= 0 || !w || !r_up || !Ginv || !keys || !RT || !e_L || !projection_counter || (!r_dn && h->sys.n_dn > 0))
-    return fail(QE_ERR_INVALID, "qe_lrdmc_project_tau: bad argument");
-  if (!(alat > 0)) return fail(QE_ERR_INVALID, "qe_lrdmc_project_tau: alat must be positive");
-  if (!(tau > 0)) return fail(QE_ERR_INVALID, "qe_lrdmc_project_tau: tau must be positive");
-  if (non_local_move != 0 && non_local_move != 1)
-    return fail(QE_ERR_INVALID, "qe_lrdmc_project_tau: non_local_move must be 0 (tmove) or 1 (dltmove)");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (use_wide(h))
-    return wide_lrdmc_tau(h, nw, w, r_up, r_dn, Ginv, keys, tau, random_discretized_mesh, non_local_move, alat, projection_counter,
-                          e_L, RT, st);
-  int rc = ensure_ws(h, (size_t)(nw + 8) * sizeof(int) + 4096);
-  if (rc) return rc;
-  WsCarve c{(char*)h->ws};
-  int* n_max = c.take<int>(4);
-  int* n_cta = c.take<int>((size_t)nw);
-  CUDA_TRY(cudaMemsetAsync(n_max, 0, 4 * sizeof(int), st));
-  WalkerArgs A{};
-  A.nw = nw;
-  A.nmpm = 1;
-  A.mode = 0;
-  A.dlt = non_local_move;
-  A.alat = alat;
-  A.w = w;
-  A.r_up = r_up;
-  A.r_dn = r_dn;
-  A.Ginv = Ginv;
-  A.RT_out = RT;
-  A.e_L = e_L;
-  A.tau = tau;
-  A.random_mesh = random_discretized_mesh;
-  A.keys = keys;
-  A.pc = projection_counter;
-  A.n_cta = n_cta;
-  A.n_max = n_max;
-  A.tail = 0;
-  rc = launch_walker(h, A, st, K_LRDMC_TAU, true);
-  if (rc) return rc;
-  A.tail = 1;
-  return launch_walker(h, A, st, K_LRDMC_TAU_TAIL, true);
+  return launch_walker<false>(h, A, st, K_LRDMC_PROJ);
 }
 
 extern "C" int qe_lrdmc_velements(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,
@@ -1015,7 +77,7 @@ extern "C" int qe_lrdmc_velements(qe_engine* h, int nw, const double* r_up, cons
   A.RT_in = RT;
   A.V_diag = V_diag;
   A.V_nondiag = V_nondiag;
-  return launch_walker(h, A, (cudaStream_t)stream, K_LRDMC);
+  return launch_walker<false>(h, A, (cudaStream_t)stream, K_LRDMC);
 }
 
 // fused local energy (mode 2); returns QE_ERR_UNSUPPORTED when the system does not fit, so that the caller
@@ -1034,11 +96,17 @@ int qe_local_energy_fused(qe_engine* h, int nw, const double* r_up, const double
   A.e_L = e_L;
   A.T_elem = T_elem;
   A.V_parts = V_parts;
-  return launch_walker(h, A, st, K_EL_FUSED);
+  return launch_walker<false>(h, A, st, K_EL_FUSED);
 }
 
 extern "C" int qe_set_walkers_per_cta(qe_engine* h, int wpc) {
   if (!h || wpc < 0 || wpc > 32) return fail(QE_ERR_INVALID, "qe_set_walkers_per_cta: wpc must be 0 (automatic) .. 32");
   h->wpc_override = wpc;
+  return QE_OK;
+}
+
+extern "C" int qe_set_walker_warps(qe_engine* h, int warps) {
+  if (!h || (warps != 0 && warps != 4 && warps != 8 && warps != 16)) return fail(QE_ERR_INVALID, "qe_set_walker_warps: warps must be 0 (default), 4, 8 or 16");
+  h->walker_warps = warps;
   return QE_OK;
 }

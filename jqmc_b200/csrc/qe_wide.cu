@@ -1551,8 +1551,8 @@ extern "C" int qe_set_gemm_reference(int on) {
 // -------------------------------------------------------------------------------------------------
 // _geminal_inv_batched / evaluate_ln_wavefunction
 // -------------------------------------------------------------------------------------------------
-int wide_geminal_init(qe_engine* h, int nw, const double* r_up, const double* r_dn, double* G, double* Ginv, double* ln_psi,
-                      double* sign, cudaStream_t st) {
+static int wide_geminal_init_1(qe_engine* h, int nw, const double* r_up, const double* r_dn, double* G, double* Ginv, double* ln_psi,
+                               double* sign, cudaStream_t st) {
   const SysDev& S = h->sys;
   const WideTabs& T = h->wt;
   TRY(ensure_ws(h, state_bytes(h, nw, 1, true) + 4096));
@@ -1571,8 +1571,8 @@ int wide_geminal_init(qe_engine* h, int nw, const double* r_up, const double* r_
 // -------------------------------------------------------------------------------------------------
 // compute_local_energy_fast
 // -------------------------------------------------------------------------------------------------
-int wide_local_energy(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,
-                      double* e_L, double* T_elem, double* V_parts, cudaStream_t st) {
+static int wide_local_energy_1(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,
+                               double* e_L, double* T_elem, double* V_parts, cudaStream_t st) {
   const SysDev& S = h->sys;
   const WideTabs& T = h->wt;
   const int N = S.n_up, Ne = S.n_e;
@@ -1660,8 +1660,8 @@ int wide_eval_orbitals(qe_engine* h, int which, int n_pts, const double* r, doub
 // -------------------------------------------------------------------------------------------------
 // _update_electron_positions: nmpm Metropolis proposals
 // -------------------------------------------------------------------------------------------------
-int wide_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, uint32_t* keys, double* G, double* Ginv, int nmpm, double Dt,
-                     double epsilon_AS, int32_t* acc, int32_t* rej, cudaStream_t st) {
+static int wide_mcmc_update_1(qe_engine* h, int nw, double* r_up, double* r_dn, uint32_t* keys, double* G, double* Ginv, int nmpm,
+                              double Dt, double epsilon_AS, int32_t* acc, int32_t* rej, cudaStream_t st) {
   const SysDev& S = h->sys;
   const WideTabs& T = h->wt;
   const int N = S.n_up, Nd = S.n_dn, Ne = S.n_e;
@@ -1748,12 +1748,71 @@ struct TauArgs {
 static int wide_lrdmc_impl(qe_engine* h, int mode, int nw, double* w, double* r_up, double* r_dn, double* Ginv, uint32_t* keys,
                            double E_scf, int nmpm, int random_mesh, int non_local_move, double alat, const double* RT_in,
                            double* RT_out, double* V_diag, double* V_nondiag, const TauArgs* ta, cudaStream_t st);
+// -------------------------------------------------------------------------------------------------
+// Walker slices.  The cached state of this family is O(5 n_row N_e) doubles per walker (4.9 MB for the 100 e / 1000 AO
+// system), so a call over many walkers (BASELINE configs[4] sweeps to 64k per GPU = 320 GB) is run as consecutive slices
+// of walkers through the same workspace: walkers are independent (their draws come from their own keys), the caller's
+// arrays are walker-major, so a slice is a pointer offset and the results are identical to one big call.
+// -------------------------------------------------------------------------------------------------
+static int g_wide_slice = 0;  // 0: automatic (workspace budget), > 0: walkers per slice
+extern "C" int qe_set_wide_slice(int walkers) {
+  if (walkers < 0) return fail(QE_ERR_INVALID, "qe_set_wide_slice: walkers must be >= 0");
+  g_wide_slice = walkers;
+  return QE_OK;
+}
+static int wide_slice(qe_engine* h, int nw, int nmpm) {
+  if (g_wide_slice > 0) return std::min(nw, g_wide_slice);
+  const size_t per_walker = (state_bytes(h, 1024, 5, true) + 2 * newpoint_bytes(h, 1024, 5) + lrdmc_draws_bytes(1024, nmpm) +
+                             mcmc_draws_bytes(1024, nmpm)) / 1024 + (size_t)h->sys.n_e * 8 * 130;
+  if (per_walker * (size_t)nw <= ((size_t)1 << 30)) return nw;  // small call: no need to ask the driver
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return nw;
+  const size_t budget = std::max<size_t>((size_t)1 << 30, (size_t)(0.45 * (double)(free_b + h->ws_bytes)));
+  size_t n = budget / std::max<size_t>(per_walker, 1);
+  if (n >= (size_t)nw) return nw;
+  n = std::max<size_t>(32, n / 32 * 32);
+  return (int)std::min<size_t>(n, (size_t)nw);
+}
+#define OFF(p, stride) ((p) ? (p) + (size_t)w0 * (stride) : nullptr)
+int wide_geminal_init(qe_engine* h, int nw, const double* r_up, const double* r_dn, double* G, double* Ginv, double* ln_psi,
+                      double* sign, cudaStream_t st) {
+  const size_t N = h->sys.n_up, Nd = h->sys.n_dn;
+  const int sl = wide_slice(h, nw, 1);
+  for (int w0 = 0; w0 < nw; w0 += sl)
+    TRY(wide_geminal_init_1(h, std::min(sl, nw - w0), OFF(r_up, N * 3), OFF(r_dn, Nd * 3), OFF(G, N * N), OFF(Ginv, N * N),
+                            OFF(ln_psi, 1), OFF(sign, 1), st));
+  return QE_OK;
+}
+int wide_local_energy(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,
+                      double* e_L, double* T_elem, double* V_parts, cudaStream_t st) {
+  const size_t N = h->sys.n_up, Nd = h->sys.n_dn, Ne = h->sys.n_e;
+  const int sl = wide_slice(h, nw, 1);
+  for (int w0 = 0; w0 < nw; w0 += sl)
+    TRY(wide_local_energy_1(h, std::min(sl, nw - w0), OFF(r_up, N * 3), OFF(r_dn, Nd * 3), OFF(RT, 9), OFF(Ginv, N * N), OFF(e_L, 1),
+                            OFF(T_elem, Ne), OFF(V_parts, 4), st));
+  return QE_OK;
+}
+int wide_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, uint32_t* keys, double* G, double* Ginv, int nmpm, double Dt,
+                     double epsilon_AS, int32_t* acc, int32_t* rej, cudaStream_t st) {
+  const size_t N = h->sys.n_up, Nd = h->sys.n_dn;
+  const int sl = wide_slice(h, nw, nmpm);
+  for (int w0 = 0; w0 < nw; w0 += sl)
+    TRY(wide_mcmc_update_1(h, std::min(sl, nw - w0), OFF(r_up, N * 3), OFF(r_dn, Nd * 3), OFF(keys, 2), OFF(G, N * N), OFF(Ginv, N * N),
+                           nmpm, Dt, epsilon_AS, OFF(acc, 1), OFF(rej, 1), st));
+  return QE_OK;
+}
 int wide_lrdmc(qe_engine* h, int mode, int nw, double* w, double* r_up, double* r_dn, double* Ginv, uint32_t* keys, double E_scf,
                int nmpm, int random_mesh, int non_local_move, double alat, const double* RT_in, double* RT_out, double* V_diag,
                double* V_nondiag, cudaStream_t st) {
-  return wide_lrdmc_impl(h, mode, nw, w, r_up, r_dn, Ginv, keys, E_scf, nmpm, random_mesh, non_local_move, alat, RT_in, RT_out, V_diag,
-                         V_nondiag, nullptr, st);
+  const size_t N = h->sys.n_up, Nd = h->sys.n_dn;
+  const int sl = wide_slice(h, nw, nmpm);
+  for (int w0 = 0; w0 < nw; w0 += sl)
+    TRY(wide_lrdmc_impl(h, mode, std::min(sl, nw - w0), OFF(w, 1), OFF(r_up, N * 3), OFF(r_dn, Nd * 3), OFF(Ginv, N * N), OFF(keys, 2),
+                        E_scf, nmpm, random_mesh, non_local_move, alat, OFF(RT_in, 9), OFF(RT_out, 9), OFF(V_diag, 1), OFF(V_nondiag, 1),
+                        nullptr, st));
+  return QE_OK;
 }
+#undef OFF
 // GFMC_t projection on the general path: the reference's while_loop literally -- every walker runs every iteration (walkers
 // that are out of time make no move) until none has time left (jqmc/jqmc_gfmc.py:1539-1570).  The loop condition is read
 // back once per iteration (4 bytes; the iteration itself is ~ms of launches on the systems this path serves).

@@ -371,9 +371,17 @@ class WalkerEngine:
         """Debugging aid: plain DFMA GEMM instead of the fp64 tensor-core kernel in the general path."""
         _lib.check(self._lib.qe_set_gemm_reference(1 if on else 0), "qe_set_gemm_reference")
 
+    def set_wide_slice(self, walkers: int):
+        """General family: walkers per slice of one call (0 = automatic from the free device memory); process-wide."""
+        _lib.check(self._lib.qe_set_wide_slice(int(walkers)), "qe_set_wide_slice")
+
     def set_walkers_per_cta(self, wpc: int):
         """Walkers per CTA of the fused walker kernel (0 = automatic)."""
         _lib.check(self._lib.qe_set_walkers_per_cta(self._h, int(wpc)), "qe_set_walkers_per_cta")
+
+    def set_walker_warps(self, warps: int):
+        """Warps per CTA of the fused walker kernel (0 = default 16 = one CTA per SM; 8 = two CTAs per SM; 4 = four)."""
+        _lib.check(self._lib.qe_set_walker_warps(self._h, int(warps)), "qe_set_walker_warps")
 
     # ---- LRDMC (GFMC_n) seams: jqmc/jqmc_gfmc.py:4716, 5656-5663 ------------------------------------
     _NLM = {"tmove": 0, "dltmove": 1}

@@ -404,6 +404,39 @@ def test_wide_lrdmc_projection_trajectory(case, nlm, E_scf, nmpm):
         np.testing.assert_allclose(Gi[i], oGi, rtol=1e-6, atol=1e-8 * np.abs(oGi).max())
 
 
+def test_wide_walker_slices_give_identical_results():
+    """BASELINE configs[4] sweeps to 64k walkers per GPU; the general family then runs a call as consecutive walker slices
+    through one workspace.  Slicing must not change anything: every entry, 70 walkers in slices of 32 vs one call, bit for bit."""
+    H, eng = _engine("water_jagp_j3mo")
+    nw = 70
+    r_up, r_dn = _walkers(H, nw, 47, scale=0.7)
+    keys = np.array([[0, 31 + 7 * i] for i in range(nw)], dtype=np.uint32)
+    RT = eng.generate_RTs(keys)
+
+    def run():
+        G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
+        e_L = eng.e_L_fast(r_up, r_dn, RT, Ginv)
+        ln = eng.ln_wavefunction(r_up, r_dn)
+        up = eng.update(r_up, r_dn, keys, 6, 2.0, 0.0, Ginv, G)
+        pr = eng.projection_n(np.ones(nw), r_up, r_dn, Ginv, keys, -17.0, 4, True, "tmove", 0.3)
+        ve = eng.V_elements_n(r_up, r_dn, RT, "tmove", 0.3)
+        out = []
+        for x in (G, Ginv, e_L, ln, *up, *pr, *ve):
+            out += [y.cpu().numpy() for y in (x if isinstance(x, (tuple, list)) else (x,))]
+        return out
+
+    try:
+        eng.set_wide_slice(0)
+        whole = run()
+        eng.set_wide_slice(32)
+        sliced = run()
+    finally:
+        eng.set_wide_slice(0)
+    assert len(whole) == len(sliced)
+    for a, b in zip(whole, sliced):
+        np.testing.assert_array_equal(a, b)
+
+
 @pytest.mark.parametrize("case,nlm,tau", [("water_jsd", "tmove", 0.04), ("li_ae", "tmove", 0.03), ("water_jagp", "dltmove", 0.03), ("water_jagp_j3mo", "tmove", 0.03)])
 def test_wide_lrdmc_projection_t_trajectory(case, nlm, tau):
     """(f).2 GFMC_t on the general path: the literal while_loop (every walker runs every iteration, walkers out of time do

@@ -2,7 +2,7 @@
 """Step times of the BASELINE configurations that run on the general kernel family (never the bench line; bench.py measures
 configs[1]):  water JAGP (configs[2]), benzene shape JSD+J1J2J3 (configs[3]), 100 e / 1000 AO JSD (configs[4]).
 
-    python tools/time_configs.py --out gpurun_out/configs.json [--cases water_jagp,benzene,S] [--walkers 4096]
+    python tools/time_configs.py --out gpurun_out/configs.json [--cases water_jagp,benzene,S] [--walkers 4096] [--s-walkers 1024]
 
 Per case: ms of one VMC step (nmpm Metropolis proposals + RT + e_L + AS factor) and one LRDMC step (inverse + nmpm projections
 + V elements), CUDA events on the launch stream after warm-up, plus the engine's per-kernel CUDA-event shares (qe_profile).
@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--walkers", type=int, default=4096)
     ap.add_argument("--nmpm", type=int, default=40)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--s-walkers", type=int, default=1024, help="walkers of the 100 e / 1000 AO case (configs[4] sweeps 1k..64k per GPU)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     import numpy as np
@@ -67,7 +68,7 @@ def main():
         if force:
             eng.set_path(True)
         gem = H.wavefunction_data.geminal_data
-        nw = args.walkers if case != "S" else min(args.walkers, 1024)
+        nw = args.walkers if case != "S" else args.s_walkers
         if len(H.structure_data.positions) > 3:
             r_up, r_dn = SY.init_walkers(H, nw, 1, sigma=0.8)
             keys = rng_host.split(rng_host.PRNGKey(5), nw)
