@@ -103,7 +103,7 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
   double* s_Gi = s_G + NN2 * 32;          // N*N
   double* s_phi = s_Gi + NN2 * 32;        // Ne*NMO   (orbital values at the electrons: [e][mo])
   double* s_part = s_phi + Ne * NMO * 32; // nch*NMO
-  double* s_TJ = s_part + nch * NMO * 32; // 2: T_ratio, J_ratio
+  double* s_TJ = s_part + nch * NMO * 32; // 1 + (nch+1): T_ratio, per-warp partial Jastrow exponent differences
 #define SR(e, c) s_r[((e) * 3 + (c)) * 32 + lane]
 #define SG(i, j) s_G[((i) * N + (j)) * 32 + lane]
 #define SGI(i, j) s_Gi[((i) * N + (j)) * 32 + lane]
@@ -195,6 +195,39 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
     else nz = oz + g;
 
     // ---- phase B ---------------------------------------------------------------------------------
+    // The J1/J2 terms of J(r') - J(r) (one per nucleus / per other electron) are dealt out over all warps, so that no
+    // single warp carries the whole pair loop (it used to bound this phase: profiles/r01_mcmc_v6.md)
+    struct PosS {
+      const double* s_r;
+      int lane;
+      __device__ __forceinline__ void get(int e, double& x, double& y, double& z) const {
+        x = s_r[(e * 3 + 0) * 32 + lane];
+        y = s_r[(e * 3 + 1) * 32 + lane];
+        z = s_r[(e * 3 + 2) * 32 + lane];
+      }
+    } pos{s_r, lane};
+    const int n_j1 = S.j1_type ? S.n_atom : 0, n_jt = n_j1 + (S.j2_type ? Ne : 0);
+    auto jastrow_terms = [&]() {
+      double dJ = 0.0;
+      for (int t = wid; t < n_jt; t += nch + 1) {
+        if (t < n_j1) {
+          const double X = S.Rn[3 * t], Y = S.Rn[3 * t + 1], Z = S.Rn[3 * t + 2];
+          const double dn_ = sqrt((nx - X) * (nx - X) + (ny - Y) * (ny - Y) + (nz - Z) * (nz - Z));
+          const double do_ = sqrt((ox - X) * (ox - X) + (oy - Y) * (oy - Y) + (oz - Z) * (oz - Z));
+          const double A = S.j1_A[t], c = S.j1_c[t];
+          dJ += j1_f(S.j1_type, S.j1_a, A, c, dn_) - j1_f(S.j1_type, S.j1_a, A, c, do_);
+        } else {
+          const int j = t - n_j1;
+          if (j == ke) continue;
+          double x, y, z;
+          pos.get(j, x, y, z);
+          const double dn_ = sqrt((nx - x) * (nx - x) + (ny - y) * (ny - y) + (nz - z) * (nz - z));
+          const double do_ = sqrt((ox - x) * (ox - x) + (oy - y) * (oy - y) + (oz - z) * (oz - z));
+          dJ += j2_f(S.j2_type, S.j2_a, dn_) - j2_f(S.j2_type, S.j2_a, do_);
+        }
+      }
+      s_TJ[(1 + wid) * 32 + lane] = dJ;
+    };
     if (wid < nch) {
       // same AO tables for both spins (checked at create); the MO coefficients may differ per lane
       SinkMO<NMO> sink;
@@ -202,6 +235,7 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
       eval_val<CART, QE_LMAX>(B.g, B, P.off_cseg, nx, ny, nz, cbeg[wid], cbeg[wid + 1], sink);
 #pragma unroll
       for (int mo = 0; mo < NMO; ++mo) SPART(wid, mo) = sink.acc[mo];
+      jastrow_terms();
     } else {
       ia = nearest_atom(S.Rn, S.n_atom, nx, ny, nz, 0, &dist);
       Zc = S.Zeff[ia];
@@ -209,18 +243,8 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
       const double dd = (nx - ox) * (nx - ox) + (ny - oy) * (ny - oy) + (nz - oz) * (nz - oz);
       const double T_ratio =
           (f_l / f_p) * qexp(-dd * (1.0 / (2.0 * f_p * f_p * P.Dt * P.Dt) - 1.0 / (2.0 * f_l * f_l * P.Dt * P.Dt)));
-      struct PosS {
-        const double* s_r;
-        int lane;
-        __device__ __forceinline__ void get(int e, double& x, double& y, double& z) const {
-          x = s_r[(e * 3 + 0) * 32 + lane];
-          y = s_r[(e * 3 + 1) * 32 + lane];
-          z = s_r[(e * 3 + 2) * 32 + lane];
-        }
-      } pos{s_r, lane};
-      const double J_ratio = qexp(jastrow_delta(S, pos, ke, ox, oy, oz, nx, ny, nz));
       s_TJ[lane] = T_ratio;
-      s_TJ[32 + lane] = J_ratio;
+      jastrow_terms();
     }
     __syncthreads();
 
@@ -233,8 +257,11 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
         for (int c = 0; c < nch; ++c) s += SPART(c, mo);
         phi[mo] = s;
       }
-      // v (row difference) or u (column difference), Det_ratio = 1 + v^T Ginv u
-      double dvec[8 > NMO ? 8 : NMO];  // N <= 8 enforced on the host for this kernel
+      // v (row difference) or u (column difference), Det_ratio = 1 + v^T Ginv u.  All loops over electrons run to the
+      // compile-time bound NB >= N with a uniform predicate, so that dvec / col / vt stay in registers (runtime bounds put them
+      // in local memory and made this single-warp section 40 % of the kernel, profiles/r01_mcmc_v5.md)
+      constexpr int NB = NMO < 8 ? NMO : 8;  // N <= 8 (host check) and N <= n_mo <= NMO
+      double dvec[NB];
       double Det;
       if (up) {
         const int k = ke;
@@ -247,19 +274,23 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
           t[b] = s;
         }
         double acc = 0;
-        for (int j = 0; j < Nd; ++j) {
-          double s = 0;
 #pragma unroll
-          for (int b = 0; b < NMO; ++b) s = fma(t[b], SPHI(N + j, b), s);
-          dvec[j] = s - SG(k, j);
-          acc = fma(dvec[j], SGI(j, k), acc);
-        }
-        for (int q = 0; q < S.n_unp; ++q) {
+        for (int j = 0; j < NB; ++j) {
           double s = 0;
+          if (j < Nd) {
 #pragma unroll
-          for (int a = 0; a < NMO; ++a) s = fma(phi[a], S.lam_u[a * S.n_unp + q], s);
-          dvec[Nd + q] = s - SG(k, Nd + q);
-          acc = fma(dvec[Nd + q], SGI(Nd + q, k), acc);
+            for (int b = 0; b < NMO; ++b) s = fma(t[b], SPHI(N + j, b), s);
+          } else if (j < N) {
+            const int q = j - Nd;
+#pragma unroll
+            for (int a = 0; a < NMO; ++a) s = fma(phi[a], S.lam_u[a * S.n_unp + q], s);
+          }
+          if (j < N) {
+            dvec[j] = s - SG(k, j);
+            acc = fma(dvec[j], SGI(j, k), acc);
+          } else {
+            dvec[j] = 0.0;
+          }
         }
         Det = 1.0 + acc;
       } else {
@@ -273,26 +304,38 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
           t[a] = s;
         }
         double acc = 0;
-        for (int i = 0; i < N; ++i) {
-          double s = 0;
 #pragma unroll
-          for (int a = 0; a < NMO; ++a) s = fma(SPHI(i, a), t[a], s);
-          dvec[i] = s - SG(i, k);
-          acc = fma(SGI(k, i), dvec[i], acc);
+        for (int i = 0; i < NB; ++i) {
+          if (i < N) {
+            double s = 0;
+#pragma unroll
+            for (int a = 0; a < NMO; ++a) s = fma(SPHI(i, a), t[a], s);
+            dvec[i] = s - SG(i, k);
+            acc = fma(SGI(k, i), dvec[i], acc);
+          } else {
+            dvec[i] = 0.0;
+          }
         }
         Det = 1.0 + acc;
       }
-      const double T_ratio = s_TJ[lane], J_ratio = s_TJ[32 + lane];
+      const double T_ratio = s_TJ[lane];
+      double dJ = 0.0;
+      for (int c = 0; c <= nch; ++c) dJ += s_TJ[(1 + c) * 32 + lane];  // fixed order
+      const double J_ratio = qexp(dJ);
       // AS regularisation of the proposed state without materialising it
       double R_AS_ratio = 1.0, R_AS_p = R_AS_cur;
       if (P.eps_AS > 0.0) {
         double F = 0, Smin = 1e300;
+        double* s_dv = s_part;  // the partial sums have been consumed: scratch for the dynamically indexed copy of dvec
+#pragma unroll
+        for (int j = 0; j < NB; ++j) s_dv[j * 32 + lane] = dvec[j];
+#define DV(j) s_dv[(j) * 32 + lane]
         if (up) {
           const int k = ke;
           // Ginv' = Ginv - Ginv[:,k] (v^T Ginv) / Det
           for (int jp = 0; jp < N; ++jp) {
             double vt = 0;
-            for (int j = 0; j < N; ++j) vt = fma(dvec[j], SGI(j, jp), vt);
+            for (int j = 0; j < N; ++j) vt = fma(DV(j), SGI(j, jp), vt);
             vt /= Det;
             for (int i = 0; i < N; ++i) {
               const double x = SGI(i, jp) - SGI(i, k) * vt;
@@ -302,8 +345,8 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
           for (int i = 0; i < N; ++i) {
             double r = 0, c = 0;
             for (int j = 0; j < N; ++j) {
-              const double gij = SG(i, j) + (i == k ? dvec[j] : 0.0);
-              const double gji = SG(j, i) + (j == k ? dvec[i] : 0.0);
+              const double gij = SG(i, j) + (i == k ? DV(j) : 0.0);
+              const double gji = SG(j, i) + (j == k ? DV(i) : 0.0);
               r = fma(gij, gij, r);
               c = fma(gji, gji, c);
             }
@@ -314,7 +357,7 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
           // Ginv' = Ginv - (Ginv u) Ginv[k,:] / Det
           for (int i = 0; i < N; ++i) {
             double au = 0;
-            for (int j = 0; j < N; ++j) au = fma(SGI(i, j), dvec[j], au);
+            for (int j = 0; j < N; ++j) au = fma(SGI(i, j), DV(j), au);
             au /= Det;
             for (int j = 0; j < N; ++j) {
               const double x = SGI(i, j) - au * SGI(k, j);
@@ -324,14 +367,15 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
           for (int i = 0; i < N; ++i) {
             double r = 0, c = 0;
             for (int j = 0; j < N; ++j) {
-              const double gij = SG(i, j) + (j == k ? dvec[i] : 0.0);
-              const double gji = SG(j, i) + (i == k ? dvec[j] : 0.0);
+              const double gij = SG(i, j) + (j == k ? DV(i) : 0.0);
+              const double gji = SG(j, i) + (i == k ? DV(j) : 0.0);
               r = fma(gij, gij, r);
               c = fma(gji, gji, c);
             }
             Smin = fmin(Smin, fmin(r, c));
           }
         }
+#undef DV
         const double SF = Smin * F;
         R_AS_p = SF > 0.0 ? pow(SF, -0.375) : 0.0;
         R_AS_ratio = (fmax(R_AS_p, P.eps_AS) / R_AS_p) / (fmax(R_AS_cur, P.eps_AS) / R_AS_cur);
@@ -351,28 +395,50 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
         const double invD = 1.0 / Det;
         if (up) {
           const int k = ke;
-          double col[8], vt[8];
-          for (int i = 0; i < N; ++i) col[i] = SGI(i, k);
-          for (int jp = 0; jp < N; ++jp) {
+          double col[NB], vt[NB];
+#pragma unroll
+          for (int i = 0; i < NB; ++i) col[i] = i < N ? SGI(i, k) : 0.0;
+#pragma unroll
+          for (int jp = 0; jp < NB; ++jp) {
             double s = 0;
-            for (int j = 0; j < N; ++j) s = fma(dvec[j], SGI(j, jp), s);
+            if (jp < N) {
+#pragma unroll
+              for (int j = 0; j < NB; ++j)
+                if (j < N) s = fma(dvec[j], SGI(j, jp), s);
+            }
             vt[jp] = s;
           }
-          for (int i = 0; i < N; ++i)
-            for (int jp = 0; jp < N; ++jp) SGI(i, jp) = SGI(i, jp) - (col[i] * vt[jp]) * invD;
-          for (int j = 0; j < N; ++j) SG(k, j) += dvec[j];
+#pragma unroll
+          for (int i = 0; i < NB; ++i)
+#pragma unroll
+            for (int jp = 0; jp < NB; ++jp)
+              if (i < N && jp < N) SGI(i, jp) = SGI(i, jp) - (col[i] * vt[jp]) * invD;
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+            if (j < N) SG(k, j) += dvec[j];
         } else {
           const int k = ke - N;
-          double au[8], row[8];
-          for (int i = 0; i < N; ++i) {
+          double au[NB], row[NB];
+#pragma unroll
+          for (int i = 0; i < NB; ++i) {
             double s = 0;
-            for (int j = 0; j < N; ++j) s = fma(SGI(i, j), dvec[j], s);
+            if (i < N) {
+#pragma unroll
+              for (int j = 0; j < NB; ++j)
+                if (j < N) s = fma(SGI(i, j), dvec[j], s);
+            }
             au[i] = s;
           }
-          for (int j = 0; j < N; ++j) row[j] = SGI(k, j);
-          for (int i = 0; i < N; ++i)
-            for (int j = 0; j < N; ++j) SGI(i, j) = SGI(i, j) - (au[i] * row[j]) * invD;
-          for (int i = 0; i < N; ++i) SG(i, k) += dvec[i];
+#pragma unroll
+          for (int j = 0; j < NB; ++j) row[j] = j < N ? SGI(k, j) : 0.0;
+#pragma unroll
+          for (int i = 0; i < NB; ++i)
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+              if (i < N && j < N) SGI(i, j) = SGI(i, j) - (au[i] * row[j]) * invD;
+#pragma unroll
+          for (int i = 0; i < NB; ++i)
+            if (i < N) SG(i, k) += dvec[i];
         }
       } else {
         ++n_rej;
@@ -449,6 +515,7 @@ extern "C" int qe_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, 
   if (use_wide(h)) return wide_mcmc_update(h, nw, r_up, r_dn, keys, G, Ginv, nmpm, Dt, epsilon_AS, acc, rej, (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
   const int P = h->nmo_pad, nch = h->b_up.n_chunk;
+  if (S.n_up > std::min(P, 8)) return fail(QE_ERR_UNSUPPORTED, "qe_mcmc_update: register kernel needs n_up <= min(n_mo, 8)");
   int rc = ensure_ws(h, mcmc_draws_bytes(nw, nmpm) + 4096);
   if (rc) return rc;
   WsCarve c{(char*)h->ws};
@@ -457,7 +524,7 @@ extern "C" int qe_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, 
   rc = mcmc_draws(h, nw, nmpm, keys, c, &rsel, &raxis, &rg, &rb, st);
   if (rc) return rc;
   McmcArgs A{nw, nmpm, nch, Dt, epsilon_AS, r_up, r_dn, G, Ginv, acc, rej, rsel, raxis, rg, rb, h->b_up.off_cseg, h->b_up.off_cbeg};
-  const size_t smem = (size_t)(S.n_e * 3 + 2 * S.n_up * S.n_up + S.n_e * P + nch * P + 2) * 32 * 8;
+  const size_t smem = (size_t)(S.n_e * 3 + 2 * S.n_up * S.n_up + S.n_e * P + nch * P + 2 + nch) * 32 * 8;
   dim3 block(32, nch + 1);
   { LaunchScope ls_(h, K_MCMC, st);
 #define CALL(NMO, CART)                                                                                           \
