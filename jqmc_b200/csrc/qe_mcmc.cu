@@ -104,6 +104,7 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
   double* s_phi = s_Gi + NN2 * 32;        // Ne*NMO   (orbital values at the electrons: [e][mo])
   double* s_part = s_phi + Ne * NMO * 32; // nch*NMO
   double* s_TJ = s_part + nch * NMO * 32; // 1 + (nch+1): T_ratio, per-warp partial Jastrow exponent differences
+  double* s_fl = s_TJ + (nch + 2) * 32;   // Ne + 1: proposal width factor f of every electron at its current position, f'
 #define SR(e, c) s_r[((e) * 3 + (c)) * 32 + lane]
 #define SG(i, j) s_G[((i) * N + (j)) * 32 + lane]
 #define SGI(i, j) s_Gi[((i) * N + (j)) * 32 + lane]
@@ -123,6 +124,14 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
   (void)tid;
   (void)nthr;
   __syncthreads();
+  // f = (1 + Z^2 d) / (Z^2 (1 + d)) with the nearest nucleus (jqmc/jqmc_mcmc.py:4340-4357) for every electron; an accepted
+  // move replaces the electron's entry by the f' of the proposal, which is the same function of the same position
+  for (int e = wid; e < Ne; e += nch + 1) {
+    double dist;
+    const int ia = nearest_atom(S.Rn, S.n_atom, SR(e, 0), SR(e, 1), SR(e, 2), 0, &dist);
+    const double Zc = S.Zeff[ia];
+    s_fl[e * 32 + lane] = 1.0 / (Zc * Zc) * (1.0 + Zc * Zc * dist) / (1.0 + dist);
+  }
 
   // ---- orbital values at every electron (cache for the row/column rebuild) -----------------------
   for (int e = 0; e < Ne; ++e) {
@@ -184,10 +193,7 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
     }
     const bool up = ke < N;
     const double ox = SR(ke, 0), oy = SR(ke, 1), oz = SR(ke, 2);
-    double dist;
-    int ia = nearest_atom(S.Rn, S.n_atom, ox, oy, oz, 0, &dist);
-    double Zc = S.Zeff[ia];
-    const double f_l = 1.0 / (Zc * Zc) * (1.0 + Zc * Zc * dist) / (1.0 + dist);
+    const double f_l = s_fl[ke * 32 + lane];
     const double g = rg_c * (f_l * P.Dt);
     double nx = ox, ny = oy, nz = oz;
     if (axis == 0) nx = ox + g;
@@ -237,13 +243,15 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
       for (int mo = 0; mo < NMO; ++mo) SPART(wid, mo) = sink.acc[mo];
       jastrow_terms();
     } else {
-      ia = nearest_atom(S.Rn, S.n_atom, nx, ny, nz, 0, &dist);
-      Zc = S.Zeff[ia];
+      double dist;
+      const int ia = nearest_atom(S.Rn, S.n_atom, nx, ny, nz, 0, &dist);
+      const double Zc = S.Zeff[ia];
       const double f_p = 1.0 / (Zc * Zc) * (1.0 + Zc * Zc * dist) / (1.0 + dist);
       const double dd = (nx - ox) * (nx - ox) + (ny - oy) * (ny - oy) + (nz - oz) * (nz - oz);
       const double T_ratio =
           (f_l / f_p) * qexp(-dd * (1.0 / (2.0 * f_p * f_p * P.Dt * P.Dt) - 1.0 / (2.0 * f_l * f_l * P.Dt * P.Dt)));
       s_TJ[lane] = T_ratio;
+      s_fl[Ne * 32 + lane] = f_p;
       jastrow_terms();
     }
     __syncthreads();
@@ -390,6 +398,7 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
         SR(ke, 0) = nx;
         SR(ke, 1) = ny;
         SR(ke, 2) = nz;
+        s_fl[ke * 32 + lane] = s_fl[Ne * 32 + lane];
 #pragma unroll
         for (int mo = 0; mo < NMO; ++mo) SPHI(ke, mo) = phi[mo];
         const double invD = 1.0 / Det;
@@ -524,7 +533,7 @@ extern "C" int qe_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, 
   rc = mcmc_draws(h, nw, nmpm, keys, c, &rsel, &raxis, &rg, &rb, st);
   if (rc) return rc;
   McmcArgs A{nw, nmpm, nch, Dt, epsilon_AS, r_up, r_dn, G, Ginv, acc, rej, rsel, raxis, rg, rb, h->b_up.off_cseg, h->b_up.off_cbeg};
-  const size_t smem = (size_t)(S.n_e * 3 + 2 * S.n_up * S.n_up + S.n_e * P + nch * P + 2 + nch) * 32 * 8;
+  const size_t smem = (size_t)(S.n_e * 3 + 2 * S.n_up * S.n_up + S.n_e * P + nch * P + 2 + nch + S.n_e + 1) * 32 * 8;
   dim3 block(32, nch + 1);
   { LaunchScope ls_(h, K_MCMC, st);
 #define CALL(NMO, CART)                                                                                           \
