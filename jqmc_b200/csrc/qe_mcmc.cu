@@ -89,14 +89,23 @@ struct McmcArgs {
 template <int NMO, bool CART>
 __global__ void __launch_bounds__(512)
 k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm_all[];
   const int lane = threadIdx.x, wid = threadIdx.y;
+  // basis image (shells, primitives, MO coefficients) staged in shared memory: every table read of the AO phase is a
+  // warp-broadcast LDS instead of an L1-cached global load on the dependent chain shell -> primitives -> coefficients
+  const char* tab = (const char*)sm_all;
+  {
+    const int4* src = (const int4*)B.g;
+    int4* dst = (int4*)sm_all;
+    for (int i = wid * 32 + lane; i < B.bytes / 16; i += 32 * (P.n_chunk + 1)) dst[i] = src[i];
+  }
+  double* sm = sm_all + B.bytes / 8;
   const int w = blockIdx.x * 32 + lane;
   const bool live = w < P.nw;
   const int ww = live ? w : P.nw - 1;  // dead lanes shadow the last walker (no stores)
   const int N = S.n_up, Nd = S.n_dn, Ne = S.n_e, NN2 = N * N;
   const int nch = P.n_chunk;
-  const int* cbeg = (const int*)(B.g + P.off_cbeg);
+  const int* cbeg = (const int*)(tab + P.off_cbeg);
   // shared-memory carve-up (all [item][32])
   double* s_r = sm;                       // Ne*3
   double* s_G = s_r + Ne * 3 * 32;        // N*N
@@ -137,8 +146,8 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
   for (int e = 0; e < Ne; ++e) {
     if (wid < nch) {
       SinkMO<NMO> sink;
-      sink.init(B.g + (e < N ? B.off_C : B.off_C2));
-      eval_val<CART, QE_LMAX>(B.g, B, P.off_cseg, SR(e, 0), SR(e, 1), SR(e, 2), cbeg[wid], cbeg[wid + 1], sink);
+      sink.init(tab + (e < N ? B.off_C : B.off_C2));
+      eval_val<CART, QE_LMAX>(tab, B, P.off_cseg, SR(e, 0), SR(e, 1), SR(e, 2), cbeg[wid], cbeg[wid + 1], sink);
 #pragma unroll
       for (int mo = 0; mo < NMO; ++mo) SPART(wid, mo) = sink.acc[mo];
     }
@@ -237,8 +246,8 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
     if (wid < nch) {
       // same AO tables for both spins (checked at create); the MO coefficients may differ per lane
       SinkMO<NMO> sink;
-      sink.init(B.g + (up ? B.off_C : B.off_C2));
-      eval_val<CART, QE_LMAX>(B.g, B, P.off_cseg, nx, ny, nz, cbeg[wid], cbeg[wid + 1], sink);
+      sink.init(tab + (up ? B.off_C : B.off_C2));
+      eval_val<CART, QE_LMAX>(tab, B, P.off_cseg, nx, ny, nz, cbeg[wid], cbeg[wid + 1], sink);
 #pragma unroll
       for (int mo = 0; mo < NMO; ++mo) SPART(wid, mo) = sink.acc[mo];
       jastrow_terms();
@@ -258,12 +267,40 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
 
     // ---- phase C: warp 0 -------------------------------------------------------------------------
     if (wid == 0) {
+      // sums over the warps' partials: three interleaved accumulators per quantity (fixed order, short dependent chains --
+      // this warp works alone here, so every exposed latency is on the critical path of the proposal)
       double phi[NMO];
+      {
+        double a0[NMO], a1[NMO], a2[NMO];
 #pragma unroll
-      for (int mo = 0; mo < NMO; ++mo) {
-        double s = 0;
-        for (int c = 0; c < nch; ++c) s += SPART(c, mo);
-        phi[mo] = s;
+        for (int mo = 0; mo < NMO; ++mo) a0[mo] = a1[mo] = a2[mo] = 0.0;
+        int c = 0;
+        for (; c + 2 < nch; c += 3) {
+#pragma unroll
+          for (int mo = 0; mo < NMO; ++mo) {
+            a0[mo] += SPART(c, mo);
+            a1[mo] += SPART(c + 1, mo);
+            a2[mo] += SPART(c + 2, mo);
+          }
+        }
+        for (; c < nch; ++c) {
+#pragma unroll
+          for (int mo = 0; mo < NMO; ++mo) a0[mo] += SPART(c, mo);
+        }
+#pragma unroll
+        for (int mo = 0; mo < NMO; ++mo) phi[mo] = (a0[mo] + a1[mo]) + a2[mo];
+      }
+      double dJ;
+      {
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+        int c = 0;
+        for (; c + 2 <= nch; c += 3) {
+          d0 += s_TJ[(1 + c) * 32 + lane];
+          d1 += s_TJ[(2 + c) * 32 + lane];
+          d2 += s_TJ[(3 + c) * 32 + lane];
+        }
+        for (; c <= nch; ++c) d0 += s_TJ[(1 + c) * 32 + lane];
+        dJ = (d0 + d1) + d2;
       }
       // v (row difference) or u (column difference), Det_ratio = 1 + v^T Ginv u.  All loops over electrons run to the
       // compile-time bound NB >= N with a uniform predicate, so that dvec / col / vt stay in registers (runtime bounds put them
@@ -327,8 +364,6 @@ k_mcmc(BasisDev B, SysDev S, McmcArgs P) {
         Det = 1.0 + acc;
       }
       const double T_ratio = s_TJ[lane];
-      double dJ = 0.0;
-      for (int c = 0; c <= nch; ++c) dJ += s_TJ[(1 + c) * 32 + lane];  // fixed order
       const double J_ratio = qexp(dJ);
       // AS regularisation of the proposed state without materialising it
       double R_AS_ratio = 1.0, R_AS_p = R_AS_cur;
@@ -533,7 +568,8 @@ extern "C" int qe_mcmc_update(qe_engine* h, int nw, double* r_up, double* r_dn, 
   rc = mcmc_draws(h, nw, nmpm, keys, c, &rsel, &raxis, &rg, &rb, st);
   if (rc) return rc;
   McmcArgs A{nw, nmpm, nch, Dt, epsilon_AS, r_up, r_dn, G, Ginv, acc, rej, rsel, raxis, rg, rb, h->b_up.off_cseg, h->b_up.off_cbeg};
-  const size_t smem = (size_t)(S.n_e * 3 + 2 * S.n_up * S.n_up + S.n_e * P + nch * P + 2 + nch + S.n_e + 1) * 32 * 8;
+  const size_t smem = (size_t)(S.n_e * 3 + 2 * S.n_up * S.n_up + S.n_e * P + nch * P + 2 + nch + S.n_e + 1) * 32 * 8 + (size_t)h->b_up.dev.bytes;
+  if (smem > 227 * 1024) return fail(QE_ERR_UNSUPPORTED, "qe_mcmc_update: basis image does not fit in shared memory");
   dim3 block(32, nch + 1);
   { LaunchScope ls_(h, K_MCMC, st);
 #define CALL(NMO, CART)                                                                                           \
