@@ -32,12 +32,6 @@ extern "C" int qe_lrdmc_project(qe_engine* h, int nw, double* w, double* r_up, d
   if (use_wide(h))
     return wide_lrdmc(h, 0, nw, w, r_up, r_dn, Ginv, keys, E_scf, nmpm, random_discretized_mesh, non_local_move, alat, nullptr, RT,
                       V_diag, V_nondiag, st);
-  int rc = ensure_ws(h, lrdmc_draws_bytes(nw, nmpm) + 4096);
-  if (rc) return rc;
-  WsCarve c{(char*)h->ws};
-  double *rRT, *ru;
-  rc = lrdmc_draws(h, nw, nmpm, random_discretized_mesh, keys, c, &rRT, &ru, st);
-  if (rc) return rc;
   WalkerArgs A{};
   A.nw = nw;
   A.nmpm = nmpm;
@@ -52,8 +46,8 @@ extern "C" int qe_lrdmc_project(qe_engine* h, int nw, double* w, double* r_up, d
   A.RT_out = RT;
   A.V_diag = V_diag;
   A.V_nondiag = V_nondiag;
-  A.rRT = rRT;
-  A.ru = ru;
+  A.keys = keys;
+  A.random_mesh = random_discretized_mesh;
   return launch_walker<false>(h, A, st, K_LRDMC_PROJ);
 }
 

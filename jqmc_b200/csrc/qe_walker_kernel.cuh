@@ -36,8 +36,6 @@ struct WalkerArgs {
   double* e_L;
   double* T_elem;
   double* V_parts;
-  const double* rRT;  // mode 0 draws: [(it*9+c)][nw]
-  const double* ru;   //               [it][nw]
   int off_cseg, off_cbeg, n_chunk;
   // continuous-time projection (GFMC_t, template TAU): the draws are made in the kernel because the number of
   // projections is not known in advance
@@ -159,11 +157,13 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
   double* s_p = cv.take<double>((size_t)(NPT > 0 ? NPT : 1) * WPC);
   double* s_j = cv.take<double>((size_t)(n_ecp > 0 ? n_ecp : 1) * WPC);
   double* s_el = cv.take<double>((size_t)Ne * 8 * WPC);  // [e*8 + {ke|opt, ei, eid, loc, ee, kinFN, kinSP, -}]
+  double* s_e2 = cv.take<double>((size_t)Ne * 2 * WPC);  // [e*2 + {sum of the fixed-node ECP elements of electron e, of their positive parts}]
   double* s_part = cv.take<double>((size_t)NWARP * 5 * NMO * WPC);
   double* s_stage = cv.take<double>((size_t)5 * NMO * WPC);
   double* s_misc = cv.take<double>((size_t)16 * WPC);  // 0..8 RT, 9..11 new position, 12 selected electron, 13 total
   int* s_ctr = cv.take<int>(4);
   int* s_act = cv.take<int>((size_t)WPC);  // GFMC_t: compact list of the walkers that still have time left
+  uint32_t* s_key = cv.take<uint32_t>((size_t)2 * WPC);  // GFMC_n: running PRNG keys (the draws are made in the kernel)
 #define SR(e, c) s_r[((e) * 3 + (c)) * WPC + wl]
 #define SGI(i, j) s_Gi[((i) * N + (j)) * WPC + wl]
 #define SPHI(e, q, mo) s_phi[(((e) * 5 + (q)) * NMO + (mo)) * WPC + wl]
@@ -187,6 +187,11 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       s_misc[idx] = P.RT_in ? P.RT_in[(size_t)GW(wl) * 9 + c] : (c % 4 == 0 ? 1.0 : 0.0);
     }
   if (tid == 0) s_ctr[0] = 0;
+  if (!TAU && P.mode == 0)
+    for (int wl = tid; wl < WPC; wl += nthr) {
+      s_key[2 * wl] = P.keys[2 * GW(wl)];
+      s_key[2 * wl + 1] = P.keys[2 * GW(wl) + 1];
+    }
   if constexpr (TAU)
     for (int wl = tid; wl < WPC; wl += nthr) {
       s_act[wl] = wl;
@@ -277,13 +282,44 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
         rng_split(key, sub);
         u_move = rng_uniform_bits(rng_bits64(sub), 0.0, 1.0);
       }
-    } else if (P.mode == 0)
-      for (int idx = tid; idx < 9 * WPC; idx += nthr) {
-        const int wl = idx % WPC, c = idx / WPC;
-        s_misc[idx] = P.rRT[((size_t)it * 9 + c) * P.nw + GW(wl)];
+    } else if (P.mode == 0) {
+      // GFMC_n: two splits per projection, rotation angles and move draw (_split_step_keys, jqmc/jqmc_gfmc.py:5275-5283),
+      // made by the first WPC threads while warps 1.. work on P1 (no draw tables in HBM: the launch moves walker state only)
+      if (tid < WPC) {
+        const int wl = tid;
+        Key key{s_key[2 * wl], s_key[2 * wl + 1]}, sub;
+        rng_split(key, sub);
+        double al = 0, be = 0, ga = 0;
+        if (P.random_mesh) {
+          const double two_pi = 6.283185307179586;
+          al = rng_uniform_bits(rng_bits64(sub, 0u), -two_pi, two_pi);
+          be = rng_uniform_bits(rng_bits64(sub, 1u), -two_pi, two_pi);
+          ga = rng_uniform_bits(rng_bits64(sub, 2u), -two_pi, two_pi);
+        }
+        double RTl[9];
+        rt_from_angles(al, be, ga, RTl);
+#pragma unroll
+        for (int c = 0; c < 9; ++c) SMISC(c) = RTl[c];
+        rng_split(key, sub);
+        SMISC(15) = rng_uniform_bits(rng_bits64(sub), 0.0, 1.0);
+        s_key[2 * wl] = key.a;
+        s_key[2 * wl + 1] = key.b;
       }
-    for (int s = tid; s < Ne * NACT; s += nthr) {
+    }
+    // (in the projection modes the tasks start at warp 1: the first warp is busy with the draws)
+    const int p1_off = (P.mode == 0 && nthr > 32) ? 32 : 0;
+    // two task kinds per (walker, electron): the ratio weight vector, and the Jastrow terms at the current position
+    for (int s0 = tid - p1_off; s0 < 2 * Ne * NACT; s0 += nthr - p1_off) {
+      if (s0 < 0) continue;
+      const bool jtask = s0 >= Ne * NACT;
+      const int s = jtask ? s0 - Ne * NACT : s0;
       const int wl = WLOF(s % NACT), e = s / NACT;
+      if (jtask) {
+        // Jastrow terms of electron e at its current position (shared by all of its mesh points)
+        PosShared pos{s_r, WPC, wl};
+        SEL(e, 7) = jastrow_single(S, pos, e, SR(e, 0), SR(e, 1), SR(e, 2));
+        continue;
+      }
       double Wv[NMO];
       if (e < N) {
         double y[NMO];
@@ -320,9 +356,6 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       }
 #pragma unroll
       for (int mo = 0; mo < NMO; ++mo) SW(e, mo) = Wv[mo];
-      // Jastrow terms of electron e at its current position (shared by all of its mesh points)
-      PosShared pos{s_r, WPC, wl};
-      SEL(e, 7) = jastrow_single(S, pos, e, SR(e, 0), SR(e, 1), SR(e, 2));
     }
     __syncthreads();
 
@@ -534,14 +567,27 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       SEL(e, 5) = kinFN;
       SEL(e, 6) = kinSP;
     }
-    // (a') per (walker, ECP point): fixed-node split of the non-local elements (s_j: Jastrow ratio -> positive part)
-    for (int c = tid; c < n_ecp * NACT; c += nthr) {
-      const int s = TAU ? (c / NACT) * WPC + WLOF(c % NACT) : c;
-      const double v = s_p[n_kin * WPC + s];
-      double fn = fmin(v, 0.0);
-      if (P.dlt) fn *= s_j[s];
-      s_p[n_kin * WPC + s] = fn;
-      s_j[s] = fmax(v, 0.0);
+    // (a') per (walker, electron): fixed-node split of its NN*Nv non-local elements (s_j: Jastrow ratio -> positive part) and
+    //      their sums.  The 6 kinetic and the NN*Nv ECP elements of an electron are contiguous in the move vector
+    //      [kinetic mesh, ECP mesh], so these per-electron sums are also the chunk sums of the move selection below
+    if (n_ecp > 0) {
+      const int per = S.NN * S.Nv;
+      for (int c = tid; c < Ne * NACT; c += nthr) {
+        const int wl = WLOF(c % NACT), e = c / NACT;
+        double sFN = 0, sSP = 0;
+        for (int k = e * per; k < (e + 1) * per; ++k) {
+          const double v = s_p[(n_kin + k) * WPC + wl];
+          double fn = fmin(v, 0.0);
+          if (P.dlt) fn *= s_j[k * WPC + wl];
+          const double sp = fmax(v, 0.0);
+          s_p[(n_kin + k) * WPC + wl] = fn;
+          s_j[k * WPC + wl] = sp;
+          sFN += fn;
+          sSP += sp;
+        }
+        s_e2[(e * 2 + 0) * WPC + wl] = sFN;
+        s_e2[(e * 2 + 1) * WPC + wl] = sSP;
+      }
     }
     __syncthreads();
     // (b) per walker: sums, weight, normalisation of the move probabilities
@@ -558,10 +604,11 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       }
       const double disc_bare = ee + S.v_ion_ion + sum_opt;
       double sum_eFN = 0, SP_e = 0;
-      for (int k = 0; k < n_ecp; ++k) {
-        sum_eFN += s_p[(n_kin + k) * WPC + wl];
-        SP_e += s_j[k * WPC + wl];
-      }
+      if (n_ecp > 0)
+        for (int e = 0; e < Ne; ++e) {
+          sum_eFN += s_e2[(e * 2 + 0) * WPC + wl];
+          SP_e += s_e2[(e * 2 + 1) * WPC + wl];
+        }
       nondiag = sum_kinFN + sum_eFN;
       diag = S.ecp_flag ? diag_kin + disc_bare + loc + SP_kin + SP_e : diag_kin + disc_bare + SP_kin;
       if constexpr (TAU) {
@@ -573,15 +620,11 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
         w_L *= qexp(-tau_update * e_L);
         tau_left -= tau_update;
         SMISC(14) = tau_left <= 0.0 ? 0.0 : 1.0;
-        double tot = 0;
-        for (int k = 0; k < NPT; ++k) tot += s_p[k * WPC + wl];
-        SMISC(13) = tot;
+        SMISC(13) = nondiag;  // sum of all fixed-node elements = normalisation of the move probabilities
       } else if (P.mode == 0) {
         const double b_x = 1.0 / (diag - P.E_scf) * (-nondiag);
         w_L *= b_x;
-        double tot = 0;
-        for (int k = 0; k < NPT; ++k) tot += s_p[k * WPC + wl];  // sequential fp64 sum in the reference's vector order
-        SMISC(13) = tot;
+        SMISC(13) = nondiag;
       }
     }
     if constexpr (TAU) {
@@ -592,21 +635,25 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       if (P.mode != 0) break;
       __syncthreads();
     }
-    // (c) all threads: p / total
-    for (int c = tid; c < NPT * NACT; c += nthr) {
-      const int wl = WLOF(c % NACT), s = TAU ? (c / NACT) * WPC + wl : c;
-      s_p[s] = s_p[s] / s_misc[13 * WPC + wl];
-    }
-    __syncthreads();
-    // (d) per walker: sequential cumulative sum, first c >= u (searchsorted 'left', jqmc/jqmc_gfmc.py:5057-5062)
+    // (d) per walker: first index whose cumulative probability reaches u (searchsorted 'left' on cumsum(p / sum p),
+    //     jqmc/jqmc_gfmc.py:5057-5062): skip whole electrons by their chunk sums, then scan element by element; the scan
+    //     runs on past the chunk if round-off moved the crossing
     if (tid < WPC && (!TAU || s_misc[14 * WPC + tid] != 0.0)) {
       const int wl = tid;
       PosShared pos{s_r, WPC, wl};
-      const double u = TAU ? u_move : P.ru[(size_t)it * P.nw + GW(wl)];
-      int ksel = NPT - 1;
+      const double u = TAU ? u_move : SMISC(15);
+      const double tot = SMISC(13);
+      const int per = S.ecp_flag ? S.NN * S.Nv : 0, n_ch = n_ecp > 0 ? 2 * Ne : Ne;
+      int ksel = NPT - 1, kstart = 0;
       double c = 0;
-      for (int k = 0; k < NPT; ++k) {
-        c += s_p[k * WPC + wl];
+      for (int ci = 0; ci < n_ch; ++ci) {
+        const double cs = (ci < Ne ? SEL(ci, 5) : s_e2[((ci - Ne) * 2) * WPC + wl]) / tot;
+        if (c + cs >= u) break;
+        c += cs;
+        kstart = ci + 1 < Ne ? 6 * (ci + 1) : n_kin + (ci + 1 - Ne) * per;
+      }
+      for (int k = kstart; k < NPT; ++k) {
+        c += s_p[k * WPC + wl] / tot;
         if (c >= u) {
           ksel = k;
           break;
@@ -779,6 +826,8 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
     if (P.mode == 0) {
       P.w[w] = w_L;
       for (int c = 0; c < 9; ++c) P.RT_out[(size_t)w * 9 + c] = SMISC(c);
+      P.keys[2 * w] = s_key[2 * wl];
+      P.keys[2 * w + 1] = s_key[2 * wl + 1];
     }
   }
   if (P.mode == 0) {
@@ -882,8 +931,8 @@ int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
   const int n_kin = A.mode == 2 ? 0 : 6 * Ne;
   const int n_ecp = S.ecp_flag ? Ne * S.NN * S.Nv : 0;
   const size_t per_walker = (size_t)Ne * 3 + (size_t)S.n_up * S.n_up + (size_t)Ne * 5 * P + (size_t)Ne * P + std::max(1, n_kin + n_ecp) +
-                            std::max(1, n_ecp) + (size_t)Ne * 8 + (size_t)NWARP * 5 * P + 5 * P + 16;
-  const size_t fixed = (size_t)h->b_up.dev.bytes + sys_bytes(S, P) + 15 * 16 + 64 + 128;
+                            std::max(1, n_ecp) + (size_t)Ne * 10 + (size_t)NWARP * 5 * P + 5 * P + 16;
+  const size_t fixed = (size_t)h->b_up.dev.bytes + sys_bytes(S, P) + 17 * 16 + 64 + 128 + 256;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
