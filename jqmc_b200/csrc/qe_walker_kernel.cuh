@@ -199,16 +199,29 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
     }
   __syncthreads();
 
-  // ---- value/grad/lap of the MOs at every electron (cache): task = (walker, electron) ------------------------
-  for (int s = tid; s < Ne * WPC; s += nthr) {
-    const int wl = s % WPC, e = s / WPC;
-    SinkMO5<NMO> sink;
-    sink.init(tab + (e < N ? B.off_C : B.off_C2));
-    eval_vgl<CART, LMAX>(tab, B, B.off_seg, SR(e, 0), SR(e, 1), SR(e, 2), 0, B.n_grp, sink);
+  // ---- value/grad/lap of the MOs at every electron (cache): task = (walker, electron, half of the basis chunks); the two
+  //      halves land in the cache and in the scratch of the chunked sweep and are added in a second pass (2 N_e WPC tasks
+  //      fill the CTA; one task per (walker, electron) left more than half of the warps idle during the longest sweep) -----
+  {
+    const int* cbeg = (const int*)(tab + P.off_cbeg);
+    const bool split = Ne <= NWARP && P.n_chunk >= 2;  // the scratch holds NWARP x 5 NMO WPC values
+    const int c_mid = split ? P.n_chunk / 2 : P.n_chunk;
+    for (int s0 = tid; s0 < (split ? 2 : 1) * Ne * WPC; s0 += nthr) {
+      const int half = s0 / (Ne * WPC), s = s0 % (Ne * WPC);
+      const int wl = s % WPC, e = s / WPC;
+      SinkMO5<NMO> sink;
+      sink.init(tab + (e < N ? B.off_C : B.off_C2));
+      eval_vgl<CART, LMAX>(tab, B, P.off_cseg, SR(e, 0), SR(e, 1), SR(e, 2), half ? cbeg[c_mid] : cbeg[0],
+                           half ? cbeg[P.n_chunk] : cbeg[c_mid], sink);
+      double* dst = half ? s_part : s_phi;  // same [(e*5+q)*NMO+mo][walker] layout (s_part holds 16 x 5 NMO WPC >= N_e x 5 NMO WPC)
 #pragma unroll
-    for (int q = 0; q < 5; ++q)
+      for (int q = 0; q < 5; ++q)
 #pragma unroll
-      for (int mo = 0; mo < NMO; ++mo) SPHI(e, q, mo) = sink.acc[q][mo];
+        for (int mo = 0; mo < NMO; ++mo) dst[(((e) * 5 + q) * NMO + mo) * WPC + wl] = sink.acc[q][mo];
+    }
+    __syncthreads();
+    if (split)
+      for (int i = tid; i < Ne * 5 * NMO * WPC; i += nthr) s_phi[i] += s_part[i];
   }
   __syncthreads();
 
