@@ -7,15 +7,21 @@
 //   mesh elements) lives in shared memory as [item][walker].
 //
 //   A thread is a (walker, task) pair.  The dominant tasks -- one AO sweep per mesh point -- are the SAME code for every
-//   point, so the 32 lanes of a warp hold 32/WPC consecutive mesh points of WPC walkers: control flow stays uniform, table
-//   reads are warp-broadcast LDS, and WPC is free to make the grid fill the 148 SMs (4096 walkers / 8 = 512 CTAs, 4 per SM).
-//   Several CTAs per SM also hide each other's short serial sections (selection, Sherman-Morrison).
+//   point, so the 32 lanes of a warp hold consecutive (walker, point) pairs: control flow stays uniform and table reads are
+//   warp-broadcast LDS.  One 16-warp CTA per SM; WPC is chosen so that the grid is a single wave (4096 walkers -> 28 per
+//   CTA, 147 CTAs; choose_wpc below).  Several smaller CTAs per SM were measured slower (instruction-cache thrash between
+//   CTAs sitting in different phases).
 //
-//   per projection:  P1  ratio weight vectors W[:,e] = lambda Phi_dn Ginv[:,e] from the running inverse   (walker, electron)
-//                    P2  6 N_e kinetic-mesh ratios + N_e*NN*Nv ECP-mesh ratios (warp rounds handed out
-//                        by a shared counter), per-electron continuum kinetic energy and potentials          (walker, point)
-//                    P3  fixed-node split, diagonal / off-diagonal sums, weight, sequential-cumsum move selection
+//   per projection:  P0  draws: two Threefry splits, mesh rotation, move uniform (first warp, concurrently with P1)
+//                    P1  ratio weight vectors W[:,e] = lambda Phi_dn Ginv[:,e] from the running inverse, and the
+//                        Jastrow terms of every electron at its current position             (walker, electron) x 2 task kinds
+//                    P2  6 N_e kinetic-mesh ratios + N_e*NN*Nv ECP-mesh ratios, two points per thread (warp rounds handed
+//                        out by a shared counter), per-electron continuum kinetic energy and potentials     (walker, point)
+//                    P3  fixed-node split and per-electron chunk sums (walker, electron); diagonal / off-diagonal sums,
+//                        weight and move selection (walker): whole electrons are skipped by their chunk sums
 //                    P4  value/grad/lap of the moved electron (warp = basis chunk), Sherman-Morrison update
+//   GFMC_t (template TAU): the same loop until the walkers of the CTA are out of time, every phase enumerating only the
+//   walkers that still have time left; see qe_walker_tau.cu.
 #pragma once
 #include "qe_common.cuh"
 
