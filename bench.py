@@ -223,7 +223,7 @@ def run_reference(args, rank):
         e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
         gpu_launches=0,
     )  # fmt: skip
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -436,9 +436,21 @@ def run_gpu(args, rank, local_rank, world):
             clocks=clocks, roofline=roofline, cpu_baseline=cpu,
             check=dict(e_L_vmc_mean=e_mean, acceptance=acc_ratio, e_L_lrdmc=e_lrdmc, survived_ratio=surv, wall_s=t_wall),
         )  # fmt: skip
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_RESULT_FD = None
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -454,7 +466,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line (NCCL prints its version banner there)
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version banner there) are sent to
+    # stderr, and the result line goes to the saved descriptor
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank)
         return
