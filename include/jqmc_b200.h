@@ -194,11 +194,11 @@ int qe_dln_wf(qe_engine* h, int nw, const double* r_up, const double* r_dn, cons
  * orbital count, <= 112 electrons per spin, three-body Jastrow; contractions on the fp64 tensor cores).  1: always the
  * general path.  Same results to round-off; bit-identical accept/reject and branching decisions are asserted in tests. */
 int qe_set_path(qe_engine* h, int path);
-/* Debugging aid: nonzero replaces the tensor-core GEMM of the general path by a plain DFMA kernel (process-wide). */
-int qe_set_gemm_reference(int on);
+/* Debugging aid: nonzero replaces the tensor-core GEMM of the general path by a plain DFMA kernel (this handle only). */
+int qe_set_gemm_reference(qe_engine* h, int on);
 /* General family: walkers per slice of a call (0 = automatic from the free device memory).  Calls over more walkers run as
- * consecutive slices through one workspace; results do not depend on the slicing.  Process-wide, like the switch above. */
-int qe_set_wide_slice(int walkers);
+ * consecutive slices through one workspace; results do not depend on the slicing.  Per handle, like every other switch. */
+int qe_set_wide_slice(qe_engine* h, int walkers);
 
 /* Walkers per CTA of the fused walker kernel: 0 = chosen automatically so that the grid fills the SMs (default),
  * 1..32 = fixed (tuning / tests; results do not depend on it beyond round-off of partial-sum order). */
@@ -206,6 +206,11 @@ int qe_set_walkers_per_cta(qe_engine* h, int wpc);
 /* Tuning knob: warps per CTA of the fused walker kernel: 0 / 16 = one 16-warp CTA per SM (default), 8 = two CTAs per SM,
  * 4 = four.  Same results. */
 int qe_set_walker_warps(qe_engine* h, int warps);
+
+/* Diagnostic: per-phase cycle counters of the fused walker kernel (projection loop phases P0..P4 and write-back), summed
+ * over CTAs (thread 0 of each) and launches since they were enabled.  enable != 0 allocates / clears them, out12 (host,
+ * may be NULL) receives the sums accumulated so far (synchronises); enable == 0 switches the timing off again. */
+int qe_phase_clocks(qe_engine* h, int enable, int64_t* out12);
 
 /* Microbenchmark used by bench.py for the fp64 roofline denominator: runs `iters` dependent-free
  * DFMA per thread on a full grid and returns the achieved TFLOP/s (synchronous). */

@@ -106,10 +106,11 @@ EXPORTS = {
     "qe_set_fused": (C.c_int, [C.c_void_p, C.c_int]),
     "qe_set_walkers_per_cta": (C.c_int, [C.c_void_p, C.c_int]),
     "qe_set_walker_warps": (C.c_int, [C.c_void_p, C.c_int]),
-    "qe_set_wide_slice": (C.c_int, [C.c_int]),
+    "qe_set_wide_slice": (C.c_int, [C.c_void_p, C.c_int]),
     "qe_dln_wf": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p]),
     "qe_set_path": (C.c_int, [C.c_void_p, C.c_int]),
-    "qe_set_gemm_reference": (C.c_int, [C.c_int]),
+    "qe_set_gemm_reference": (C.c_int, [C.c_void_p, C.c_int]),
+    "qe_phase_clocks": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "qe_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "qe_profile_kernels": (C.c_int, []),
     "qe_profile_name": (C.c_char_p, [C.c_int]),

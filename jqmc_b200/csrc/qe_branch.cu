@@ -141,7 +141,6 @@ __global__ void k_branch_select(int nw, int world, const double* __restrict__ c,
                                 int* __restrict__ chosen) {
   const int N = nw * world;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= N) return;
   __shared__ double off[64];
   if (threadIdx.x == 0) {
     // MPI.Exscan(SUM): off_r = P_0 + ... + P_{r-1}; rank 0 uses 0.0 (jqmc/jqmc_gfmc.py:6088-6095)
@@ -152,6 +151,7 @@ __global__ void k_branch_select(int nw, int world, const double* __restrict__ c,
     }
   }
   __syncthreads();
+  if (g >= N) return;  // after the barrier: every thread of the last block takes part in it
   const double z = ((double)g + zeta) / (double)N;
   int lo = 0, hi = N;  // first i with cg[i] >= z
   while (lo < hi) {

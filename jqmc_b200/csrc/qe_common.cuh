@@ -119,6 +119,9 @@ struct qe_engine {
   bool profiling = false;
   bool fused = true;  // qe_local_energy uses the fused walker kernel when the system fits
   int wpc_override = 0;  // walkers per CTA of the fused walker kernel (0 = automatic)
+  long long* phase_clk = nullptr;  // optional per-phase cycle counters of the fused walker kernel (qe_phase_clocks)
+  bool gemm_ref = false;  // general family: plain DFMA GEMM instead of the tensor-core kernel (qe_set_gemm_reference)
+  int wide_slice = 0;     // general family: walkers per slice of a call, 0 = automatic (qe_set_wide_slice)
   int walker_warps = 0;  // warps per CTA of the fused walker kernel (0 = 16: one CTA per SM; 8: two CTAs per SM; 4: four)
   struct ProfRec { int id; cudaEvent_t e0, e1; };
   std::vector<ProfRec> prof;

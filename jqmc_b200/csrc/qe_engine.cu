@@ -406,14 +406,20 @@ __global__ void k_geminal(SysDev S, int nw, int n_chunk, const double* __restric
     for (int i = 0; i < NMAX * NMAX; ++i)
       if (i < N * N) G_out[(size_t)w * N * N + i] = G[i];
   }
-  // Gauss-Jordan with partial pivoting on a copy
+  // Gauss-Jordan with partial pivoting on a copy.  The reference inverts by a thresholded-SVD pseudo-inverse (rcond 1e-20,
+  // jqmc/jqmc_mcmc.py:4258-4260): for a non-singular G both are the inverse; a pivot that vanishes relative to the largest
+  // element of G marks a null direction whose row of the result is set to zero instead of dividing by it, so a singular G
+  // (two same-spin electrons on top of each other) gives a finite generalised inverse and ln|det| = -inf, never inf / NaN.
   double A[NMAX * NMAX];
+  double gmax = 0.0;
 #pragma unroll
   for (int i = 0; i < NMAX * NMAX; ++i)
     if (i < N * N) {
       A[i] = G[i];
+      gmax = fmax(gmax, fabs(G[i]));
       I[i] = (i / N == i % N) ? 1.0 : 0.0;
     }
+  const double tiny = 1.0e-20 * gmax;
   double lndet = 0.0, sgn = 1.0;
 #pragma unroll
   for (int c = 0; c < N; ++c) {
@@ -455,7 +461,7 @@ __global__ void k_geminal(SysDev S, int nw, int n_chunk, const double* __restric
     const double d = A[c * N + c];
     lndet += log(fabs(d));
     if (d < 0) sgn = -sgn;
-    const double inv = 1.0 / d;
+    const double inv = fabs(d) > tiny ? 1.0 / d : 0.0;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       A[c * N + j] *= inv;
@@ -857,6 +863,7 @@ extern "C" void qe_destroy(qe_engine* h) {
   if (h->ws) cudaFree(h->ws);
   if (h->branch_ws) cudaFree(h->branch_ws);
   if (h->gemm_ws) cudaFree(h->gemm_ws);
+  if (h->phase_clk) cudaFree(h->phase_clk);
   delete h;
 }
 

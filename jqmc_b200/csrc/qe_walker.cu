@@ -104,3 +104,23 @@ extern "C" int qe_set_walker_warps(qe_engine* h, int warps) {
   h->walker_warps = warps;
   return QE_OK;
 }
+
+// Diagnostic: per-phase cycle counters of the fused walker kernel (thread 0 of every CTA, summed over CTAs and launches).
+// enable != 0 allocates/clears the counters; out12 (host, may be NULL) receives the current sums; enable == 0 switches off.
+extern "C" int qe_phase_clocks(qe_engine* h, int enable, int64_t* out12) {
+  if (!h) return fail(QE_ERR_INVALID, "qe_phase_clocks: bad argument");
+  if (out12 && h->phase_clk) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out12, h->phase_clk, 12 * sizeof(long long), cudaMemcpyDeviceToHost));
+  } else if (out12) {
+    for (int i = 0; i < 12; ++i) out12[i] = 0;
+  }
+  if (enable) {
+    if (!h->phase_clk) CUDA_TRY(cudaMalloc(&h->phase_clk, 16 * sizeof(long long)));
+    CUDA_TRY(cudaMemset(h->phase_clk, 0, 16 * sizeof(long long)));
+  } else if (h->phase_clk) {
+    cudaFree(h->phase_clk);
+    h->phase_clk = nullptr;
+  }
+  return QE_OK;
+}

@@ -50,6 +50,7 @@ struct WalkerArgs {
   uint32_t* keys;  // [nw][2], advanced in place
   int* pc;         // [nw] projection counter (out in the main pass, in in the tail pass)
   int* n_max;      // [1] max over the walkers of the call (atomicMax in the main pass)
+  long long* clk;  // optional [16] per-phase cycle counters (qe_set_phase_clocks; thread 0 of every CTA adds its own)
 };
 
 // R^T (row-major) of R = Rz(gamma) Ry(beta) Rx(alpha), jqmc/jqmc_mcmc.py:4237-4244
@@ -141,6 +142,16 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
   const int lane = tid & 31, wid = tid >> 5, NWARP = nthr >> 5;
   const int WPC = P.wpc;
   const int w0 = blockIdx.x * WPC;
+  // optional phase timing: thread 0 accumulates the cycles between consecutive PHASE() marks (placed after barriers)
+  long long clk_last = 0;
+  long long* clk_acc = nullptr;  // 12 counters in shared memory (carved below), touched by thread 0 only
+  const bool clk_on = P.clk != nullptr && tid == 0;
+#define PHASE(i)                          \
+  if (clk_on) {                           \
+    const long long t_ = clock64();       \
+    clk_acc[i] += t_ - clk_last;          \
+    clk_last = t_;                        \
+  }
 
   // ---- stage tables ------------------------------------------------------------------------------
   {
@@ -170,6 +181,11 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
   int* s_ctr = cv.take<int>(4);
   int* s_act = cv.take<int>((size_t)WPC);  // GFMC_t: compact list of the walkers that still have time left
   uint32_t* s_key = cv.take<uint32_t>((size_t)2 * WPC);  // GFMC_n: running PRNG keys (the draws are made in the kernel)
+  clk_acc = cv.take<long long>(12);
+  if (clk_on) {
+    for (int i = 0; i < 12; ++i) clk_acc[i] = 0;
+    clk_last = clock64();
+  }
 #define SR(e, c) s_r[((e) * 3 + (c)) * WPC + wl]
 #define SGI(i, j) s_Gi[((i) * N + (j)) * WPC + wl]
 #define SPHI(e, q, mo) s_phi[(((e) * 5 + (q)) * NMO + (mo)) * WPC + wl]
@@ -230,6 +246,7 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       for (int i = tid; i < Ne * 5 * NMO * WPC; i += nthr) s_phi[i] += s_part[i];
   }
   __syncthreads();
+  PHASE(0)
 
   const double a2 = P.alat * P.alat;
   const int n_it = P.mode == 0 ? P.nmpm : 1;
@@ -377,6 +394,7 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       for (int mo = 0; mo < NMO; ++mo) SW(e, mo) = Wv[mo];
     }
     __syncthreads();
+    PHASE(1)
 
     // ---- P2: mesh ratios (rounds 0 .. n_rounds_pt-1) and per-electron terms (the following n_rounds_el rounds); a warp
     //      takes the next round from a shared counter.  A thread evaluates TWO mesh points of the same spin block at once
@@ -538,6 +556,7 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       }
     }
     __syncthreads();
+    PHASE(2)
     if (tid == 0) s_ctr[0] = 0;  // the next P2 starts after at least one more barrier
 
     // ---- P3: assemble -----------------------------------------------------------------------------------------------
@@ -609,6 +628,7 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       }
     }
     __syncthreads();
+    PHASE(3)
     // (b) per walker: sums, weight, normalisation of the move probabilities
     if (tid < WPC && (!TAU || P.tail || tau_left > 0.0)) {
       const int wl = tid;
@@ -654,6 +674,7 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       if (P.mode != 0) break;
       __syncthreads();
     }
+    PHASE(4)
     // (d) per walker: first index whose cumulative probability reaches u (searchsorted 'left' on cumsum(p / sum p),
     //     jqmc/jqmc_gfmc.py:5057-5062): skip whole electrons by their chunk sums, then scan element by element; the scan
     //     runs on past the chunk if round-off moved the crossing
@@ -704,6 +725,7 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       SMISC(12) = (double)e;
     }
     __syncthreads();
+    PHASE(5)
 
     // ---- P4: value/grad/lap of the moved electron: warp = basis chunks wid, wid+NWARP, ..., lane = walker --------------
     {
@@ -722,12 +744,14 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       }
     }
     __syncthreads();
+    PHASE(6)
     for (int s = tid; s < 5 * NMO * WPC; s += nthr) {  // fixed-order sum over the warps' partials
       double sum = 0;
       for (int c = 0; c < NWARP; ++c) sum += s_part[(size_t)c * 5 * NMO * WPC + s];
       s_stage[s] = sum;
     }
     __syncthreads();
+    PHASE(7)
     // Sherman-Morrison (jqmc/jqmc_gfmc.py:5083-5141): task = (walker, row i); read phase, barrier, write phase
     {  // N * WPC <= blockDim.x is guaranteed by launch_walker: one pass
       double newrow[16];
@@ -806,6 +830,7 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
         for (int j = 0; j < N; ++j) SGI(i, j) = newrow[j];
     }
     __syncthreads();
+    PHASE(8)
     for (int s = tid; s < 5 * NMO * WPC; s += nthr) {
       const int wl = s % WPC, item = s / WPC;
       if (TAU && SMISC(14) == 0.0) continue;
@@ -820,9 +845,14 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       SR(es, 2) = SMISC(11);
     }
     __syncthreads();
+    PHASE(9)
   }
 
   // ---- write back -------------------------------------------------------------------------------------------
+  if (clk_on) {
+    PHASE(10)
+    for (int i = 0; i < 12; ++i) atomicAdd((unsigned long long*)&P.clk[i], (unsigned long long)clk_acc[i]);
+  }
   if (P.mode == 2) return;
   if constexpr (TAU) {
     if (tid < WPC && w0 + tid < P.nw && (!P.tail || n_extra > 0)) {
@@ -862,6 +892,7 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       if (w0 + wl < P.nw) P.Ginv[(size_t)(w0 + wl) * NN2 + it] = s_Gi[idx];
     }
   }
+#undef PHASE
 #undef NACT
 #undef WLOF
 #undef SR
@@ -946,12 +977,13 @@ int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
   A.off_cseg = h->b_up.off_cseg;
   A.off_cbeg = h->b_up.off_cbeg;
   A.n_chunk = h->b_up.n_chunk;
+  A.clk = h->phase_clk;
   const int Ne = S.n_e;
   const int n_kin = A.mode == 2 ? 0 : 6 * Ne;
   const int n_ecp = S.ecp_flag ? Ne * S.NN * S.Nv : 0;
   const size_t per_walker = (size_t)Ne * 3 + (size_t)S.n_up * S.n_up + (size_t)Ne * 5 * P + (size_t)Ne * P + std::max(1, n_kin + n_ecp) +
                             std::max(1, n_ecp) + (size_t)Ne * 10 + (size_t)NWARP * 5 * P + 5 * P + 16;
-  const size_t fixed = (size_t)h->b_up.dev.bytes + sys_bytes(S, P) + 17 * 16 + 64 + 128 + 256;
+  const size_t fixed = (size_t)h->b_up.dev.bytes + sys_bytes(S, P) + 17 * 16 + 64 + 128 + 256 + 112;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -584,7 +584,10 @@ __global__ void kw_reduce_eL(SysDev S, int nw, int n_ecp, const double* __restri
 // =================================================================================================
 // per-walker matrix inverse: one warp per walker, in-place Gauss-Jordan with partial (row) pivoting in shared memory,
 // row swaps undone as column swaps at the end.  Gs[i][j][w] -> Gi[i][j][w] (+ AoS copies, ln|det|, sign)
-// (reference: thresholded-SVD pseudo-inverse jqmc/jqmc_mcmc.py:4248-4261 -- identical for a non-singular G)
+// (reference: thresholded-SVD pseudo-inverse jqmc/jqmc_mcmc.py:4248-4261 -- identical for a non-singular G).  A pivot
+// that vanishes relative to the largest element of G (the reference's rcond, 1e-20) marks a null direction: its row and
+// column of the result are set to zero instead of dividing by it, so a singular G (e.g. two same-spin electrons on top of
+// each other after branching) gives a finite generalised inverse and ln|det| = -inf, never inf / NaN in the running inverse.
 // =================================================================================================
 __global__ void kw_inverse(int N, int nw, const double* __restrict__ Gs, double* __restrict__ Gi, double* __restrict__ G_aos,
                            double* __restrict__ Ginv_aos, double* __restrict__ lndet_out, double* __restrict__ sign_out) {
@@ -595,12 +598,17 @@ __global__ void kw_inverse(int N, int nw, const double* __restrict__ Gs, double*
   double* A = sm_inv + (size_t)wl * (N * ld + N);
   int* piv = (int*)(A + N * ld);
   if (w >= nw) return;  // whole warp
+  double gmax = 0.0;
   for (int idx = lane; idx < N * N; idx += 32) {
     const int i = idx / N, j = idx % N;
     const double v = Gs[(size_t)idx * nw + w];
     A[i * ld + j] = v;
+    gmax = fmax(gmax, fabs(v));
     if (G_aos) G_aos[(size_t)w * N * N + idx] = v;
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
+  const double tiny = 1.0e-20 * gmax;
   __syncwarp();
   double lndet = 0.0, sgn = 1.0;
   for (int c = 0; c < N; ++c) {
@@ -636,7 +644,7 @@ __global__ void kw_inverse(int N, int nw, const double* __restrict__ Gs, double*
     const double d = A[c * ld + c];
     lndet += log(fabs(d));
     if (d < 0) sgn = -sgn;
-    const double inv = 1.0 / d;
+    const double inv = fabs(d) > tiny ? 1.0 / d : 0.0;  // null direction: zero row (and, below, column) of the result
     __syncwarp();
     if (lane == 0) A[c * ld + c] = 1.0;
     __syncwarp();
@@ -1241,12 +1249,11 @@ struct WState {
   double *AOJ = nullptr, *Chi = nullptr, *U = nullptr, *V = nullptr, *gJ = nullptr, *gJrow = nullptr, *cJ = nullptr;
 };
 
-bool g_gemm_ref = false;  // qe_set_path debugging: plain DFMA GEMM instead of the tensor-core kernel
 
 int w_gemm(qe_engine* h, cudaStream_t st, int m, long long n, int k, const double* A, int lda, const double* B, long long ldb,
            double* D, long long ldd, int batch = 1, long long sB = 0, long long sD = 0) {
   if (m <= 0 || n <= 0 || k <= 0) return QE_OK;
-  if (g_gemm_ref) {
+  if (h->gemm_ref) {  // qe_set_gemm_reference: plain DFMA GEMM instead of the tensor-core kernel
     LaunchScope ls_(h, K_W_GEMM, st);
     dim3 grid(nblk(n, 128), m, batch);
     kw_dgemm_ref<<<grid, 128, 0, st>>>(m, n, k, A, lda, B, ldb, D, ldd, sB, sD);
@@ -1543,8 +1550,9 @@ int eval_newpoint(qe_engine* h, cudaStream_t st, int nw, int NQ, const double* p
 
 }  // namespace
 
-extern "C" int qe_set_gemm_reference(int on) {
-  g_gemm_ref = on != 0;
+extern "C" int qe_set_gemm_reference(qe_engine* h, int on) {
+  if (!h) return fail(QE_ERR_INVALID, "qe_set_gemm_reference: bad argument");
+  h->gemm_ref = on != 0;
   return QE_OK;
 }
 
@@ -1754,14 +1762,13 @@ static int wide_lrdmc_impl(qe_engine* h, int mode, int nw, double* w, double* r_
 // of walkers through the same workspace: walkers are independent (their draws come from their own keys), the caller's
 // arrays are walker-major, so a slice is a pointer offset and the results are identical to one big call.
 // -------------------------------------------------------------------------------------------------
-static int g_wide_slice = 0;  // 0: automatic (workspace budget), > 0: walkers per slice
-extern "C" int qe_set_wide_slice(int walkers) {
-  if (walkers < 0) return fail(QE_ERR_INVALID, "qe_set_wide_slice: walkers must be >= 0");
-  g_wide_slice = walkers;
+extern "C" int qe_set_wide_slice(qe_engine* h, int walkers) {
+  if (!h || walkers < 0) return fail(QE_ERR_INVALID, "qe_set_wide_slice: walkers must be >= 0");
+  h->wide_slice = walkers;  // 0: automatic (workspace budget), > 0: walkers per slice
   return QE_OK;
 }
 static int wide_slice(qe_engine* h, int nw, int nmpm) {
-  if (g_wide_slice > 0) return std::min(nw, g_wide_slice);
+  if (h->wide_slice > 0) return std::min(nw, h->wide_slice);
   const size_t per_walker = (state_bytes(h, 1024, 5, true) + 2 * newpoint_bytes(h, 1024, 5) + lrdmc_draws_bytes(1024, nmpm) +
                              mcmc_draws_bytes(1024, nmpm)) / 1024 + (size_t)h->sys.n_e * 8 * 130;
   if (per_walker * (size_t)nw <= ((size_t)1 << 30)) return nw;  // small call: no need to ask the driver

@@ -176,11 +176,8 @@ class WalkerEngine:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
-            try:
-                self._lib.qe_destroy(h)
-            except Exception:
-                pass
+        if h and self._lib is not None:  # (at interpreter shutdown the ctypes handle may already be gone)
+            self._lib.qe_destroy(h)
 
     # ---- tensor plumbing -------------------------------------------------------------------------
     def _dev(self, x, dtype=torch.float64):
@@ -369,11 +366,11 @@ class WalkerEngine:
 
     def set_gemm_reference(self, on: bool):
         """Debugging aid: plain DFMA GEMM instead of the fp64 tensor-core kernel in the general path."""
-        _lib.check(self._lib.qe_set_gemm_reference(1 if on else 0), "qe_set_gemm_reference")
+        _lib.check(self._lib.qe_set_gemm_reference(self._h, 1 if on else 0), "qe_set_gemm_reference")
 
     def set_wide_slice(self, walkers: int):
         """General family: walkers per slice of one call (0 = automatic from the free device memory); process-wide."""
-        _lib.check(self._lib.qe_set_wide_slice(int(walkers)), "qe_set_wide_slice")
+        _lib.check(self._lib.qe_set_wide_slice(self._h, int(walkers)), "qe_set_wide_slice")
 
     def set_walkers_per_cta(self, wpc: int):
         """Walkers per CTA of the fused walker kernel (0 = automatic)."""
@@ -512,6 +509,15 @@ class WalkerEngine:
 
     def launch_count(self) -> int:
         return int(self._lib.qe_launch_count(self._h))
+
+    PHASE_NAMES = ("stage+VGL", "P1 weights/draws", "P2 mesh", "P3a FN split", "P3b sums", "P3d select", "P4 VGL",
+                   "P4 reduce", "P4 Sherman-Morrison", "P4 commit", "write-back", "-")  # fmt: skip
+
+    def phase_clocks(self, enable: bool = True):
+        """Per-phase cycle sums of the fused walker kernel since the last call (diagnostic); (re)arms or disarms them."""
+        out = (C.c_int64 * 12)()
+        _lib.check(self._lib.qe_phase_clocks(self._h, 1 if enable else 0, out), "qe_phase_clocks")
+        return dict(zip(self.PHASE_NAMES, [int(v) for v in out]))
 
     def profile(self, enable: bool):
         """Switch per-kernel CUDA-event timing on/off (clears previous records)."""

@@ -34,6 +34,7 @@ Out of scope: atomic forces (``comput_position_deriv``).
 
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
@@ -41,7 +42,7 @@ import torch
 
 from . import rng_host
 from .engine import WalkerEngine
-from .mcmc import _dist, _rank_size, generate_init_electron_configurations
+from .mcmc import _dist, _rank_size, generate_init_electron_configurations, should_stop, write_control_file
 
 # jqmc/_setting.py:59-61
 GFMC_ON_THE_FLY_WARMUP_STEPS = 20
@@ -207,6 +208,8 @@ class _GFMC:
     def run(self, num_mcmc_steps: int = 50, max_time: int = 86400) -> None:
         rank, world = _rank_size()
         eng = self.engine
+        toml_filename = "external_control_gfmc.toml"  # jqmc_gfmc.py:4685
+        write_control_file(toml_filename)
         t_start = time.perf_counter()
         zeta_rng = np.random.RandomState(self._mcmc_seed % (2**32))  # rank 0's stream after np.random.seed(mpi_seed), :4669
         A_inv = eng.A_inv_n(self._r_up, self._r_dn)
@@ -251,11 +254,15 @@ class _GFMC:
             if (i + 1) % mcmc_interval == 0 and i > eq_steps:  # :6345-6378
                 flush()
                 self._after_interval(i, eq_steps, n_bins)
-            done += 1
-            if time.perf_counter() - t_start > max_time:
-                flush()
+            # stop conditions (max_time, external stop flag): rank 0's decision, received by every rank so that all of them
+            # leave at the same step (jqmc_gfmc.py:6386-6414).  Checked once per print interval -- the points where the host
+            # reads the device anyway -- instead of every step; the interrupted step is not counted, as in the reference.
+            if (i + 1) % mcmc_interval == 0 and should_stop(t_start, max_time, toml_filename, eng.device):
                 break
+            done += 1
         flush()
+        if rank == 0 and os.path.isfile(toml_filename):
+            os.remove(toml_filename)
         self._mcmc_counter += done
         ns = self._mcmc_counter
         self._stored_e_L = self._stored_e_L[:ns]

@@ -24,6 +24,7 @@ and block symmetrisation of ``get_dln_WF``, ``run_optimize``.
 
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
@@ -44,6 +45,37 @@ def _dist():
 def _rank_size():
     d = _dist()
     return (d.get_rank(), d.get_world_size()) if d else (0, 1)
+
+
+def should_stop(t_start: float, max_time: float, toml_filename: str, device=None) -> bool:
+    """Rank 0 decides (wall-clock limit exceeded, or ``[external_control] stop = true`` in the run's control file) and every
+    rank receives that decision, so that all ranks leave the step loop at the same iteration and none is left waiting in a
+    collective (jqmc/jqmc_gfmc.py:6386-6414, jqmc/jqmc_mcmc.py:985-1010)."""
+    import os
+
+    rank, world = _rank_size()
+    stop = False
+    if rank == 0:
+        stop = max_time < time.perf_counter() - t_start
+        if not stop and os.path.isfile(toml_filename):
+            import tomllib
+
+            try:
+                with open(toml_filename, "rb") as f:
+                    stop = bool(tomllib.load(f).get("external_control", {}).get("stop", False))
+            except (tomllib.TOMLDecodeError, OSError):
+                stop = False
+    if world > 1:
+        stop = bool(_allreduce_sum([1.0 if stop else 0.0], device)[0] > 0.0)
+    return stop
+
+
+def write_control_file(toml_filename: str) -> None:
+    """Rank 0 (re)creates the external control file with ``stop = false`` (jqmc/jqmc_gfmc.py:4684-4698)."""
+    rank, _ = _rank_size()
+    if rank == 0:
+        with open(toml_filename, "w") as f:
+            f.write("[external_control]\nstop = false\n")
 
 
 def _allreduce_sum(values, device=None):
@@ -248,6 +280,8 @@ class MCMC:
     # ---- sampling ------------------------------------------------------------------------------------
     def run(self, num_mcmc_steps: int = 0, max_time=86400) -> None:
         eng = self.engine
+        toml_filename = "external_control_mcmc.toml"  # jqmc_mcmc.py:475
+        write_control_file(toml_filename)
         t_start = time.perf_counter()
         G, Ginv = eng.geminal_inv_batched(self.__r_up, self.__r_dn)
         r_up, r_dn, keys = self.__r_up, self.__r_dn, self.__keys
@@ -271,14 +305,22 @@ class MCMC:
                 for name, g in eng.grad_ln_psi_params_fast(r_up, r_dn, Ginv).items():
                     self.__stored_dln.setdefault(name, []).append(g.cpu().numpy())
             pack = torch.stack([e_L, w_L, acc.to(torch.float64), rej.to(torch.float64)]).cpu().numpy()
+            # rank 0's stop decision (max_time / external stop flag), shared by all ranks; the interrupted step is not
+            # counted and its observables are dropped, as in the reference (jqmc_mcmc.py:930-967, 978-985)
+            if should_stop(t_start, max_time, toml_filename, eng.device):
+                if self.__comput_log_WF_param_deriv:
+                    for v in self.__stored_dln.values():
+                        v.pop()
+                break
             self.__stored_e_L.append(pack[0])
             self.__stored_e_L2.append(pack[0] ** 2)
             self.__stored_w_L.append(pack[1])
             self.__accepted_moves += int(pack[2].sum())
             self.__rejected_moves += int(pack[3].sum())
             self.__mcmc_counter += 1
-            if time.perf_counter() - t_start > max_time:
-                break
+        rank, _ = _rank_size()
+        if rank == 0 and os.path.isfile(toml_filename):
+            os.remove(toml_filename)
         self.__r_up, self.__r_dn, self.__keys = r_up, r_dn, keys
         self.__timer["total"] += time.perf_counter() - t_start
 
