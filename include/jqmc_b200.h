@@ -175,6 +175,19 @@ int qe_lrdmc_branch(qe_engine* h, int nw, int world, const double* w_all, double
 int qe_gather_walkers(qe_engine* h, int nw, const int32_t* chosen_local, const double* src_r_up, const double* src_r_dn,
                       double* dst_r_up, double* dst_r_dn, void* stream);
 
+/* Packed exchange of the reconfiguration: ONE all_gather per branching step instead of the reference's reduce + Exscan +
+ * Allgather x 2 + Alltoallv + Isend/Irecv rounds (jqmc/jqmc_gfmc.py:6016-6020, 6081-6296).  Every rank packs its record
+ *   [5 weighted sums of qe_lrdmc_collect | 3 pad | w[nw] | r_up[nw,n_up,3] | r_dn[nw,n_dn,3]]   (qe_lrdmc_record_len doubles)
+ * with qe_lrdmc_pack; the caller all-gathers the records (rank order); qe_lrdmc_reconfigure_packed then sums the five sums
+ * over ranks in rank order (sums5 may be NULL), evaluates the comb exactly as qe_lrdmc_branch does (chosen_all[world*nw],
+ * *n_survived) and writes this rank's nw new walkers straight from the gathered records. */
+int64_t qe_lrdmc_record_len(qe_engine* h, int nw);
+int qe_lrdmc_pack(qe_engine* h, int nw, const double* sums5, const double* w, const double* r_up, const double* r_dn,
+                  double* record, void* stream);
+int qe_lrdmc_reconfigure_packed(qe_engine* h, int nw, int world, int rank, const double* records, double zeta,
+                                int32_t* chosen_all, int32_t* n_survived, double* sums5, double* dst_r_up, double* dst_r_dn,
+                                void* stream);
+
 /* qe_local_energy runs as ONE fused kernel (shared-memory resident walker state) when the system fits and
  * `on` != 0 (default); otherwise as a chain of staged kernels through a global workspace.  Same results. */
 int qe_set_fused(qe_engine* h, int on);

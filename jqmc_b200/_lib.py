@@ -101,6 +101,12 @@ EXPORTS = {
     "qe_lrdmc_collect": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_double, C.c_void_p, C.c_void_p]),
     "qe_lrdmc_branch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qe_gather_walkers": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p]),
+    "qe_lrdmc_record_len": (C.c_int64, [C.c_void_p, C.c_int]),
+    "qe_lrdmc_pack": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p]),
+    "qe_lrdmc_reconfigure_packed": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double] + [C.c_void_p] * 5 + [C.c_void_p],
+    ),
     "qe_measure_fp64_peak": (C.c_int, [C.c_int, f64p]),
     "qe_launch_count": (C.c_int64, [C.c_void_p]),
     "qe_set_fused": (C.c_int, [C.c_void_p, C.c_int]),

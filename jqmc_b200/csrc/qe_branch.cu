@@ -90,15 +90,17 @@ __device__ double block_np_sum(const double* __restrict__ a, int n, int* s_lo, i
 }
 
 // block r: S[r] = np.sum(w_all[r*nw : (r+1)*nw])
-__global__ void k_branch_rank_sums(int nw, const double* __restrict__ w_all, double* __restrict__ S) {
+// (w_stride: distance between the weight vectors of consecutive ranks -- nw for a dense all-gathered vector, the packed
+//  record length for qe_lrdmc_reconfigure_packed)
+__global__ void k_branch_rank_sums(int nw, size_t w_stride, const double* __restrict__ w_all, double* __restrict__ S) {
   __shared__ int s_lo[MAX_LEAVES], s_ln[MAX_LEAVES], s_cnt;
   __shared__ double s_leaf[MAX_LEAVES];
-  const double v = block_np_sum(w_all + (size_t)blockIdx.x * nw, nw, s_lo, s_ln, s_leaf, &s_cnt);
+  const double v = block_np_sum(w_all + (size_t)blockIdx.x * w_stride, nw, s_lo, s_ln, s_leaf, &s_cnt);
   if (threadIdx.x == 0) S[blockIdx.x] = v;
 }
 
 // block r: p = w / sum_r S[r];  P[r] = np.sum(p_r);  c_r = cumsum(p_r) (sequential fp64, staged through shared memory)
-__global__ void k_branch_cumprob(int nw, int world, const double* __restrict__ w_all, const double* __restrict__ S,
+__global__ void k_branch_cumprob(int nw, int world, size_t w_stride, const double* __restrict__ w_all, const double* __restrict__ S,
                                  double* __restrict__ c, double* __restrict__ P) {
   __shared__ int s_lo[MAX_LEAVES], s_ln[MAX_LEAVES], s_cnt;
   __shared__ double s_leaf[MAX_LEAVES];
@@ -109,7 +111,7 @@ __global__ void k_branch_cumprob(int nw, int world, const double* __restrict__ w
   double gsum = 0.0;
   for (int q = 0; q < world; ++q) gsum += S[q];
   double* cr = c + (size_t)r * nw;
-  const double* wr = w_all + (size_t)r * nw;
+  const double* wr = w_all + (size_t)r * w_stride;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) cr[i] = wr[i] / gsum;
   __syncthreads();
   const double pr = block_np_sum(cr, nw, s_lo, s_ln, s_leaf, &s_cnt);
@@ -228,8 +230,8 @@ extern "C" int qe_lrdmc_collect(qe_engine* h, int nw, const double* w, const dou
   return QE_OK;
 }
 
-extern "C" int qe_lrdmc_branch(qe_engine* h, int nw, int world, const double* w_all, double zeta, int32_t* chosen_all,
-                               int32_t* n_survived, void* stream) {
+static int branch_impl(qe_engine* h, int nw, int world, const double* w_all, size_t w_stride, double zeta, int32_t* chosen_all,
+                       int32_t* n_survived, void* stream) {
   if (!h || nw <= 0 || world <= 0 || world > 64 || !w_all || !chosen_all || !n_survived)
     return fail(QE_ERR_INVALID, "qe_lrdmc_branch: bad argument (world must be 1..64)");
   if (!(zeta >= 0.0 && zeta < 1.0)) return fail(QE_ERR_INVALID, "qe_lrdmc_branch: zeta must be in [0, 1)");
@@ -248,11 +250,90 @@ extern "C" int qe_lrdmc_branch(qe_engine* h, int nw, int world, const double* w_
   CUDA_TRY(cudaMemsetAsync(n_survived, 0, sizeof(int32_t), st));
   {
     LaunchScope ls_(h, K_BRANCH, st);
-    k_branch_rank_sums<<<world, 256, 0, st>>>(nw, w_all, S);
-    k_branch_cumprob<<<world, 256, 0, st>>>(nw, world, w_all, S, c, P);
+    k_branch_rank_sums<<<world, 256, 0, st>>>(nw, w_stride, w_all, S);
+    k_branch_cumprob<<<world, 256, 0, st>>>(nw, world, w_stride, w_all, S, c, P);
     k_branch_select<<<nblk(N, 128), 128, 0, st>>>(nw, world, c, P, zeta, chosen_all);
     k_branch_count<<<nblk(N, 128), 128, 0, st>>>(N, chosen_all, n_survived);
     h->launches += 3;
+  }
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+
+extern "C" int qe_lrdmc_branch(qe_engine* h, int nw, int world, const double* w_all, double zeta, int32_t* chosen_all,
+                               int32_t* n_survived, void* stream) {
+  return branch_impl(h, nw, world, w_all, (size_t)nw, zeta, chosen_all, n_survived, stream);
+}
+
+// ---- packed exchange: ONE all_gather per branching -----------------------------------------------------------------------
+// record of a rank (doubles): [0..4] the five weighted sums of qe_lrdmc_collect, [5..7] padding, then w[nw], r_up[nw*3 n_up],
+// r_dn[nw*3 n_dn]
+namespace {
+__global__ void k_pack_record(int nw, int pu, int pd, const double* __restrict__ sums5, const double* __restrict__ w,
+                              const double* __restrict__ r_up, const double* __restrict__ r_dn, double* __restrict__ rec) {
+  const long long n = 8 + (long long)nw * (1 + pu + pd);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    double v;
+    if (t < 8) v = t < 5 ? sums5[t] : 0.0;
+    else if (t < 8 + nw) v = w[t - 8];
+    else if (t < 8 + (long long)nw * (1 + pu)) v = r_up[t - 8 - nw];
+    else v = r_dn[t - 8 - (long long)nw * (1 + pu)];
+    rec[t] = v;
+  }
+}
+// sums over ranks in rank order (the reference: MPI reduce), and this rank's new walkers from the gathered records
+__global__ void k_unpack_records(int nw, int world, int pu, int pd, size_t stride, const double* __restrict__ all,
+                                 const int* __restrict__ chosen_local, double* __restrict__ sums5, double* __restrict__ dst_up,
+                                 double* __restrict__ dst_dn) {
+  const int per = pu + pd;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 5 && sums5) {
+    double s = 0.0;
+    for (int r = 0; r < world; ++r) s += all[(size_t)r * stride + t];
+    sums5[t] = s;
+  }
+  if (t >= (long long)nw * per) return;
+  const int i = (int)(t / per), k = (int)(t % per);
+  const int g = chosen_local[i], r = g / nw, j = g % nw;
+  const double* rec = all + (size_t)r * stride + 8 + nw;
+  if (k < pu) dst_up[(size_t)i * pu + k] = rec[(size_t)j * pu + k];
+  else dst_dn[(size_t)i * pd + (k - pu)] = rec[(size_t)nw * pu + (size_t)j * pd + (k - pu)];
+}
+}  // namespace
+
+extern "C" int64_t qe_lrdmc_record_len(qe_engine* h, int nw) {
+  if (!h || nw <= 0) return 0;
+  return 8 + (int64_t)nw * (1 + 3 * h->sys.n_up + 3 * h->sys.n_dn);
+}
+
+extern "C" int qe_lrdmc_pack(qe_engine* h, int nw, const double* sums5, const double* w, const double* r_up, const double* r_dn,
+                             double* record, void* stream) {
+  if (!h || nw <= 0 || !sums5 || !w || !r_up || !record || (h->sys.n_dn > 0 && !r_dn))
+    return fail(QE_ERR_INVALID, "qe_lrdmc_pack: bad argument");
+  const int pu = 3 * h->sys.n_up, pd = 3 * h->sys.n_dn;
+  {
+    LaunchScope ls_(h, K_GATHER, (cudaStream_t)stream);
+    k_pack_record<<<std::min(1024u, nblk(8 + (long long)nw * (1 + pu + pd), 256)), 256, 0, (cudaStream_t)stream>>>(nw, pu, pd, sums5, w, r_up,
+                                                                                                                r_dn, record);
+  }
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+
+extern "C" int qe_lrdmc_reconfigure_packed(qe_engine* h, int nw, int world, int rank, const double* records, double zeta,
+                                           int32_t* chosen_all, int32_t* n_survived, double* sums5, double* dst_r_up,
+                                           double* dst_r_dn, void* stream) {
+  if (!h || nw <= 0 || world <= 0 || rank < 0 || rank >= world || !records || !chosen_all || !n_survived || !dst_r_up ||
+      (h->sys.n_dn > 0 && !dst_r_dn))
+    return fail(QE_ERR_INVALID, "qe_lrdmc_reconfigure_packed: bad argument");
+  const size_t stride = (size_t)qe_lrdmc_record_len(h, nw);
+  int rc = branch_impl(h, nw, world, records + 8, stride, zeta, chosen_all, n_survived, stream);
+  if (rc) return rc;
+  const int pu = 3 * h->sys.n_up, pd = 3 * h->sys.n_dn;
+  {
+    LaunchScope ls_(h, K_GATHER, (cudaStream_t)stream);
+    k_unpack_records<<<nblk(std::max<long long>(5, (long long)nw * (pu + pd)), 256), 256, 0, (cudaStream_t)stream>>>(
+        nw, world, pu, pd, stride, records, chosen_all + (size_t)rank * nw, sums5, dst_r_up, dst_r_dn);
   }
   CHECK_LAUNCH();
   return QE_OK;

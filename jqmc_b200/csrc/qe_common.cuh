@@ -187,6 +187,21 @@ __device__ __forceinline__ double qrcp(double x) {
   y = y * fma(-x, y, 2.0);
   return y;
 }
+// The same two functions seeded by the fp64 MUFU approximations (rsqrt.approx.ftz.f64 / rcp.approx.ftz.f64: ~2^-22, no
+// float conversions) with ONE third-order correction step each: 5 / 3 fp64-pipe instructions, relative error ~1e-16
+// (the IEEE sqrt and divide sequences cost ~20 each and carry special-case branches).  x must be a positive normal number.
+__device__ __forceinline__ double mrsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-(x * y), y, 1.0);           // 1 - x y^2
+  return fma(y * e, fma(0.375, e, 0.5), y);         // y (1 + e/2 + 3 e^2/8)
+}
+__device__ __forceinline__ double mrcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);                 // 1 - x y
+  return fma(y, fma(e, e, e), y);                   // y (1 + e + e^2)
+}
 // |(dx,dy,dz)| ; distances below 1e-15 bohr are clamped (the reference's Jastrow derivatives clamp at 1e-12)
 __device__ __forceinline__ double qdist(double dx, double dy, double dz) {
   const double r2 = fmax(fma(dx, dx, fma(dy, dy, dz * dz)), 1.0e-30);
@@ -340,6 +355,53 @@ __device__ __forceinline__ double jastrow_single(const SysDev& S, const Pos& pos
   return J;
 }
 
+// jastrow_single with the MUFU-seeded reciprocal square root / reciprocal (mesh phase of the fused walker kernel: one call
+// per mesh point, N_e + N_at terms each).  Distances are clamped at 1e-150 (a mesh point on top of another particle).
+__device__ __forceinline__ double j1_fm(int type, double a, double inv2a, double A, double c, double d) {
+  if (type == 1) return -A * (1.0 - qexp(-a * c * d)) * inv2a;
+  return -0.5 * A * d * mrcp(fma(a * c, d, 1.0));
+}
+__device__ __forceinline__ double j2_fm(int type, double a, double inv2a, double d) {
+  if (type == 1) return 0.5 * d * mrcp(fma(a, d, 1.0));
+  return (1.0 - qexp(-a * d)) * inv2a;
+}
+template <class Pos>
+__device__ __forceinline__ double jastrow_single_m(const SysDev& S, const Pos& pos, int e, double x, double y, double z) {
+  double J = 0.0;
+  if (S.j1_type) {
+    const double inv2a = 1.0 / (2.0 * S.j1_a);
+    for (int a = 0; a < S.n_atom; ++a) {
+      const double dx = x - S.Rn[3 * a], dy = y - S.Rn[3 * a + 1], dz = z - S.Rn[3 * a + 2];
+      const double r2 = fmax(fma(dx, dx, fma(dy, dy, dz * dz)), 1.0e-300);
+      J += j1_fm(S.j1_type, S.j1_a, inv2a, S.j1_A[a], S.j1_c[a], r2 * mrsqrt(r2));
+    }
+  }
+  if (S.j2_type) {
+    const double inv2a = 1.0 / (2.0 * S.j2_a);
+    double J0 = 0.0, J1 = 0.0;  // two accumulators: the terms of consecutive electrons are independent chains
+    int j = 0;
+    for (; j + 1 < S.n_e; j += 2) {
+      double xa, ya, za, xb, yb, zb;
+      pos.get(j, xa, ya, za);
+      pos.get(j + 1, xb, yb, zb);
+      const double ax = x - xa, ay = y - ya, az = z - za, bx = x - xb, by = y - yb, bz = z - zb;
+      const double ra = fmax(fma(ax, ax, fma(ay, ay, az * az)), 1.0e-300), rb = fmax(fma(bx, bx, fma(by, by, bz * bz)), 1.0e-300);
+      const double fa = j2_fm(S.j2_type, S.j2_a, inv2a, ra * mrsqrt(ra)), fb = j2_fm(S.j2_type, S.j2_a, inv2a, rb * mrsqrt(rb));
+      J0 += j == e ? 0.0 : fa;
+      J1 += j + 1 == e ? 0.0 : fb;
+    }
+    if (j < S.n_e && j != e) {
+      double xa, ya, za;
+      pos.get(j, xa, ya, za);
+      const double ax = x - xa, ay = y - ya, az = z - za;
+      const double ra = fmax(fma(ax, ax, fma(ay, ay, az * az)), 1.0e-300);
+      J0 += j2_fm(S.j2_type, S.j2_a, inv2a, ra * mrsqrt(ra));
+    }
+    J += J0 + J1;
+  }
+  return J;
+}
+
 // Jastrow (J1+J2) difference J(r') - J(r) for moving electron e from (ox,oy,oz) to (nx,ny,nz)
 template <class Pos>
 __device__ __forceinline__ double jastrow_delta(const SysDev& S, const Pos& pos, int e, double ox, double oy, double oz,
@@ -417,6 +479,20 @@ __device__ __forceinline__ double jastrow_delta_q(const SysDev& S, const Pos& po
 }
 
 
+// QE_DEV_MINIMAL (development builds only, never shipped: __graft_entry__.build(minimal=True)): compile the kernels for the
+// benchmark shape alone (4 padded orbitals, spherical basis) -- everything else reports QE_ERR_UNSUPPORTED
+#ifdef QE_DEV_MINIMAL
+#define DISPATCH_NMO_CART(h, CALL)                                                                              \
+  do {                                                                                                          \
+    if ((h)->b_up.dev.cart != 0 || (h)->nmo_pad != 4) return fail(QE_ERR_UNSUPPORTED, "QE_DEV_MINIMAL build"); \
+    CALL(4, false);                                                                                             \
+  } while (0)
+#define DISPATCH_NMO(h, CALL)                                                            \
+  do {                                                                                   \
+    if ((h)->nmo_pad != 4) return fail(QE_ERR_UNSUPPORTED, "QE_DEV_MINIMAL build");     \
+    CALL(4);                                                                             \
+  } while (0)
+#else
 #define DISPATCH_NMO_CART(h, CALL)                                  \
   do {                                                              \
     const bool cart_ = (h)->b_up.dev.cart != 0;                     \
@@ -434,6 +510,7 @@ __device__ __forceinline__ double jastrow_delta_q(const SysDev& S, const Pos& po
       default: CALL(16); break;     \
     }                               \
   } while (0)
+#endif
 
 static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 #define CHECK_LAUNCH()                                                                    \

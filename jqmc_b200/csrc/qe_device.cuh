@@ -18,8 +18,10 @@ constexpr int MAXF = 28;  // max functions per shell: Cartesian l=6 -> 28; spher
 // whichever copy a kernel uses; every table is addressed as tab + byte offset so that the compiler keeps the address
 // space of `tab`: LDS for staged tables, LDG otherwise).
 //   seg  int4   {nucleus, l, shell_begin, shell_end}       one per (nucleus, l) group; chunk lists reuse the format
-//   sh   int4   {prim_begin, prim_end, row0, 0}            row0 = first row of the shell in the row-ordered tables
+//   sh   int4   {prim_begin, prim_end, row0, pair}         row0 = first row of the shell in the row-ordered tables; pair = 1:
+//                                                           this shell and the next one (same group) are both uncontracted
 //   pr   double2{-exponent, coefficient * N_p * sqrt((2l+1)/4pi)}   (jqmc/atomic_orbital.py:2316-2349; Cartesian :2243-2244)
+//   pr2  double2{-exponent * 32/ln2, same coefficient}   value sweeps (qexp_s below);  et double[32] = 2^(j/32)
 //   C    double [n_row][nmo_pad]   transposed MO coefficients * per-AO scale, rows in canonical shell order (row0 + k);
 //                                  rows of functions a shell does not have are zero
 //   row_ao int[n_row], row_scale double[n_row]            AO index (-1: hole) and per-AO scale of each row
@@ -29,6 +31,7 @@ struct BasisDev {
   int n_ao, n_mo, n_orb, n_grp, n_shell, n_prim, n_row, cart, lmax;
   int nmo_pad;                // MO accumulators per thread (4, 8 or 16); C rows are zero-padded to this
   int off_seg, off_sh, off_pr, off_C, off_C2, off_rowao, off_rowscale, off_Rn;  // byte offsets into the blob (16-aligned)
+  int off_pr2, off_et;        // value-sweep primitive table {-exponent * 32/ln2, coefficient}; 2^(j/32) table of qexp_s
   int bytes;                  // blob size (multiple of 16)
   const char* g;              // blob in global memory
 };
@@ -64,6 +67,44 @@ __device__ __forceinline__ double qexp(double x) {
   p = fma(p, r, QE_EXPC[14]);
   return __hiloint2double(under ? 0 : __double2hiint(p) + (__double2loint(t) << 20), __double2loint(p));
 }
+
+// ------------------------------------------------------------------------------------------------
+// exp(-Z r2) of the Gaussian primitives in the value sweeps, the dominant arithmetic of the engine: 10 fp64-pipe
+// instructions instead of the 19 of `a = -Z r2; qexp(a)`.  With zs = -Z 32/ln2 (table pr2) the argument is reduced in units
+// of ln2/32:  k = rint(r2 zs) by the magic-number trick,  u = fma(r2, zs, -k) in [-1/2, 1/2] (one FMA, no separate product),
+// exp = 2^(k >> 5) * 2^((k & 31)/32) * 2^(u/32): the middle factor from a 32-entry table (`et`, staged with the basis image
+// in shared memory: the lookup runs on the LSU, not on the fp64 pipe), the last one a degree-6 polynomial (truncation
+// 3.5e-18), the first one through the exponent field.  Relative error <= 1.2e-16 + |Z r2| 1.1e-16 (rounding of zs; terms
+// with a large argument are exponentially small).  Arguments must be <= 0; results below 2^-1020 are flushed to zero.
+// ------------------------------------------------------------------------------------------------
+__constant__ double QE_EXPS[8] = {6755399441055744.0,     0.02166084939249829,    0.0002345961982022468, 1.693850972437182e-06,
+                                  9.172562701824643e-09,  3.973709984549416e-11,  1.4345655584131934e-13, 1.0};
+__device__ __forceinline__ double qexp_s(double r2, double zs, const double* __restrict__ et) {
+  const double t = fma(r2, zs, QE_EXPS[0]);
+  const long long tb = __double_as_longlong(t);
+  const int ki = (int)tb;  // rint(r2 zs) <= 0 (two's complement in the low mantissa bits)
+  const double kf = t - QE_EXPS[0];
+  const double u = fma(r2, zs, -kf);
+  double p = QE_EXPS[6];
+  p = fma(p, u, QE_EXPS[5]);
+  p = fma(p, u, QE_EXPS[4]);
+  p = fma(p, u, QE_EXPS[3]);
+  p = fma(p, u, QE_EXPS[2]);
+  p = fma(p, u, QE_EXPS[1]);
+  p = fma(p, u, QE_EXPS[7]);
+  const double v = et[ki & 31] * p;
+  // valid iff magic - 32640 <= t <= magic (positive doubles order like their bit patterns): k >= -1020 * 32
+  const bool under = tb < 0x4337FFFFFFFF8080ll;
+  return __hiloint2double(under ? 0 : __double2hiint(v) + ((ki >> 5) << 20), __double2loint(v));
+}
+// the 2^(j/32) table (copied into every basis image at build time; also used to fill it on the host)
+static const double QE_EXP2_TABLE[32] = {
+    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924, 1.1387886347566916,
+    1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332, 1.2968395546510096,
+    1.3252366431597413, 1.3542555469368927, 1.383909881963832, 1.4142135623730951, 1.4451808069770467, 1.4768261459394993,
+    1.5091644275934228, 1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965, 1.681792830507429,
+    1.718619298122478, 1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103, 1.9152065613971474,
+    1.9571441241754002};
 
 // ------------------------------------------------------------------------------------------------
 // Threefry-2x32 and the jax.random draws used by jQMC (semantics: oracle/jaxrng.py)
@@ -182,23 +223,6 @@ struct Ang<true, L> {
 };
 
 // radial sums of one shell: R0 = sum c e, and (VGL) R1 = sum Z c e, R2 = sum Z^2 c e, with e = exp(-Z r2)
-__device__ __forceinline__ double shell_radial(const double2* __restrict__ pr, int pb, int pe, double r2) {
-  double R = 0.0;
-  int p = pb;
-  for (; p + 3 < pe; p += 4) {  // four independent exp chains per trip
-    const double2 a = pr[p], b = pr[p + 1], c = pr[p + 2], d = pr[p + 3];
-    const double ea = qexp(a.x * r2), eb = qexp(b.x * r2), ec = qexp(c.x * r2), ed = qexp(d.x * r2);
-    R = fma(a.y, ea, R);
-    R = fma(b.y, eb, R);
-    R = fma(c.y, ec, R);
-    R = fma(d.y, ed, R);
-  }
-  for (; p < pe; ++p) {
-    const double2 a = pr[p];
-    R = fma(a.y, qexp(a.x * r2), R);
-  }
-  return R;
-}
 __device__ __forceinline__ void shell_radial3(const double2* __restrict__ pr, int pb, int pe, double r2, double& R0, double& R1,
                                               double& R2) {
   R0 = 0.0;
@@ -225,9 +249,16 @@ __device__ __forceinline__ void shell_radial3(const double2* __restrict__ pr, in
 }
 
 // radial sums R[i] = sum_p c_p exp(-Z_p r2[i]) of one shell at NP points (independent exp chains: 2 primitives x NP points)
+// (pr = the value-sweep table pr2: {-exponent * 32/ln2, coefficient}; et = 2^(j/32) table, see qexp_s)
 template <int NP>
-__device__ __forceinline__ void shell_radial_n(const double2* __restrict__ pr, int pb, int pe, const double* __restrict__ r2,
-                                               double* __restrict__ R) {
+__device__ __forceinline__ void shell_radial_n(const double2* __restrict__ pr, const double* __restrict__ et, int pb, int pe,
+                                               const double* __restrict__ r2, double* __restrict__ R) {
+  if (pe - pb == 1) {  // uncontracted shell (most shells of a correlation-consistent basis): straight-line code
+    const double2 a = pr[pb];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) R[i] = a.y * qexp_s(r2[i], a.x, et);
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < NP; ++i) R[i] = 0.0;
   int p = pb;
@@ -236,8 +267,8 @@ __device__ __forceinline__ void shell_radial_n(const double2* __restrict__ pr, i
     double ea[NP], eb[NP];
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-      ea[i] = qexp(a.x * r2[i]);
-      eb[i] = qexp(b.x * r2[i]);
+      ea[i] = qexp_s(r2[i], a.x, et);
+      eb[i] = qexp_s(r2[i], b.x, et);
     }
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
@@ -248,12 +279,13 @@ __device__ __forceinline__ void shell_radial_n(const double2* __restrict__ pr, i
   if (p < pe) {
     const double2 a = pr[p];
 #pragma unroll
-    for (int i = 0; i < NP; ++i) R[i] = fma(a.y, qexp(a.x * r2[i]), R[i]);
+    for (int i = 0; i < NP; ++i) R[i] = fma(a.y, qexp_s(r2[i], a.x, et), R[i]);
   }
 }
 
 template <class A, int NP, class Sink>
-__device__ __forceinline__ void eval_seg_val_n(const int4* __restrict__ sh, const double2* __restrict__ pr, int sb, int se,
+__device__ __forceinline__ void eval_seg_val_n(const int4* __restrict__ sh, const double2* __restrict__ pr,
+                                               const double* __restrict__ et, int sb, int se,
                                                const double* __restrict__ dx, const double* __restrict__ dy,
                                                const double* __restrict__ dz, const double* __restrict__ r2, Sink& sink) {
   double S[NP][A::NF];
@@ -261,12 +293,43 @@ __device__ __forceinline__ void eval_seg_val_n(const int4* __restrict__ sh, cons
   for (int i = 0; i < NP; ++i) A::val(dx[i], dy[i], dz[i], S[i]);
   for (int s = sb; s < se; ++s) {
     const int4 q = sh[s];
+    if (q.w && s + 1 < se) {  // (a chunk boundary may separate the two: then each is swept on its own)
+      // two consecutive uncontracted shells (flagged at build time): their exponentials are evaluated together -- 2 NP
+      // independent chains in one straight-line block instead of NP -- and contracted one after the other
+      const int4 q2 = sh[s + 1];
+      double wv[A::NF], wv2[A::NF];
+      sink.template prefetch<A::NF>(q.z, wv);
+      sink.template prefetch<A::NF>(q2.z, wv2);
+      const double2 a = pr[q.x], b = pr[q2.x];
+      double Ra[NP], Rb[NP];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        Ra[i] = a.y * qexp_s(r2[i], a.x, et);
+        Rb[i] = b.y * qexp_s(r2[i], b.x, et);
+      }
+#pragma unroll
+      for (int k = 0; k < A::NF; ++k) {
+        double v[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) v[i] = Ra[i] * S[i][k];
+        sink.add_nw(q.z + k, v, wv[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < A::NF; ++k) {
+        double v[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) v[i] = Rb[i] * S[i][k];
+        sink.add_nw(q2.z + k, v, wv2[k]);
+      }
+      ++s;
+      continue;
+    }
     // sinks that contract with a per-walker weight vector issue the loads of this shell's weights BEFORE the exponentials
     // (the loads then overlap the radial part instead of stalling every multiply-add); a no-op for the other sinks
     double wv[A::NF];
     sink.template prefetch<A::NF>(q.z, wv);
     double R[NP];
-    shell_radial_n<NP>(pr, q.x, q.y, r2, R);
+    shell_radial_n<NP>(pr, et, q.x, q.y, r2, R);
 #pragma unroll
     for (int k = 0; k < A::NF; ++k) {
       double v[NP];
@@ -285,7 +348,8 @@ __device__ __forceinline__ void eval_val_n(const char* __restrict__ tab, const B
                                            Sink& sink) {
   const int4* seg = (const int4*)(tab + off_list);
   const int4* sh = (const int4*)(tab + B.off_sh);
-  const double2* pr = (const double2*)(tab + B.off_pr);
+  const double2* pr = (const double2*)(tab + B.off_pr2);
+  const double* et = (const double*)(tab + B.off_et);
   const double* Rn = (const double*)(tab + B.off_Rn);
   for (int g = gb; g < ge; ++g) {
     const int4 q = seg[g];
@@ -299,13 +363,13 @@ __device__ __forceinline__ void eval_val_n(const char* __restrict__ tab, const B
       r2[i] = dx[i] * dx[i] + dy[i] * dy[i] + dz[i] * dz[i];
     }
     switch (q.y) {
-      case 0: eval_seg_val_n<typename Ang<CART, 0>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
-      case 1: eval_seg_val_n<typename Ang<CART, 1>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
-      case 2: eval_seg_val_n<typename Ang<CART, 2>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
-      case 3: if (LMAX >= 3) eval_seg_val_n<typename Ang<CART, (LMAX >= 3 ? 3 : 0)>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
-      case 4: if (LMAX >= 4) eval_seg_val_n<typename Ang<CART, (LMAX >= 4 ? 4 : 0)>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
-      case 5: if (LMAX >= 5) eval_seg_val_n<typename Ang<CART, (LMAX >= 5 ? 5 : 0)>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
-      default: if (LMAX >= 6) eval_seg_val_n<typename Ang<CART, (LMAX >= 6 ? 6 : 0)>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 0: eval_seg_val_n<typename Ang<CART, 0>::type, NP>(sh, pr, et, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 1: eval_seg_val_n<typename Ang<CART, 1>::type, NP>(sh, pr, et, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 2: eval_seg_val_n<typename Ang<CART, 2>::type, NP>(sh, pr, et, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 3: if (LMAX >= 3) eval_seg_val_n<typename Ang<CART, (LMAX >= 3 ? 3 : 0)>::type, NP>(sh, pr, et, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 4: if (LMAX >= 4) eval_seg_val_n<typename Ang<CART, (LMAX >= 4 ? 4 : 0)>::type, NP>(sh, pr, et, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 5: if (LMAX >= 5) eval_seg_val_n<typename Ang<CART, (LMAX >= 5 ? 5 : 0)>::type, NP>(sh, pr, et, q.z, q.w, dx, dy, dz, r2, sink); break;
+      default: if (LMAX >= 6) eval_seg_val_n<typename Ang<CART, (LMAX >= 6 ? 6 : 0)>::type, NP>(sh, pr, et, q.z, q.w, dx, dy, dz, r2, sink); break;
     }
   }
 }

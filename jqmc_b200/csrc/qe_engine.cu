@@ -213,6 +213,16 @@ static int build_basis(const qe_basis_desc& d, const qe_basis_desc* d2, int n_at
     sh_cost.push_back(22.0 * t.Z.size() + (nmo_pad + 3.0) * nf);
   }
   if (!grp.empty()) grp.back().w = (int)shells.size();
+  // pair flags: consecutive uncontracted shells of a group are swept two at a time (eval_seg_val_n)
+  for (const int4& g : grp)
+    for (int si = g.z; si + 1 < g.w;) {
+      if (sh[si].y - sh[si].x == 1 && sh[si + 1].y - sh[si + 1].x == 1) {
+        sh[si].w = 1;
+        si += 2;
+      } else {
+        ++si;
+      }
+    }
   const int n_row = (int)row_ao.size();
 
   BasisDev& B = hb.dev;
@@ -245,6 +255,12 @@ static int build_basis(const qe_basis_desc& d, const qe_basis_desc* d2, int n_at
   B.off_seg = blob.put(grp);
   B.off_sh = blob.put(sh);
   B.off_pr = blob.put(pr);
+  {
+    std::vector<double2> pr2(pr.size());
+    for (size_t i = 0; i < pr.size(); ++i) pr2[i] = make_double2(pr[i].x * 46.16624130844683, pr[i].y);  // -Z * 32/ln2
+    B.off_pr2 = blob.put(pr2);
+    B.off_et = blob.put(std::vector<double>(QE_EXP2_TABLE, QE_EXP2_TABLE + 32));
+  }
   B.off_C = B.off_C2 = 0;
   if (d.n_mo > 0 && with_C) {
     const std::vector<double> Cu = c_table(d);

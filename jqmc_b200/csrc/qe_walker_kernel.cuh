@@ -59,10 +59,16 @@ __device__ __forceinline__ void rt_from_angles(double al, double be, double ga, 
   sincos(al, &sa, &ca);
   sincos(be, &sb, &cb);
   sincos(ga, &sg, &cg);
-  const double R[9] = {cb * cg, cg * sa * sb - ca * sg, sa * sg + ca * cg * sb, cb * sg, ca * cg + sa * sb * sg,
-                       ca * sb * sg - cg * sa, -sb, cb * sa, ca * cb};
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) RT[i * 3 + j] = R[j * 3 + i];
+  // R rows written transposed (compile-time indices: the matrix stays in registers)
+  RT[0] = cb * cg;
+  RT[3] = cg * sa * sb - ca * sg;
+  RT[6] = sa * sg + ca * cg * sb;
+  RT[1] = cb * sg;
+  RT[4] = ca * cg + sa * sb * sg;
+  RT[7] = ca * sb * sg - cg * sa;
+  RT[2] = -sb;
+  RT[5] = cb * sa;
+  RT[8] = ca * cb;
 }
 
 // shared-memory carve-up by byte offsets from the (16-byte aligned) dynamic shared memory base
@@ -124,7 +130,7 @@ struct PosShared {
   }
 };
 
-template <int NMO, bool CART, int LMAX, bool TAU>
+template <int NMO, bool CART, int LMAX, bool TAU, int WS_T>
 __global__ void __launch_bounds__(512, 1)
 k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
   extern __shared__ __align__(16) char smem_raw[];
@@ -140,7 +146,10 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
     }
   }
   const int lane = tid & 31, wid = tid >> 5, NWARP = nthr >> 5;
-  const int WPC = P.wpc;
+  const int WPC = P.wpc;  // live walkers of this CTA
+  // walker stride of the [item][walker] shared arrays: the compile-time constant 32 when the padded arrays fit (addresses
+  // become immediate offsets: the index arithmetic was a quarter of the kernel's instructions), otherwise WPC (dense)
+  const int WS = WS_T ? WS_T : P.wpc;
   const int w0 = blockIdx.x * WPC;
   // optional phase timing: thread 0 accumulates the cycles between consecutive PHASE() marks (placed after barriers)
   long long clk_last = 0;
@@ -167,17 +176,24 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
   const int n_ecp = S.ecp_flag ? Ne * S.NN * S.Nv : 0;
   const int NPT = n_kin + n_ecp;
 
-  double* s_r = cv.take<double>((size_t)Ne * 3 * WPC);
-  double* s_Gi = cv.take<double>((size_t)NN2 * WPC);
-  double* s_phi = cv.take<double>((size_t)Ne * 5 * NMO * WPC);  // [(e*5+q)*NMO+mo]
-  double* s_W = cv.take<double>((size_t)Ne * NMO * WPC);
-  double* s_p = cv.take<double>((size_t)(NPT > 0 ? NPT : 1) * WPC);
-  double* s_j = cv.take<double>((size_t)(n_ecp > 0 ? n_ecp : 1) * WPC);
-  double* s_el = cv.take<double>((size_t)Ne * 8 * WPC);  // [e*8 + {ke|opt, ei, eid, loc, ee, kinFN, kinSP, -}]
-  double* s_e2 = cv.take<double>((size_t)Ne * 2 * WPC);  // [e*2 + {sum of the fixed-node ECP elements of electron e, of their positive parts}]
-  double* s_part = cv.take<double>((size_t)NWARP * 5 * NMO * WPC);
-  double* s_stage = cv.take<double>((size_t)5 * NMO * WPC);
-  double* s_misc = cv.take<double>((size_t)16 * WPC);  // 0..8 RT, 9..11 new position, 12 selected electron, 13 total
+  double* s_r = cv.take<double>((size_t)Ne * 3 * WS);
+  double* s_Gi = cv.take<double>((size_t)NN2 * WS);
+  double* s_phi = cv.take<double>((size_t)Ne * 5 * NMO * WS);  // [(e*5+q)*NMO+mo]
+  double* s_W = cv.take<double>((size_t)Ne * NMO * WS);
+  double* s_el = cv.take<double>((size_t)Ne * 8 * WS);  // [e*8 + {ke|opt, ei, eid, loc, ee, kinFN, kinSP, -}]
+  double* s_e2 = cv.take<double>((size_t)Ne * 2 * WS);  // [e*2 + {sum of the fixed-node ECP elements of electron e, of their positive parts}]
+  // s_part (partial sums of the chunked value/grad/lap sweeps: start-up and P4) shares its storage with the mesh elements
+  // s_p and the ECP Jastrow ratios s_j (P2 -> P3): the move has been selected before P4 overwrites them
+  const int n_pj = (NPT > 0 ? NPT : 1) + (n_ecp > 0 ? n_ecp : 1);
+  double* s_part = cv.take<double>((size_t)(NWARP * 5 * NMO > n_pj ? NWARP * 5 * NMO : n_pj) * WS);
+  double* s_p = s_part;
+  double* s_j = s_part + (size_t)(NPT > 0 ? NPT : 1) * WS;
+  // non-local ECP data of every (electron, nn-th nearest nucleus), shared by its Nv quadrature points:
+  // [0] nucleus index, [1] distance d, [2..4] unit vector nucleus -> electron, [5 + l] V_l(d) (2l+1) / d^2
+  const int ECPW = 5 + S.ecp_lmax;
+  double* s_ecp = cv.take<double>((size_t)(S.ecp_flag ? Ne * S.NN * ECPW : 1) * WS);
+  double* s_stage = cv.take<double>((size_t)5 * NMO * WS);
+  double* s_misc = cv.take<double>((size_t)16 * WS);  // 0..8 RT, 9..11 new position, 12 selected electron, 13 total
   int* s_ctr = cv.take<int>(4);
   int* s_act = cv.take<int>((size_t)WPC);  // GFMC_t: compact list of the walkers that still have time left
   uint32_t* s_key = cv.take<uint32_t>((size_t)2 * WPC);  // GFMC_n: running PRNG keys (the draws are made in the kernel)
@@ -186,27 +202,27 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
     for (int i = 0; i < 12; ++i) clk_acc[i] = 0;
     clk_last = clock64();
   }
-#define SR(e, c) s_r[((e) * 3 + (c)) * WPC + wl]
-#define SGI(i, j) s_Gi[((i) * N + (j)) * WPC + wl]
-#define SPHI(e, q, mo) s_phi[(((e) * 5 + (q)) * NMO + (mo)) * WPC + wl]
-#define SW(e, mo) s_W[((e) * NMO + (mo)) * WPC + wl]
-#define SEL(e, i) s_el[((e) * 8 + (i)) * WPC + wl]
-#define SMISC(i) s_misc[(i) * WPC + wl]
+#define SR(e, c) s_r[((e) * 3 + (c)) * WS + wl]
+#define SGI(i, j) s_Gi[((i) * N + (j)) * WS + wl]
+#define SPHI(e, q, mo) s_phi[(((e) * 5 + (q)) * NMO + (mo)) * WS + wl]
+#define SW(e, mo) s_W[((e) * NMO + (mo)) * WS + wl]
+#define SEL(e, i) s_el[((e) * 8 + (i)) * WS + wl]
+#define SMISC(i) s_misc[(i) * WS + wl]
 #define GW(wl_) (min(w0 + (wl_), P.nw - 1)) /* dead walkers of the last CTA shadow the last walker (no stores) */
 
   for (int idx = tid; idx < Ne * 3 * WPC; idx += nthr) {
     const int wl = idx % WPC, it = idx / WPC, e = it / 3, c = it % 3;
     const int ww = GW(wl);
-    s_r[idx] = e < N ? P.r_up[((size_t)ww * N + e) * 3 + c] : P.r_dn[((size_t)ww * Nd + (e - N)) * 3 + c];
+    s_r[it * WS + wl] = e < N ? P.r_up[((size_t)ww * N + e) * 3 + c] : P.r_dn[((size_t)ww * Nd + (e - N)) * 3 + c];
   }
   for (int idx = tid; idx < NN2 * WPC; idx += nthr) {
     const int wl = idx % WPC, it = idx / WPC;
-    s_Gi[idx] = P.Ginv[(size_t)GW(wl) * NN2 + it];
+    s_Gi[it * WS + wl] = P.Ginv[(size_t)GW(wl) * NN2 + it];
   }
   if (P.mode != 0)
     for (int idx = tid; idx < 9 * WPC; idx += nthr) {
       const int wl = idx % WPC, c = idx / WPC;
-      s_misc[idx] = P.RT_in ? P.RT_in[(size_t)GW(wl) * 9 + c] : (c % 4 == 0 ? 1.0 : 0.0);
+      s_misc[c * WS + wl] = P.RT_in ? P.RT_in[(size_t)GW(wl) * 9 + c] : (c % 4 == 0 ? 1.0 : 0.0);
     }
   if (tid == 0) s_ctr[0] = 0;
   if (!TAU && P.mode == 0)
@@ -217,7 +233,7 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
   if constexpr (TAU)
     for (int wl = tid; wl < WPC; wl += nthr) {
       s_act[wl] = wl;
-      s_misc[14 * WPC + wl] = 1.0;  // has time left
+      s_misc[14 * WS + wl] = 1.0;  // has time left
     }
   __syncthreads();
 
@@ -239,11 +255,11 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
 #pragma unroll
       for (int q = 0; q < 5; ++q)
 #pragma unroll
-        for (int mo = 0; mo < NMO; ++mo) dst[(((e) * 5 + q) * NMO + mo) * WPC + wl] = sink.acc[q][mo];
+        for (int mo = 0; mo < NMO; ++mo) dst[(((e) * 5 + q) * NMO + mo) * WS + wl] = sink.acc[q][mo];
     }
     __syncthreads();
     if (split)
-      for (int i = tid; i < Ne * 5 * NMO * WPC; i += nthr) s_phi[i] += s_part[i];
+      for (int i = tid; i < Ne * 5 * NMO * WS; i += nthr) s_phi[i] += s_part[i];  // (padding slots included: never read)
   }
   __syncthreads();
   PHASE(0)
@@ -284,16 +300,16 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       if (tid == 0) {
         int n = 0;
         for (int wl = 0; wl < WPC; ++wl)
-          if (s_misc[14 * WPC + wl] != 0.0) s_act[n++] = wl;
+          if (s_misc[14 * WS + wl] != 0.0) s_act[n++] = wl;
         s_ctr[1] = n;
       }
       __syncthreads();
       n_act = s_ctr[1];
     }
-    const int blk_size[4] = {n_ku * NACT, n_kd * NACT, n_eu * NACT, n_ed * NACT};
-    const int blk_start[4] = {0, n_ku * NACT, n_kin * NACT, (n_kin + n_eu) * NACT};
-    const int blk_pairs[4] = {(blk_size[0] + 1) / 2, (blk_size[1] + 1) / 2, (blk_size[2] + 1) / 2, (blk_size[3] + 1) / 2};
-    const int n_rounds_pt = (blk_pairs[0] + blk_pairs[1] + blk_pairs[2] + blk_pairs[3] + 31) / 32;
+    // (scalars, not arrays: a run-time block index would put arrays into local memory)
+    const int bs0 = n_ku * NACT, bs1 = n_kd * NACT, bs2 = n_eu * NACT, bs3 = n_ed * NACT;
+    const int bp0 = (bs0 + 1) / 2, bp1 = (bs1 + 1) / 2, bp2 = (bs2 + 1) / 2, bp3 = (bs3 + 1) / 2;
+    const int n_rounds_pt = (bp0 + bp1 + bp2 + bp3 + 31) / 32;
     const int n_rounds_el = (Ne * NACT + 31) / 32;
     // ---- P1: ratio weight vectors, task = (walker, electron) -----------------------------------------------------
     if constexpr (TAU) {
@@ -345,15 +361,42 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
     // (in the projection modes the tasks start at warp 1: the first warp is busy with the draws)
     const int p1_off = (P.mode == 0 && nthr > 32) ? 32 : 0;
     // two task kinds per (walker, electron): the ratio weight vector, and the Jastrow terms at the current position
-    for (int s0 = tid - p1_off; s0 < 2 * Ne * NACT; s0 += nthr - p1_off) {
+    const int n_etask = S.ecp_flag ? Ne * S.NN * NACT : 0;
+    for (int s0 = tid - p1_off; s0 < 2 * Ne * NACT + n_etask; s0 += nthr - p1_off) {
       if (s0 < 0) continue;
+      if (s0 >= 2 * Ne * NACT) {
+        // non-local ECP radial factors of (electron, nn): nearest-nucleus search, distance and the channel sums are done
+        // once here instead of at each of the Nv quadrature points (jqmc/coulomb_potential.py:1562-1575, 1607-1645)
+        const int s = s0 - 2 * Ne * NACT;
+        const int wl = WLOF(s % NACT), t = s / NACT, nn = t % S.NN, e = t / S.NN;
+        const double x = SR(e, 0), y = SR(e, 1), z = SR(e, 2);
+        double d;
+        const int a = nearest_atom(S.Rn, S.n_atom, x, y, z, nn, &d);
+        const double relx = S.Rn[3 * a] - x, rely = S.Rn[3 * a + 1] - y, relz = S.Rn[3 * a + 2] - z;
+        d = sqrt(relx * relx + rely * rely + relz * relz);
+        double* o = s_ecp + (size_t)t * ECPW * WS + wl;
+        o[0] = (double)a;
+        o[WS] = d;
+        o[2 * WS] = -relx / d;
+        o[3 * WS] = -rely / d;
+        o[4 * WS] = -relz / d;
+        const int lloc = S.ecp_lmax_atom[a];
+        for (int l = 0; l < S.ecp_lmax; ++l) {
+          double vl = 0.0;
+          if (l < lloc)
+            for (int kk = S.ecp_off[a]; kk < S.ecp_off[a + 1]; ++kk)
+              if (S.ecp_l[kk] == l) vl += S.ecp_c[kk] * ipow(d, S.ecp_p[kk]) * qexp(-S.ecp_z[kk] * d * d);
+          o[(5 + l) * WS] = vl / (d * d) * (2 * l + 1);
+        }
+        continue;
+      }
       const bool jtask = s0 >= Ne * NACT;
       const int s = jtask ? s0 - Ne * NACT : s0;
       const int wl = WLOF(s % NACT), e = s / NACT;
       if (jtask) {
         // Jastrow terms of electron e at its current position (shared by all of its mesh points)
-        PosShared pos{s_r, WPC, wl};
-        SEL(e, 7) = jastrow_single(S, pos, e, SR(e, 0), SR(e, 1), SR(e, 2));
+        PosShared pos{s_r, WS, wl};
+        SEL(e, 7) = jastrow_single_m(S, pos, e, SR(e, 0), SR(e, 1), SR(e, 2));
         continue;
       }
       double Wv[NMO];
@@ -406,15 +449,14 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       if (r >= n_rounds_pt + n_rounds_el) break;
       if (r < n_rounds_pt) {
         int pi = r * 32 + lane;  // pair index -> block (kin up, kin dn, ecp up, ecp dn)
-        int blk = 0;
-        while (blk < 4 && pi >= blk_pairs[blk]) {
-          pi -= blk_pairs[blk];
-          ++blk;
-        }
+        int blk = 0, half = bp0, bstart = 0, bsize = bs0;
+        if (pi >= half) { pi -= half; blk = 1; half = bp1; bstart = bs0; bsize = bs1;
+          if (pi >= half) { pi -= half; blk = 2; half = bp2; bstart = n_kin * NACT; bsize = bs2;
+            if (pi >= half) { pi -= half; blk = 3; half = bp3; bstart = (n_kin + n_eu) * NACT; bsize = bs3;
+              if (pi >= half) blk = 4; } } }
         if (blk < 4) {
-          const int half = blk_pairs[blk];
-          const int sA = blk_start[blk] + pi;
-          const bool validB = pi + half < blk_size[blk];
+          const int sA = bstart + pi;
+          const bool validB = pi + half < bsize;
           const int sB = validB ? sA + half : sA;
           int sl[2] = {sA, sB};
           double px[2], py[2], pz[2], angw[2], jold[2];
@@ -423,11 +465,8 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
           for (int i = 0; i < 2; ++i) {
             const int wl = WLOF(sl[i] % NACT), t = sl[i] / NACT;
             wls[i] = wl;
-            if constexpr (TAU) sl[i] = t * WPC + wl;  // storage slot
-            PosShared pos{s_r, WPC, wl};
-            double rt[9];
-#pragma unroll
-            for (int c = 0; c < 9; ++c) rt[c] = SMISC(c);
+            sl[i] = t * WS + wl;  // storage slot
+            PosShared pos{s_r, WS, wl};
             double x, y, z;
             angw[i] = 0.0;
             if (blk < 2) {
@@ -435,17 +474,30 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
               const int s6 = t % 6, ax = s6 >> 1;
               const double sg = (s6 & 1) ? -P.alat : P.alat;
               pos.get(e, x, y, z);
-              px[i] = x + sg * rt[3 * ax];
-              py[i] = y + sg * rt[3 * ax + 1];
-              pz[i] = z + sg * rt[3 * ax + 2];
+              px[i] = x + sg * SMISC(3 * ax);
+              py[i] = y + sg * SMISC(3 * ax + 1);
+              pz[i] = z + sg * SMISC(3 * ax + 2);
               el[i] = e;
             } else {
               const int pt = t - n_kin;
-              const int k = pt % S.Nv, nn = (pt / S.Nv) % S.NN;
-              const int e = pt / (S.Nv * S.NN);
-              pos.get(e, x, y, z);
-              ecp_point(S, rt, x, y, z, nn, k, px[i], py[i], pz[i], angw[i], true);
-              el[i] = e;
+              const int k = pt % S.Nv, en = pt / S.Nv;  // en = e * NN + nn
+              el[i] = en / S.NN;
+              const double* o = s_ecp + (size_t)en * ECPW * WS + wl;
+              const int a = (int)o[0];
+              const double d = o[WS];
+              // rotated quadrature direction g = q RT (jqmc/coulomb_potential.py:1547), point R_a + d g (:1607-1610)
+              const double q0 = S.quad_g[3 * k], q1 = S.quad_g[3 * k + 1], q2 = S.quad_g[3 * k + 2];
+              const double gx = q0 * SMISC(0) + q1 * SMISC(3) + q2 * SMISC(6);
+              const double gy = q0 * SMISC(1) + q1 * SMISC(4) + q2 * SMISC(7);
+              const double gz = q0 * SMISC(2) + q1 * SMISC(5) + q2 * SMISC(8);
+              px[i] = fma(d, gx, S.Rn[3 * a]);
+              py[i] = fma(d, gy, S.Rn[3 * a + 1]);
+              pz[i] = fma(d, gz, S.Rn[3 * a + 2]);
+              // cos(theta) between nucleus -> electron and the quadrature direction (:1643-1645), channel sum (:1573-1575)
+              const double cos_t = (o[2 * WS] * gx + o[3 * WS] * gy + o[4 * WS] * gz) * mrsqrt(gx * gx + gy * gy + gz * gz);
+              double ang = 0.0;
+              for (int l = 0; l < S.ecp_lmax; ++l) ang = fma(o[(5 + l) * WS], legendre_l(l, cos_t), ang);
+              angw[i] = ang * S.quad_w[k];
             }
             jold[i] = SEL(el[i], 7);
           }
@@ -455,17 +507,17 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             const int wl = wls[i], e = el[i];
-            PosShared pos{s_r, WPC, wl};
+            PosShared pos{s_r, WS, wl};
             double ratio = 0.0;
 #pragma unroll
             for (int mo = 0; mo < NMO; ++mo) ratio = fma(sink.acc[i][mo], SW(e, mo), ratio);
-            const double jr = qexp(jastrow_single(S, pos, e, px[i], py[i], pz[i]) - jold[i]);
+            const double jr = qexp(jastrow_single_m(S, pos, e, px[i], py[i], pz[i]) - jold[i]);
             if (i == 0 || validB) {
               if (blk < 2) {
                 s_p[sl[i]] = -1.0 / (2.0 * a2) * (ratio * jr);
               } else {
                 s_p[sl[i]] = P.dlt ? angw[i] * ratio : angw[i] * (ratio * jr);
-                s_j[sl[i] - n_kin * WPC] = jr;
+                s_j[sl[i] - n_kin * WS] = jr;
               }
             }
           }
@@ -475,7 +527,7 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
         const int s = (r - n_rounds_pt) * 32 + lane;
         if (s < Ne * NACT) {
           const int wl = WLOF(s % NACT), e = s / NACT;
-          PosShared pos{s_r, WPC, wl};
+          PosShared pos{s_r, WS, wl};
           double x, y, z;
           pos.get(e, x, y, z);
           double gD[3] = {0, 0, 0}, lD = 0;
@@ -571,7 +623,7 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
           vl += SEL(e, 3);
           if (P.T_elem && live) P.T_elem[(size_t)w * Ne + e] = SEL(e, 0);
         }
-        for (int k = 0; k < n_ecp; ++k) vnl += s_p[k * WPC + wl];
+        for (int k = 0; k < n_ecp; ++k) vnl += s_p[k * WS + wl];
         if (live) {
           P.e_L[w] = T + (vbare + (vl + vnl));
           if (P.V_parts) {
@@ -591,13 +643,13 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       bool flip = false;
       double nd = 0, kinFN = 0, kinSP = 0;
       for (int s6 = 0; s6 < 6; ++s6) {
-        const double v = s_p[(6 * e + s6) * WPC + wl];
+        const double v = s_p[(6 * e + s6) * WS + wl];
         flip = flip || (v >= 0.0);
         nd += v + 1.0 / (4.0 * a2);
         const double fn = fmin(v, 0.0);
         kinFN += fn;
         kinSP += fmax(v, 0.0);
-        s_p[(6 * e + s6) * WPC + wl] = fn;
+        s_p[(6 * e + s6) * WS + wl] = fn;
       }
       const double zv = SEL(e, 1) + SEL(e, 0) - nd;
       const double eib = S.ecp_flag ? SEL(e, 1) : SEL(e, 2);
@@ -614,17 +666,17 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
         const int wl = WLOF(c % NACT), e = c / NACT;
         double sFN = 0, sSP = 0;
         for (int k = e * per; k < (e + 1) * per; ++k) {
-          const double v = s_p[(n_kin + k) * WPC + wl];
+          const double v = s_p[(n_kin + k) * WS + wl];
           double fn = fmin(v, 0.0);
-          if (P.dlt) fn *= s_j[k * WPC + wl];
+          if (P.dlt) fn *= s_j[k * WS + wl];
           const double sp = fmax(v, 0.0);
-          s_p[(n_kin + k) * WPC + wl] = fn;
-          s_j[k * WPC + wl] = sp;
+          s_p[(n_kin + k) * WS + wl] = fn;
+          s_j[k * WS + wl] = sp;
           sFN += fn;
           sSP += sp;
         }
-        s_e2[(e * 2 + 0) * WPC + wl] = sFN;
-        s_e2[(e * 2 + 1) * WPC + wl] = sSP;
+        s_e2[(e * 2 + 0) * WS + wl] = sFN;
+        s_e2[(e * 2 + 1) * WS + wl] = sSP;
       }
     }
     __syncthreads();
@@ -645,8 +697,8 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       double sum_eFN = 0, SP_e = 0;
       if (n_ecp > 0)
         for (int e = 0; e < Ne; ++e) {
-          sum_eFN += s_e2[(e * 2 + 0) * WPC + wl];
-          SP_e += s_e2[(e * 2 + 1) * WPC + wl];
+          sum_eFN += s_e2[(e * 2 + 0) * WS + wl];
+          SP_e += s_e2[(e * 2 + 1) * WS + wl];
         }
       nondiag = sum_kinFN + sum_eFN;
       diag = S.ecp_flag ? diag_kin + disc_bare + loc + SP_kin + SP_e : diag_kin + disc_bare + SP_kin;
@@ -668,7 +720,7 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
     }
     if constexpr (TAU) {
       n_done = it + 1;
-      const int mv = (tid < WPC) ? (s_misc[14 * WPC + tid] != 0.0) : 0;
+      const int mv = (tid < WPC) ? (s_misc[14 * WS + tid] != 0.0) : 0;
       if (!__syncthreads_or(mv)) break;  // every walker of the CTA has used up its time
     } else {
       if (P.mode != 0) break;
@@ -678,46 +730,48 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
     // (d) per walker: first index whose cumulative probability reaches u (searchsorted 'left' on cumsum(p / sum p),
     //     jqmc/jqmc_gfmc.py:5057-5062): skip whole electrons by their chunk sums, then scan element by element; the scan
     //     runs on past the chunk if round-off moved the crossing
-    if (tid < WPC && (!TAU || s_misc[14 * WPC + tid] != 0.0)) {
+    if (tid < WPC && (!TAU || s_misc[14 * WS + tid] != 0.0)) {
       const int wl = tid;
-      PosShared pos{s_r, WPC, wl};
+      PosShared pos{s_r, WS, wl};
       const double u = TAU ? u_move : SMISC(15);
       const double tot = SMISC(13);
       const int per = S.ecp_flag ? S.NN * S.Nv : 0, n_ch = n_ecp > 0 ? 2 * Ne : Ne;
       int ksel = NPT - 1, kstart = 0;
       double c = 0;
       for (int ci = 0; ci < n_ch; ++ci) {
-        const double cs = (ci < Ne ? SEL(ci, 5) : s_e2[((ci - Ne) * 2) * WPC + wl]) / tot;
+        const double cs = (ci < Ne ? SEL(ci, 5) : s_e2[((ci - Ne) * 2) * WS + wl]) / tot;
         if (c + cs >= u) break;
         c += cs;
         kstart = ci + 1 < Ne ? 6 * (ci + 1) : n_kin + (ci + 1 - Ne) * per;
       }
       for (int k = kstart; k < NPT; ++k) {
-        c += s_p[k * WPC + wl] / tot;
+        c += s_p[k * WS + wl] / tot;
         if (c >= u) {
           ksel = k;
           break;
         }
       }
-      double rt[9];
-#pragma unroll
-      for (int cc = 0; cc < 9; ++cc) rt[cc] = SMISC(cc);
       int e;
-      double x, y, z, px, py, pz, dummy;
+      double x, y, z, px, py, pz;
       if (ksel < n_kin) {
         e = ksel / 6;
         const int s6 = ksel % 6, ax = s6 >> 1;
         const double sg = (s6 & 1) ? -P.alat : P.alat;
         pos.get(e, x, y, z);
-        px = x + sg * rt[3 * ax];
-        py = y + sg * rt[3 * ax + 1];
-        pz = z + sg * rt[3 * ax + 2];
+        px = x + sg * SMISC(3 * ax);
+        py = y + sg * SMISC(3 * ax + 1);
+        pz = z + sg * SMISC(3 * ax + 2);
       } else {
         const int pt = ksel - n_kin;
-        const int k = pt % S.Nv, nn = (pt / S.Nv) % S.NN;
-        e = pt / (S.Nv * S.NN);
-        pos.get(e, x, y, z);
-        ecp_point(S, rt, x, y, z, nn, k, px, py, pz, dummy, false);
+        const int k = pt % S.Nv, en = pt / S.Nv;
+        e = en / S.NN;
+        const double* o = s_ecp + (size_t)en * ECPW * WS + wl;
+        const int a = (int)o[0];
+        const double d = o[WS];
+        const double q0 = S.quad_g[3 * k], q1 = S.quad_g[3 * k + 1], q2 = S.quad_g[3 * k + 2];
+        px = fma(d, q0 * SMISC(0) + q1 * SMISC(3) + q2 * SMISC(6), S.Rn[3 * a]);
+        py = fma(d, q0 * SMISC(1) + q1 * SMISC(4) + q2 * SMISC(7), S.Rn[3 * a + 1]);
+        pz = fma(d, q0 * SMISC(2) + q1 * SMISC(5) + q2 * SMISC(8), S.Rn[3 * a + 2]);
       }
       SMISC(9) = px;
       SMISC(10) = py;
@@ -740,21 +794,23 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
 #pragma unroll
         for (int q = 0; q < 5; ++q)
 #pragma unroll
-          for (int mo = 0; mo < NMO; ++mo) s_part[((wid * 5 + q) * NMO + mo) * WPC + wl] = sink.acc[q][mo];
+          for (int mo = 0; mo < NMO; ++mo) s_part[((wid * 5 + q) * NMO + mo) * WS + wl] = sink.acc[q][mo];
       }
     }
     __syncthreads();
     PHASE(6)
-    for (int s = tid; s < 5 * NMO * WPC; s += nthr) {  // fixed-order sum over the warps' partials
+    for (int s = tid; s < 5 * NMO * WS; s += nthr) {  // fixed-order sum over the warps' partials
       double sum = 0;
-      for (int c = 0; c < NWARP; ++c) sum += s_part[(size_t)c * 5 * NMO * WPC + s];
+      for (int c = 0; c < NWARP; ++c) sum += s_part[(size_t)c * 5 * NMO * WS + s];
       s_stage[s] = sum;
     }
     __syncthreads();
     PHASE(7)
     // Sherman-Morrison (jqmc/jqmc_gfmc.py:5083-5141): task = (walker, row i); read phase, barrier, write phase
-    {  // N * WPC <= blockDim.x is guaranteed by launch_walker: one pass
-      double newrow[16];
+    {  // N * WPC <= blockDim.x is guaranteed by launch_walker: one pass.  All loops over electrons run to the compile-time
+       // bound NB >= N with uniform predicates, so that newrow / vvec / uvec stay in registers (no local memory)
+      constexpr int NB = 8;
+      double newrow[NB];
       const int s = tid;
       bool act = s < N * WPC;
       int wl = 0, i = 0;
@@ -767,10 +823,10 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
         const int es = (int)SMISC(12);
         double pn[NMO];
 #pragma unroll
-        for (int mo = 0; mo < NMO; ++mo) pn[mo] = s_stage[mo * WPC + wl] - SPHI(es, 0, mo);  // phi_new - phi_old
+        for (int mo = 0; mo < NMO; ++mo) pn[mo] = s_stage[mo * WS + wl] - SPHI(es, 0, mo);  // phi_new - phi_old
         if (es < N) {
           const int k = es;
-          double t[NMO], vvec[16];
+          double t[NMO], vvec[NB];
 #pragma unroll
           for (int b = 0; b < NMO; ++b) {
             double sum = 0;
@@ -779,30 +835,36 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
             t[b] = sum;
           }
           double acc = 0;
-          for (int j = 0; j < Nd; ++j) {
-            double sum = 0;
 #pragma unroll
-            for (int b = 0; b < NMO; ++b) sum = fma(t[b], SPHI(N + j, 0, b), sum);
+          for (int j = 0; j < NB; ++j) {
+            double sum = 0;
+            if (j < Nd) {
+#pragma unroll
+              for (int b = 0; b < NMO; ++b) sum = fma(t[b], SPHI(N + j, 0, b), sum);
+            } else if (j < N) {
+              const int q = j - Nd;
+#pragma unroll
+              for (int a = 0; a < NMO; ++a) sum = fma(pn[a], S.lam_u[a * S.n_unp + q], sum);
+            }
             vvec[j] = sum;
-            acc = fma(sum, SGI(j, k), acc);
-          }
-          for (int q = 0; q < S.n_unp; ++q) {
-            double sum = 0;
-#pragma unroll
-            for (int a = 0; a < NMO; ++a) sum = fma(pn[a], S.lam_u[a * S.n_unp + q], sum);
-            vvec[Nd + q] = sum;
-            acc = fma(sum, SGI(Nd + q, k), acc);
+            if (j < N) acc = fma(sum, SGI(j, k), acc);
           }
           const double invD = 1.0 / (1.0 + acc);
           const double coli = SGI(i, k);
-          for (int jp = 0; jp < N; ++jp) {
+#pragma unroll
+          for (int jp = 0; jp < NB; ++jp) {
             double vt = 0;
-            for (int j = 0; j < N; ++j) vt = fma(vvec[j], SGI(j, jp), vt);
-            newrow[jp] = SGI(i, jp) - (coli * vt) * invD;
+            if (jp < N) {
+#pragma unroll
+              for (int j = 0; j < NB; ++j)
+                if (j < N) vt = fma(vvec[j], SGI(j, jp), vt);
+              vt = SGI(i, jp) - (coli * vt) * invD;
+            }
+            newrow[jp] = vt;
           }
         } else {
           const int k = es - N;
-          double t[NMO], uvec[16];
+          double t[NMO], uvec[NB];
 #pragma unroll
           for (int a = 0; a < NMO; ++a) {
             double sum = 0;
@@ -810,34 +872,44 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
             for (int b = 0; b < NMO; ++b) sum = fma(S.lam_p[a * NMO + b], pn[b], sum);
             t[a] = sum;
           }
-          for (int ii = 0; ii < N; ++ii) {
-            double sum = 0;
 #pragma unroll
-            for (int a = 0; a < NMO; ++a) sum = fma(SPHI(ii, 0, a), t[a], sum);
+          for (int ii = 0; ii < NB; ++ii) {
+            double sum = 0;
+            if (ii < N) {
+#pragma unroll
+              for (int a = 0; a < NMO; ++a) sum = fma(SPHI(ii, 0, a), t[a], sum);
+            }
             uvec[ii] = sum;
           }
           double au_i = 0, au_k = 0;
-          for (int j = 0; j < N; ++j) {
-            au_i = fma(SGI(i, j), uvec[j], au_i);
-            au_k = fma(SGI(k, j), uvec[j], au_k);
-          }
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+            if (j < N) {
+              au_i = fma(SGI(i, j), uvec[j], au_i);
+              au_k = fma(SGI(k, j), uvec[j], au_k);
+            }
           const double invD = 1.0 / (1.0 + au_k);
-          for (int j = 0; j < N; ++j) newrow[j] = SGI(i, j) - (au_i * SGI(k, j)) * invD;
+#pragma unroll
+          for (int j = 0; j < NB; ++j) newrow[j] = j < N ? SGI(i, j) - (au_i * SGI(k, j)) * invD : 0.0;
         }
       }
       __syncthreads();
-      if (act)
-        for (int j = 0; j < N; ++j) SGI(i, j) = newrow[j];
+      if (act) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          if (j < N) SGI(i, j) = newrow[j];
+      }
     }
     __syncthreads();
     PHASE(8)
-    for (int s = tid; s < 5 * NMO * WPC; s += nthr) {
-      const int wl = s % WPC, item = s / WPC;
+    for (int s = tid; s < 5 * NMO * WS; s += nthr) {
+      const int wl = s % WS, item = s / WS;
+      if (wl >= WPC) continue;  // padding slot
       if (TAU && SMISC(14) == 0.0) continue;
       const int es = (int)SMISC(12);
-      s_phi[(es * 5 * NMO + item) * WPC + wl] = s_stage[s];
+      s_phi[(es * 5 * NMO + item) * WS + wl] = s_stage[s];
     }
-    if (tid < WPC && !(TAU && s_misc[14 * WPC + tid] == 0.0)) {
+    if (tid < WPC && !(TAU && s_misc[14 * WS + tid] == 0.0)) {
       const int wl = tid;
       const int es = (int)SMISC(12);
       SR(es, 0) = SMISC(9);
@@ -884,12 +956,12 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       const int wl = idx % WPC, it = idx / WPC, e = it / 3, c = it % 3;
       const int w = w0 + wl;
       if (w >= P.nw) continue;
-      if (e < N) P.r_up[((size_t)w * N + e) * 3 + c] = s_r[idx];
-      else P.r_dn[((size_t)w * Nd + (e - N)) * 3 + c] = s_r[idx];
+      if (e < N) P.r_up[((size_t)w * N + e) * 3 + c] = s_r[it * WS + wl];
+      else P.r_dn[((size_t)w * Nd + (e - N)) * 3 + c] = s_r[it * WS + wl];
     }
     for (int idx = tid; idx < NN2 * WPC; idx += nthr) {
       const int wl = idx % WPC, it = idx / WPC;
-      if (w0 + wl < P.nw) P.Ginv[(size_t)(w0 + wl) * NN2 + it] = s_Gi[idx];
+      if (w0 + wl < P.nw) P.Ginv[(size_t)(w0 + wl) * NN2 + it] = s_Gi[it * WS + wl];
     }
   }
 #undef PHASE
@@ -971,7 +1043,7 @@ template <bool TAU>
 int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
   const SysDev& S = h->sys;
   const int P = h->nmo_pad;
-  if (S.n_up > 16) return fail(QE_ERR_UNSUPPORTED, "more than 16 electrons per spin is not implemented in this build");
+  if (S.n_up > 8) return fail(QE_ERR_UNSUPPORTED, "the fused walker kernel holds at most 8 electrons per spin (larger systems run on the general family)");
   const int NWARP = h->walker_warps > 0 ? h->walker_warps : 16;
   const int ctas_per_sm = 16 / NWARP;
   A.off_cseg = h->b_up.off_cseg;
@@ -981,25 +1053,40 @@ int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
   const int Ne = S.n_e;
   const int n_kin = A.mode == 2 ? 0 : 6 * Ne;
   const int n_ecp = S.ecp_flag ? Ne * S.NN * S.Nv : 0;
-  const size_t per_walker = (size_t)Ne * 3 + (size_t)S.n_up * S.n_up + (size_t)Ne * 5 * P + (size_t)Ne * P + std::max(1, n_kin + n_ecp) +
-                            std::max(1, n_ecp) + (size_t)Ne * 10 + (size_t)NWARP * 5 * P + 5 * P + 16;
+  const size_t per_walker = (size_t)Ne * 3 + (size_t)S.n_up * S.n_up + (size_t)Ne * 5 * P + (size_t)Ne * P +
+                            std::max<size_t>((size_t)NWARP * 5 * P, (size_t)std::max(1, n_kin + n_ecp) + std::max(1, n_ecp)) +
+                            (S.ecp_flag ? (size_t)Ne * S.NN * (5 + S.ecp_lmax) : 1) + (size_t)Ne * 10 + 5 * P + 16;
   const size_t fixed = (size_t)h->b_up.dev.bytes + sys_bytes(S, P) + 17 * 16 + 64 + 128 + 256 + 112;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t budget = (size_t)227 * 1024 / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
   if (budget < fixed + per_walker * 8) return fail(QE_ERR_UNSUPPORTED, "system too large for the fused walker kernel (shared memory)");
-  int wpc_max = (int)std::min<size_t>(32, (budget - fixed) / (per_walker * 8));
+  // walker stride of the shared arrays: 32 (compile-time: immediate address offsets) when 32 padded slots fit, else dense
+  // (instantiated for l <= 4 bases and the GFMC_n / VMC modes only: every instantiation of this kernel costs ~1 min of nvcc)
+  // measured on B200 (water, 4096 walkers, profiles/r02_walker_history.md): padded 4.23 ms vs dense 4.37 ms per 40 projections
+  static const bool dense_env = getenv("QE_WALKER_DENSE") && atoi(getenv("QE_WALKER_DENSE")) != 0;  // tuning switch
+  const bool pad32 = !dense_env && !TAU && h->b_up.dev.lmax <= 4 && fixed + per_walker * 8 * 32 <= budget;
+  int wpc_max = pad32 ? 32 : (int)std::min<size_t>(32, (budget - fixed) / (per_walker * 8));
   wpc_max = std::max(1, std::min(wpc_max, NWARP * 32 / S.n_up));  // Sherman-Morrison: one (walker, row) task per thread
   A.wpc = h->wpc_override > 0 ? std::min(h->wpc_override, wpc_max)
                               : choose_wpc(A.nw, std::max(1, n_kin + n_ecp), sms, ctas_per_sm, wpc_max, NWARP * 32);
-  const size_t smem = fixed + per_walker * 8 * A.wpc;
+  const size_t smem = fixed + per_walker * 8 * (pad32 ? 32 : A.wpc);
   {
     LaunchScope ls_(h, kid, st);
-#define CALL3(NMO, CART, LMAX, TAU)                                                                                         \
-  do {                                                                                                                      \
-    CUDA_TRY(cudaFuncSetAttribute(k_walker<NMO, CART, LMAX, TAU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_walker<NMO, CART, LMAX, TAU><<<nblk(A.nw, A.wpc), NWARP * 32, smem, st>>>(h->b_up.dev, S, A);                          \
+#define CALL4(NMO, CART, LMAX, TAU, WS)                                                                                         \
+  do {                                                                                                                          \
+    CUDA_TRY(cudaFuncSetAttribute(k_walker<NMO, CART, LMAX, TAU, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_walker<NMO, CART, LMAX, TAU, WS><<<nblk(A.nw, A.wpc), NWARP * 32, smem, st>>>(h->b_up.dev, S, A);                          \
+  } while (0)
+#define CALL3(NMO, CART, LMAX, TAU)                                        \
+  do {                                                                     \
+    if constexpr (!(TAU) && (LMAX) == 4) {                                 \
+      if (pad32) CALL4(NMO, CART, LMAX, TAU, 32);                          \
+      else CALL4(NMO, CART, LMAX, TAU, 0);                                 \
+    } else {                                                               \
+      CALL4(NMO, CART, LMAX, TAU, 0);                                      \
+    }                                                                      \
   } while (0)
 #define CALL2(NMO, CART, LMAX) CALL3(NMO, CART, LMAX, TAU)
 #define CALL(NMO, CART)                                  \
@@ -1011,6 +1098,7 @@ int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
 #undef CALL
 #undef CALL2
 #undef CALL3
+#undef CALL4
   }
   CHECK_LAUNCH();
   return QE_OK;

@@ -507,6 +507,33 @@ class WalkerEngine:
         _lib.check(rc, "qe_gather_walkers")
         return dst_up, dst_dn
 
+    def lrdmc_record_len(self, nw: int) -> int:
+        """Doubles per rank record of the packed reconfiguration exchange (qe_lrdmc_record_len)."""
+        return int(self._lib.qe_lrdmc_record_len(self._h, int(nw)))
+
+    def lrdmc_pack(self, sums5, w, r_up, r_dn, record):
+        """record <- [sums5 | pad | w | r_up | r_dn] (this rank's contribution to the one all_gather of a branching step)."""
+        nw = w.shape[0]
+        rc = self._lib.qe_lrdmc_pack(self._h, nw, self._ptr(sums5), self._ptr(w), self._ptr(r_up), self._ptr(r_dn), self._ptr(record),
+                                     self._stream())  # fmt: skip
+        _lib.check(rc, "qe_lrdmc_pack")
+        return record
+
+    def lrdmc_reconfigure_packed(self, records, nw: int, world: int, rank: int, zeta: float):
+        """Comb + new walkers of this rank from the all-gathered records (rank order): returns (sums5 summed over ranks,
+        r_up, r_dn, n_survived, chosen_all)."""
+        chosen = torch.empty(world * nw, dtype=torch.int32, device=self.device)
+        nsurv = torch.empty(1, dtype=torch.int32, device=self.device)
+        sums = torch.empty(5, dtype=torch.float64, device=self.device)
+        dst_up = torch.empty((nw, self.n_up, 3), dtype=torch.float64, device=self.device)
+        dst_dn = torch.empty((nw, self.n_dn, 3), dtype=torch.float64, device=self.device)
+        rc = self._lib.qe_lrdmc_reconfigure_packed(
+            self._h, int(nw), int(world), int(rank), self._ptr(records), float(zeta), self._ptr(chosen), self._ptr(nsurv), self._ptr(sums),
+            self._ptr(dst_up), self._ptr(dst_dn), self._stream(),
+        )  # fmt: skip
+        _lib.check(rc, "qe_lrdmc_reconfigure_packed")
+        return sums, dst_up, dst_dn, nsurv, chosen
+
     def launch_count(self) -> int:
         return int(self._lib.qe_launch_count(self._h))
 

@@ -8,8 +8,8 @@ statistics as the reference; the per-step device work is done by ``WalkerEngine`
     for each branching step (jqmc_gfmc.py:5774-6417)
         w = 1;  projection_n  -> qe_lrdmc_project     (nmpm lattice-regularised projections per walker)
         V_elements_n          -> qe_geminal_init + qe_lrdmc_velements   (e_L = V_diag + V_nondiag)
-        weighted sums         -> qe_lrdmc_collect + all_reduce(SUM) of 5 doubles            (:5971-6051)
-        reconfiguration       -> all_gather(w, r_up, r_dn) + qe_lrdmc_branch + qe_gather_walkers (:6059-6318)
+        weighted sums         -> qe_lrdmc_collect                                             (:5971-6051)
+        reconfiguration       -> qe_lrdmc_pack + ONE all_gather + qe_lrdmc_reconfigure_packed (:6059-6318)
         A_inv refresh         -> qe_geminal_init                                             (:6319)
         E_scf update          -> host jackknife of the stored (w, e_L) history               (:6327-6383)
 
@@ -17,8 +17,8 @@ Differences from the reference, all behind the same observable results:
 
 * the reference moves every array to the host and talks mpi4py (reduce -> rank 0, Exscan, Allgather,
   Alltoallv negotiation, Isend/Irecv of the migrating walkers); here the walker state never leaves the
-  GPU: one ``all_reduce`` of 5 doubles and one ``all_gather`` per array over NCCL/NVLink, and every rank
-  evaluates the identical comb redundantly (no negotiation round);
+  GPU: ONE ``all_gather`` of a packed record [5 sums | w | r_up | r_dn] per branching over NCCL/NVLink (persistent
+  buffers), and every rank evaluates the identical comb redundantly (no negotiation round);
 * the comb offset ``zeta`` is rank 0's ``np.random.random()`` after ``np.random.seed(mcmc_seed)`` at the top of
   ``run`` (:4669, :5948-5952); every rank replays that stream locally instead of receiving a broadcast;
 * the per-step averages are all-reduced, so every rank stores them (the reference keeps them on rank 0 only).
@@ -29,6 +29,7 @@ Differences from the reference, all behind the same observable results:
     weighted sums  sum w, sum w e_L, sum w e_L^2 (no division by V_diag - E_scf, :1929-1932) -> qe_lrdmc_collect
     reconfiguration, A_inv refresh as above; the mean projection count of the rank is stored per step (:2095, 2271)
 
+Restart: ``save_to_hdf5`` / ``load_from_hdf5`` in jQMC's checkpoint layout (jqmc_b200/checkpoint.py).
 Out of scope: atomic forces (``comput_position_deriv``).
 """
 
@@ -84,12 +85,14 @@ class _GFMC:
         self._alat = float(alat)
         self._random_discretized_mesh = bool(random_discretized_mesh)
         self._non_local_move = non_local_move
+        self._comput_position_deriv = bool(comput_position_deriv)
         rank, _ = _rank_size()
         self._mpi_seed = self._mcmc_seed * (rank + 1)
         self.engine = engine if engine is not None else WalkerEngine(hamiltonian_data)
         dev = self.engine.device
         keys = rng_host.split(rng_host.PRNGKey(self._mpi_seed), self._num_walkers)
         self._keys = torch.from_numpy(keys).to(dev)
+        self._keys_init = np.array(keys, copy=True)  # jax_PRNG_key_list_init of the reference (checkpoint field)
         np.random.seed(self._mpi_seed % (2**32))
         gem = hamiltonian_data.wavefunction_data.geminal_data
         cp = hamiltonian_data.coulomb_potential_data
@@ -154,17 +157,97 @@ class _GFMC:
     def e_L2(self):
         return np.asarray(self._stored_e_L2)[self._num_gfmc_collect_steps :]
 
+    # walker state as NumPy arrays, like the reference's properties (the device tensors stay private: `_r_up`, `_r_dn`, `_keys`)
     @property
-    def latest_r_up_carts(self):
-        return self._r_up
+    def latest_r_up_carts(self) -> np.ndarray:
+        return self._r_up.detach().cpu().numpy()
 
     @property
-    def latest_r_dn_carts(self):
-        return self._r_dn
+    def latest_r_dn_carts(self) -> np.ndarray:
+        return self._r_dn.detach().cpu().numpy()
 
     @property
-    def jax_PRNG_key_list(self):
-        return self._keys
+    def jax_PRNG_key_list(self) -> np.ndarray:
+        return self._keys.detach().cpu().numpy()
+
+    @property
+    def comput_position_deriv(self) -> bool:
+        return self._comput_position_deriv
+
+    # ---- restart checkpoints (jqmc_gfmc.py:377-530 GFMC_t, :4390-4548 GFMC_n; layout: jqmc_b200/checkpoint.py) ------------
+    def _driver_config(self) -> dict:
+        raise NotImplementedError
+
+    def save_to_hdf5(self, filepath: str) -> None:
+        """This rank's state as a temporary per-rank file (merged into restart.h5 by checkpoint.merge_rank_checkpoints)."""
+        from .checkpoint import save_rank_checkpoint
+
+        cfg = self._driver_config()
+        cfg.update(mcmc_counter=int(self._mcmc_counter), num_survived_walkers=int(self._num_survived_walkers),
+                   num_killed_walkers=int(self._num_killed_walkers))  # fmt: skip
+        obs = {"e_L": np.asarray(self._stored_e_L), "e_L2": np.asarray(self._stored_e_L2), "w_L": np.asarray(self._stored_w_L)}
+        if isinstance(self, GFMC_t):
+            obs["average_projection_counter"] = np.asarray(self._stored_average_projection_counter)
+        else:
+            obs["G_L"] = np.array(self._G_L) if len(self._G_L) else np.empty(0)
+            obs["G_e_L"] = np.array(self._G_e_L) if len(self._G_e_L) else np.empty(0)
+        save_rank_checkpoint(
+            filepath, driver_type=type(self).__name__, driver_config=cfg,
+            rng_state={"jax_PRNG_key_list": self.jax_PRNG_key_list, "jax_PRNG_key_list_init": np.asarray(self._keys_init),
+                       "mpi_seed": int(self._mpi_seed)},
+            walker_state={"latest_r_up_carts": self.latest_r_up_carts, "latest_r_dn_carts": self.latest_r_dn_carts},
+            observables=obs,
+        )  # fmt: skip
+
+    @classmethod
+    def load_from_hdf5(cls, filepath: str, rank: int | None = None, engine=None):
+        """Restore a driver from a merged checkpoint without calling ``__init__`` (same contract as the reference): the
+        Hamiltonian comes from the file's root, everything else from this rank's group; a following ``run`` continues the
+        chain exactly (walkers, PRNG keys, stored observables, counters)."""
+        from .checkpoint import check_checkpoint_version, load_hamiltonian_from_checkpoint, load_rank_checkpoint
+
+        if rank is None:
+            rank, _ = _rank_size()
+        check_checkpoint_version(filepath)
+        data = load_rank_checkpoint(filepath, rank)
+        cfg, rng, ws, obs = data["driver_config"], data["rng_state"], data["walker_state"], data["observables"]
+        H = load_hamiltonian_from_checkpoint(filepath)
+        obj = cls.__new__(cls)
+        obj._hamiltonian_data = H
+        obj._num_walkers = int(cfg["num_walkers"])
+        obj._num_gfmc_collect_steps = int(cfg["num_gfmc_collect_steps"])
+        obj._mcmc_seed = int(cfg["mcmc_seed"])
+        obj._alat = float(cfg["alat"])
+        obj._random_discretized_mesh = bool(cfg.get("random_discretized_mesh", True))
+        obj._non_local_move = cfg.get("non_local_move", "tmove")
+        obj._comput_position_deriv = bool(cfg.get("comput_position_deriv", False))
+        if obj._comput_position_deriv:
+            raise NotImplementedError("atomic forces are outside the walker engine (SURVEY.md §8f)")
+        obj._restore_config(cfg)
+        obj._mpi_seed = int(rng["mpi_seed"])
+        obj.engine = engine if engine is not None else WalkerEngine(H)
+        dev = obj.engine.device
+        obj._keys = torch.from_numpy(np.ascontiguousarray(rng["jax_PRNG_key_list"]).astype(np.uint32)).to(dev)
+        obj._keys_init = np.asarray(rng.get("jax_PRNG_key_list_init", rng["jax_PRNG_key_list"])).astype(np.uint32)
+        obj._r_up = torch.from_numpy(np.ascontiguousarray(ws["latest_r_up_carts"], dtype=np.float64)).to(dev)
+        obj._r_dn = torch.from_numpy(np.ascontiguousarray(ws["latest_r_dn_carts"], dtype=np.float64)).to(dev)
+        obj._init_attributes()
+        obj._mcmc_counter = int(cfg.get("mcmc_counter", 0))
+        obj._num_survived_walkers = int(cfg.get("num_survived_walkers", 0))
+        obj._num_killed_walkers = int(cfg.get("num_killed_walkers", 0))
+
+        def get(name, default):
+            a = obs.get(name)
+            return default if a is None or np.size(a) == 0 else np.asarray(a)
+
+        obj._stored_e_L = get("e_L", np.zeros((0, 1)))
+        obj._stored_e_L2 = get("e_L2", np.zeros((0, 1)))
+        obj._stored_w_L = get("w_L", np.zeros((0, 1)))
+        obj._stored_average_projection_counter = get("average_projection_counter", np.zeros((obj._mcmc_counter,)))
+        g, ge = get("G_L", None), get("G_e_L", None)
+        obj._G_L = [g[i] for i in range(g.shape[0])] if g is not None else []
+        obj._G_e_L = [ge[i] for i in range(ge.shape[0])] if ge is not None else []
+        return obj
 
     @property
     def num_survived_walkers(self):
@@ -180,24 +263,25 @@ class _GFMC:
 
     # ---- walker reconfiguration on the device (jqmc_gfmc.py:6059-6321 == :2008-2277) -------------------
     def _reconfigure(self, w, r_up, r_dn, sums, zeta, rank, world):
+        """One branching: this rank's record [sums | w | r_up | r_dn] goes through ONE all_gather (persistent buffers, NCCL
+        over NVLink); every rank then sums the five sums in rank order, evaluates the identical comb and copies its new
+        walkers out of the gathered records.  Returns (r_up, r_dn, A_inv, n_survived, sums over all ranks)."""
         eng = self.engine
         nw = self._num_walkers
+        L = eng.lrdmc_record_len(nw)
+        buf = getattr(self, "_exchange", None)
+        if buf is None or buf[0].numel() != L or buf[1].numel() != world * L:
+            rec = torch.empty(L, dtype=torch.float64, device=eng.device)
+            buf = (rec, torch.empty(world * L, dtype=torch.float64, device=eng.device) if world > 1 else rec)
+            self._exchange = buf
+        rec, allrec = buf
+        eng.lrdmc_pack(sums, w, r_up, r_dn, rec)
         d = _dist()
         if d is not None and world > 1:
-            d.all_reduce(sums, op=d.ReduceOp.SUM)
-            w_all = torch.empty(world * nw, dtype=w.dtype, device=w.device)
-            up_all = torch.empty((world * nw,) + tuple(r_up.shape[1:]), dtype=r_up.dtype, device=r_up.device)
-            dn_all = torch.empty((world * nw,) + tuple(r_dn.shape[1:]), dtype=r_dn.dtype, device=r_dn.device)
-            d.all_gather_into_tensor(w_all, w.contiguous())
-            d.all_gather_into_tensor(up_all, r_up.contiguous())
-            if r_dn.numel():
-                d.all_gather_into_tensor(dn_all, r_dn.contiguous())
-        else:
-            w_all, up_all, dn_all = w, r_up, r_dn
-        chosen_all, n_surv = eng.lrdmc_branch(w_all, nw, zeta)
-        r_up, r_dn = eng.gather_walkers(chosen_all[rank * nw : (rank + 1) * nw], up_all, dn_all)
+            d.all_gather_into_tensor(allrec, rec)
+        sums_all, r_up, r_dn, n_surv, _ = eng.lrdmc_reconfigure_packed(allrec, nw, world, rank, zeta)
         A_inv = eng.A_inv_n(r_up, r_dn)
-        return r_up, r_dn, A_inv, n_surv
+        return r_up, r_dn, A_inv, n_surv, sums_all
 
     def _step(self, r_up, r_dn, keys, A_inv, zeta, rank, world):  # -> r_up, r_dn, keys, A_inv, sums, n_surv, extra
         raise NotImplementedError
@@ -321,12 +405,25 @@ class GFMC_n(_GFMC):
     ) -> None:
         self._nmpm = int(num_mcmc_per_measurement)
         self._E_scf = float(E_scf)
+        self._epsilon_PW, self._use_swct = float(epsilon_PW), bool(use_swct)
         self._setup(hamiltonian_data, num_walkers, num_gfmc_collect_steps, mcmc_seed, alat, random_discretized_mesh, non_local_move,
                     comput_position_deriv, engine)  # fmt: skip
 
     @property
     def E_scf(self):
         return self._E_scf
+
+    def _driver_config(self) -> dict:  # jqmc_gfmc.py:4400-4416
+        return dict(mcmc_seed=self._mcmc_seed, num_walkers=self._num_walkers, num_mcmc_per_measurement=self._nmpm,
+                    num_gfmc_collect_steps=self._num_gfmc_collect_steps, E_scf=float(self._E_scf), alat=self._alat,
+                    random_discretized_mesh=self._random_discretized_mesh, non_local_move=self._non_local_move,
+                    comput_position_deriv=self._comput_position_deriv, epsilon_PW=float(self._epsilon_PW), use_swct=self._use_swct)  # fmt: skip
+
+    def _restore_config(self, cfg) -> None:
+        self._nmpm = int(cfg["num_mcmc_per_measurement"])
+        self._E_scf = float(cfg["E_scf"])
+        self._epsilon_PW = float(cfg.get("epsilon_PW", 0.0))
+        self._use_swct = bool(cfg.get("use_swct", False))
 
     # ---- one branching step on the device (no host synchronisation) ----------------------------------
     def _step(self, r_up, r_dn, keys, A_inv, zeta, rank, world):
@@ -339,7 +436,7 @@ class GFMC_n(_GFMC):
         )  # fmt: skip
         V_diag, V_nondiag = eng.V_elements_n(r_up, r_dn, RTs, self._non_local_move, self._alat)
         sums = eng.lrdmc_collect(w, V_diag, V_nondiag, self._E_scf)
-        r_up, r_dn, A_inv, n_surv = self._reconfigure(w, r_up, r_dn, sums, zeta, rank, world)
+        r_up, r_dn, A_inv, n_surv, sums = self._reconfigure(w, r_up, r_dn, sums, zeta, rank, world)
         return r_up, r_dn, keys, A_inv, sums, n_surv, None
 
     def _after_interval(self, i, eq_steps, n_bins):  # on-the-fly E_scf, jqmc_gfmc.py:6345-6378
@@ -369,12 +466,24 @@ class GFMC_t(_GFMC):
         engine=None,
     ) -> None:
         self._tau = float(tau)
+        self._epsilon_PW, self._use_swct = float(epsilon_PW), bool(use_swct)
         self._setup(hamiltonian_data, num_walkers, num_gfmc_collect_steps, mcmc_seed, alat, random_discretized_mesh, non_local_move,
                     comput_position_deriv, engine)  # fmt: skip
 
     @property
     def tau(self):
         return self._tau
+
+    def _driver_config(self) -> dict:  # jqmc_gfmc.py:387-401
+        return dict(mcmc_seed=self._mcmc_seed, num_walkers=self._num_walkers, num_gfmc_collect_steps=self._num_gfmc_collect_steps,
+                    tau=float(self._tau), alat=self._alat, random_discretized_mesh=self._random_discretized_mesh,
+                    non_local_move=self._non_local_move, comput_position_deriv=self._comput_position_deriv,
+                    epsilon_PW=float(self._epsilon_PW), use_swct=self._use_swct)  # fmt: skip
+
+    def _restore_config(self, cfg) -> None:
+        self._tau = float(cfg["tau"])
+        self._epsilon_PW = float(cfg.get("epsilon_PW", 0.0))
+        self._use_swct = bool(cfg.get("use_swct", False))
 
     @property
     def average_projection_counter(self):
@@ -388,5 +497,5 @@ class GFMC_t(_GFMC):
             w, r_up, r_dn, A_inv, keys, self._tau, self._random_discretized_mesh, self._non_local_move, self._alat, inplace=True
         )
         sums = eng.lrdmc_collect_t(w, e_L)
-        r_up, r_dn, A_inv, n_surv = self._reconfigure(w, r_up, r_dn, sums, zeta, rank, world)
+        r_up, r_dn, A_inv, n_surv, sums = self._reconfigure(w, r_up, r_dn, sums, zeta, rank, world)
         return r_up, r_dn, keys, A_inv, sums, n_surv, pc.to(torch.float64).mean()  # rank-local mean, as the reference (:2095)

@@ -200,6 +200,8 @@ class MCMC:
         self.__Dt = float(Dt)
         self.__epsilon_AS = float(epsilon_AS)
         self.__random_discretized_mesh = bool(random_discretized_mesh)
+        self.__use_swct = bool(use_swct)
+        self.__i_opt = 0
         rank, _ = _rank_size()
         self.__mpi_seed = mcmc_seed * (rank + 1)
         self.engine = engine if engine is not None else WalkerEngine(hamiltonian_data)
@@ -250,20 +252,86 @@ class MCMC:
 
     @property
     def dln_Psi_dc(self):
-        """{block name: array (steps, num_walkers, *block shape)} of d ln|Psi| / d parameter (jqmc_mcmc.py:300-330)."""
-        return {k: np.array(v) for k, v in self.__stored_dln.items()}
+        """{block name: array (steps, num_walkers, *block shape)} of d ln|Psi| / d parameter (jqmc_mcmc.py:300-330).  The
+        samples are kept on the device while sampling (the SR solve consumes them there); this property copies them out."""
+        return {k: self.__dln_block(k).cpu().numpy() for k in self.__stored_dln}
+
+    def __dln_block(self, name):
+        """One derivative block as a device tensor (steps, num_walkers, *block shape)."""
+        v = self.__stored_dln[name]
+        return torch.stack(v) if len(v) else torch.zeros((0, self.__num_walkers), dtype=torch.float64, device=self.engine.device)
+
+    # walker state as NumPy arrays, like the reference's properties (the device tensors stay private)
+    @property
+    def latest_r_up_carts(self) -> np.ndarray:
+        return self.__r_up.detach().cpu().numpy()
 
     @property
-    def latest_r_up_carts(self):
-        return self.__r_up
+    def latest_r_dn_carts(self) -> np.ndarray:
+        return self.__r_dn.detach().cpu().numpy()
 
     @property
-    def latest_r_dn_carts(self):
-        return self.__r_dn
+    def jax_PRNG_key_list(self) -> np.ndarray:
+        return self.__keys.detach().cpu().numpy()
 
-    @property
-    def jax_PRNG_key_list(self):
-        return self.__keys
+    # ---- restart checkpoints (jqmc_mcmc.py:3912-4120; layout: jqmc_b200/checkpoint.py) ----------------------------------
+    def save_to_hdf5(self, filepath: str) -> None:
+        from .checkpoint import save_rank_checkpoint
+
+        cfg = dict(mcmc_seed=int(self.__mcmc_seed), num_walkers=self.__num_walkers, num_mcmc_per_measurement=self.__nmpm, Dt=self.__Dt,
+                   epsilon_AS=self.__epsilon_AS, comput_log_WF_param_deriv=self.__comput_log_WF_param_deriv, comput_e_L_param_deriv=False,
+                   comput_position_deriv=False, random_discretized_mesh=self.__random_discretized_mesh, use_swct=self.__use_swct,
+                   mcmc_counter=int(self.__mcmc_counter), accepted_moves=int(self.__accepted_moves),
+                   rejected_moves=int(self.__rejected_moves), i_opt=int(self.__i_opt))  # fmt: skip
+        obs = {"e_L": self.e_L, "e_L2": self.e_L2, "w_L": self.w_L, "param_grads": self.dln_Psi_dc}
+        save_rank_checkpoint(
+            filepath, driver_type="MCMC", driver_config=cfg,
+            rng_state={"jax_PRNG_key_list": self.jax_PRNG_key_list, "mpi_seed": int(self.__mpi_seed)},
+            walker_state={"latest_r_up_carts": self.latest_r_up_carts, "latest_r_dn_carts": self.latest_r_dn_carts},
+            observables=obs,
+        )  # fmt: skip
+
+    @classmethod
+    def load_from_hdf5(cls, filepath: str, rank: int | None = None, engine: WalkerEngine | None = None) -> "MCMC":
+        """Restore a sampler from a merged checkpoint (no ``__init__`` call, as in the reference): a following ``run``
+        continues the chain exactly."""
+        from .checkpoint import check_checkpoint_version, load_hamiltonian_from_checkpoint, load_rank_checkpoint
+
+        if rank is None:
+            rank, _ = _rank_size()
+        check_checkpoint_version(filepath)
+        data = load_rank_checkpoint(filepath, rank)
+        cfg, rng, ws, obs = data["driver_config"], data["rng_state"], data["walker_state"], data["observables"]
+        if cfg.get("comput_e_L_param_deriv") or cfg.get("comput_position_deriv"):
+            raise NotImplementedError("e_L parameter derivatives / position derivatives are outside the walker engine (SURVEY.md §8f)")
+        H = load_hamiltonian_from_checkpoint(filepath)
+        obj = cls.__new__(cls)
+        obj._MCMC__comput_log_WF_param_deriv = bool(cfg.get("comput_log_WF_param_deriv", False))
+        obj.hamiltonian_data = H
+        obj._MCMC__mcmc_seed = int(cfg["mcmc_seed"])
+        obj._MCMC__num_walkers = int(cfg["num_walkers"])
+        obj._MCMC__nmpm = int(cfg["num_mcmc_per_measurement"])
+        obj._MCMC__Dt = float(cfg["Dt"])
+        obj._MCMC__epsilon_AS = float(cfg["epsilon_AS"])
+        obj._MCMC__random_discretized_mesh = bool(cfg.get("random_discretized_mesh", True))
+        obj._MCMC__use_swct = bool(cfg.get("use_swct", True))
+        obj._MCMC__mpi_seed = int(rng["mpi_seed"])
+        obj.engine = engine if engine is not None else WalkerEngine(H)
+        dev = obj.engine.device
+        obj._MCMC__keys = torch.from_numpy(np.ascontiguousarray(rng["jax_PRNG_key_list"]).astype(np.uint32)).to(dev)
+        obj._MCMC__r_up = torch.from_numpy(np.ascontiguousarray(ws["latest_r_up_carts"], dtype=np.float64)).to(dev)
+        obj._MCMC__r_dn = torch.from_numpy(np.ascontiguousarray(ws["latest_r_dn_carts"], dtype=np.float64)).to(dev)
+        obj._MCMC__init_attributes()
+        obj._MCMC__mcmc_counter = int(cfg.get("mcmc_counter", 0))
+        obj._MCMC__accepted_moves = int(cfg.get("accepted_moves", 0))
+        obj._MCMC__rejected_moves = int(cfg.get("rejected_moves", 0))
+        obj._MCMC__i_opt = int(cfg.get("i_opt", 0))
+        for name, store in (("e_L", "_MCMC__stored_e_L"), ("e_L2", "_MCMC__stored_e_L2"), ("w_L", "_MCMC__stored_w_L")):
+            a = obs.get(name)
+            setattr(obj, store, [row for row in np.asarray(a)] if a is not None and np.size(a) else [])
+        for name, a in (obs.get("param_grads") or {}).items():
+            obj._MCMC__stored_dln[name] = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in np.asarray(a)]
+        return obj
 
     @property
     def accepted_moves(self):
@@ -303,7 +371,7 @@ class MCMC:
             # one device->host read per step (the reference does three: jqmc_mcmc.py:720, 739, 747)
             if self.__comput_log_WF_param_deriv:  # jqmc_mcmc.py:854-876
                 for name, g in eng.grad_ln_psi_params_fast(r_up, r_dn, Ginv).items():
-                    self.__stored_dln.setdefault(name, []).append(g.cpu().numpy())
+                    self.__stored_dln.setdefault(name, []).append(g)  # stays on the device: the SR solve consumes it there
             pack = torch.stack([e_L, w_L, acc.to(torch.float64), rej.to(torch.float64)]).cpu().numpy()
             # rank 0's stop decision (max_time / external stop flag), shared by all ranks; the interrupted step is not
             # counted and its observables are dropped, as in the reference (jqmc_mcmc.py:930-967, 978-985)
@@ -344,13 +412,17 @@ class MCMC:
         flattened row-major (jqmc_mcmc.py:1372-1420).  ``blocks``: optional list of block names (default: all stored)."""
         if not self.__stored_dln:
             raise ValueError("no parameter derivatives stored: construct MCMC with comput_log_WF_param_deriv=True")
+        O = self._dln_WF_device(num_mcmc_warmup_steps, blocks).cpu().numpy()
+        return O if chosen_param_index is None else O[:, :, chosen_param_index]
+
+    def _dln_WF_device(self, num_mcmc_warmup_steps: int = 0, blocks=None):
+        """The same matrix as a device tensor (no host round trip: the path of get_sr_direction / run_optimize)."""
         names = [n for n in self.BLOCK_ORDER if n in self.__stored_dln and (blocks is None or n in blocks)]
         parts = []
         for n in names:
-            a = np.array(self.__stored_dln[n])
+            a = self.__dln_block(n)
             parts.append(a.reshape(a.shape[0], a.shape[1], -1))
-        O = np.concatenate(parts, axis=2)[num_mcmc_warmup_steps:]
-        return O if chosen_param_index is None else O[:, :, chosen_param_index]
+        return torch.cat(parts, dim=2)[num_mcmc_warmup_steps:]
 
     def get_gF(self, num_mcmc_warmup_steps: int = 50, num_mcmc_bin_blocks: int = 10, chosen_param_index=None, blocks=None):
         """Generalised forces f_k = -2 (<e_L O_k> - <e_L><O_k>) with jackknife error bars over (bins x walkers) samples of all
@@ -368,7 +440,7 @@ class MCMC:
         from .sr import sr_natural_gradient
 
         dev = self.engine.device
-        O = torch.from_numpy(self.get_dln_WF(num_mcmc_warmup_steps, None, blocks)).to(dev)
+        O = self._dln_WF_device(num_mcmc_warmup_steps, blocks)
         w = torch.from_numpy(self.w_L[num_mcmc_warmup_steps:]).to(dev)
         e = torch.from_numpy(self.e_L[num_mcmc_warmup_steps:]).to(dev)
         theta, info = sr_natural_gradient(w, e, O, epsilon=epsilon, use_cg=use_cg, cg_max_iter=cg_max_iter, cg_tol=cg_tol)
@@ -398,7 +470,7 @@ class MCMC:
             jd, gem = wf.jastrow_data, wf.geminal_data
             off = 0
             for n in blocks:
-                shape = np.array(self.__stored_dln[n][0]).shape[1:]
+                shape = tuple(self.__stored_dln[n][0].shape[1:])
                 size = int(np.prod(shape)) if shape else 1
                 step = delta * theta[off : off + size].reshape(shape)
                 off += size

@@ -26,8 +26,12 @@ def _dist():
     return dist if dist.is_available() and dist.is_initialized() else None
 
 
+_COLLECTIVE_BYTES = [0]  # payload of the collectives issued since the last sr_natural_gradient call started (reported in info)
+
+
 def _allreduce(t):
     d = _dist()
+    _COLLECTIVE_BYTES[0] += t.numel() * t.element_size()
     if d is not None:
         d.all_reduce(t, op=d.ReduceOp.SUM)
     return t
@@ -38,6 +42,7 @@ def _allgather_cat(t):
     d = _dist()
     if d is None:
         return t
+    _COLLECTIVE_BYTES[0] += t.numel() * t.element_size() * d.get_world_size()
     parts = [torch.empty_like(t) for _ in range(d.get_world_size())]
     d.all_gather(parts, t.contiguous())
     return torch.cat(parts)
@@ -69,6 +74,7 @@ def sr_natural_gradient(w, e_L, O, epsilon=1e-3, use_cg=False, cg_max_iter=10000
                         force_dual=None):  # fmt: skip
     """theta[K] (see module docstring).  w[n], e_L[n], O[n, K]: this rank's samples (any leading shape is flattened; torch
     tensors on one device, fp64).  Returns (theta, info) with info = dict(f, diag_S, method, cg_iterations, frozen)."""
+    _COLLECTIVE_BYTES[0] = 0
     w = w.reshape(-1).to(torch.float64)
     e_L = e_L.reshape(-1).to(torch.float64)
     O = O.reshape(w.numel(), -1).to(torch.float64)
@@ -119,4 +125,5 @@ def sr_natural_gradient(w, e_L, O, epsilon=1e-3, use_cg=False, cg_max_iter=10000
         theta = _allreduce(X @ y[lo : lo + n_local])
     theta = theta / torch.sqrt(diag_S)
     theta = torch.where(frozen, torch.zeros_like(theta), theta)
-    return theta, dict(f=f, diag_S=diag_S, method=method, cg_iterations=iters, frozen=int(frozen.sum()), n_total=n_total)
+    return theta, dict(f=f, diag_S=diag_S, method=method, cg_iterations=iters, frozen=int(frozen.sum()), n_total=n_total,
+                       allreduce_bytes=_COLLECTIVE_BYTES[0])

@@ -101,3 +101,31 @@ class OracleEngine:
     def gather_walkers(self, chosen_local, src_up, src_dn):
         idx = torch.as_tensor(_np(chosen_local).astype(np.int64))
         return src_up[idx].clone(), src_dn[idx].clone()
+
+    # ---- packed reconfiguration exchange (mirrors qe_lrdmc_record_len / qe_lrdmc_pack / qe_lrdmc_reconfigure_packed) ----------
+    def lrdmc_record_len(self, nw):
+        return 8 + nw * (1 + 3 * self.n_up + 3 * self.n_dn)
+
+    def lrdmc_pack(self, sums5, w, r_up, r_dn, record):
+        nw = w.shape[0]
+        record[:5] = torch.as_tensor(_np(sums5))
+        record[5:8] = 0.0
+        record[8 : 8 + nw] = torch.as_tensor(_np(w))
+        o = 8 + nw
+        record[o : o + nw * 3 * self.n_up] = torch.as_tensor(_np(r_up)).reshape(-1)
+        o += nw * 3 * self.n_up
+        record[o : o + nw * 3 * self.n_dn] = torch.as_tensor(_np(r_dn)).reshape(-1)
+        return record
+
+    def lrdmc_reconfigure_packed(self, records, nw, world, rank, zeta):
+        L = self.lrdmc_record_len(nw)
+        rec = _np(records).reshape(world, L)
+        sums = np.zeros(5)
+        for r in range(world):  # rank order, like the device kernel and the reference's MPI reduce
+            sums = sums + rec[r, :5]
+        chosen, ns = OD.lrdmc_branch_indices([rec[r, 8 : 8 + nw] for r in range(world)], zeta)
+        pu, pd = 3 * self.n_up, 3 * self.n_dn
+        up = rec[:, 8 + nw : 8 + nw + nw * pu].reshape(world * nw, self.n_up, 3)
+        dn = rec[:, 8 + nw + nw * pu :].reshape(world * nw, self.n_dn, 3)
+        mine = chosen[rank * nw : (rank + 1) * nw]
+        return self._t(sums), self._t(up[mine]), self._t(dn[mine]), torch.tensor([ns], dtype=torch.int32), torch.from_numpy(chosen)

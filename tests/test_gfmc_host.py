@@ -78,9 +78,9 @@ def _check(g, hist, ranks, rank):
     np.testing.assert_allclose(g.e_L[:, 0], [h[1] for h in hist][1:], rtol=1e-12)
     np.testing.assert_allclose(g.e_L2[:, 0], [h[2] for h in hist][1:], rtol=1e-12)
     assert g.num_survived_walkers == sum(h[3] for h in hist)
-    np.testing.assert_array_equal(g.latest_r_up_carts.numpy(), ranks[rank]["r_up"])
-    np.testing.assert_array_equal(g.latest_r_dn_carts.numpy(), ranks[rank]["r_dn"])
-    assert [tuple(int(x) for x in k) for k in g.jax_PRNG_key_list.numpy()] == ranks[rank]["keys"]
+    np.testing.assert_array_equal(g.latest_r_up_carts, ranks[rank]["r_up"])
+    np.testing.assert_array_equal(g.latest_r_dn_carts, ranks[rank]["r_dn"])
+    assert [tuple(int(x) for x in k) for k in g.jax_PRNG_key_list] == ranks[rank]["keys"]
 
 
 def test_gfmc_n_single_rank():
@@ -99,8 +99,8 @@ def _worker(rank, world, port, q, kind="n"):
     try:
         H = _system()
         g = _driver_run(H) if kind == "n" else _driver_run_t(H)
-        q.put((rank, g.bare_w_L.copy(), g.e_L.copy(), g.e_L2.copy(), g.num_survived_walkers, g.latest_r_up_carts.numpy().copy(),
-               g.latest_r_dn_carts.numpy().copy(), g.jax_PRNG_key_list.numpy().copy()))  # fmt: skip
+        q.put((rank, g.bare_w_L.copy(), g.e_L.copy(), g.e_L2.copy(), g.num_survived_walkers, g.latest_r_up_carts.copy(),
+               g.latest_r_dn_carts.copy(), g.jax_PRNG_key_list.copy()))  # fmt: skip
     finally:
         dist.destroy_process_group()
 

@@ -417,9 +417,9 @@ def test_gfmc_t_driver_matches_oracle_loop():
     np.testing.assert_allclose(g.e_L[:, 0], [h[1] for h in hist][1:], rtol=1e-9)
     np.testing.assert_allclose(g.average_projection_counter, ranks[0]["pc"])
     assert g.num_survived_walkers == sum(h[3] for h in hist)
-    np.testing.assert_allclose(g.latest_r_up_carts.cpu().numpy(), ranks[0]["r_up"], rtol=0, atol=1e-11)
-    np.testing.assert_allclose(g.latest_r_dn_carts.cpu().numpy(), ranks[0]["r_dn"], rtol=0, atol=1e-11)
-    assert [tuple(int(x) for x in k) for k in g.jax_PRNG_key_list.cpu().numpy()] == ranks[0]["keys"]
+    np.testing.assert_allclose(g.latest_r_up_carts, ranks[0]["r_up"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(g.latest_r_dn_carts, ranks[0]["r_dn"], rtol=0, atol=1e-11)
+    assert [tuple(int(x) for x in k) for k in g.jax_PRNG_key_list] == ranks[0]["keys"]
 
 
 def test_gfmc_t_driver_water_runs(water):
@@ -488,9 +488,9 @@ def test_gfmc_n_driver_matches_oracle_loop():
     np.testing.assert_allclose(g.bare_w_L[:, 0], [h[0] for h in hist], rtol=1e-9)
     np.testing.assert_allclose(g.e_L[:, 0], [h[1] for h in hist][1:], rtol=1e-9)
     assert g.num_survived_walkers == sum(h[3] for h in hist)
-    np.testing.assert_allclose(g.latest_r_up_carts.cpu().numpy(), ranks[0]["r_up"], rtol=0, atol=1e-11)
-    np.testing.assert_allclose(g.latest_r_dn_carts.cpu().numpy(), ranks[0]["r_dn"], rtol=0, atol=1e-11)
-    assert [tuple(int(x) for x in k) for k in g.jax_PRNG_key_list.cpu().numpy()] == ranks[0]["keys"]
+    np.testing.assert_allclose(g.latest_r_up_carts, ranks[0]["r_up"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(g.latest_r_dn_carts, ranks[0]["r_dn"], rtol=0, atol=1e-11)
+    assert [tuple(int(x) for x in k) for k in g.jax_PRNG_key_list] == ranks[0]["keys"]
 
 
 def test_gfmc_n_driver_water_runs(water):

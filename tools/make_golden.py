@@ -24,6 +24,10 @@ FILES = [
     "N2_ecp_ccpvtz_cart.h5",
     "H_ecp_ccpvqz.h5",
     "H2_ae_ccpvqz.h5",
+    # multi-channel ccECPs (several non-local channels, heavier atoms, more electrons than the register kernels hold)
+    "Cl2_ecp_ccpvtz_cart.h5",
+    "CuBr_ecp_ccpvtz_cart.h5",
+    "Ti2_ecp_ccpvtz_cart.h5",
 ]
 
 
