@@ -407,7 +407,7 @@ def run_gpu(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     H = make_hamiltonian(args.config)
-    eng = WalkerEngine(H)
+    eng = WalkerEngine(H, precision=args.precision)
     nw = args.walkers
     e_scf = _e_scf(args.config)
     r_up_h, r_dn_h, keys_h = init_walkers(H, nw, SEED * (rank + 1))
@@ -661,9 +661,10 @@ def run_gpu(args, rank, local_rank, world):
             coll = "VMC: no data-path collective; SR solve: all_reduce of K-vectors (and of the K x K / sample-space matrix)"
         line = dict(
             metric=cfg["metric"], value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=n_warm,
-            ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+            ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="f64" if args.precision == "full" else "mixed (fp32 zones ao_eval, jastrow_eval, jastrow_ratio; fp64 elsewhere)", data="synthetic",
             config=dict(
-                workload=cfg["workload"], baseline_config_index=cfg["baseline"], walkers_per_gpu=nw, nmpm=NMPM, Dt=DT,
+                workload=cfg["workload"], precision=args.precision, baseline_config_index=cfg["baseline"], walkers_per_gpu=nw, nmpm=NMPM, Dt=DT,
                 epsilon_AS=EPS_AS, alat=ALAT, non_local_move=NLM, E_scf=e_scf, Nv=6, NN=1,
                 parallelism=f"walkers sharded over {world} rank(s); {coll}",
                 l2="flushed between steps (256 MiB memset outside the per-step CUDA-event pairs)",
@@ -706,6 +707,8 @@ def main():
     ap.add_argument("--config", default="water_jsd", choices=sorted(CONFIGS))
     ap.add_argument("--walkers", type=int, default=None, help="walkers per GPU (default: per config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--precision", default="full", choices=["full", "mixed"],
+                    help="mixed = the reference's mixed-precision mode (fp32 AO values / Jastrow ratios); reported with dtype \"mixed\", never the headline")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.steps is None:

@@ -79,12 +79,30 @@ typedef struct {
   const int32_t* ecp_max_ang_mom_plus_1; /* [n_atom]                                                */
   int32_t Nv;                     /* quadrature points: 4, 6, 12 or 18 (jqmc/_setting.py:46)        */
   int32_t NN;                     /* nearest nuclei for the non-local ECP (jqmc/_setting.py:47)     */
+  int32_t precision;              /* 0: 'full' (every zone fp64, default); 1: 'mixed' (jqmc/_precision.py:345-374): AO values
+                                     (zone ao_eval) and Jastrow values / ratios (jastrow_eval, jastrow_ratio) in fp32 with r - R
+                                     formed in fp64 first, everything else -- MO contraction, determinant algebra, gradients
+                                     and Laplacians, potentials, assembly -- in fp64.  Honoured by the register kernel family
+                                     (bases with l <= 4); the general family evaluates every zone in fp64.              */
 } qe_system_desc;
 
 /* Build device tables for one Hamiltonian on the current CUDA device.  Rebuild whenever
  * hamiltonian_data changes (e.g. every optimisation step). */
 int qe_create(const qe_system_desc* desc, qe_engine** out);
 void qe_destroy(qe_engine* h);
+
+/* Native input path: the same engine built straight from jQMC's HDF5 files -- `hamiltonian_data.h5` (the
+ * dataclass tree of jqmc/hamiltonians.py:369-573 at the root: group = "" or "/") or a restart checkpoint (`restart.h5`,
+ * group "hamiltonian_data"; jqmc/_checkpoint.py:1-30) -- without the Python stack; the HDF5 subset reader is part of the
+ * library (no libhdf5).  Nv / NN / precision as in qe_system_desc.
+ * qe_hdf5_summary parses the same tree without touching the device: counts16 = {n_atom, n_up, n_dn, n_ao, n_prim, n_mo,
+ * cartesian, n_ecp, ecp_flag, j1_type, j2_type, j3_flag, n_ao_j3, n_mo_j3, 0, 0}, checks8 = position-weighted sums of
+ * {positions, effective charges, exponents, coefficients, mo_coefficients, lambda_matrix, ECP exponents, j_matrix}.
+ * qe_hdf5_read_walkers reads rank `rank`'s walkers of a restart checkpoint into HOST buffers (r_up_host == NULL: only *nw). */
+int qe_create_from_hdf5(const char* path, const char* group, int Nv, int NN, int precision, qe_engine** out);
+int qe_hdf5_summary(const char* path, const char* group, int64_t* counts16, double* checks8);
+int qe_hdf5_read_walkers(const char* path, int rank, int capacity_walkers, int n_up, int n_dn, int* nw, double* r_up_host,
+                         double* r_dn_host, uint32_t* keys_host);
 const char* qe_last_error(void);
 /* Library/ABI version and whether it was compiled for sm_100a. */
 int qe_version(void);
@@ -108,6 +126,16 @@ int qe_rotation(qe_engine* h, int nw, const uint32_t* keys, double* RT, void* st
  * (jqmc/wavefunction.py:1141-1207), V_parts[nw,4] = {bare Coulomb, ECP local, ECP non-local, 0}. */
 int qe_local_energy(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT,
                     const double* Ginv, double* e_L, double* T_elem, double* V_parts, void* stream);
+
+/* Position derivatives (atomic forces; the reference: jax.grad of compute_local_energy, jqmc/jqmc_mcmc.py:749-790, 4744-4746).
+ * The engine differentiates by central finite differences of qe_local_energy / qe_ln_wavefunction on the device
+ * (jqmc_b200/forces.py).  Automatic differentiation treats the nearest-nucleus assignment of the non-local ECP as a constant;
+ * to do the same, qe_nearest_nuclei returns that assignment at the base point -- nn_index[nw, n_up + n_dn, NN] (int32) -- and
+ * qe_local_energy_frozen evaluates e_L at displaced points with it (register kernel family only; nn_index may be NULL for
+ * all-electron systems). */
+int qe_nearest_nuclei(qe_engine* h, int nw, const double* r_up, const double* r_dn, int32_t* nn_index, void* stream);
+int qe_local_energy_frozen(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,
+                           const int32_t* nn_index, double* e_L, void* stream);
 
 /* _jit_vmap_as_reg_fast (jqmc/determinant.py:1223-1260, jqmc_mcmc.py:4739). */
 int qe_as_factor(qe_engine* h, int nw, const double* G, const double* Ginv, double* R_AS, void* stream);

@@ -63,6 +63,7 @@ class qe_system_desc(C.Structure):
         ("ecp_max_ang_mom_plus_1", i32p),
         ("Nv", C.c_int32),
         ("NN", C.c_int32),
+        ("precision", C.c_int32),
     ]
 
 
@@ -70,6 +71,9 @@ EXPORTS = {
     # name: (restype, argtypes)
     "qe_create": (C.c_int, [C.POINTER(qe_system_desc), C.POINTER(C.c_void_p)]),
     "qe_destroy": (None, [C.c_void_p]),
+    "qe_create_from_hdf5": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "qe_hdf5_summary": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int64), f64p]),
+    "qe_hdf5_read_walkers": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, f64p, f64p, C.POINTER(C.c_uint32)]),
     "qe_last_error": (C.c_char_p, []),
     "qe_version": (C.c_int, []),
     "qe_geminal_init": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_void_p]),
@@ -79,6 +83,8 @@ EXPORTS = {
     ),
     "qe_rotation": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qe_local_energy": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_void_p]),
+    "qe_nearest_nuclei": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_void_p]),
+    "qe_local_energy_frozen": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_void_p]),
     "qe_as_factor": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_void_p]),
     "qe_ln_wavefunction": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_void_p]),
     "qe_eval_orbitals": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -51,6 +51,8 @@ struct HostBasis {
   int n_chunk = 1;   // balanced shell-granular chunks of the basis (deterministic partial sums)
   int off_cseg = 0;  // byte offset of the chunk segment list (int4, same format as the group list) in the blob
   int off_cbeg = 0;  // byte offset of chunk_begin[n_chunk+1] (first segment of each chunk)
+  int chunk_warp[32] = {0};  // chunk evaluated by warp w of the Metropolis kernel: warps that share an SM sub-partition (w mod 4)
+                             // get chunks of the same angular momentum, i.e. the same code (instruction-cache locality)
   bool present = false;
 };
 
@@ -120,6 +122,7 @@ struct qe_engine {
   bool fused = true;  // qe_local_energy uses the fused walker kernel when the system fits
   int wpc_override = 0;  // walkers per CTA of the fused walker kernel (0 = automatic)
   long long* phase_clk = nullptr;  // optional per-phase cycle counters of the fused walker kernel (qe_phase_clocks)
+  bool mixed = false;     // precision mode 'mixed' (qe_system_desc.precision = 1): fp32 AO values and Jastrow ratios in the register kernels
   bool gemm_ref = false;  // general family: plain DFMA GEMM instead of the tensor-core kernel (qe_set_gemm_reference)
   int wide_slice = 0;     // general family: walkers per slice of a call, 0 = automatic (qe_set_wide_slice)
   int walker_warps = 0;  // warps per CTA of the fused walker kernel (0 = 16: one CTA per SM; 8: two CTAs per SM; 4: four)
@@ -398,6 +401,34 @@ __device__ __forceinline__ double jastrow_single_m(const SysDev& S, const Pos& p
       J0 += j2_fm(S.j2_type, S.j2_a, inv2a, ra * mrsqrt(ra));
     }
     J += J0 + J1;
+  }
+  return J;
+}
+
+// Mixed-precision mode (jqmc/_precision.py:345-374): zones `jastrow_eval` / `jastrow_ratio` in fp32.  The coordinate
+// differences are formed in fp64 and then rounded (:61-76); distances, the J1 / J2 functions and their sum run in float.
+template <class Pos>
+__device__ __forceinline__ float jastrow_single_f32(const SysDev& S, const Pos& pos, int e, double x, double y, double z) {
+  float J = 0.0f;
+  if (S.j1_type) {
+    const float a = (float)S.j1_a, inv2a = 1.0f / (2.0f * a);
+    for (int k = 0; k < S.n_atom; ++k) {
+      const float dx = (float)(x - S.Rn[3 * k]), dy = (float)(y - S.Rn[3 * k + 1]), dz = (float)(z - S.Rn[3 * k + 2]);
+      const float d = sqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1.0e-37f));
+      const float A = (float)S.j1_A[k], c = (float)S.j1_c[k];
+      J += S.j1_type == 1 ? -A * (1.0f - expf(-a * c * d)) * inv2a : -0.5f * A * d / (1.0f + a * c * d);
+    }
+  }
+  if (S.j2_type) {
+    const float a = (float)S.j2_a, inv2a = 1.0f / (2.0f * a);
+    for (int j = 0; j < S.n_e; ++j) {
+      if (j == e) continue;
+      double xj, yj, zj;
+      pos.get(j, xj, yj, zj);
+      const float dx = (float)(x - xj), dy = (float)(y - yj), dz = (float)(z - zj);
+      const float d = sqrtf(fmaxf(dx * dx + dy * dy + dz * dz, 1.0e-37f));
+      J += S.j2_type == 1 ? 0.5f * d / (1.0f + a * d) : (1.0f - expf(-a * d)) * inv2a;
+    }
   }
   return J;
 }

@@ -32,6 +32,7 @@ struct BasisDev {
   int nmo_pad;                // MO accumulators per thread (4, 8 or 16); C rows are zero-padded to this
   int off_seg, off_sh, off_pr, off_C, off_C2, off_rowao, off_rowscale, off_Rn;  // byte offsets into the blob (16-aligned)
   int off_pr2, off_et;        // value-sweep primitive table {-exponent * 32/ln2, coefficient}; 2^(j/32) table of qexp_s
+  int off_prf;                // float2 {-exponent / ln2, coefficient}: value sweeps of the mixed-precision mode
   int bytes;                  // blob size (multiple of 16)
   const char* g;              // blob in global memory
 };
@@ -336,6 +337,69 @@ __device__ __forceinline__ void eval_seg_val_n(const int4* __restrict__ sh, cons
 #pragma unroll
       for (int i = 0; i < NP; ++i) v[i] = R[i] * S[i][k];
       sink.add_nw(q.z + k, v, wv[k]);
+    }
+  }
+}
+
+// ---- mixed-precision mode (jqmc/_precision.py:345-374): the `ao_eval` zone in fp32 -------------------------------------------
+// AO VALUES are evaluated in single precision -- r - R is formed in fp64 first and then rounded (jqmc/_precision.py:61-76),
+// exponentials through exp2f -- and handed to the sink in fp64: the AO -> MO contraction (zone `mo_eval`) stays in double
+// precision, exactly the reference's split.  Gradients / Laplacians (zone `ao_grad_lap`) are never evaluated here.
+template <class A, int NP, class Sink>
+__device__ __forceinline__ void eval_seg_val_n_f32(const int4* __restrict__ sh, const float2* __restrict__ prf, int sb, int se,
+                                                   const float* __restrict__ dx, const float* __restrict__ dy,
+                                                   const float* __restrict__ dz, const float* __restrict__ r2, Sink& sink) {
+  float S[NP][A::NF];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) A::template val<float>(dx[i], dy[i], dz[i], S[i]);
+  for (int s = sb; s < se; ++s) {
+    const int4 q = sh[s];
+    double wv[A::NF];
+    sink.template prefetch<A::NF>(q.z, wv);
+    float R[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) R[i] = 0.0f;
+    for (int p = q.x; p < q.y; ++p) {
+      const float2 a = prf[p];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) R[i] = fmaf(a.y, exp2f(a.x * r2[i]), R[i]);
+    }
+#pragma unroll
+    for (int k = 0; k < A::NF; ++k) {
+      double v[NP];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) v[i] = (double)(R[i] * S[i][k]);
+      sink.add_nw(q.z + k, v, wv[k]);
+    }
+  }
+}
+template <bool CART, int LMAX, int NP, class Sink>
+__device__ __forceinline__ void eval_val_n_f32(const char* __restrict__ tab, const BasisDev& B, int off_list, const double* __restrict__ px,
+                                               const double* __restrict__ py, const double* __restrict__ pz, int gb, int ge,
+                                               Sink& sink) {
+  const int4* seg = (const int4*)(tab + off_list);
+  const int4* sh = (const int4*)(tab + B.off_sh);
+  const float2* pr = (const float2*)(tab + B.off_prf);
+  const double* Rn = (const double*)(tab + B.off_Rn);
+  for (int g = gb; g < ge; ++g) {
+    const int4 q = seg[g];
+    const double X = Rn[3 * q.x], Y = Rn[3 * q.x + 1], Z = Rn[3 * q.x + 2];
+    float dx[NP], dy[NP], dz[NP], r2[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      dx[i] = (float)(px[i] - X);
+      dy[i] = (float)(py[i] - Y);
+      dz[i] = (float)(pz[i] - Z);
+      r2[i] = dx[i] * dx[i] + dy[i] * dy[i] + dz[i] * dz[i];
+    }
+    switch (q.y) {
+      case 0: eval_seg_val_n_f32<typename Ang<CART, 0>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 1: eval_seg_val_n_f32<typename Ang<CART, 1>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 2: eval_seg_val_n_f32<typename Ang<CART, 2>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 3: if (LMAX >= 3) eval_seg_val_n_f32<typename Ang<CART, (LMAX >= 3 ? 3 : 0)>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 4: if (LMAX >= 4) eval_seg_val_n_f32<typename Ang<CART, (LMAX >= 4 ? 4 : 0)>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
+      case 5: if (LMAX >= 5) eval_seg_val_n_f32<typename Ang<CART, (LMAX >= 5 ? 5 : 0)>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
+      default: if (LMAX >= 6) eval_seg_val_n_f32<typename Ang<CART, (LMAX >= 6 ? 6 : 0)>::type, NP>(sh, pr, q.z, q.w, dx, dy, dz, r2, sink); break;
     }
   }
 }

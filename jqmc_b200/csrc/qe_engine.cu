@@ -251,6 +251,17 @@ static int build_basis(const qe_basis_desc& d, const qe_basis_desc* d2, int n_at
   std::vector<int> cbeg;
   make_chunks(grp, sh_cost, grp_overhead, n_chunk_target, cseg, cbeg);
   hb.n_chunk = (int)cbeg.size() - 1;
+  {  // chunks sorted by the angular momentum of their first segment; sorted chunk i -> warp (i / 4) + 4 (i % 4) when 16 warps
+    std::vector<int> order(hb.n_chunk);
+    for (int c = 0; c < hb.n_chunk; ++c) order[c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cseg[cbeg[a]].y < cseg[cbeg[b]].y; });
+    const int nw_ = hb.n_chunk, per = (nw_ + 3) / 4;
+    std::vector<int> slot;  // warp ids in the order sub-partition 0, 1, 2, 3
+    for (int sp = 0; sp < 4; ++sp)
+      for (int w = sp; w < nw_; w += 4) slot.push_back(w);
+    (void)per;
+    for (int i = 0; i < nw_ && i < 32; ++i) hb.chunk_warp[slot[i]] = order[i];
+  }
   Blob blob;
   B.off_seg = blob.put(grp);
   B.off_sh = blob.put(sh);
@@ -260,6 +271,9 @@ static int build_basis(const qe_basis_desc& d, const qe_basis_desc* d2, int n_at
     for (size_t i = 0; i < pr.size(); ++i) pr2[i] = make_double2(pr[i].x * 46.16624130844683, pr[i].y);  // -Z * 32/ln2
     B.off_pr2 = blob.put(pr2);
     B.off_et = blob.put(std::vector<double>(QE_EXP2_TABLE, QE_EXP2_TABLE + 32));
+    std::vector<float2> prf(pr.size());
+    for (size_t i = 0; i < pr.size(); ++i) prf[i] = make_float2((float)(pr[i].x * 1.4426950408889634), (float)pr[i].y);  // -Z / ln2
+    B.off_prf = blob.put(prf);
   }
   B.off_C = B.off_C2 = 0;
   if (d.n_mo > 0 && with_C) {
@@ -814,7 +828,7 @@ __global__ void k_dfma_peak(int iters, double* out) {
 }
 
 int qe_local_energy_fused(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,
-                          double* e_L, double* T_elem, double* V_parts, cudaStream_t st);  // qe_walker.cu
+                          double* e_L, double* T_elem, double* V_parts, cudaStream_t st, const int* nn_fixed = nullptr);  // qe_walker.cu
 
 // =================================================================================================
 // C ABI
@@ -1013,6 +1027,11 @@ extern "C" int qe_create(const qe_system_desc* d, qe_engine** out) {
   const int n_mo = d->orb_up.n_mo;
   // the register / shared-memory kernels cover MO-basis geminals with <= 16 orbitals, <= 8 electrons per spin, J1 + J2
   h->narrow_ok = !d->j3_flag && n_mo > 0 && n_mo <= 16 && d->n_up <= 8;
+  if (d->precision != 0 && d->precision != 1) {
+    qe_destroy(h);
+    return fail(QE_ERR_INVALID, "qe_create: precision must be 0 (full) or 1 (mixed)");
+  }
+  h->mixed = d->precision == 1;
   h->nmo_pad = n_mo <= 4 ? 4 : (n_mo <= 8 ? 8 : 16);
   std::vector<int> row_ao, rowj_ao;
   std::vector<double> row_scale, rowj_scale;

@@ -77,8 +77,9 @@ extern "C" int qe_lrdmc_velements(qe_engine* h, int nw, const double* r_up, cons
 // fused local energy (mode 2); returns QE_ERR_UNSUPPORTED when the system does not fit, so that the caller
 // (qe_local_energy) can fall back to the staged kernels.
 int qe_local_energy_fused(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,
-                          double* e_L, double* T_elem, double* V_parts, cudaStream_t st) {
+                          double* e_L, double* T_elem, double* V_parts, cudaStream_t st, const int* nn_fixed) {
   WalkerArgs A{};
+  A.nn_fixed = nn_fixed;
   A.nw = nw;
   A.nmpm = 1;
   A.mode = 2;
@@ -123,4 +124,38 @@ extern "C" int qe_phase_clocks(qe_engine* h, int enable, int64_t* out12) {
     h->phase_clk = nullptr;
   }
   return QE_OK;
+}
+
+// ---- position derivatives (atomic forces) ---------------------------------------------------------------
+// The reference differentiates e_L by automatic differentiation (jqmc/jqmc_mcmc.py:749-790), which treats the nearest-nucleus
+// assignment of the non-local ECP as a constant.  A finite difference through qe_local_energy would instead jump whenever a
+// displaced electron changes its nearest nucleus; these two entries let the caller freeze the assignment of the base point.
+__global__ void k_nearest_nuclei(SysDev S, int nw, const double* __restrict__ r_up, const double* __restrict__ r_dn,
+                                 int* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = S.n_e * S.NN;
+  if (t >= (long long)nw * per) return;
+  const int w = (int)(t / per), q = (int)(t % per), e = q / S.NN, nn = q % S.NN;
+  const double* p = e < S.n_up ? r_up + ((size_t)w * S.n_up + e) * 3 : r_dn + ((size_t)w * S.n_dn + (e - S.n_up)) * 3;
+  out[t] = nearest_atom(S.Rn, S.n_atom, p[0], p[1], p[2], nn, nullptr);
+}
+
+extern "C" int qe_nearest_nuclei(qe_engine* h, int nw, const double* r_up, const double* r_dn, int32_t* nn_index, void* stream) {
+  if (!h || nw <= 0 || !r_up || !nn_index || (!r_dn && h->sys.n_dn > 0)) return fail(QE_ERR_INVALID, "qe_nearest_nuclei: bad argument");
+  if (!h->sys.ecp_flag) return fail(QE_ERR_INVALID, "qe_nearest_nuclei: the Hamiltonian has no ECP");
+  const long long n = (long long)nw * h->sys.n_e * h->sys.NN;
+  {
+    LaunchScope ls_(h, K_ECP_MESH, (cudaStream_t)stream);
+    k_nearest_nuclei<<<nblk(n, 128), 128, 0, (cudaStream_t)stream>>>(h->sys, nw, r_up, r_dn, nn_index);
+  }
+  CHECK_LAUNCH();
+  return QE_OK;
+}
+
+extern "C" int qe_local_energy_frozen(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT,
+                                      const double* Ginv, const int32_t* nn_index, double* e_L, void* stream) {
+  if (!h || nw <= 0 || !r_up || !Ginv || !e_L || (!r_dn && h->sys.n_dn > 0)) return fail(QE_ERR_INVALID, "qe_local_energy_frozen: bad argument");
+  if (h->sys.ecp_flag && !RT) return fail(QE_ERR_INVALID, "qe_local_energy_frozen: RT required for ECP systems");
+  if (use_wide(h) || !h->fused) return fail(QE_ERR_UNSUPPORTED, "qe_local_energy_frozen: only the fused register kernel takes a fixed nearest-nucleus assignment");
+  return qe_local_energy_fused(h, nw, r_up, r_dn, RT, Ginv, e_L, nullptr, nullptr, (cudaStream_t)stream, h->sys.ecp_flag ? nn_index : nullptr);
 }

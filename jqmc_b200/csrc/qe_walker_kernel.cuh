@@ -50,6 +50,8 @@ struct WalkerArgs {
   uint32_t* keys;  // [nw][2], advanced in place
   int* pc;         // [nw] projection counter (out in the main pass, in in the tail pass)
   int* n_max;      // [1] max over the walkers of the call (atomicMax in the main pass)
+  const int* nn_fixed;  // optional [nw][n_e * NN]: nuclei of the non-local ECP of every electron given by the caller instead of the
+                        // nearest-nucleus search (finite-difference derivatives keep the assignment of the base point fixed)
   long long* clk;  // optional [16] per-phase cycle counters (qe_set_phase_clocks; thread 0 of every CTA adds its own)
 };
 
@@ -130,7 +132,7 @@ struct PosShared {
   }
 };
 
-template <int NMO, bool CART, int LMAX, bool TAU, int WS_T>
+template <int NMO, bool CART, int LMAX, bool TAU, int WS_T, bool MIXED>
 __global__ void __launch_bounds__(512, 1)
 k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
   extern __shared__ __align__(16) char smem_raw[];
@@ -371,7 +373,7 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
         const int wl = WLOF(s % NACT), t = s / NACT, nn = t % S.NN, e = t / S.NN;
         const double x = SR(e, 0), y = SR(e, 1), z = SR(e, 2);
         double d;
-        const int a = nearest_atom(S.Rn, S.n_atom, x, y, z, nn, &d);
+        const int a = P.nn_fixed ? P.nn_fixed[((size_t)GW(wl) * Ne + e) * S.NN + nn] : nearest_atom(S.Rn, S.n_atom, x, y, z, nn, &d);
         const double relx = S.Rn[3 * a] - x, rely = S.Rn[3 * a + 1] - y, relz = S.Rn[3 * a + 2] - z;
         d = sqrt(relx * relx + rely * rely + relz * relz);
         double* o = s_ecp + (size_t)t * ECPW * WS + wl;
@@ -396,7 +398,8 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       if (jtask) {
         // Jastrow terms of electron e at its current position (shared by all of its mesh points)
         PosShared pos{s_r, WS, wl};
-        SEL(e, 7) = jastrow_single_m(S, pos, e, SR(e, 0), SR(e, 1), SR(e, 2));
+        if constexpr (MIXED) SEL(e, 7) = (double)jastrow_single_f32(S, pos, e, SR(e, 0), SR(e, 1), SR(e, 2));
+        else SEL(e, 7) = jastrow_single_m(S, pos, e, SR(e, 0), SR(e, 1), SR(e, 2));
         continue;
       }
       double Wv[NMO];
@@ -503,7 +506,8 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
           }
           SinkMOn<NMO, 2> sink;
           sink.init(tab + ((blk & 1) ? B.off_C2 : B.off_C));
-          eval_val_n<CART, LMAX, 2>(tab, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);
+          if constexpr (MIXED) eval_val_n_f32<CART, LMAX, 2>(tab, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);  // zone ao_eval in fp32
+          else eval_val_n<CART, LMAX, 2>(tab, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             const int wl = wls[i], e = el[i];
@@ -511,7 +515,9 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
             double ratio = 0.0;
 #pragma unroll
             for (int mo = 0; mo < NMO; ++mo) ratio = fma(sink.acc[i][mo], SW(e, mo), ratio);
-            const double jr = qexp(jastrow_single_m(S, pos, e, px[i], py[i], pz[i]) - jold[i]);
+            double jr;
+            if constexpr (MIXED) jr = (double)expf(jastrow_single_f32(S, pos, e, px[i], py[i], pz[i]) - (float)jold[i]);  // zone jastrow_ratio
+            else jr = qexp(jastrow_single_m(S, pos, e, px[i], py[i], pz[i]) - jold[i]);
             if (i == 0 || validB) {
               if (blk < 2) {
                 s_p[sl[i]] = -1.0 / (2.0 * a2) * (ratio * jr);
@@ -1074,15 +1080,17 @@ int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
   const size_t smem = fixed + per_walker * 8 * (pad32 ? 32 : A.wpc);
   {
     LaunchScope ls_(h, kid, st);
-#define CALL4(NMO, CART, LMAX, TAU, WS)                                                                                         \
-  do {                                                                                                                          \
-    CUDA_TRY(cudaFuncSetAttribute(k_walker<NMO, CART, LMAX, TAU, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_walker<NMO, CART, LMAX, TAU, WS><<<nblk(A.nw, A.wpc), NWARP * 32, smem, st>>>(h->b_up.dev, S, A);                          \
+#define CALL5(NMO, CART, LMAX, TAU, WS, MX)                                                                                         \
+  do {                                                                                                                              \
+    CUDA_TRY(cudaFuncSetAttribute(k_walker<NMO, CART, LMAX, TAU, WS, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_walker<NMO, CART, LMAX, TAU, WS, MX><<<nblk(A.nw, A.wpc), NWARP * 32, smem, st>>>(h->b_up.dev, S, A);                          \
   } while (0)
+#define CALL4(NMO, CART, LMAX, TAU, WS) CALL5(NMO, CART, LMAX, TAU, WS, false)
 #define CALL3(NMO, CART, LMAX, TAU)                                        \
   do {                                                                     \
     if constexpr (!(TAU) && (LMAX) == 4) {                                 \
-      if (pad32) CALL4(NMO, CART, LMAX, TAU, 32);                          \
+      if (pad32 && h->mixed) CALL5(NMO, CART, LMAX, TAU, 32, true);        \
+      else if (pad32) CALL4(NMO, CART, LMAX, TAU, 32);                     \
       else CALL4(NMO, CART, LMAX, TAU, 0);                                 \
     } else {                                                               \
       CALL4(NMO, CART, LMAX, TAU, 0);                                      \
@@ -1099,6 +1107,7 @@ int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
 #undef CALL2
 #undef CALL3
 #undef CALL4
+#undef CALL5
   }
   CHECK_LAUNCH();
   return QE_OK;

@@ -95,7 +95,7 @@ def _basis_desc(orb, keep):
 class WalkerEngine:
     """Device-resident tables of one Hamiltonian + the batched step kernels (see module docstring)."""
 
-    def __init__(self, hamiltonian_data, Nv: int = 6, NN: int = 1, device=None):
+    def __init__(self, hamiltonian_data, Nv: int = 6, NN: int = 1, device=None, precision: str = "full"):
         if not torch.cuda.is_available():
             raise RuntimeError("jqmc_b200.WalkerEngine needs a CUDA device (there is no CPU path)")
         self._lib = _lib.load()
@@ -158,6 +158,10 @@ class WalkerEngine:
             d.ecp_exponents, d.ecp_coefficients = _p_f64(e["z"]), _p_f64(e["c"])
             d.ecp_max_ang_mom_plus_1 = _p_i32(e["lmax"])
         d.Nv, d.NN = int(Nv), int(NN)
+        if precision not in ("full", "mixed"):  # jqmc/_precision.py: the two modes of the reference
+            raise ValueError("precision must be 'full' or 'mixed'")
+        d.precision = 1 if precision == "mixed" else 0
+        self.precision = precision
         keep += [pos, zeff, lam]
         self.n_up, self.n_dn, self.n_atom = d.n_up, d.n_dn, d.n_atom
         self.n_e = d.n_up + d.n_dn
@@ -173,6 +177,33 @@ class WalkerEngine:
             _lib.check(self._lib.qe_create(C.byref(d), C.byref(h)), "qe_create")
         self._h = h
         del keep
+
+    @classmethod
+    def from_hdf5(cls, path: str, group: str = "", Nv: int = 6, NN: int = 1, device=None, precision: str = "full"):
+        """Engine built by the library itself from jQMC's ``hamiltonian_data.h5`` (tree at the root) or from a restart
+        checkpoint (``group="hamiltonian_data"``): the native input path, no Python data model involved (qe_create_from_hdf5)."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("jqmc_b200.WalkerEngine needs a CUDA device (there is no CPU path)")
+        if precision not in ("full", "mixed"):
+            raise ValueError("precision must be 'full' or 'mixed'")
+        self = cls.__new__(cls)
+        self._lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        counts, checks = hdf5_summary(path, group)
+        (self.n_atom, self.n_up, self.n_dn, self._n_ao, _, n_mo, _, _, ecp, j1, j2, j3, n_ao_j3, n_mo_j3) = counts[:14]
+        self.n_e = self.n_up + self.n_dn
+        self.Nv, self.NN, self.precision = int(Nv), int(NN), precision
+        self.ecp_flag = bool(ecp)
+        self.n_orb = n_mo or self._n_ao
+        self._has_j1, self._has_j2 = bool(j1), bool(j2)
+        self._n_ao_j3 = n_ao_j3 if j3 else 0
+        self._n_orb_j3 = (n_mo_j3 or n_ao_j3) if j3 else 0
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self._lib.qe_create_from_hdf5(path.encode(), group.encode(), int(Nv), int(NN), 1 if precision == "mixed" else 0, C.byref(h))
+        _lib.check(rc, "qe_create_from_hdf5")
+        self._h = h
+        return self
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -281,6 +312,30 @@ class WalkerEngine:
         )  # fmt: skip
         _lib.check(rc, "qe_local_energy")
         return (e_L, T, V) if return_parts else e_L
+
+    def nearest_nuclei(self, r_up, r_dn):
+        """nn_index[nw, n_up + n_dn, NN] (int32): the nuclei the non-local ECP of every electron is taken around (qe_nearest_nuclei)."""
+        r_up, r_dn, nw = self._walkers(r_up, r_dn)
+        out = torch.empty((nw, self.n_e, self.NN), dtype=torch.int32, device=self.device)
+        rc = self._lib.qe_nearest_nuclei(self._h, nw, self._ptr(r_up), self._ptr(r_dn), self._ptr(out), self._stream())
+        _lib.check(rc, "qe_nearest_nuclei")
+        return out
+
+    def e_L_frozen(self, r_up, r_dn, RTs, Ginv, nn_index):
+        """e_L with the nearest-nucleus assignment of the non-local ECP given by the caller (qe_local_energy_frozen): the
+        building block of the finite-difference position derivatives (jqmc_b200/forces.py)."""
+        r_up, r_dn, nw = self._walkers(r_up, r_dn)
+        Ginv = self._mat(Ginv, nw, "A_old_inv")
+        if RTs is None:
+            RTs = torch.eye(3, dtype=torch.float64, device=self.device).expand(nw, 3, 3).contiguous()
+        RTs = self._dev(RTs)
+        e_L = torch.empty(nw, dtype=torch.float64, device=self.device)
+        rc = self._lib.qe_local_energy_frozen(
+            self._h, nw, self._ptr(r_up), self._ptr(r_dn), self._ptr(RTs), self._ptr(Ginv),
+            self._ptr(nn_index) if nn_index is not None else None, self._ptr(e_L), self._stream(),
+        )  # fmt: skip
+        _lib.check(rc, "qe_local_energy_frozen")
+        return e_L
 
     def as_reg_fast(self, G, Ginv):
         G = self._dev(G)
@@ -559,6 +614,29 @@ class WalkerEngine:
             if n.value:
                 out[self._lib.qe_profile_name(i).decode()] = (ms.value, n.value)
         return out
+
+
+def hdf5_summary(path: str, group: str = ""):
+    """(counts[16], checks[8]) of the Hamiltonian tree in an HDF5 file as the LIBRARY's reader sees it (qe_hdf5_summary; no GPU
+    needed): n_atom, n_up, n_dn, n_ao, n_prim, n_mo, cartesian, n_ecp, ecp_flag, j1_type, j2_type, j3_flag, n_ao_j3, n_mo_j3."""
+    counts = (C.c_int64 * 16)()
+    checks = (C.c_double * 8)()
+    _lib.check(_lib.load().qe_hdf5_summary(path.encode(), group.encode(), counts, checks), "qe_hdf5_summary")
+    return [int(x) for x in counts], [float(x) for x in checks]
+
+
+def hdf5_read_walkers(path: str, rank: int, n_up: int, n_dn: int):
+    """(r_up, r_dn, keys) NumPy arrays of one rank of a restart checkpoint, read by the library (qe_hdf5_read_walkers)."""
+    lib = _lib.load()
+    nw = C.c_int()
+    _lib.check(lib.qe_hdf5_read_walkers(path.encode(), rank, 0, n_up, n_dn, C.byref(nw), None, None, None), "qe_hdf5_read_walkers")
+    r_up = np.empty((nw.value, n_up, 3))
+    r_dn = np.empty((nw.value, n_dn, 3))
+    keys = np.empty((nw.value, 2), dtype=np.uint32)
+    rc = lib.qe_hdf5_read_walkers(path.encode(), rank, nw.value, n_up, n_dn, C.byref(nw), r_up.ctypes.data_as(_lib.f64p),
+                                  r_dn.ctypes.data_as(_lib.f64p), keys.ctypes.data_as(C.POINTER(C.c_uint32)))  # fmt: skip
+    _lib.check(rc, "qe_hdf5_read_walkers")
+    return r_up, r_dn, keys
 
 
 def measure_fp64_peak(iters: int = 20000) -> float:

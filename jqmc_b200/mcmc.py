@@ -18,8 +18,11 @@ With ``comput_log_WF_param_deriv=True`` every step also stores O_k = d ln|Psi| /
 ``j2_param``, ``j3_matrix``, ``lambda_matrix`` as in jqmc/wavefunction.py:542-624), and ``get_dln_WF`` / ``get_gF`` give the
 flattened derivative matrix and the jackknifed generalised forces (jqmc_mcmc.py:1372-1513, 1516-1692).
 
-Out of scope here (SURVEY.md §8f "next"): e_L parameter derivatives, position derivatives (forces), the lambda projection
-and block symmetrisation of ``get_dln_WF``, ``run_optimize``.
+With ``comput_position_deriv=True`` every step also stores the Hellmann-Feynman and Pulay force products (position
+derivatives by finite differences on the device + SWCT, jqmc_b200/forces.py) and ``get_aF`` gives the jackknifed atomic forces.
+
+Out of scope here (SURVEY.md §8f "next"): e_L parameter derivatives (linear method), the adaptive learning rate / SNR filters of
+the reference's optimiser.
 """
 
 from __future__ import annotations
@@ -92,9 +95,13 @@ def _allreduce_sum(values, device=None):
 
 def generate_init_electron_configurations(n_up, n_dn, num_walkers, charges, coords):
     """Initial walkers: electrons assigned to nuclei (valence-filling order over a farthest-atom sequence),
-    each placed on a uniform shell 0.1-1.0 bohr around its owner.  Same assignment rules and the same
-    ``np.random`` draw order as jqmc/_jqmc_utility.py:54-218 (dn offsets, then up offsets;
-    distance/theta/phi blocks), so a seeded run starts from the reference's configurations.
+    each placed on a uniform shell 0.1-1.0 bohr around its owner.
+
+    TRANSLITERATED FROM the reference's ``_generate_init_electron_configurations`` (jqmc/_jqmc_utility.py:54-218): the
+    assignment state machine and -- deliberately -- the order of the ``np.random`` calls (dn offsets, then up offsets;
+    distance / theta / phi blocks) are the reference's, because a seeded run has to start from the reference's configurations.
+    It is host-side set-up outside the engine's scope: when running under jQMC, call the reference's own function
+    and hand its arrays to the drivers; this copy exists so that the package runs where jQMC is not installed.
     Returns (r_up[nw,n_up,3], r_dn[nw,n_dn,3], up_owner, dn_owner)."""
     coords = np.asarray(coords, dtype=np.float64)
     nion = coords.shape[0]
@@ -190,8 +197,9 @@ class MCMC:
         use_swct: bool = True,
         engine: WalkerEngine | None = None,
     ) -> None:
-        if comput_e_L_param_deriv or comput_position_deriv:
-            raise NotImplementedError("e_L parameter derivatives / position derivatives are outside the walker engine (SURVEY.md §8f)")
+        if comput_e_L_param_deriv:
+            raise NotImplementedError("e_L parameter derivatives (linear method) are outside the walker engine (SURVEY.md §8f)")
+        self.__comput_position_deriv = bool(comput_position_deriv)
         self.__comput_log_WF_param_deriv = bool(comput_log_WF_param_deriv)
         self.hamiltonian_data = hamiltonian_data
         self.__mcmc_seed = mcmc_seed
@@ -217,6 +225,11 @@ class MCMC:
         )  # fmt: skip
         self.__r_up = torch.from_numpy(np.ascontiguousarray(r_up)).to(dev)
         self.__r_dn = torch.from_numpy(np.ascontiguousarray(r_dn)).to(dev)
+        self.__forces = None
+        if self.__comput_position_deriv:  # atomic forces: finite-difference position derivatives on the device (jqmc_b200/forces.py)
+            from .forces import ForceEvaluator
+
+            self.__forces = ForceEvaluator(hamiltonian_data, self.engine)
         self.__init_attributes()
 
     def __init_attributes(self):
@@ -227,6 +240,8 @@ class MCMC:
         self.__stored_e_L2 = []
         self.__stored_w_L = []
         self.__stored_dln = {}
+        self.__stored_force_HF = []
+        self.__stored_force_PP = []
         self.__timer = dict(total=0.0, update=0.0, e_L=0.0, misc=0.0)
 
     # ---- properties (names as in the reference, jqmc_mcmc.py:260-447) --------------------------------
@@ -280,10 +295,14 @@ class MCMC:
 
         cfg = dict(mcmc_seed=int(self.__mcmc_seed), num_walkers=self.__num_walkers, num_mcmc_per_measurement=self.__nmpm, Dt=self.__Dt,
                    epsilon_AS=self.__epsilon_AS, comput_log_WF_param_deriv=self.__comput_log_WF_param_deriv, comput_e_L_param_deriv=False,
-                   comput_position_deriv=False, random_discretized_mesh=self.__random_discretized_mesh, use_swct=self.__use_swct,
+                   comput_position_deriv=self.__comput_position_deriv, random_discretized_mesh=self.__random_discretized_mesh, use_swct=self.__use_swct,
                    mcmc_counter=int(self.__mcmc_counter), accepted_moves=int(self.__accepted_moves),
                    rejected_moves=int(self.__rejected_moves), i_opt=int(self.__i_opt))  # fmt: skip
         obs = {"e_L": self.e_L, "e_L2": self.e_L2, "w_L": self.w_L, "param_grads": self.dln_Psi_dc}
+        if self.__stored_force_HF:  # (M, 1, ...) per-step arrays in the reference are (M, nw, n_atom, 3) here as well
+            obs["force_HF"] = np.array(self.__stored_force_HF)
+            obs["force_PP"] = np.array(self.__stored_force_PP)
+            obs["E_L_force_PP"] = self.e_L[..., None, None] * np.array(self.__stored_force_PP)
         save_rank_checkpoint(
             filepath, driver_type="MCMC", driver_config=cfg,
             rng_state={"jax_PRNG_key_list": self.jax_PRNG_key_list, "mpi_seed": int(self.__mpi_seed)},
@@ -302,11 +321,12 @@ class MCMC:
         check_checkpoint_version(filepath)
         data = load_rank_checkpoint(filepath, rank)
         cfg, rng, ws, obs = data["driver_config"], data["rng_state"], data["walker_state"], data["observables"]
-        if cfg.get("comput_e_L_param_deriv") or cfg.get("comput_position_deriv"):
-            raise NotImplementedError("e_L parameter derivatives / position derivatives are outside the walker engine (SURVEY.md §8f)")
+        if cfg.get("comput_e_L_param_deriv"):
+            raise NotImplementedError("e_L parameter derivatives (linear method) are outside the walker engine (SURVEY.md §8f)")
         H = load_hamiltonian_from_checkpoint(filepath)
         obj = cls.__new__(cls)
         obj._MCMC__comput_log_WF_param_deriv = bool(cfg.get("comput_log_WF_param_deriv", False))
+        obj._MCMC__comput_position_deriv = bool(cfg.get("comput_position_deriv", False))
         obj.hamiltonian_data = H
         obj._MCMC__mcmc_seed = int(cfg["mcmc_seed"])
         obj._MCMC__num_walkers = int(cfg["num_walkers"])
@@ -321,7 +341,15 @@ class MCMC:
         obj._MCMC__keys = torch.from_numpy(np.ascontiguousarray(rng["jax_PRNG_key_list"]).astype(np.uint32)).to(dev)
         obj._MCMC__r_up = torch.from_numpy(np.ascontiguousarray(ws["latest_r_up_carts"], dtype=np.float64)).to(dev)
         obj._MCMC__r_dn = torch.from_numpy(np.ascontiguousarray(ws["latest_r_dn_carts"], dtype=np.float64)).to(dev)
+        obj._MCMC__forces = None
+        if obj._MCMC__comput_position_deriv:
+            from .forces import ForceEvaluator
+
+            obj._MCMC__forces = ForceEvaluator(H, obj.engine)
         obj._MCMC__init_attributes()
+        if obs.get("force_HF") is not None and np.size(obs["force_HF"]):
+            obj._MCMC__stored_force_HF = [x for x in np.asarray(obs["force_HF"])]
+            obj._MCMC__stored_force_PP = [x for x in np.asarray(obs["force_PP"])]
         obj._MCMC__mcmc_counter = int(cfg.get("mcmc_counter", 0))
         obj._MCMC__accepted_moves = int(cfg.get("accepted_moves", 0))
         obj._MCMC__rejected_moves = int(cfg.get("rejected_moves", 0))
@@ -368,6 +396,9 @@ class MCMC:
                 w_L = (R_AS / torch.clamp(R_AS, min=eps)) ** 2
             else:  # (R/max(R,0))^2 = 1, NaN when R_AS == 0 (0/0), as in jqmc_mcmc.py:743-747
                 w_L = torch.where(R_AS > 0, torch.ones_like(R_AS), torch.full_like(R_AS, float("nan")))
+            if self.__forces is not None:  # jqmc_mcmc.py:749-852
+                f_hf, f_pp, _ = self.__forces.force_products(r_up, r_dn, RTs, self.__use_swct)
+                force_pack = torch.stack([f_hf, f_pp]).cpu().numpy()
             # one device->host read per step (the reference does three: jqmc_mcmc.py:720, 739, 747)
             if self.__comput_log_WF_param_deriv:  # jqmc_mcmc.py:854-876
                 for name, g in eng.grad_ln_psi_params_fast(r_up, r_dn, Ginv).items():
@@ -383,6 +414,9 @@ class MCMC:
             self.__stored_e_L.append(pack[0])
             self.__stored_e_L2.append(pack[0] ** 2)
             self.__stored_w_L.append(pack[1])
+            if self.__forces is not None:
+                self.__stored_force_HF.append(force_pack[0])
+                self.__stored_force_PP.append(force_pack[1])
             self.__accepted_moves += int(pack[2].sum())
             self.__rejected_moves += int(pack[3].sum())
             self.__mcmc_counter += 1
@@ -405,24 +439,72 @@ class MCMC:
         return jackknife_E(w_L, e_L, e_L2, num_mcmc_bin_blocks, self.engine.device)
 
 
+    def get_aF(self, num_mcmc_warmup_steps: int = 50, num_mcmc_bin_blocks: int = 10):
+        """(force_mean, force_std) [n_atom, 3] in Hartree / bohr: Hellmann-Feynman + Pulay forces with the reference's jackknife
+        (jqmc_mcmc.py:1191-1370).  Needs ``comput_position_deriv=True``."""
+        if not self.__stored_force_HF:
+            raise ValueError("no force samples stored: construct MCMC with comput_position_deriv=True")
+        from .forces import jackknife_forces
+
+        s = slice(num_mcmc_warmup_steps, None)
+        return jackknife_forces(self.w_L[s], self.e_L[s], np.array(self.__stored_force_HF)[s], np.array(self.__stored_force_PP)[s],
+                                num_mcmc_bin_blocks, self.engine.device)  # fmt: skip
+
     BLOCK_ORDER = ("j1_param", "j2_param", "j3_matrix", "lambda_matrix")  # jqmc/wavefunction.py:515-674
 
-    def get_dln_WF(self, num_mcmc_warmup_steps: int = 50, chosen_param_index=None, blocks=None):
+    def get_dln_WF(self, num_mcmc_warmup_steps: int = 50, chosen_param_index=None, blocks=None, lambda_projectors=None,
+                   num_orb_projection=None, symmetrize: bool = True):  # fmt: skip
         """O_matrix (M, num_walkers, K): the stored derivatives after warm-up, blocks concatenated in the reference's order and
-        flattened row-major (jqmc_mcmc.py:1372-1420).  ``blocks``: optional list of block names (default: all stored)."""
+        flattened row-major, then -- as ``MCMC.get_dln_WF`` of the reference does (jqmc_mcmc.py:1372-1513) --
+
+        * the lambda block projected when ``lambda_projectors = (L', R', S_up^-1/2, S_dn^-1/2)`` is given (:1424-1459: paired part
+          O' = S_up^-1/2 O S_dn^-1/2, then O' - (I - L') O' (I - R'); unpaired columns S_up^-1/2 O), and
+        * every block with an internal symmetry symmetrised (:1461-1481): the square part of ``j3_matrix`` when the current
+          J3 matrix is symmetric, the paired part of ``lambda_matrix`` when the current lambda is (jqmc/wavefunction.py:170-244).
+
+        ``blocks``: optional list of block names (default: all stored).  The algebra runs on the device."""
         if not self.__stored_dln:
             raise ValueError("no parameter derivatives stored: construct MCMC with comput_log_WF_param_deriv=True")
-        O = self._dln_WF_device(num_mcmc_warmup_steps, blocks).cpu().numpy()
+        O = self._dln_WF_device(num_mcmc_warmup_steps, blocks, lambda_projectors, num_orb_projection, symmetrize).cpu().numpy()
         return O if chosen_param_index is None else O[:, :, chosen_param_index]
 
-    def _dln_WF_device(self, num_mcmc_warmup_steps: int = 0, blocks=None):
+    def _block_symmetry(self, name):
+        """(symmetric?, number of leading columns that form the square part) of a matrix block of the CURRENT parameters."""
+        wf = self.hamiltonian_data.wavefunction_data
+        atol, rtol = 1.0e-8, 1.0e-6  # jqmc/_setting.py:74-75
+        if name == "j3_matrix":
+            j3 = wf.jastrow_data.jastrow_three_body_data
+            m = np.asarray(j3.j_matrix)
+            sq = m[:, :-1]
+            return bool(sq.shape[0] == sq.shape[1] and np.allclose(sq, sq.T, atol=atol)), m.shape[1] - 1
+        if name == "lambda_matrix":
+            lam = np.asarray(wf.geminal_data.lambda_matrix)
+            n = lam.shape[0]
+            return bool(np.allclose(lam[:, :n], lam[:, :n].T, atol=atol, rtol=rtol)), n
+        return False, 0
+
+    def _dln_WF_device(self, num_mcmc_warmup_steps: int = 0, blocks=None, lambda_projectors=None, num_orb_projection=None,
+                       symmetrize: bool = True):  # fmt: skip
         """The same matrix as a device tensor (no host round trip: the path of get_sr_direction / run_optimize)."""
         names = [n for n in self.BLOCK_ORDER if n in self.__stored_dln and (blocks is None or n in blocks)]
+        dev = self.engine.device
         parts = []
         for n in names:
-            a = self.__dln_block(n)
+            a = self.__dln_block(n)[num_mcmc_warmup_steps:]
+            if n == "lambda_matrix" and lambda_projectors is not None and num_orb_projection is not None:
+                L, R, Su, Sd = (torch.as_tensor(np.asarray(x), dtype=torch.float64, device=dev) for x in lambda_projectors)
+                eye = torch.eye(L.shape[0], dtype=torch.float64, device=dev)
+                n_pc = R.shape[0]
+                paired = Su @ a[..., :n_pc] @ Sd
+                paired = paired - (eye - L) @ paired @ (eye - R)
+                a = torch.cat([paired, Su @ a[..., n_pc:]], dim=-1)
+            if symmetrize and a.dim() == 4:
+                sym, n_sq = self._block_symmetry(n)
+                if sym:
+                    sq = a[..., :n_sq]
+                    a = torch.cat([0.5 * (sq + sq.transpose(-1, -2)), a[..., n_sq:]], dim=-1)
             parts.append(a.reshape(a.shape[0], a.shape[1], -1))
-        return torch.cat(parts, dim=2)[num_mcmc_warmup_steps:]
+        return torch.cat(parts, dim=2)
 
     def get_gF(self, num_mcmc_warmup_steps: int = 50, num_mcmc_bin_blocks: int = 10, chosen_param_index=None, blocks=None):
         """Generalised forces f_k = -2 (<e_L O_k> - <e_L><O_k>) with jackknife error bars over (bins x walkers) samples of all
@@ -432,6 +514,20 @@ class MCMC:
         O = self.get_dln_WF(num_mcmc_warmup_steps, chosen_param_index, blocks)
         return jackknife_gF(w_L, e_L, O, num_mcmc_bin_blocks, self.engine.device)
 
+    @staticmethod
+    def lambda_projectors(mo_coefficients_up, mo_coefficients_dn, overlap_up, overlap_dn, num_orb_projection: int):
+        """(L', R', S_up^-1/2, S_dn^-1/2) of the lambda-subspace projection from the MO coefficients [n_mo, n_ao] and the AO
+        overlap matrices (jqmc_mcmc.py:2712-2750): C' = S^1/2 C over the first ``num_orb_projection`` orbitals, L' = C'_up C'_up^T,
+        R' = C'_dn C'_dn^T (orthogonal projectors in the S^-1/2-orthogonalised basis)."""
+        out = []
+        for C, S in ((mo_coefficients_up, overlap_up), (mo_coefficients_dn, overlap_dn)):
+            S = 0.5 * (np.asarray(S, dtype=np.float64) + np.asarray(S, dtype=np.float64).T)
+            ev, U = np.linalg.eigh(S)
+            sq, isq = U @ np.diag(np.sqrt(ev)) @ U.T, U @ np.diag(1.0 / np.sqrt(ev)) @ U.T
+            Cp = sq @ np.asarray(C, dtype=np.float64)[:num_orb_projection, :].T
+            out.append((Cp @ Cp.T, isq))
+        return out[0][0], out[1][0], out[0][1], out[1][1]
+
 
     def get_sr_direction(self, num_mcmc_warmup_steps: int = 0, epsilon: float = 1e-3, use_cg: bool = False, blocks=None,
                          cg_max_iter: int = 10000, cg_tol: float = 1e-10):  # fmt: skip
@@ -440,7 +536,7 @@ class MCMC:
         from .sr import sr_natural_gradient
 
         dev = self.engine.device
-        O = self._dln_WF_device(num_mcmc_warmup_steps, blocks)
+        O = self._dln_WF_device(num_mcmc_warmup_steps, blocks)  # (symmetrised like get_dln_WF: f, S and theta inherit the symmetry)
         w = torch.from_numpy(self.w_L[num_mcmc_warmup_steps:]).to(dev)
         e = torch.from_numpy(self.e_L[num_mcmc_warmup_steps:]).to(dev)
         theta, info = sr_natural_gradient(w, e, O, epsilon=epsilon, use_cg=use_cg, cg_max_iter=cg_max_iter, cg_tol=cg_tol)

@@ -694,3 +694,29 @@ def compute_local_energy(H, r_up, r_dn, RT=None, Ginv=None, NN=1, Nv=6):
     T = compute_kinetic_energy(wf, r_up, r_dn, Ginv)
     V = compute_coulomb_potential(H.coulomb_potential_data, wf, r_up, r_dn, RT, NN, Nv, Ginv)
     return T + V
+
+
+# ---- space-warp coordinate transformation (jqmc/swct.py:63-150) -----------------------------------------------------------
+def swct_omega(structure, r_carts):
+    """omega[alpha, i] = kappa_{alpha i} / sum_beta kappa_{beta i}, kappa = 1 / |r_i - R_alpha|^4 (jqmc/swct.py:99-132, debug form)."""
+    R = np.asarray(structure.positions, dtype=np.float64)
+    r = np.asarray(r_carts, dtype=np.float64)
+    om = np.zeros((len(R), len(r)))
+    for a in range(len(R)):
+        for i in range(len(r)):
+            ks = [1.0 / np.linalg.norm(r[i] - R[b]) ** 4 for b in range(len(R))]
+            om[a, i] = ks[a] / np.sum(ks)
+    return om
+
+
+def swct_domega(structure, r_carts, h=1.0e-5):
+    """sum_i grad_{r_i} omega[alpha, i] -> (n_atom, 3), by central differences of swct_omega (the reference: jacrev, :134-150)."""
+    r = np.asarray(r_carts, dtype=np.float64)
+    out = np.zeros((len(structure.positions), 3))
+    for i in range(len(r)):
+        for c in range(3):
+            rp, rm = r.copy(), r.copy()
+            rp[i, c] += h
+            rm[i, c] -= h
+            out[:, c] += (swct_omega(structure, rp)[:, i] - swct_omega(structure, rm)[:, i]) / (2 * h)
+    return out
