@@ -646,7 +646,11 @@ def run_gpu(args, rank, local_rank, world):
             per_kernel=rl_kernels, kernels=kern,
         )  # fmt: skip
         cpu = None
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.config == "synthetic_100e":
+            # one brute-force oracle LRDMC step of a 100-electron walker (600 + 600 mesh points x 40 projections) takes hours
+            cpu = dict(value=None, unit=UNIT, cores=0, kind="port", extrapolated=False,
+                       sample="not run: a full oracle step of this system does not fit a bounded CPU sample; see --config water_jsd")
+        elif world == 1 and not args.no_cpu:
             procs = max(1, min(os.cpu_count() or 1, 16))
             v, dt, res, wall = cpu_sample(args.config, procs, procs, legs)
             cpu = dict(value=v, unit=UNIT, cores=procs, kind="port", extrapolated=False,

@@ -225,9 +225,15 @@ def lrdmc_V_elements(H, r_up, r_dn, RT, non_local_move="tmove", alat=0.3):
     return diag, nondiag
 
 
-def lrdmc_projection(H, w, r_up, r_dn, Ginv, key, E_scf, nmpm, random_discretized_mesh, non_local_move, alat, trace=None):
+def lrdmc_projection(H, w, r_up, r_dn, Ginv, key, E_scf, nmpm, random_discretized_mesh, non_local_move, alat, trace=None,
+                     norm_order="reference"):
     """``nmpm`` GFMC_n projections of one walker (jqmc/jqmc_gfmc.py:4738-5358).
-    Returns (w, r_up, r_dn, Ginv, key, RT, V_diag, V_nondiag)."""
+    Returns (w, r_up, r_dn, Ginv, key, RT, V_diag, V_nondiag).
+
+    norm_order: how the normaliser of the move probabilities is summed.  "reference" = ``p_list.sum()`` as the reference writes
+    it (jqmc_gfmc.py:5025; NumPy's pairwise order here, XLA leaves the order unspecified); "sequential" = a running sum in vector
+    order, which is what the engine does.  The two differ in the last ulp of the normaliser; tests/test_oracle_golden.py checks
+    that they select the same moves on the test seeds."""
     r_up = np.array(r_up, dtype=np.float64)
     r_dn = np.array(r_dn, dtype=np.float64)
     Ginv = np.array(Ginv, dtype=np.float64)
@@ -249,9 +255,12 @@ def lrdmc_projection(H, w, r_up, r_dn, Ginv, key, E_scf, nmpm, random_discretize
         diag, nondiag, p, moves = lrdmc_elements(H, r_up, r_dn, Ginv, RT, alat, non_local_move)
         b_x = 1.0 / (diag - E_scf) * (-nondiag)
         w = w * b_x
-        tot = 0.0
-        for x in p:  # sequential fp64 sum (the engine's order; jnp.sum leaves the order unspecified)
-            tot += x
+        if norm_order == "sequential":
+            tot = 0.0
+            for x in p:
+                tot += x
+        else:
+            tot = np.asarray(p).sum()
         cdf = np.cumsum(p / tot)
         u = R.uniform(move_keys[i])
         k = min(int(np.searchsorted(cdf, u, side="left")), len(cdf) - 1)

@@ -282,3 +282,25 @@ def test_parameter_derivatives_match_finite_differences():
             w.geminal_data = dataclasses.replace(w.geminal_data, lambda_matrix=m)
 
         np.testing.assert_allclose(g["lambda_matrix"][idx], fd(set_lam, 1e-6), rtol=1e-6, atol=1e-8)
+
+
+def test_move_selection_does_not_depend_on_the_summation_order_of_the_normaliser():
+    """The reference normalises the move probabilities with ``p_list.sum()`` (jqmc_gfmc.py:5025; order unspecified under XLA); the
+    engine sums them sequentially.  Both orders must select the same moves and give the same weights to round-off."""
+    import copy
+
+    from jqmc_b200.data import Jastrow_data, Jastrow_two_body_data
+    from oracle import drivers as OD
+    from tests.conftest import load_system, random_walkers
+
+    H = copy.deepcopy(load_system("H2_ecp_ccpvtz"))
+    H.wavefunction_data.jastrow_data = Jastrow_data(jastrow_two_body_data=Jastrow_two_body_data(jastrow_2b_param=0.8))
+    r_up, r_dn = random_walkers(H, 4, 41, scale=0.7)
+    for w in range(4):
+        _, Ginv = OD.geminal_inv(H.wavefunction_data.geminal_data, r_up[w], r_dn[w])
+        ta, tb = [], []
+        a = OD.lrdmc_projection(H, 1.0, r_up[w], r_dn[w], Ginv, (0, 777 + w), -1.1, 12, True, "tmove", 0.3, trace=ta, norm_order="reference")
+        b = OD.lrdmc_projection(H, 1.0, r_up[w], r_dn[w], Ginv, (0, 777 + w), -1.1, 12, True, "tmove", 0.3, trace=tb, norm_order="sequential")
+        assert [t["k"] for t in ta] == [t["k"] for t in tb]
+        np.testing.assert_allclose(a[0], b[0], rtol=1e-13)
+        np.testing.assert_array_equal(a[1], b[1])

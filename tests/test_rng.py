@@ -71,3 +71,33 @@ def test_erf_inv_and_ranges():
     assert set(ints) == set(range(8))
     ns = np.array([R.normal(k) for k in R.split(key, 2000)])
     assert abs(ns.mean()) < 0.1 and abs(ns.std() - 1.0) < 0.1
+
+
+def test_against_jax_goldens():
+    """jax.random itself, when somebody has run tools/make_jax_goldens.py where JAX is installed (it is not in this project's
+    image: DESIGN.md §6).  Every call pattern of the hot path -- key layout, split counters, the per-proposal split chain,
+    randint's two-draw composition, the fp64 mantissa fill of uniform, erf_inv of normal -- against oracle/jaxrng.py."""
+    import os
+
+    import pytest
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jax_rng_goldens.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/jax_rng_goldens.npz not generated yet (needs a JAX install: tools/make_jax_goldens.py)")
+    g = np.load(path)
+    assert bool(g["threefry_partitionable"]), "goldens were generated with the legacy (non-partitionable) Threefry layout"
+    for s in (0, 42, 34456, 2**33 + 5):
+        key = R.PRNGKey(s)
+        assert key == tuple(int(x) for x in g[f"key_{s}"])
+        assert R.split(key) == [tuple(int(x) for x in k) for k in g[f"split_{s}"]]
+        assert R.split(key, 4) == [tuple(int(x) for x in k) for k in g[f"split4_{s}"]]
+        k = key
+        for ref in g[f"chain_{s}"]:
+            k, sub = R.split(k)
+            assert sub == tuple(int(x) for x in ref)
+        sub = R.split(key)[1]
+        for n in (3, 4, 8, 13):
+            assert R.randint(sub, 0, n) == int(g[f"randint_{s}_{n}"])
+        assert R.normal(sub) == float(g[f"normal_{s}"])
+        assert R.uniform(sub) == float(g[f"uniform_{s}"])
+        np.testing.assert_array_equal(np.array(R.uniform(sub, 3, -2 * np.pi, 2 * np.pi)), g[f"angles_{s}"])
