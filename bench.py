@@ -143,8 +143,10 @@ def algorithmic_flops(H, n_prim=None):
     aos = getattr(orb, "aos_data", orb)
     n_ao = aos.num_ao
     n_prim = aos.num_ao_prim if n_prim is None else n_prim
-    n_mo = getattr(orb, "num_mo", 0) or n_ao
     n_up, n_dn = gem.num_electron_up, gem.num_electron_dn
+    # width of the per-point contraction: AO -> MO (n_mo columns) for an MO-basis geminal; for an AO-basis (JAGP) geminal the
+    # reference contracts the AO row with the pre-contracted M = lambda Phi_dn, i.e. N_up columns (determinant.py:1665-1783)
+    n_mo = getattr(orb, "num_mo", 0) or n_up
     n_e = n_up + n_dn
     n_at = len(H.structure_data.atomic_numbers)
     c_ang, c_val = 60, 15
@@ -482,6 +484,13 @@ def run_gpu(args, rank, local_rank, world):
             lstate, lobs = step_lrdmc(lstate)
             ev_l[i][1].record()
     sr = None
+    if with_ok and ok_store:  # (library warm-up outside the timed solve: cuBLAS / cuSOLVER handles, workspaces)
+        from jqmc_b200.sr import sr_natural_gradient as _sr_warm
+
+        _O = torch.stack([o for o, _ in ok_store[:2]])
+        _e = torch.stack([e for _, e in ok_store[:2]])
+        _sr_warm(torch.ones_like(_e), _e, _O, epsilon=1e-3, use_cg=False, force_dual=False)
+        torch.cuda.synchronize()
     if with_ok:  # one stochastic-reconfiguration solve on the samples of the timed steps (all on the device, all ranks)
         from jqmc_b200.sr import sr_natural_gradient
 
