@@ -441,7 +441,7 @@ def run_gpu(args, rank, local_rank, world):
 
     def step_lrdmc(state):
         r_up, r_dn, keys, A_inv = state
-        r_up, r_dn, keys, A_inv, sums, n_surv, _ = gf._step(r_up, r_dn, keys, A_inv, float(zeta_rng.random_sample()), rank, world)
+        r_up, r_dn, keys, A_inv, sums, n_surv, _, _ = gf._step(r_up, r_dn, keys, A_inv, float(zeta_rng.random_sample()), rank, world)
         return (r_up, r_dn, keys, A_inv), (sums, n_surv)
 
     def barrier():
@@ -562,6 +562,16 @@ def run_gpu(args, rank, local_rank, world):
         e2e_step()
     barrier()
     t_e2e = (time.perf_counter() - t0) / n_e2e
+    if with_ok:  # the SR solve of the timed samples with its result read back to the host, amortised over the steps like `value`
+        th_host = torch.empty(O.shape[2], dtype=torch.float64).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        th2, _ = sr_natural_gradient(torch.ones_like(e), e, O, epsilon=1e-3, use_cg=O.shape[2] > 2000)
+        th_host.copy_(th2, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        barrier()
+        t_e2e += (time.perf_counter() - t0) / args.steps
+        d2h += th_host.numel() * 8 // args.steps
     clocks = sampler.stop()
 
     # ---- per-kernel share and roofline (separate profiled pass; events on the launch stream) ---------

@@ -136,6 +136,11 @@ int qe_local_energy(qe_engine* h, int nw, const double* r_up, const double* r_dn
 int qe_nearest_nuclei(qe_engine* h, int nw, const double* r_up, const double* r_dn, int32_t* nn_index, void* stream);
 int qe_local_energy_frozen(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,
                            const int32_t* nn_index, double* e_L, void* stream);
+/* The same for the lattice-regularised local energy V_diag + V_nondiag of LRDMC, whose position gradient is the LRDMC force
+ * term (grad of _compute_local_energy_n / _compute_local_energy_t, jqmc/jqmc_gfmc.py:5630-5667, 1461-1486). */
+int qe_lrdmc_velements_frozen(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,
+                              const int32_t* nn_index, int non_local_move, double alat, double* V_diag, double* V_nondiag,
+                              void* stream);
 
 /* _jit_vmap_as_reg_fast (jqmc/determinant.py:1223-1260, jqmc_mcmc.py:4739). */
 int qe_as_factor(qe_engine* h, int nw, const double* G, const double* Ginv, double* R_AS, void* stream);

@@ -104,6 +104,10 @@ EXPORTS = {
         C.c_int,
         [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_double] + [C.c_void_p] * 3,
     ),
+    "qe_lrdmc_velements_frozen": (
+        C.c_int,
+        [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_double] + [C.c_void_p] * 3,
+    ),
     "qe_lrdmc_collect": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_double, C.c_void_p, C.c_void_p]),
     "qe_lrdmc_branch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qe_gather_walkers": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p]),

@@ -74,6 +74,32 @@ extern "C" int qe_lrdmc_velements(qe_engine* h, int nw, const double* r_up, cons
   return launch_walker<false>(h, A, (cudaStream_t)stream, K_LRDMC);
 }
 
+// V_diag / V_nondiag with the nearest-nucleus assignment of the non-local ECP given by the caller: the lattice-regularised
+// local energy whose finite differences are the LRDMC force terms (jqmc/jqmc_gfmc.py:5630-5667, 5840-5850).
+extern "C" int qe_lrdmc_velements_frozen(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT,
+                                         const double* Ginv, const int32_t* nn_index, int non_local_move, double alat,
+                                         double* V_diag, double* V_nondiag, void* stream) {
+  if (!h || nw <= 0 || !r_up || !Ginv || !V_diag || !V_nondiag || (!r_dn && h->sys.n_dn > 0))
+    return fail(QE_ERR_INVALID, "qe_lrdmc_velements_frozen: bad argument");
+  if (!(alat > 0)) return fail(QE_ERR_INVALID, "qe_lrdmc_velements_frozen: alat must be positive");
+  if (use_wide(h))
+    return fail(QE_ERR_UNSUPPORTED, "qe_lrdmc_velements_frozen: only the fused register kernel takes a fixed nearest-nucleus assignment");
+  WalkerArgs A{};
+  A.nn_fixed = h->sys.ecp_flag ? nn_index : nullptr;
+  A.nw = nw;
+  A.nmpm = 1;
+  A.mode = 1;
+  A.dlt = non_local_move;
+  A.alat = alat;
+  A.r_up = const_cast<double*>(r_up);
+  A.r_dn = const_cast<double*>(r_dn);
+  A.Ginv = const_cast<double*>(Ginv);
+  A.RT_in = RT;
+  A.V_diag = V_diag;
+  A.V_nondiag = V_nondiag;
+  return launch_walker<false>(h, A, (cudaStream_t)stream, K_LRDMC);
+}
+
 // fused local energy (mode 2); returns QE_ERR_UNSUPPORTED when the system does not fit, so that the caller
 // (qe_local_energy) can fall back to the staged kernels.
 int qe_local_energy_fused(qe_engine* h, int nw, const double* r_up, const double* r_dn, const double* RT, const double* Ginv,

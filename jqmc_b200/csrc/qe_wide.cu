@@ -461,6 +461,9 @@ struct ElecArgs {
 };
 __global__ void __launch_bounds__(128)
 kw_electron(SysDev S, ElecArgs P) {
+  // thread = (electron, walker).  The orbital sums stream 4 derivative planes of Phi plus the weights (~180 MB per launch for
+  // water JAGP at 4096 walkers); splitting them over several warps per item was measured slower (62 vs 52 us: the planes are
+  // already read at about half the HBM peak and the extra warps only scatter the DRAM pages).
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int Ne = S.n_e, nw = P.nw;
   if (t >= (long long)Ne * nw) return;
@@ -478,7 +481,6 @@ kw_electron(SysDev S, ElecArgs P) {
     gD[2] = fma(P.Phi[3 * sq + idx], wv, gD[2]);
     lD = fma(P.Phi[4 * sq + idx], wv, lD);
   }
-  lD -= gD[0] * gD[0] + gD[1] * gD[1] + gD[2] * gD[2];
   double gJ[3] = {0, 0, 0}, lJ = 0, ei = 0, eid = 0, loc = 0, ee = 0;
   if (P.has_j3) {
     const size_t sj = (size_t)P.nj * Ne * nw;
@@ -491,6 +493,7 @@ kw_electron(SysDev S, ElecArgs P) {
       lJ = fma(P.Chi[4 * sj + idx], g, lJ);
     }
   }
+  lD -= gD[0] * gD[0] + gD[1] * gD[1] + gD[2] * gD[2];
   const double eps = 1.0e-12;
   for (int a = 0; a < S.n_atom; ++a) {
     const double dx = x - S.Rn[3 * a], dy = y - S.Rn[3 * a + 1], dz = z - S.Rn[3 * a + 2];
@@ -961,6 +964,7 @@ kw_move(SysDev S, MoveArgs P) {
   double* s_c = s_t + N * 32;        // old column / row [N][32]
   double* s_red = s_c + N * 32;      // [TY][32] partial sums
   double* s_flag = s_red + TY * 32;  // [4][32]: accept flag, Det, ...
+  double* s_p1 = s_flag + 4 * 32;    // [max(N, TY)][32] partial orbital sums of phase 1
   const int es = P.es[ww];
   const bool up = es < N;
   const int k = up ? es : es - N;
@@ -968,15 +972,26 @@ kw_move(SysDev S, MoveArgs P) {
 #define GI(i, j) P.Gi[((size_t)(i) * N + (j)) * nw + ww]
 #define GS(i, j) P.Gs[((size_t)(i) * N + (j)) * nw + ww]
   // ---- phase 1: row / column difference ----------------------------------------------------------------
+  // With few electrons per spin (N < TY) the orbital sum of every element is split into NP = TY / N contiguous parts so
+  // that all warps stream the state; the parts are added in a fixed order.
+  const int NP = N < TY ? TY / N : 1, OB = (no + NP - 1) / NP;
+  for (int q = ty; q < N * NP; q += TY) {
+    const int j = q % N, part_i = q / N;
+    const int o0 = min(no, part_i * OB), o1 = min(no, o0 + OB);
+    double s0 = 0.0, s1 = 0.0;
+    const double* Mx = up ? P.Mfull : P.MupT;
+    int o = o0;
+    for (; o + 1 < o1; o += 2) {
+      s0 = fma(PhiN[(size_t)o * nw + ww] - P.Phi[((size_t)o * Ne + es) * nw + ww], Mx[((size_t)o * N + j) * nw + ww], s0);
+      s1 = fma(PhiN[(size_t)(o + 1) * nw + ww] - P.Phi[((size_t)(o + 1) * Ne + es) * nw + ww], Mx[((size_t)(o + 1) * N + j) * nw + ww], s1);
+    }
+    if (o < o1) s0 = fma(PhiN[(size_t)o * nw + ww] - P.Phi[((size_t)o * Ne + es) * nw + ww], Mx[((size_t)o * N + j) * nw + ww], s0);
+    s_p1[q * 32 + lane] = s0 + s1;
+  }
+  __syncthreads();
   for (int j = ty; j < N; j += TY) {
     double s = 0.0;
-    if (up) {
-      for (int o = 0; o < no; ++o)
-        s = fma(PhiN[(size_t)o * nw + ww] - P.Phi[((size_t)o * Ne + es) * nw + ww], P.Mfull[((size_t)o * N + j) * nw + ww], s);
-    } else {
-      for (int o = 0; o < no; ++o)
-        s = fma(P.MupT[((size_t)o * N + j) * nw + ww], PhiN[(size_t)o * nw + ww] - P.Phi[((size_t)o * Ne + es) * nw + ww], s);
-    }
+    for (int pi = 0; pi < NP; ++pi) s += s_p1[(pi * N + j) * 32 + lane];
     s_d[j * 32 + lane] = s;
     s_c[j * 32 + lane] = up ? GI(j, k) : GI(k, j);  // old column k (up) / old row k (dn)
   }
@@ -1491,7 +1506,7 @@ int launch_mesh(qe_engine* h, cudaStream_t st, const MeshArgs& A) {
 int launch_move(qe_engine* h, cudaStream_t st, const MoveArgs& A) {
   const int N = h->sys.n_up;
   const int TY = 16;
-  const size_t smem = ((size_t)3 * N + TY + 4) * 32 * 8;
+  const size_t smem = ((size_t)3 * N + TY + 4 + std::max(N, TY)) * 32 * 8;
   LaunchScope ls_(h, A.decide ? K_W_DECIDE : K_W_COMMIT, st);
   CUDA_TRY(cudaFuncSetAttribute(kw_move, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kw_move<<<nblk(A.nw, 32), dim3(32, TY), smem, st>>>(h->sys, A);

@@ -236,6 +236,10 @@ class WalkerEngine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def clone_for(self, hamiltonian_data):
+        """A second engine with this one's settings for another Hamiltonian (the displaced geometries of the force terms)."""
+        return WalkerEngine(hamiltonian_data, Nv=self.Nv, NN=self.NN, device=self.device, precision=self.precision)
+
     def _walkers(self, r_up, r_dn):
         r_up = self._dev(r_up)
         nw = r_up.shape[0]
@@ -491,8 +495,10 @@ class WalkerEngine:
         _lib.check(rc, "qe_lrdmc_project_tau")
         return e_L, pc, w, r_up, r_dn, Ginv, keys, RT
 
-    def V_elements_n(self, r_up, r_dn, RTs, non_local_move, alat, A_inv=None):
-        """``_jit_vmap_V_elements_n``: (V_diag, V_nondiag); the inverse is rebuilt unless ``A_inv`` is given."""
+    def V_elements_n(self, r_up, r_dn, RTs, non_local_move, alat, A_inv=None, nn_index=None):
+        """``_jit_vmap_V_elements_n``: (V_diag, V_nondiag); the inverse is rebuilt unless ``A_inv`` is given.  With
+        ``nn_index`` (``nearest_nuclei`` of a base point) the non-local ECP keeps that nucleus assignment
+        (qe_lrdmc_velements_frozen: the function whose finite differences are the LRDMC force terms)."""
         r_up, r_dn, nw = self._walkers(r_up, r_dn)
         if non_local_move not in self._NLM:
             raise NotImplementedError(f"non_local_move = {non_local_move} is not yet implemented.")
@@ -502,6 +508,16 @@ class WalkerEngine:
             raise ValueError(f"RTs shape {tuple(RTs.shape)} != ({nw}, 3, 3)")
         Vd = torch.empty(nw, dtype=torch.float64, device=self.device)
         Vn = torch.empty(nw, dtype=torch.float64, device=self.device)
+        if nn_index is not None:
+            nn = nn_index
+            if not isinstance(nn, torch.Tensor) or nn.dtype != torch.int32 or tuple(nn.shape) != (nw, self.n_up + self.n_dn, self.NN):
+                raise ValueError(f"nn_index must be int32[{nw}, {self.n_up + self.n_dn}, {self.NN}]")
+            rc = self._lib.qe_lrdmc_velements_frozen(
+                self._h, nw, self._ptr(r_up), self._ptr(r_dn), self._ptr(RTs), self._ptr(Ginv), self._ptr(nn.contiguous()),
+                self._NLM[non_local_move], float(alat), self._ptr(Vd), self._ptr(Vn), self._stream(),
+            )  # fmt: skip
+            _lib.check(rc, "qe_lrdmc_velements_frozen")
+            return Vd, Vn
         rc = self._lib.qe_lrdmc_velements(
             self._h, nw, self._ptr(r_up), self._ptr(r_dn), self._ptr(RTs), self._ptr(Ginv), self._NLM[non_local_move],
             float(alat), self._ptr(Vd), self._ptr(Vn), self._stream(),

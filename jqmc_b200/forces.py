@@ -20,7 +20,9 @@ therefore freezes that assignment at the base point (``qe_nearest_nuclei`` / ``q
 
 for every electron coordinate (two evaluations of inverse + e_L + ln|Psi| each, all walkers at once) and every nuclear
 coordinate (a displaced Hamiltonian -> a second engine per displaced geometry, built once).  Water: 2 (24 + 9) = 66 batched
-evaluations per measurement step.  Scope: the register kernel family (the one that takes the frozen assignment); the mesh
+evaluations per measurement step.  For LRDMC (``lattice=(alat, non_local_move)``) the differentiated energy is the lattice-regularised
+V_diag + V_nondiag (qe_lrdmc_velements_frozen), whose fixed-node min / max branches automatic differentiation follows piecewise:
+a walker within h of such a kink (probability ~ h) gets a one-sided slope mixed in, which the tests bound.  Scope: the register kernel family (the one that takes the frozen assignment); the mesh
 rotation RT of the step is shared by all displaced evaluations, as in the reference (RTs is an argument of its gradient).
 """
 
@@ -57,8 +59,12 @@ def swct_domega(positions, r):
 class ForceEvaluator:
     """Position derivatives of e_L and ln|Psi| for a batch of walkers (see module docstring)."""
 
-    def __init__(self, hamiltonian_data, engine: WalkerEngine, h: float = 1.0e-4):
+    def __init__(self, hamiltonian_data, engine: WalkerEngine, h: float = 1.0e-4, lattice=None):
+        """``lattice = (alat, non_local_move)`` switches the differentiated energy from the VMC local energy
+        (compute_local_energy, jqmc_mcmc.py:756-781) to the lattice-regularised one of LRDMC, V_diag + V_nondiag
+        (_compute_local_energy_n / _t, jqmc/jqmc_gfmc.py:5630-5667, 1461-1486)."""
         self.H, self.engine, self.h = hamiltonian_data, engine, float(h)
+        self.lattice = None if lattice is None else (float(lattice[0]), lattice[1])
         self.n_atom = len(hamiltonian_data.structure_data.atomic_numbers)
         self._displaced = {}
         self.positions = torch.as_tensor(np.asarray(hamiltonian_data.structure_data.positions, dtype=np.float64), device=engine.device)
@@ -66,14 +72,20 @@ class ForceEvaluator:
     def _engine_at(self, atom: int, axis: int, sign: int) -> WalkerEngine:
         key = (atom, axis, sign)
         if key not in self._displaced:
-            self._displaced[key] = WalkerEngine(displace_nucleus(self.H, atom, axis, sign * self.h), Nv=self.engine.Nv, NN=self.engine.NN,
-                                                precision=self.engine.precision)  # fmt: skip
+            self._displaced[key] = self.engine.clone_for(displace_nucleus(self.H, atom, axis, sign * self.h))
         return self._displaced[key]
 
-    @staticmethod
-    def _values(eng, r_up, r_dn, RT, nn):
+    def _values(self, eng, r_up, r_dn, RT, nn):
         G, Ginv = eng.geminal_inv_batched(r_up, r_dn)
-        e = eng.e_L_frozen(r_up, r_dn, RT, Ginv, nn)
+        if self.lattice is None:
+            e = eng.e_L_frozen(r_up, r_dn, RT, Ginv, nn)
+        else:
+            alat, nlm = self.lattice
+            if nn is None:  # all-electron: nothing to freeze
+                Vd, Vn = eng.V_elements_n(r_up, r_dn, RT, nlm, alat, A_inv=Ginv)
+            else:
+                Vd, Vn = eng.V_elements_n(r_up, r_dn, RT, nlm, alat, A_inv=Ginv, nn_index=nn)
+            e = Vd + Vn
         ln, _ = eng.ln_wavefunction(r_up, r_dn)
         return e, ln
 
@@ -122,7 +134,25 @@ class ForceEvaluator:
         f_hf = d["de_L_dR"] + torch.einsum("wjk,wkl->wjl", om_u, d["de_L_dr_up"]) + torch.einsum("wjk,wkl->wjl", om_d, d["de_L_dr_dn"])
         f_pp = (d["dln_Psi_dR"] + torch.einsum("wjk,wkl->wjl", om_u, d["dln_Psi_dr_up"])
                 + torch.einsum("wjk,wkl->wjl", om_d, d["dln_Psi_dr_dn"]) + 0.5 * dom)  # fmt: skip
+        self._last = d
         return f_hf, f_pp, d["e_L"]
+
+    def weighted_force_sums(self, r_up, r_dn, RT, weight, e_L, use_swct: bool, epsilon_PW: float = 0.0):
+        """LRDMC per-branching force sums of this rank -> device tensor [3, n_atom, 3]:
+        sum_w g_w force_HF_w, sum_w g_w force_PP_w, sum_w g_w e_L_w force_PP_w with g = weight * f_eps, where f_eps is the
+        Pathak-Wagner regularisation 7 t^6 - 15 t^4 + 9 t^2 for t = 1 / (|grad ln Psi| epsilon_PW) < 1 and 1 otherwise
+        (jqmc/jqmc_gfmc.py:5977-6019 GFMC_n with weight = w / (V_diag - E_scf); :1926-1970 GFMC_t with weight = w)."""
+        f_hf, f_pp, _ = self.force_products(r_up, r_dn, RT, use_swct)
+        g = weight
+        if epsilon_PW > 0.0:
+            d = self._last
+            gn2 = (d["dln_Psi_dr_up"] ** 2).sum(dim=(1, 2)) + (d["dln_Psi_dr_dn"] ** 2).sum(dim=(1, 2))
+            t = 1.0 / torch.sqrt(gn2) / epsilon_PW
+            t2 = t * t
+            t4 = t2 * t2
+            g = g * torch.where(t < 1.0, 7.0 * t4 * t2 - 15.0 * t4 + 9.0 * t2, torch.ones_like(t))
+        return torch.stack([torch.einsum("i,ijk->jk", g, f_hf), torch.einsum("i,ijk->jk", g, f_pp),
+                            torch.einsum("i,ijk->jk", g * e_L, f_pp)])  # fmt: skip
 
 
 def displace_nucleus(H, atom: int, axis: int, delta: float):

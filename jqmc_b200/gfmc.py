@@ -30,7 +30,12 @@ Differences from the reference, all behind the same observable results:
     reconfiguration, A_inv refresh as above; the mean projection count of the rank is stored per step (:2095, 2271)
 
 Restart: ``save_to_hdf5`` / ``load_from_hdf5`` in jQMC's checkpoint layout (jqmc_b200/checkpoint.py).
-Out of scope: atomic forces (``comput_position_deriv``).
+
+Atomic forces (``comput_position_deriv=True``; jqmc_gfmc.py:5840-6051 GFMC_n, :1811-1998 GFMC_t): before every branching the
+position derivatives of the lattice-regularised local energy and of ln|Psi| are taken on the device by finite differences
+(jqmc_b200/forces.py), combined with the space-warp weights (``use_swct``) and the Pathak-Wagner factor (``epsilon_PW``)
+into three weighted [n_atom, 3] sums per rank, all-reduced, and stored as (M, 1, n_atom, 3) histories; ``get_aF`` is the
+reference's binned jackknife of -<F_HF> - 2 (<e_L F_PP> - <e_L><F_PP>) with the accumulated weights G_L.
 """
 
 from __future__ import annotations
@@ -76,8 +81,6 @@ class _GFMC:
 
     def _setup(self, hamiltonian_data, num_walkers, num_gfmc_collect_steps, mcmc_seed, alat, random_discretized_mesh,
                non_local_move, comput_position_deriv, engine):  # fmt: skip
-        if comput_position_deriv:
-            raise NotImplementedError("atomic forces are outside the walker engine (SURVEY.md §8f)")
         self._hamiltonian_data = hamiltonian_data
         self._num_walkers = int(num_walkers)
         self._num_gfmc_collect_steps = int(num_gfmc_collect_steps)
@@ -102,7 +105,15 @@ class _GFMC:
         )  # fmt: skip
         self._r_up = torch.from_numpy(np.ascontiguousarray(r_up)).to(dev)
         self._r_dn = torch.from_numpy(np.ascontiguousarray(r_dn)).to(dev)
+        self._init_forces()
         self._init_attributes()
+
+    def _init_forces(self):
+        self._forces = None
+        if self._comput_position_deriv:
+            from .forces import ForceEvaluator
+
+            self._forces = ForceEvaluator(self._hamiltonian_data, self.engine, lattice=(self._alat, self._non_local_move))
 
     def _init_attributes(self):
         self._mcmc_counter = 0
@@ -112,6 +123,10 @@ class _GFMC:
         self._stored_e_L = np.zeros((0, 1))
         self._stored_e_L2 = np.zeros((0, 1))
         self._stored_average_projection_counter = np.zeros((0,))
+        n_atoms = len(self._hamiltonian_data.structure_data.atomic_numbers)
+        self._stored_force_HF = np.zeros((0, 1, n_atoms, 3))
+        self._stored_force_PP = np.zeros((0, 1, n_atoms, 3))
+        self._stored_E_L_force_PP = np.zeros((0, 1, n_atoms, 3))
         self._G_L = []
         self._G_e_L = []
         self._timer = dict(total=0.0)
@@ -157,6 +172,18 @@ class _GFMC:
     def e_L2(self):
         return np.asarray(self._stored_e_L2)[self._num_gfmc_collect_steps :]
 
+    @property
+    def force_HF(self):
+        return self._stored_force_HF[self._num_gfmc_collect_steps :]
+
+    @property
+    def force_PP(self):
+        return self._stored_force_PP[self._num_gfmc_collect_steps :]
+
+    @property
+    def E_L_force_PP(self):
+        return self._stored_E_L_force_PP[self._num_gfmc_collect_steps :]
+
     # walker state as NumPy arrays, like the reference's properties (the device tensors stay private: `_r_up`, `_r_dn`, `_keys`)
     @property
     def latest_r_up_carts(self) -> np.ndarray:
@@ -186,6 +213,9 @@ class _GFMC:
         cfg.update(mcmc_counter=int(self._mcmc_counter), num_survived_walkers=int(self._num_survived_walkers),
                    num_killed_walkers=int(self._num_killed_walkers))  # fmt: skip
         obs = {"e_L": np.asarray(self._stored_e_L), "e_L2": np.asarray(self._stored_e_L2), "w_L": np.asarray(self._stored_w_L)}
+        for name, arr in (("force_HF", self._stored_force_HF), ("force_PP", self._stored_force_PP),
+                          ("E_L_force_PP", self._stored_E_L_force_PP)):  # fmt: skip
+            obs[name] = arr if arr.size > 0 else np.empty(0)
         if isinstance(self, GFMC_t):
             obs["average_projection_counter"] = np.asarray(self._stored_average_projection_counter)
         else:
@@ -221,8 +251,6 @@ class _GFMC:
         obj._random_discretized_mesh = bool(cfg.get("random_discretized_mesh", True))
         obj._non_local_move = cfg.get("non_local_move", "tmove")
         obj._comput_position_deriv = bool(cfg.get("comput_position_deriv", False))
-        if obj._comput_position_deriv:
-            raise NotImplementedError("atomic forces are outside the walker engine (SURVEY.md §8f)")
         obj._restore_config(cfg)
         obj._mpi_seed = int(rng["mpi_seed"])
         obj.engine = engine if engine is not None else WalkerEngine(H)
@@ -231,6 +259,7 @@ class _GFMC:
         obj._keys_init = np.asarray(rng.get("jax_PRNG_key_list_init", rng["jax_PRNG_key_list"])).astype(np.uint32)
         obj._r_up = torch.from_numpy(np.ascontiguousarray(ws["latest_r_up_carts"], dtype=np.float64)).to(dev)
         obj._r_dn = torch.from_numpy(np.ascontiguousarray(ws["latest_r_dn_carts"], dtype=np.float64)).to(dev)
+        obj._init_forces()
         obj._init_attributes()
         obj._mcmc_counter = int(cfg.get("mcmc_counter", 0))
         obj._num_survived_walkers = int(cfg.get("num_survived_walkers", 0))
@@ -243,6 +272,9 @@ class _GFMC:
         obj._stored_e_L = get("e_L", np.zeros((0, 1)))
         obj._stored_e_L2 = get("e_L2", np.zeros((0, 1)))
         obj._stored_w_L = get("w_L", np.zeros((0, 1)))
+        obj._stored_force_HF = get("force_HF", obj._stored_force_HF)
+        obj._stored_force_PP = get("force_PP", obj._stored_force_PP)
+        obj._stored_E_L_force_PP = get("E_L_force_PP", obj._stored_E_L_force_PP)
         obj._stored_average_projection_counter = get("average_projection_counter", np.zeros((obj._mcmc_counter,)))
         g, ge = get("G_L", None), get("G_e_L", None)
         obj._G_L = [g[i] for i in range(g.shape[0])] if g is not None else []
@@ -283,8 +315,18 @@ class _GFMC:
         A_inv = eng.A_inv_n(r_up, r_dn)
         return r_up, r_dn, A_inv, n_surv, sums_all
 
-    def _step(self, r_up, r_dn, keys, A_inv, zeta, rank, world):  # -> r_up, r_dn, keys, A_inv, sums, n_surv, extra
+    def _step(self, r_up, r_dn, keys, A_inv, zeta, rank, world):  # -> r_up, r_dn, keys, A_inv, sums, n_surv, extra, force sums
         raise NotImplementedError
+
+    def _force_sums(self, r_up, r_dn, RTs, weight, e_L, world):
+        """[3, n_atom, 3] weighted force sums over the walkers of all ranks (one small all-reduce), or None."""
+        if self._forces is None:
+            return None
+        fs = self._forces.weighted_force_sums(r_up, r_dn, RTs, weight, e_L, self._use_swct, self._epsilon_PW)
+        d = _dist()
+        if d is not None and world > 1:
+            d.all_reduce(fs)
+        return fs
 
     def _after_interval(self, i, eq_steps, n_bins):
         pass
@@ -304,6 +346,11 @@ class _GFMC:
         self._stored_e_L2 = np.concatenate([self._stored_e_L2, np.zeros((num_mcmc_steps, 1))])
         self._stored_w_L = np.concatenate([self._stored_w_L, np.zeros((num_mcmc_steps, 1))])
         self._stored_average_projection_counter = np.concatenate([self._stored_average_projection_counter, np.zeros(num_mcmc_steps)])
+        if self._forces is not None:
+            z = np.zeros((num_mcmc_steps,) + self._stored_force_HF.shape[1:])
+            self._stored_force_HF = np.concatenate([self._stored_force_HF, z])
+            self._stored_force_PP = np.concatenate([self._stored_force_PP, z])
+            self._stored_E_L_force_PP = np.concatenate([self._stored_E_L_force_PP, z])
         mcmc_interval = int(np.maximum(num_mcmc_steps / 100, 1))
         eq_steps, n_collect, n_bins = GFMC_ON_THE_FLY_WARMUP_STEPS, GFMC_ON_THE_FLY_COLLECT_STEPS, GFMC_ON_THE_FLY_BIN_BLOCKS
         pending = []  # (step index, device sums, device n_survived, device extra) not yet read back
@@ -316,13 +363,18 @@ class _GFMC:
             S = torch.stack([p[1] for p in pending]).cpu().numpy()
             NS = torch.stack([p[2].reshape(()) for p in pending]).cpu().numpy()
             X = torch.stack([p[3].reshape(()) for p in pending]).cpu().numpy() if pending[0][3] is not None else None
-            for n, ((i, _, _, _), s, ns) in enumerate(zip(pending, S, NS)):
+            F = torch.stack([p[4] for p in pending]).cpu().numpy() if pending[0][4] is not None else None
+            for n, ((i, _, _, _, _), s, ns) in enumerate(zip(pending, S, NS)):
                 nw_sum, w_sum, wq, weq, we2q = s
                 self._stored_w_L[base + i, 0] = w_sum / nw_sum
                 self._stored_e_L[base + i, 0] = weq / wq
                 self._stored_e_L2[base + i, 0] = we2q / wq
                 if X is not None:
                     self._stored_average_projection_counter[base + i] = X[n]
+                if F is not None:  # averaged with the same denominator as e_L (:6031-6035 / :1980-1983)
+                    self._stored_force_HF[base + i, 0] = F[n, 0] / wq
+                    self._stored_force_PP[base + i, 0] = F[n, 1] / wq
+                    self._stored_E_L_force_PP[base + i, 0] = F[n, 2] / wq
                 self._num_survived_walkers += int(ns)
                 self._num_killed_walkers += int(nw_sum) - int(ns)
                 if i >= n_collect:  # :6336-6343
@@ -333,8 +385,8 @@ class _GFMC:
 
         for i in range(num_mcmc_steps):
             zeta = float(zeta_rng.random_sample())
-            r_up, r_dn, keys, A_inv, sums, n_surv, extra = self._step(r_up, r_dn, keys, A_inv, zeta, rank, world)
-            pending.append((i, sums, n_surv, extra))
+            r_up, r_dn, keys, A_inv, sums, n_surv, extra, fsum = self._step(r_up, r_dn, keys, A_inv, zeta, rank, world)
+            pending.append((i, sums, n_surv, extra, fsum))
             if (i + 1) % mcmc_interval == 0 and i > eq_steps:  # :6345-6378
                 flush()
                 self._after_interval(i, eq_steps, n_bins)
@@ -353,6 +405,10 @@ class _GFMC:
         self._stored_e_L2 = self._stored_e_L2[:ns]
         self._stored_w_L = self._stored_w_L[:ns]
         self._stored_average_projection_counter = self._stored_average_projection_counter[:ns]
+        if self._forces is not None:
+            self._stored_force_HF = self._stored_force_HF[:ns]
+            self._stored_force_PP = self._stored_force_PP[:ns]
+            self._stored_E_L_force_PP = self._stored_E_L_force_PP[:ns]
         assert n_store >= ns
         self._r_up, self._r_dn, self._keys = r_up, r_dn, keys
         self._timer["total"] += time.perf_counter() - t_start
@@ -381,6 +437,31 @@ class _GFMC:
         Var_mean = np.sum(Var_jk) / M
         Var_std = np.sqrt((M - 1) * np.sum((Var_jk - Var_mean) ** 2) / M)
         return float(E_mean), float(E_std), float(Var_mean), float(Var_std)
+
+    def get_aF(self, num_mcmc_warmup_steps: int = 50, num_mcmc_bin_blocks: int = 10):
+        """(force_mean, force_std) [n_atom, 3]: binned jackknife of -<F_HF> - 2 (<e_L F_PP> - <e_L><F_PP>) over the stored
+        histories weighted with G_L (jqmc/jqmc_gfmc.py:6694-6990, 2587-2880; the reference scatters the bins over ranks only to
+        share the arithmetic -- every rank holds the same history here and evaluates all bins)."""
+        if self._stored_force_HF.shape[0] == 0:
+            raise ValueError("no force samples stored: construct the driver with comput_position_deriv=True")
+        s = slice(num_mcmc_warmup_steps, None)
+        w_L, e_L = self.w_L[s], self.e_L[s]
+        f_hf, f_pp, ef_pp = self.force_HF[s], self.force_PP[s], self.E_L_force_PP[s]
+
+        def binned(x):  # (M, 1, ...) -> (bins, ...)
+            b = np.array([np.sum(a, axis=0) for a in np.array_split(x, num_mcmc_bin_blocks, axis=0)])
+            return b.reshape((b.shape[0] * b.shape[1],) + b.shape[2:])
+
+        wb, web = binned(w_L), binned(w_L * e_L)
+        whf, wpp, wef = (binned(w_L[..., None, None] * f) for f in (f_hf, f_pp, ef_pp))
+        M = wb.size
+        den = (np.sum(wb) - wb)[:, None, None]
+        F_hf = -(np.sum(whf, axis=0) - whf) / den
+        F_pl = -2.0 * ((np.sum(wef, axis=0) - wef) / den - ((np.sum(web) - web)[:, None, None] / den) * ((np.sum(wpp, axis=0) - wpp) / den))
+        F = F_hf + F_pl
+        mean = np.sum(F, axis=0) / M
+        var = np.sum((F - mean) ** 2, axis=0) / M
+        return mean, np.sqrt((M - 1) * var)
 
 
 class GFMC_n(_GFMC):
@@ -436,8 +517,9 @@ class GFMC_n(_GFMC):
         )  # fmt: skip
         V_diag, V_nondiag = eng.V_elements_n(r_up, r_dn, RTs, self._non_local_move, self._alat)
         sums = eng.lrdmc_collect(w, V_diag, V_nondiag, self._E_scf)
+        fsum = self._force_sums(r_up, r_dn, RTs, w / (V_diag - self._E_scf), V_diag + V_nondiag, world)  # :5977-6019
         r_up, r_dn, A_inv, n_surv, sums = self._reconfigure(w, r_up, r_dn, sums, zeta, rank, world)
-        return r_up, r_dn, keys, A_inv, sums, n_surv, None
+        return r_up, r_dn, keys, A_inv, sums, n_surv, None, fsum
 
     def _after_interval(self, i, eq_steps, n_bins):  # on-the-fly E_scf, jqmc_gfmc.py:6345-6378
         n_warm = int(np.minimum(eq_steps, i - eq_steps))
@@ -493,9 +575,10 @@ class GFMC_t(_GFMC):
         eng = self.engine
         nw = self._num_walkers
         w = torch.ones(nw, dtype=torch.float64, device=eng.device)  # weights, time and counter restart every step (:1700-1703)
-        e_L, pc, w, r_up, r_dn, A_inv, keys, _ = eng.projection_t(
+        e_L, pc, w, r_up, r_dn, A_inv, keys, RTs = eng.projection_t(
             w, r_up, r_dn, A_inv, keys, self._tau, self._random_discretized_mesh, self._non_local_move, self._alat, inplace=True
         )
         sums = eng.lrdmc_collect_t(w, e_L)
+        fsum = self._force_sums(r_up, r_dn, RTs, w, e_L, world)  # weights without the V_diag - E_scf division (:1963-1968)
         r_up, r_dn, A_inv, n_surv, sums = self._reconfigure(w, r_up, r_dn, sums, zeta, rank, world)
-        return r_up, r_dn, keys, A_inv, sums, n_surv, pc.to(torch.float64).mean()  # rank-local mean, as the reference (:2095)
+        return r_up, r_dn, keys, A_inv, sums, n_surv, pc.to(torch.float64).mean(), fsum  # rank-local mean, as the reference (:2095)

@@ -85,6 +85,21 @@ class OracleEngine:
         s = OD.lrdmc_collect_t(_np(w), _np(e_L))
         return self._t([s[0], s[1], s[1], s[2], s[3]])
 
+    # ---- what jqmc_b200.forces.ForceEvaluator needs (no nearest-nucleus freezing on the oracle side: ecp_flag False) --------
+    ecp_flag = False
+
+    def clone_for(self, H):
+        return OracleEngine(H)
+
+    def _walkers(self, r_up, r_dn):
+        r_up, r_dn = self._t(_np(r_up)), self._t(_np(r_dn))
+        return r_up, r_dn, r_up.shape[0]
+
+    def ln_wavefunction(self, r_up, r_dn):
+        r_up, r_dn = _np(r_up), _np(r_dn)
+        ln = [OP.evaluate_ln_wavefunction(self.H.wavefunction_data, u, d) for u, d in zip(r_up, r_dn)]
+        return self._t(ln), None
+
     def V_elements_n(self, r_up, r_dn, RTs, nlm, alat, A_inv=None):
         r_up, r_dn, RTs = _np(r_up), _np(r_dn), _np(RTs)
         res = [OD.lrdmc_V_elements(self.H, r_up[i], r_dn[i], RTs[i], nlm, alat) for i in range(len(r_up))]

@@ -259,3 +259,98 @@ def test_branch_oracle_properties():
     chosen, ns = OD.lrdmc_branch_indices([ww], 0.2)
     assert ns == 1 and np.all(chosen == 5)
     assert isinstance(torch.tensor(chosen), torch.Tensor)
+
+
+# ---- atomic forces in the LRDMC drivers (jqmc_gfmc.py:5840-6051, 6694-6990) -------------------------------------------------
+def _force_driver(kind, H, deriv, **kw):
+    if kind == "n":
+        return GFMC_n(H, num_walkers=3, num_mcmc_per_measurement=NMPM, num_gfmc_collect_steps=1, mcmc_seed=SEED, E_scf=E_SCF, alat=ALAT,
+                      comput_position_deriv=deriv, engine=OracleEngine(H), **kw)  # fmt: skip
+    return GFMC_t(H, num_walkers=3, num_gfmc_collect_steps=1, mcmc_seed=SEED, tau=TAU, alat=ALAT, comput_position_deriv=deriv,
+                  engine=OracleEngine(H), **kw)  # fmt: skip
+
+
+@pytest.mark.parametrize("kind", ["n", "t"])
+def test_gfmc_force_histories(kind, tmp_path):
+    """The force terms ride on the chain without changing it; with SWCT the per-step sums over the atoms of F_HF and F_PP
+    vanish (translation invariance: sum_alpha omega_alpha = 1), the stored averages equal a direct per-walker evaluation at the
+    pre-branching walkers, and the histories survive a checkpoint round trip."""
+    from jqmc_b200 import checkpoint
+    from jqmc_b200.forces import ForceEvaluator
+
+    H = _system()
+    plain = _force_driver(kind, H, False)
+    plain.run(4)
+    g = _force_driver(kind, H, True, use_swct=True, epsilon_PW=0.4)
+    seen = []
+    fs0 = g._force_sums
+
+    def spy(r_up, r_dn, RTs, weight, e_L, world):  # record the arguments of every step
+        seen.append([x.detach().cpu().numpy().copy() for x in (r_up, r_dn, RTs, weight, e_L)])
+        return fs0(r_up, r_dn, RTs, weight, e_L, world)
+
+    g._force_sums = spy
+    g.run(4)
+    np.testing.assert_array_equal(g.bare_w_L, plain.bare_w_L)
+    np.testing.assert_array_equal(g.e_L, plain.e_L)
+    np.testing.assert_array_equal(g.latest_r_up_carts, plain.latest_r_up_carts)
+    assert g.force_HF.shape == (3, 1, 2, 3) and g.force_PP.shape == (3, 1, 2, 3) and g.E_L_force_PP.shape == (3, 1, 2, 3)
+    scale = np.abs(g.force_HF).max()
+    assert np.isfinite(scale) and scale > 0
+    np.testing.assert_allclose(g.force_HF.sum(axis=2), 0.0, atol=2e-5 * max(1.0, scale))
+    np.testing.assert_allclose(g.force_PP.sum(axis=2), 0.0, atol=2e-6 * max(1.0, np.abs(g.force_PP).max()))
+    # direct evaluation of the last step: per-walker products, Pathak-Wagner factor and weighted averages written out
+    r_up, r_dn, RTs, weight, e_L = seen[-1]
+    fe = ForceEvaluator(H, OracleEngine(H), lattice=(ALAT, "tmove"))
+    f_hf, f_pp, e0 = (x.numpy() for x in fe.force_products(r_up, r_dn, RTs, True))
+    if kind == "n":
+        np.testing.assert_allclose(e0, e_L, rtol=1e-12)  # V_diag + V_nondiag at the base point
+    gl = fe._last
+    gn2 = (gl["dln_Psi_dr_up"].numpy() ** 2).sum(axis=(1, 2)) + (gl["dln_Psi_dr_dn"].numpy() ** 2).sum(axis=(1, 2))
+    t = 1.0 / np.sqrt(gn2) / 0.4
+    f_eps = np.where(t < 1.0, 7.0 * t**6 - 15.0 * t**4 + 9.0 * t**2, 1.0)
+    assert np.any(t < 1.0) or np.all(f_eps == 1.0)
+    den = weight.sum()
+    np.testing.assert_allclose(g.force_HF[-1, 0], np.einsum("i,ijk->jk", weight * f_eps, f_hf) / den, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(g.force_PP[-1, 0], np.einsum("i,ijk->jk", weight * f_eps, f_pp) / den, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(g.E_L_force_PP[-1, 0], np.einsum("i,ijk->jk", weight * f_eps * e_L, f_pp) / den, rtol=1e-10, atol=1e-12)
+    # checkpoint round trip keeps the histories and the switch
+    full = str(tmp_path / "restart.h5")
+    checkpoint.save_checkpoint(g, full, tmp_pattern=str(tmp_path / "._restart_rank{rank}.h5"))
+    g2 = type(g).load_from_hdf5(full, rank=0, engine=OracleEngine(H))
+    assert g2.comput_position_deriv and g2._forces is not None
+    np.testing.assert_array_equal(g2.force_HF, g.force_HF)
+    np.testing.assert_array_equal(g2.E_L_force_PP, g.E_L_force_PP)
+
+
+def test_gfmc_get_aF_matches_definition():
+    """get_aF against the estimator written out bin by bin (jqmc_gfmc.py:6712-6812): leave-one-bin-out ratios of G_L-weighted sums."""
+    H = _system()
+    g = _force_driver("n", H, False)
+    rng = np.random.default_rng(5)
+    A, c, nb, warm = 31, 1, 5, 3
+    g._num_gfmc_collect_steps = c
+    g._mcmc_counter = A
+    g._stored_w_L = rng.uniform(0.8, 1.2, size=(A, 1))
+    g._stored_e_L = rng.normal(-1.1, 0.1, size=(A, 1))
+    g._stored_force_HF = rng.normal(size=(A, 1, 2, 3))
+    g._stored_force_PP = rng.normal(size=(A, 1, 2, 3))
+    g._stored_E_L_force_PP = g._stored_e_L[..., None, None] * g._stored_force_PP + 0.01 * rng.normal(size=(A, 1, 2, 3))
+    mean, std = g.get_aF(num_mcmc_warmup_steps=warm, num_mcmc_bin_blocks=nb)
+    G = compute_G_L(g._stored_w_L, c)[warm:, 0]
+    e, fh, fp, ef = (x[c:][warm:, 0] for x in (g._stored_e_L, g._stored_force_HF, g._stored_force_PP, g._stored_E_L_force_PP))
+    idx = np.array_split(np.arange(len(G)), nb)
+    est = []
+    for j in range(nb):
+        keep = np.concatenate([idx[k] for k in range(nb) if k != j])
+        W = G[keep].sum()
+        hf = np.einsum("i,ijk->jk", G[keep], fh[keep]) / W
+        pp = np.einsum("i,ijk->jk", G[keep], fp[keep]) / W
+        epp = np.einsum("i,ijk->jk", G[keep], ef[keep]) / W
+        E = (G[keep] * e[keep]).sum() / W
+        est.append(-hf - 2.0 * (epp - E * pp))
+    est = np.array(est)
+    np.testing.assert_allclose(mean, est.mean(axis=0), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(std, np.sqrt((nb - 1) * ((est - est.mean(axis=0)) ** 2).mean(axis=0)), rtol=1e-10)
+    with pytest.raises(ValueError):
+        _force_driver("n", H, False).get_aF()

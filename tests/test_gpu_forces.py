@@ -89,3 +89,74 @@ def test_mcmc_forces_h2_symmetric():
     axis /= np.linalg.norm(axis)
     perp = F[0] - (F[0] @ axis) * axis
     assert np.abs(perp).max() < 6 * dF[0].max() + 1e-3  # no force perpendicular to the bond
+
+
+def _oracle_e_L_lattice(H, ru, rd, RT, alat, nlm):
+    Vd, Vn = OD.lrdmc_V_elements(H, ru, rd, RT, nlm, alat)
+    return Vd + Vn
+
+
+@pytest.mark.parametrize("name,nlm", [("water_ccecp_ccpvqz", "tmove"), ("water_ccecp_ccpvqz", "dltmove"), ("H2_ae_ccpvdz_cart", "tmove")])
+def test_lrdmc_position_derivatives(name, nlm):
+    """Gradient of the lattice-regularised local energy V_diag + V_nondiag (the LRDMC force term, jqmc_gfmc.py:5630-5667,
+    5840-5850) by device-side finite differences against the oracle's own central differences of lrdmc_V_elements."""
+    from jqmc_b200.engine import WalkerEngine
+    from jqmc_b200.forces import ForceEvaluator, displace_nucleus
+
+    H = _system(name)
+    alat = 0.3
+    eng = WalkerEngine(H)
+    fe = ForceEvaluator(H, eng, lattice=(alat, nlm))
+    nw, h = 3, fe.h
+    r_up, r_dn = random_walkers(H, nw, 9, scale=0.7)
+    RT = eng.generate_RTs(np.array([[2, 11 + i] for i in range(nw)], dtype=np.uint32))
+    d = {k: v.cpu().numpy() for k, v in fe(r_up, r_dn, RT).items()}
+    RTh = RT.cpu().numpy()
+    n_at = len(H.structure_data.atomic_numbers)
+    for w in range(nw):
+        np.testing.assert_allclose(d["e_L"][w], _oracle_e_L_lattice(H, r_up[w], r_dn[w], RTh[w], alat, nlm), rtol=1e-9)
+        for spin, r, key in (("up", r_up, "de_L_dr_up"), ("dn", r_dn, "de_L_dr_dn")):
+            for i, c in ((0, 1), (r.shape[1] - 1, 0)):
+                rp, rm = r[w].copy(), r[w].copy()
+                rp[i, c] += h
+                rm[i, c] -= h
+                if spin == "up":
+                    fd = _oracle_e_L_lattice(H, rp, r_dn[w], RTh[w], alat, nlm) - _oracle_e_L_lattice(H, rm, r_dn[w], RTh[w], alat, nlm)
+                else:
+                    fd = _oracle_e_L_lattice(H, r_up[w], rp, RTh[w], alat, nlm) - _oracle_e_L_lattice(H, r_up[w], rm, RTh[w], alat, nlm)
+                np.testing.assert_allclose(d[key][w, i, c], fd / (2 * h), rtol=1e-5, atol=1e-5)
+        for a, c in ((0, 2), (n_at - 1, 1)):
+            Hp, Hm = displace_nucleus(H, a, c, h), displace_nucleus(H, a, c, -h)
+            fd = (_oracle_e_L_lattice(Hp, r_up[w], r_dn[w], RTh[w], alat, nlm) - _oracle_e_L_lattice(Hm, r_up[w], r_dn[w], RTh[w], alat, nlm)) / (2 * h)
+            np.testing.assert_allclose(d["de_L_dR"][w, a, c], fd, rtol=1e-5, atol=1e-5)
+    tot_e = d["de_L_dR"].sum(1) + d["de_L_dr_up"].sum(1) + d["de_L_dr_dn"].sum(1)
+    np.testing.assert_allclose(tot_e, 0.0, atol=2e-5 * max(1.0, np.abs(d["de_L_dR"]).max()))
+
+
+@pytest.mark.parametrize("kind", ["n", "t"])
+def test_gfmc_forces_h2_symmetric(kind):
+    """LRDMC forces on H2 through the drivers (SWCT + Pathak-Wagner switched on): finite, opposite on the two atoms and along the
+    bond within the error bars; the force terms do not disturb the chain."""
+    from jqmc_b200.gfmc import GFMC_n, GFMC_t
+
+    H = _system("H2_ecp_ccpvtz")
+    common = dict(num_walkers=128, num_gfmc_collect_steps=2, mcmc_seed=9, alat=0.3, use_swct=True, epsilon_PW=0.05)
+    if kind == "n":
+        mk = lambda deriv: GFMC_n(H, num_mcmc_per_measurement=10, E_scf=-1.1, comput_position_deriv=deriv, **common)  # noqa: E731
+    else:
+        mk = lambda deriv: GFMC_t(H, tau=0.05, comput_position_deriv=deriv, **common)  # noqa: E731
+    g, plain = mk(True), mk(False)
+    g.run(num_mcmc_steps=24)
+    plain.run(num_mcmc_steps=24)
+    np.testing.assert_array_equal(g.bare_w_L, plain.bare_w_L)
+    np.testing.assert_array_equal(g.e_L, plain.e_L)
+    assert g.force_HF.shape == (22, 1, 2, 3)
+    np.testing.assert_allclose(g.force_HF.sum(axis=2), 0.0, atol=2e-5 * max(1.0, np.abs(g.force_HF).max()))
+    np.testing.assert_allclose(g.force_PP.sum(axis=2), 0.0, atol=2e-6 * max(1.0, np.abs(g.force_PP).max()))
+    F, dF = g.get_aF(num_mcmc_warmup_steps=2, num_mcmc_bin_blocks=5)
+    assert F.shape == (2, 3) and np.all(np.isfinite(F)) and np.all(dF > 0)
+    np.testing.assert_allclose(F[0] + F[1], 0.0, atol=1e-6 + 1e-3 * np.abs(F).max())  # exact up to the finite-difference error
+    axis = np.asarray(H.structure_data.positions)[1] - np.asarray(H.structure_data.positions)[0]
+    axis /= np.linalg.norm(axis)
+    perp = F[0] - (F[0] @ axis) * axis
+    assert np.abs(perp).max() < 6 * dF[0].max() + 1e-3
