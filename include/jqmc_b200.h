@@ -177,7 +177,11 @@ int qe_lrdmc_project(qe_engine* h, int nw, double* w, double* r_up, double* r_dn
  * (time step log(1-xi)/V_nondiag, weight *= exp(-dt e_L), move chosen as in GFMC_n) until its time is used up.
  * w[nw], r_up, r_dn, Ginv, keys updated in place; projection_counter[nw] (int32), e_L[nw], RT[nw,3,3] written.
  * As in the reference's vmapped while_loop, walkers that finish early keep splitting their keys (three splits per
- * iteration) until the slowest walker OF THIS CALL is done, and e_L / RT belong to that last iteration. */
+ * iteration) until the slowest walker OF THIS CALL is done, and e_L / RT belong to that last iteration.
+ * Register kernel family: asynchronous like every other entry (main pass + tail pass, the projection count stays on the device).
+ * General kernel family: NOT asynchronous -- the number of projections is data dependent and that family launches one kernel
+ * sequence per projection, so the host reads an "any walker still running" flag back after every projection
+ * (cudaStreamSynchronize on `stream`), and all walkers run in one slice. */
 int qe_lrdmc_project_tau(qe_engine* h, int nw, double* w, double* r_up, double* r_dn, double* Ginv, uint32_t* keys,
                          double tau, int random_discretized_mesh, int non_local_move, double alat,
                          int32_t* projection_counter, double* e_L, double* RT, void* stream);
