@@ -6,6 +6,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges named like the profile() kernel table
 
 #include "../../include/jqmc_b200.h"
 #include "qe_device.cuh"
@@ -147,6 +148,7 @@ struct LaunchScope {
   int id;
   LaunchScope(qe_engine* h_, int id_, cudaStream_t st_) : h(h_), st(st_), id(id_) {
     h->launches++;
+    nvtxRangePushA(KERNEL_NAMES[id]);  // host-side NVTX range per launch (a no-op unless a tool is attached)
     if (h->profiling) {
       cudaEventCreate(&e0);
       cudaEventCreate(&e1);
@@ -154,6 +156,7 @@ struct LaunchScope {
     }
   }
   ~LaunchScope() {
+    nvtxRangePop();
     if (e0) {
       cudaEventRecord(e1, st);
       h->prof.push_back({id, e0, e1});

@@ -86,6 +86,19 @@ __device__ __forceinline__ double qexp_s(double r2, double zs, const double* __r
   const int ki = (int)tb;  // rint(r2 zs) <= 0 (two's complement in the low mantissa bits)
   const double kf = t - QE_EXPS[0];
   const double u = fma(r2, zs, -kf);
+#ifdef QE_EXP_ESTRIN
+  // Estrin: 1 + c1 u + u^2 (c2 + c3 u) + u^4 ((c4 + c5 u) + u^2 c6): dependent depth 4 instead of 6 for two more
+  // instructions (same truncation error, rounding differs in the last place).  Selected per translation unit: measured
+  // faster in the fused walker kernel only (profiles/r02_walker_history.md, A/B table)
+  const double u2 = u * u;
+  const double pa = fma(QE_EXPS[1], u, QE_EXPS[7]);
+  const double pb = fma(QE_EXPS[3], u, QE_EXPS[2]);
+  const double pc = fma(QE_EXPS[5], u, QE_EXPS[4]);
+  const double u4 = u2 * u2;
+  const double pd = fma(u2, pb, pa);
+  const double pe = fma(u2, QE_EXPS[6], pc);
+  const double p = fma(u4, pe, pd);
+#else
   double p = QE_EXPS[6];
   p = fma(p, u, QE_EXPS[5]);
   p = fma(p, u, QE_EXPS[4]);
@@ -93,6 +106,7 @@ __device__ __forceinline__ double qexp_s(double r2, double zs, const double* __r
   p = fma(p, u, QE_EXPS[2]);
   p = fma(p, u, QE_EXPS[1]);
   p = fma(p, u, QE_EXPS[7]);
+#endif
   const double v = et[ki & 31] * p;
   // valid iff magic - 32640 <= t <= magic (positive doubles order like their bit patterns): k >= -1020 * 32
   const bool under = tb < 0x4337FFFFFFFF8080ll;

@@ -1032,7 +1032,10 @@ extern "C" int qe_create(const qe_system_desc* d, qe_engine** out) {
     return fail(QE_ERR_INVALID, "qe_create: precision must be 0 (full) or 1 (mixed)");
   }
   h->mixed = d->precision == 1;
-  h->nmo_pad = n_mo <= 4 ? 4 : (n_mo <= 8 ? 8 : 16);
+  // orbital padding of the register kernels (template NMO).  A non-singular geminal needs n_mo >= n_up; the padding follows
+  // max(n_mo, n_up) so that "NMO = 4 implies n_up <= 4" holds for any input (k_walker sizes its Sherman-Morrison rows by it)
+  const int n_pad_src = std::max(n_mo, d->n_up);
+  h->nmo_pad = n_pad_src <= 4 ? 4 : (n_pad_src <= 8 ? 8 : 16);
   std::vector<int> row_ao, rowj_ao;
   std::vector<double> row_scale, rowj_scale;
   int rc = build_basis(d->orb_up, &d->orb_dn, d->n_atom, d->positions, h->nmo_pad, QE_N_CHUNK, h->pool, h->b_up, h->narrow_ok, row_ao, row_scale);

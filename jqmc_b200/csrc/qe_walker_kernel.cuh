@@ -27,6 +27,26 @@
 
 namespace {
 
+// Determinant ratios of TWO mesh points (same spin block): sweep of all AOs at both points, contraction with the MO
+// coefficients on the fly, dot product with the ratio weight vectors w0 / w1 (stride ws) of the two (walker, electron) pairs.
+template <int NMO, bool CART, int LMAX, bool MIXED>
+__device__ __noinline__ double2 mesh_ratio2(const char* __restrict__ tab, const BasisDev B, int coff, double px0, double py0, double pz0,
+                                            double px1, double py1, double pz1, const double* __restrict__ w0,
+                                            const double* __restrict__ w1, int ws) {
+  const double px[2] = {px0, px1}, py[2] = {py0, py1}, pz[2] = {pz0, pz1};
+  SinkMOn<NMO, 2> sink;
+  sink.init(tab + coff);
+  if constexpr (MIXED) eval_val_n_f32<CART, LMAX, 2>(tab, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);  // zone ao_eval in fp32
+  else eval_val_n<CART, LMAX, 2>(tab, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);
+  double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+  for (int mo = 0; mo < NMO; ++mo) {
+    r0 = fma(sink.acc[0][mo], w0[mo * ws], r0);
+    r1 = fma(sink.acc[1][mo], w1[mo * ws], r1);
+  }
+  return make_double2(r0, r1);
+}
+
 struct WalkerArgs {
   int nw, nmpm, mode;  // mode 0: projection, 1: V elements (no move), 2: VMC local energy
   int dlt, wpc;
@@ -504,17 +524,15 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
             }
             jold[i] = SEL(el[i], 7);
           }
-          SinkMOn<NMO, 2> sink;
-          sink.init(tab + ((blk & 1) ? B.off_C2 : B.off_C));
-          if constexpr (MIXED) eval_val_n_f32<CART, LMAX, 2>(tab, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);  // zone ao_eval in fp32
-          else eval_val_n<CART, LMAX, 2>(tab, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);
+          // AO sweep + MO contraction + dot with the ratio weight vectors: its own function, NOT inlined, so that it gets a
+          // register allocation of its own (no spills inside) instead of sharing the kernel's
+          const double2 rr = mesh_ratio2<NMO, CART, LMAX, MIXED>(tab, B, (blk & 1) ? B.off_C2 : B.off_C, px[0], py[0], pz[0], px[1], py[1],
+                                                                 pz[1], s_W + (el[0] * NMO) * WS + wls[0], s_W + (el[1] * NMO) * WS + wls[1], WS);
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             const int wl = wls[i], e = el[i];
             PosShared pos{s_r, WS, wl};
-            double ratio = 0.0;
-#pragma unroll
-            for (int mo = 0; mo < NMO; ++mo) ratio = fma(sink.acc[i][mo], SW(e, mo), ratio);
+            const double ratio = i == 0 ? rr.x : rr.y;
             double jr;
             if constexpr (MIXED) jr = (double)expf(jastrow_single_f32(S, pos, e, px[i], py[i], pz[i]) - (float)jold[i]);  // zone jastrow_ratio
             else jr = qexp(jastrow_single_m(S, pos, e, px[i], py[i], pz[i]) - jold[i]);
@@ -648,6 +666,8 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       const int wl = WLOF(s % NACT), e = s / NACT;
       bool flip = false;
       double nd = 0, kinFN = 0, kinSP = 0;
+#pragma unroll 1  // (the short loops of P3 stay rolled: the phase runs once per projection on cold instruction caches, and every
+                  //  instruction line it does not have to fetch counts; A/B on one box: projection 4.240 -> 4.203 ms)
       for (int s6 = 0; s6 < 6; ++s6) {
         const double v = s_p[(6 * e + s6) * WS + wl];
         flip = flip || (v >= 0.0);
@@ -668,9 +688,14 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
     //      [kinetic mesh, ECP mesh], so these per-electron sums are also the chunk sums of the move selection below
     if (n_ecp > 0) {
       const int per = S.NN * S.Nv;
-      for (int c = tid; c < Ne * NACT; c += nthr) {
+      // (these tasks start at the upper half of the CTA when both task lists fit side by side: (a) and (a') then run on
+      //  different warps at the same time)
+      const int off2 = 2 * Ne * NACT <= nthr ? nthr - Ne * NACT : 0;
+      for (int c = tid - off2; c < Ne * NACT; c += nthr) {
+        if (c < 0) continue;
         const int wl = WLOF(c % NACT), e = c / NACT;
         double sFN = 0, sSP = 0;
+#pragma unroll 1
         for (int k = e * per; k < (e + 1) * per; ++k) {
           const double v = s_p[(n_kin + k) * WS + wl];
           double fn = fmin(v, 0.0);
@@ -692,6 +717,7 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       const int wl = tid;
       const double diag_kin = 3.0 / (2.0 * a2) * Ne;
       double sum_kinFN = 0, SP_kin = 0, sum_opt = 0, ee = 0, loc = 0;
+#pragma unroll 1
       for (int e = 0; e < Ne; ++e) {
         sum_kinFN += SEL(e, 5);
         SP_kin += SEL(e, 6);
@@ -729,8 +755,9 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       const int mv = (tid < WPC) ? (s_misc[14 * WS + tid] != 0.0) : 0;
       if (!__syncthreads_or(mv)) break;  // every walker of the CTA has used up its time
     } else {
+      // (no barrier: (d) below runs on the same threads as (b) and reads, besides its own thread's results, only what was
+      //  complete at the previous barrier)
       if (P.mode != 0) break;
-      __syncthreads();
     }
     PHASE(4)
     // (d) per walker: first index whose cumulative probability reaches u (searchsorted 'left' on cumsum(p / sum p),
@@ -744,12 +771,14 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
       const int per = S.ecp_flag ? S.NN * S.Nv : 0, n_ch = n_ecp > 0 ? 2 * Ne : Ne;
       int ksel = NPT - 1, kstart = 0;
       double c = 0;
+#pragma unroll 1
       for (int ci = 0; ci < n_ch; ++ci) {
         const double cs = (ci < Ne ? SEL(ci, 5) : s_e2[((ci - Ne) * 2) * WS + wl]) / tot;
         if (c + cs >= u) break;
         c += cs;
         kstart = ci + 1 < Ne ? 6 * (ci + 1) : n_kin + (ci + 1 - Ne) * per;
       }
+#pragma unroll 1
       for (int k = kstart; k < NPT; ++k) {
         c += s_p[k * WS + wl] / tot;
         if (c >= u) {
@@ -814,8 +843,9 @@ k_walker(BasisDev B, SysDev S_g, WalkerArgs P) {
     PHASE(7)
     // Sherman-Morrison (jqmc/jqmc_gfmc.py:5083-5141): task = (walker, row i); read phase, barrier, write phase
     {  // N * WPC <= blockDim.x is guaranteed by launch_walker: one pass.  All loops over electrons run to the compile-time
-       // bound NB >= N with uniform predicates, so that newrow / vvec / uvec stay in registers (no local memory)
-      constexpr int NB = 8;
+       // bound NB >= N with uniform predicates, so that newrow / vvec / uvec stay in registers (no local memory); NB = 4
+       // for the 4-orbital instantiation (half the instructions)
+      constexpr int NB = NMO <= 4 ? 4 : 8;  // NMO = 4 is dispatched only for n_up <= 4 (qe_create: nmo_pad)
       double newrow[NB];
       const int s = tid;
       bool act = s < N * WPC;
