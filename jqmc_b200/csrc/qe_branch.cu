@@ -125,8 +125,23 @@ __global__ void k_branch_cumprob(int nw, int world, size_t w_stride, const doubl
     for (int i = threadIdx.x; i < m; i += blockDim.x) s_buf[i] = cr[base + i];
     __syncthreads();
     if (threadIdx.x == 0) {
+      // the sequential fp64 chain of np.cumsum (one dependent add per element, 8 cycles each); loads and stores of 16
+      // elements are batched around it so that only the adds sit on the critical path
       double acc = s_acc;
-      for (int i = 0; i < m; ++i) {
+      int i = 0;
+      for (; i + 16 <= m; i += 16) {
+        double v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = s_buf[i + k];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          acc += v[k];
+          v[k] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) s_buf[i + k] = v[k];
+      }
+      for (; i < m; ++i) {
         acc += s_buf[i];
         s_buf[i] = acc;
       }
