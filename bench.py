@@ -536,23 +536,38 @@ def run_gpu(args, rank, local_rank, world):
         d2h += nbytes(host_l) + nbytes(host_lo)
     n_e2e = max(3, min(args.steps, 20))
 
+    copy_stream = torch.cuda.Stream(device=dev)  # host<->device copies of one driver overlap the other driver's kernels
+
     def e2e_step():
+        main = torch.cuda.current_stream()
+        ev_in_v = ev_in_l = None
+        with torch.cuda.stream(copy_stream):  # every input of the step leaves the host at once
+            if has_vmc:
+                dstate = tuple(t.to(dev, non_blocking=True) for t in host_v)
+                ev_in_v = copy_stream.record_event()
+            if has_lrdmc:
+                lr = tuple(t.to(dev, non_blocking=True) for t in host_l)
+                ev_in_l = copy_stream.record_event()
         if has_vmc:
-            dstate = tuple(t.to(dev, non_blocking=True) for t in host_v)
+            main.wait_event(ev_in_v)
             dstate, dobs = step_vmc(dstate)
-            for h, d in zip(host_v, dstate):
-                h.copy_(d, non_blocking=True)
-            for h, d in zip(host_vo, dobs):
-                h.copy_(d, non_blocking=True)
+            ev_v = main.record_event()
+            with torch.cuda.stream(copy_stream):  # results go back while the LRDMC step runs
+                copy_stream.wait_event(ev_v)
+                for h, d in zip(host_v, dstate):
+                    h.copy_(d, non_blocking=True)
+                for h, d in zip(host_vo, dobs):
+                    h.copy_(d, non_blocking=True)
         if has_lrdmc:
-            lr = tuple(t.to(dev, non_blocking=True) for t in host_l)
+            main.wait_event(ev_in_l)
             lr = lr + (eng.A_inv_n(lr[0], lr[1]),)
             lr, lo = step_lrdmc(lr)
             for h, d in zip(host_l, lr[:3]):
                 h.copy_(d, non_blocking=True)
             for h, d in zip(host_lo, lo):
                 h.copy_(d, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        copy_stream.synchronize()
+        main.synchronize()
 
     for _ in range(2):
         e2e_step()
@@ -694,7 +709,7 @@ def run_gpu(args, rank, local_rank, world):
                 timing="sum of per-step CUDA-event durations on the launch stream, max over ranks",
             ),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=n_e2e,
-                     path="WalkerEngine update/generate_RTs/e_L_fast/as_reg_fast (+ grad_ln_psi_params_fast) and GFMC_n._step on pinned host buffers"),
+                     path="WalkerEngine update/generate_RTs/e_L_fast/as_reg_fast (+ grad_ln_psi_params_fast) and GFMC_n._step on pinned host buffers; host<->device copies on a second stream"),
             gpu_launches=int(launches),
             clocks=clocks, roofline=roofline, cpu_baseline=cpu, check=check,
         )  # fmt: skip
