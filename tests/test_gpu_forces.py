@@ -107,7 +107,7 @@ def test_lrdmc_position_derivatives(name, nlm):
     alat = 0.3
     eng = WalkerEngine(H)
     fe = ForceEvaluator(H, eng, lattice=(alat, nlm))
-    nw, h = 3, fe.h
+    nw, h = 2, fe.h
     r_up, r_dn = random_walkers(H, nw, 9, scale=0.7)
     RT = eng.generate_RTs(np.array([[2, 11 + i] for i in range(nw)], dtype=np.uint32))
     d = {k: v.cpu().numpy() for k, v in fe(r_up, r_dn, RT).items()}

@@ -390,7 +390,7 @@ def _check_projection_t(H, eng, nw, tau, mesh, nlm, alat, seed=41):
     return opc, n_it
 
 
-@pytest.mark.parametrize("name,jas,nlm,mesh,tau,wpc", [("water_ccecp_ccpvqz", "j2pade", "tmove", True, 0.04, 2), ("water_ccecp_ccpvqz", "j1exp_j2exp", "dltmove", True, 0.03, 0),
+@pytest.mark.parametrize("name,jas,nlm,mesh,tau,wpc", [("water_ccecp_ccpvqz", "j2pade", "tmove", True, 0.025, 2), ("water_ccecp_ccpvqz", "j1exp_j2exp", "dltmove", True, 0.02, 0),
                                                        ("Li_ae_ccpvdz_cart", "j1exp_j2exp", "tmove", True, 0.03, 1), ("H2_ecp_ccpvtz_cart", "j2pade", "tmove", False, 0.1, 2),
                                                        ("H_ecp_ccpvqz", "j1exp_j2exp", "tmove", True, 0.2, 3)])  # fmt: skip
 def test_lrdmc_projection_t_trajectory(name, jas, nlm, mesh, tau, wpc):
