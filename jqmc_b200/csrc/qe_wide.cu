@@ -161,6 +161,53 @@ __global__ void kw_bmm(int ni, int nj, int na, int nw, const double* __restrict_
   D[i * sdi + j * sdj + w] = s;
 }
 
+// Ratio weight vectors of both spins in one pass for small determinants (N_up <= 8):
+//   Worb[o][e][w]     = sum_j Mfull[o][j][w] Ginv[j][e][w]   (e < N_up)
+//   Worb[o][N+j'][w]  = sum_i MupT[o][i][w]  Ginv[j'][i][w]  (j' < N_dn)
+// block = 32 walkers (x) x 8 (y): the running inverse of the block's walkers is staged in shared memory once, a thread then
+// walks orbitals o = y, y + 8, ... with the 2 N coefficients of the orbital in registers.  Same summation order as kw_bmm.
+template <int NB>
+__global__ void __launch_bounds__(256)
+kw_worb_small(int no, int N, int Nd, int nw, const double* __restrict__ Mfull, const double* __restrict__ MupT,
+              const double* __restrict__ Gi, double* __restrict__ Worb) {
+  __shared__ double s_g[NB * NB][32];
+  const int lane = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
+  const int wq = blockIdx.x * 32 + lane;
+  const bool live = wq < nw;
+  const int w = live ? wq : nw - 1;
+  const int Ne = N + Nd;
+  for (int i = ty; i < N * N; i += TY) s_g[i][lane] = Gi[(size_t)i * nw + w];
+  __syncthreads();
+  if (!live) return;
+  for (int o = ty + blockIdx.y * TY; o < no; o += TY * gridDim.y) {
+    double mf[NB], mu[NB];
+#pragma unroll
+    for (int a = 0; a < NB; ++a) {
+      mf[a] = a < N ? Mfull[((size_t)o * N + a) * nw + w] : 0.0;
+      mu[a] = a < N ? MupT[((size_t)o * N + a) * nw + w] : 0.0;
+    }
+    double* out = Worb + (size_t)o * Ne * nw + w;
+#pragma unroll
+    for (int e = 0; e < NB; ++e) {
+      if (e >= N) break;
+      double sacc = 0.0;
+#pragma unroll
+      for (int a = 0; a < NB; ++a)
+        if (a < N) sacc = fma(mf[a], s_g[a * N + e][lane], sacc);
+      out[(size_t)e * nw] = sacc;
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (j >= Nd) break;
+      double sacc = 0.0;
+#pragma unroll
+      for (int a = 0; a < NB; ++a)
+        if (a < N) sacc = fma(mu[a], s_g[j * N + a][lane], sacc);
+      out[(size_t)(N + j) * nw] = sacc;
+    }
+  }
+}
+
 // AoS <-> SoA:  src[w][n_item] -> dst[item][w]  and back
 __global__ void kw_to_soa(int nw, int n_item, const double* __restrict__ src, double* __restrict__ dst) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -473,6 +520,7 @@ kw_electron(SysDev S, ElecArgs P) {
   pos.get(e, x, y, z);
   const size_t sq = (size_t)P.no * Ne * nw;
   double gD[3] = {0, 0, 0}, lD = 0;
+#pragma unroll 4
   for (int o = 0; o < P.no; ++o) {
     const size_t idx = ((size_t)o * Ne + e) * nw + w;
     const double wv = P.Worb[idx];
@@ -981,6 +1029,7 @@ kw_move(SysDev S, MoveArgs P) {
     double s0 = 0.0, s1 = 0.0;
     const double* Mx = up ? P.Mfull : P.MupT;
     int o = o0;
+#pragma unroll 2
     for (; o + 1 < o1; o += 2) {
       s0 = fma(PhiN[(size_t)o * nw + ww] - P.Phi[((size_t)o * Ne + es) * nw + ww], Mx[((size_t)o * N + j) * nw + ww], s0);
       s1 = fma(PhiN[(size_t)(o + 1) * nw + ww] - P.Phi[((size_t)(o + 1) * Ne + es) * nw + ww], Mx[((size_t)(o + 1) * N + j) * nw + ww], s1);
@@ -1089,6 +1138,7 @@ kw_move(SysDev S, MoveArgs P) {
       if (P.Gs) GS(i, k) += s_d[i * 32 + lane];
     }
   }
+#pragma unroll 4  // (independent copies: more loads in flight per thread; the kernel is bound by memory latency)
   for (int o = ty; o < no; o += TY) {
     for (int q = 0; q < P.NQ; ++q) P.Phi[(((size_t)q * no + o) * Ne + es) * nw + w] = PhiN[((size_t)q * no + o) * nw + w];
     if (up) P.MupT[((size_t)o * N + k) * nw + w] = P.T2[(size_t)o * nw + w];
@@ -1436,8 +1486,16 @@ int build_weights(qe_engine* h, cudaStream_t st, WState& X) {
   const WideTabs& T = h->wt;
   const SysDev& S = h->sys;
   const long long nw = X.nw, N = S.n_up, Nd = S.n_dn, Ne = S.n_e;
-  TRY(w_bmm(h, st, T.no, (int)N, (int)N, (int)nw, X.Mfull, nw, N * nw, X.Gi, N * nw, nw, X.Worb, Ne * nw, nw));
-  TRY(w_bmm(h, st, T.no, (int)Nd, (int)N, (int)nw, X.MupT, nw, N * nw, X.Gi, nw, N * nw, X.Worb + N * nw, Ne * nw, nw));
+  if (N <= 8) {
+    LaunchScope ls_(h, K_W_BMM, st);
+    const dim3 grid(nblk(nw, 32), 4), block(32, 8);
+    if (N <= 4) kw_worb_small<4><<<grid, block, 0, st>>>(T.no, (int)N, (int)Nd, (int)nw, X.Mfull, X.MupT, X.Gi, X.Worb);
+    else kw_worb_small<8><<<grid, block, 0, st>>>(T.no, (int)N, (int)Nd, (int)nw, X.Mfull, X.MupT, X.Gi, X.Worb);
+    CHECK_LAUNCH();
+  } else {
+    TRY(w_bmm(h, st, T.no, (int)N, (int)N, (int)nw, X.Mfull, nw, N * nw, X.Gi, N * nw, nw, X.Worb, Ne * nw, nw));
+    TRY(w_bmm(h, st, T.no, (int)Nd, (int)N, (int)nw, X.MupT, nw, N * nw, X.Gi, nw, N * nw, X.Worb + N * nw, Ne * nw, nw));
+  }
   if (T.has_mo) {
     if (T.restricted) {
       TRY(w_gemm(h, st, T.n_row, Ne * nw, T.no, T.Cw_up, T.no, X.Worb, Ne * nw, X.Wrow, Ne * nw));
