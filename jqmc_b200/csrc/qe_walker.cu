@@ -1,6 +1,5 @@
 // Exported entries of the fused per-walker kernel (qe_walker_kernel.cuh): GFMC_n projection, V elements, VMC local energy.
-// The GFMC_t instantiations live in qe_walker_tau.cu (separate translation unit: the two compile in parallel).
-#define QE_EXP_ESTRIN 1  // qexp_s of this translation unit: see qe_device.cuh
+// The kernel instantiations themselves live in qe_walker_i_*.cu (one translation unit per orbital padding / basis kind).
 #include "qe_walker_kernel.cuh"
 
 size_t lrdmc_draws_bytes(int nw, int nmpm) { return (size_t)nmpm * nw * (2 * 8 + 9 * 8 + 8) + 4 * 256; }

@@ -25,28 +25,7 @@
 #pragma once
 #include "qe_common.cuh"
 
-namespace {
-
-// Determinant ratios of TWO mesh points (same spin block): sweep of all AOs at both points, contraction with the MO
-// coefficients on the fly, dot product with the ratio weight vectors w0 / w1 (stride ws) of the two (walker, electron) pairs.
-template <int NMO, bool CART, int LMAX, bool MIXED>
-__device__ __noinline__ double2 mesh_ratio2(const char* __restrict__ tab, const BasisDev B, int coff, double px0, double py0, double pz0,
-                                            double px1, double py1, double pz1, const double* __restrict__ w0,
-                                            const double* __restrict__ w1, int ws) {
-  const double px[2] = {px0, px1}, py[2] = {py0, py1}, pz[2] = {pz0, pz1};
-  SinkMOn<NMO, 2> sink;
-  sink.init(tab + coff);
-  if constexpr (MIXED) eval_val_n_f32<CART, LMAX, 2>(tab, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);  // zone ao_eval in fp32
-  else eval_val_n<CART, LMAX, 2>(tab, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);
-  double r0 = 0.0, r1 = 0.0;
-#pragma unroll
-  for (int mo = 0; mo < NMO; ++mo) {
-    r0 = fma(sink.acc[0][mo], w0[mo * ws], r0);
-    r1 = fma(sink.acc[1][mo], w1[mo * ws], r1);
-  }
-  return make_double2(r0, r1);
-}
-
+// (outside the unnamed namespace: the per-instantiation translation units and the front ends exchange it)
 struct WalkerArgs {
   int nw, nmpm, mode;  // mode 0: projection, 1: V elements (no move), 2: VMC local energy
   int dlt, wpc;
@@ -74,6 +53,29 @@ struct WalkerArgs {
                         // nearest-nucleus search (finite-difference derivatives keep the assignment of the base point fixed)
   long long* clk;  // optional [16] per-phase cycle counters (qe_set_phase_clocks; thread 0 of every CTA adds its own)
 };
+
+namespace {
+
+// Determinant ratios of TWO mesh points (same spin block): sweep of all AOs at both points, contraction with the MO
+// coefficients on the fly, dot product with the ratio weight vectors w0 / w1 (stride ws) of the two (walker, electron) pairs.
+template <int NMO, bool CART, int LMAX, bool MIXED>
+__device__ __noinline__ double2 mesh_ratio2(const char* __restrict__ tab, const BasisDev B, int coff, double px0, double py0, double pz0,
+                                            double px1, double py1, double pz1, const double* __restrict__ w0,
+                                            const double* __restrict__ w1, int ws) {
+  const double px[2] = {px0, px1}, py[2] = {py0, py1}, pz[2] = {pz0, pz1};
+  SinkMOn<NMO, 2> sink;
+  sink.init(tab + coff);
+  if constexpr (MIXED) eval_val_n_f32<CART, LMAX, 2>(tab, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);  // zone ao_eval in fp32
+  else eval_val_n<CART, LMAX, 2>(tab, B, B.off_seg, px, py, pz, 0, B.n_grp, sink);
+  double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+  for (int mo = 0; mo < NMO; ++mo) {
+    r0 = fma(sink.acc[0][mo], w0[mo * ws], r0);
+    r1 = fma(sink.acc[1][mo], w1[mo * ws], r1);
+  }
+  return make_double2(r0, r1);
+}
+
 
 // R^T (row-major) of R = Rz(gamma) Ry(beta) Rx(alpha), jqmc/jqmc_mcmc.py:4237-4244
 __device__ __forceinline__ void rt_from_angles(double al, double be, double ga, double* RT) {
@@ -1072,11 +1074,13 @@ int choose_wpc(int nw, int n_points, int sms, int ctas_per_sm, int wpc_max, int 
   return best;
 }
 
+}  // namespace
+
 // One CTA of 16 warps per SM: the warps of an SM then run the same phase of the projection loop at the same time, which
 // keeps the instruction working set (one phase, not the whole loop) inside the instruction caches; four independent
 // 4-warp CTAs per SM were measured 5x stalled on instruction fetch (profiles/r01_*).
-template <bool TAU>
-int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
+template <bool TAU, int NMO_I, bool CART_I>
+int launch_walker_one(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
   const SysDev& S = h->sys;
   const int P = h->nmo_pad;
   if (S.n_up > 8) return fail(QE_ERR_UNSUPPORTED, "the fused walker kernel holds at most 8 electrons per spin (larger systems run on the general family)");
@@ -1132,7 +1136,7 @@ int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
     if (h->b_up.dev.lmax <= 4) CALL2(NMO, CART, 4);      \
     else CALL2(NMO, CART, 6);                            \
   } while (0)
-    DISPATCH_NMO_CART(h, CALL);
+    CALL(NMO_I, CART_I);
 #undef CALL
 #undef CALL2
 #undef CALL3
@@ -1143,4 +1147,37 @@ int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
   return QE_OK;
 }
 
-}  // namespace
+// Front end: the instantiations of the kernel family live in one translation unit per (TAU, orbital padding, Cartesian) --
+// jqmc_b200/csrc/qe_walker_i_*.cu -- so that every file goes through a single-threaded (deterministic) ptxas and the files
+// compile in parallel.  (`nvcc --split-compile` was measured to produce DIFFERENT machine code from identical sources on
+// every run, and builds of this kernel differ by up to 10 % in speed: profiles/r02_walker_history.md.)
+#define QE_WALKER_EXTERN(TAU_, NMO_, CART_) \
+  extern template int launch_walker_one<TAU_, NMO_, CART_>(qe_engine*, WalkerArgs&, cudaStream_t, int);
+QE_WALKER_EXTERN(false, 4, false)
+QE_WALKER_EXTERN(false, 4, true)
+QE_WALKER_EXTERN(false, 8, false)
+QE_WALKER_EXTERN(false, 8, true)
+QE_WALKER_EXTERN(false, 16, false)
+QE_WALKER_EXTERN(false, 16, true)
+QE_WALKER_EXTERN(true, 4, false)
+QE_WALKER_EXTERN(true, 4, true)
+QE_WALKER_EXTERN(true, 8, false)
+QE_WALKER_EXTERN(true, 8, true)
+QE_WALKER_EXTERN(true, 16, false)
+QE_WALKER_EXTERN(true, 16, true)
+#undef QE_WALKER_EXTERN
+
+template <bool TAU>
+int launch_walker(qe_engine* h, WalkerArgs& A, cudaStream_t st, int kid) {
+  const bool cart = h->b_up.dev.cart != 0;
+#ifdef QE_DEV_MINIMAL
+  if (cart || h->nmo_pad != 4) return fail(QE_ERR_UNSUPPORTED, "QE_DEV_MINIMAL build");
+  return launch_walker_one<TAU, 4, false>(h, A, st, kid);
+#else
+  switch (h->nmo_pad) {
+    case 4: return cart ? launch_walker_one<TAU, 4, true>(h, A, st, kid) : launch_walker_one<TAU, 4, false>(h, A, st, kid);
+    case 8: return cart ? launch_walker_one<TAU, 8, true>(h, A, st, kid) : launch_walker_one<TAU, 8, false>(h, A, st, kid);
+    default: return cart ? launch_walker_one<TAU, 16, true>(h, A, st, kid) : launch_walker_one<TAU, 16, false>(h, A, st, kid);
+  }
+#endif
+}
