@@ -673,7 +673,9 @@ def run_gpu(args, rank, local_rank, world):
                         "evaluates -- the hardware-utilisation figure"),
             traffic=traffic,
             peak_source="DFMA microbenchmark measured live in this run (qe_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
-            note="the path is fp64-ALU bound (SURVEY.md 8d): HBM carries only walker state, see hbm",
+            note=("the path is fp64-ALU bound (SURVEY.md 8d): HBM carries only walker state, see hbm" if args.precision == "full" else
+                  "precision 'mixed': the AO values and Jastrow ratios run on the fp32 pipe, so the fp64 peak is NOT the bound of this mode and "
+                  "`frac` (reference-formulation flops / fp64 peak) can exceed 1; reported for comparison with the fp64 line only"),
             whole_step=dict(achieved=step_flops * nw / step_s / 1e12, achieved_executed=step_flops_x * nw / step_s / 1e12, unit="TFLOP/s"),
             hbm=dict(achieved=n_drivers * fl["bytes_step"] * nw / step_s / 1e9, peak=hbm_peak, unit="GB/s",
                      peak_source="MEASURED_PEAKS.json" if peaks else "fallback"),
