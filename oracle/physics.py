@@ -8,6 +8,7 @@ sums, generated solid-harmonic polynomials, rank-1 updates).  All arithmetic is 
 
 from __future__ import annotations
 
+import functools
 import itertools
 from math import comb, factorial, pi, sqrt
 
@@ -22,25 +23,19 @@ RCOND_SVD = 1.0e-20  # jqmc/_setting.py:103-106
 # --------------------------------------------------------------------------------------
 # Atomic orbitals
 # --------------------------------------------------------------------------------------
-def solid_harmonic(l: int, m: int, d):
-    """Real regular solid harmonic S_lm(d), closed form of jqmc/atomic_orbital.py:3019-3109.
-
-    ``d`` has shape (..., 3) and may be complex (used for complex-step derivatives): the formula is
-    a polynomial in (x, y, z) once r^(2k) is written as (x^2+y^2+z^2)^k.
-    """
-    x, y, z = d[..., 0], d[..., 1], d[..., 2]
-    r2 = x * x + y * y + z * z
+@functools.lru_cache(maxsize=None)
+def _solid_harmonic_tables(l: int, m: int):
+    """Coefficient tables of S_lm (pure functions of l, m; cached -- the evaluation below multiplies in the same order as the
+    un-tabulated closed form, so the values are bit-identical): [(c, p, q)] for sum c x^p y^q, [(lam, k, n)] for sum lam r^2k z^n."""
     ma = abs(m)
-    # (x,y) part: A_m = Re (x+iy)^|m|, B_m = Im (x+iy)^|m|   (:3069-3083)
     cs = [1.0, 0.0, -1.0, 0.0]  # cos(k*pi/2)
     sn = [0.0, 1.0, 0.0, -1.0]  # sin(k*pi/2)
-    xy = 0.0
+    xy = []
     for p in range(ma + 1):
         trig = cs[(ma - p) % 4] if m >= 0 else sn[(ma - p) % 4]
         if trig != 0.0:
-            xy = xy + comb(ma, p) * trig * x**p * y ** (ma - p)
-    # z part (:3086-3103)
-    zz = 0.0
+            xy.append((comb(ma, p) * trig, p, ma - p))
+    zz = []
     for k in range((l - ma) // 2 + 1):
         lam = (
             (-1.0) ** k
@@ -50,14 +45,52 @@ def solid_harmonic(l: int, m: int, d):
             * factorial(l - 2 * k)
             / factorial(l - 2 * k - ma)
         )
-        zz = zz + lam * r2**k * z ** (l - 2 * k - ma)
+        zz.append((lam, k, l - 2 * k - ma))
     pref = sqrt((2 - int(ma == 0)) * factorial(l - ma) / factorial(l + ma))
+    return tuple(xy), tuple(zz), pref
+
+
+def solid_harmonic(l: int, m: int, d):
+    """Real regular solid harmonic S_lm(d), closed form of jqmc/atomic_orbital.py:3019-3109.
+
+    ``d`` has shape (..., 3) and may be complex (used for complex-step derivatives): the formula is
+    a polynomial in (x, y, z) once r^(2k) is written as (x^2+y^2+z^2)^k.
+    """
+    x, y, z = d[..., 0], d[..., 1], d[..., 2]
+    r2 = x * x + y * y + z * z
+    txy, tzz, pref = _solid_harmonic_tables(int(l), int(m))
+    # (x,y) part: A_m = Re (x+iy)^|m|, B_m = Im (x+iy)^|m|   (:3069-3083)
+    xy = 0.0
+    for c, p, q in txy:
+        xy = xy + c * x**p * y**q
+    # z part (:3086-3103)
+    zz = 0.0
+    for lam, k, n in tzz:
+        zz = zz + lam * r2**k * z**n
     return pref * zz * xy
 
 
+def _aos_cache(aos):
+    """Per-object memo of the primitive lists and the normalised per-AO terms (they depend only on the basis definition and are
+    needed at every one of the thousands of AO evaluations of a trajectory test).  The memo lives on the AOs object and is
+    valid only while the defining fields are the very same objects (identity check), so a modified copy never sees stale terms."""
+    fields = (aos.orbital_indices, aos.exponents, aos.coefficients, aos.angular_momentums, aos.nucleus_index)
+    c = getattr(aos, "_oracle_cache", None)
+    if c is None or len(c["fields"]) != len(fields) or any(a is not b for a, b in zip(c["fields"], fields)):
+        c = {"fields": fields, "prims": None, "terms": {}}
+        try:
+            object.__setattr__(aos, "_oracle_cache", c)
+        except (AttributeError, TypeError):
+            pass  # (an object without a __dict__: no memo, same results)
+    return c
+
+
 def _ao_prim_lists(aos):
-    oi = np.asarray(aos.orbital_indices)
-    return [np.nonzero(oi == a)[0] for a in range(aos.num_ao)]
+    c = _aos_cache(aos)
+    if c["prims"] is None:
+        oi = np.asarray(aos.orbital_indices)
+        c["prims"] = [np.nonzero(oi == a)[0] for a in range(aos.num_ao)]
+    return c["prims"]
 
 
 def _norm_sphe(l, Z):
@@ -78,7 +111,17 @@ def _norm_cart(l, nx, ny, nz, Z):
 
 
 def _ao_terms(aos, a, prims):
-    """Per-AO primitive exponents and fully normalised coefficients, and the angular function."""
+    """Per-AO primitive exponents and fully normalised coefficients, and the angular function (memoised per AOs object)."""
+    memo = _aos_cache(aos)["terms"]
+    hit = memo.get(a)
+    if hit is not None and hit[0] is prims:
+        return hit[1]
+    out = _ao_terms_uncached(aos, a, prims)
+    memo[a] = (prims, out)
+    return out
+
+
+def _ao_terms_uncached(aos, a, prims):
     Z = np.asarray(aos.exponents, dtype=np.float64)[prims]
     c = np.asarray(aos.coefficients, dtype=np.float64)[prims]
     l = int(aos.angular_momentums[a])
