@@ -57,3 +57,16 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_build_is_deterministic_by_construction():
+    """The build must not use `nvcc --split-compile`: it produced different machine code (and different speed) from identical
+    sources on every run (profiles/r02_walker_history.md).  The large kernel families are split over translation units instead."""
+    import __graft_entry__ as g
+
+    assert not any("split-compile" in f for f in g.NVCC_FLAGS)
+    src = open(os.path.join(ROOT, "__graft_entry__.py")).read()
+    assert '"--split-compile"' not in src
+    csrc = os.path.join(ROOT, "jqmc_b200", "csrc")
+    units = [f for f in os.listdir(csrc) if f.endswith(".cu")]
+    assert sum(f.startswith("qe_walker_i_") for f in units) == 12 and sum(f.startswith("qe_mcmc_i_") for f in units) == 3
